@@ -1,0 +1,386 @@
+"""ctypes binding of include/afx_rans.h (libaeroflex_rans_b200.so).
+
+``GpuSolver`` mirrors the public surface of the reference's ``rans::solver``
+(src/rans/include/rans/solver.h:104-175: set_bcs, set_cfl, set_second_order,
+set_gradient_scheme, set_limiter_k, init, refill_bcs, bcs_from_internal, get_q,
+get_uniform_residual, fill, compute, solve) with the same argument meaning and
+error behaviour (unknown patch -> KeyError like ``bcs.at``; numeric failure ->
+negative return from solve).  All arithmetic happens in the CUDA library.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+CSRC = os.path.join(PKG, "csrc")
+LIBDIR = os.path.join(PKG, "lib")
+LIBNAME = "libaeroflex_rans_b200.so"
+
+BC_KINDS = {"farfield": 1, "slip-wall": 2, "wall": 3}          # solver.h:220-227; anything else -> 0 (internal)
+VISCOSITY = {"inviscid": 0, "laminar": 1, "spallart-allmaras": 2}  # core.h:176 (spelling is the reference's)
+GRADIENT = {"green-gauss": 0, "least-squares": 1}               # core.h:175
+FIELDS = {"q": 0, "qW": 1, "gx": 2, "gy": 3, "limiters": 4, "dt": 5, "rhs": 6}
+
+EXPORTED_SYMBOLS = [
+    "afx_last_error", "afx_version", "afx_device_count",
+    "afx_mesh_read_msh", "afx_mesh_from_elements", "afx_mesh_synth_omesh", "afx_mesh_free", "afx_mesh_get_desc",
+    "afx_mesh_n_nodes", "afx_mesh_n_patches", "afx_mesh_patch_name", "afx_mesh_patch_id", "afx_mesh_get_elements",
+    "afx_mesh_write_msh",
+    "afx_rans_create", "afx_rans_destroy", "afx_rans_set_bcs", "afx_rans_set_options", "afx_rans_set_cfl",
+    "afx_rans_init", "afx_rans_refill_bcs", "afx_rans_bcs_from_internal", "afx_rans_set_q", "afx_rans_get_q",
+    "afx_rans_get_field", "afx_rans_boundary_variables", "afx_rans_uniform_residual", "afx_rans_step_explicit",
+    "afx_rans_run_explicit", "afx_rans_phase_dt_gradients", "afx_rans_phase_limiters", "afx_rans_phase_residual",
+    "afx_rans_residual", "afx_rans_fill_jacobian", "afx_rans_get_jacobian_blocks", "afx_rans_step_implicit",
+    "afx_rans_wall_forces", "afx_rans_wall_cp", "afx_rans_last_device_ms", "afx_rans_launch_count",
+    "afx_rans_profile_explicit",
+]
+
+
+class AfxError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("afx error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Gas(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("gamma", "R", "mu_L", "Pr_L", "cp")]
+
+
+class BVars(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("mach", "angle", "T", "p")]
+
+
+class MeshDesc(C.Structure):
+    _fields_ = [("n_cells", C.c_uint32), ("n_ghost", C.c_uint32), ("n_edges", C.c_uint32),
+                ("edges_cells", C.POINTER(C.c_uint32)),
+                ("edges_nx", C.POINTER(C.c_double)), ("edges_ny", C.POINTER(C.c_double)),
+                ("edges_len", C.POINTER(C.c_double)), ("edges_cx", C.POINTER(C.c_double)),
+                ("edges_cy", C.POINTER(C.c_double)),
+                ("cells_cx", C.POINTER(C.c_double)), ("cells_cy", C.POINTER(C.c_double)),
+                ("cells_area", C.POINTER(C.c_double)),
+                ("cells_edges", C.POINTER(C.c_uint32)), ("cells_is_tri", C.POINTER(C.c_uint8)),
+                ("boundary_edges", C.POINTER(C.c_uint32)), ("boundary_patch", C.POINTER(C.c_int32))]
+
+
+def library_path():
+    return os.path.join(LIBDIR, LIBNAME)
+
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false", "-std=c++17",
+              "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fPIC,-fopenmp,-O3", "-shared"]
+SOURCES = ["rans_solver.cu", "mesh_host.cpp", "mesh_capi.cpp"]
+
+
+def build_library(force=False, verbose=False):
+    """nvcc cross-compiles the library for sm_100a (works without a GPU)."""
+    out = library_path()
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))] + \
+        [os.path.join(ROOT, "include", "afx_rans.h")]
+    if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
+        return out
+    os.makedirs(LIBDIR, exist_ok=True)
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + srcs + ["-lgomp"]
+    subprocess.run(cmd, check=True, cwd=CSRC)
+    return out
+
+
+_lib = None
+
+
+def load_library():
+    """Load the CUDA library; raises (never falls back) if it is absent and cannot be built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        build_library()
+    L = C.CDLL(path)
+    L.afx_last_error.restype = C.c_char_p
+    L.afx_version.restype = C.c_char_p
+    vp, dp, u32p, u8p, i32p = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint32), C.POINTER(C.c_uint8), C.POINTER(C.c_int32)
+    L.afx_mesh_read_msh.argtypes = [C.POINTER(vp), C.c_char_p]
+    L.afx_mesh_from_elements.argtypes = [C.POINTER(vp), C.c_uint32, vp, vp, C.c_uint32, vp, vp, C.c_uint32, vp, vp, vp,
+                                         C.c_int, C.POINTER(C.c_char_p)]
+    L.afx_mesh_synth_omesh.argtypes = [C.POINTER(vp), C.c_uint32, C.c_uint32, C.c_uint32, C.c_double]
+    L.afx_mesh_free.argtypes = [vp]
+    L.afx_mesh_get_desc.argtypes = [vp, C.POINTER(MeshDesc)]
+    L.afx_mesh_n_nodes.restype = C.c_uint32
+    L.afx_mesh_n_nodes.argtypes = [vp]
+    L.afx_mesh_n_patches.argtypes = [vp]
+    L.afx_mesh_patch_name.restype = C.c_char_p
+    L.afx_mesh_patch_name.argtypes = [vp, C.c_int]
+    L.afx_mesh_patch_id.argtypes = [vp, C.c_char_p]
+    L.afx_mesh_get_elements.argtypes = [vp] * 6
+    L.afx_mesh_write_msh.argtypes = [vp, C.c_char_p]
+    L.afx_rans_create.argtypes = [C.POINTER(vp), C.POINTER(MeshDesc), C.POINTER(Gas), C.c_int, C.c_int]
+    L.afx_rans_destroy.argtypes = [vp]
+    L.afx_rans_set_bcs.argtypes = [vp, C.c_int, vp, C.POINTER(BVars)]
+    L.afx_rans_set_options.argtypes = [vp, C.c_int, C.c_int, C.c_double]
+    L.afx_rans_set_cfl.argtypes = [vp, C.c_double]
+    for n in ("afx_rans_init", "afx_rans_refill_bcs", "afx_rans_bcs_from_internal", "afx_rans_phase_dt_gradients",
+              "afx_rans_phase_limiters", "afx_rans_fill_jacobian"):
+        getattr(L, n).argtypes = [vp]
+    L.afx_rans_set_q.argtypes = [vp, vp]
+    L.afx_rans_get_q.argtypes = [vp, vp]
+    L.afx_rans_get_field.argtypes = [vp, C.c_int, vp]
+    L.afx_rans_boundary_variables.argtypes = [vp, C.POINTER(BVars)]
+    L.afx_rans_uniform_residual.argtypes = [vp, dp]
+    L.afx_rans_step_explicit.argtypes = [vp, C.c_double, dp]
+    L.afx_rans_run_explicit.argtypes = [vp, C.c_double, C.c_int, vp]
+    L.afx_rans_phase_residual.argtypes = [vp, dp]
+    L.afx_rans_residual.argtypes = [vp, dp]
+    L.afx_rans_get_jacobian_blocks.argtypes = [vp, vp, vp, vp]
+    L.afx_rans_step_implicit.argtypes = [vp, C.c_double, C.c_double, C.c_int, dp]
+    L.afx_rans_wall_forces.argtypes = [vp, C.c_int, vp]
+    L.afx_rans_wall_cp.argtypes = [vp, C.c_int, vp]
+    L.afx_rans_last_device_ms.argtypes = [vp, dp]
+    L.afx_rans_launch_count.restype = C.c_int64
+    L.afx_rans_launch_count.argtypes = [vp]
+    L.afx_rans_profile_explicit.argtypes = [vp, C.c_double, C.c_int, vp]
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc < 0:
+        raise AfxError(rc, load_library().afx_last_error().decode())
+    return rc
+
+
+def device_count():
+    return load_library().afx_device_count()
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Mesh:
+    """Host mesh in the reference's layout (rans::mesh, mesh.h:198-273)."""
+
+    def __init__(self, handle):
+        self.L = load_library()
+        self.h = handle
+        self.d = MeshDesc()
+        _check(self.L.afx_mesh_get_desc(self.h, C.byref(self.d)))
+        d = self.d
+        self.N, self.G, self.E = d.n_cells, d.n_ghost, d.n_edges
+        self.patch_names = [self.L.afx_mesh_patch_name(self.h, p).decode() for p in range(self.L.afx_mesh_n_patches(self.h))]
+
+    @classmethod
+    def read_msh(cls, path):
+        L = load_library()
+        h = C.c_void_p()
+        _check(L.afx_mesh_read_msh(C.byref(h), str(path).encode()))
+        return cls(h)
+
+    @classmethod
+    def from_elements(cls, x, y, cells, is_tri, b0, b1, bpatch, patch_names):
+        L = load_library()
+        x = np.ascontiguousarray(x, np.float64); y = np.ascontiguousarray(y, np.float64)
+        cells = np.ascontiguousarray(cells, np.uint32); is_tri = np.ascontiguousarray(is_tri, np.uint8)
+        b0 = np.ascontiguousarray(b0, np.uint32); b1 = np.ascontiguousarray(b1, np.uint32)
+        bpatch = np.ascontiguousarray(bpatch, np.int32)
+        names = (C.c_char_p * max(len(patch_names), 1))(*[n.encode() for n in patch_names])
+        h = C.c_void_p()
+        _check(L.afx_mesh_from_elements(C.byref(h), len(x), _ptr(x), _ptr(y), len(is_tri), _ptr(cells), _ptr(is_tri),
+                                        len(b0), _ptr(b0), _ptr(b1), _ptr(bpatch), len(patch_names), names))
+        return cls(h)
+
+    @classmethod
+    def synth_omesh(cls, ni, nj, n_quad_layers, far_radius=150.0):
+        L = load_library()
+        h = C.c_void_p()
+        _check(L.afx_mesh_synth_omesh(C.byref(h), ni, nj, n_quad_layers, far_radius))
+        return cls(h)
+
+    def __del__(self):
+        try:
+            self.L.afx_mesh_free(self.h)
+        except Exception:
+            pass
+
+    def _arr(self, ptr, n, shape=None):
+        a = np.ctypeslib.as_array(ptr, shape=(n,)) if n else np.zeros(0)
+        return a.reshape(shape) if shape else a
+
+    # numpy views of the reference arrays (borrowed from the C++ object)
+    @property
+    def edge_cells(self): return self._arr(self.d.edges_cells, 2 * self.E, (-1, 2))
+    @property
+    def enx(self): return self._arr(self.d.edges_nx, self.E)
+    @property
+    def eny(self): return self._arr(self.d.edges_ny, self.E)
+    @property
+    def elen(self): return self._arr(self.d.edges_len, self.E)
+    @property
+    def ecx(self): return self._arr(self.d.edges_cx, self.E)
+    @property
+    def ecy(self): return self._arr(self.d.edges_cy, self.E)
+    @property
+    def ccx(self): return self._arr(self.d.cells_cx, self.N + self.G)
+    @property
+    def ccy(self): return self._arr(self.d.cells_cy, self.N + self.G)
+    @property
+    def area(self): return self._arr(self.d.cells_area, self.N + self.G)
+    @property
+    def cell_edges(self): return self._arr(self.d.cells_edges, 4 * self.N, (-1, 4))
+    @property
+    def is_tri(self): return self._arr(self.d.cells_is_tri, self.N)
+    @property
+    def bnd_edge(self): return self._arr(self.d.boundary_edges, self.G)
+    @property
+    def bnd_patch(self): return self._arr(self.d.boundary_patch, self.G)
+
+    def elements(self):
+        nn = self.L.afx_mesh_n_nodes(self.h)
+        x = np.zeros(nn); y = np.zeros(nn)
+        cells = np.zeros((self.N, 4), np.uint32); b0 = np.zeros(self.G, np.uint32); b1 = np.zeros(self.G, np.uint32)
+        self.L.afx_mesh_get_elements(self.h, _ptr(x), _ptr(y), _ptr(cells), _ptr(b0), _ptr(b1))
+        return x, y, cells, b0, b1
+
+    def write_msh(self, path):
+        _check(self.L.afx_mesh_write_msh(self.h, str(path).encode()))
+
+
+class GpuSolver:
+    """rans::solver on one B200 through the C ABI."""
+
+    def __init__(self, mesh, gas=None, viscosity="inviscid", device=0):
+        self.L = load_library()
+        self.mesh = mesh
+        g = gas or {}
+        self.gas = Gas(g.get("gamma", 1.4), g.get("R", 0.71428571428), g.get("mu_L", 1e-5), g.get("Pr_L", 0.72), g.get("cp", 1.0))
+        if viscosity not in VISCOSITY:
+            raise KeyError(viscosity)
+        self.h = C.c_void_p()
+        _check(self.L.afx_rans_create(C.byref(self.h), C.byref(mesh.d), C.byref(self.gas), VISCOSITY[viscosity], device))
+        self.n4 = 4 * (mesh.N + mesh.G)
+        self.bcs = {}
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.afx_rans_destroy(self.h)
+        except Exception:
+            pass
+
+    # bcs: {patch name: (type string, dict(mach, angle, T, p) or None)} like rans::Settings::bcs
+    def set_bcs(self, bcs):
+        names = self.mesh.patch_names
+        used = set(int(p) for p in np.unique(self.mesh.bnd_patch))
+        kinds = np.zeros(max(len(names), 1), np.uint8)
+        vars_ = (BVars * max(len(names), 1))()
+        for i, nm in enumerate(names):
+            if nm not in bcs:
+                if i in used:
+                    raise KeyError(nm)  # std::out_of_range from bcs.at() in the reference
+                continue
+            typ, v = bcs[nm]
+            v = v or {}
+            kinds[i] = BC_KINDS.get(typ, 0)
+            vars_[i] = BVars(v.get("mach", 0.2), v.get("angle", 0.0), v.get("T", 1.0), v.get("p", 1.0))
+        self.bcs = dict(bcs)
+        _check(self.L.afx_rans_set_bcs(self.h, len(names), _ptr(kinds), vars_))
+
+    def set_options(self, second_order=True, gradient="green-gauss", limiter_k=5.0, cfl=None):
+        _check(self.L.afx_rans_set_options(self.h, int(bool(second_order)), GRADIENT[gradient], limiter_k))
+        if cfl is not None:
+            self.set_cfl(cfl)
+
+    def set_cfl(self, cfl): _check(self.L.afx_rans_set_cfl(self.h, cfl))
+    def init(self): _check(self.L.afx_rans_init(self.h))
+    def refill_bcs(self): _check(self.L.afx_rans_refill_bcs(self.h))
+    def bcs_from_internal(self): _check(self.L.afx_rans_bcs_from_internal(self.h))
+
+    def set_q(self, q):
+        q = np.ascontiguousarray(q, np.float64)
+        if q.size != self.n4:
+            raise ValueError("q must have 4*(N+G) entries")
+        _check(self.L.afx_rans_set_q(self.h, _ptr(q)))
+
+    def get_q(self, out=None):
+        out = np.empty(self.n4) if out is None else out
+        _check(self.L.afx_rans_get_q(self.h, _ptr(out)))
+        return out
+
+    def get(self, name):
+        out = np.empty(self.mesh.N + self.mesh.G if name == "dt" else self.n4)
+        _check(self.L.afx_rans_get_field(self.h, FIELDS[name], _ptr(out)))
+        return out
+
+    def get_uniform_residual(self):
+        v = C.c_double()
+        _check(self.L.afx_rans_uniform_residual(self.h, C.byref(v)))
+        return v.value
+
+    # explicitSolver: fill() and compute() are no-ops returning 0 (solver.h:738-739)
+    def fill(self): return None
+    def compute(self): return 0
+
+    def solve(self, relaxation=1.0, tol=0.0, rhs_iterations=5):
+        """explicitSolver::solve: one iteration, returns ||qW||_2 (or -1 on numeric failure)."""
+        v = C.c_double()
+        rc = self.L.afx_rans_step_explicit(self.h, relaxation, C.byref(v))
+        if rc == -3:
+            return -1.0
+        _check(rc)
+        return v.value
+
+    def run(self, n_iter, relaxation=1.0):
+        norms = np.zeros(n_iter)
+        _check(self.L.afx_rans_run_explicit(self.h, relaxation, n_iter, _ptr(norms)))
+        return norms
+
+    def phase_dt_gradients(self): _check(self.L.afx_rans_phase_dt_gradients(self.h))
+    def phase_limiters(self): _check(self.L.afx_rans_phase_limiters(self.h))
+
+    def phase_residual(self):
+        v = C.c_double()
+        _check(self.L.afx_rans_phase_residual(self.h, C.byref(v)))
+        return v.value
+
+    def residual(self):
+        v = C.c_double()
+        _check(self.L.afx_rans_residual(self.h, C.byref(v)))
+        return v.value
+
+    def fill_jacobian(self): _check(self.L.afx_rans_fill_jacobian(self.h))
+
+    def jacobian_blocks(self):
+        NT, E = self.mesh.N + self.mesh.G, self.mesh.E
+        d = np.zeros((NT, 4, 4)); o01 = np.zeros((E, 4, 4)); o10 = np.zeros((E, 4, 4))
+        _check(self.L.afx_rans_get_jacobian_blocks(self.h, _ptr(d), _ptr(o01), _ptr(o10)))
+        return d, o01, o10
+
+    def wall_forces(self, patch_name):
+        out = np.zeros(3)
+        p = self.mesh.patch_names.index(patch_name) if patch_name in self.mesh.patch_names else -1
+        _check(self.L.afx_rans_wall_forces(self.h, p, _ptr(out)))
+        return tuple(out)  # cl, cd, cm
+
+    def wall_cp(self, patch_name):
+        p = self.mesh.patch_names.index(patch_name)
+        n = _check(self.L.afx_rans_wall_cp(self.h, p, None))
+        cp = np.zeros(n)
+        _check(self.L.afx_rans_wall_cp(self.h, p, _ptr(cp)))
+        return cp
+
+    def last_device_ms(self):
+        v = C.c_double()
+        self.L.afx_rans_last_device_ms(self.h, C.byref(v))
+        return v.value
+
+    def launch_count(self):
+        return int(self.L.afx_rans_launch_count(self.h))
+
+    def profile_explicit(self, n_iter=5, relaxation=1.0):
+        out = np.zeros(4)
+        _check(self.L.afx_rans_profile_explicit(self.h, relaxation, n_iter, _ptr(out)))
+        return dict(dt_grad=out[0], limiter=out[1], flux=out[2], gather_update=out[3])

@@ -1,0 +1,512 @@
+// rans_kernels.cuh -- sm_100a kernels of the rans hot path.
+//
+// Data layout in HBM (all in the solver's internal, renumbered order):
+//   cell states q, qk*, gx, gy, lim, qW : AoS, one 32-byte d4 per cell (real
+//       cells first, ghost cells after) -> one 256-bit load per gathered cell,
+//       one full 32-byte DRAM sector per access;
+//   faces: cells (uint2), geomA = {nx, ny, len, w_gg}, geomB = {d0x, d0y, d1x,
+//       d1y} (face centre minus the two cell centres), kind (u8), all indexed
+//       by face and read fully coalesced by the face kernel;
+//   cell->face lists: cf[slot][cell], slot-major so a warp reads consecutive
+//       words; slots are sorted by the ORIGINAL edge id, so per-cell sums run
+//       in the order of the reference's serial edge loops (deterministic, and
+//       bit-identical to the CPU result).
+//   flux: one d4 per face, written once by the face kernel (each face is
+//       evaluated once, in the reference's cell0 -> cell1 orientation) and
+//       gathered by the two owner cells (owner-computes scatter, no atomics).
+#pragma once
+#include "rans_physics.cuh"
+
+namespace afx {
+
+constexpr uint32_t CF_NONE = 0xFFFFFFFFu;
+constexpr uint32_t CF_SIDE = 0x80000000u;  // this cell is cell1 of the face
+constexpr uint32_t CF_BND = 0x40000000u;   // boundary face (cell1 is a ghost)
+constexpr uint32_t CF_ID = 0x3FFFFFFFu;
+
+struct DevMesh {
+    uint32_t N, G, E, NT;        // real cells, ghosts, faces, N+G
+    const uint2* fcells;         // [E]
+    const d4* fgA;               // [E] nx, ny, len, w
+    const d4* fgB;               // [E] d0x, d0y, d1x, d1y
+    const d4* ftij;              // [E] t0, t1, l, - (laminar face-gradient direction, solver.h:369-376)
+    const uint8_t* fkind;        // [E]
+    const uint32_t* cf;          // [4][N]
+    const double* area;          // [NT]
+    const double* lsqM;          // [8][N]  (M * dT) rows in cellsEdges order, LSQ only
+    const uint16_t* lsq_perm;    // [N] bits 0-7: slot of local side j (2 bits each), bits 8-10: number of sides
+};
+
+// ---------------------------------------------------------------------------
+// Local time step + gradients of q, one thread per real cell.
+// calc_dt (solver.h:308-356), set_walls_from_internal (289-305, folded in: the
+// owner writes its wall ghosts), calc_gradients Green-Gauss (428-469) or
+// least-squares (470-513).  Source state is the iteration-start q.
+// ---------------------------------------------------------------------------
+template <int GRAD>
+__global__ void __launch_bounds__(256) k_dt_grad(DevMesh m, d4* __restrict__ q, double* __restrict__ dt,
+                                                 d4* __restrict__ gx, d4* __restrict__ gy, const double* __restrict__ prm,
+                                                 double gam, int want_grad, int walls)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m.N) return;
+    const d4 qi = q[i];
+    double dsum = 0;
+    d4 ax = mk4(0, 0, 0, 0), ay = mk4(0, 0, 0, 0);
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const uint32_t cfv = m.cf[(size_t)s * m.N + i];
+        if (cfv == CF_NONE) continue;
+        const uint32_t f = cfv & CF_ID;
+        const bool side = cfv & CF_SIDE;
+        const uint2 fc = m.fcells[f];
+        const d4 gA = m.fgA[f];
+        const int kind = m.fkind[f];
+        const uint32_t j = side ? fc.x : fc.y;
+        const bool wall_ghost = walls && (cfv & CF_BND) && (kind == K_SLIPWALL || kind == K_WALL);
+        if (wall_ghost) q[j] = qi;  // ghost <- owner (set_walls_from_internal)
+        const d4 qj = wall_ghost ? qi : q[j];
+        const d4 qL = side ? qj : qi, qR = side ? qi : qj;  // states of cell0 / cell1
+        const double nx = gA.x, ny = gA.y, len = gA.z;
+        // spectral radius, solver.h:328-345
+        const double V_L = (qL.y * nx + qL.z * ny) / qL.x;
+        const double p_L = (gam - 1) * (qL.w - 0.5 / qL.x * (qL.y * qL.y + qL.z * qL.z));
+        const double eig_L = sqrt(p_L * gam / qL.x) + fabs(V_L);
+        double eig = eig_L;
+        if (kind == K_INTERNAL) {
+            const double V_R = (qR.y * nx + qR.z * ny) / qR.x;
+            const double p_R = (gam - 1) * (qR.w - 0.5 / qR.x * (qR.y * qR.y + qR.z * qR.z));
+            const double eig_R = sqrt(p_R * gam / qR.x) + fabs(V_R);
+            eig = (eig_L < eig_R) ? eig_R : eig_L;
+        }
+        dsum += eig * len;
+        if (GRAD == 0 && want_grad) {  // Green-Gauss face value, solver.h:444-457
+            const d4 qv = bc_vars(kind, qL, qR, nx, ny, gam);
+            const double w = gA.w;
+            const double f0 = (qL.x * (1.0 - w) + qv.x * w) * len;
+            const double f1 = (qL.y * (1.0 - w) + qv.y * w) * len;
+            const double f2 = (qL.z * (1.0 - w) + qv.z * w) * len;
+            const double f3 = (qL.w * (1.0 - w) + qv.w * w) * len;
+            if (!side) {
+                ax.x += f0 * nx; ax.y += f1 * nx; ax.z += f2 * nx; ax.w += f3 * nx;
+                ay.x += f0 * ny; ay.y += f1 * ny; ay.z += f2 * ny; ay.w += f3 * ny;
+            } else {
+                ax.x -= f0 * nx; ax.y -= f1 * nx; ax.z -= f2 * nx; ax.w -= f3 * nx;
+                ay.x -= f0 * ny; ay.y -= f1 * ny; ay.z -= f2 * ny; ay.w -= f3 * ny;
+            }
+        }
+    }
+    const double A = m.area[i];
+    dt[i] = prm[0] * A / dsum;  // prm[0] = cfl
+    if (!want_grad) return;
+    if (GRAD == 0) {
+        ax.x /= A; ax.y /= A; ax.z /= A; ax.w /= A;
+        ay.x /= A; ay.y /= A; ay.z /= A; ay.w /= A;
+    } else {  // least squares, rows in cellsEdges order, solver.h:471-508
+        const uint32_t perm = m.lsq_perm[i];  // bits 0-7: slot of local side j (2 bits each); bits 8-10: number of sides
+        const int nside = (int)(perm >> 8);
+#pragma unroll
+        for (int jrow = 0; jrow < 4; ++jrow) {
+            if (jrow >= nside) break;
+            const int s = (perm >> (2 * jrow)) & 3;
+            const uint32_t cfv = m.cf[(size_t)s * m.N + i];
+            const uint32_t f = cfv & CF_ID;
+            const uint2 fc = m.fcells[f];
+            const d4 gA = m.fgA[f];
+            const int kind = m.fkind[f];
+            const uint32_t j = (cfv & CF_SIDE) ? fc.x : fc.y;
+            const d4 qn = q[j];
+            const d4 qv = bc_vars(kind, qi, qn, gA.x, gA.y, gam);  // (q_p, q_n) whatever the orientation
+            const double d0 = qi.x - qv.x, d1 = qi.y - qv.y, d2 = qi.z - qv.z, d3 = qi.w - qv.w;
+            const double m0 = m.lsqM[(size_t)jrow * m.N + i], m1 = m.lsqM[(size_t)(4 + jrow) * m.N + i];
+            ax.x += m0 * d0; ax.y += m0 * d1; ax.z += m0 * d2; ax.w += m0 * d3;
+            ay.x += m1 * d0; ay.y += m1 * d1; ay.z += m1 * d2; ay.w += m1 * d3;
+        }
+    }
+    gx[i] = ax;
+    gy[i] = ay;
+}
+
+// ---------------------------------------------------------------------------
+// Venkatakrishnan limiter, one thread per real cell.  calc_limiters
+// (solver.h:517-593): min/max over the edge neighbours (ghosts included) of the
+// stage state, then the minimum of the limiter function over the cell's faces.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double venkat(double dqg, double dmax, double dmin, double K3a)
+{
+    if (dqg > 1e-16)
+        return 1 / dqg * ((dmax * dmax + K3a) * dqg + 2 * dqg * dqg * dmax) / (dmax * dmax + 2 * dqg * dqg + dmax * dqg + K3a);
+    if (dqg < -1e-16)
+        return 1 / dqg * ((dmin * dmin + K3a) * dqg + 2 * dqg * dqg * dmin) / (dmin * dmin + 2 * dqg * dqg + dmin * dqg + K3a);
+    return 1.0;
+}
+
+__global__ void __launch_bounds__(256) k_limiter(DevMesh m, const d4* __restrict__ qk, const d4* __restrict__ gx,
+                                                 const d4* __restrict__ gy, d4* __restrict__ lim, double limiter_k)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m.N) return;
+    const d4 qi = qk[i];
+    d4 lo = qi, hi = qi;
+    uint32_t cfs[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const uint32_t cfv = m.cf[(size_t)s * m.N + i];
+        cfs[s] = cfv;
+        if (cfv == CF_NONE) continue;
+        const uint2 fc = m.fcells[cfv & CF_ID];
+        const d4 qj = qk[(cfv & CF_SIDE) ? fc.x : fc.y];
+        lo.x = fmin(lo.x, qj.x); lo.y = fmin(lo.y, qj.y); lo.z = fmin(lo.z, qj.z); lo.w = fmin(lo.w, qj.w);
+        hi.x = fmax(hi.x, qj.x); hi.y = fmax(hi.y, qj.y); hi.z = fmax(hi.z, qj.z); hi.w = fmax(hi.w, qj.w);
+    }
+    const d4 gxi = gx[i], gyi = gy[i];
+    const double Ka = limiter_k * sqrt(m.area[i]);
+    const double K3a = Ka * Ka * Ka;
+    const d4 dmax = mk4(hi.x - qi.x, hi.y - qi.y, hi.z - qi.z, hi.w - qi.w);
+    const d4 dmin = mk4(lo.x - qi.x, lo.y - qi.y, lo.z - qi.z, lo.w - qi.w);
+    d4 l = mk4(1, 1, 1, 1);
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const uint32_t cfv = cfs[s];
+        if (cfv == CF_NONE) continue;
+        const d4 gB = m.fgB[cfv & CF_ID];
+        const double dx = (cfv & CF_SIDE) ? gB.z : gB.x, dy = (cfv & CF_SIDE) ? gB.w : gB.y;
+        l.x = fmin(l.x, venkat(gxi.x * dx + gyi.x * dy, dmax.x, dmin.x, K3a));
+        l.y = fmin(l.y, venkat(gxi.y * dx + gyi.y * dy, dmax.y, dmin.y, K3a));
+        l.z = fmin(l.z, venkat(gxi.z * dx + gyi.z * dy, dmax.z, dmin.z, K3a));
+        l.w = fmin(l.w, venkat(gxi.w * dx + gyi.w * dy, dmax.w, dmin.w, K3a));
+    }
+    lim[i] = l;
+}
+
+// ---------------------------------------------------------------------------
+// Face loop, one thread per face: MUSCL reconstruction + flux, written once.
+// explicitSolver::calc_residual (solver.h:751-786) / fillRhoRHS (1097-1134) /
+// get_uniform_residual (659-686, UNIFORM=1: both states are the far-field state).
+// average_gradients (solver.h:359-398) feeds the laminar term with the
+// iteration-start q.
+// ---------------------------------------------------------------------------
+template <int SECOND, int VISC, int UNIFORM>
+__global__ void __launch_bounds__(256) k_flux(DevMesh m, const d4* __restrict__ qk, const d4* __restrict__ q0,
+                                              const d4* __restrict__ gx, const d4* __restrict__ gy,
+                                              const d4* __restrict__ lim, d4* __restrict__ flux, GasC g, d4 qfar)
+{
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= m.E) return;
+    const uint2 fc = m.fcells[f];
+    const d4 gA = m.fgA[f];
+    const int kind = m.fkind[f];
+    d4 qL, qR;
+    if (UNIFORM) { qL = qfar; qR = qfar; }
+    else { qL = qk[fc.x]; qR = qk[fc.y]; }
+    d4 gL0, gL1, gR0, gR1;
+    if ((SECOND && !UNIFORM) || VISC == 1) { gL0 = gx[fc.x]; gL1 = gy[fc.x]; gR0 = gx[fc.y]; gR1 = gy[fc.y]; }
+    if (SECOND && !UNIFORM) {  // solver.h:774-781
+        const d4 gB = m.fgB[f];
+        const d4 lL = lim[fc.x], lR = lim[fc.y];
+        qL.x = qL.x + (gL0.x * gB.x + gL1.x * gB.y) * lL.x;
+        qL.y = qL.y + (gL0.y * gB.x + gL1.y * gB.y) * lL.y;
+        qL.z = qL.z + (gL0.z * gB.x + gL1.z * gB.y) * lL.z;
+        qL.w = qL.w + (gL0.w * gB.x + gL1.w * gB.y) * lL.w;
+        qR.x = qR.x + (gR0.x * gB.z + gR1.x * gB.w) * lR.x;
+        qR.y = qR.y + (gR0.y * gB.z + gR1.y * gB.w) * lR.y;
+        qR.z = qR.z + (gR0.z * gB.z + gR1.z * gB.w) * lR.z;
+        qR.w = qR.w + (gR0.w * gB.z + gR1.w * gB.w) * lR.w;
+    }
+    d4 gfx = mk4(0, 0, 0, 0), gfy = mk4(0, 0, 0, 0);
+    if (VISC == 1 && kind == K_INTERNAL) {  // face gradient, solver.h:369-397
+        const d4 t = m.ftij[f];
+        const d4 a = q0[fc.x], b = q0[fc.y];
+        const double bx0 = (gL0.x + gR0.x) * 0.5, by0 = (gL1.x + gR1.x) * 0.5;
+        const double bx1 = (gL0.y + gR0.y) * 0.5, by1 = (gL1.y + gR1.y) * 0.5;
+        const double bx2 = (gL0.z + gR0.z) * 0.5, by2 = (gL1.z + gR1.z) * 0.5;
+        const double bx3 = (gL0.w + gR0.w) * 0.5, by3 = (gL1.w + gR1.w) * 0.5;
+        const double e0 = (bx0 * t.x + by0 * t.y) - (a.x - b.x) / t.z;
+        const double e1 = (bx1 * t.x + by1 * t.y) - (a.y - b.y) / t.z;
+        const double e2 = (bx2 * t.x + by2 * t.y) - (a.z - b.z) / t.z;
+        const double e3 = (bx3 * t.x + by3 * t.y) - (a.w - b.w) / t.z;
+        gfx = mk4(bx0 - e0 * t.x, bx1 - e1 * t.x, bx2 - e2 * t.x, bx3 - e3 * t.x);
+        gfy = mk4(by0 - e0 * t.y, by1 - e1 * t.y, by2 - e2 * t.y, by3 - e3 * t.y);
+    }
+    d4 fl = face_flux<VISC>(kind, qL, qR, gfx, gfy, gA.x, gA.y, g);
+    fl.x *= gA.z; fl.y *= gA.z; fl.z *= gA.z; fl.w *= gA.z;
+    flux[f] = fl;
+}
+
+// ---------------------------------------------------------------------------
+// Block-level deterministic sum of one double per thread -> partial[blockIdx];
+// the last block to finish adds the partials in index order and stores the
+// square root (residual L2 norm, solver.h:827 / 1178).
+// ---------------------------------------------------------------------------
+constexpr unsigned int NORM_RING = 1u << 16;  // capacity of the device-side residual history ring
+
+__device__ __forceinline__ void block_norm_accumulate(double v, double* partial, unsigned int* counter,
+                                                      double* norms, unsigned int* norm_idx)
+{
+    __shared__ double sh[32];
+    __shared__ bool last;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) sh[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+        double t = lane < nw ? sh[lane] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+        if (lane == 0) {
+            partial[blockIdx.x] = t;
+            __threadfence();
+            last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+        }
+    }
+    __syncthreads();
+    if (last) {  // fixed-order final reduction by one block
+        double t = 0;
+        for (uint32_t b = threadIdx.x; b < gridDim.x; b += blockDim.x) t += __ldcg(&partial[b]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+        __syncthreads();
+        if (lane == 0) sh[wid] = t;
+        __syncthreads();
+        if (wid == 0) {
+            double u = lane < nw ? sh[lane] : 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) u += __shfl_down_sync(0xffffffffu, u, o);
+            if (lane == 0) { const unsigned int k = *norm_idx; norms[k % NORM_RING] = sqrt(u); *norm_idx = k + 1; *counter = 0; }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Owner-computes gather of the face fluxes + stage update, one thread per real
+// cell.  MODE 0: explicit stage (solver.h:787-798, 818-821): qW = sum/area,
+// qk_out = q + qW*dt*alpha*relax, wall ghosts of qk_out follow their owner
+// (solver.h:811 of the next stage); qk_out may alias q on the last stage.
+// MODE 1: implicit right-hand side (solver.h:1135-1151): rhs = sum, no
+// division, no update, ghost rows zero.  MODE 2: uniform-flow residual
+// (solver.h:680-689): like MODE 1 but the ghost rows of two-sided boundary
+// faces count in the norm.  LAST adds the squared entries to the residual norm
+// and stores the vector (qW or rhs).
+// ---------------------------------------------------------------------------
+template <int MODE, int LAST>
+__global__ void __launch_bounds__(256) k_gather_update(DevMesh m, const d4* __restrict__ flux,
+                                                       const d4* q, const d4* qk_in,
+                                                       d4* qk_out, const double* __restrict__ dt,
+                                                       d4* __restrict__ qW, double alpha, const double* __restrict__ prm,
+                                                       int walls, double* partial, unsigned int* counter, double* norms,
+                                                       unsigned int* norm_idx)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    double nrm = 0;
+    if (i < m.N) {
+        d4 r = mk4(0, 0, 0, 0);
+        uint32_t bnd[4];
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const uint32_t cfv = m.cf[(size_t)s * m.N + i];
+            bnd[s] = cfv;
+            if (cfv == CF_NONE) continue;
+            const d4 fl = flux[cfv & CF_ID];
+            if (cfv & CF_SIDE) { r.x += fl.x; r.y += fl.y; r.z += fl.z; r.w += fl.w; }
+            else { r.x -= fl.x; r.y -= fl.y; r.z -= fl.z; r.w -= fl.w; }
+            if (LAST && MODE != 1 && (cfv & CF_BND) && m.fkind[cfv & CF_ID] == K_INTERNAL)  // two-sided boundary face: the ghost row of qW holds +flux
+                nrm += fl.x * fl.x + fl.y * fl.y + fl.z * fl.z + fl.w * fl.w;
+        }
+        if (MODE == 0) {
+            const double A = m.area[i];
+            r.x /= A; r.y /= A; r.z /= A; r.w /= A;
+            const d4 q0 = q[i];
+            const double dti = dt[i];
+            d4 o;
+            const double relax = prm[1];
+            o.x = q0.x + r.x * dti * alpha * relax;
+            o.y = q0.y + r.y * dti * alpha * relax;
+            o.z = q0.z + r.z * dti * alpha * relax;
+            o.w = q0.w + r.w * dti * alpha * relax;
+            const d4 prev = LAST ? qk_in[i] : o;
+            qk_out[i] = o;
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                const uint32_t cfv = bnd[s];
+                if (!walls || cfv == CF_NONE || !(cfv & CF_BND)) continue;
+                const int kind = m.fkind[cfv & CF_ID];
+                if (kind == K_SLIPWALL || kind == K_WALL) qk_out[m.fcells[cfv & CF_ID].y] = prev;
+            }
+        }
+        if (LAST) {
+            qW[i] = r;
+            nrm += r.x * r.x + r.y * r.y + r.z * r.z + r.w * r.w;
+        }
+    }
+    if (LAST) block_norm_accumulate(nrm, partial, counter, norms, norm_idx);
+}
+
+// ---------------------------------------------------------------------------
+// Finite-difference flux Jacobian per face (calc_convective_jacobian,
+// physics.h:533-578, called from fillRhoLHS solver.h:1021-1058 with first-order
+// states and the face gradient).  Writes the four 4x4 blocks times the face
+// length: J[f][0]=dF/dqL (row c0,col c0), [1]=dF/dqR (c0,c1), [2]=-dF/dqL
+// (c1,c0), [3]=-dF/dqR (c1,c1).
+// ---------------------------------------------------------------------------
+template <int VISC>
+__device__ __forceinline__ d4 jac_flux(int kind, const double* qL, const double* qR, const d4& gfx, const d4& gfy,
+                                       double nx, double ny, const GasC& g)
+{
+    return face_flux<VISC>(kind, mk4(qL[0], qL[1], qL[2], qL[3]), mk4(qR[0], qR[1], qR[2], qR[3]), gfx, gfy, nx, ny, g);
+}
+
+template <int VISC>
+__global__ void __launch_bounds__(128) k_jacobian(DevMesh m, const d4* __restrict__ q, const d4* __restrict__ gx,
+                                                  const d4* __restrict__ gy, d4* __restrict__ J, GasC g)
+{
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= m.E) return;
+    const uint2 fc = m.fcells[f];
+    const d4 gA = m.fgA[f];
+    const int kind = m.fkind[f];
+    const d4 a = q[fc.x], b = q[fc.y];
+    d4 gfx = mk4(0, 0, 0, 0), gfy = mk4(0, 0, 0, 0);
+    if (VISC == 1 && kind == K_INTERNAL) {
+        const d4 t = m.ftij[f];
+        const d4 gL0 = gx[fc.x], gL1 = gy[fc.x], gR0 = gx[fc.y], gR1 = gy[fc.y];
+        const double bx0 = (gL0.x + gR0.x) * 0.5, by0 = (gL1.x + gR1.x) * 0.5;
+        const double bx1 = (gL0.y + gR0.y) * 0.5, by1 = (gL1.y + gR1.y) * 0.5;
+        const double bx2 = (gL0.z + gR0.z) * 0.5, by2 = (gL1.z + gR1.z) * 0.5;
+        const double bx3 = (gL0.w + gR0.w) * 0.5, by3 = (gL1.w + gR1.w) * 0.5;
+        const double e0 = (bx0 * t.x + by0 * t.y) - (a.x - b.x) / t.z;
+        const double e1 = (bx1 * t.x + by1 * t.y) - (a.y - b.y) / t.z;
+        const double e2 = (bx2 * t.x + by2 * t.y) - (a.z - b.z) / t.z;
+        const double e3 = (bx3 * t.x + by3 * t.y) - (a.w - b.w) / t.z;
+        gfx = mk4(bx0 - e0 * t.x, bx1 - e1 * t.x, bx2 - e2 * t.x, bx3 - e3 * t.x);
+        gfy = mk4(by0 - e0 * t.y, by1 - e1 * t.y, by2 - e2 * t.y, by3 - e3 * t.y);
+    }
+    double qL[4] = {a.x, a.y, a.z, a.w}, qR[4] = {b.x, b.y, b.z, b.w};
+    const d4 f0 = jac_flux<VISC>(kind, qL, qR, gfx, gfy, gA.x, gA.y, g);
+    const double len = gA.z;
+    double JL[4][4], JR[4][4];  // [row][col]
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        {
+            const double h = fmax(1e-6, fabs(qL[i]) * 1e-6);
+            qL[i] += h;
+            const d4 fp = jac_flux<VISC>(kind, qL, qR, gfx, gfy, gA.x, gA.y, g);
+            qL[i] -= h;  // restored by subtraction, residue kept (physics.h:556-558)
+            JL[0][i] = (fp.x - f0.x) / h; JL[1][i] = (fp.y - f0.y) / h; JL[2][i] = (fp.z - f0.z) / h; JL[3][i] = (fp.w - f0.w) / h;
+        }
+        {
+            const double h = fmax(1e-6, fabs(qR[i]) * 1e-6);
+            qR[i] += h;
+            const d4 fp = jac_flux<VISC>(kind, qL, qR, gfx, gfy, gA.x, gA.y, g);
+            qR[i] -= h;
+            JR[0][i] = (fp.x - f0.x) / h; JR[1][i] = (fp.y - f0.y) / h; JR[2][i] = (fp.z - f0.z) / h; JR[3][i] = (fp.w - f0.w) / h;
+        }
+    }
+    d4* Jf = J + (size_t)f * 16;  // 4 blocks x 4 rows
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        Jf[0 + r] = mk4(JL[r][0] * len, JL[r][1] * len, JL[r][2] * len, JL[r][3] * len);
+        Jf[4 + r] = mk4(JR[r][0] * len, JR[r][1] * len, JR[r][2] * len, JR[r][3] * len);
+        Jf[8 + r] = mk4(-JL[r][0] * len, -JL[r][1] * len, -JL[r][2] * len, -JL[r][3] * len);
+        Jf[12 + r] = mk4(-JR[r][0] * len, -JR[r][1] * len, -JR[r][2] * len, -JR[r][3] * len);
+    }
+}
+
+// Diagonal blocks: area/dt on the diagonal plus the face blocks in edge order
+// (solver.h:1012-1018, 1048-1054); ghost rows are the identity (1062-1070).
+__global__ void __launch_bounds__(256) k_jac_diag(DevMesh m, const double* __restrict__ J, const double* __restrict__ dt,
+                                                  double* __restrict__ D)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m.NT) return;
+    double d[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) d[k] = 0;
+    if (i >= m.N) {
+        d[0] = d[5] = d[10] = d[15] = 1;
+    } else {
+        const double t = m.area[i] / dt[i];
+        d[0] = d[5] = d[10] = d[15] = t;
+        for (int s = 0; s < 4; ++s) {
+            const uint32_t cfv = m.cf[(size_t)s * m.N + i];
+            if (cfv == CF_NONE) continue;
+            const double* b = J + (size_t)(cfv & CF_ID) * 64 + ((cfv & CF_SIDE) ? 48 : 0);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) d[k] += b[k];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) D[(size_t)i * 16 + k] = d[k];
+}
+
+// ---------------------------------------------------------------------------
+// Wall forces (get_wall_profile, post.h:341-376): one block, boundary edges of
+// one patch, warp-shuffle reduction of (fx, fy, -m).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_wall_forces(const uint32_t* __restrict__ bface, const int32_t* __restrict__ bpatch,
+                                                     uint32_t G, int patch, DevMesh m, const d4* __restrict__ q,
+                                                     const double* __restrict__ bcx, const double* __restrict__ bcy,
+                                                     double gam, double p_inf, double mach_inf, double xmin, double xmax,
+                                                     double x_moment, double y_moment, double* __restrict__ out3,
+                                                     double* __restrict__ cp_out)
+{
+    __shared__ double sh[3][8];
+    double fx = 0, fy = 0, mm = 0;
+    for (uint32_t b = threadIdx.x; b < G; b += blockDim.x) {
+        if (bpatch[b] != patch) continue;
+        const uint32_t f = bface[b];
+        const d4 qc = q[m.fcells[f].x];
+        const d4 gA = m.fgA[f];
+        const double p = (gam - 1) * (qc.w - 0.5 / qc.x * (qc.y * qc.y + qc.z * qc.z));
+        const double cp = 2. / (gam * mach_inf * mach_inf) * (p / p_inf - 1.);
+        if (cp_out) cp_out[b] = cp;
+        const double fxi = cp * gA.x * gA.z / (xmax - xmin);
+        const double fyi = cp * gA.y * gA.z / (xmax - xmin);
+        const double mi = (bcx[b] - x_moment) / (xmax - xmin) * fyi - (bcy[b] - y_moment) / (xmax - xmin) * fxi;
+        fx += fxi; fy += fyi; mm -= mi;
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        fx += __shfl_down_sync(0xffffffffu, fx, o);
+        fy += __shfl_down_sync(0xffffffffu, fy, o);
+        mm += __shfl_down_sync(0xffffffffu, mm, o);
+    }
+    if (lane == 0) { sh[0][wid] = fx; sh[1][wid] = fy; sh[2][wid] = mm; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0, b = 0, c = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += sh[0][w]; b += sh[1][w]; c += sh[2][w]; }
+        out3[0] = a; out3[1] = b; out3[2] = c;
+    }
+}
+
+// small utilities -----------------------------------------------------------
+__global__ void k_fill_cells(d4* __restrict__ q, uint32_t n, d4 v)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) q[i] = v;
+}
+// ghost rows: dst[ghost] = src_state[b] (refill_bcs) or dst[ghost] = dst[owner] (bcs_from_internal)
+__global__ void k_ghost_fill(d4* __restrict__ q, const uint32_t* __restrict__ bghost, const uint32_t* __restrict__ bowner,
+                             const d4* __restrict__ bstate, uint32_t G, int from_owner)
+{
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < G) q[bghost[b]] = from_owner ? q[bowner[b]] : bstate[b];
+}
+// permuted copies between reference order (host layout) and internal order
+__global__ void k_permute4(const d4* __restrict__ src, d4* __restrict__ dst, const uint32_t* __restrict__ idx, uint32_t n, int scatter)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (scatter) dst[idx[i]] = src[i]; else dst[i] = src[idx[i]];
+}
+__global__ void k_permute1(const double* __restrict__ src, double* __restrict__ dst, const uint32_t* __restrict__ idx, uint32_t n, uint32_t nsrc)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t j = idx[i];
+    dst[i] = j < nsrc ? src[j] : 0.0;
+}
+
+}  // namespace afx

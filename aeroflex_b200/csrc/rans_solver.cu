@@ -1,0 +1,983 @@
+// rans_solver.cu -- device state, launch sequences and the afx_rans_* C ABI.
+//
+// One afx_rans handle == one rans::solver of the reference on one B200.  All
+// state lives in HBM in a renumbered layout (Hilbert order of the cell centres,
+// faces sorted by their lower cell); the ABI speaks the reference's order.
+// The explicit iteration (explicitSolver::solve, solver.h:802-828) is 10
+// kernels -- dt+gradients once (the gradients of all three stages are those of
+// the iteration-start state), then limiter / face flux / gather+update
+// per stage -- captured once into a CUDA graph and replayed per iteration; the
+// residual norm is reduced on the device into a ring that the host reads once
+// per call.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/afx_rans.h"
+#include "rans_kernels.cuh"
+
+namespace afx {
+
+thread_local std::string g_last_error;
+void set_error(const std::string& s) { g_last_error = s; }
+
+struct CudaError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+struct InvalidArg : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+struct NumericError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+#define CK(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess)                                                                         \
+            throw ::afx::CudaError(std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" + \
+                            std::to_string(__LINE__) + ")");                                           \
+    } while (0)
+
+template <class T>
+struct DBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    void alloc(size_t n_)
+    {
+        free();
+        n = n_;
+        if (n) CK(cudaMalloc(&p, n * sizeof(T)));
+    }
+    void zero(cudaStream_t st) { if (n) CK(cudaMemsetAsync(p, 0, n * sizeof(T), st)); }
+    void upload(const std::vector<T>& h, cudaStream_t st)
+    {
+        if (h.size() != n) alloc(h.size());
+        if (n) CK(cudaMemcpyAsync(p, h.data(), n * sizeof(T), cudaMemcpyHostToDevice, st));
+    }
+    void free() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    ~DBuf() { free(); }
+};
+
+// ---- Hilbert index on rank coordinates -----------------------------------
+static uint64_t hilbert_d(uint32_t x, uint32_t y, int order)
+{
+    uint64_t d = 0;
+    for (uint32_t s = 1u << (order - 1); s > 0; s >>= 1) {
+        const uint32_t rx = (x & s) ? 1 : 0, ry = (y & s) ? 1 : 0;
+        d += (uint64_t)s * s * ((3 * rx) ^ ry);
+        if (ry == 0) {
+            if (rx == 1) { x = s - 1 - (x & (s - 1)) + (x & ~(2 * s - 1)); y = s - 1 - (y & (s - 1)) + (y & ~(2 * s - 1)); }
+            const uint32_t t = x; x = y; y = t;
+        }
+    }
+    return d;
+}
+
+struct Solver {
+    int device = 0;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t evp[16] = {};
+    uint32_t N = 0, G = 0, E = 0, NT = 0;
+    GasC gas{};
+    int viscosity_model = 0, viscous_type = 0, visc_not_inviscid = 0;
+    int second_order = 1, gradient_scheme = AFX_GRAD_GREEN_GAUSS;
+    double limiter_k = 5., cfl = 1.;
+    double relax_dev = -1, cfl_dev = -1;
+
+    // permutations (host)
+    std::vector<uint32_t> c_old2new, c_new2old, f_old2new, f_new2old;
+    // host copies needed after creation
+    std::vector<uint32_t> h_fcells;           // new order [E][2]
+    std::vector<uint32_t> h_bnd_face;         // [G] new face id of boundary b (reference boundary order)
+    std::vector<int32_t> h_bnd_patch;         // [G]
+    std::vector<uint8_t> h_bnd_kind;          // [G]
+    std::vector<afx_bvars> h_bnd_vars;        // [G]
+    std::vector<double> h_bcx, h_bcy;         // [G] boundary edge centres
+    bool bcs_set = false;
+
+    // device geometry
+    DBuf<uint2> fcells; DBuf<d4> fgA, fgB, ftij; DBuf<uint8_t> fkind; DBuf<uint32_t> cf; DBuf<double> area;
+    DBuf<double> lsqM; DBuf<uint16_t> lsq_perm;
+    DBuf<uint32_t> bface, bghost, bowner; DBuf<int32_t> bpatch; DBuf<d4> bstate; DBuf<double> bcx, bcy;
+    DBuf<uint32_t> perm_c_new2old, perm_c_old2new;
+    // device state
+    DBuf<d4> q, qkA, qkB, gx, gy, lim, qW, rhs, flux, stage;
+    DBuf<double> dt, dt_ref;
+    DBuf<d4> J; DBuf<double> D;   // Jacobian face blocks [E][16] d4 and diagonal blocks [NT][16]
+    DBuf<double> partial, norms, prm, scratch;
+    DBuf<unsigned int> counters;  // [0] block counter, [1] norm ring index
+    double* h_pinned = nullptr;   // pinned staging for scalars
+    unsigned int norm_idx_host = 0;
+
+    cudaGraphExec_t graph_exec = nullptr;
+    uint64_t graph_key = 0;
+    bool use_graph = true;
+    int64_t launches = 0;
+    double last_ms = 0;
+    bool jac_valid = false;
+
+    DevMesh dm{};
+
+    ~Solver()
+    {
+        cudaSetDevice(device);
+        if (graph_exec) cudaGraphExecDestroy(graph_exec);
+        if (h_pinned) cudaFreeHost(h_pinned);
+        for (auto& e : evp) if (e) cudaEventDestroy(e);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (st) cudaStreamDestroy(st);
+    }
+
+    void use() { CK(cudaSetDevice(device)); }
+    static unsigned blocks(size_t n, unsigned bs = 256) { return (unsigned)((n + bs - 1) / bs); }
+
+    void create(const afx_mesh_desc& m, const afx_gas& g, int visc, int dev);
+    void set_bcs(int n_patch, const uint8_t* kinds, const afx_bvars* vars);
+    void set_options(int so, int grad, double k);
+    void push_params(double relax);
+    void launch_dt_grad(bool want_grad, bool walls);
+    void launch_limiter(const d4* qk);
+    void launch_flux(const d4* qk, bool uniform, d4 qfar);
+    template <int MODE, int LAST>
+    void launch_gather(const d4* qk_in, d4* qk_out, d4* vec_out, double alpha, bool walls);
+    void explicit_iteration();
+    void invalidate_graph() { if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; } }
+    void run_explicit(double relax, int n_iter, double* norms_out);
+    double fetch_last_norm();
+    void check_norm(double v) { if (!(v == v) || std::isinf(v)) throw NumericError("residual norm is not finite"); }
+    double residual_rhs();
+    double uniform_residual();
+    void fill_jacobian();
+    void to_ref_order4(const d4* dev_new, double* host_out);
+    void from_ref_order4(const double* host_in, d4* dev_new);
+    void sync_ghost_rows();
+    bool boundary_variables(afx_bvars* out) const;
+    void conservative(const afx_bvars& v, double q4[4]) const;
+};
+
+// core.h:73-83
+void Solver::conservative(const afx_bvars& b, double q4[4]) const
+{
+    const double c = std::sqrt(gas.gamma * gas.R * b.T);
+    const double u = b.mach * c * std::cos(b.angle);
+    const double v = b.mach * c * std::sin(b.angle);
+    const double rho = b.p / (gas.R * b.T);
+    const double rhoE = b.p / (gas.gamma - 1) + 0.5 * rho * (u * u + v * v);
+    q4[0] = rho; q4[1] = rho * u; q4[2] = rho * v; q4[3] = rhoE;
+}
+
+// solver.h:597-611
+bool Solver::boundary_variables(afx_bvars* out) const
+{
+    *out = afx_bvars{0.2, 0., 1., 1.};
+    for (uint32_t b = 0; b < G; ++b)
+        if (h_bnd_kind[b] == AFX_BC_FARFIELD) { *out = h_bnd_vars[b]; return true; }
+    return false;
+}
+
+void Solver::create(const afx_mesh_desc& m, const afx_gas& g, int visc, int dev)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        throw CudaError("no CUDA device available: libaeroflex_rans_b200 has no CPU fallback");
+    if (dev < 0 || dev >= ndev) throw InvalidArg("device ordinal out of range");
+    device = dev;
+    use();
+    cudaDeviceProp prop{};
+    CK(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major < 10) throw CudaError(std::string("device '") + prop.name + "' is not sm_100 class; this library is built for sm_100a only");
+    CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
+    for (auto& e : evp) CK(cudaEventCreate(&e));
+    CK(cudaMallocHost(&h_pinned, 64 * sizeof(double)));
+    if (const char* e = getenv("AFX_NO_GRAPH")) use_graph = !(e[0] == '1');
+
+    N = m.n_cells; G = m.n_ghost; E = m.n_edges; NT = N + G;
+    if (!N || !E) throw InvalidArg("empty mesh");
+    if (E > CF_ID) throw InvalidArg("too many edges for the 30-bit face index");
+    gas = GasC{g.gamma, g.R, g.mu_L, g.Pr_L, g.cp};
+    viscosity_model = visc;
+    viscous_type = (visc == AFX_VISC_LAMINAR) ? 1 : 0;   // solver.h:203-208 ("SA" never matches)
+    visc_not_inviscid = (visc != AFX_VISC_INVISCID);
+
+    // ---- cell renumbering: Hilbert curve over rank coordinates ----
+    c_old2new.resize(NT); c_new2old.resize(NT);
+    const char* ord = getenv("AFX_ORDER");
+    const bool hilbert = !(ord && std::string(ord) == "none");
+    {
+        std::vector<uint32_t> idx(N);
+        std::iota(idx.begin(), idx.end(), 0u);
+        if (hilbert && N > 64) {
+            std::vector<uint32_t> rx(N), ry(N), tmp(N);
+            std::iota(tmp.begin(), tmp.end(), 0u);
+            std::stable_sort(tmp.begin(), tmp.end(), [&](uint32_t a, uint32_t b) { return m.cells_cx[a] < m.cells_cx[b]; });
+            for (uint32_t r = 0; r < N; ++r) rx[tmp[r]] = r;
+            std::iota(tmp.begin(), tmp.end(), 0u);
+            std::stable_sort(tmp.begin(), tmp.end(), [&](uint32_t a, uint32_t b) { return m.cells_cy[a] < m.cells_cy[b]; });
+            for (uint32_t r = 0; r < N; ++r) ry[tmp[r]] = r;
+            int order = 1;
+            while ((1u << order) < N && order < 31) ++order;
+            std::vector<uint64_t> key(N);
+            for (uint32_t i = 0; i < N; ++i) key[i] = hilbert_d(rx[i], ry[i], order);
+            std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return key[a] < key[b]; });
+        }
+        for (uint32_t n = 0; n < N; ++n) { c_new2old[n] = idx[n]; c_old2new[idx[n]] = n; }
+        // ghosts follow their owners
+        std::vector<uint32_t> gb(G);
+        std::iota(gb.begin(), gb.end(), 0u);
+        std::stable_sort(gb.begin(), gb.end(), [&](uint32_t a, uint32_t b) {
+            return c_old2new[m.edges_cells[2 * (size_t)m.boundary_edges[a]]] < c_old2new[m.edges_cells[2 * (size_t)m.boundary_edges[b]]];
+        });
+        for (uint32_t k = 0; k < G; ++k) {
+            const uint32_t old_ghost = m.edges_cells[2 * (size_t)m.boundary_edges[gb[k]] + 1];
+            if (old_ghost < N || old_ghost >= NT) throw InvalidArg("boundary edge without a ghost cell");
+            c_new2old[N + k] = old_ghost; c_old2new[old_ghost] = N + k;
+        }
+    }
+    // ---- faces sorted by their lower (new) cell ----
+    f_old2new.resize(E); f_new2old.resize(E);
+    {
+        std::vector<uint32_t> fi(E);
+        std::iota(fi.begin(), fi.end(), 0u);
+        std::vector<uint32_t> key(E);
+        for (uint32_t e = 0; e < E; ++e) {
+            const uint32_t a = c_old2new[m.edges_cells[2 * (size_t)e]], b = c_old2new[m.edges_cells[2 * (size_t)e + 1]];
+            key[e] = std::min(a, b);
+        }
+        std::stable_sort(fi.begin(), fi.end(), [&](uint32_t a, uint32_t b) { return key[a] < key[b]; });
+        for (uint32_t n = 0; n < E; ++n) { f_new2old[n] = fi[n]; f_old2new[fi[n]] = n; }
+    }
+    // ---- face records ----
+    std::vector<uint2> h_fc(E); std::vector<d4> h_gA(E), h_gB(E), h_t(E);
+    h_fcells.resize(2 * (size_t)E);
+    std::vector<uint8_t> is_bnd(E, 0);
+    for (uint32_t b = 0; b < G; ++b) is_bnd[m.boundary_edges[b]] = 1;
+    for (uint32_t n = 0; n < E; ++n) {
+        const uint32_t e = f_new2old[n];
+        const uint32_t o0 = m.edges_cells[2 * (size_t)e], o1 = m.edges_cells[2 * (size_t)e + 1];
+        h_fc[n] = make_uint2(c_old2new[o0], c_old2new[o1]);
+        h_fcells[2 * (size_t)n] = h_fc[n].x; h_fcells[2 * (size_t)n + 1] = h_fc[n].y;
+        // Green-Gauss weight exactly as solver.h:436-444
+        const double dxif = m.edges_cx[e] - m.cells_cx[o0], dyif = m.edges_cy[e] - m.cells_cy[o0];
+        const double dif = std::sqrt(dxif * dxif + dyif * dyif);
+        const double dxij = m.cells_cx[o0] - m.cells_cx[o1], dyij = m.cells_cy[o0] - m.cells_cy[o1];
+        const double dij = std::sqrt(dxij * dxij + dyij * dyij);
+        h_gA[n] = d4{m.edges_nx[e], m.edges_ny[e], m.edges_len[e], dif / dij};
+        // reconstruction / limiter offsets, solver.h:541-542, 774-778
+        h_gB[n] = d4{m.edges_cx[e] - m.cells_cx[o0], m.edges_cy[e] - m.cells_cy[o0],
+                     m.edges_cx[e] - m.cells_cx[o1], m.edges_cy[e] - m.cells_cy[o1]};
+        // face-gradient direction, solver.h:369-376
+        double t0 = m.cells_cx[o0] + m.cells_cx[o1], t1 = m.cells_cy[o0] + m.cells_cy[o1];
+        const double l = std::sqrt(t0 * t0 + t1 * t1);
+        t0 /= l; t1 /= l;
+        h_t[n] = d4{t0, t1, l, 0.};
+    }
+    // ---- cell -> face lists, slots in ascending ORIGINAL edge id ----
+    std::vector<uint32_t> h_cf((size_t)4 * N, CF_NONE);
+    std::vector<uint16_t> h_perm(N, 0);
+    std::vector<double> h_area(NT);
+    for (uint32_t n = 0; n < NT; ++n) h_area[n] = m.cells_area[c_new2old[n]];
+    for (uint32_t n = 0; n < N; ++n) {
+        const uint32_t o = c_new2old[n];
+        const uint32_t sz = m.cells_is_tri[o] ? 3u : 4u;
+        uint32_t es[4]; int order[4] = {0, 1, 2, 3};
+        for (uint32_t k = 0; k < sz; ++k) {
+            es[k] = m.cells_edges[4 * (size_t)o + k];
+            if (es[k] >= E) throw InvalidArg("cellsEdges refers to a missing edge");
+        }
+        std::sort(order, order + sz, [&](int a, int b) { return es[a] < es[b]; });
+        uint16_t perm = (uint16_t)(sz << 8);
+        for (uint32_t slot = 0; slot < sz; ++slot) {
+            const uint32_t e = es[order[slot]];
+            uint32_t v = f_old2new[e];
+            if (m.edges_cells[2 * (size_t)e] != o) v |= CF_SIDE;
+            if (is_bnd[e]) v |= CF_BND;
+            h_cf[(size_t)slot * N + n] = v;
+            perm |= (uint16_t)(slot << (2 * order[slot]));  // local side order[slot] lives in this slot
+        }
+        h_perm[n] = perm;
+    }
+    // ---- boundary tables (reference boundary order) ----
+    h_bnd_face.resize(G); h_bnd_patch.assign(m.boundary_patch, m.boundary_patch + G);
+    h_bnd_kind.assign(G, 0); h_bnd_vars.assign(G, afx_bvars{0.2, 0., 1., 1.});
+    h_bcx.resize(G); h_bcy.resize(G);
+    std::vector<uint32_t> h_bghost(G), h_bowner(G);
+    for (uint32_t b = 0; b < G; ++b) {
+        const uint32_t e = m.boundary_edges[b];
+        h_bnd_face[b] = f_old2new[e];
+        h_bowner[b] = c_old2new[m.edges_cells[2 * (size_t)e]];
+        h_bghost[b] = c_old2new[m.edges_cells[2 * (size_t)e + 1]];
+        h_bcx[b] = m.edges_cx[e]; h_bcy[b] = m.edges_cy[e];
+    }
+
+    // ---- upload ----
+    fcells.upload(h_fc, st); fgA.upload(h_gA, st); fgB.upload(h_gB, st);
+    if (viscous_type == 1) ftij.upload(h_t, st);
+    std::vector<uint8_t> h_kind(E, 0);
+    fkind.upload(h_kind, st);
+    cf.upload(h_cf, st); area.upload(h_area, st); lsq_perm.upload(h_perm, st);
+    bface.upload(h_bnd_face, st); bghost.upload(h_bghost, st); bowner.upload(h_bowner, st);
+    bpatch.upload(h_bnd_patch, st); bcx.upload(h_bcx, st); bcy.upload(h_bcy, st);
+    bstate.alloc(G ? G : 1);
+    perm_c_new2old.upload(c_new2old, st); perm_c_old2new.upload(c_old2new, st);
+
+    for (DBuf<d4>* b : {&q, &qkA, &qkB, &gx, &gy, &lim, &qW, &rhs, &stage}) { b->alloc(NT); b->zero(st); }
+    flux.alloc(E); flux.zero(st);
+    dt.alloc(NT); dt.zero(st); dt_ref.alloc(NT);
+    partial.alloc(blocks(NT) + 1); norms.alloc(NORM_RING); norms.zero(st);
+    prm.alloc(8); prm.zero(st); counters.alloc(4); counters.zero(st); scratch.alloc(16);
+    // limiters start at 1 (ghost rows keep that value, solver.h:519)
+    k_fill_cells<<<blocks(NT), 256, 0, st>>>(lim.p, NT, d4{1, 1, 1, 1});
+    ++launches;
+
+    // least-squares coefficients (M * dT), rows in cellsEdges order, solver.h:402-422 + 504
+    {
+        std::vector<double> h_M((size_t)8 * N, 0.);
+        for (uint32_t n = 0; n < N; ++n) {
+            const uint32_t o = c_new2old[n];
+            const uint32_t sz = m.cells_is_tri[o] ? 3u : 4u;
+            double d[4][2], a00 = 0, a01 = 0, a10 = 0, a11 = 0;
+            for (uint32_t j = 0; j < sz; ++j) {
+                const uint32_t e = m.cells_edges[4 * (size_t)o + j];
+                const uint32_t nb = m.edges_cells[2 * (size_t)e] == o ? m.edges_cells[2 * (size_t)e + 1] : m.edges_cells[2 * (size_t)e];
+                d[j][0] = m.cells_cx[nb] - m.cells_cx[o];
+                d[j][1] = m.cells_cy[nb] - m.cells_cy[o];
+                a00 += d[j][0] * d[j][0]; a01 += d[j][0] * d[j][1]; a10 += d[j][1] * d[j][0]; a11 += d[j][1] * d[j][1];
+            }
+            const double det = a00 * a11 - a10 * a01, inv = 1. / det;
+            const double M0 = a11 * inv, M1 = -a01 * inv, M2 = -a10 * inv, M3 = a00 * inv;
+            for (uint32_t j = 0; j < sz; ++j) {
+                h_M[(size_t)j * N + n] = M0 * d[j][0] + M1 * d[j][1];
+                h_M[(size_t)(4 + j) * N + n] = M2 * d[j][0] + M3 * d[j][1];
+            }
+        }
+        lsqM.upload(h_M, st);
+    }
+    CK(cudaStreamSynchronize(st));
+
+    dm.N = N; dm.G = G; dm.E = E; dm.NT = NT;
+    dm.fcells = fcells.p; dm.fgA = fgA.p; dm.fgB = fgB.p; dm.ftij = ftij.p; dm.fkind = fkind.p;
+    dm.cf = cf.p; dm.area = area.p; dm.lsqM = lsqM.p; dm.lsq_perm = lsq_perm.p;
+}
+
+// solver::set_bcs, solver.h:200-247
+void Solver::set_bcs(int n_patch, const uint8_t* kinds, const afx_bvars* vars)
+{
+    use();
+    std::vector<uint8_t> h_kind(E, 0);
+    std::vector<d4> h_state(G ? G : 1);
+    for (uint32_t b = 0; b < G; ++b) {
+        const int p = h_bnd_patch[b];
+        if (p < 0 || p >= n_patch) throw InvalidArg("boundary patch " + std::to_string(p) + " has no boundary condition (bcs.at)");
+        const uint8_t k = kinds[p] <= 3 ? kinds[p] : 0;
+        h_bnd_kind[b] = k;
+        h_bnd_vars[b] = (k == AFX_BC_FARFIELD) ? vars[p] : afx_bvars{0.2, 0., 1., 1.};  // solver.h:219-229
+        h_kind[h_bnd_face[b]] = k;
+        double s4[4];
+        conservative(h_bnd_vars[b], s4);
+        h_state[b] = d4{s4[0], s4[1], s4[2], s4[3]};
+    }
+    fkind.upload(h_kind, st);
+    bstate.upload(h_state, st);
+    CK(cudaStreamSynchronize(st));
+    dm.fkind = fkind.p;
+    bcs_set = true;
+    jac_valid = false;
+}
+
+void Solver::set_options(int so, int grad, double k)
+{
+    if (grad != AFX_GRAD_GREEN_GAUSS && grad != AFX_GRAD_LEAST_SQUARES) throw InvalidArg("unknown gradient scheme");
+    if (so != second_order || grad != gradient_scheme) invalidate_graph();
+    second_order = so ? 1 : 0; gradient_scheme = grad; limiter_k = k;
+    invalidate_graph();
+}
+
+void Solver::push_params(double relax)
+{
+    if (relax == relax_dev && cfl == cfl_dev) return;
+    h_pinned[32] = cfl; h_pinned[33] = relax;
+    CK(cudaMemcpyAsync(prm.p, h_pinned + 32, 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));  // the pinned slot is reused
+    relax_dev = relax; cfl_dev = cfl;
+}
+
+void Solver::launch_dt_grad(bool want_grad, bool walls)
+{
+    if (gradient_scheme == AFX_GRAD_GREEN_GAUSS)
+        k_dt_grad<0><<<blocks(N), 256, 0, st>>>(dm, q.p, dt.p, gx.p, gy.p, prm.p, gas.gamma, want_grad, walls);
+    else
+        k_dt_grad<1><<<blocks(N), 256, 0, st>>>(dm, q.p, dt.p, gx.p, gy.p, prm.p, gas.gamma, want_grad, walls);
+    ++launches;
+}
+
+void Solver::launch_limiter(const d4* qk)
+{
+    k_limiter<<<blocks(N), 256, 0, st>>>(dm, qk, gx.p, gy.p, lim.p, limiter_k);
+    ++launches;
+}
+
+void Solver::launch_flux(const d4* qk, bool uniform, d4 qfar)
+{
+    const unsigned nb = blocks(E);
+#define AFX_FLUX(S, V, U) k_flux<S, V, U><<<nb, 256, 0, st>>>(dm, qk, q.p, gx.p, gy.p, lim.p, flux.p, gas, qfar)
+    if (uniform) {
+        if (viscous_type) AFX_FLUX(0, 1, 1); else AFX_FLUX(0, 0, 1);
+    } else if (second_order) {
+        if (viscous_type) AFX_FLUX(1, 1, 0); else AFX_FLUX(1, 0, 0);
+    } else {
+        if (viscous_type) AFX_FLUX(0, 1, 0); else AFX_FLUX(0, 0, 0);
+    }
+#undef AFX_FLUX
+    ++launches;
+}
+
+template <int MODE, int LAST>
+void Solver::launch_gather(const d4* qk_in, d4* qk_out, d4* vec_out, double alpha, bool walls)
+{
+    k_gather_update<MODE, LAST><<<blocks(N), 256, 0, st>>>(dm, flux.p, q.p, qk_in, qk_out, dt.p, vec_out, alpha, prm.p,
+                                                           walls ? 1 : 0, partial.p, counters.p, norms.p, counters.p + 1);
+    ++launches;
+}
+
+// explicitSolver::solve, solver.h:802-828.  Stage 0 reads q in place of qk (they
+// are equal), stage 2 writes q in place; qkA/qkB carry the intermediate stages.
+void Solver::explicit_iteration()
+{
+    const bool grads = visc_not_inviscid || second_order;  // solver.h:810
+    launch_dt_grad(grads, grads);
+    const d4* in[3] = {q.p, qkA.p, qkB.p};
+    d4* out[3] = {qkA.p, qkB.p, q.p};
+    const double alpha[3] = {0.25, 0.5, 1.};  // solver.h:723
+    for (int s = 0; s < 3; ++s) {
+        if (second_order) launch_limiter(in[s]);
+        launch_flux(in[s], false, d4{0, 0, 0, 0});
+        if (s < 2) launch_gather<0, 0>(in[s], out[s], qW.p, alpha[s], grads);
+        else launch_gather<0, 1>(in[s], out[s], qW.p, alpha[s], grads);
+    }
+}
+
+double Solver::fetch_last_norm()
+{
+    unsigned int* h_idx = reinterpret_cast<unsigned int*>(h_pinned + 8);
+    CK(cudaMemcpyAsync(h_idx, counters.p + 1, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const unsigned int k = *h_idx;
+    if (k == 0) throw NumericError("no residual norm has been computed");
+    CK(cudaMemcpyAsync(h_pinned, norms.p + ((k - 1) % NORM_RING), sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    norm_idx_host = k;
+    return h_pinned[0];
+}
+
+void Solver::run_explicit(double relax, int n_iter, double* norms_out)
+{
+    use();
+    if (!bcs_set) throw InvalidArg("set_bcs has not been called");
+    if (n_iter <= 0) return;
+    push_params(relax);
+    CK(cudaEventRecord(ev0, st));
+    int done = 0;
+    while (done < n_iter) {
+        const int chunk = std::min<int>(n_iter - done, (int)NORM_RING / 2);
+        // ring index before this chunk
+        unsigned int* h_idx = reinterpret_cast<unsigned int*>(h_pinned + 8);
+        CK(cudaMemcpyAsync(h_idx, counters.p + 1, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        const unsigned int k0 = *h_idx;
+        if (use_graph) {
+            if (!graph_exec) {
+                cudaGraph_t g = nullptr;
+                const int64_t l0 = launches;
+                CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+                explicit_iteration();
+                CK(cudaStreamEndCapture(st, &g));
+                launches = l0;
+                CK(cudaGraphInstantiate(&graph_exec, g, 0));
+                CK(cudaGraphDestroy(g));
+            }
+            const int per_iter = 1 + 3 * (second_order ? 3 : 2);
+            for (int it = 0; it < chunk; ++it) CK(cudaGraphLaunch(graph_exec, st));
+            launches += (int64_t)per_iter * chunk;
+        } else {
+            for (int it = 0; it < chunk; ++it) explicit_iteration();
+        }
+        CK(cudaGetLastError());
+        if (norms_out) {
+            // copy this chunk of the ring (it may wrap)
+            std::vector<double> tmp(chunk);
+            for (int it = 0; it < chunk;) {
+                const unsigned int pos = (k0 + it) % NORM_RING;
+                const int n = std::min<int>(chunk - it, (int)(NORM_RING - pos));
+                CK(cudaMemcpyAsync(tmp.data() + it, norms.p + pos, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+                it += n;
+            }
+            CK(cudaStreamSynchronize(st));
+            std::copy(tmp.begin(), tmp.end(), norms_out + done);
+        }
+        done += chunk;
+    }
+    CK(cudaEventRecord(ev1, st));
+    CK(cudaEventSynchronize(ev1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ev0, ev1));
+    last_ms = ms;
+    jac_valid = false;
+}
+
+// implicitSolver::fillRhoRHS, solver.h:1079-1152
+double Solver::residual_rhs()
+{
+    use();
+    if (!bcs_set) throw InvalidArg("set_bcs has not been called");
+    push_params(relax_dev < 0 ? 1.0 : relax_dev);
+    const bool grads = second_order || visc_not_inviscid;  // solver.h:1083
+    launch_dt_grad(grads, grads);
+    if (second_order) launch_limiter(q.p);
+    launch_flux(q.p, false, d4{0, 0, 0, 0});
+    launch_gather<1, 1>(q.p, nullptr, rhs.p, 0., false);
+    CK(cudaGetLastError());
+    const double v = fetch_last_norm();
+    return v;
+}
+
+// solver::get_uniform_residual, solver.h:636-690 (accumulating from zero)
+double Solver::uniform_residual()
+{
+    use();
+    if (!bcs_set) throw InvalidArg("set_bcs has not been called");
+    push_params(relax_dev < 0 ? 1.0 : relax_dev);
+    afx_bvars far;
+    boundary_variables(&far);
+    double s4[4];
+    conservative(far, s4);
+    launch_flux(q.p, true, d4{s4[0], s4[1], s4[2], s4[3]});
+    launch_gather<2, 1>(q.p, nullptr, qW.p, 0., false);
+    CK(cudaGetLastError());
+    return fetch_last_norm();
+}
+
+// implicitSolver::fillRhoLHS, solver.h:979-1071
+void Solver::fill_jacobian()
+{
+    use();
+    if (!bcs_set) throw InvalidArg("set_bcs has not been called");
+    push_params(relax_dev < 0 ? 1.0 : relax_dev);
+    if (!J.p) { J.alloc((size_t)E * 16); D.alloc((size_t)NT * 16); }
+    launch_dt_grad(visc_not_inviscid, visc_not_inviscid);  // solver.h:981-986
+    if (viscous_type) k_jacobian<1><<<blocks(E, 128), 128, 0, st>>>(dm, q.p, gx.p, gy.p, J.p, gas);
+    else k_jacobian<0><<<blocks(E, 128), 128, 0, st>>>(dm, q.p, gx.p, gy.p, J.p, gas);
+    k_jac_diag<<<blocks(NT), 256, 0, st>>>(dm, reinterpret_cast<const double*>(J.p), dt.p, D.p);
+    launches += 2;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    jac_valid = true;
+}
+
+void Solver::to_ref_order4(const d4* dev_new, double* host_out)
+{
+    // stage[old] = dev_new[old2new[old]]
+    k_permute4<<<blocks(NT), 256, 0, st>>>(dev_new, stage.p, perm_c_old2new.p, NT, 0);
+    ++launches;
+    CK(cudaMemcpyAsync(host_out, stage.p, (size_t)NT * sizeof(d4), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+}
+
+void Solver::from_ref_order4(const double* host_in, d4* dev_new)
+{
+    CK(cudaMemcpyAsync(stage.p, host_in, (size_t)NT * sizeof(d4), cudaMemcpyHostToDevice, st));
+    // dev_new[new] = stage[new2old[new]]
+    k_permute4<<<blocks(NT), 256, 0, st>>>(stage.p, dev_new, perm_c_new2old.p, NT, 0);
+    ++launches;
+    CK(cudaStreamSynchronize(st));
+}
+
+// the stage buffers carry the same ghost rows as q (far-field ghosts never change inside an iteration)
+void Solver::sync_ghost_rows()
+{
+    if (!G) return;
+    CK(cudaMemcpyAsync(qkA.p + N, q.p + N, (size_t)G * sizeof(d4), cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(qkB.p + N, q.p + N, (size_t)G * sizeof(d4), cudaMemcpyDeviceToDevice, st));
+}
+
+}  // namespace afx
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+struct afx_rans {
+    afx::Solver s;
+};
+
+namespace {
+
+template <class F>
+int guard(F&& f)
+{
+    try {
+        f();
+        return AFX_OK;
+    } catch (const afx::CudaError& e) { afx::set_error(e.what()); return AFX_ERR_CUDA; }
+    catch (const afx::InvalidArg& e) { afx::set_error(e.what()); return AFX_ERR_INVALID; }
+    catch (const afx::NumericError& e) { afx::set_error(e.what()); return AFX_ERR_NUMERIC; }
+    catch (const std::exception& e) { afx::set_error(e.what()); return AFX_ERR_INVALID; }
+    catch (...) { afx::set_error("unknown error"); return AFX_ERR_INVALID; }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* afx_last_error(void) { return afx::g_last_error.c_str(); }
+const char* afx_version(void) { return "aeroflex_rans_b200 0.1 (sm_100a)"; }
+
+int afx_device_count(void)
+{
+    int n = 0;
+    const cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { afx::set_error(cudaGetErrorString(e)); return AFX_ERR_CUDA; }
+    return n;
+}
+
+int afx_rans_create(afx_rans** out, const afx_mesh_desc* mesh, const afx_gas* gas, int viscosity_model, int device)
+{
+    if (!out || !mesh || !gas) { afx::set_error("null argument"); return AFX_ERR_INVALID; }
+    *out = nullptr;
+    afx_rans* h = nullptr;
+    const int rc = guard([&] {
+        if (viscosity_model < 0 || viscosity_model > 2) throw afx::InvalidArg("viscosity model must be 0, 1 or 2");
+        h = new afx_rans;
+        h->s.create(*mesh, *gas, viscosity_model, device);
+    });
+    if (rc) { delete h; return rc; }
+    *out = h;
+    return AFX_OK;
+}
+
+void afx_rans_destroy(afx_rans* s) { delete s; }
+
+int afx_rans_set_bcs(afx_rans* s, int n_patch, const uint8_t* patch_kind, const afx_bvars* patch_vars)
+{
+    return guard([&] { s->s.set_bcs(n_patch, patch_kind, patch_vars); });
+}
+
+int afx_rans_set_options(afx_rans* s, int second_order, int gradient_scheme, double limiter_k)
+{
+    return guard([&] { s->s.set_options(second_order, gradient_scheme, limiter_k); });
+}
+
+int afx_rans_set_cfl(afx_rans* s, double cfl)
+{
+    s->s.cfl = cfl;
+    return AFX_OK;
+}
+
+int afx_rans_init(afx_rans* s)
+{
+    return guard([&] {
+        auto& S = s->s;
+        S.use();
+        afx_bvars v;
+        S.boundary_variables(&v);
+        double q4[4];
+        S.conservative(v, q4);
+        afx::k_fill_cells<<<afx::Solver::blocks(S.N), 256, 0, S.st>>>(S.q.p, S.N, afx::d4{q4[0], q4[1], q4[2], q4[3]});
+        ++S.launches;
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(S.st));
+        S.jac_valid = false;
+    });
+}
+
+int afx_rans_refill_bcs(afx_rans* s)
+{
+    return guard([&] {
+        auto& S = s->s;
+        S.use();
+        if (!S.bcs_set) throw afx::InvalidArg("set_bcs has not been called");
+        if (S.G) {
+            afx::k_ghost_fill<<<afx::Solver::blocks(S.G), 256, 0, S.st>>>(S.q.p, S.bghost.p, S.bowner.p, S.bstate.p, S.G, 0);
+            ++S.launches;
+        }
+        S.sync_ghost_rows();
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(S.st));
+        S.jac_valid = false;
+    });
+}
+
+int afx_rans_bcs_from_internal(afx_rans* s)
+{
+    return guard([&] {
+        auto& S = s->s;
+        S.use();
+        if (S.G) {
+            afx::k_ghost_fill<<<afx::Solver::blocks(S.G), 256, 0, S.st>>>(S.q.p, S.bghost.p, S.bowner.p, S.bstate.p, S.G, 1);
+            ++S.launches;
+        }
+        S.sync_ghost_rows();
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(S.st));
+        S.jac_valid = false;
+    });
+}
+
+int afx_rans_set_q(afx_rans* s, const double* q)
+{
+    return guard([&] {
+        auto& S = s->s;
+        S.use();
+        S.from_ref_order4(q, S.q.p);
+        S.sync_ghost_rows();
+        CK(cudaStreamSynchronize(S.st));
+        S.jac_valid = false;
+    });
+}
+
+int afx_rans_get_q(afx_rans* s, double* q)
+{
+    return guard([&] { s->s.use(); s->s.to_ref_order4(s->s.q.p, q); });
+}
+
+int afx_rans_get_field(afx_rans* s, int field, double* out)
+{
+    return guard([&] {
+        auto& S = s->s;
+        S.use();
+        switch (field) {
+            case AFX_F_Q: S.to_ref_order4(S.q.p, out); break;
+            case AFX_F_QW: S.to_ref_order4(S.qW.p, out); break;
+            case AFX_F_GX: S.to_ref_order4(S.gx.p, out); break;
+            case AFX_F_GY: S.to_ref_order4(S.gy.p, out); break;
+            case AFX_F_LIMITERS: S.to_ref_order4(S.lim.p, out); break;
+            case AFX_F_RHS: S.to_ref_order4(S.rhs.p, out); break;
+            case AFX_F_DT: {
+                afx::k_permute1<<<afx::Solver::blocks(S.NT), 256, 0, S.st>>>(S.dt.p, S.dt_ref.p, S.perm_c_old2new.p, S.NT, S.N);
+                ++S.launches;
+                CK(cudaMemcpyAsync(out, S.dt_ref.p, (size_t)S.NT * sizeof(double), cudaMemcpyDeviceToHost, S.st));
+                CK(cudaStreamSynchronize(S.st));
+                break;
+            }
+            default: throw afx::InvalidArg("unknown field id");
+        }
+    });
+}
+
+int afx_rans_boundary_variables(afx_rans* s, afx_bvars* out) { return s->s.boundary_variables(out) ? 1 : 0; }
+
+int afx_rans_uniform_residual(afx_rans* s, double* norm)
+{
+    return guard([&] { const double v = s->s.uniform_residual(); if (norm) *norm = v; });
+}
+
+int afx_rans_step_explicit(afx_rans* s, double relaxation, double* norm)
+{
+    return guard([&] {
+        double v = 0;
+        s->s.run_explicit(relaxation, 1, &v);
+        if (norm) *norm = v;
+        s->s.check_norm(v);
+    });
+}
+
+int afx_rans_run_explicit(afx_rans* s, double relaxation, int n_iter, double* norms)
+{
+    return guard([&] {
+        if (n_iter <= 0) return;
+        std::vector<double> tmp;
+        double* dst = norms;
+        if (!dst) { tmp.resize((size_t)n_iter); dst = tmp.data(); }
+        s->s.run_explicit(relaxation, n_iter, dst);
+        s->s.check_norm(dst[n_iter - 1]);
+    });
+}
+
+int afx_rans_phase_dt_gradients(afx_rans* s)
+{
+    return guard([&] {
+        auto& S = s->s;
+        S.use();
+        if (!S.bcs_set) throw afx::InvalidArg("set_bcs has not been called");
+        S.push_params(S.relax_dev < 0 ? 1.0 : S.relax_dev);
+        S.launch_dt_grad(true, true);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(S.st));
+    });
+}
+
+int afx_rans_phase_limiters(afx_rans* s)
+{
+    return guard([&] {
+        auto& S = s->s;
+        S.use();
+        S.launch_limiter(S.q.p);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(S.st));
+    });
+}
+
+int afx_rans_phase_residual(afx_rans* s, double* norm)
+{
+    return guard([&] {
+        auto& S = s->s;
+        S.use();
+        if (!S.bcs_set) throw afx::InvalidArg("set_bcs has not been called");
+        S.push_params(0.0);  // relax = 0: the stage "update" below leaves the state untouched
+        S.launch_flux(S.q.p, false, afx::d4{0, 0, 0, 0});
+        S.launch_gather<0, 1>(S.q.p, S.stage.p, S.qW.p, 0., false);
+        CK(cudaGetLastError());
+        const double v = S.fetch_last_norm();
+        if (norm) *norm = v;
+    });
+}
+
+int afx_rans_residual(afx_rans* s, double* norm)
+{
+    return guard([&] { const double v = s->s.residual_rhs(); if (norm) *norm = v; });
+}
+
+int afx_rans_fill_jacobian(afx_rans* s)
+{
+    return guard([&] { s->s.fill_jacobian(); });
+}
+
+int afx_rans_get_jacobian_blocks(afx_rans* s, double* diag, double* off01, double* off10)
+{
+    return guard([&] {
+        auto& S = s->s;
+        S.use();
+        if (!S.jac_valid) throw afx::InvalidArg("afx_rans_fill_jacobian has not been called for the current state");
+        std::vector<double> hJ((size_t)S.E * 64), hD((size_t)S.NT * 16);
+        CK(cudaMemcpy(hJ.data(), S.J.p, hJ.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(hD.data(), S.D.p, hD.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        if (diag)
+            for (uint32_t n = 0; n < S.NT; ++n) std::memcpy(diag + 16 * (size_t)S.c_new2old[n], hD.data() + 16 * (size_t)n, 16 * sizeof(double));
+        for (uint32_t n = 0; n < S.E; ++n) {
+            const size_t e = S.f_new2old[n];
+            if (off01) std::memcpy(off01 + 16 * e, hJ.data() + 64 * (size_t)n + 16, 16 * sizeof(double));
+            if (off10) {
+                const bool two_sided = S.h_fcells[2 * (size_t)n + 1] < S.N;
+                // one-sided faces never touch row c1 (solver.h:1051-1054)
+                for (int k = 0; k < 16; ++k) off10[16 * e + k] = two_sided ? hJ[64 * (size_t)n + 32 + k] : 0.0;
+            }
+        }
+    });
+}
+
+int afx_rans_step_implicit(afx_rans*, double, double, int, double*)
+{
+    afx::set_error("afx_rans_step_implicit: the device Krylov solver is not built yet");
+    return AFX_ERR_INVALID;
+}
+
+int afx_rans_wall_forces(afx_rans* s, int patch, double out[3])
+{
+    return guard([&] {
+        auto& S = s->s;
+        S.use();
+        afx_bvars far;
+        S.boundary_variables(&far);
+        // chord extent and moment centre of the patch, post.h:314-338
+        double xmin = 0., xmax = 0., ym = 0.;
+        uint32_t n_added = 0;
+        for (uint32_t b = 0; b < S.G; ++b) {
+            if (S.h_bnd_patch[b] != patch) continue;
+            if (!n_added) { xmin = xmax = S.h_bcx[b]; ym = S.h_bcy[b]; }
+            else { xmin = std::min(xmin, S.h_bcx[b]); xmax = std::max(xmax, S.h_bcx[b]); ym += S.h_bcy[b]; }
+            ++n_added;
+        }
+        if (!n_added) throw afx::InvalidArg("patch has no boundary edges");
+        ym /= (double)n_added;
+        const double xm = (xmax - xmin) * 0.25 + xmin;
+        afx::k_wall_forces<<<1, 256, 0, S.st>>>(S.bface.p, S.bpatch.p, S.G, patch, S.dm, S.q.p, S.bcx.p, S.bcy.p, S.gas.gamma,
+                                                far.p, far.mach, xmin, xmax, xm, ym, S.scratch.p, nullptr);
+        ++S.launches;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(S.h_pinned + 16, S.scratch.p, 3 * sizeof(double), cudaMemcpyDeviceToHost, S.st));
+        CK(cudaStreamSynchronize(S.st));
+        const double fx = S.h_pinned[16], fy = S.h_pinned[17], cm = S.h_pinned[18], aoa = far.angle;
+        out[1] = fx * std::cos(aoa) + fy * std::sin(aoa);   // cd, post.h:383
+        out[0] = -fx * std::sin(aoa) + fy * std::cos(aoa);  // cl, post.h:384
+        out[2] = cm;
+    });
+}
+
+int afx_rans_wall_cp(afx_rans* s, int patch, double* cp)
+{
+    int count = 0;
+    const int rc = guard([&] {
+        auto& S = s->s;
+        S.use();
+        for (uint32_t b = 0; b < S.G; ++b) count += (S.h_bnd_patch[b] == patch);
+        if (!cp || !count) return;
+        afx_bvars far;
+        S.boundary_variables(&far);
+        afx::DBuf<double> d_cp;
+        d_cp.alloc(S.G);
+        afx::k_wall_forces<<<1, 256, 0, S.st>>>(S.bface.p, S.bpatch.p, S.G, patch, S.dm, S.q.p, S.bcx.p, S.bcy.p, S.gas.gamma,
+                                                far.p, far.mach, 0., 1., 0., 0., S.scratch.p, d_cp.p);
+        ++S.launches;
+        std::vector<double> h(S.G);
+        CK(cudaMemcpyAsync(h.data(), d_cp.p, S.G * sizeof(double), cudaMemcpyDeviceToHost, S.st));
+        CK(cudaStreamSynchronize(S.st));
+        int k = 0;
+        for (uint32_t b = 0; b < S.G; ++b) if (S.h_bnd_patch[b] == patch) cp[k++] = h[b];
+    });
+    return rc ? rc : count;
+}
+
+int afx_rans_last_device_ms(afx_rans* s, double* ms) { *ms = s->s.last_ms; return AFX_OK; }
+int64_t afx_rans_launch_count(afx_rans* s) { return s->s.launches; }
+
+int afx_rans_profile_explicit(afx_rans* s, double relaxation, int n_iter, double out_ms[4])
+{
+    return guard([&] {
+        auto& S = s->s;
+        S.use();
+        if (!S.bcs_set) throw afx::InvalidArg("set_bcs has not been called");
+        S.push_params(relaxation);
+        for (int k = 0; k < 4; ++k) out_ms[k] = 0;
+        const bool grads = S.visc_not_inviscid || S.second_order;
+        const afx::d4* in[3] = {S.q.p, S.qkA.p, S.qkB.p};
+        afx::d4* outp[3] = {S.qkA.p, S.qkB.p, S.q.p};
+        const double alpha[3] = {0.25, 0.5, 1.};
+        for (int it = 0; it < n_iter; ++it) {
+            int e = 0;
+            CK(cudaEventRecord(S.evp[e++], S.st));
+            S.launch_dt_grad(grads, grads);
+            CK(cudaEventRecord(S.evp[e++], S.st));
+            for (int st = 0; st < 3; ++st) {
+                if (S.second_order) S.launch_limiter(in[st]);
+                CK(cudaEventRecord(S.evp[e++], S.st));
+                S.launch_flux(in[st], false, afx::d4{0, 0, 0, 0});
+                CK(cudaEventRecord(S.evp[e++], S.st));
+                if (st < 2) S.launch_gather<0, 0>(in[st], outp[st], S.qW.p, alpha[st], grads);
+                else S.launch_gather<0, 1>(in[st], outp[st], S.qW.p, alpha[st], grads);
+                CK(cudaEventRecord(S.evp[e++], S.st));
+            }
+            CK(cudaStreamSynchronize(S.st));
+            float ms;
+            CK(cudaEventElapsedTime(&ms, S.evp[0], S.evp[1])); out_ms[0] += ms;
+            for (int st = 0; st < 3; ++st) {
+                CK(cudaEventElapsedTime(&ms, S.evp[1 + 3 * st], S.evp[2 + 3 * st])); out_ms[1] += ms;
+                CK(cudaEventElapsedTime(&ms, S.evp[2 + 3 * st], S.evp[3 + 3 * st])); out_ms[2] += ms;
+                CK(cudaEventElapsedTime(&ms, S.evp[3 + 3 * st], S.evp[4 + 3 * st])); out_ms[3] += ms;
+            }
+        }
+        for (int k = 0; k < 4; ++k) out_ms[k] /= n_iter;
+        S.jac_valid = false;
+    });
+}
+
+}  // extern "C"

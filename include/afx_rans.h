@@ -1,0 +1,187 @@
+/*
+ * afx_rans.h -- C ABI of libaeroflex_rans_b200.so: the B200 (sm_100a) drop-in
+ * for AeroFLEX's src/rans residual / pseudo-time hot path.
+ *
+ * The reference has no FFI for this path; its seam is the C++ class
+ * rans::solver (fill / compute / solve, solver.h:171-173) used as the template
+ * argument of rans::multigrid<solverType> (multigrid.h:28-56).  The adapter
+ * class rans::gpuSolver (aeroflex_b200/host/rans_b200/gpu_solver.h) mirrors
+ * that class and forwards every call to the entry points below; each entry
+ * point cites the reference member it replaces (paths relative to
+ * src/rans/include/rans/ of the reference).
+ *
+ * Conventions
+ *  - plain C types only; no exceptions cross; every int-returning function
+ *    returns 0 on success or a negative afx_status, with afx_last_error()
+ *    giving a message for the calling thread;
+ *  - all cell / edge / boundary arrays are in the REFERENCE's order and
+ *    layout (mesh.h:209-246; state = 4 doubles per cell, real cells first,
+ *    then one ghost cell per boundary edge, solver.h:182-196).  Renumbering
+ *    for coalescing is internal and invisible;
+ *  - double precision throughout; indices are uint32_t (core.h:22);
+ *  - one handle drives one GPU from one host thread at a time; distinct
+ *    handles are independent.
+ */
+#ifndef AFX_RANS_H
+#define AFX_RANS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AFX_EDGE_NULL 0xFFFFFFFFu /* mesh.h:35 MESH_EDGE_NULL */
+
+typedef enum {
+    AFX_OK = 0,
+    AFX_ERR_INVALID = -1,   /* bad argument / unknown name (std::invalid_argument, std::out_of_range) */
+    AFX_ERR_CUDA = -2,      /* CUDA runtime failure or no usable device */
+    AFX_ERR_NUMERIC = -3,   /* NaN/Inf residual, linear solver failure (the reference returns -1) */
+    AFX_ERR_IO = -4,        /* mesh / config file problems (std::runtime_error) */
+    AFX_ERR_COMM = -5       /* NCCL failure */
+} afx_status;
+
+/* edge flux kinds chosen by solver::set_bcs (solver.h:216-246) */
+enum { AFX_BC_INTERNAL = 0, AFX_BC_FARFIELD = 1, AFX_BC_SLIPWALL = 2, AFX_BC_WALL = 3 };
+/* Settings::viscosity_options (core.h:176) */
+enum { AFX_VISC_INVISCID = 0, AFX_VISC_LAMINAR = 1, AFX_VISC_SA = 2 };
+/* Settings::gradient_options (core.h:175), by meaning not by index */
+enum { AFX_GRAD_GREEN_GAUSS = 0, AFX_GRAD_LEAST_SQUARES = 1 };
+/* fields readable with afx_rans_get_field (solver.h:54-69) */
+enum { AFX_F_Q = 0, AFX_F_QW = 1, AFX_F_GX = 2, AFX_F_GY = 3, AFX_F_LIMITERS = 4, AFX_F_DT = 5, AFX_F_RHS = 6 };
+
+/* rans::gas, core.h:27-46 */
+typedef struct afx_gas {
+    double gamma, R, mu_L, Pr_L, cp;
+} afx_gas;
+
+/* rans::boundary_variables, core.h:61-84 */
+typedef struct afx_bvars {
+    double mach, angle, T, p;
+} afx_bvars;
+
+/* Borrowed view of a rans::mesh (mesh.h:209-246). */
+typedef struct afx_mesh_desc {
+    uint32_t n_cells;               /* nRealCells */
+    uint32_t n_ghost;               /* boundaryEdges.size() */
+    uint32_t n_edges;               /* edgesCells.cols() */
+    const uint32_t* edges_cells;    /* [E][2]  edgesCells */
+    const double* edges_nx;         /* [E] edgesNormalsX (out of cell 0) */
+    const double* edges_ny;
+    const double* edges_len;
+    const double* edges_cx;         /* [E] edgesCentersX */
+    const double* edges_cy;
+    const double* cells_cx;         /* [N+G] cellsCentersX */
+    const double* cells_cy;
+    const double* cells_area;       /* [N+G] */
+    const uint32_t* cells_edges;    /* [N][4] cellsEdges, AFX_EDGE_NULL padded */
+    const uint8_t* cells_is_tri;    /* [N] */
+    const uint32_t* boundary_edges; /* [G] boundaryEdges */
+    const int32_t* boundary_patch;  /* [G] patch id of boundaryEdgesPhysicals[b] */
+} afx_mesh_desc;
+
+const char* afx_last_error(void);
+const char* afx_version(void);
+/* number of CUDA devices visible, or a negative afx_status */
+int afx_device_count(void);
+
+/* ------------------------------------------------------------------ */
+/* Mesh ingest (host only; replaces rans::mesh, mesh.h:250,834-884)     */
+/* ------------------------------------------------------------------ */
+typedef struct afx_mesh afx_mesh;
+
+/* rans::mesh(filename): Gmsh MSH 4.1 ASCII, triangles + quads (mesh.h:457-738) */
+int afx_mesh_read_msh(afx_mesh** out, const char* path);
+/* the same construction from in-memory elements: cells [nc][4] (triangles
+ * padded with node 0, mesh.h:715-717), boundary segments with a patch id each */
+int afx_mesh_from_elements(afx_mesh** out, uint32_t n_nodes, const double* x, const double* y,
+                           uint32_t n_cells, const uint32_t* cells, const uint8_t* is_tri,
+                           uint32_t n_bnd, const uint32_t* b0, const uint32_t* b1, const int32_t* bpatch,
+                           int n_patch, const char* const* patch_names);
+/* Synthetic NACA0012 O-mesh: ni cells around x nj radial
+ * layers, the inner n_quad_layers layers quads, the rest split into two
+ * triangles each; patches "wall" and "farfield"; cells in (j,i) order. */
+int afx_mesh_synth_omesh(afx_mesh** out, uint32_t ni, uint32_t nj, uint32_t n_quad_layers, double far_radius);
+void afx_mesh_free(afx_mesh* m);
+int afx_mesh_get_desc(const afx_mesh* m, afx_mesh_desc* out);
+uint32_t afx_mesh_n_nodes(const afx_mesh* m);
+int afx_mesh_n_patches(const afx_mesh* m);
+const char* afx_mesh_patch_name(const afx_mesh* m, int patch);
+int afx_mesh_patch_id(const afx_mesh* m, const char* name); /* -1 if absent */
+/* raw inputs back out (nodes, connectivity, boundary segments); any pointer may be NULL */
+int afx_mesh_get_elements(const afx_mesh* m, double* x, double* y, uint32_t* cells, uint32_t* b0, uint32_t* b1);
+/* write MSH 4.1 ASCII that rans::mesh can read back (so the CPU reference can run on synthetic meshes) */
+int afx_mesh_write_msh(const afx_mesh* m, const char* path);
+
+/* ------------------------------------------------------------------ */
+/* Solver (replaces rans::solver / explicitSolver / implicitSolver)     */
+/* ------------------------------------------------------------------ */
+typedef struct afx_rans afx_rans;
+
+/* solver(mesh, gas, viscosity_model) + set_mesh_and_gas (solver.h:108-110,177-197).
+ * device = CUDA ordinal.  All state vectors start at zero (the reference
+ * leaves them uninitialised, see DESIGN.md "F9"). */
+int afx_rans_create(afx_rans** out, const afx_mesh_desc* mesh, const afx_gas* gas, int viscosity_model, int device);
+void afx_rans_destroy(afx_rans* s);
+
+/* solver::set_bcs (solver.h:200-247): kind and far-field variables per patch id */
+int afx_rans_set_bcs(afx_rans* s, int n_patch, const uint8_t* patch_kind, const afx_bvars* patch_vars);
+/* set_second_order / set_gradient_scheme / set_limiter_k (solver.h:135,149-152,162) */
+int afx_rans_set_options(afx_rans* s, int second_order, int gradient_scheme, double limiter_k);
+/* solver::set_cfl (solver.h:250-252) */
+int afx_rans_set_cfl(afx_rans* s, double cfl);
+/* solver::init / refill_bcs / bcs_from_internal (solver.h:615-631, 259-287) */
+int afx_rans_init(afx_rans* s);
+int afx_rans_refill_bcs(afx_rans* s);
+int afx_rans_bcs_from_internal(afx_rans* s);
+/* solver::get_q as value transfer: q has 4*(N+G) doubles in reference order */
+int afx_rans_set_q(afx_rans* s, const double* q);
+int afx_rans_get_q(afx_rans* s, double* q);
+/* one of AFX_F_*: 4*(N+G) doubles (N+G for AFX_F_DT) in reference order */
+int afx_rans_get_field(afx_rans* s, int field, double* out);
+/* solver::get_boundary_variables (solver.h:597-611); returns 1 if a far-field patch was found, else 0 (defaults) */
+int afx_rans_boundary_variables(afx_rans* s, afx_bvars* out);
+
+/* solver::get_uniform_residual (solver.h:636-690), accumulating from zero */
+int afx_rans_uniform_residual(afx_rans* s, double* norm);
+/* explicitSolver::solve (solver.h:802-828): local dt, 3 stages of
+ * [wall ghosts, gradients, limiter, residual, update]; *norm = ||qW||_2 */
+int afx_rans_step_explicit(afx_rans* s, double relaxation, double* norm);
+/* n_iter explicit iterations back to back without host round trips;
+ * norms[n_iter] (may be NULL) receives every iteration's norm at the end */
+int afx_rans_run_explicit(afx_rans* s, double relaxation, int n_iter, double* norms);
+/* the single phases, for parity tests: on_qk=0 works on q.  They mirror
+ * calc_dt / set_walls_from_internal+calc_gradients / calc_limiters /
+ * explicitSolver::calc_residual (solver.h:308,289,425,517,745) */
+int afx_rans_phase_dt_gradients(afx_rans* s);
+int afx_rans_phase_limiters(afx_rans* s);
+int afx_rans_phase_residual(afx_rans* s, double* norm);
+/* implicitSolver::fillRhoRHS (solver.h:1079-1152): RHS into AFX_F_RHS, *norm = ||RhoVector||_2 */
+int afx_rans_residual(afx_rans* s, double* norm);
+/* implicitSolver::fillRhoLHS (solver.h:979-1071): block Jacobian on the device */
+int afx_rans_fill_jacobian(afx_rans* s);
+/* the 4x4 blocks of that matrix: diag[(N+G)][16], off01[E][16] (row c0, col c1), off10[E][16]; row-major blocks */
+int afx_rans_get_jacobian_blocks(afx_rans* s, double* diag, double* off01, double* off10);
+/* implicitSolver::compute + solve (solver.h:1160-1213): GMRES(30) on the device with the frozen Jacobian
+ * of the last afx_rans_fill_jacobian; *norm = final ||RhoVector||_2, AFX_ERR_NUMERIC where the reference returns -1 */
+int afx_rans_step_implicit(afx_rans* s, double relaxation, double tol, int rhs_iterations, double* norm);
+/* get_wall_profile (post.h:301-387): out = {cl, cd, cm} of one patch */
+int afx_rans_wall_forces(afx_rans* s, int patch, double out_cl_cd_cm[3]);
+/* CpProfile::calc_cp (post.h:248-298): cp of the owner cell of every boundary edge of the patch, boundary order;
+ * returns the count (cp may be NULL to query it) */
+int afx_rans_wall_cp(afx_rans* s, int patch, double* cp);
+
+/* device time of the kernels of the last step/run call, milliseconds (CUDA events on the solver's stream) */
+int afx_rans_last_device_ms(afx_rans* s, double* ms);
+/* kernels launched by this handle since creation (bench.py's gpu_launches) */
+int64_t afx_rans_launch_count(afx_rans* s);
+/* per-phase device milliseconds of one explicit iteration, timed with CUDA events between the phases:
+ * out[0]=dt+gradients, out[1]=limiter (3 stages), out[2]=face flux (3 stages), out[3]=gather+update (3 stages) */
+int afx_rans_profile_explicit(afx_rans* s, double relaxation, int n_iter, double out_ms[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AFX_RANS_H */

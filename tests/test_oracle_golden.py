@@ -1,0 +1,92 @@
+"""The restated oracle against the frozen outputs of the unmodified reference
+(tests/golden, made by oracle/make_golden.py).  CPU only.  Integer/index data
+and, since neither side contracts FMAs, every floating-point vector are
+compared bit for bit; norms (whose summation order inside Eigen is not
+specified) to 1e-13 relative."""
+import numpy as np
+import pytest
+
+from oracle import orc
+from tests import helpers as H
+
+
+def test_face_vectors_bit_exact():
+    d = H.load("faces")
+    g = orc.Gas(*d["gas5"])
+    for r in d["rows"]:
+        kind, visc, nx, ny = int(r[0]), int(r[1]), r[2], r[3]
+        qL, qR, gx, gy = r[4:8], r[8:12], r[12:16], r[16:20]
+        f, v, J = r[20:24], r[24:28], r[28:92].reshape(8, 8)
+        assert np.array_equal(orc.flux(kind, g, visc, nx, ny, qL, qR, gx, gy), f)
+        assert np.array_equal(orc.bc_vars(kind, g, nx, ny, qL, qR), v)
+        assert np.array_equal(orc.fd_jacobian(kind, g, visc, nx, ny, qL, qR, gx, gy), J)
+    for c in d["conservative"]:
+        assert np.array_equal(orc.get_conservative(c[0], c[1], c[2], c[3], g), c[4:8])
+
+
+@pytest.mark.parametrize("tag", H.EXPLICIT_CASES + H.IMPLICIT_CASES)
+def test_mesh_arrays_match_reference(tag):
+    d = H.load(tag)
+    m = H.oracle_mesh(d)
+    assert (m.N, m.G, m.E) == tuple(int(v) for v in d["sizes"])
+    for a in H.MESH_ARRAYS:
+        assert H.sha(getattr(m, a)) == str(d["sha_" + a]), a
+
+
+@pytest.mark.parametrize("tag", H.EXPLICIT_CASES)
+def test_explicit_history_matches_reference(tag):
+    d = H.load(tag)
+    meta = d["meta"]
+    m = H.oracle_mesh(d)
+    s = orc.OracleSolver(m, viscosity=meta["viscosity"])
+    H.setup_solver(s, meta)
+    assert s.uniform_residual() == pytest.approx(float(d["uniform_residual_fresh"]), rel=1e-13)
+    s.q[:] = d["q0"]
+    norms = np.zeros(meta["n_iter"])
+    for it in range(meta["n_iter"]):
+        norms[it] = s.explicit_solve(meta["relax"])
+        if it == 0:
+            for nm, attr in (("q", "q"), ("qW", "qW"), ("gx", "gx"), ("gy", "gy"), ("limiters", "lim")):
+                assert H.sha(getattr(s, attr)) == str(d["sha_it1_" + nm]), nm
+                if "it1_" + nm in d:
+                    assert np.array_equal(getattr(s, attr), d["it1_" + nm])
+            assert H.sha(s.dt[:m.N]) == str(d["sha_it1_dt"])
+    assert np.all(np.isfinite(norms))
+    np.testing.assert_allclose(norms, d["norms"], rtol=1e-13, atol=0)
+    assert H.sha(s.q) == str(d["sha_qN"])
+    np.testing.assert_allclose(s.wall_forces(str(d["forces_patch"])), d["forces"], rtol=1e-14, atol=1e-16)
+
+
+@pytest.mark.parametrize("tag", H.IMPLICIT_CASES)
+def test_implicit_rhs_and_jacobian_blocks_match_reference(tag):
+    d = H.load(tag)
+    meta = d["meta"]
+    m = H.oracle_mesh(d)
+    s = orc.OracleSolver(m, viscosity=meta["viscosity"])
+    H.setup_solver(s, meta)
+    s.q[:] = d["q0"]
+    nrm = s.implicit_rhs()
+    assert nrm == pytest.approx(float(d["rhs_norm"]), rel=1e-13)
+    assert np.array_equal(s.rhs, d["rhs"])
+    assert np.array_equal(s.q, d["q_after_rhs"])
+    dg, o01, o10 = s.implicit_lhs()
+    assert H.sha(dg) == str(d["sha_diag"])
+    assert H.sha(o01) == str(d["sha_off01"])
+    assert H.sha(o10) == str(d["sha_off10"])
+    assert np.array_equal(dg[d["diag_idx"]], d["diag_blk"])
+    assert np.array_equal(o01[d["edge_idx"]], d["off01_blk"])
+
+
+def test_sanity_anchors_independent_of_any_oracle():
+    """uniform free stream on a closed mesh telescopes to zero on interior cells."""
+    d = H.load("naca0012q_coarse_euler_gg_o2")
+    m = H.oracle_mesh(d)
+    s = orc.OracleSolver(m)
+    H.setup_solver(s, d["meta"])
+    s.init(); s.refill_bcs()
+    s.s.second_order = 0
+    s.calc_residual(0)
+    qW = s.qW.reshape(-1, 4)[:m.N]
+    touches_bnd = np.zeros(m.N, bool)
+    touches_bnd[m.edge_cells[m.bnd_edge, 0]] = True
+    assert np.abs(qW[~touches_bnd]).max() < 1e-9 * np.abs(qW).max() + 1e-9
