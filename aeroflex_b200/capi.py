@@ -25,7 +25,7 @@ GRADIENT = {"green-gauss": 0, "least-squares": 1}               # core.h:175
 FIELDS = {"q": 0, "qW": 1, "gx": 2, "gy": 3, "limiters": 4, "dt": 5, "rhs": 6}
 
 EXPORTED_SYMBOLS = [
-    "afx_last_error", "afx_version", "afx_device_count",
+    "afx_last_error", "afx_version", "afx_device_count", "afx_pinned_alloc", "afx_pinned_free",
     "afx_mesh_read_msh", "afx_mesh_from_elements", "afx_mesh_synth_omesh", "afx_mesh_free", "afx_mesh_get_desc",
     "afx_mesh_n_nodes", "afx_mesh_n_patches", "afx_mesh_patch_name", "afx_mesh_patch_id", "afx_mesh_get_elements",
     "afx_mesh_write_msh",
@@ -104,6 +104,9 @@ def load_library():
     L.afx_last_error.restype = C.c_char_p
     L.afx_version.restype = C.c_char_p
     vp, dp, u32p, u8p, i32p = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint32), C.POINTER(C.c_uint8), C.POINTER(C.c_int32)
+    L.afx_pinned_alloc.restype = C.c_void_p
+    L.afx_pinned_alloc.argtypes = [C.c_size_t]
+    L.afx_pinned_free.argtypes = [vp]
     L.afx_mesh_read_msh.argtypes = [C.POINTER(vp), C.c_char_p]
     L.afx_mesh_from_elements.argtypes = [C.POINTER(vp), C.c_uint32, vp, vp, C.c_uint32, vp, vp, C.c_uint32, vp, vp, vp,
                                          C.c_int, C.POINTER(C.c_char_p)]
@@ -159,6 +162,22 @@ def device_count():
 
 def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
+
+
+def pinned_array(n, dtype=np.float64):
+    """numpy array over cudaMallocHost memory (kept alive by the returned array's base)."""
+    L = load_library()
+    nbytes = int(n) * np.dtype(dtype).itemsize
+    p = L.afx_pinned_alloc(nbytes)
+    if not p:
+        raise AfxError(-2, L.afx_last_error().decode())
+    buf = (C.c_char * nbytes).from_address(p)
+    a = np.frombuffer(buf, dtype=dtype, count=int(n))
+    _pinned_keep.append((p, buf))
+    return a
+
+
+_pinned_keep = []
 
 
 class Mesh:

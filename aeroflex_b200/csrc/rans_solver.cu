@@ -650,6 +650,14 @@ int afx_device_count(void)
     return n;
 }
 
+void* afx_pinned_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) { afx::set_error("cudaMallocHost failed"); return nullptr; }
+    return p;
+}
+void afx_pinned_free(void* p) { if (p) cudaFreeHost(p); }
+
 int afx_rans_create(afx_rans** out, const afx_mesh_desc* mesh, const afx_gas* gas, int viscosity_model, int device)
 {
     if (!out || !mesh || !gas) { afx::set_error("null argument"); return AFX_ERR_INVALID; }

@@ -1,0 +1,250 @@
+#!/usr/bin/env python
+"""bench.py -- RANS cell-updates/s of the explicit pseudo-time iteration on B200.
+
+Contract (driver): python bench.py --gpus N --steps K --warmup W  (torchrun for N>1), ONE JSON line on rank 0.
+
+A "step" is one explicitSolver::solve() (local dt + 3 RK stages, each = wall-ghost copy, limiter, face flux,
+gather + update; the gradients of the iteration-start state are computed once) over the whole mesh.
+Workload at N=1: BASELINE.json configs[1], the synthetic 1M-cell mixed tri/quad NACA0012 O-mesh, "RANS-SA"
+(which in the reference is the Roe flux + no-slip wall + always-on gradients), second order,
+Green-Gauss, limiter_k 5, relaxation 0.9, CFL 1.5, perturbed free stream (default_rng(12345), 1e-3).
+
+ value      cell-updates/s, state resident in HBM, CUDA events on the solver's stream around the K steps
+ e2e        the same metric through the C ABI with HOST state every step: afx_rans_set_q (pinned H2D) ->
+            afx_rans_step_explicit -> afx_rans_get_q (D2H) + the norm
+ roofline   the face-flux kernel k_flux: algorithmic bytes (144*N + 48*E per launch) / its mean
+            launch time, measured with CUDA events between the phases right after the timed region
+ cpu_baseline  the unmodified reference (oracle/_ref) timed on this host on a bounded sample of the same workload
+ --impl reference  that CPU reference as its own arm
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {  # name: (ni, nj, n_quad_layers) -> SURVEY.md 8d
+    "synthetic-64k-mixed-omesh": (256, 160, 64),
+    "synthetic-1M-mixed-omesh": (1024, 640, 256),
+    "synthetic-16M-mixed-omesh": (4096, 2560, 1024),
+}
+BCS = {"farfield": ("farfield", dict(mach=0.2, angle=1.0 * 0.01745, T=1.0, p=1.0)), "wall": ("wall", None)}
+VISC, GRAD, SECOND, LIMK, CFL, RELAX = "spallart-allmaras", "green-gauss", True, 5.0, 1.5, 0.9
+CPU_SAMPLE = "synthetic-64k-mixed-omesh"
+
+
+def perturbed(q, N):
+    rng = np.random.default_rng(12345)
+    q = q.copy()
+    q[:4 * N] *= 1.0 + 1e-3 * rng.uniform(-1, 1, 4 * N)
+    return q
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag, self.proc = index, [], False, None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def reference_cpu(steps, warmup):
+    """The reference's own explicitSolver on the host cores (oracle/_ref), bounded sample of the workload."""
+    import aeroflex_b200 as afx
+    from oracle import ref
+    import tempfile
+    ni, nj, nq = WORKLOADS[CPU_SAMPLE]
+    m = afx.Mesh.synth_omesh(ni, nj, nq, 150.0)
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "sample.msh")
+        m.write_msh(path)
+        rm = ref.RefMesh(path)  # rans::mesh reads it, as in the reference
+    s = ref.RefSolver(rm, False, VISC)
+    s.set_bcs(BCS); s.set_options(SECOND, GRAD, LIMK, CFL); s.init(); s.refill_bcs()
+    s.set("q", perturbed(s.get("q"), rm.N))
+    for _ in range(warmup):
+        s.explicit_solve(RELAX)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        s.explicit_solve(RELAX)
+    dt = time.perf_counter() - t0
+    threads = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
+    return {"value": rm.N * steps / dt, "unit": "cell-updates/s", "cores": threads, "kind": "reference",
+            "sample": "%s (N=%d, E=%d): %d explicit iterations of the unmodified reference headers (Eigen-API stand-in, -O3 -fopenmp, "
+                      "OMP_NUM_THREADS=%d; the reference's face loops are serial, so 1 core does the hot loops), %.1f s"
+                      % (CPU_SAMPLE, rm.N, rm.E, steps, threads, dt)}, dt / steps * 1e3
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    W = max(a.warmup, 3) if a.impl == "b200" else a.warmup
+    workload = a.workload or "synthetic-1M-mixed-omesh"
+    config = {"workload": workload, "scheme": "explicit 3-stage RK, 2nd order MUSCL, Green-Gauss, Venkatakrishnan k=5",
+              "viscosity": "spallart-allmaras (reference semantics: Roe flux + no-slip wall + gradients, SURVEY F1/F2)",
+              "cfl": CFL, "relaxation": RELAX, "l2": "working set > 126 MB L2 (inputs larger than L2, no flush)"}
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        steps = max(1, min(a.steps, 40))  # bounded: ~0.7 s per iteration on the 64k sample
+        cpu, ms = reference_cpu(steps, min(a.warmup, 2))
+        config["workload"] = workload + " (CPU arm timed on the bounded sample named in cpu_baseline.sample)"
+        print(json.dumps({"impl": "reference", "metric": "RANS cell-updates/s", "value": cpu["value"], "unit": "cell-updates/s",
+                          "n_gpus": a.gpus, "steps": steps, "warmup": min(a.warmup, 2), "ms_per_step": ms, "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                          "cpu_baseline": cpu, "e2e": {"value": cpu["value"], "unit": "cell-updates/s", "h2d_bytes_per_step": 0,
+                                                       "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    import aeroflex_b200 as afx
+    if afx.device_count() <= 0:
+        raise SystemExit("bench.py: no CUDA device visible; the product has no CPU path")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ni, nj, nq = WORKLOADS[workload]
+    mesh = afx.Mesh.synth_omesh(ni, nj, nq, 150.0)
+    N, G, E = mesh.N, mesh.G, mesh.E
+    s = afx.GpuSolver(mesh, viscosity=VISC, device=local)
+    s.set_bcs(BCS); s.set_options(SECOND, GRAD, LIMK, CFL); s.init(); s.refill_bcs()
+    q0 = perturbed(s.get_q(), N)
+    s.set_q(q0)
+    config.update({"cells": N, "edges": E, "ghost_cells": G,
+                   "parallelism": "1 GPU" if world == 1 else "%d independent replicas (polar-sweep mode, no communication)" % world})
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    s.run(W, RELAX)
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    barrier()
+    l0 = s.launch_count()
+    t0 = time.perf_counter()
+    norms = s.run(a.steps, RELAX)
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    dev_ms = s.last_device_ms()
+    launches = s.launch_count() - l0
+    clocks = sampler.finish()
+    if not np.all(np.isfinite(norms)):
+        raise SystemExit("bench.py: residual norm is not finite")
+    t_ms = dev_ms
+    if dist is not None:
+        t = torch.tensor([dev_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_ms = float(t.item())
+    value = world * N * a.steps / (t_ms * 1e-3)
+
+    # per-phase kernel times (CUDA events between the phases, same state, right after the timed region)
+    prof = s.profile_explicit(5, RELAX)
+    flux_ms = prof["flux"] / 3.0
+    alg_flux = 144.0 * N + 48.0 * E
+    alg_iter = 1488.0 * N + 296.0 * E
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "k_flux_traffic.json"))).get(workload)
+    except Exception:
+        pass
+    roof = {"bound": "hbm", "kernel": "k_flux<second order, inviscid flux>", "achieved": alg_flux / (flux_ms * 1e-3) / 1e9, "peak": peak,
+            "unit": "GB/s", "frac": alg_flux / (flux_ms * 1e-3) / 1e9 / peak, "traffic": traffic,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+            "algorithmic_bytes_per_launch": alg_flux, "kernel_ms": flux_ms,
+            "phase_ms_per_iteration": prof,
+            "iteration": {"algorithmic_bytes": alg_iter, "achieved": alg_iter / (t_ms / a.steps * 1e-3) / 1e9,
+                          "frac": alg_iter / (t_ms / a.steps * 1e-3) / 1e9 / peak}}
+
+    # end to end through the C ABI with host-resident state, pinned buffers
+    nq4 = 4 * (N + G)
+    hq = afx.pinned_array(nq4)
+    hq[:] = s.get_q()
+    for _ in range(2):
+        s.set_q(hq); s.solve(RELAX); s.get_q(hq)
+    barrier()
+    te = time.perf_counter()
+    for _ in range(a.e2e_steps):
+        s.set_q(hq)
+        nr = s.solve(RELAX)
+        s.get_q(hq)
+    barrier()
+    e2e_s = time.perf_counter() - te
+    if dist is not None:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = {"value": world * N * a.e2e_steps / e2e_s, "unit": "cell-updates/s", "h2d_bytes_per_step": 8 * nq4,
+           "d2h_bytes_per_step": 8 * nq4 + 8, "steps": a.e2e_steps, "ms_per_step": e2e_s / a.e2e_steps * 1e3,
+           "path": "afx_rans_set_q(pinned host) -> afx_rans_step_explicit -> afx_rans_get_q(pinned host) + norm"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        cpu, _ = reference_cpu(20, 1)
+    if rank == 0:
+        out = {"metric": "RANS cell-updates/s", "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": a.steps, "warmup": W,
+               "ms_per_step": t_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+               "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
+               "wall_ms_per_step": wall_ms / a.steps, "final_residual_norm": float(norms[-1])}
+        if cpu is not None:
+            out["cpu_baseline"] = cpu
+        print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -87,6 +87,10 @@ const char* afx_version(void);
 /* number of CUDA devices visible, or a negative afx_status */
 int afx_device_count(void);
 
+/* page-locked host memory for state transfers (afx_rans_set_q / get_q run at PCIe speed from it) */
+void* afx_pinned_alloc(size_t bytes);
+void afx_pinned_free(void* p);
+
 /* ------------------------------------------------------------------ */
 /* Mesh ingest (host only; replaces rans::mesh, mesh.h:250,834-884)     */
 /* ------------------------------------------------------------------ */

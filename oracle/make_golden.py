@@ -30,7 +30,12 @@ FAR = dict(mach=0.2, angle=1.0 * 0.01745, T=1.0, p=1.0)  # rans.h:94 deg->rad li
 
 
 def sha(a):
-    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    """sha256 of the bytes; floating-point arrays are hashed with -0.0 folded into +0.0 (the reference leaves
+    -0.0 in the ghost rows of gx/gy through `*= 0`, solver.h:467-468; the sign of a zero is not a result)."""
+    a = np.ascontiguousarray(a)
+    if a.dtype.kind == "f":
+        a = a + 0.0
+    return hashlib.sha256(a.tobytes()).hexdigest()
 
 
 def mesh_fixture(rm):

@@ -9,6 +9,8 @@ edge order, so states/gradients/limiters/residual vectors are required to be
 BIT-IDENTICAL; only norms and force integrals (tree reductions on the device)
 get a tolerance, 1e-12 relative -- two orders inside BASELINE.json's 1e-10 /
 1e-8 bars."""
+import math
+
 import numpy as np
 import pytest
 
@@ -37,7 +39,8 @@ def test_explicit_history_vs_reference_golden(afx, gpu, tag):
     s.set_q(d["q0"])
     n = meta["n_iter"]
     first = s.solve(meta["relax"])
-    for nm in ("q", "qW", "gx", "gy", "limiters"):
+    # first-order runs never call calc_limiters (solver.h:813): that vector is uninitialised in the reference
+    for nm in ("q", "qW", "gx", "gy") + (("limiters",) if meta["second_order"] else ()):
         v = s.get(nm)
         assert H.sha(v) == str(d["sha_it1_" + nm]), nm
         if "it1_" + nm in d:
@@ -196,10 +199,12 @@ def test_full_size_mesh_vs_oracle_and_conservation(afx, gpu):
         z.set_bcs(bcs); z.set_options(True, "green-gauss", 5.0, 1.5); z.init(); z.refill_bcs()
     q0 = H.synth_state(m.N, o.q.copy())
     s.set_q(q0); o.q[:] = q0
-    gn = s.solve(0.9); on = o.explicit_solve(0.9)
-    assert gn == pytest.approx(on, rel=NORM_RTOL)
+    gn = s.solve(0.9); o.explicit_solve(0.9)
     assert np.array_equal(s.get_q(), o.q)
     assert np.array_equal(s.get("qW"), o.qW)
+    # 4M squares: the oracle's left-to-right sum is itself only good to ~1e-12, so compare with the exactly
+    # rounded sum of the (bit-identical) vector
+    assert gn == pytest.approx(math.sqrt(math.fsum(o.qW * o.qW)), rel=1e-13)
     # (b) conservation of the last-stage residual: interior fluxes cancel pairwise
     qW = s.get("qW").reshape(-1, 4)[:m.N]
     total = (qW * m.area[:m.N, None]).sum(axis=0)
