@@ -30,6 +30,7 @@ EXPORTED_SYMBOLS = [
     "afx_mesh_n_nodes", "afx_mesh_n_patches", "afx_mesh_patch_name", "afx_mesh_patch_id", "afx_mesh_get_elements",
     "afx_mesh_write_msh",
     "afx_rans_create", "afx_rans_destroy", "afx_rans_set_bcs", "afx_rans_set_options", "afx_rans_set_cfl",
+    "afx_rans_set_math_mode", "afx_rans_get_math_mode",
     "afx_rans_init", "afx_rans_refill_bcs", "afx_rans_bcs_from_internal", "afx_rans_set_q", "afx_rans_get_q",
     "afx_rans_get_field", "afx_rans_boundary_variables", "afx_rans_uniform_residual", "afx_rans_step_explicit",
     "afx_rans_run_explicit", "afx_rans_phase_dt_gradients", "afx_rans_phase_limiters", "afx_rans_phase_residual",
@@ -66,26 +67,43 @@ class MeshDesc(C.Structure):
 
 
 def library_path():
-    return os.path.join(LIBDIR, LIBNAME)
+    """AFX_LIB overrides the path (used to A/B differently tuned builds of the same sources)."""
+    return os.environ.get("AFX_LIB") or os.path.join(LIBDIR, LIBNAME)
 
 
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false", "-std=c++17",
-              "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fPIC,-fopenmp,-O3", "-shared"]
-SOURCES = ["rans_solver.cu", "mesh_host.cpp", "mesh_capi.cpp"]
+NVCC_COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-ccbin", "/usr/bin/g++",
+               "-Xcompiler", "-fPIC,-fopenmp,-O3"]
+# (source, object, extra flags): the kernels are compiled twice, once per arithmetic mode
+UNITS = [("rans_kernels_tu.cu", "kernels_strict.o", ["-DAFX_FAST=0", "-fmad=false"]),
+         ("rans_kernels_tu.cu", "kernels_fast.o", ["-DAFX_FAST=1", "-fmad=true"]),
+         ("rans_solver.cu", "rans_solver.o", ["-fmad=false"]),
+         ("mesh_host.cpp", "mesh_host.o", []),
+         ("mesh_capi.cpp", "mesh_capi.o", [])]
 
 
-def build_library(force=False, verbose=False):
-    """nvcc cross-compiles the library for sm_100a (works without a GPU)."""
-    out = library_path()
-    srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))] + \
-        [os.path.join(ROOT, "include", "afx_rans.h")]
+def build_library(force=False, verbose=False, defines=(), out=None):
+    """nvcc cross-compiles the library for sm_100a (works without a GPU).  `defines` (e.g. ["-DAFX_FLUX_MINB=4"])
+    and `out` build a tuning variant next to the default library."""
+    from concurrent.futures import ThreadPoolExecutor
+    variant = out is not None
+    out = out or os.path.join(LIBDIR, LIBNAME)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cpp", ".cuh", ".h"))] + \
+        [os.path.join(ROOT, "include", "afx_rans.h"), os.path.abspath(__file__)]
     if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
         return out
     os.makedirs(LIBDIR, exist_ok=True)
+    bdir = os.path.join(PKG, "build", os.path.basename(out) if variant else "default")
+    os.makedirs(bdir, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + srcs + ["-lgomp"]
-    subprocess.run(cmd, check=True, cwd=CSRC)
+
+    def cc(unit):
+        src, obj, extra = unit
+        cmd = [nvcc] + NVCC_COMMON + extra + list(defines) + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", os.path.join(bdir, obj)]
+        subprocess.run(cmd, check=True, cwd=CSRC)
+    with ThreadPoolExecutor(len(UNITS)) as ex:
+        list(ex.map(cc, UNITS))
+    subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", "/usr/bin/g++", "-shared", "-o", out] +
+                   [os.path.join(bdir, u[1]) for u in UNITS] + ["-lgomp"], check=True)
     return out
 
 
@@ -126,6 +144,8 @@ def load_library():
     L.afx_rans_set_bcs.argtypes = [vp, C.c_int, vp, C.POINTER(BVars)]
     L.afx_rans_set_options.argtypes = [vp, C.c_int, C.c_int, C.c_double]
     L.afx_rans_set_cfl.argtypes = [vp, C.c_double]
+    L.afx_rans_set_math_mode.argtypes = [vp, C.c_int]
+    L.afx_rans_get_math_mode.argtypes = [vp]
     for n in ("afx_rans_init", "afx_rans_refill_bcs", "afx_rans_bcs_from_internal", "afx_rans_phase_dt_gradients",
               "afx_rans_phase_limiters", "afx_rans_fill_jacobian"):
         getattr(L, n).argtypes = [vp]
@@ -271,7 +291,9 @@ class Mesh:
 class GpuSolver:
     """rans::solver on one B200 through the C ABI."""
 
-    def __init__(self, mesh, gas=None, viscosity="inviscid", device=0):
+    def __init__(self, mesh, gas=None, viscosity="inviscid", device=0, math=None):
+        """math: "strict" (bit-identical to the CPU reference), "fast" (default; shared reciprocals + FMA) or None
+        (library default / AFX_MATH)."""
         self.L = load_library()
         self.mesh = mesh
         g = gas or {}
@@ -282,6 +304,12 @@ class GpuSolver:
         _check(self.L.afx_rans_create(C.byref(self.h), C.byref(mesh.d), C.byref(self.gas), VISCOSITY[viscosity], device))
         self.n4 = 4 * (mesh.N + mesh.G)
         self.bcs = {}
+        if math is not None:
+            _check(self.L.afx_rans_set_math_mode(self.h, {"strict": 0, "fast": 1}[math]))
+
+    @property
+    def math(self):
+        return "strict" if self.L.afx_rans_get_math_mode(self.h) == 0 else "fast"
 
     def __del__(self):
         try:

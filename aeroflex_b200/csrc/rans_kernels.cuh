@@ -17,25 +17,31 @@
 #pragma once
 #include "rans_physics.cuh"
 
+// resident CTAs per SM asked of ptxas for the two heavy kernels (register cap = 65536 / (256 * n))
+#ifndef AFX_FLUX_MINB
+#define AFX_FLUX_MINB 3
+#endif
+#ifndef AFX_LIM_MINB
+#define AFX_LIM_MINB 3
+#endif
+
 namespace afx {
+namespace AFX_NS {
 
-constexpr uint32_t CF_NONE = 0xFFFFFFFFu;
-constexpr uint32_t CF_SIDE = 0x80000000u;  // this cell is cell1 of the face
-constexpr uint32_t CF_BND = 0x40000000u;   // boundary face (cell1 is a ghost)
-constexpr uint32_t CF_ID = 0x3FFFFFFFu;
-
-struct DevMesh {
-    uint32_t N, G, E, NT;        // real cells, ghosts, faces, N+G
-    const uint2* fcells;         // [E]
-    const d4* fgA;               // [E] nx, ny, len, w
-    const d4* fgB;               // [E] d0x, d0y, d1x, d1y
-    const d4* ftij;              // [E] t0, t1, l, - (laminar face-gradient direction, solver.h:369-376)
-    const uint8_t* fkind;        // [E]
-    const uint32_t* cf;          // [4][N]
-    const double* area;          // [NT]
-    const double* lsqM;          // [8][N]  (M * dT) rows in cellsEdges order, LSQ only
-    const uint16_t* lsq_perm;    // [N] bits 0-7: slot of local side j (2 bits each), bits 8-10: number of sides
-};
+// spectral radius c + |V.n| of one state, solver.h:329-336
+__device__ __forceinline__ double spectral_radius(const d4& q, double nx, double ny, double gam)
+{
+#if AFX_FAST
+    const double r = 1.0 / q.x;
+    const double V = (q.y * nx + q.z * ny) * r;
+    const double p = (gam - 1) * (q.w - 0.5 * r * (q.y * q.y + q.z * q.z));
+    return sqrt(p * gam * r) + fabs(V);
+#else
+    const double V = (q.y * nx + q.z * ny) / q.x;
+    const double p = (gam - 1) * (q.w - 0.5 / q.x * (q.y * q.y + q.z * q.z));
+    return sqrt(p * gam / q.x) + fabs(V);
+#endif
+}
 
 // ---------------------------------------------------------------------------
 // Local time step + gradients of q, one thread per real cell.
@@ -69,14 +75,10 @@ __global__ void __launch_bounds__(256) k_dt_grad(DevMesh m, d4* __restrict__ q, 
         const d4 qL = side ? qj : qi, qR = side ? qi : qj;  // states of cell0 / cell1
         const double nx = gA.x, ny = gA.y, len = gA.z;
         // spectral radius, solver.h:328-345
-        const double V_L = (qL.y * nx + qL.z * ny) / qL.x;
-        const double p_L = (gam - 1) * (qL.w - 0.5 / qL.x * (qL.y * qL.y + qL.z * qL.z));
-        const double eig_L = sqrt(p_L * gam / qL.x) + fabs(V_L);
+        const double eig_L = spectral_radius(qL, nx, ny, gam);
         double eig = eig_L;
         if (kind == K_INTERNAL) {
-            const double V_R = (qR.y * nx + qR.z * ny) / qR.x;
-            const double p_R = (gam - 1) * (qR.w - 0.5 / qR.x * (qR.y * qR.y + qR.z * qR.z));
-            const double eig_R = sqrt(p_R * gam / qR.x) + fabs(V_R);
+            const double eig_R = spectral_radius(qR, nx, ny, gam);
             eig = (eig_L < eig_R) ? eig_R : eig_L;
         }
         dsum += eig * len;
@@ -134,6 +136,13 @@ __global__ void __launch_bounds__(256) k_dt_grad(DevMesh m, d4* __restrict__ q, 
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ double venkat(double dqg, double dmax, double dmin, double K3a)
 {
+#if AFX_FAST
+    // one division: the reference's 1/dqg * num / den with the common factor dqg cancelled analytically
+    const double dm = dqg > 0 ? dmax : dmin;
+    const double num = dm * dm + K3a + 2 * dqg * dm;
+    const double den = dm * dm + 2 * dqg * dqg + dm * dqg + K3a;
+    return (dqg > 1e-16 || dqg < -1e-16) ? num / den : 1.0;
+#endif
     if (dqg > 1e-16)
         return 1 / dqg * ((dmax * dmax + K3a) * dqg + 2 * dqg * dqg * dmax) / (dmax * dmax + 2 * dqg * dqg + dmax * dqg + K3a);
     if (dqg < -1e-16)
@@ -141,7 +150,7 @@ __device__ __forceinline__ double venkat(double dqg, double dmax, double dmin, d
     return 1.0;
 }
 
-__global__ void __launch_bounds__(256) k_limiter(DevMesh m, const d4* __restrict__ qk, const d4* __restrict__ gx,
+__global__ void __launch_bounds__(256, AFX_LIM_MINB) k_limiter(DevMesh m, const d4* __restrict__ qk, const d4* __restrict__ gx,
                                                  const d4* __restrict__ gy, d4* __restrict__ lim, double limiter_k)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -187,7 +196,7 @@ __global__ void __launch_bounds__(256) k_limiter(DevMesh m, const d4* __restrict
 // iteration-start q.
 // ---------------------------------------------------------------------------
 template <int SECOND, int VISC, int UNIFORM>
-__global__ void __launch_bounds__(256) k_flux(DevMesh m, const d4* __restrict__ qk, const d4* __restrict__ q0,
+__global__ void __launch_bounds__(256, AFX_FLUX_MINB) k_flux(DevMesh m, const d4* __restrict__ qk, const d4* __restrict__ q0,
                                               const d4* __restrict__ gx, const d4* __restrict__ gy,
                                               const d4* __restrict__ lim, d4* __restrict__ flux, GasC g, d4 qfar)
 {
@@ -238,8 +247,6 @@ __global__ void __launch_bounds__(256) k_flux(DevMesh m, const d4* __restrict__ 
 // the last block to finish adds the partials in index order and stores the
 // square root (residual L2 norm, solver.h:827 / 1178).
 // ---------------------------------------------------------------------------
-constexpr unsigned int NORM_RING = 1u << 16;  // capacity of the device-side residual history ring
-
 __device__ __forceinline__ void block_norm_accumulate(double v, double* partial, unsigned int* counter,
                                                       double* norms, unsigned int* norm_idx)
 {
@@ -443,13 +450,14 @@ __global__ void __launch_bounds__(256) k_jac_diag(DevMesh m, const double* __res
 // Wall forces (get_wall_profile, post.h:341-376): one block, boundary edges of
 // one patch, warp-shuffle reduction of (fx, fy, -m).
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_wall_forces(const uint32_t* __restrict__ bface, const int32_t* __restrict__ bpatch,
-                                                     uint32_t G, int patch, DevMesh m, const d4* __restrict__ q,
-                                                     const double* __restrict__ bcx, const double* __restrict__ bcy,
-                                                     double gam, double p_inf, double mach_inf, double xmin, double xmax,
-                                                     double x_moment, double y_moment, double* __restrict__ out3,
-                                                     double* __restrict__ cp_out)
+__global__ void __launch_bounds__(256) k_wall_forces(WallArgs a, DevMesh m, const d4* __restrict__ q)
 {
+    const uint32_t* __restrict__ bface = a.bface; const int32_t* __restrict__ bpatch = a.bpatch;
+    const uint32_t G = a.G; const int patch = a.patch;
+    const double* __restrict__ bcx = a.bcx; const double* __restrict__ bcy = a.bcy;
+    const double gam = a.gam, p_inf = a.p_inf, mach_inf = a.mach_inf, xmin = a.xmin, xmax = a.xmax;
+    const double x_moment = a.x_moment, y_moment = a.y_moment;
+    double* __restrict__ out3 = a.out3; double* __restrict__ cp_out = a.cp_out;
     __shared__ double sh[3][8];
     double fx = 0, fy = 0, mm = 0;
     for (uint32_t b = threadIdx.x; b < G; b += blockDim.x) {
@@ -495,11 +503,10 @@ __global__ void k_ghost_fill(d4* __restrict__ q, const uint32_t* __restrict__ bg
     if (b < G) q[bghost[b]] = from_owner ? q[bowner[b]] : bstate[b];
 }
 // permuted copies between reference order (host layout) and internal order
-__global__ void k_permute4(const d4* __restrict__ src, d4* __restrict__ dst, const uint32_t* __restrict__ idx, uint32_t n, int scatter)
+__global__ void k_permute4(const d4* __restrict__ src, d4* __restrict__ dst, const uint32_t* __restrict__ idx, uint32_t n)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    if (scatter) dst[idx[i]] = src[i]; else dst[i] = src[idx[i]];
+    if (i < n) dst[i] = src[idx[i]];
 }
 __global__ void k_permute1(const double* __restrict__ src, double* __restrict__ dst, const uint32_t* __restrict__ idx, uint32_t n, uint32_t nsrc)
 {
@@ -509,4 +516,65 @@ __global__ void k_permute1(const double* __restrict__ src, double* __restrict__ 
     dst[i] = j < nsrc ? src[j] : 0.0;
 }
 
+
+// ---------------------------------------------------------------------------
+// Launchers (one kernel each) collected in the mode's KernelTable.
+// ---------------------------------------------------------------------------
+namespace launch {
+
+inline unsigned nblk(size_t n, unsigned bs = 256) { return (unsigned)((n + bs - 1) / bs); }
+
+static void dt_grad(int grad, const DevMesh& m, d4* q, double* dt, d4* gx, d4* gy, const double* prm, double gam, int want_grad,
+                    int walls, cudaStream_t st)
+{
+    if (grad == 0) k_dt_grad<0><<<nblk(m.N), 256, 0, st>>>(m, q, dt, gx, gy, prm, gam, want_grad, walls);
+    else k_dt_grad<1><<<nblk(m.N), 256, 0, st>>>(m, q, dt, gx, gy, prm, gam, want_grad, walls);
+}
+static void limiter(const DevMesh& m, const d4* qk, const d4* gx, const d4* gy, d4* lim, double k, cudaStream_t st)
+{
+    k_limiter<<<nblk(m.N), 256, 0, st>>>(m, qk, gx, gy, lim, k);
+}
+static void flux(int second, int visc, int uniform, const DevMesh& m, const d4* qk, const d4* q0, const d4* gx, const d4* gy,
+                 const d4* lim, d4* fl, const GasC& g, d4 qfar, cudaStream_t st)
+{
+    const unsigned nb = nblk(m.E);
+#define AFX_FLUX(S, V, U) k_flux<S, V, U><<<nb, 256, 0, st>>>(m, qk, q0, gx, gy, lim, fl, g, qfar)
+    if (uniform) { if (visc) AFX_FLUX(0, 1, 1); else AFX_FLUX(0, 0, 1); }
+    else if (second) { if (visc) AFX_FLUX(1, 1, 0); else AFX_FLUX(1, 0, 0); }
+    else { if (visc) AFX_FLUX(0, 1, 0); else AFX_FLUX(0, 0, 0); }
+#undef AFX_FLUX
+}
+static void gather(int mode, int last, const DevMesh& m, const d4* fl, const d4* q, const d4* qk_in, d4* qk_out, const double* dt,
+                   d4* vec_out, double alpha, const double* prm, int walls, const NormOut& no, cudaStream_t st)
+{
+    const unsigned nb = nblk(m.N);
+#define AFX_G(M, L) k_gather_update<M, L><<<nb, 256, 0, st>>>(m, fl, q, qk_in, qk_out, dt, vec_out, alpha, prm, walls, no.partial, no.counter, no.norms, no.norm_idx)
+    if (mode == 0) { if (last) AFX_G(0, 1); else AFX_G(0, 0); }
+    else if (mode == 1) AFX_G(1, 1);
+    else AFX_G(2, 1);
+#undef AFX_G
+}
+static void jacobian(int visc, const DevMesh& m, const d4* q, const d4* gx, const d4* gy, d4* J, const GasC& g, cudaStream_t st)
+{
+    if (visc) k_jacobian<1><<<nblk(m.E, 128), 128, 0, st>>>(m, q, gx, gy, J, g);
+    else k_jacobian<0><<<nblk(m.E, 128), 128, 0, st>>>(m, q, gx, gy, J, g);
+}
+static void jac_diag(const DevMesh& m, const d4* J, const double* dt, double* D, cudaStream_t st)
+{
+    k_jac_diag<<<nblk(m.NT), 256, 0, st>>>(m, reinterpret_cast<const double*>(J), dt, D);
+}
+static void wall_forces(const WallArgs& a, const DevMesh& m, const d4* q, cudaStream_t st) { k_wall_forces<<<1, 256, 0, st>>>(a, m, q); }
+static void fill_cells(d4* q, uint32_t n, d4 v, cudaStream_t st) { k_fill_cells<<<nblk(n), 256, 0, st>>>(q, n, v); }
+static void ghost_fill(d4* q, const uint32_t* bghost, const uint32_t* bowner, const d4* bstate, uint32_t G, int from_owner, cudaStream_t st)
+{
+    k_ghost_fill<<<nblk(G), 256, 0, st>>>(q, bghost, bowner, bstate, G, from_owner);
+}
+static void permute4(const d4* src, d4* dst, const uint32_t* idx, uint32_t n, cudaStream_t st) { k_permute4<<<nblk(n), 256, 0, st>>>(src, dst, idx, n); }
+static void permute1(const double* src, double* dst, const uint32_t* idx, uint32_t n, uint32_t nsrc, cudaStream_t st)
+{
+    k_permute1<<<nblk(n), 256, 0, st>>>(src, dst, idx, n, nsrc);
+}
+
+}  // namespace launch
+}  // namespace AFX_NS
 }  // namespace afx

@@ -1,0 +1,23 @@
+// rans_kernels_tu.cu -- one translation unit per arithmetic mode:
+//   nvcc -DAFX_FAST=0 -fmad=false -> namespace afx::strict (bit-identical to the CPU reference)
+//   nvcc -DAFX_FAST=1 -fmad=true  -> namespace afx::fast   (shared reciprocals, FMA contraction)
+#include "rans_kernels.cuh"
+
+namespace afx {
+namespace AFX_NS {
+
+const KernelTable& table()
+{
+    static const KernelTable t = {
+#if AFX_FAST
+        "fast",
+#else
+        "strict",
+#endif
+        launch::dt_grad, launch::limiter, launch::flux, launch::gather, launch::jacobian, launch::jac_diag,
+        launch::wall_forces, launch::fill_cells, launch::ghost_fill, launch::permute4, launch::permute1};
+    return t;
+}
+
+}  // namespace AFX_NS
+}  // namespace afx

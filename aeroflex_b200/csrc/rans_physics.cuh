@@ -5,20 +5,24 @@
 // so in double precision (IEEE div/sqrt) the results are bit-identical to the
 // CPU code built without FMA contraction.
 #pragma once
-#include <cstdint>
+#include "rans_types.h"
 
+#ifndef AFX_FAST
+#define AFX_FAST 0
+#endif
+#if AFX_FAST
+#define AFX_NS fast
+#else
+#define AFX_NS strict
+#endif
+
+// Two arithmetic modes share this file (one translation unit each, rans_kernels_tu.cu):
+//   strict (AFX_FAST=0, -fmad=false): the reference's expression order, every division where the reference
+//          divides -> bit-identical to the CPU reference built without FMA contraction;
+//   fast   (AFX_FAST=1, -fmad=true) : the same formulas with reciprocals shared between divisions by the same
+//          denominator and FMA contraction allowed -> each face flux within a few ulp of strict.
 namespace afx {
-
-// 32-byte aligned 4-vector: one LDG.E.256 / STG.E.256 per cell state on sm_100a
-struct __align__(32) d4 {
-    double x, y, z, w;
-};
-
-struct GasC {
-    double gamma, R, mu_L, Pr_L, cp;
-};
-
-enum : int { K_INTERNAL = 0, K_FARFIELD = 1, K_SLIPWALL = 2, K_WALL = 3 };
+namespace AFX_NS {
 
 __device__ __forceinline__ d4 mk4(double a, double b, double c, double d) { d4 r; r.x = a; r.y = b; r.z = c; r.w = d; return r; }
 
@@ -33,6 +37,52 @@ __device__ __forceinline__ double sabs(double x) { return sqrt(x * x + 1e-4); }
 // physics.h:133-135
 __device__ __forceinline__ double entropy_fix(double l, double d) { return l > d ? l : (l * l + d * d) / (2 * d); }
 
+#if AFX_FAST
+// Roe flux, physics.h:180-228, with 4 divisions (1/rhoL, 1/rhoR, 1/(sL+sR), 1/c^2) instead of 19
+__device__ __forceinline__ d4 roe_flux(const d4& qL, const d4& qR, double nx, double ny, double gam)
+{
+    const double gm1 = gam - 1;
+    const double rL = 1.0 / qL.x, rR = 1.0 / qR.x;
+    const double uL = qL.y * rL, vL = qL.z * rL, uR = qR.y * rR, vR = qR.z * rR;
+    const double VL = uL * nx + vL * ny, VR = uR * nx + vR * ny;
+    const double pL = gm1 * (qL.w - 0.5 * (qL.y * uL + qL.z * vL));
+    const double pR = gm1 * (qR.w - 0.5 * (qR.y * uR + qR.z * vR));
+    d4 f;
+    f.x = (VL * qL.x + VR * qR.x) * 0.5;
+    f.y = (VL * qL.y + VR * qR.y + (pL + pR) * nx) * 0.5;
+    f.z = (VL * qL.z + VR * qR.z + (pL + pR) * ny) * 0.5;
+    f.w = (VL * (qL.w + pL) + VR * (qR.w + pR)) * 0.5;
+
+    const double sL = sqrt(qL.x), sR = sqrt(qR.x);
+    const double rho = sR * sL;
+    const double rs = 1.0 / (sL + sR);
+    const double wL = sL * rs, wR = sR * rs;
+    const double u = uL * wL + uR * wR;
+    const double v = vL * wL + vR * wR;
+    const double h = (qL.w + pL) * rL * wL + (qR.w + pR) * rR * wR;
+    const double q2 = u * u + v * v;
+    const double c2 = gm1 * (h - 0.5 * q2);
+    const double c = sqrt(c2);
+    const double rc2 = 1.0 / c2;
+    const double V = u * nx + v * ny;
+    const double d = 0.05 * c, hd = 10.0 * c * rc2;  // 1/(2d) = 10/c
+    const double a_cm = sabs(V - c), a_c = sabs(V), a_cp = sabs(V + c);
+    const double l_cm = a_cm > d ? a_cm : (a_cm * a_cm + d * d) * hd;
+    const double l_c = a_c > d ? a_c : (a_c * a_c + d * d) * hd;
+    const double l_cp = a_cp > d ? a_cp : (a_cp * a_cp + d * d) * hd;
+    const double dp = pR - pL, dV = VR - VL, rcdV = rho * c * dV;
+    const double k1 = l_cm * (dp - rcdV) * (0.5 * rc2);
+    const double k2 = l_c * ((qR.x - qL.x) - dp * rc2);
+    const double k3 = l_c * rho;
+    const double k5 = l_cp * (dp + rcdV) * (0.5 * rc2);
+    const double du = uR - uL, dv = vR - vL;
+    f.x -= 0.5 * (k1 + k2 + k5);
+    f.y -= 0.5 * (k1 * (u - c * nx) + k2 * u + k3 * (du - dV * nx) + k5 * (u + c * nx));
+    f.z -= 0.5 * (k1 * (v - c * ny) + k2 * v + k3 * (dv - dV * ny) + k5 * (v + c * ny));
+    f.w -= 0.5 * (k1 * (h - c * V) + k2 * q2 * 0.5 + k3 * (u * du + v * dv - V * dV) + k5 * (h + c * V));
+    return f;
+}
+#else
 // Roe flux, physics.h:180-228
 __device__ __forceinline__ d4 roe_flux(const d4& qL, const d4& qR, double nx, double ny, double gam)
 {
@@ -75,6 +125,7 @@ __device__ __forceinline__ d4 roe_flux(const d4& qL, const d4& qR, double nx, do
     f.w -= 0.5 * (k1 * (h - c * V) + k2 * q2 * 0.5 + k3 * (u * (uR - uL) + v * (vR - vL) - V * (VR - VL)) + k5 * (h + c * V));
     return f;
 }
+#endif
 
 // Laminar viscous part, physics.h:230-257 with helpers :33-82. Subtracted from f in place.
 __device__ __forceinline__ void laminar_flux(d4& f, const d4& qL, const d4& qR, const d4& gx, const d4& gy,
@@ -184,4 +235,5 @@ __device__ __forceinline__ d4 face_flux(int kind, const d4& qL, const d4& qR, co
     return f;
 }
 
+}  // namespace AFX_NS
 }  // namespace afx

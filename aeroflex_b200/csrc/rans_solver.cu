@@ -22,7 +22,7 @@
 #include <vector>
 
 #include "../../include/afx_rans.h"
-#include "rans_kernels.cuh"
+#include "rans_types.h"
 
 namespace afx {
 
@@ -127,6 +127,14 @@ struct Solver {
     bool jac_valid = false;
 
     DevMesh dm{};
+    const KernelTable* kt = &fast::table();  // arithmetic mode, see afx_rans_set_math_mode
+    NormOut norm_out() { return NormOut{partial.p, counters.p, norms.p, counters.p + 1}; }
+    void set_math_mode(int mode)
+    {
+        if (mode != AFX_MATH_STRICT && mode != AFX_MATH_FAST) throw InvalidArg("unknown math mode");
+        const KernelTable* t = (mode == AFX_MATH_STRICT) ? &strict::table() : &fast::table();
+        if (t != kt) { kt = t; invalidate_graph(); jac_valid = false; }
+    }
 
     ~Solver()
     {
@@ -202,6 +210,7 @@ void Solver::create(const afx_mesh_desc& m, const afx_gas& g, int visc, int dev)
     for (auto& e : evp) CK(cudaEventCreate(&e));
     CK(cudaMallocHost(&h_pinned, 64 * sizeof(double)));
     if (const char* e = getenv("AFX_NO_GRAPH")) use_graph = !(e[0] == '1');
+    if (const char* e = getenv("AFX_MATH")) kt = (std::string(e) == "strict") ? &strict::table() : &fast::table();
 
     N = m.n_cells; G = m.n_ghost; E = m.n_edges; NT = N + G;
     if (!N || !E) throw InvalidArg("empty mesh");
@@ -338,7 +347,7 @@ void Solver::create(const afx_mesh_desc& m, const afx_gas& g, int visc, int dev)
     partial.alloc(blocks(NT) + 1); norms.alloc(NORM_RING); norms.zero(st);
     prm.alloc(8); prm.zero(st); counters.alloc(4); counters.zero(st); scratch.alloc(16);
     // limiters start at 1 (ghost rows keep that value, solver.h:519)
-    k_fill_cells<<<blocks(NT), 256, 0, st>>>(lim.p, NT, d4{1, 1, 1, 1});
+    kt->fill_cells(lim.p, NT, d4{1, 1, 1, 1}, st);
     ++launches;
 
     // least-squares coefficients (M * dT), rows in cellsEdges order, solver.h:402-422 + 504
@@ -415,39 +424,26 @@ void Solver::push_params(double relax)
 
 void Solver::launch_dt_grad(bool want_grad, bool walls)
 {
-    if (gradient_scheme == AFX_GRAD_GREEN_GAUSS)
-        k_dt_grad<0><<<blocks(N), 256, 0, st>>>(dm, q.p, dt.p, gx.p, gy.p, prm.p, gas.gamma, want_grad, walls);
-    else
-        k_dt_grad<1><<<blocks(N), 256, 0, st>>>(dm, q.p, dt.p, gx.p, gy.p, prm.p, gas.gamma, want_grad, walls);
+    kt->dt_grad(gradient_scheme == AFX_GRAD_GREEN_GAUSS ? 0 : 1, dm, q.p, dt.p, gx.p, gy.p, prm.p, gas.gamma, want_grad, walls, st);
     ++launches;
 }
 
 void Solver::launch_limiter(const d4* qk)
 {
-    k_limiter<<<blocks(N), 256, 0, st>>>(dm, qk, gx.p, gy.p, lim.p, limiter_k);
+    kt->limiter(dm, qk, gx.p, gy.p, lim.p, limiter_k, st);
     ++launches;
 }
 
 void Solver::launch_flux(const d4* qk, bool uniform, d4 qfar)
 {
-    const unsigned nb = blocks(E);
-#define AFX_FLUX(S, V, U) k_flux<S, V, U><<<nb, 256, 0, st>>>(dm, qk, q.p, gx.p, gy.p, lim.p, flux.p, gas, qfar)
-    if (uniform) {
-        if (viscous_type) AFX_FLUX(0, 1, 1); else AFX_FLUX(0, 0, 1);
-    } else if (second_order) {
-        if (viscous_type) AFX_FLUX(1, 1, 0); else AFX_FLUX(1, 0, 0);
-    } else {
-        if (viscous_type) AFX_FLUX(0, 1, 0); else AFX_FLUX(0, 0, 0);
-    }
-#undef AFX_FLUX
+    kt->flux(second_order, viscous_type, uniform ? 1 : 0, dm, qk, q.p, gx.p, gy.p, lim.p, flux.p, gas, qfar, st);
     ++launches;
 }
 
 template <int MODE, int LAST>
 void Solver::launch_gather(const d4* qk_in, d4* qk_out, d4* vec_out, double alpha, bool walls)
 {
-    k_gather_update<MODE, LAST><<<blocks(N), 256, 0, st>>>(dm, flux.p, q.p, qk_in, qk_out, dt.p, vec_out, alpha, prm.p,
-                                                           walls ? 1 : 0, partial.p, counters.p, norms.p, counters.p + 1);
+    kt->gather(MODE, LAST, dm, flux.p, q.p, qk_in, qk_out, dt.p, vec_out, alpha, prm.p, walls ? 1 : 0, norm_out(), st);
     ++launches;
 }
 
@@ -576,9 +572,8 @@ void Solver::fill_jacobian()
     push_params(relax_dev < 0 ? 1.0 : relax_dev);
     if (!J.p) { J.alloc((size_t)E * 16); D.alloc((size_t)NT * 16); }
     launch_dt_grad(visc_not_inviscid, visc_not_inviscid);  // solver.h:981-986
-    if (viscous_type) k_jacobian<1><<<blocks(E, 128), 128, 0, st>>>(dm, q.p, gx.p, gy.p, J.p, gas);
-    else k_jacobian<0><<<blocks(E, 128), 128, 0, st>>>(dm, q.p, gx.p, gy.p, J.p, gas);
-    k_jac_diag<<<blocks(NT), 256, 0, st>>>(dm, reinterpret_cast<const double*>(J.p), dt.p, D.p);
+    kt->jacobian(viscous_type, dm, q.p, gx.p, gy.p, J.p, gas, st);
+    kt->jac_diag(dm, J.p, dt.p, D.p, st);
     launches += 2;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));
@@ -588,7 +583,7 @@ void Solver::fill_jacobian()
 void Solver::to_ref_order4(const d4* dev_new, double* host_out)
 {
     // stage[old] = dev_new[old2new[old]]
-    k_permute4<<<blocks(NT), 256, 0, st>>>(dev_new, stage.p, perm_c_old2new.p, NT, 0);
+    kt->permute4(dev_new, stage.p, perm_c_old2new.p, NT, st);
     ++launches;
     CK(cudaMemcpyAsync(host_out, stage.p, (size_t)NT * sizeof(d4), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -598,7 +593,7 @@ void Solver::from_ref_order4(const double* host_in, d4* dev_new)
 {
     CK(cudaMemcpyAsync(stage.p, host_in, (size_t)NT * sizeof(d4), cudaMemcpyHostToDevice, st));
     // dev_new[new] = stage[new2old[new]]
-    k_permute4<<<blocks(NT), 256, 0, st>>>(stage.p, dev_new, perm_c_new2old.p, NT, 0);
+    kt->permute4(stage.p, dev_new, perm_c_new2old.p, NT, st);
     ++launches;
     CK(cudaStreamSynchronize(st));
 }
@@ -685,6 +680,13 @@ int afx_rans_set_options(afx_rans* s, int second_order, int gradient_scheme, dou
     return guard([&] { s->s.set_options(second_order, gradient_scheme, limiter_k); });
 }
 
+int afx_rans_set_math_mode(afx_rans* s, int mode)
+{
+    return guard([&] { s->s.set_math_mode(mode); });
+}
+
+int afx_rans_get_math_mode(afx_rans* s) { return s->s.kt == &afx::strict::table() ? AFX_MATH_STRICT : AFX_MATH_FAST; }
+
 int afx_rans_set_cfl(afx_rans* s, double cfl)
 {
     s->s.cfl = cfl;
@@ -700,7 +702,7 @@ int afx_rans_init(afx_rans* s)
         S.boundary_variables(&v);
         double q4[4];
         S.conservative(v, q4);
-        afx::k_fill_cells<<<afx::Solver::blocks(S.N), 256, 0, S.st>>>(S.q.p, S.N, afx::d4{q4[0], q4[1], q4[2], q4[3]});
+        S.kt->fill_cells(S.q.p, S.N, afx::d4{q4[0], q4[1], q4[2], q4[3]}, S.st);
         ++S.launches;
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(S.st));
@@ -715,7 +717,7 @@ int afx_rans_refill_bcs(afx_rans* s)
         S.use();
         if (!S.bcs_set) throw afx::InvalidArg("set_bcs has not been called");
         if (S.G) {
-            afx::k_ghost_fill<<<afx::Solver::blocks(S.G), 256, 0, S.st>>>(S.q.p, S.bghost.p, S.bowner.p, S.bstate.p, S.G, 0);
+            S.kt->ghost_fill(S.q.p, S.bghost.p, S.bowner.p, S.bstate.p, S.G, 0, S.st);
             ++S.launches;
         }
         S.sync_ghost_rows();
@@ -731,7 +733,7 @@ int afx_rans_bcs_from_internal(afx_rans* s)
         auto& S = s->s;
         S.use();
         if (S.G) {
-            afx::k_ghost_fill<<<afx::Solver::blocks(S.G), 256, 0, S.st>>>(S.q.p, S.bghost.p, S.bowner.p, S.bstate.p, S.G, 1);
+            S.kt->ghost_fill(S.q.p, S.bghost.p, S.bowner.p, S.bstate.p, S.G, 1, S.st);
             ++S.launches;
         }
         S.sync_ghost_rows();
@@ -771,7 +773,7 @@ int afx_rans_get_field(afx_rans* s, int field, double* out)
             case AFX_F_LIMITERS: S.to_ref_order4(S.lim.p, out); break;
             case AFX_F_RHS: S.to_ref_order4(S.rhs.p, out); break;
             case AFX_F_DT: {
-                afx::k_permute1<<<afx::Solver::blocks(S.NT), 256, 0, S.st>>>(S.dt.p, S.dt_ref.p, S.perm_c_old2new.p, S.NT, S.N);
+                S.kt->permute1(S.dt.p, S.dt_ref.p, S.perm_c_old2new.p, S.NT, S.N, S.st);
                 ++S.launches;
                 CK(cudaMemcpyAsync(out, S.dt_ref.p, (size_t)S.NT * sizeof(double), cudaMemcpyDeviceToHost, S.st));
                 CK(cudaStreamSynchronize(S.st));
@@ -908,8 +910,8 @@ int afx_rans_wall_forces(afx_rans* s, int patch, double out[3])
         if (!n_added) throw afx::InvalidArg("patch has no boundary edges");
         ym /= (double)n_added;
         const double xm = (xmax - xmin) * 0.25 + xmin;
-        afx::k_wall_forces<<<1, 256, 0, S.st>>>(S.bface.p, S.bpatch.p, S.G, patch, S.dm, S.q.p, S.bcx.p, S.bcy.p, S.gas.gamma,
-                                                far.p, far.mach, xmin, xmax, xm, ym, S.scratch.p, nullptr);
+        S.kt->wall_forces(afx::WallArgs{S.bface.p, S.bpatch.p, S.G, patch, S.bcx.p, S.bcy.p, S.gas.gamma, far.p, far.mach, xmin, xmax, xm, ym,
+                                        S.scratch.p, nullptr}, S.dm, S.q.p, S.st);
         ++S.launches;
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(S.h_pinned + 16, S.scratch.p, 3 * sizeof(double), cudaMemcpyDeviceToHost, S.st));
@@ -933,8 +935,8 @@ int afx_rans_wall_cp(afx_rans* s, int patch, double* cp)
         S.boundary_variables(&far);
         afx::DBuf<double> d_cp;
         d_cp.alloc(S.G);
-        afx::k_wall_forces<<<1, 256, 0, S.st>>>(S.bface.p, S.bpatch.p, S.G, patch, S.dm, S.q.p, S.bcx.p, S.bcy.p, S.gas.gamma,
-                                                far.p, far.mach, 0., 1., 0., 0., S.scratch.p, d_cp.p);
+        S.kt->wall_forces(afx::WallArgs{S.bface.p, S.bpatch.p, S.G, patch, S.bcx.p, S.bcy.p, S.gas.gamma, far.p, far.mach, 0., 1., 0., 0.,
+                                        S.scratch.p, d_cp.p}, S.dm, S.q.p, S.st);
         ++S.launches;
         std::vector<double> h(S.G);
         CK(cudaMemcpyAsync(h.data(), d_cp.p, S.G * sizeof(double), cudaMemcpyDeviceToHost, S.st));

@@ -1,0 +1,77 @@
+// rans_types.h -- types shared by the host solver and the two kernel
+// translation units (strict / fast arithmetic, see rans_kernels_tu.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+
+namespace afx {
+
+// 32-byte aligned 4-vector: one LDG.E.256 / STG.E.256 per cell state on sm_100a
+struct __align__(32) d4 {
+    double x, y, z, w;
+};
+
+struct GasC {
+    double gamma, R, mu_L, Pr_L, cp;
+};
+
+enum : int { K_INTERNAL = 0, K_FARFIELD = 1, K_SLIPWALL = 2, K_WALL = 3 };
+
+constexpr uint32_t CF_NONE = 0xFFFFFFFFu;
+constexpr uint32_t CF_SIDE = 0x80000000u;  // this cell is cell1 of the face
+constexpr uint32_t CF_BND = 0x40000000u;   // boundary face (cell1 is a ghost)
+constexpr uint32_t CF_ID = 0x3FFFFFFFu;
+constexpr unsigned int NORM_RING = 1u << 16;  // capacity of the device-side residual history ring
+
+struct DevMesh {
+    uint32_t N, G, E, NT;        // real cells, ghosts, faces, N+G
+    const uint2* fcells;         // [E]
+    const d4* fgA;               // [E] nx, ny, len, w
+    const d4* fgB;               // [E] d0x, d0y, d1x, d1y
+    const d4* ftij;              // [E] t0, t1, l, - (laminar face-gradient direction, solver.h:369-376)
+    const uint8_t* fkind;        // [E]
+    const uint32_t* cf;          // [4][N]
+    const double* area;          // [NT]
+    const double* lsqM;          // [8][N]  (M * dT) rows in cellsEdges order, LSQ only
+    const uint16_t* lsq_perm;    // [N] bits 0-7: slot of local side j (2 bits each), bits 8-10: number of sides
+};
+
+struct NormOut {
+    double* partial;        // [gridDim.x]
+    unsigned int* counter;  // block counter
+    double* norms;          // [NORM_RING]
+    unsigned int* norm_idx; // running index into norms
+};
+
+struct WallArgs {
+    const uint32_t* bface; const int32_t* bpatch; uint32_t G; int patch;
+    const double* bcx; const double* bcy;
+    double gam, p_inf, mach_inf, xmin, xmax, x_moment, y_moment;
+    double* out3; double* cp_out;
+};
+
+// Launchers of one arithmetic mode.  Every function enqueues exactly one kernel on `st`.
+struct KernelTable {
+    const char* name;
+    void (*dt_grad)(int grad_scheme, const DevMesh& m, d4* q, double* dt, d4* gx, d4* gy, const double* prm, double gam,
+                    int want_grad, int walls, cudaStream_t st);
+    void (*limiter)(const DevMesh& m, const d4* qk, const d4* gx, const d4* gy, d4* lim, double limiter_k, cudaStream_t st);
+    void (*flux)(int second, int visc, int uniform, const DevMesh& m, const d4* qk, const d4* q0, const d4* gx, const d4* gy,
+                 const d4* lim, d4* flux, const GasC& g, d4 qfar, cudaStream_t st);
+    void (*gather)(int mode, int last, const DevMesh& m, const d4* flux, const d4* q, const d4* qk_in, d4* qk_out,
+                   const double* dt, d4* vec_out, double alpha, const double* prm, int walls, const NormOut& no, cudaStream_t st);
+    void (*jacobian)(int visc, const DevMesh& m, const d4* q, const d4* gx, const d4* gy, d4* J, const GasC& g, cudaStream_t st);
+    void (*jac_diag)(const DevMesh& m, const d4* J, const double* dt, double* D, cudaStream_t st);
+    void (*wall_forces)(const WallArgs& a, const DevMesh& m, const d4* q, cudaStream_t st);
+    void (*fill_cells)(d4* q, uint32_t n, d4 v, cudaStream_t st);
+    void (*ghost_fill)(d4* q, const uint32_t* bghost, const uint32_t* bowner, const d4* bstate, uint32_t G, int from_owner, cudaStream_t st);
+    void (*permute4)(const d4* src, d4* dst, const uint32_t* idx, uint32_t n, cudaStream_t st);
+    void (*permute1)(const double* src, double* dst, const uint32_t* idx, uint32_t n, uint32_t nsrc, cudaStream_t st);
+};
+
+namespace strict { const KernelTable& table(); }  // -fmad=false, reference expression order: bit-identical to the CPU reference
+namespace fast { const KernelTable& table(); }    // shared reciprocals + FMA contraction: ~1e-15 relative per face
+
+}  // namespace afx

@@ -116,6 +116,7 @@ def main():
     ap.add_argument("--workload", default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--math", default="fast", choices=["fast", "strict"])
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -150,7 +151,8 @@ def main():
     ni, nj, nq = WORKLOADS[workload]
     mesh = afx.Mesh.synth_omesh(ni, nj, nq, 150.0)
     N, G, E = mesh.N, mesh.G, mesh.E
-    s = afx.GpuSolver(mesh, viscosity=VISC, device=local)
+    s = afx.GpuSolver(mesh, viscosity=VISC, device=local, math=a.math)
+    config["math"] = a.math + (" (shared reciprocals + FMA; parity 1e-10 tested)" if a.math == "fast" else " (bit-identical to the CPU reference)")
     s.set_bcs(BCS); s.set_options(SECOND, GRAD, LIMK, CFL); s.init(); s.refill_bcs()
     q0 = perturbed(s.get_q(), N)
     s.set_q(q0)

@@ -49,6 +49,11 @@ enum { AFX_BC_INTERNAL = 0, AFX_BC_FARFIELD = 1, AFX_BC_SLIPWALL = 2, AFX_BC_WAL
 enum { AFX_VISC_INVISCID = 0, AFX_VISC_LAMINAR = 1, AFX_VISC_SA = 2 };
 /* Settings::gradient_options (core.h:175), by meaning not by index */
 enum { AFX_GRAD_GREEN_GAUSS = 0, AFX_GRAD_LEAST_SQUARES = 1 };
+/* arithmetic mode of the kernels.  STRICT: the reference's expression order, no FMA contraction -> vectors are
+ * bit-identical to the CPU reference built without -march (its default).  FAST (default): the same formulas
+ * with reciprocals shared between divisions by one denominator and FMA contraction; every face flux agrees
+ * with STRICT to a few ulp, residual histories to ~1e-13 relative (BASELINE tolerance: 1e-10). */
+enum { AFX_MATH_STRICT = 0, AFX_MATH_FAST = 1 };
 /* fields readable with afx_rans_get_field (solver.h:54-69) */
 enum { AFX_F_Q = 0, AFX_F_QW = 1, AFX_F_GX = 2, AFX_F_GY = 3, AFX_F_LIMITERS = 4, AFX_F_DT = 5, AFX_F_RHS = 6 };
 
@@ -134,6 +139,9 @@ void afx_rans_destroy(afx_rans* s);
 int afx_rans_set_bcs(afx_rans* s, int n_patch, const uint8_t* patch_kind, const afx_bvars* patch_vars);
 /* set_second_order / set_gradient_scheme / set_limiter_k (solver.h:135,149-152,162) */
 int afx_rans_set_options(afx_rans* s, int second_order, int gradient_scheme, double limiter_k);
+/* arithmetic mode (AFX_MATH_*); the environment variable AFX_MATH=strict|fast sets the default at creation */
+int afx_rans_set_math_mode(afx_rans* s, int mode);
+int afx_rans_get_math_mode(afx_rans* s);
 /* solver::set_cfl (solver.h:250-252) */
 int afx_rans_set_cfl(afx_rans* s, double cfl);
 /* solver::init / refill_bcs / bcs_from_internal (solver.h:615-631, 259-287) */

@@ -23,9 +23,9 @@ NORM_RTOL = 1e-12   # north_star: 1e-10 relative over the first 100 iterations
 FORCE_RTOL = 1e-12  # north_star: 1e-8 relative on CL/CD/CM
 
 
-def gpu_solver(afx, d, **kw):
+def gpu_solver(afx, d, math="strict", **kw):
     m = H.product_mesh(afx, d)
-    s = afx.GpuSolver(m, viscosity=d["meta"]["viscosity"], **kw)
+    s = afx.GpuSolver(m, viscosity=d["meta"]["viscosity"], math=math, **kw)
     H.setup_solver(s, d["meta"])
     return m, s
 
@@ -100,7 +100,7 @@ def test_synthetic_mixed_mesh_vs_oracle(afx, gpu, visc, grad, so, wall):
     x, y, cells, b0, b1 = m.elements()
     om = orc.OracleMesh(x, y, cells, m.is_tri, b0, b1, m.bnd_patch, m.patch_names, fast=False)
     bcs = {"farfield": ("farfield", dict(mach=0.2, angle=2 * 0.01745, T=1.0, p=1.0)), "wall": (wall, None)}
-    s = afx.GpuSolver(m, viscosity=visc); o = orc.OracleSolver(om, viscosity=visc)
+    s = afx.GpuSolver(m, viscosity=visc, math="strict"); o = orc.OracleSolver(om, viscosity=visc)
     for z in (s, o):
         z.set_bcs(bcs); z.set_options(so, grad, 5.0, 1.2); z.init(); z.refill_bcs()
     q0 = H.synth_state(m.N, o.q.copy(), amp=1e-4 if visc == "laminar" else 1e-3)
@@ -117,7 +117,7 @@ def test_unknown_bc_type_is_a_two_sided_face(afx, gpu):
     """solver.h:211-212,237-238: a bc_type that is none of the three names leaves an internal flux against the ghost cell."""
     d = H.load("naca0012q_coarse_euler_gg_o2")
     meta = dict(d["meta"]); bcs = dict(meta["bcs"]); bcs["wall"] = ("inlet-outlet", None); meta["bcs"] = bcs
-    m = H.product_mesh(afx, d); s = afx.GpuSolver(m); H.setup_solver(s, meta)
+    m = H.product_mesh(afx, d); s = afx.GpuSolver(m, math="strict"); H.setup_solver(s, meta)
     om = H.oracle_mesh(d); o = orc.OracleSolver(om); H.setup_solver(o, meta)
     for z in (s, o):
         z.init(); z.refill_bcs()
@@ -163,7 +163,7 @@ def test_renumbering_is_invisible(afx, gpu, monkeypatch):
     outs = []
     for order in ("hilbert", "none"):
         monkeypatch.setenv("AFX_ORDER", order)
-        s = afx.GpuSolver(m)
+        s = afx.GpuSolver(m, math="strict")
         s.set_bcs(bcs); s.set_options(True, "green-gauss", 5.0, 1.5); s.init(); s.refill_bcs()
         s.set_q(H.synth_state(m.N, s.get_q()))
         n = s.run(5, 0.9)
@@ -178,7 +178,7 @@ def test_graph_replay_equals_plain_launches(afx, gpu, monkeypatch):
     outs = []
     for ng in ("0", "1"):
         monkeypatch.setenv("AFX_NO_GRAPH", ng)
-        s = afx.GpuSolver(m, viscosity="spallart-allmaras")
+        s = afx.GpuSolver(m, viscosity="spallart-allmaras", math="strict")
         s.set_bcs(bcs); s.set_options(True, "green-gauss", 5.0, 1.5); s.init(); s.refill_bcs()
         s.set_q(H.synth_state(m.N, s.get_q()))
         outs.append((s.run(7, 0.9), s.get_q(), s.launch_count()))
@@ -194,7 +194,7 @@ def test_full_size_mesh_vs_oracle_and_conservation(afx, gpu):
     x, y, cells, b0, b1 = m.elements()
     om = orc.OracleMesh(x, y, cells, m.is_tri, b0, b1, m.bnd_patch, m.patch_names)
     bcs = {"farfield": ("farfield", dict(mach=0.2, angle=0.01745, T=1.0, p=1.0)), "wall": ("wall", None)}
-    s = afx.GpuSolver(m, viscosity="spallart-allmaras"); o = orc.OracleSolver(om, viscosity="spallart-allmaras")
+    s = afx.GpuSolver(m, viscosity="spallart-allmaras", math="strict"); o = orc.OracleSolver(om, viscosity="spallart-allmaras")
     for z in (s, o):
         z.set_bcs(bcs); z.set_options(True, "green-gauss", 5.0, 1.5); z.init(); z.refill_bcs()
     q0 = H.synth_state(m.N, o.q.copy())
@@ -218,3 +218,47 @@ def test_full_size_mesh_vs_oracle_and_conservation(afx, gpu):
     s.set_q(q0); a = s.run(3, 0.9); qa = s.get_q()
     s.set_q(q0); b = s.run(3, 0.9); qb = s.get_q()
     assert np.array_equal(a, b) and np.array_equal(qa, qb)
+    # (d) the fast arithmetic mode (what bench.py times) on the same input: inside the north-star tolerances
+    f = afx.GpuSolver(m, viscosity="spallart-allmaras", math="fast")
+    f.set_bcs(bcs); f.set_options(True, "green-gauss", 5.0, 1.5); f.set_q(q0)
+    c = f.run(3, 0.9)
+    np.testing.assert_allclose(c, a, rtol=1e-10, atol=0)
+    np.testing.assert_allclose(f.get_q(), qa, rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(f.wall_forces("wall"), s.wall_forces("wall"), rtol=1e-8, atol=1e-12)
+
+
+# ---------------------------------------------------------------------------
+# fast arithmetic mode (default; shared reciprocals + FMA contraction): BASELINE.json tolerances
+# ---------------------------------------------------------------------------
+HIST_RTOL = 1e-10   # per-iteration residual norms over the first 100 iterations
+CLCD_RTOL = 1e-8    # CL / CD / CM
+
+
+@pytest.mark.parametrize("tag", H.EXPLICIT_CASES)
+def test_fast_mode_history_vs_reference_golden(afx, gpu, tag):
+    d = H.load(tag)
+    meta = d["meta"]
+    m, s = gpu_solver(afx, d, math="fast")
+    assert s.math == "fast"
+    assert s.get_uniform_residual() == pytest.approx(float(d["uniform_residual_fresh"]), rel=HIST_RTOL)
+    s.set_q(d["q0"])
+    norms = s.run(meta["n_iter"], meta["relax"])
+    np.testing.assert_allclose(norms, d["norms"], rtol=HIST_RTOL, atol=0)
+    np.testing.assert_allclose(s.wall_forces(str(d["forces_patch"])), d["forces"], rtol=CLCD_RTOL, atol=1e-13)
+    if "qN" in d:
+        np.testing.assert_allclose(s.get_q(), d["qN"], rtol=1e-10, atol=1e-13)
+
+
+@pytest.mark.parametrize("tag", H.IMPLICIT_CASES)
+def test_fast_mode_rhs_and_jacobian(afx, gpu, tag):
+    d = H.load(tag)
+    m, s = gpu_solver(afx, d, math="fast")
+    s.set_q(d["q0"])
+    assert s.residual() == pytest.approx(float(d["rhs_norm"]), rel=HIST_RTOL)
+    scale = np.abs(d["rhs"]).max()
+    np.testing.assert_allclose(s.get("rhs"), d["rhs"], rtol=1e-9, atol=1e-12 * scale)
+    s.fill_jacobian()
+    dg, o01, o10 = s.jacobian_blocks()
+    # forward differences with eps = 1e-6 amplify rounding by 1e6: a few 1e-10 absolute on O(1) entries
+    np.testing.assert_allclose(dg[d["diag_idx"]], d["diag_blk"], rtol=1e-6, atol=1e-8 * np.abs(d["diag_blk"]).max())
+    np.testing.assert_allclose(o01[d["edge_idx"]], d["off01_blk"], rtol=1e-6, atol=1e-8 * np.abs(d["off01_blk"]).max())
