@@ -29,6 +29,8 @@ EXPORTED_SYMBOLS = [
     "afx_mesh_read_msh", "afx_mesh_from_elements", "afx_mesh_synth_omesh", "afx_mesh_free", "afx_mesh_get_desc",
     "afx_mesh_n_nodes", "afx_mesh_n_patches", "afx_mesh_patch_name", "afx_mesh_patch_id", "afx_mesh_get_elements",
     "afx_mesh_write_msh",
+    "afx_partition_create", "afx_partition_free", "afx_partition_get_desc", "afx_partition_info", "afx_partition_cell_l2g",
+    "afx_partition_edge_l2g", "afx_partition_peer", "afx_nccl_unique_id", "afx_rans_create_partitioned",
     "afx_rans_create", "afx_rans_destroy", "afx_rans_set_bcs", "afx_rans_set_options", "afx_rans_set_cfl",
     "afx_rans_set_math_mode", "afx_rans_get_math_mode",
     "afx_rans_init", "afx_rans_refill_bcs", "afx_rans_bcs_from_internal", "afx_rans_set_q", "afx_rans_get_q",
@@ -78,6 +80,8 @@ UNITS = [("rans_kernels_tu.cu", "kernels_strict.o", ["-DAFX_FAST=0", "-fmad=fals
          ("rans_kernels_tu.cu", "kernels_fast.o", ["-DAFX_FAST=1", "-fmad=true"]),
          ("rans_solver.cu", "rans_solver.o", ["-fmad=false"]),
          ("mesh_host.cpp", "mesh_host.o", []),
+         ("ordering.cpp", "ordering.o", []),
+         ("partition.cpp", "partition.o", []),
          ("mesh_capi.cpp", "mesh_capi.o", [])]
 
 
@@ -103,7 +107,7 @@ def build_library(force=False, verbose=False, defines=(), out=None):
     with ThreadPoolExecutor(len(UNITS)) as ex:
         list(ex.map(cc, UNITS))
     subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", "/usr/bin/g++", "-shared", "-o", out] +
-                   [os.path.join(bdir, u[1]) for u in UNITS] + ["-lgomp"], check=True)
+                   [os.path.join(bdir, u[1]) for u in UNITS] + ["-lgomp", "-ldl"], check=True)
     return out
 
 
@@ -140,6 +144,17 @@ def load_library():
     L.afx_mesh_get_elements.argtypes = [vp] * 6
     L.afx_mesh_write_msh.argtypes = [vp, C.c_char_p]
     L.afx_rans_create.argtypes = [C.POINTER(vp), C.POINTER(MeshDesc), C.POINTER(Gas), C.c_int, C.c_int]
+    L.afx_partition_create.argtypes = [C.POINTER(vp), C.POINTER(MeshDesc), C.c_int, C.c_int]
+    L.afx_partition_free.argtypes = [vp]
+    L.afx_partition_get_desc.argtypes = [vp, C.POINTER(MeshDesc)]
+    L.afx_partition_info.argtypes = [vp, u32p]
+    L.afx_partition_cell_l2g.restype = u32p
+    L.afx_partition_cell_l2g.argtypes = [vp]
+    L.afx_partition_edge_l2g.restype = u32p
+    L.afx_partition_edge_l2g.argtypes = [vp]
+    L.afx_partition_peer.argtypes = [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(u32p), u32p, C.POINTER(u32p), u32p]
+    L.afx_nccl_unique_id.argtypes = [C.c_char_p]
+    L.afx_rans_create_partitioned.argtypes = [C.POINTER(vp), vp, C.POINTER(Gas), C.c_int, C.c_int, C.c_char_p]
     L.afx_rans_destroy.argtypes = [vp]
     L.afx_rans_set_bcs.argtypes = [vp, C.c_int, vp, C.POINTER(BVars)]
     L.afx_rans_set_options.argtypes = [vp, C.c_int, C.c_int, C.c_double]
@@ -288,10 +303,59 @@ class Mesh:
         _check(self.L.afx_mesh_write_msh(self.h, str(path).encode()))
 
 
+class Partition:
+    """One rank's piece of a mesh: owned | ring 1 | ring 2 cells + its boundary ghosts, and the exchange plan."""
+
+    def __init__(self, mesh, nranks, rank):
+        self.L = load_library()
+        self.global_mesh = mesh
+        self.h = C.c_void_p()
+        _check(self.L.afx_partition_create(C.byref(self.h), C.byref(mesh.d), nranks, rank))
+        info = (C.c_uint32 * 8)()
+        self.L.afx_partition_info(self.h, info)
+        self.n_own, self.n_r1, self.n_r2, self.n_bc, self.n_edges, self.n_peers, self.rank, self.nranks = (int(v) for v in info)
+        self.d = MeshDesc()
+        _check(self.L.afx_partition_get_desc(self.h, C.byref(self.d)))
+        self.N, self.G, self.E = self.d.n_cells, self.d.n_ghost, self.d.n_edges
+        self.patch_names = list(mesh.patch_names)
+        self.cell_l2g = np.ctypeslib.as_array(self.L.afx_partition_cell_l2g(self.h), shape=(self.N + self.G,)).copy()
+        self.edge_l2g = np.ctypeslib.as_array(self.L.afx_partition_edge_l2g(self.h), shape=(self.E,)).copy()
+        self.peers = []
+        for i in range(self.n_peers):
+            r = C.c_int(); ns = C.c_uint32(); nr = C.c_uint32()
+            sp = C.POINTER(C.c_uint32)(); rp = C.POINTER(C.c_uint32)()
+            _check(self.L.afx_partition_peer(self.h, i, C.byref(r), C.byref(sp), C.byref(ns), C.byref(rp), C.byref(nr)))
+            send = np.ctypeslib.as_array(sp, shape=(ns.value,)).copy() if ns.value else np.zeros(0, np.uint32)
+            recv = np.ctypeslib.as_array(rp, shape=(nr.value,)).copy() if nr.value else np.zeros(0, np.uint32)
+            self.peers.append((r.value, send, recv))
+
+    def __del__(self):
+        try:
+            self.L.afx_partition_free(self.h)
+        except Exception:
+            pass
+
+    def local_arrays(self):
+        """numpy copies of the local mesh arrays (reference layout) -- what an independent solver needs."""
+        d, NT, E, N = self.d, self.N + self.G, self.E, self.N
+        a = lambda p, n: np.ctypeslib.as_array(p, shape=(n,)).copy()
+        return dict(edge_cells=a(d.edges_cells, 2 * E).reshape(-1, 2), enx=a(d.edges_nx, E), eny=a(d.edges_ny, E), elen=a(d.edges_len, E),
+                    ecx=a(d.edges_cx, E), ecy=a(d.edges_cy, E), ccx=a(d.cells_cx, NT), ccy=a(d.cells_cy, NT), area=a(d.cells_area, NT),
+                    cell_edges=a(d.cells_edges, 4 * N).reshape(-1, 4), is_tri=a(d.cells_is_tri, N),
+                    bnd_edge=a(d.boundary_edges, self.G) if self.G else np.zeros(0, np.uint32),
+                    bnd_patch=a(d.boundary_patch, self.G) if self.G else np.zeros(0, np.int32))
+
+
+def nccl_unique_id():
+    buf = C.create_string_buffer(128)
+    _check(load_library().afx_nccl_unique_id(buf))
+    return buf.raw
+
+
 class GpuSolver:
     """rans::solver on one B200 through the C ABI."""
 
-    def __init__(self, mesh, gas=None, viscosity="inviscid", device=0, math=None):
+    def __init__(self, mesh, gas=None, viscosity="inviscid", device=0, math=None, nccl_id=None):
         """math: "strict" (bit-identical to the CPU reference), "fast" (default; shared reciprocals + FMA) or None
         (library default / AFX_MATH)."""
         self.L = load_library()
@@ -301,7 +365,14 @@ class GpuSolver:
         if viscosity not in VISCOSITY:
             raise KeyError(viscosity)
         self.h = C.c_void_p()
-        _check(self.L.afx_rans_create(C.byref(self.h), C.byref(mesh.d), C.byref(self.gas), VISCOSITY[viscosity], device))
+        if isinstance(mesh, Partition):
+            # one piece of a partitioned mesh: mesh = Partition, nccl_id = the 128-byte id made on rank 0
+            self.partition = mesh
+            _check(self.L.afx_rans_create_partitioned(C.byref(self.h), mesh.h, C.byref(self.gas), VISCOSITY[viscosity], device, nccl_id))
+            mesh = mesh.global_mesh
+            self.mesh = mesh
+        else:
+            _check(self.L.afx_rans_create(C.byref(self.h), C.byref(mesh.d), C.byref(self.gas), VISCOSITY[viscosity], device))
         self.n4 = 4 * (mesh.N + mesh.G)
         self.bcs = {}
         if math is not None:
@@ -428,6 +499,6 @@ class GpuSolver:
         return int(self.L.afx_rans_launch_count(self.h))
 
     def profile_explicit(self, n_iter=5, relaxation=1.0):
-        out = np.zeros(4)
+        out = np.zeros(5)
         _check(self.L.afx_rans_profile_explicit(self.h, relaxation, n_iter, _ptr(out)))
-        return dict(dt_grad=out[0], limiter=out[1], flux=out[2], gather_update=out[3])
+        return dict(dt_grad=out[0], limiter=out[1], flux=out[2], gather_update=out[3], halo_exchange=out[4])

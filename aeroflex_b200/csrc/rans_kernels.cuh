@@ -19,10 +19,10 @@
 
 // resident CTAs per SM asked of ptxas for the two heavy kernels (register cap = 65536 / (256 * n))
 #ifndef AFX_FLUX_MINB
-#define AFX_FLUX_MINB 3
+#define AFX_FLUX_MINB 4
 #endif
 #ifndef AFX_LIM_MINB
-#define AFX_LIM_MINB 3
+#define AFX_LIM_MINB 4
 #endif
 
 namespace afx {
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256) k_dt_grad(DevMesh m, d4* __restrict__ q, 
                                                  double gam, int want_grad, int walls)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m.N) return;
+    if (i >= m.n_grad) return;
     const d4 qi = q[i];
     double dsum = 0;
     d4 ax = mk4(0, 0, 0, 0), ay = mk4(0, 0, 0, 0);
@@ -151,10 +151,10 @@ __device__ __forceinline__ double venkat(double dqg, double dmax, double dmin, d
 }
 
 __global__ void __launch_bounds__(256, AFX_LIM_MINB) k_limiter(DevMesh m, const d4* __restrict__ qk, const d4* __restrict__ gx,
-                                                 const d4* __restrict__ gy, d4* __restrict__ lim, double limiter_k)
+                                                 const d4* __restrict__ gy, d4* __restrict__ lim, double limiter_k, int walls)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m.N) return;
+    if (i >= m.n_grad) return;
     const d4 qi = qk[i];
     d4 lo = qi, hi = qi;
     uint32_t cfs[4];
@@ -164,7 +164,9 @@ __global__ void __launch_bounds__(256, AFX_LIM_MINB) k_limiter(DevMesh m, const 
         cfs[s] = cfv;
         if (cfv == CF_NONE) continue;
         const uint2 fc = m.fcells[cfv & CF_ID];
-        const d4 qj = qk[(cfv & CF_SIDE) ? fc.x : fc.y];
+        // a wall ghost holds its owner's state (set_walls_from_internal): no need to read it
+        const bool wall_ghost = walls && (cfv & CF_BND) && (m.fkind[cfv & CF_ID] == K_SLIPWALL || m.fkind[cfv & CF_ID] == K_WALL);
+        const d4 qj = wall_ghost ? qi : qk[(cfv & CF_SIDE) ? fc.x : fc.y];
         lo.x = fmin(lo.x, qj.x); lo.y = fmin(lo.y, qj.y); lo.z = fmin(lo.z, qj.z); lo.w = fmin(lo.w, qj.w);
         hi.x = fmax(hi.x, qj.x); hi.y = fmax(hi.y, qj.y); hi.z = fmax(hi.z, qj.z); hi.w = fmax(hi.w, qj.w);
     }
@@ -201,7 +203,7 @@ __global__ void __launch_bounds__(256, AFX_FLUX_MINB) k_flux(DevMesh m, const d4
                                               const d4* __restrict__ lim, d4* __restrict__ flux, GasC g, d4 qfar)
 {
     const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= m.E) return;
+    if (f >= m.e_flux) return;
     const uint2 fc = m.fcells[f];
     const d4 gA = m.fgA[f];
     const int kind = m.fkind[f];
@@ -247,9 +249,9 @@ __global__ void __launch_bounds__(256, AFX_FLUX_MINB) k_flux(DevMesh m, const d4
 // the last block to finish adds the partials in index order and stores the
 // square root (residual L2 norm, solver.h:827 / 1178).
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void block_norm_accumulate(double v, double* partial, unsigned int* counter,
-                                                      double* norms, unsigned int* norm_idx)
+__device__ __forceinline__ void block_norm_accumulate(double v, const NormOut& no)
 {
+    double* partial = no.partial; unsigned int* counter = no.counter; double* norms = no.norms; unsigned int* norm_idx = no.norm_idx;
     __shared__ double sh[32];
     __shared__ bool last;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
@@ -280,7 +282,7 @@ __device__ __forceinline__ void block_norm_accumulate(double v, double* partial,
             double u = lane < nw ? sh[lane] : 0.0;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) u += __shfl_down_sync(0xffffffffu, u, o);
-            if (lane == 0) { const unsigned int k = *norm_idx; norms[k % NORM_RING] = sqrt(u); *norm_idx = k + 1; *counter = 0; }
+            if (lane == 0) { const unsigned int k = *norm_idx; norms[k % NORM_RING] = no.store_square ? u : sqrt(u); *norm_idx = k + 1; *counter = 0; }
         }
     }
 }
@@ -301,12 +303,11 @@ __global__ void __launch_bounds__(256) k_gather_update(DevMesh m, const d4* __re
                                                        const d4* q, const d4* qk_in,
                                                        d4* qk_out, const double* __restrict__ dt,
                                                        d4* __restrict__ qW, double alpha, const double* __restrict__ prm,
-                                                       int walls, double* partial, unsigned int* counter, double* norms,
-                                                       unsigned int* norm_idx)
+                                                       int walls, NormOut no)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     double nrm = 0;
-    if (i < m.N) {
+    if (i < m.n_upd) {
         d4 r = mk4(0, 0, 0, 0);
         uint32_t bnd[4];
 #pragma unroll
@@ -346,7 +347,7 @@ __global__ void __launch_bounds__(256) k_gather_update(DevMesh m, const d4* __re
             nrm += r.x * r.x + r.y * r.y + r.z * r.z + r.w * r.w;
         }
     }
-    if (LAST) block_norm_accumulate(nrm, partial, counter, norms, norm_idx);
+    if (LAST) block_norm_accumulate(nrm, no);
 }
 
 // ---------------------------------------------------------------------------
@@ -463,6 +464,7 @@ __global__ void __launch_bounds__(256) k_wall_forces(WallArgs a, DevMesh m, cons
     for (uint32_t b = threadIdx.x; b < G; b += blockDim.x) {
         if (bpatch[b] != patch) continue;
         const uint32_t f = bface[b];
+        if (m.fcells[f].x >= m.n_upd) continue;  // the wall face of a halo cell belongs to another rank
         const d4 qc = q[m.fcells[f].x];
         const d4 gA = m.fgA[f];
         const double p = (gam - 1) * (qc.w - 0.5 / qc.x * (qc.y * qc.y + qc.z * qc.z));
@@ -508,6 +510,11 @@ __global__ void k_permute4(const d4* __restrict__ src, d4* __restrict__ dst, con
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = src[idx[i]];
 }
+__global__ void k_scatter4(const d4* __restrict__ src, d4* __restrict__ dst, const uint32_t* __restrict__ idx, uint32_t n)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[idx[i]] = src[i];
+}
 __global__ void k_permute1(const double* __restrict__ src, double* __restrict__ dst, const uint32_t* __restrict__ idx, uint32_t n, uint32_t nsrc)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -527,17 +534,17 @@ inline unsigned nblk(size_t n, unsigned bs = 256) { return (unsigned)((n + bs - 
 static void dt_grad(int grad, const DevMesh& m, d4* q, double* dt, d4* gx, d4* gy, const double* prm, double gam, int want_grad,
                     int walls, cudaStream_t st)
 {
-    if (grad == 0) k_dt_grad<0><<<nblk(m.N), 256, 0, st>>>(m, q, dt, gx, gy, prm, gam, want_grad, walls);
-    else k_dt_grad<1><<<nblk(m.N), 256, 0, st>>>(m, q, dt, gx, gy, prm, gam, want_grad, walls);
+    if (grad == 0) k_dt_grad<0><<<nblk(m.n_grad), 256, 0, st>>>(m, q, dt, gx, gy, prm, gam, want_grad, walls);
+    else k_dt_grad<1><<<nblk(m.n_grad), 256, 0, st>>>(m, q, dt, gx, gy, prm, gam, want_grad, walls);
 }
-static void limiter(const DevMesh& m, const d4* qk, const d4* gx, const d4* gy, d4* lim, double k, cudaStream_t st)
+static void limiter(const DevMesh& m, const d4* qk, const d4* gx, const d4* gy, d4* lim, double k, int walls, cudaStream_t st)
 {
-    k_limiter<<<nblk(m.N), 256, 0, st>>>(m, qk, gx, gy, lim, k);
+    k_limiter<<<nblk(m.n_grad), 256, 0, st>>>(m, qk, gx, gy, lim, k, walls);
 }
 static void flux(int second, int visc, int uniform, const DevMesh& m, const d4* qk, const d4* q0, const d4* gx, const d4* gy,
                  const d4* lim, d4* fl, const GasC& g, d4 qfar, cudaStream_t st)
 {
-    const unsigned nb = nblk(m.E);
+    const unsigned nb = nblk(m.e_flux);
 #define AFX_FLUX(S, V, U) k_flux<S, V, U><<<nb, 256, 0, st>>>(m, qk, q0, gx, gy, lim, fl, g, qfar)
     if (uniform) { if (visc) AFX_FLUX(0, 1, 1); else AFX_FLUX(0, 0, 1); }
     else if (second) { if (visc) AFX_FLUX(1, 1, 0); else AFX_FLUX(1, 0, 0); }
@@ -547,8 +554,8 @@ static void flux(int second, int visc, int uniform, const DevMesh& m, const d4* 
 static void gather(int mode, int last, const DevMesh& m, const d4* fl, const d4* q, const d4* qk_in, d4* qk_out, const double* dt,
                    d4* vec_out, double alpha, const double* prm, int walls, const NormOut& no, cudaStream_t st)
 {
-    const unsigned nb = nblk(m.N);
-#define AFX_G(M, L) k_gather_update<M, L><<<nb, 256, 0, st>>>(m, fl, q, qk_in, qk_out, dt, vec_out, alpha, prm, walls, no.partial, no.counter, no.norms, no.norm_idx)
+    const unsigned nb = nblk(m.n_upd);
+#define AFX_G(M, L) k_gather_update<M, L><<<nb, 256, 0, st>>>(m, fl, q, qk_in, qk_out, dt, vec_out, alpha, prm, walls, no)
     if (mode == 0) { if (last) AFX_G(0, 1); else AFX_G(0, 0); }
     else if (mode == 1) AFX_G(1, 1);
     else AFX_G(2, 1);
@@ -570,6 +577,7 @@ static void ghost_fill(d4* q, const uint32_t* bghost, const uint32_t* bowner, co
     k_ghost_fill<<<nblk(G), 256, 0, st>>>(q, bghost, bowner, bstate, G, from_owner);
 }
 static void permute4(const d4* src, d4* dst, const uint32_t* idx, uint32_t n, cudaStream_t st) { k_permute4<<<nblk(n), 256, 0, st>>>(src, dst, idx, n); }
+static void scatter4(const d4* src, d4* dst, const uint32_t* idx, uint32_t n, cudaStream_t st) { k_scatter4<<<nblk(n), 256, 0, st>>>(src, dst, idx, n); }
 static void permute1(const double* src, double* dst, const uint32_t* idx, uint32_t n, uint32_t nsrc, cudaStream_t st)
 {
     k_permute1<<<nblk(n), 256, 0, st>>>(src, dst, idx, n, nsrc);

@@ -16,12 +16,16 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <numeric>
 #include <stdexcept>
 #include <string>
 #include <vector>
 
 #include "../../include/afx_rans.h"
+#include "nccl_dl.h"
+#include "ordering.h"
+#include "partition.h"
 #include "rans_types.h"
 
 namespace afx {
@@ -36,6 +40,9 @@ struct InvalidArg : std::runtime_error {
     using std::runtime_error::runtime_error;
 };
 struct NumericError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+struct CommError : std::runtime_error {
     using std::runtime_error::runtime_error;
 };
 
@@ -67,20 +74,28 @@ struct DBuf {
     ~DBuf() { free(); }
 };
 
-// ---- Hilbert index on rank coordinates -----------------------------------
-static uint64_t hilbert_d(uint32_t x, uint32_t y, int order)
-{
-    uint64_t d = 0;
-    for (uint32_t s = 1u << (order - 1); s > 0; s >>= 1) {
-        const uint32_t rx = (x & s) ? 1 : 0, ry = (y & s) ? 1 : 0;
-        d += (uint64_t)s * s * ((3 * rx) ^ ry);
-        if (ry == 0) {
-            if (rx == 1) { x = s - 1 - (x & (s - 1)) + (x & ~(2 * s - 1)); y = s - 1 - (y & (s - 1)) + (y & ~(2 * s - 1)); }
-            const uint32_t t = x; x = y; y = t;
-        }
-    }
-    return d;
-}
+#define NK(call)                                                                                     \
+    do {                                                                                             \
+        ncclResult_t r_ = (call);                                                                    \
+        if (r_ != ncclSuccess)                                                                       \
+            throw ::afx::CommError(std::string(#call) + ": " + ::afx::NcclApi::get().GetErrorString(r_) + " (" + __FILE__ + ":" + \
+                                   std::to_string(__LINE__) + ")");                                  \
+    } while (0)
+
+// halo exchange of one partitioned solver: one NCCL communicator, packed sends, scattered receives
+struct Halo {
+    ncclComm_t comm = nullptr;
+    int rank = 0, nranks = 1;
+    struct Peer { int rank; uint32_t send_off, send_cnt, recv_off, recv_cnt; };
+    std::vector<Peer> peers;
+    DBuf<uint32_t> send_idx, recv_idx;  // internal cell ids, all peers back to back
+    DBuf<d4> send_buf, recv_buf;
+    uint32_t n_send = 0, n_recv = 0;
+    // global patch extents for the force integrals
+    std::vector<double> patch_xmin, patch_xmax, patch_ysum;
+    std::vector<uint32_t> patch_count;
+    ~Halo() { if (comm) NcclApi::get().CommDestroy(comm); }
+};
 
 struct Solver {
     int device = 0;
@@ -88,6 +103,10 @@ struct Solver {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t evp[16] = {};
     uint32_t N = 0, G = 0, E = 0, NT = 0;
+    uint32_t n_upd = 0, n_grad = 0, e_flux = 0;  // sub-ranges of a partition (== N, N, E on one GPU)
+    std::unique_ptr<Halo> halo;                  // null on one GPU
+    std::vector<uint32_t> cell_l2g;              // partitioned: local reference-order cell -> global cell
+    uint32_t n_global = 0;                       // partitioned: global N+G
     GasC gas{};
     int viscosity_model = 0, viscous_type = 0, visc_not_inviscid = 0;
     int second_order = 1, gradient_scheme = AFX_GRAD_GREEN_GAUSS;
@@ -128,7 +147,7 @@ struct Solver {
 
     DevMesh dm{};
     const KernelTable* kt = &fast::table();  // arithmetic mode, see afx_rans_set_math_mode
-    NormOut norm_out() { return NormOut{partial.p, counters.p, norms.p, counters.p + 1}; }
+    NormOut norm_out() { return NormOut{partial.p, counters.p, norms.p, counters.p + 1, halo ? 1 : 0}; }
     void set_math_mode(int mode)
     {
         if (mode != AFX_MATH_STRICT && mode != AFX_MATH_FAST) throw InvalidArg("unknown math mode");
@@ -150,7 +169,10 @@ struct Solver {
     void use() { CK(cudaSetDevice(device)); }
     static unsigned blocks(size_t n, unsigned bs = 256) { return (unsigned)((n + bs - 1) / bs); }
 
-    void create(const afx_mesh_desc& m, const afx_gas& g, int visc, int dev);
+    void create(const afx_mesh_desc& m, const afx_gas& g, int visc, int dev, const Partition* part = nullptr);
+    void init_halo(const Partition& part, const char* nccl_id);
+    void exchange(d4* field);
+    void reduce_norms(double* v, int n);
     void set_bcs(int n_patch, const uint8_t* kinds, const afx_bvars* vars);
     void set_options(int so, int grad, double k);
     void push_params(double relax);
@@ -194,7 +216,7 @@ bool Solver::boundary_variables(afx_bvars* out) const
     return false;
 }
 
-void Solver::create(const afx_mesh_desc& m, const afx_gas& g, int visc, int dev)
+void Solver::create(const afx_mesh_desc& m, const afx_gas& g, int visc, int dev, const Partition* part)
 {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -214,6 +236,8 @@ void Solver::create(const afx_mesh_desc& m, const afx_gas& g, int visc, int dev)
 
     N = m.n_cells; G = m.n_ghost; E = m.n_edges; NT = N + G;
     if (!N || !E) throw InvalidArg("empty mesh");
+    n_upd = part ? part->n_own : N;
+    n_grad = part ? part->n_own + part->n_r1 : N;
     if (E > CF_ID) throw InvalidArg("too many edges for the 30-bit face index");
     gas = GasC{g.gamma, g.R, g.mu_L, g.Pr_L, g.cp};
     viscosity_model = visc;
@@ -227,20 +251,8 @@ void Solver::create(const afx_mesh_desc& m, const afx_gas& g, int visc, int dev)
     {
         std::vector<uint32_t> idx(N);
         std::iota(idx.begin(), idx.end(), 0u);
-        if (hilbert && N > 64) {
-            std::vector<uint32_t> rx(N), ry(N), tmp(N);
-            std::iota(tmp.begin(), tmp.end(), 0u);
-            std::stable_sort(tmp.begin(), tmp.end(), [&](uint32_t a, uint32_t b) { return m.cells_cx[a] < m.cells_cx[b]; });
-            for (uint32_t r = 0; r < N; ++r) rx[tmp[r]] = r;
-            std::iota(tmp.begin(), tmp.end(), 0u);
-            std::stable_sort(tmp.begin(), tmp.end(), [&](uint32_t a, uint32_t b) { return m.cells_cy[a] < m.cells_cy[b]; });
-            for (uint32_t r = 0; r < N; ++r) ry[tmp[r]] = r;
-            int order = 1;
-            while ((1u << order) < N && order < 31) ++order;
-            std::vector<uint64_t> key(N);
-            for (uint32_t i = 0; i < N; ++i) key[i] = hilbert_d(rx[i], ry[i], order);
-            std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return key[a] < key[b]; });
-        }
+        // a partition arrives in curve order inside each class (owned | ring 1 | ring 2) and must keep its classes
+        if (hilbert && N > 64 && !part) idx = hilbert_order(m.cells_cx, m.cells_cy, idx);
         for (uint32_t n = 0; n < N; ++n) { c_new2old[n] = idx[n]; c_old2new[idx[n]] = n; }
         // ghosts follow their owners
         std::vector<uint32_t> gb(G);
@@ -266,6 +278,8 @@ void Solver::create(const afx_mesh_desc& m, const afx_gas& g, int visc, int dev)
         }
         std::stable_sort(fi.begin(), fi.end(), [&](uint32_t a, uint32_t b) { return key[a] < key[b]; });
         for (uint32_t n = 0; n < E; ++n) { f_new2old[n] = fi[n]; f_old2new[fi[n]] = n; }
+        e_flux = 0;
+        while (e_flux < E && key[fi[e_flux]] < n_upd) ++e_flux;  // faces touching an advanced cell come first
     }
     // ---- face records ----
     std::vector<uint2> h_fc(E); std::vector<d4> h_gA(E), h_gB(E), h_t(E);
@@ -297,7 +311,7 @@ void Solver::create(const afx_mesh_desc& m, const afx_gas& g, int visc, int dev)
     std::vector<uint16_t> h_perm(N, 0);
     std::vector<double> h_area(NT);
     for (uint32_t n = 0; n < NT; ++n) h_area[n] = m.cells_area[c_new2old[n]];
-    for (uint32_t n = 0; n < N; ++n) {
+    for (uint32_t n = 0; n < n_grad; ++n) {
         const uint32_t o = c_new2old[n];
         const uint32_t sz = m.cells_is_tri[o] ? 3u : 4u;
         uint32_t es[4]; int order[4] = {0, 1, 2, 3};
@@ -353,7 +367,7 @@ void Solver::create(const afx_mesh_desc& m, const afx_gas& g, int visc, int dev)
     // least-squares coefficients (M * dT), rows in cellsEdges order, solver.h:402-422 + 504
     {
         std::vector<double> h_M((size_t)8 * N, 0.);
-        for (uint32_t n = 0; n < N; ++n) {
+        for (uint32_t n = 0; n < n_grad; ++n) {
             const uint32_t o = c_new2old[n];
             const uint32_t sz = m.cells_is_tri[o] ? 3u : 4u;
             double d[4][2], a00 = 0, a01 = 0, a10 = 0, a11 = 0;
@@ -376,6 +390,7 @@ void Solver::create(const afx_mesh_desc& m, const afx_gas& g, int visc, int dev)
     CK(cudaStreamSynchronize(st));
 
     dm.N = N; dm.G = G; dm.E = E; dm.NT = NT;
+    dm.n_upd = n_upd; dm.n_grad = n_grad; dm.e_flux = e_flux;
     dm.fcells = fcells.p; dm.fgA = fgA.p; dm.fgB = fgB.p; dm.ftij = ftij.p; dm.fkind = fkind.p;
     dm.cf = cf.p; dm.area = area.p; dm.lsqM = lsqM.p; dm.lsq_perm = lsq_perm.p;
 }
@@ -430,7 +445,7 @@ void Solver::launch_dt_grad(bool want_grad, bool walls)
 
 void Solver::launch_limiter(const d4* qk)
 {
-    kt->limiter(dm, qk, gx.p, gy.p, lim.p, limiter_k, st);
+    kt->limiter(dm, qk, gx.p, gy.p, lim.p, limiter_k, (visc_not_inviscid || second_order) ? 1 : 0, st);
     ++launches;
 }
 
@@ -461,7 +476,62 @@ void Solver::explicit_iteration()
         launch_flux(in[s], false, d4{0, 0, 0, 0});
         if (s < 2) launch_gather<0, 0>(in[s], out[s], qW.p, alpha[s], grads);
         else launch_gather<0, 1>(in[s], out[s], qW.p, alpha[s], grads);
+        if (halo) exchange(out[s]);  // ring cells of the new stage state
     }
+}
+
+// NCCL halo: the ring cells' states come from their owners after every stage
+void Solver::init_halo(const Partition& part, const char* nccl_id)
+{
+    halo.reset(new Halo);
+    Halo& h = *halo;
+    h.rank = part.rank; h.nranks = part.nranks;
+    h.patch_xmin = part.patch_xmin; h.patch_xmax = part.patch_xmax; h.patch_ysum = part.patch_ysum; h.patch_count = part.patch_count;
+    std::vector<uint32_t> si, ri;
+    for (const auto& p : part.peers) {
+        Halo::Peer q{p.rank, (uint32_t)si.size(), (uint32_t)p.send.size(), (uint32_t)ri.size(), (uint32_t)p.recv.size()};
+        for (uint32_t c : p.send) si.push_back(c_old2new[c]);
+        for (uint32_t c : p.recv) ri.push_back(c_old2new[c]);
+        h.peers.push_back(q);
+    }
+    h.n_send = (uint32_t)si.size(); h.n_recv = (uint32_t)ri.size();
+    if (si.empty()) si.push_back(0);
+    if (ri.empty()) ri.push_back(0);
+    h.send_idx.upload(si, st); h.recv_idx.upload(ri, st);
+    h.send_buf.alloc(si.size()); h.recv_buf.alloc(ri.size());
+    CK(cudaStreamSynchronize(st));
+    ncclUniqueId id;
+    static_assert(sizeof(id) == 128, "ncclUniqueId is 128 bytes");
+    std::memcpy(&id, nccl_id, sizeof(id));
+    NK(NcclApi::get().CommInitRank(&h.comm, h.nranks, id, h.rank));
+    cell_l2g = part.cell_l2g;
+    n_global = part.n_global_cells + part.n_global_ghost;
+}
+
+void Solver::exchange(d4* field)
+{
+    Halo& h = *halo;
+    if (h.n_send) { kt->permute4(field, h.send_buf.p, h.send_idx.p, h.n_send, st); ++launches; }
+    NK(NcclApi::get().GroupStart());
+    for (const auto& p : h.peers) {
+        if (p.send_cnt) NK(NcclApi::get().Send(h.send_buf.p + p.send_off, (size_t)p.send_cnt * 4, ncclDouble, p.rank, h.comm, st));
+        if (p.recv_cnt) NK(NcclApi::get().Recv(h.recv_buf.p + p.recv_off, (size_t)p.recv_cnt * 4, ncclDouble, p.rank, h.comm, st));
+    }
+    NK(NcclApi::get().GroupEnd());
+    if (h.n_recv) { kt->scatter4(h.recv_buf.p, field, h.recv_idx.p, h.n_recv, st); ++launches; }
+}
+
+// partitioned runs keep per-rank sums of squares: add them over the ranks, then take the root
+void Solver::reduce_norms(double* v, int n)
+{
+    if (!halo || n <= 0) return;
+    DBuf<double> d;
+    d.alloc((size_t)n);
+    CK(cudaMemcpyAsync(d.p, v, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+    NK(NcclApi::get().AllReduce(d.p, d.p, (size_t)n, ncclDouble, ncclSum, halo->comm, st));
+    CK(cudaMemcpyAsync(v, d.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int i = 0; i < n; ++i) v[i] = std::sqrt(v[i]);
 }
 
 double Solver::fetch_last_norm()
@@ -474,7 +544,9 @@ double Solver::fetch_last_norm()
     CK(cudaMemcpyAsync(h_pinned, norms.p + ((k - 1) % NORM_RING), sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     norm_idx_host = k;
-    return h_pinned[0];
+    double v = h_pinned[0];
+    reduce_norms(&v, 1);
+    return v;
 }
 
 void Solver::run_explicit(double relax, int n_iter, double* norms_out)
@@ -503,7 +575,7 @@ void Solver::run_explicit(double relax, int n_iter, double* norms_out)
                 CK(cudaGraphInstantiate(&graph_exec, g, 0));
                 CK(cudaGraphDestroy(g));
             }
-            const int per_iter = 1 + 3 * (second_order ? 3 : 2);
+            const int per_iter = 1 + 3 * (second_order ? 3 : 2) + (halo ? 3 * ((halo->n_send ? 1 : 0) + (halo->n_recv ? 1 : 0)) : 0);
             for (int it = 0; it < chunk; ++it) CK(cudaGraphLaunch(graph_exec, st));
             launches += (int64_t)per_iter * chunk;
         } else {
@@ -520,6 +592,7 @@ void Solver::run_explicit(double relax, int n_iter, double* norms_out)
                 it += n;
             }
             CK(cudaStreamSynchronize(st));
+            reduce_norms(tmp.data(), chunk);
             std::copy(tmp.begin(), tmp.end(), norms_out + done);
         }
         done += chunk;
@@ -626,6 +699,7 @@ int guard(F&& f)
     } catch (const afx::CudaError& e) { afx::set_error(e.what()); return AFX_ERR_CUDA; }
     catch (const afx::InvalidArg& e) { afx::set_error(e.what()); return AFX_ERR_INVALID; }
     catch (const afx::NumericError& e) { afx::set_error(e.what()); return AFX_ERR_NUMERIC; }
+    catch (const afx::CommError& e) { afx::set_error(e.what()); return AFX_ERR_COMM; }
     catch (const std::exception& e) { afx::set_error(e.what()); return AFX_ERR_INVALID; }
     catch (...) { afx::set_error("unknown error"); return AFX_ERR_INVALID; }
 }
@@ -662,6 +736,33 @@ int afx_rans_create(afx_rans** out, const afx_mesh_desc* mesh, const afx_gas* ga
         if (viscosity_model < 0 || viscosity_model > 2) throw afx::InvalidArg("viscosity model must be 0, 1 or 2");
         h = new afx_rans;
         h->s.create(*mesh, *gas, viscosity_model, device);
+    });
+    if (rc) { delete h; return rc; }
+    *out = h;
+    return AFX_OK;
+}
+
+int afx_nccl_unique_id(char out[128])
+{
+    return guard([&] {
+        ncclUniqueId id;
+        NK(afx::NcclApi::get().GetUniqueId(&id));
+        std::memcpy(out, &id, 128);
+    });
+}
+
+int afx_rans_create_partitioned(afx_rans** out, const afx_partition* part, const afx_gas* gas, int viscosity_model, int device,
+                                const char nccl_id[128])
+{
+    if (!out || !part || !gas || !nccl_id) { afx::set_error("null argument"); return AFX_ERR_INVALID; }
+    *out = nullptr;
+    afx_rans* h = nullptr;
+    const int rc = guard([&] {
+        if (viscosity_model < 0 || viscosity_model > 2) throw afx::InvalidArg("viscosity model must be 0, 1 or 2");
+        h = new afx_rans;
+        const afx_mesh_desc d = part->p.desc();
+        h->s.create(d, *gas, viscosity_model, device, &part->p);
+        h->s.init_halo(part->p, nccl_id);
     });
     if (rc) { delete h; return rc; }
     *out = h;
@@ -748,6 +849,12 @@ int afx_rans_set_q(afx_rans* s, const double* q)
     return guard([&] {
         auto& S = s->s;
         S.use();
+        std::vector<double> local;
+        if (S.halo) {  // q is the GLOBAL vector: pick this rank's cells (owned, rings, boundary ghosts)
+            local.resize(4 * (size_t)S.NT);
+            for (uint32_t l = 0; l < S.NT; ++l) std::memcpy(&local[4 * (size_t)l], q + 4 * (size_t)S.cell_l2g[l], 32);
+            q = local.data();
+        }
         S.from_ref_order4(q, S.q.p);
         S.sync_ghost_rows();
         CK(cudaStreamSynchronize(S.st));
@@ -757,7 +864,15 @@ int afx_rans_set_q(afx_rans* s, const double* q)
 
 int afx_rans_get_q(afx_rans* s, double* q)
 {
-    return guard([&] { s->s.use(); s->s.to_ref_order4(s->s.q.p, q); });
+    return guard([&] {
+        auto& S = s->s;
+        S.use();
+        if (!S.halo) { S.to_ref_order4(S.q.p, q); return; }
+        // partitioned: fill this rank's entries of the GLOBAL vector, leave the rest untouched
+        std::vector<double> local(4 * (size_t)S.NT);
+        S.to_ref_order4(S.q.p, local.data());
+        for (uint32_t l = 0; l < S.NT; ++l) std::memcpy(q + 4 * (size_t)S.cell_l2g[l], &local[4 * (size_t)l], 32);
+    });
 }
 
 int afx_rans_get_field(afx_rans* s, int field, double* out)
@@ -907,6 +1022,11 @@ int afx_rans_wall_forces(afx_rans* s, int patch, double out[3])
             else { xmin = std::min(xmin, S.h_bcx[b]); xmax = std::max(xmax, S.h_bcx[b]); ym += S.h_bcy[b]; }
             ++n_added;
         }
+        if (S.halo) {  // extents of the whole patch, not of this rank's piece
+            const auto& H = *S.halo;
+            if (patch < 0 || patch >= (int)H.patch_count.size()) throw afx::InvalidArg("unknown patch");
+            xmin = H.patch_xmin[patch]; xmax = H.patch_xmax[patch]; ym = H.patch_ysum[patch]; n_added = H.patch_count[patch];
+        }
         if (!n_added) throw afx::InvalidArg("patch has no boundary edges");
         ym /= (double)n_added;
         const double xm = (xmax - xmin) * 0.25 + xmin;
@@ -914,6 +1034,7 @@ int afx_rans_wall_forces(afx_rans* s, int patch, double out[3])
                                         S.scratch.p, nullptr}, S.dm, S.q.p, S.st);
         ++S.launches;
         CK(cudaGetLastError());
+        if (S.halo) NK(afx::NcclApi::get().AllReduce(S.scratch.p, S.scratch.p, 3, ncclDouble, ncclSum, S.halo->comm, S.st));
         CK(cudaMemcpyAsync(S.h_pinned + 16, S.scratch.p, 3 * sizeof(double), cudaMemcpyDeviceToHost, S.st));
         CK(cudaStreamSynchronize(S.st));
         const double fx = S.h_pinned[16], fy = S.h_pinned[17], cm = S.h_pinned[18], aoa = far.angle;
@@ -950,42 +1071,48 @@ int afx_rans_wall_cp(afx_rans* s, int patch, double* cp)
 int afx_rans_last_device_ms(afx_rans* s, double* ms) { *ms = s->s.last_ms; return AFX_OK; }
 int64_t afx_rans_launch_count(afx_rans* s) { return s->s.launches; }
 
-int afx_rans_profile_explicit(afx_rans* s, double relaxation, int n_iter, double out_ms[4])
+int afx_rans_profile_explicit(afx_rans* s, double relaxation, int n_iter, double out_ms[5])
 {
     return guard([&] {
         auto& S = s->s;
         S.use();
         if (!S.bcs_set) throw afx::InvalidArg("set_bcs has not been called");
         S.push_params(relaxation);
-        for (int k = 0; k < 4; ++k) out_ms[k] = 0;
+        for (int k = 0; k < 5; ++k) out_ms[k] = 0;
         const bool grads = S.visc_not_inviscid || S.second_order;
         const afx::d4* in[3] = {S.q.p, S.qkA.p, S.qkB.p};
         afx::d4* outp[3] = {S.qkA.p, S.qkB.p, S.q.p};
         const double alpha[3] = {0.25, 0.5, 1.};
+        cudaEvent_t ev[14];
+        for (auto& e : ev) CK(cudaEventCreate(&e));
         for (int it = 0; it < n_iter; ++it) {
             int e = 0;
-            CK(cudaEventRecord(S.evp[e++], S.st));
+            CK(cudaEventRecord(ev[e++], S.st));
             S.launch_dt_grad(grads, grads);
-            CK(cudaEventRecord(S.evp[e++], S.st));
+            CK(cudaEventRecord(ev[e++], S.st));
             for (int st = 0; st < 3; ++st) {
                 if (S.second_order) S.launch_limiter(in[st]);
-                CK(cudaEventRecord(S.evp[e++], S.st));
+                CK(cudaEventRecord(ev[e++], S.st));
                 S.launch_flux(in[st], false, afx::d4{0, 0, 0, 0});
-                CK(cudaEventRecord(S.evp[e++], S.st));
+                CK(cudaEventRecord(ev[e++], S.st));
                 if (st < 2) S.launch_gather<0, 0>(in[st], outp[st], S.qW.p, alpha[st], grads);
                 else S.launch_gather<0, 1>(in[st], outp[st], S.qW.p, alpha[st], grads);
-                CK(cudaEventRecord(S.evp[e++], S.st));
+                CK(cudaEventRecord(ev[e++], S.st));
+                if (S.halo) S.exchange(outp[st]);
+                CK(cudaEventRecord(ev[e++], S.st));
             }
             CK(cudaStreamSynchronize(S.st));
             float ms;
-            CK(cudaEventElapsedTime(&ms, S.evp[0], S.evp[1])); out_ms[0] += ms;
+            CK(cudaEventElapsedTime(&ms, ev[0], ev[1])); out_ms[0] += ms;
             for (int st = 0; st < 3; ++st) {
-                CK(cudaEventElapsedTime(&ms, S.evp[1 + 3 * st], S.evp[2 + 3 * st])); out_ms[1] += ms;
-                CK(cudaEventElapsedTime(&ms, S.evp[2 + 3 * st], S.evp[3 + 3 * st])); out_ms[2] += ms;
-                CK(cudaEventElapsedTime(&ms, S.evp[3 + 3 * st], S.evp[4 + 3 * st])); out_ms[3] += ms;
+                CK(cudaEventElapsedTime(&ms, ev[1 + 4 * st], ev[2 + 4 * st])); out_ms[1] += ms;
+                CK(cudaEventElapsedTime(&ms, ev[2 + 4 * st], ev[3 + 4 * st])); out_ms[2] += ms;
+                CK(cudaEventElapsedTime(&ms, ev[3 + 4 * st], ev[4 + 4 * st])); out_ms[3] += ms;
+                CK(cudaEventElapsedTime(&ms, ev[4 + 4 * st], ev[5 + 4 * st])); out_ms[4] += ms;
             }
         }
-        for (int k = 0; k < 4; ++k) out_ms[k] /= n_iter;
+        for (auto& e : ev) cudaEventDestroy(e);
+        for (int k = 0; k < 5; ++k) out_ms[k] /= n_iter;
         S.jac_valid = false;
     });
 }

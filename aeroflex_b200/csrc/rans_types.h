@@ -27,6 +27,8 @@ constexpr unsigned int NORM_RING = 1u << 16;  // capacity of the device-side res
 
 struct DevMesh {
     uint32_t N, G, E, NT;        // real cells, ghosts, faces, N+G
+    uint32_t n_upd, n_grad;      // cells [0,n_upd) are advanced; cells [0,n_grad) get dt/gradients/limiters (halo ring 1 included)
+    uint32_t e_flux;             // faces [0,e_flux) touch an advanced cell and get a flux
     const uint2* fcells;         // [E]
     const d4* fgA;               // [E] nx, ny, len, w
     const d4* fgB;               // [E] d0x, d0y, d1x, d1y
@@ -43,6 +45,7 @@ struct NormOut {
     unsigned int* counter;  // block counter
     double* norms;          // [NORM_RING]
     unsigned int* norm_idx; // running index into norms
+    int store_square;       // 1: store the sum of squares (partitioned runs add the ranks' sums before the root)
 };
 
 struct WallArgs {
@@ -57,7 +60,7 @@ struct KernelTable {
     const char* name;
     void (*dt_grad)(int grad_scheme, const DevMesh& m, d4* q, double* dt, d4* gx, d4* gy, const double* prm, double gam,
                     int want_grad, int walls, cudaStream_t st);
-    void (*limiter)(const DevMesh& m, const d4* qk, const d4* gx, const d4* gy, d4* lim, double limiter_k, cudaStream_t st);
+    void (*limiter)(const DevMesh& m, const d4* qk, const d4* gx, const d4* gy, d4* lim, double limiter_k, int walls, cudaStream_t st);
     void (*flux)(int second, int visc, int uniform, const DevMesh& m, const d4* qk, const d4* q0, const d4* gx, const d4* gy,
                  const d4* lim, d4* flux, const GasC& g, d4 qfar, cudaStream_t st);
     void (*gather)(int mode, int last, const DevMesh& m, const d4* flux, const d4* q, const d4* qk_in, d4* qk_out,
@@ -69,6 +72,7 @@ struct KernelTable {
     void (*ghost_fill)(d4* q, const uint32_t* bghost, const uint32_t* bowner, const d4* bstate, uint32_t G, int from_owner, cudaStream_t st);
     void (*permute4)(const d4* src, d4* dst, const uint32_t* idx, uint32_t n, cudaStream_t st);
     void (*permute1)(const double* src, double* dst, const uint32_t* idx, uint32_t n, uint32_t nsrc, cudaStream_t st);
+    void (*scatter4)(const d4* src, d4* dst, const uint32_t* idx, uint32_t n, cudaStream_t st);  // dst[idx[i]] = src[i]
 };
 
 namespace strict { const KernelTable& table(); }  // -fmad=false, reference expression order: bit-identical to the CPU reference

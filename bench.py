@@ -33,8 +33,13 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {  # name: (ni, nj, n_quad_layers) -> SURVEY.md 8d
     "synthetic-64k-mixed-omesh": (256, 160, 64),
     "synthetic-1M-mixed-omesh": (1024, 640, 256),
+    "synthetic-2M-mixed-omesh": (2048, 640, 256),
+    "synthetic-4M-mixed-omesh": (2048, 1280, 512),
+    "synthetic-8M-mixed-omesh": (4096, 1280, 512),
     "synthetic-16M-mixed-omesh": (4096, 2560, 1024),
 }
+# weak scaling: 2^20 cells per GPU, the whole mesh cut into N pieces along a Hilbert curve, 2-layer halo over NCCL
+WEAK = {1: "synthetic-1M-mixed-omesh", 2: "synthetic-2M-mixed-omesh", 4: "synthetic-4M-mixed-omesh", 8: "synthetic-8M-mixed-omesh"}
 BCS = {"farfield": ("farfield", dict(mach=0.2, angle=1.0 * 0.01745, T=1.0, p=1.0)), "wall": ("wall", None)}
 VISC, GRAD, SECOND, LIMK, CFL, RELAX = "spallart-allmaras", "green-gauss", True, 5.0, 1.5, 0.9
 CPU_SAMPLE = "synthetic-64k-mixed-omesh"
@@ -121,7 +126,7 @@ def main():
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     W = max(a.warmup, 3) if a.impl == "b200" else a.warmup
-    workload = a.workload or "synthetic-1M-mixed-omesh"
+    workload = a.workload or WEAK.get(world, "synthetic-1M-mixed-omesh")
     config = {"workload": workload, "scheme": "explicit 3-stage RK, 2nd order MUSCL, Green-Gauss, Venkatakrishnan k=5",
               "viscosity": "spallart-allmaras (reference semantics: Roe flux + no-slip wall + gradients, SURVEY F1/F2)",
               "cfl": CFL, "relaxation": RELAX, "l2": "working set > 126 MB L2 (inputs larger than L2, no flush)"}
@@ -151,13 +156,24 @@ def main():
     ni, nj, nq = WORKLOADS[workload]
     mesh = afx.Mesh.synth_omesh(ni, nj, nq, 150.0)
     N, G, E = mesh.N, mesh.G, mesh.E
-    s = afx.GpuSolver(mesh, viscosity=VISC, device=local, math=a.math)
+    part = None
+    if world > 1:
+        part = afx.Partition(mesh, world, rank)
+        ids = [afx.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        s = afx.GpuSolver(part, viscosity=VISC, device=local, math=a.math, nccl_id=ids[0])
+    else:
+        s = afx.GpuSolver(mesh, viscosity=VISC, device=local, math=a.math)
     config["math"] = a.math + (" (shared reciprocals + FMA; parity 1e-10 tested)" if a.math == "fast" else " (bit-identical to the CPU reference)")
     s.set_bcs(BCS); s.set_options(SECOND, GRAD, LIMK, CFL); s.init(); s.refill_bcs()
-    q0 = perturbed(s.get_q(), N)
+    base = np.zeros(4 * (N + G))
+    s.get_q(base)  # a partitioned solver fills its own entries of the global vector
+    q0 = perturbed(base, N)
     s.set_q(q0)
     config.update({"cells": N, "edges": E, "ghost_cells": G,
-                   "parallelism": "1 GPU" if world == 1 else "%d independent replicas (polar-sweep mode, no communication)" % world})
+                   "parallelism": "1 GPU" if world == 1 else
+                   "domain decomposition: %d Hilbert-curve partitions, 2-layer halo, one NCCL send/recv group per RK stage "
+                   "(this rank: %d owned + %d halo cells, %d peers)" % (world, part.n_own, part.n_r1 + part.n_r2, part.n_peers)})
 
     def barrier():
         torch.cuda.synchronize()
@@ -185,13 +201,14 @@ def main():
         t = torch.tensor([dev_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_ms = float(t.item())
-    value = world * N * a.steps / (t_ms * 1e-3)
+    value = N * a.steps / (t_ms * 1e-3)  # N is the whole (partitioned) mesh
 
     # per-phase kernel times (CUDA events between the phases, same state, right after the timed region)
     prof = s.profile_explicit(5, RELAX)
     flux_ms = prof["flux"] / 3.0
-    alg_flux = 144.0 * N + 48.0 * E
-    alg_iter = 1488.0 * N + 296.0 * E
+    n_loc = N if part is None else part.n_own
+    alg_flux = (144.0 * N + 48.0 * E) * n_loc / N      # this rank's share
+    alg_iter = (1488.0 * N + 296.0 * E) * n_loc / N
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -214,7 +231,8 @@ def main():
     # end to end through the C ABI with host-resident state, pinned buffers
     nq4 = 4 * (N + G)
     hq = afx.pinned_array(nq4)
-    hq[:] = s.get_q()
+    hq[:] = q0
+    s.get_q(hq)
     for _ in range(2):
         s.set_q(hq); s.solve(RELAX); s.get_q(hq)
     barrier()
@@ -229,8 +247,9 @@ def main():
         t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e = {"value": world * N * a.e2e_steps / e2e_s, "unit": "cell-updates/s", "h2d_bytes_per_step": 8 * nq4,
-           "d2h_bytes_per_step": 8 * nq4 + 8, "steps": a.e2e_steps, "ms_per_step": e2e_s / a.e2e_steps * 1e3,
+    loc4 = nq4 if part is None else 4 * (part.N + part.G) * world  # every rank moves its piece (owned + halo + ghosts)
+    e2e = {"value": N * a.e2e_steps / e2e_s, "unit": "cell-updates/s", "h2d_bytes_per_step": 8 * loc4,
+           "d2h_bytes_per_step": 8 * loc4 + 8, "steps": a.e2e_steps, "ms_per_step": e2e_s / a.e2e_steps * 1e3,
            "path": "afx_rans_set_q(pinned host) -> afx_rans_step_explicit -> afx_rans_get_q(pinned host) + norm"}
 
     cpu = None

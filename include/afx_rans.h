@@ -135,6 +135,28 @@ typedef struct afx_rans afx_rans;
 int afx_rans_create(afx_rans** out, const afx_mesh_desc* mesh, const afx_gas* gas, int viscosity_model, int device);
 void afx_rans_destroy(afx_rans* s);
 
+/* ---- multi-GPU: one process per GPU, one partition per process (no counterpart in the reference) ----
+ * Host-only planning: cut the global mesh into `nranks` pieces along a Hilbert curve, each with a 2-cell halo. */
+typedef struct afx_partition afx_partition;
+int afx_partition_create(afx_partition** out, const afx_mesh_desc* global_mesh, int nranks, int rank);
+void afx_partition_free(afx_partition* p);
+/* the piece as a mesh of its own, reference layout: cells = owned | ring 1 | ring 2, then its boundary ghosts */
+int afx_partition_get_desc(const afx_partition* p, afx_mesh_desc* out);
+/* out = {n_owned, n_ring1, n_ring2, n_boundary_ghosts, n_local_edges, n_peers, rank, nranks} */
+int afx_partition_info(const afx_partition* p, uint32_t out[8]);
+const uint32_t* afx_partition_cell_l2g(const afx_partition* p); /* local cell (incl. ghosts) -> global cell */
+const uint32_t* afx_partition_edge_l2g(const afx_partition* p); /* local edge -> global edge, ascending */
+/* exchange plan with peer i: owned cells to send, halo cells to fill (local ids, matching order on both sides) */
+int afx_partition_peer(const afx_partition* p, int i, int* peer_rank, const uint32_t** send, uint32_t* n_send,
+                       const uint32_t** recv, uint32_t* n_recv);
+/* NCCL bootstrap: rank 0 makes the 128-byte id, the host program broadcasts it (torch.distributed, MPI, ...) */
+int afx_nccl_unique_id(char out[128]);
+/* a solver on this rank's piece; halo cells are refreshed over NCCL after every stage, norms and forces are
+ * all-reduced.  Collective: every rank must make the same calls.  set_q takes the GLOBAL vector, get_q fills
+ * this rank's entries of the GLOBAL vector. */
+int afx_rans_create_partitioned(afx_rans** out, const afx_partition* part, const afx_gas* gas, int viscosity_model,
+                                int device, const char nccl_id[128]);
+
 /* solver::set_bcs (solver.h:200-247): kind and far-field variables per patch id */
 int afx_rans_set_bcs(afx_rans* s, int n_patch, const uint8_t* patch_kind, const afx_bvars* patch_vars);
 /* set_second_order / set_gradient_scheme / set_limiter_k (solver.h:135,149-152,162) */
@@ -190,8 +212,9 @@ int afx_rans_last_device_ms(afx_rans* s, double* ms);
 /* kernels launched by this handle since creation (bench.py's gpu_launches) */
 int64_t afx_rans_launch_count(afx_rans* s);
 /* per-phase device milliseconds of one explicit iteration, timed with CUDA events between the phases:
- * out[0]=dt+gradients, out[1]=limiter (3 stages), out[2]=face flux (3 stages), out[3]=gather+update (3 stages) */
-int afx_rans_profile_explicit(afx_rans* s, double relaxation, int n_iter, double out_ms[4]);
+ * out[0]=dt+gradients, out[1]=limiter (3 stages), out[2]=face flux (3 stages), out[3]=gather+update (3 stages),
+ * out[4]=halo exchange (3 stages; 0 on one GPU) */
+int afx_rans_profile_explicit(afx_rans* s, double relaxation, int n_iter, double out_ms[5]);
 
 #ifdef __cplusplus
 }

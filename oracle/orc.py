@@ -148,9 +148,36 @@ class OracleMesh:
 
     def __del__(self):
         try:
-            self.L.orc_mesh_free(C.byref(self.m))
+            if getattr(self, "_owned", True):
+                self.L.orc_mesh_free(C.byref(self.m))
         except Exception:
             pass
+
+    @classmethod
+    def from_arrays(cls, a, N, G, patch_names, fast=False):
+        """Wrap ready-made reference-layout arrays (e.g. one rank's piece of a partitioned mesh) without rebuilding."""
+        self = cls.__new__(cls)
+        self.L = lib(fast)
+        self._owned = False
+        self.patch_names = list(patch_names)
+        E = len(a["enx"])
+        keep = dict(edge_cells=np.ascontiguousarray(a["edge_cells"], np.uint32).reshape(-1, 2),
+                    cell_edges=np.ascontiguousarray(a["cell_edges"], np.uint32).reshape(-1, 4),
+                    is_tri=np.ascontiguousarray(np.concatenate([a["is_tri"], np.ones(G, np.uint8)]), np.uint8),
+                    bnd_edge=np.ascontiguousarray(a["bnd_edge"], np.uint32), bnd_patch=np.ascontiguousarray(a["bnd_patch"], np.int32))
+        for n in ("enx", "eny", "elen", "ecx", "ecy", "ccx", "ccy", "area"):
+            keep[n] = np.ascontiguousarray(a[n], np.float64)
+        self._keep = keep
+        m = Mesh()
+        m.N, m.G, m.E = N, G, E
+        for n, t in (("edge_cells", C.c_uint32), ("cell_edges", C.c_uint32), ("is_tri", C.c_uint8), ("bnd_edge", C.c_uint32),
+                     ("bnd_patch", C.c_int32), ("enx", C.c_double), ("eny", C.c_double), ("elen", C.c_double), ("ecx", C.c_double),
+                     ("ecy", C.c_double), ("ccx", C.c_double), ("ccy", C.c_double), ("area", C.c_double)):
+            setattr(m, n, keep[n].ctypes.data_as(C.POINTER(t)))
+            setattr(self, n, keep[n])
+        self.m = m
+        self.N, self.G, self.E = N, G, E
+        return self
 
 
 class OracleSolver:

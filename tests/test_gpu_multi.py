@@ -1,0 +1,82 @@
+"""Partitioned (multi-GPU) runs: N processes, one GPU each, NCCL halo exchange -- against the single-GPU run
+and the oracle.  Needs >= 2 visible GPUs (gpurun --gpus 2); skipped on a 1-GPU box."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+BCS = {"farfield": ("farfield", dict(mach=0.2, angle=0.03, T=1.0, p=1.0)), "wall": ("wall", None)}
+DIMS = (256, 160, 64)  # 65 536 mixed cells
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    return port
+
+
+def _q0(afx, mesh):
+    s = afx.GpuSolver(mesh, viscosity="spallart-allmaras", math="strict", device=0)
+    s.set_bcs(BCS); s.set_options(True, "green-gauss", 5.0, 1.4); s.init(); s.refill_bcs()
+    q = s.get_q()
+    rng = np.random.default_rng(77)
+    q[:4 * mesh.N] *= 1 + 1e-3 * rng.uniform(-1, 1, 4 * mesh.N)
+    return s, q
+
+
+def _worker(rank, world, port, n_iter, out_dir, math):
+    import torch.distributed as dist
+    import aeroflex_b200 as afx
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mesh = afx.Mesh.synth_omesh(*DIMS, 150.0)
+    part = afx.Partition(mesh, world, rank)
+    ids = [afx.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    s = afx.GpuSolver(part, viscosity="spallart-allmaras", math=math, device=rank, nccl_id=ids[0])
+    s.set_bcs(BCS); s.set_options(True, "green-gauss", 5.0, 1.4); s.init(); s.refill_bcs()
+    q0 = np.load(os.path.join(out_dir, "q0.npy"))
+    s.set_q(q0)
+    ur = s.get_uniform_residual()
+    norms = s.run(n_iter, 0.9)
+    out = np.full(4 * (mesh.N + mesh.G), np.nan)
+    s.get_q(out)
+    forces = s.wall_forces("wall")
+    np.savez(os.path.join(out_dir, "r%d.npz" % rank), q=out, norms=norms, forces=np.array(forces), owned=part.cell_l2g[:part.n_own], ur=ur)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,math", [(2, "strict"), (2, "fast")])
+def test_partitioned_run_matches_single_gpu(afx, gpu, tmp_path, world, math):
+    if gpu < world:
+        pytest.skip("needs %d GPUs, %d visible" % (world, gpu))
+    import torch.multiprocessing as mp
+    n_iter = 6
+    mesh = afx.Mesh.synth_omesh(*DIMS, 150.0)
+    single, q0 = _q0(afx, mesh)
+    np.save(tmp_path / "q0.npy", q0)
+    single.set_q(q0)
+    ur = single.get_uniform_residual()
+    ref_norms = single.run(n_iter, 0.9)
+    Q = single.get_q().reshape(-1, 4)
+    F = np.array(single.wall_forces("wall"))
+    del single
+    mp.spawn(_worker, args=(world, _free_port(), n_iter, str(tmp_path), math), nprocs=world, join=True)
+    seen = 0
+    for r in range(world):
+        d = np.load(tmp_path / ("r%d.npz" % r))
+        own = d["owned"]
+        got = d["q"].reshape(-1, 4)[own]
+        if math == "strict":
+            assert np.array_equal(got, Q[own])  # bit-identical to the single-GPU strict run (itself bit-identical to the oracle)
+            np.testing.assert_allclose(d["norms"], ref_norms, rtol=1e-12)
+            np.testing.assert_allclose(d["forces"], F, rtol=1e-12, atol=1e-15)
+            assert d["ur"] == pytest.approx(ur, rel=1e-12)
+        else:
+            np.testing.assert_allclose(got, Q[own], rtol=1e-10, atol=1e-13)
+            np.testing.assert_allclose(d["norms"], ref_norms, rtol=1e-10)
+            np.testing.assert_allclose(d["forces"], F, rtol=1e-8, atol=1e-12)
+        seen += len(own)
+    assert seen == mesh.N
