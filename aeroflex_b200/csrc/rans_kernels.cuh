@@ -264,15 +264,15 @@ __device__ __forceinline__ void block_norm_accumulate(double v, const NormOut& n
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
         if (lane == 0) {
-            partial[blockIdx.x] = t;
+            partial[no.blk_off + blockIdx.x] = t;
             __threadfence();
-            last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+            last = (atomicAdd(counter, 1u) == no.blk_total - 1);
         }
     }
     __syncthreads();
     if (last) {  // fixed-order final reduction by one block
         double t = 0;
-        for (uint32_t b = threadIdx.x; b < gridDim.x; b += blockDim.x) t += __ldcg(&partial[b]);
+        for (uint32_t b = threadIdx.x; b < no.blk_total; b += blockDim.x) t += __ldcg(&partial[b]);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
         __syncthreads();
@@ -303,11 +303,11 @@ __global__ void __launch_bounds__(256) k_gather_update(DevMesh m, const d4* __re
                                                        const d4* q, const d4* qk_in,
                                                        d4* qk_out, const double* __restrict__ dt,
                                                        d4* __restrict__ qW, double alpha, const double* __restrict__ prm,
-                                                       int walls, NormOut no)
+                                                       int walls, NormOut no, uint32_t lo, uint32_t hi)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t i = lo + blockIdx.x * blockDim.x + threadIdx.x;
     double nrm = 0;
-    if (i < m.n_upd) {
+    if (i < hi) {
         d4 r = mk4(0, 0, 0, 0);
         uint32_t bnd[4];
 #pragma unroll
@@ -551,11 +551,14 @@ static void flux(int second, int visc, int uniform, const DevMesh& m, const d4* 
     else { if (visc) AFX_FLUX(0, 1, 0); else AFX_FLUX(0, 0, 0); }
 #undef AFX_FLUX
 }
-static void gather(int mode, int last, const DevMesh& m, const d4* fl, const d4* q, const d4* qk_in, d4* qk_out, const double* dt,
-                   d4* vec_out, double alpha, const double* prm, int walls, const NormOut& no, cudaStream_t st)
+static unsigned gather_blocks(uint32_t n_cells) { return nblk(n_cells); }
+static void gather(int mode, int last, const DevMesh& m, uint32_t lo, uint32_t hi, const d4* fl, const d4* q, const d4* qk_in, d4* qk_out,
+                   const double* dt, d4* vec_out, double alpha, const double* prm, int walls, NormOut no, cudaStream_t st)
 {
-    const unsigned nb = nblk(m.n_upd);
-#define AFX_G(M, L) k_gather_update<M, L><<<nb, 256, 0, st>>>(m, fl, q, qk_in, qk_out, dt, vec_out, alpha, prm, walls, no)
+    if (hi <= lo) return;
+    const unsigned nb = nblk(hi - lo);
+    if (no.blk_total == 0) { no.blk_off = 0; no.blk_total = nb; }
+#define AFX_G(M, L) k_gather_update<M, L><<<nb, 256, 0, st>>>(m, fl, q, qk_in, qk_out, dt, vec_out, alpha, prm, walls, no, lo, hi)
     if (mode == 0) { if (last) AFX_G(0, 1); else AFX_G(0, 0); }
     else if (mode == 1) AFX_G(1, 1);
     else AFX_G(2, 1);

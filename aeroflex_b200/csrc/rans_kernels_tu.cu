@@ -14,7 +14,7 @@ const KernelTable& table()
 #else
         "strict",
 #endif
-        launch::dt_grad, launch::limiter, launch::flux, launch::gather, launch::jacobian, launch::jac_diag,
+        launch::dt_grad, launch::limiter, launch::flux, launch::gather, launch::gather_blocks, launch::jacobian, launch::jac_diag,
         launch::wall_forces, launch::fill_cells, launch::ghost_fill, launch::permute4, launch::permute1, launch::scatter4};
     return t;
 }

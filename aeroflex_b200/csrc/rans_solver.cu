@@ -104,6 +104,10 @@ struct Solver {
     cudaEvent_t evp[16] = {};
     uint32_t N = 0, G = 0, E = 0, NT = 0;
     uint32_t n_upd = 0, n_grad = 0, e_flux = 0;  // sub-ranges of a partition (== N, N, E on one GPU)
+    uint32_t n_front = 0;                        // partitioned: owned cells [0,n_front) are sent to peers and are advanced first
+    cudaStream_t cs = nullptr;                   // halo stream: the exchange overlaps the interior cells' update
+    cudaEvent_t ev_front = nullptr, ev_halo = nullptr;
+    d4* h_stage = nullptr;                       // pinned staging of a partition's local state
     std::unique_ptr<Halo> halo;                  // null on one GPU
     std::vector<uint32_t> cell_l2g;              // partitioned: local reference-order cell -> global cell
     uint32_t n_global = 0;                       // partitioned: global N+G
@@ -139,7 +143,7 @@ struct Solver {
     unsigned int norm_idx_host = 0;
 
     cudaGraphExec_t graph_exec = nullptr;
-    uint64_t graph_key = 0;
+    int64_t graph_per_iter = 0;  // kernels of ours in one captured iteration
     bool use_graph = true;
     int64_t launches = 0;
     double last_ms = 0;
@@ -147,7 +151,7 @@ struct Solver {
 
     DevMesh dm{};
     const KernelTable* kt = &fast::table();  // arithmetic mode, see afx_rans_set_math_mode
-    NormOut norm_out() { return NormOut{partial.p, counters.p, norms.p, counters.p + 1, halo ? 1 : 0}; }
+    NormOut norm_out() { return NormOut{partial.p, counters.p, norms.p, counters.p + 1, halo ? 1 : 0, 0, 0}; }
     void set_math_mode(int mode)
     {
         if (mode != AFX_MATH_STRICT && mode != AFX_MATH_FAST) throw InvalidArg("unknown math mode");
@@ -163,6 +167,10 @@ struct Solver {
         for (auto& e : evp) if (e) cudaEventDestroy(e);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        if (ev_front) cudaEventDestroy(ev_front);
+        if (ev_halo) cudaEventDestroy(ev_halo);
+        if (h_stage) cudaFreeHost(h_stage);
+        if (cs) cudaStreamDestroy(cs);
         if (st) cudaStreamDestroy(st);
     }
 
@@ -171,7 +179,7 @@ struct Solver {
 
     void create(const afx_mesh_desc& m, const afx_gas& g, int visc, int dev, const Partition* part = nullptr);
     void init_halo(const Partition& part, const char* nccl_id);
-    void exchange(d4* field);
+    void exchange(d4* field, cudaStream_t stream);
     void reduce_norms(double* v, int n);
     void set_bcs(int n_patch, const uint8_t* kinds, const afx_bvars* vars);
     void set_options(int so, int grad, double k);
@@ -253,6 +261,12 @@ void Solver::create(const afx_mesh_desc& m, const afx_gas& g, int visc, int dev,
         std::iota(idx.begin(), idx.end(), 0u);
         // a partition arrives in curve order inside each class (owned | ring 1 | ring 2) and must keep its classes
         if (hilbert && N > 64 && !part) idx = hilbert_order(m.cells_cx, m.cells_cy, idx);
+        if (part) {  // owned cells that some peer needs come first: they are advanced, then sent while the rest is advanced
+            std::vector<uint8_t> front(N, 0);
+            for (const auto& p : part->peers) for (uint32_t c : p.send) front[c] = 1;
+            std::stable_partition(idx.begin(), idx.begin() + n_upd, [&](uint32_t c) { return front[c] != 0; });
+            n_front = (uint32_t)std::count(front.begin(), front.begin() + n_upd, (uint8_t)1);
+        }
         for (uint32_t n = 0; n < N; ++n) { c_new2old[n] = idx[n]; c_old2new[idx[n]] = n; }
         // ghosts follow their owners
         std::vector<uint32_t> gb(G);
@@ -458,8 +472,25 @@ void Solver::launch_flux(const d4* qk, bool uniform, d4 qfar)
 template <int MODE, int LAST>
 void Solver::launch_gather(const d4* qk_in, d4* qk_out, d4* vec_out, double alpha, bool walls)
 {
-    kt->gather(MODE, LAST, dm, flux.p, q.p, qk_in, qk_out, dt.p, vec_out, alpha, prm.p, walls ? 1 : 0, norm_out(), st);
+    if (halo && MODE == 0 && n_front > 0 && n_front < n_upd) {
+        // send layer first, then the exchange on the halo stream while the interior cells are advanced
+        NormOut no = norm_out();
+        const unsigned b0 = kt->gather_blocks(n_front), b1 = kt->gather_blocks(n_upd - n_front);
+        no.blk_off = 0; no.blk_total = b0 + b1;
+        kt->gather(MODE, LAST, dm, 0, n_front, flux.p, q.p, qk_in, qk_out, dt.p, vec_out, alpha, prm.p, walls ? 1 : 0, no, st);
+        CK(cudaEventRecord(ev_front, st));
+        CK(cudaStreamWaitEvent(cs, ev_front, 0));
+        exchange(qk_out, cs);
+        CK(cudaEventRecord(ev_halo, cs));
+        no.blk_off = b0;
+        kt->gather(MODE, LAST, dm, n_front, n_upd, flux.p, q.p, qk_in, qk_out, dt.p, vec_out, alpha, prm.p, walls ? 1 : 0, no, st);
+        CK(cudaStreamWaitEvent(st, ev_halo, 0));
+        launches += 2;
+        return;
+    }
+    kt->gather(MODE, LAST, dm, 0, n_upd, flux.p, q.p, qk_in, qk_out, dt.p, vec_out, alpha, prm.p, walls ? 1 : 0, norm_out(), st);
     ++launches;
+    if (halo && MODE == 0) exchange(qk_out, st);
 }
 
 // explicitSolver::solve, solver.h:802-828.  Stage 0 reads q in place of qk (they
@@ -476,7 +507,6 @@ void Solver::explicit_iteration()
         launch_flux(in[s], false, d4{0, 0, 0, 0});
         if (s < 2) launch_gather<0, 0>(in[s], out[s], qW.p, alpha[s], grads);
         else launch_gather<0, 1>(in[s], out[s], qW.p, alpha[s], grads);
-        if (halo) exchange(out[s]);  // ring cells of the new stage state
     }
 }
 
@@ -485,6 +515,10 @@ void Solver::init_halo(const Partition& part, const char* nccl_id)
 {
     halo.reset(new Halo);
     Halo& h = *halo;
+    CK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ev_front, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ev_halo, cudaEventDisableTiming));
+    CK(cudaMallocHost(&h_stage, (size_t)NT * sizeof(d4)));
     h.rank = part.rank; h.nranks = part.nranks;
     h.patch_xmin = part.patch_xmin; h.patch_xmax = part.patch_xmax; h.patch_ysum = part.patch_ysum; h.patch_count = part.patch_count;
     std::vector<uint32_t> si, ri;
@@ -508,7 +542,7 @@ void Solver::init_halo(const Partition& part, const char* nccl_id)
     n_global = part.n_global_cells + part.n_global_ghost;
 }
 
-void Solver::exchange(d4* field)
+void Solver::exchange(d4* field, cudaStream_t st)
 {
     Halo& h = *halo;
     if (h.n_send) { kt->permute4(field, h.send_buf.p, h.send_idx.p, h.n_send, st); ++launches; }
@@ -571,11 +605,12 @@ void Solver::run_explicit(double relax, int n_iter, double* norms_out)
                 CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
                 explicit_iteration();
                 CK(cudaStreamEndCapture(st, &g));
+                graph_per_iter = launches - l0;
                 launches = l0;
                 CK(cudaGraphInstantiate(&graph_exec, g, 0));
                 CK(cudaGraphDestroy(g));
             }
-            const int per_iter = 1 + 3 * (second_order ? 3 : 2) + (halo ? 3 * ((halo->n_send ? 1 : 0) + (halo->n_recv ? 1 : 0)) : 0);
+            const int64_t per_iter = graph_per_iter;
             for (int it = 0; it < chunk; ++it) CK(cudaGraphLaunch(graph_exec, st));
             launches += (int64_t)per_iter * chunk;
         } else {
@@ -849,11 +884,11 @@ int afx_rans_set_q(afx_rans* s, const double* q)
     return guard([&] {
         auto& S = s->s;
         S.use();
-        std::vector<double> local;
         if (S.halo) {  // q is the GLOBAL vector: pick this rank's cells (owned, rings, boundary ghosts)
-            local.resize(4 * (size_t)S.NT);
-            for (uint32_t l = 0; l < S.NT; ++l) std::memcpy(&local[4 * (size_t)l], q + 4 * (size_t)S.cell_l2g[l], 32);
-            q = local.data();
+            double* local = reinterpret_cast<double*>(S.h_stage);
+#pragma omp parallel for
+            for (int64_t l = 0; l < (int64_t)S.NT; ++l) std::memcpy(local + 4 * (size_t)l, q + 4 * (size_t)S.cell_l2g[l], 32);
+            q = local;
         }
         S.from_ref_order4(q, S.q.p);
         S.sync_ghost_rows();
@@ -869,9 +904,10 @@ int afx_rans_get_q(afx_rans* s, double* q)
         S.use();
         if (!S.halo) { S.to_ref_order4(S.q.p, q); return; }
         // partitioned: fill this rank's entries of the GLOBAL vector, leave the rest untouched
-        std::vector<double> local(4 * (size_t)S.NT);
-        S.to_ref_order4(S.q.p, local.data());
-        for (uint32_t l = 0; l < S.NT; ++l) std::memcpy(q + 4 * (size_t)S.cell_l2g[l], &local[4 * (size_t)l], 32);
+        double* local = reinterpret_cast<double*>(S.h_stage);
+        S.to_ref_order4(S.q.p, local);
+#pragma omp parallel for
+        for (int64_t l = 0; l < (int64_t)S.NT; ++l) std::memcpy(q + 4 * (size_t)S.cell_l2g[l], local + 4 * (size_t)l, 32);
     });
 }
 
@@ -1098,7 +1134,6 @@ int afx_rans_profile_explicit(afx_rans* s, double relaxation, int n_iter, double
                 if (st < 2) S.launch_gather<0, 0>(in[st], outp[st], S.qW.p, alpha[st], grads);
                 else S.launch_gather<0, 1>(in[st], outp[st], S.qW.p, alpha[st], grads);
                 CK(cudaEventRecord(ev[e++], S.st));
-                if (S.halo) S.exchange(outp[st]);
                 CK(cudaEventRecord(ev[e++], S.st));
             }
             CK(cudaStreamSynchronize(S.st));

@@ -46,6 +46,8 @@ struct NormOut {
     double* norms;          // [NORM_RING]
     unsigned int* norm_idx; // running index into norms
     int store_square;       // 1: store the sum of squares (partitioned runs add the ranks' sums before the root)
+    unsigned int blk_off;   // this launch's first slot in partial[] (a phase may be split into several launches)
+    unsigned int blk_total; // blocks of all launches of the phase; the block that arrives last finishes the sum
 };
 
 struct WallArgs {
@@ -63,8 +65,10 @@ struct KernelTable {
     void (*limiter)(const DevMesh& m, const d4* qk, const d4* gx, const d4* gy, d4* lim, double limiter_k, int walls, cudaStream_t st);
     void (*flux)(int second, int visc, int uniform, const DevMesh& m, const d4* qk, const d4* q0, const d4* gx, const d4* gy,
                  const d4* lim, d4* flux, const GasC& g, d4 qfar, cudaStream_t st);
-    void (*gather)(int mode, int last, const DevMesh& m, const d4* flux, const d4* q, const d4* qk_in, d4* qk_out,
-                   const double* dt, d4* vec_out, double alpha, const double* prm, int walls, const NormOut& no, cudaStream_t st);
+    // cells [lo, hi); `no` carries the block bookkeeping when the phase is split into several launches
+    void (*gather)(int mode, int last, const DevMesh& m, uint32_t lo, uint32_t hi, const d4* flux, const d4* q, const d4* qk_in,
+                   d4* qk_out, const double* dt, d4* vec_out, double alpha, const double* prm, int walls, NormOut no, cudaStream_t st);
+    unsigned (*gather_blocks)(uint32_t n_cells);
     void (*jacobian)(int visc, const DevMesh& m, const d4* q, const d4* gx, const d4* gy, d4* J, const GasC& g, cudaStream_t st);
     void (*jac_diag)(const DevMesh& m, const d4* J, const double* dt, double* D, cudaStream_t st);
     void (*wall_forces)(const WallArgs& a, const DevMesh& m, const d4* q, cudaStream_t st);
