@@ -36,7 +36,8 @@ EXPORTED_SYMBOLS = [
     "afx_rans_init", "afx_rans_refill_bcs", "afx_rans_bcs_from_internal", "afx_rans_set_q", "afx_rans_get_q",
     "afx_rans_get_field", "afx_rans_boundary_variables", "afx_rans_uniform_residual", "afx_rans_step_explicit",
     "afx_rans_run_explicit", "afx_rans_phase_dt_gradients", "afx_rans_phase_limiters", "afx_rans_phase_residual",
-    "afx_rans_residual", "afx_rans_fill_jacobian", "afx_rans_get_jacobian_blocks", "afx_rans_step_implicit",
+    "afx_rans_residual", "afx_rans_fill_jacobian", "afx_rans_get_jacobian_blocks", "afx_rans_step_implicit", "afx_rans_compute",
+    "afx_rans_set_linear_solver", "afx_rans_last_linear_iterations",
     "afx_rans_wall_forces", "afx_rans_wall_cp", "afx_rans_last_device_ms", "afx_rans_launch_count",
     "afx_rans_profile_explicit",
 ]
@@ -175,6 +176,9 @@ def load_library():
     L.afx_rans_residual.argtypes = [vp, dp]
     L.afx_rans_get_jacobian_blocks.argtypes = [vp, vp, vp, vp]
     L.afx_rans_step_implicit.argtypes = [vp, C.c_double, C.c_double, C.c_int, dp]
+    L.afx_rans_compute.argtypes = [vp]
+    L.afx_rans_set_linear_solver.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_int]
+    L.afx_rans_last_linear_iterations.argtypes = [vp]
     L.afx_rans_wall_forces.argtypes = [vp, C.c_int, vp]
     L.afx_rans_wall_cp.argtypes = [vp, C.c_int, vp]
     L.afx_rans_last_device_ms.argtypes = [vp, dp]
@@ -470,6 +474,30 @@ class GpuSolver:
         return v.value
 
     def fill_jacobian(self): _check(self.L.afx_rans_fill_jacobian(self.h))
+
+    # implicitSolver surface (solver.h:966-968): fill() / compute() / solve(relaxation, tol, rhs_iterations)
+    def implicit_fill(self): self.fill_jacobian()
+
+    def implicit_compute(self):
+        rc = self.L.afx_rans_compute(self.h)
+        if rc == -3:
+            return -1
+        _check(rc)
+        return 0
+
+    def implicit_solve(self, relaxation=1.0, tol=0.0, rhs_iterations=5):
+        v = C.c_double()
+        rc = self.L.afx_rans_step_implicit(self.h, relaxation, tol, rhs_iterations, C.byref(v))
+        if rc == -3:
+            return -1.0
+        _check(rc)
+        return v.value
+
+    def set_linear_solver(self, restart=30, max_iterations=500, tolerance=1e-2, precond_sweeps=4):
+        _check(self.L.afx_rans_set_linear_solver(self.h, restart, max_iterations, tolerance, precond_sweeps))
+
+    def last_linear_iterations(self):
+        return int(self.L.afx_rans_last_linear_iterations(self.h))
 
     def jacobian_blocks(self):
         NT, E = self.mesh.N + self.mesh.G, self.mesh.E

@@ -2,6 +2,7 @@
 //   nvcc -DAFX_FAST=0 -fmad=false -> namespace afx::strict (bit-identical to the CPU reference)
 //   nvcc -DAFX_FAST=1 -fmad=true  -> namespace afx::fast   (shared reciprocals, FMA contraction)
 #include "rans_kernels.cuh"
+#include "rans_krylov.cuh"
 
 namespace afx {
 namespace AFX_NS {
@@ -15,7 +16,9 @@ const KernelTable& table()
         "strict",
 #endif
         launch::dt_grad, launch::limiter, launch::flux, launch::gather, launch::gather_blocks, launch::jacobian, launch::jac_diag,
-        launch::wall_forces, launch::fill_cells, launch::ghost_fill, launch::permute4, launch::permute1, launch::scatter4};
+        launch::wall_forces, launch::fill_cells, launch::ghost_fill, launch::permute4, launch::permute1, launch::scatter4,
+        launch::spmv, launch::jacobi_sweep, launch::invert_blocks, launch::multi_dot, launch::multi_axpy, launch::scale_from, launch::sub,
+        launch::axpy_state};
     return t;
 }
 

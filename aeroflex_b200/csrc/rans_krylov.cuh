@@ -1,0 +1,222 @@
+// rans_krylov.cuh -- device pieces of the implicit step: block matrix-vector product on the face-block Jacobian,
+// block-Jacobi smoother / preconditioner and the vector kernels of a restarted GMRES.
+//
+// The matrix of implicitSolver::fillRhoLHS (solver.h:979-1071) is never assembled into CSR: k_jacobian leaves, per face,
+// the four 4x4 blocks (512 B, one 128-byte line each) and k_jac_diag the per-cell diagonal block, so
+//   (A x)_i = D_i x_i + sum over the faces of i of  (i is cell0 ? J01_f x_c1 : J10_f x_c0),   ghost rows = identity.
+// All reductions are two-stage with a fixed grid, hence deterministic.
+#pragma once
+#include "rans_physics.cuh"
+
+namespace afx {
+namespace AFX_NS {
+
+constexpr int KRY_BLOCKS = 592;  // 4 CTAs per SM on 148 SMs: the reduction grid
+
+__device__ __forceinline__ d4 blk_mul(const d4* __restrict__ B, const d4& x)
+{
+    const d4 r0 = B[0], r1 = B[1], r2 = B[2], r3 = B[3];
+    d4 y;
+    y.x = r0.x * x.x + r0.y * x.y + r0.z * x.z + r0.w * x.w;
+    y.y = r1.x * x.x + r1.y * x.y + r1.z * x.z + r1.w * x.w;
+    y.z = r2.x * x.x + r2.y * x.y + r2.z * x.z + r2.w * x.w;
+    y.w = r3.x * x.x + r3.y * x.y + r3.z * x.z + r3.w * x.w;
+    return y;
+}
+
+__device__ __forceinline__ d4 row_Ax(const DevMesh& m, const d4* __restrict__ J, const d4* __restrict__ D, const d4* __restrict__ x, uint32_t i)
+{
+    const d4 xi = x[i];
+    if (i >= m.N) return xi;  // ghost rows are the identity (solver.h:1062-1070)
+    d4 y = blk_mul(D + (size_t)i * 4, xi);
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const uint32_t cfv = m.cf[(size_t)s * m.N + i];
+        if (cfv == CF_NONE) continue;
+        const uint32_t f = cfv & CF_ID;
+        const uint2 fc = m.fcells[f];
+        const bool side = cfv & CF_SIDE;
+        const d4 t = blk_mul(J + (size_t)f * 16 + (side ? 8 : 4), x[side ? fc.x : fc.y]);
+        y.x += t.x; y.y += t.y; y.z += t.z; y.w += t.w;
+    }
+    return y;
+}
+
+// y = A x
+__global__ void __launch_bounds__(256) k_spmv(DevMesh m, const d4* __restrict__ J, const d4* __restrict__ D, const d4* __restrict__ x, d4* __restrict__ y)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m.NT) y[i] = row_Ax(m, J, D, x, i);
+}
+
+// block-Jacobi sweep: first ? z = Dinv r : z_out = z_in + Dinv (r - A z_in)
+__global__ void __launch_bounds__(256) k_jacobi_sweep(DevMesh m, const d4* __restrict__ J, const d4* __restrict__ D, const d4* __restrict__ Dinv,
+                                                      const d4* __restrict__ r, const d4* __restrict__ z_in, d4* __restrict__ z_out, int first)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m.NT) return;
+    const d4 ri = r[i];
+    if (i >= m.N) { z_out[i] = ri; return; }
+    if (first) { z_out[i] = blk_mul(Dinv + (size_t)i * 4, ri); return; }
+    const d4 az = row_Ax(m, J, D, z_in, i);
+    const d4 d = blk_mul(Dinv + (size_t)i * 4, mk4(ri.x - az.x, ri.y - az.y, ri.z - az.z, ri.w - az.w));
+    const d4 zi = z_in[i];
+    z_out[i] = mk4(zi.x + d.x, zi.y + d.y, zi.z + d.z, zi.w + d.w);
+}
+
+// Dinv_i = D_i^-1 by Gauss-Jordan with partial pivoting, one thread per cell
+__global__ void __launch_bounds__(128) k_invert_blocks(uint32_t n, const double* __restrict__ D, double* __restrict__ Dinv, int* __restrict__ singular)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double a[4][8];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { a[r][c] = D[(size_t)i * 16 + r * 4 + c]; a[r][4 + c] = (r == c) ? 1.0 : 0.0; }
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        int piv = p;
+        double big = fabs(a[p][p]);
+#pragma unroll
+        for (int r = p + 1; r < 4; ++r) if (fabs(a[r][p]) > big) { big = fabs(a[r][p]); piv = r; }
+        if (big == 0.0) { *singular = 1; big = 1.0; }
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            if (r == piv && piv != p) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) { const double t = a[p][c]; a[p][c] = a[r][c]; a[r][c] = t; }
+            }
+        const double inv = 1.0 / a[p][p];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) a[p][c] *= inv;
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            if (r != p) {
+                const double f = a[r][p];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) a[r][c] -= f * a[p][c];
+            }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) Dinv[(size_t)i * 16 + r * 4 + c] = a[r][4 + c];
+}
+
+__device__ __forceinline__ double block_sum(double v)
+{
+    __shared__ double sh[8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if (lane == 0) sh[wid] = v;
+    __syncthreads();
+    double t = 0;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w];
+    return t;  // valid in thread 0
+}
+
+// partial[j][block] = sum over the block's cells of V_j . w   (j = 0..k-1; V_j = V + j*stride)
+__global__ void __launch_bounds__(256) k_multi_dot_partial(uint32_t n, const d4* __restrict__ V, size_t stride, int k, const d4* __restrict__ w,
+                                                           double* __restrict__ partial)
+{
+    for (int j = 0; j < k; ++j) {
+        const d4* __restrict__ vj = V + (size_t)j * stride;
+        double acc = 0;
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+            const d4 a = vj[i], b = w[i];
+            acc += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+        }
+        const double t = block_sum(acc);
+        if (threadIdx.x == 0) partial[(size_t)j * gridDim.x + blockIdx.x] = t;
+    }
+}
+// out[j] = sum_b partial[j][b], one block per j
+__global__ void __launch_bounds__(256) k_multi_dot_final(int nblocks, const double* __restrict__ partial, double* __restrict__ out)
+{
+    double acc = 0;
+    for (int b = threadIdx.x; b < nblocks; b += blockDim.x) acc += partial[(size_t)blockIdx.x * nblocks + b];
+    const double t = block_sum(acc);
+    if (threadIdx.x == 0) out[blockIdx.x] = t;
+}
+// w += sign * sum_j c[j] V_j
+__global__ void __launch_bounds__(256) k_multi_axpy(uint32_t n, const d4* __restrict__ V, size_t stride, int k, const double* __restrict__ c,
+                                                    double sign, d4* __restrict__ w)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    d4 a = w[i];
+    for (int j = 0; j < k; ++j) {
+        const double cj = sign * c[j];
+        const d4 v = V[(size_t)j * stride + i];
+        a.x += cj * v.x; a.y += cj * v.y; a.z += cj * v.z; a.w += cj * v.w;
+    }
+    w[i] = a;
+}
+// y = x * (inv ? 1/s[0] : s[0]) with the scalar taken from device memory (sqrt applied first if root)
+__global__ void __launch_bounds__(256) k_scale_from(uint32_t n, const d4* __restrict__ x, const double* __restrict__ s, int root, int inv, d4* __restrict__ y)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double f = s[0];
+    if (root) f = sqrt(f);
+    if (inv) f = 1.0 / f;
+    const d4 a = x[i];
+    y[i] = mk4(a.x * f, a.y * f, a.z * f, a.w * f);
+}
+// y = a - b
+__global__ void __launch_bounds__(256) k_sub(uint32_t n, const d4* a, const d4* b, d4* y)  // y may alias a or b
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const d4 p = a[i], q = b[i];
+    y[i] = mk4(p.x - q.x, p.y - q.y, p.z - q.z, p.w - q.w);
+}
+// q += relax * x   (solver.h:1187,1201)
+__global__ void __launch_bounds__(256) k_axpy_state(uint32_t n, double relax, const d4* __restrict__ x, d4* __restrict__ q)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const d4 a = x[i];
+    d4 b = q[i];
+    b.x += a.x * relax; b.y += a.y * relax; b.z += a.z * relax; b.w += a.w * relax;
+    q[i] = b;
+}
+
+namespace launch {
+
+static void spmv(const DevMesh& m, const d4* J, const double* D, const d4* x, d4* y, cudaStream_t st)
+{
+    k_spmv<<<(m.NT + 255) / 256, 256, 0, st>>>(m, J, reinterpret_cast<const d4*>(D), x, y);
+}
+static void jacobi_sweep(const DevMesh& m, const d4* J, const double* D, const double* Dinv, const d4* r, const d4* z_in, d4* z_out, int first,
+                         cudaStream_t st)
+{
+    k_jacobi_sweep<<<(m.NT + 255) / 256, 256, 0, st>>>(m, J, reinterpret_cast<const d4*>(D), reinterpret_cast<const d4*>(Dinv), r, z_in, z_out, first);
+}
+static void invert_blocks(uint32_t n, const double* D, double* Dinv, int* singular, cudaStream_t st)
+{
+    k_invert_blocks<<<(n + 127) / 128, 128, 0, st>>>(n, D, Dinv, singular);
+}
+static void multi_dot(uint32_t n, const d4* V, size_t stride, int k, const d4* w, double* partial, double* out, cudaStream_t st)
+{
+    k_multi_dot_partial<<<KRY_BLOCKS, 256, 0, st>>>(n, V, stride, k, w, partial);
+    k_multi_dot_final<<<k, 256, 0, st>>>(KRY_BLOCKS, partial, out);
+}
+static void multi_axpy(uint32_t n, const d4* V, size_t stride, int k, const double* c, double sign, d4* w, cudaStream_t st)
+{
+    k_multi_axpy<<<(n + 255) / 256, 256, 0, st>>>(n, V, stride, k, c, sign, w);
+}
+static void scale_from(uint32_t n, const d4* x, const double* s, int root, int inv, d4* y, cudaStream_t st)
+{
+    k_scale_from<<<(n + 255) / 256, 256, 0, st>>>(n, x, s, root, inv, y);
+}
+static void sub(uint32_t n, const d4* a, const d4* b, d4* y, cudaStream_t st) { k_sub<<<(n + 255) / 256, 256, 0, st>>>(n, a, b, y); }
+static void axpy_state(uint32_t n, double relax, const d4* x, d4* q, cudaStream_t st) { k_axpy_state<<<(n + 255) / 256, 256, 0, st>>>(n, relax, x, q); }
+
+}  // namespace launch
+}  // namespace AFX_NS
+}  // namespace afx

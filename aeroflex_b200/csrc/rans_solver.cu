@@ -137,6 +137,16 @@ struct Solver {
     DBuf<d4> q, qkA, qkB, gx, gy, lim, qW, rhs, flux, stage;
     DBuf<double> dt, dt_ref;
     DBuf<d4> J; DBuf<double> D;   // Jacobian face blocks [E][16] d4 and diagonal blocks [NT][16]
+    // implicit step: block-Jacobi preconditioned restarted GMRES on the device
+    DBuf<double> Dinv, kry_partial, kry_h; DBuf<d4> kry_V, kry_w, kry_z, kry_t, kry_x; DBuf<int> kry_flag;
+    int gmres_restart = 30, gmres_max_iter = 500, precond_sweeps = 4;
+    double gmres_tol = 1e-2;
+    int last_linear_iters = 0;
+    bool precond_valid = false;
+    int compute_preconditioner();
+    void apply_preconditioner(const d4* r, d4* z);
+    bool gmres(const d4* b, d4* x);
+    double step_implicit(double relax, double tol, int rhs_iterations);
     DBuf<double> partial, norms, prm, scratch;
     DBuf<unsigned int> counters;  // [0] block counter, [1] norm ring index
     double* h_pinned = nullptr;   // pinned staging for scalars
@@ -515,7 +525,9 @@ void Solver::init_halo(const Partition& part, const char* nccl_id)
 {
     halo.reset(new Halo);
     Halo& h = *halo;
-    CK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    int prio_lo = 0, prio_hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    CK(cudaStreamCreateWithPriority(&cs, cudaStreamNonBlocking, prio_hi));  // halo kernels go ahead of the bulk update
     CK(cudaEventCreateWithFlags(&ev_front, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ev_halo, cudaEventDisableTiming));
     CK(cudaMallocHost(&h_stage, (size_t)NT * sizeof(d4)));
@@ -686,6 +698,152 @@ void Solver::fill_jacobian()
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));
     jac_valid = true;
+    precond_valid = false;
+}
+
+// implicitSolver::compute (solver.h:1160-1167): the reference factorises an ILUT here; we invert the diagonal
+// blocks for the block-Jacobi smoother that preconditions GMRES.  0 ok / -1 singular block.
+int Solver::compute_preconditioner()
+{
+    use();
+    if (!jac_valid) throw InvalidArg("afx_rans_fill_jacobian has not been called for the current state");
+    if (!Dinv.p) {
+        Dinv.alloc((size_t)NT * 16); kry_flag.alloc(1);
+        kry_V.alloc((size_t)(gmres_restart + 1) * NT); kry_w.alloc(NT); kry_z.alloc(NT); kry_t.alloc(NT); kry_x.alloc(NT);
+        kry_partial.alloc((size_t)(gmres_restart + 2) * 1024); kry_h.alloc(gmres_restart + 4);
+    }
+    kry_flag.zero(st);
+    kt->invert_blocks(NT, D.p, Dinv.p, kry_flag.p, st);
+    ++launches;
+    int* hflag = reinterpret_cast<int*>(h_pinned + 40);
+    CK(cudaMemcpyAsync(hflag, kry_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    precond_valid = (*hflag == 0);
+    return precond_valid ? 0 : -1;
+}
+
+// z = M^-1 r with M^-1 = `precond_sweeps` block-Jacobi sweeps on A z = r starting from z = 0
+void Solver::apply_preconditioner(const d4* r, d4* z)
+{
+    d4* a = z; d4* b = kry_t.p;
+    // an even number of swaps must leave the result in z
+    const int sweeps = std::max(1, precond_sweeps);
+    if ((sweeps - 1) % 2) std::swap(a, b);
+    kt->jacobi_sweep(dm, J.p, D.p, Dinv.p, r, nullptr, a, 1, st);
+    ++launches;
+    for (int k = 1; k < sweeps; ++k) {
+        kt->jacobi_sweep(dm, J.p, D.p, Dinv.p, r, a, b, 0, st);
+        ++launches;
+        std::swap(a, b);
+    }
+}
+
+// Left-preconditioned restarted GMRES, zero initial guess, stop on ||M^-1 (b - A x)|| <= tol ||M^-1 b||
+// (the criterion of Eigen::GMRES used at solver.h:886,906-910).  Arnoldi by classical Gram-Schmidt with all
+// inner products of a step in one reduction; the Givens recurrence runs on the host (one small D2H per step).
+bool Solver::gmres(const d4* b, d4* x)
+{
+    const int m = gmres_restart;
+    const size_t stride = NT;
+    double* hh = h_pinned + 48;  // never more than m+2 <= 16?  -> use a heap buffer
+    std::vector<double> hbuf((size_t)m + 4);
+    (void)hh;
+    CK(cudaMemsetAsync(x, 0, (size_t)NT * sizeof(d4), st));
+    last_linear_iters = 0;
+    // r = M^-1 b
+    d4* V0 = kry_V.p;
+    apply_preconditioner(b, kry_w.p);
+    kt->multi_dot(NT, kry_w.p, stride, 1, kry_w.p, kry_partial.p, kry_h.p, st); launches += 2;
+    CK(cudaMemcpyAsync(hbuf.data(), kry_h.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const double r0 = std::sqrt(hbuf[0]);
+    if (!(r0 == r0)) return false;
+    if (r0 == 0) return true;
+    double beta = r0;
+    std::vector<double> H((size_t)(m + 1) * m), cs(m), sn(m), g(m + 1), y(m);
+    while (last_linear_iters < gmres_max_iter) {
+        // V0 = r / beta   (kry_h[0] holds beta^2)
+        kt->scale_from(NT, kry_w.p, kry_h.p, 1, 1, V0, st); ++launches;
+        std::fill(g.begin(), g.end(), 0.0); g[0] = beta;
+        int k = 0;
+        bool done = false;
+        for (; k < m && last_linear_iters < gmres_max_iter; ++k) {
+            ++last_linear_iters;
+            // w = M^-1 A v_k
+            kt->spmv(dm, J.p, D.p, kry_V.p + (size_t)k * stride, kry_z.p, st); ++launches;
+            apply_preconditioner(kry_z.p, kry_w.p);
+            // h = V^T w ; w -= V h ; ||w||^2
+            kt->multi_dot(NT, kry_V.p, stride, k + 1, kry_w.p, kry_partial.p, kry_h.p, st); launches += 2;
+            kt->multi_axpy(NT, kry_V.p, stride, k + 1, kry_h.p, -1.0, kry_w.p, st); ++launches;
+            kt->multi_dot(NT, kry_w.p, stride, 1, kry_w.p, kry_partial.p, kry_h.p + (k + 1), st); launches += 2;
+            CK(cudaMemcpyAsync(hbuf.data(), kry_h.p, (size_t)(k + 2) * sizeof(double), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            const double hn = std::sqrt(hbuf[k + 1]);
+            for (int i = 0; i <= k; ++i) H[(size_t)i * m + k] = hbuf[i];
+            for (int i = 0; i < k; ++i) {
+                const double a = H[(size_t)i * m + k], c = H[(size_t)(i + 1) * m + k];
+                H[(size_t)i * m + k] = cs[i] * a + sn[i] * c;
+                H[(size_t)(i + 1) * m + k] = -sn[i] * a + cs[i] * c;
+            }
+            const double a = H[(size_t)k * m + k], den = std::sqrt(a * a + hn * hn);
+            if (!(den == den)) return false;
+            cs[k] = den == 0 ? 1 : a / den; sn[k] = den == 0 ? 0 : hn / den;
+            H[(size_t)k * m + k] = den;
+            g[k + 1] = -sn[k] * g[k]; g[k] = cs[k] * g[k];
+            const double err = std::fabs(g[k + 1]) / r0;
+            if (hn != 0 && k + 1 < m + 1) {  // v_{k+1} = w / ||w||   (kry_h[k+1] holds ||w||^2)
+                kt->scale_from(NT, kry_w.p, kry_h.p + (k + 1), 1, 1, kry_V.p + (size_t)(k + 1) * stride, st); ++launches;
+            }
+            if (err < gmres_tol || hn == 0) { ++k; done = true; break; }
+        }
+        // x += V y with H y = g
+        for (int i = k - 1; i >= 0; --i) {
+            double s = g[i];
+            for (int j = i + 1; j < k; ++j) s -= H[(size_t)i * m + j] * y[j];
+            y[i] = s / H[(size_t)i * m + i];
+        }
+        CK(cudaMemcpyAsync(kry_h.p, y.data(), (size_t)k * sizeof(double), cudaMemcpyHostToDevice, st));
+        kt->multi_axpy(NT, kry_V.p, stride, k, kry_h.p, 1.0, x, st); ++launches;
+        CK(cudaStreamSynchronize(st));  // y is reused
+        if (done) return true;
+        // restart: r = M^-1 (b - A x)
+        kt->spmv(dm, J.p, D.p, x, kry_z.p, st); ++launches;
+        kt->sub(NT, b, kry_z.p, kry_z.p, st); ++launches;
+        apply_preconditioner(kry_z.p, kry_w.p);
+        kt->multi_dot(NT, kry_w.p, stride, 1, kry_w.p, kry_partial.p, kry_h.p, st); launches += 2;
+        CK(cudaMemcpyAsync(hbuf.data(), kry_h.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        beta = std::sqrt(hbuf[0]);
+        if (!(beta == beta)) return false;
+        if (beta / r0 < gmres_tol) return true;
+    }
+    return false;  // Eigen reports NoConvergence -> the reference returns -1 (solver.h:1184)
+}
+
+// implicitSolver::solve, solver.h:1170-1213, with the frozen Jacobian of the last fill_jacobian
+double Solver::step_implicit(double relax, double tol, int rhs_iterations)
+{
+    use();
+    if (!jac_valid) throw InvalidArg("afx_rans_fill_jacobian has not been called for the current state");
+    if (!precond_valid && compute_preconditioner() != 0) return -1;
+    double err = residual_rhs();
+    if (!(err == err)) return -1;
+    if (err < tol) return err;
+    const double err_ini = err;
+    if (!gmres(rhs.p, kry_x.p)) return -1;
+    kt->axpy_state(NT, relax, kry_x.p, q.p, st); ++launches;
+    for (int i = 0; i < rhs_iterations; ++i) {
+        err = residual_rhs();
+        if (!(err == err)) return -1;
+        if (err < tol) return err;
+        if (err > 10 * err_ini) return err;
+        if (!gmres(rhs.p, kry_x.p)) return -1;
+        kt->axpy_state(NT, relax, kry_x.p, q.p, st); ++launches;
+    }
+    err = residual_rhs();
+    sync_ghost_rows();
+    CK(cudaStreamSynchronize(st));
+    return err;
 }
 
 void Solver::to_ref_order4(const d4* dev_new, double* host_out)
@@ -1036,11 +1194,36 @@ int afx_rans_get_jacobian_blocks(afx_rans* s, double* diag, double* off01, doubl
     });
 }
 
-int afx_rans_step_implicit(afx_rans*, double, double, int, double*)
+int afx_rans_compute(afx_rans* s)
 {
-    afx::set_error("afx_rans_step_implicit: the device Krylov solver is not built yet");
-    return AFX_ERR_INVALID;
+    int r = 0;
+    const int rc = guard([&] { r = s->s.compute_preconditioner(); });
+    return rc ? rc : (r == 0 ? AFX_OK : AFX_ERR_NUMERIC);
 }
+
+int afx_rans_step_implicit(afx_rans* s, double relaxation, double tol, int rhs_iterations, double* norm)
+{
+    double v = -1;
+    const int rc = guard([&] {
+        if (s->s.halo) throw afx::InvalidArg("the implicit step is single-GPU in this version");
+        v = s->s.step_implicit(relaxation, tol, rhs_iterations);
+    });
+    if (norm) *norm = v;
+    if (rc) return rc;
+    return v < 0 ? AFX_ERR_NUMERIC : AFX_OK;
+}
+
+int afx_rans_set_linear_solver(afx_rans* s, int restart, int max_iterations, double tolerance, int precond_sweeps)
+{
+    return guard([&] {
+        auto& S = s->s;
+        if (restart < 1 || max_iterations < 1 || tolerance <= 0 || precond_sweeps < 1) throw afx::InvalidArg("bad linear solver settings");
+        if (restart != S.gmres_restart) { S.Dinv.free(); S.precond_valid = false; }  // buffers are sized by the restart length
+        S.gmres_restart = restart; S.gmres_max_iter = max_iterations; S.gmres_tol = tolerance; S.precond_sweeps = precond_sweeps;
+    });
+}
+
+int afx_rans_last_linear_iterations(afx_rans* s) { return s->s.last_linear_iters; }
 
 int afx_rans_wall_forces(afx_rans* s, int patch, double out[3])
 {

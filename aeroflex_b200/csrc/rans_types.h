@@ -77,6 +77,16 @@ struct KernelTable {
     void (*permute4)(const d4* src, d4* dst, const uint32_t* idx, uint32_t n, cudaStream_t st);
     void (*permute1)(const double* src, double* dst, const uint32_t* idx, uint32_t n, uint32_t nsrc, cudaStream_t st);
     void (*scatter4)(const d4* src, d4* dst, const uint32_t* idx, uint32_t n, cudaStream_t st);  // dst[idx[i]] = src[i]
+    // implicit step (rans_krylov.cuh)
+    void (*spmv)(const DevMesh& m, const d4* J, const double* D, const d4* x, d4* y, cudaStream_t st);
+    void (*jacobi_sweep)(const DevMesh& m, const d4* J, const double* D, const double* Dinv, const d4* r, const d4* z_in, d4* z_out, int first,
+                         cudaStream_t st);
+    void (*invert_blocks)(uint32_t n, const double* D, double* Dinv, int* singular, cudaStream_t st);
+    void (*multi_dot)(uint32_t n, const d4* V, size_t stride, int k, const d4* w, double* partial, double* out, cudaStream_t st);  // 2 kernels
+    void (*multi_axpy)(uint32_t n, const d4* V, size_t stride, int k, const double* c, double sign, d4* w, cudaStream_t st);
+    void (*scale_from)(uint32_t n, const d4* x, const double* s, int root, int inv, d4* y, cudaStream_t st);
+    void (*sub)(uint32_t n, const d4* a, const d4* b, d4* y, cudaStream_t st);
+    void (*axpy_state)(uint32_t n, double relax, const d4* x, d4* q, cudaStream_t st);
 };
 
 namespace strict { const KernelTable& table(); }  // -fmad=false, reference expression order: bit-identical to the CPU reference

@@ -198,9 +198,18 @@ int afx_rans_residual(afx_rans* s, double* norm);
 int afx_rans_fill_jacobian(afx_rans* s);
 /* the 4x4 blocks of that matrix: diag[(N+G)][16], off01[E][16] (row c0, col c1), off10[E][16]; row-major blocks */
 int afx_rans_get_jacobian_blocks(afx_rans* s, double* diag, double* off01, double* off10);
-/* implicitSolver::compute + solve (solver.h:1160-1213): GMRES(30) on the device with the frozen Jacobian
- * of the last afx_rans_fill_jacobian; *norm = final ||RhoVector||_2, AFX_ERR_NUMERIC where the reference returns -1 */
+/* implicitSolver::compute (solver.h:1160-1167): prepares the preconditioner of the last afx_rans_fill_jacobian.  The
+ * reference factorises an Eigen::IncompleteLUT there; this library inverts the 4x4 diagonal blocks for a
+ * block-Jacobi smoother.  AFX_ERR_NUMERIC where the reference returns -1. */
+int afx_rans_compute(afx_rans* s);
+/* implicitSolver::solve (solver.h:1170-1213): RHS, left-preconditioned restarted GMRES on the device with the
+ * frozen Jacobian, q += relaxation * dq, up to 1 + rhs_iterations times with the reference's early exits;
+ * *norm = final ||RhoVector||_2.  AFX_ERR_NUMERIC (and *norm = -1) where the reference returns -1.  The linear
+ * solver is NOT Eigen's: per-iteration histories of the implicit path are "parity unpinned" (DESIGN.md). */
 int afx_rans_step_implicit(afx_rans* s, double relaxation, double tol, int rhs_iterations, double* norm);
+/* defaults mirror solver.h:906-910 (restart 30, 500 iterations, tolerance 1e-2); precond_sweeps block-Jacobi sweeps */
+int afx_rans_set_linear_solver(afx_rans* s, int restart, int max_iterations, double tolerance, int precond_sweeps);
+int afx_rans_last_linear_iterations(afx_rans* s);
 /* get_wall_profile (post.h:301-387): out = {cl, cd, cm} of one patch */
 int afx_rans_wall_forces(afx_rans* s, int patch, double out_cl_cd_cm[3]);
 /* CpProfile::calc_cp (post.h:248-298): cp of the owner cell of every boundary edge of the patch, boundary order;
