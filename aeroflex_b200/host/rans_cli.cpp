@@ -1,0 +1,47 @@
+// rans_cli.cpp -- the RANS leg of AeroFLEX's CLI mode (reference: src/aeroflex/src/app.cpp:168-176, 829-854):
+//   rans_cli -i conf.ini [-m mesh_dir] [-a airfoil] [--math strict|fast] [-q]
+// reads the [rans-*] sections of an AeroFLEX conf.ini, runs rans.compute_alphas() and rans.solve_airfoil() on the GPU
+// and prints the polar table (alpha, CL, CD, CM) that the VLM viscous correction would consume.
+#include <cstdio>
+#include <cstdlib>
+#include <iostream>
+#include <string>
+
+#include "rans_b200/rans.h"
+
+int main(int argc, char** argv) {
+    std::string conf, mesh_dir = "../../../../examples/rans/", airfoil = "naca0012q", math;
+    bool quiet = false;
+    for (int i = 1; i < argc; ++i) {
+        const std::string a = argv[i];
+        if (a == "-i" && i + 1 < argc) conf = argv[++i];
+        else if (a == "-m" && i + 1 < argc) mesh_dir = argv[++i];
+        else if (a == "-a" && i + 1 < argc) airfoil = argv[++i];
+        else if (a == "--math" && i + 1 < argc) math = argv[++i];
+        else if (a == "-q") quiet = true;
+    }
+    if (conf.empty()) { std::fprintf(stderr, "usage: %s -i conf.ini [-m mesh_dir] [-a airfoil] [--math strict|fast] [-q]\n", argv[0]); return 2; }
+    if (!math.empty()) setenv("AFX_MATH", math.c_str(), 1);
+    try {
+        std::cout << "CLI mode" << std::endl;
+        GUIHandler gui;
+        rans::Rans rans(gui);
+        tiny::config io;
+        if (!io.read(conf)) return 1;
+        rans.settings.import_config_file(io);
+        rans.mesh_dir = mesh_dir;
+        rans.verbose = !quiet;
+        rans.compute_alphas();
+        database::airfoil db;
+        db.alpha = rans.alphas;
+        rans.solve_airfoil(airfoil, db);
+        for (auto txt = gui.msg.pop(); txt.has_value(); txt = gui.msg.pop()) std::cout << txt.value() << std::endl;
+        std::printf("# alpha_deg CL CD CM\n");
+        for (size_t i = 0; i < db.cl.size(); ++i) std::printf("POLAR %.17g %.17g %.17g %.17g\n", db.alpha[i], db.cl[i], db.cd[i], db.cmy[i]);
+        std::printf("# outer iterations recorded: %d\n", (int)rans.iters);
+    } catch (std::exception& e) {
+        std::cout << e.what() << std::endl;
+        return 1;
+    }
+    return 0;
+}

@@ -161,8 +161,37 @@ def sweep_case():
     print("sweep", r)
 
 
+def prolong_case():
+    """FMG prolongation of the reference (multigrid.h:100-178) between two synthetic O-meshes written by our MSH writer."""
+    import tempfile
+    import aeroflex_b200 as afx
+    dims = ((48, 24, 8), (96, 48, 16))
+    with tempfile.TemporaryDirectory() as td:
+        paths = []
+        for k, (ni, nj, nq) in enumerate(dims):
+            m = afx.Mesh.synth_omesh(ni, nj, nq, 60.0)
+            paths.append(os.path.join(td, "m%d.msh" % k))
+            m.write_msh(paths[-1])
+        mc = ref.RefMesh(paths[0]); mf = ref.RefMesh(paths[1])
+        rng = np.random.default_rng(99)
+        qc = rng.uniform(0.5, 1.5, 4 * (mc.N + mc.G))
+        qf = ref.prolongate(paths[0], paths[1], qc, 4 * (mf.N + mf.G))
+    np.savez_compressed(os.path.join(OUT, "prolongation.npz"), dims=np.array(dims), far_radius=np.array(60.0), q_coarse=qc, q_fine=qf)
+    print("prolongation", qf.shape, float(np.abs(qf).max()))
+
+
+def mesh_only(tag, mesh_file):
+    rm = ref.RefMesh(REF_MESHES + mesh_file)
+    np.savez_compressed(os.path.join(OUT, tag + ".npz"), **mesh_fixture(rm))
+    print(tag, rm.N, rm.G, rm.E)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "extra":
+        prolong_case()
+        mesh_only("naca0012q_mid_mesh", "naca0012q_mid.msh")
+        sys.exit(0)
     slip = {"farfield": ("farfield", FAR), "wall": ("slip-wall", None)}
     wall = {"farfield": ("farfield", FAR), "wall": ("wall", None)}
     face_cases()
@@ -179,3 +208,7 @@ if __name__ == "__main__":
     implicit_case("naca0012q_coarse_implicit_blocks", "naca0012q_coarse.msh", slip, "inviscid", "green-gauss", True)
     implicit_case("naca0012_coarse_implicit_laminar_blocks", "naca0012_coarse.msh", wall, "laminar", "green-gauss", True)
     sweep_case()
+    prolong_case()
+    mesh_only("naca0012q_mid_mesh", "naca0012q_mid.msh")
+    # tests/golden/sweep_naca0012q_fmg.npz (coarse -> mid FMG at tolerance 1e-10, ~10 minutes of CPU) is made by
+    # oracle/make_golden_fmg.py

@@ -76,6 +76,7 @@ def lib():
                                 C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
                                 C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_char_p,
                                 C.c_int, f64p, f64p, f64p, f64p, C.POINTER(C.c_int), C.POINTER(C.c_double), C.c_int]
+    L.ref_prolongate.argtypes = [C.c_char_p, C.c_char_p, f64p, f64p]
     _lib = L
     return L
 
@@ -240,3 +241,11 @@ def run_sweep(mesh_paths, alphas_deg, implicit=True, viscosity="inviscid", gradi
     if rc < 0:
         raise RuntimeError(lib().ref_last_error().decode())
     return dict(cl=cl, cd=cd, cm=cm, iters=np.array(list(iters)), seconds=secs.value, done=rc)
+
+
+def prolongate(coarse_path, fine_path, q_coarse, n_fine4):
+    """The reference's own FMG prolongation (multigrid.h:100-178): q_fine = mapper * q_coarse."""
+    out = np.zeros(n_fine4)
+    if lib().ref_prolongate(coarse_path.encode(), fine_path.encode(), np.ascontiguousarray(q_coarse, np.float64), out):
+        raise RuntimeError(lib().ref_last_error().decode())
+    return out

@@ -361,4 +361,27 @@ int ref_run_sweep(int n_mesh, const char** mesh_paths, int implicit, const char*
     return rc ? rc : done;
 }
 
+// multigrid<explicitSolver>::gen_mapper(0) applied to q_coarse (multigrid.h:100-178, 312): q_fine = mapper * q_coarse
+int ref_prolongate(const char* coarse_path, const char* fine_path, const double* q_coarse, double* q_fine) {
+    return guarded([&] {
+        std::ostringstream sink;
+        std::streambuf* old = std::cout.rdbuf(sink.rdbuf());
+        struct Restore { std::streambuf* o; ~Restore() { std::cout.rdbuf(o); } } restore{old};
+        GUIHandler gui;
+        rans::Settings st;
+        st.bcs["farfield"].bc_type = "farfield";
+        st.bcs["wall"].bc_type = "slip-wall";
+        st.set_solver_type("explicit");
+        std::vector<double> residuals = {1.0};
+        std::atomic<int> iters{0};
+        rans::CpProfile profile;
+        std::vector<rans::mesh> ms = {rans::mesh(std::string(coarse_path)), rans::mesh(std::string(fine_path))};
+        rans::multigrid<rans::explicitSolver> multi(ms, st, gui, residuals, iters, profile);
+        Eigen::VectorXd& qc = multi.solvers[0].get_q();
+        std::copy(q_coarse, q_coarse + qc.size(), qc.data());
+        Eigen::VectorXd qf = multi.mappers[0] * qc;
+        std::copy(qf.data(), qf.data() + qf.size(), q_fine);
+    });
+}
+
 }  // extern "C"

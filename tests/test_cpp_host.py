@@ -1,0 +1,134 @@
+"""The C++ host adapter (aeroflex_b200/host/rans_b200/*.h: rans::Settings, rans::mesh, rans::solver,
+rans::multigrid, rans::Rans) -- compiled with g++ against the C-ABI library and driven like the reference's CLI."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests import helpers as H
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "aeroflex_b200", "host")
+
+CONF = """[rans-gas]
+gamma = 1.4
+R = 0.71428571428
+
+[rans-bc]
+<
+    name = farfield,
+    type = farfield,
+    T = 1,
+    mach = 0.2,
+    angle = 420.0,
+    p = 1,
+>
+<name = wall, type = slip-wall>
+
+[rans-alphas]
+alpha_start = 1.0
+alpha_end = %(alpha_end)s
+alpha_step = 3.0
+
+[rans-solver]
+solver = %(solver)s
+viscosity = inviscid
+gradient = green-gauss
+second_order = true
+relaxation = 0.9
+start_cfl = %(start_cfl)s
+slope_cfl = 50.0
+max_cfl = 100.0
+tolerance = %(tol)s
+rhs_iterations = 5
+max_iterations = %(max_it)s
+limiter_k = 5.0
+"""
+
+
+def _build(afx, src, out):
+    lib_dir = os.path.dirname(afx.library_path())
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-fopenmp", "-Wall", "-Werror", "-I" + HOST, "-o", str(out), src,
+                    "-L" + lib_dir, "-laeroflex_rans_b200", "-Wl,-rpath," + lib_dir], check=True)
+    return str(out)
+
+
+@pytest.fixture(scope="module")
+def exes(afx, tmp_path_factory):
+    d = tmp_path_factory.mktemp("cpp")
+    return dict(test_host=_build(afx, os.path.join(ROOT, "tests", "cpp", "test_host.cpp"), d / "test_host"),
+                cli=_build(afx, os.path.join(HOST, "rans_cli.cpp"), d / "rans_cli"), dir=d)
+
+
+def test_conf_ini_contract(exes, tmp_path):
+    """Same sections, keys and defaults as Settings::import_config_file (core.h:238-272), incl. the vector entries."""
+    ini = tmp_path / "conf.ini"
+    ini.write_text(CONF % dict(solver="implicit", tol="1e-4", max_it=300, alpha_end="7.0", start_cfl="40.0"))
+    out = subprocess.run([exes["test_host"], "conf", str(ini), str(tmp_path / "rt.ini")], capture_output=True, text=True, check=True).stdout
+    assert "solver=implicit viscosity=inviscid gradient=green-gauss second_order=1" in out
+    assert "start_cfl=40 slope_cfl=50 max_cfl=100 tolerance=0.0001 rhs_iterations=5 max_iterations=300 limiter_k=5 alpha=1:7:3" in out
+    assert "bc farfield type=farfield mach=0.20000000000000001 angle=420 T=1 p=1" in out
+    assert "bc wall type=slip-wall" in out and "roundtrip 1" in out
+    bad = tmp_path / "bad.ini"  # exactly two rans-bc entries are required (core.h:239)
+    bad.write_text((CONF % dict(solver="implicit", tol="1e-4", max_it=300, alpha_end="7.0", start_cfl="40.0")).replace("<name = wall, type = slip-wall>", ""))
+    r = subprocess.run([exes["test_host"], "conf", str(bad), str(tmp_path / "rt2.ini")], capture_output=True, text=True)
+    assert r.returncode == 1 and "[RANS] Invalid number of boundary conditions" in r.stdout
+
+
+def test_fmg_prolongation_matches_reference(afx, exes, tmp_path):
+    """multigrid::gen_mapper (multigrid.h:100-178): same cells, same weights, same sums -> bit-identical q_fine."""
+    g = np.load(os.path.join(H.GOLDEN, "prolongation.npz"))
+    paths = []
+    for k, (ni, nj, nq) in enumerate(g["dims"]):
+        m = afx.Mesh.synth_omesh(int(ni), int(nj), int(nq), float(g["far_radius"]))
+        paths.append(str(tmp_path / ("m%d.msh" % k)))
+        m.write_msh(paths[-1])
+    g["q_coarse"].astype(np.float64).tofile(tmp_path / "qc.bin")
+    subprocess.run([exes["test_host"], "prolong", paths[0], paths[1], str(tmp_path / "qc.bin"), str(tmp_path / "qf.bin")], check=True,
+                   capture_output=True)
+    qf = np.fromfile(tmp_path / "qf.bin")
+    assert np.array_equal(qf, g["q_fine"])
+
+
+def test_cli_fails_loudly_without_gpu(afx, exes, tmp_path):
+    if afx.device_count() > 0:
+        pytest.skip("a GPU is visible")
+    ini = tmp_path / "conf.ini"
+    ini.write_text(CONF % dict(solver="explicit", tol="1e-4", max_it=10, alpha_end="1.0", start_cfl="1.5"))
+    for tag in ("naca0012q_coarse_euler_gg_o2",):
+        H.product_mesh(afx, H.load(tag)).write_msh(tmp_path / "naca0012q_coarse.msh")
+    H.product_mesh(afx, H.load("naca0012q_mid_mesh")).write_msh(tmp_path / "naca0012q_mid.msh")
+    r = subprocess.run([exes["cli"], "-i", str(ini), "-m", str(tmp_path) + "/", "-q"], capture_output=True, text=True)
+    assert r.returncode == 1 and "no CUDA device" in r.stdout
+
+
+@pytest.mark.gpu
+def test_cli_polar_sweep_matches_reference_fmg(afx, gpu, exes, tmp_path):
+    """BASELINE config 1: the conf.ini airfoil case (implicit, FMG coarse -> mid, alpha sweep) through rans::Rans::solve_airfoil
+    on the GPU against the reference's own run, both driven to 1e-10 so that the converged CL/CD/CM are comparable."""
+    gold = np.load(os.path.join(H.GOLDEN, "sweep_naca0012q_fmg.npz"))
+    H.product_mesh(afx, H.load("naca0012q_coarse_euler_gg_o2")).write_msh(tmp_path / "naca0012q_coarse.msh")
+    H.product_mesh(afx, H.load("naca0012q_mid_mesh")).write_msh(tmp_path / "naca0012q_mid.msh")
+    ini = tmp_path / "conf.ini"
+    ini.write_text(CONF % dict(solver="implicit", tol="1e-10", max_it=400, alpha_end="4.0", start_cfl="40.0"))
+    r = subprocess.run([exes["cli"], "-i", str(ini), "-m", str(tmp_path) + "/", "-q"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:]
+    rows = [[float(v) for v in l.split()[1:]] for l in r.stdout.splitlines() if l.startswith("POLAR")]
+    assert [row[0] for row in rows] == [1.0, 4.0]
+    for row, cl, cd, cm in zip(rows, gold["cl"], gold["cd"], gold["cm"]):
+        assert row[1] == pytest.approx(cl, rel=1e-6)
+        assert row[2] == pytest.approx(cd, rel=1e-5)
+        assert row[3] == pytest.approx(cm, rel=1e-5)
+
+
+@pytest.mark.gpu
+def test_cli_explicit_mode_runs(afx, gpu, exes, tmp_path):
+    H.product_mesh(afx, H.load("naca0012q_coarse_euler_gg_o2")).write_msh(tmp_path / "naca0012q_coarse.msh")
+    H.product_mesh(afx, H.load("naca0012q_mid_mesh")).write_msh(tmp_path / "naca0012q_mid.msh")
+    ini = tmp_path / "conf.ini"
+    ini.write_text(CONF % dict(solver="explicit", tol="1e-3", max_it=2000, alpha_end="1.0", start_cfl="1.5"))
+    r = subprocess.run([exes["cli"], "-i", str(ini), "-m", str(tmp_path) + "/", "-q"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:]
+    rows = [[float(v) for v in l.split()[1:]] for l in r.stdout.splitlines() if l.startswith("POLAR")]
+    assert len(rows) == 1 and 0.05 < rows[0][1] < 0.2  # CL at 1 degree
