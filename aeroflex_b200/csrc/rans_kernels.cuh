@@ -50,7 +50,7 @@ __device__ __forceinline__ double spectral_radius(const d4& q, double nx, double
 // least-squares (470-513).  Source state is the iteration-start q.
 // ---------------------------------------------------------------------------
 template <int GRAD>
-__global__ void __launch_bounds__(256) k_dt_grad(DevMesh m, d4* __restrict__ q, double* __restrict__ dt,
+__global__ void __launch_bounds__(256, 3) k_dt_grad(DevMesh m, d4* __restrict__ q, double* __restrict__ dt,
                                                  d4* __restrict__ gx, d4* __restrict__ gy, const double* __restrict__ prm,
                                                  double gam, int want_grad, int walls)
 {
@@ -176,6 +176,28 @@ __global__ void __launch_bounds__(256, AFX_LIM_MINB) k_limiter(DevMesh m, const 
     const d4 dmax = mk4(hi.x - qi.x, hi.y - qi.y, hi.z - qi.z, hi.w - qi.w);
     const d4 dmin = mk4(lo.x - qi.x, lo.y - qi.y, lo.z - qi.z, lo.w - qi.w);
     d4 l = mk4(1, 1, 1, 1);
+#if AFX_FAST
+    // Where the limiter function is below 1 it decreases monotonically with |dqg| (d phi/d dqg < 0 for dqg > dm/2), and
+    // values above 1 never survive the min with 1: the minimum over the faces is attained at the largest positive and
+    // the most negative projected increment -> 2 evaluations per component instead of one per face.
+    d4 pmax = mk4(0, 0, 0, 0), pmin = mk4(0, 0, 0, 0);
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const uint32_t cfv = cfs[s];
+        if (cfv == CF_NONE) continue;
+        const d4 gB = m.fgB[cfv & CF_ID];
+        const double dx = (cfv & CF_SIDE) ? gB.z : gB.x, dy = (cfv & CF_SIDE) ? gB.w : gB.y;
+        const double p0 = gxi.x * dx + gyi.x * dy, p1 = gxi.y * dx + gyi.y * dy, p2 = gxi.z * dx + gyi.z * dy, p3 = gxi.w * dx + gyi.w * dy;
+        pmax.x = fmax(pmax.x, p0); pmax.y = fmax(pmax.y, p1); pmax.z = fmax(pmax.z, p2); pmax.w = fmax(pmax.w, p3);
+        pmin.x = fmin(pmin.x, p0); pmin.y = fmin(pmin.y, p1); pmin.z = fmin(pmin.z, p2); pmin.w = fmin(pmin.w, p3);
+    }
+    l.x = fmin(fmin(1.0, venkat(pmax.x, dmax.x, dmin.x, K3a)), venkat(pmin.x, dmax.x, dmin.x, K3a));
+    l.y = fmin(fmin(1.0, venkat(pmax.y, dmax.y, dmin.y, K3a)), venkat(pmin.y, dmax.y, dmin.y, K3a));
+    l.z = fmin(fmin(1.0, venkat(pmax.z, dmax.z, dmin.z, K3a)), venkat(pmin.z, dmax.z, dmin.z, K3a));
+    l.w = fmin(fmin(1.0, venkat(pmax.w, dmax.w, dmin.w, K3a)), venkat(pmin.w, dmax.w, dmin.w, K3a));
+    lim[i] = l;
+    return;
+#endif
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
         const uint32_t cfv = cfs[s];
@@ -332,18 +354,19 @@ __global__ void __launch_bounds__(256) k_gather_update(DevMesh m, const d4* __re
             o.y = q0.y + r.y * dti * alpha * relax;
             o.z = q0.z + r.z * dti * alpha * relax;
             o.w = q0.w + r.w * dti * alpha * relax;
-            const d4 prev = LAST ? qk_in[i] : o;
             qk_out[i] = o;
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
                 const uint32_t cfv = bnd[s];
                 if (!walls || cfv == CF_NONE || !(cfv & CF_BND)) continue;
                 const int kind = m.fkind[cfv & CF_ID];
-                if (kind == K_SLIPWALL || kind == K_WALL) qk_out[m.fcells[cfv & CF_ID].y] = prev;
+                // wall ghosts of the next stage follow their owner; after the last stage the ghost keeps the state its
+                // owner had when the stage started (solver.h:811 ran before the update)
+                if (kind == K_SLIPWALL || kind == K_WALL) qk_out[m.fcells[cfv & CF_ID].y] = LAST ? qk_in[i] : o;
             }
         }
         if (LAST) {
-            qW[i] = r;
+            if (MODE != 0 || prm[2] != 0.0) qW[i] = r;  // prm[2]: keep qW (only the last iteration of a run needs it)
             nrm += r.x * r.x + r.y * r.y + r.z * r.z + r.w * r.w;
         }
     }

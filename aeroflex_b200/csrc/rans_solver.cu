@@ -115,7 +115,7 @@ struct Solver {
     int viscosity_model = 0, viscous_type = 0, visc_not_inviscid = 0;
     int second_order = 1, gradient_scheme = AFX_GRAD_GREEN_GAUSS;
     double limiter_k = 5., cfl = 1.;
-    double relax_dev = -1, cfl_dev = -1;
+    double relax_dev = -1, cfl_dev = -1, keep_dev = -1;
 
     // permutations (host)
     std::vector<uint32_t> c_old2new, c_new2old, f_old2new, f_new2old;
@@ -193,7 +193,7 @@ struct Solver {
     void reduce_norms(double* v, int n);
     void set_bcs(int n_patch, const uint8_t* kinds, const afx_bvars* vars);
     void set_options(int so, int grad, double k);
-    void push_params(double relax);
+    void push_params(double relax, bool keep_qW = true);
     void launch_dt_grad(bool want_grad, bool walls);
     void launch_limiter(const d4* qk);
     void launch_flux(const d4* qk, bool uniform, d4 qfar);
@@ -452,13 +452,14 @@ void Solver::set_options(int so, int grad, double k)
     invalidate_graph();
 }
 
-void Solver::push_params(double relax)
+void Solver::push_params(double relax, bool keep_qW)
 {
-    if (relax == relax_dev && cfl == cfl_dev) return;
-    h_pinned[32] = cfl; h_pinned[33] = relax;
-    CK(cudaMemcpyAsync(prm.p, h_pinned + 32, 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+    const double kq = keep_qW ? 1.0 : 0.0;
+    if (relax == relax_dev && cfl == cfl_dev && kq == keep_dev) return;
+    h_pinned[32] = cfl; h_pinned[33] = relax; h_pinned[34] = kq;
+    CK(cudaMemcpyAsync(prm.p, h_pinned + 32, 3 * sizeof(double), cudaMemcpyHostToDevice, st));
     CK(cudaStreamSynchronize(st));  // the pinned slot is reused
-    relax_dev = relax; cfl_dev = cfl;
+    relax_dev = relax; cfl_dev = cfl; keep_dev = kq;
 }
 
 void Solver::launch_dt_grad(bool want_grad, bool walls)
@@ -600,7 +601,8 @@ void Solver::run_explicit(double relax, int n_iter, double* norms_out)
     use();
     if (!bcs_set) throw InvalidArg("set_bcs has not been called");
     if (n_iter <= 0) return;
-    push_params(relax);
+    push_params(relax, n_iter == 1);  // qW is kept for the last iteration of the call only
+    h_pinned[35] = 1.0;               // constant source of the "keep qW" flag, never rewritten
     CK(cudaEventRecord(ev0, st));
     int done = 0;
     while (done < n_iter) {
@@ -623,10 +625,22 @@ void Solver::run_explicit(double relax, int n_iter, double* norms_out)
                 CK(cudaGraphDestroy(g));
             }
             const int64_t per_iter = graph_per_iter;
-            for (int it = 0; it < chunk; ++it) CK(cudaGraphLaunch(graph_exec, st));
+            for (int it = 0; it < chunk; ++it) {
+                if (done + it == n_iter - 1 && keep_dev != 1.0) {
+                    CK(cudaMemcpyAsync(prm.p + 2, h_pinned + 35, sizeof(double), cudaMemcpyHostToDevice, st));
+                    keep_dev = 1.0;
+                }
+                CK(cudaGraphLaunch(graph_exec, st));
+            }
             launches += (int64_t)per_iter * chunk;
         } else {
-            for (int it = 0; it < chunk; ++it) explicit_iteration();
+            for (int it = 0; it < chunk; ++it) {
+                if (done + it == n_iter - 1 && keep_dev != 1.0) {
+                    CK(cudaMemcpyAsync(prm.p + 2, h_pinned + 35, sizeof(double), cudaMemcpyHostToDevice, st));
+                    keep_dev = 1.0;
+                }
+                explicit_iteration();
+            }
         }
         CK(cudaGetLastError());
         if (norms_out) {

@@ -205,26 +205,37 @@ def main():
 
     # per-phase kernel times (CUDA events between the phases, same state, right after the timed region)
     prof = s.profile_explicit(5, RELAX)
-    flux_ms = prof["flux"] / 3.0
     n_loc = N if part is None else part.n_own
-    alg_flux = (144.0 * N + 48.0 * E) * n_loc / N      # this rank's share
-    alg_iter = (1488.0 * N + 296.0 * E) * n_loc / N
+    share = n_loc / N  # this rank's share of the cells
+    # algorithmic bytes per launch (DESIGN.md section 5 / SURVEY.md 8d), launches per iteration, phase time per iteration
+    kernels = {"k_flux": ((144.0 * N + 48.0 * E) * share, 3, prof["flux"]),
+               "k_limiter": ((152.0 * N + 24.0 * E) * share, 3, prof["limiter"]),
+               "k_gather_update": ((144.0 * N + 32.0 * E) * share, 3, prof["gather_update"]),
+               "k_dt_grad": ((168.0 * N + 80.0 * E) * share, 1, prof["dt_grad"])}
+    alg_iter = (1488.0 * N + 296.0 * E) * share
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    traffic = None
+    traffic_tab = {}
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "k_flux_traffic.json"))).get(workload)
+        traffic_tab = json.load(open(os.path.join(ROOT, "profiles", "kernel_traffic.json"))).get(workload, {})
     except Exception:
         pass
-    roof = {"bound": "hbm", "kernel": "k_flux<second order, inviscid flux>", "achieved": alg_flux / (flux_ms * 1e-3) / 1e9, "peak": peak,
-            "unit": "GB/s", "frac": alg_flux / (flux_ms * 1e-3) / 1e9 / peak, "traffic": traffic,
+    per_kernel = {}
+    for k, (bytes_, n_launch, ms) in kernels.items():
+        t = ms / n_launch
+        per_kernel[k] = {"algorithmic_bytes_per_launch": bytes_, "launches_per_iteration": n_launch, "kernel_ms": t,
+                         "achieved": bytes_ / (t * 1e-3) / 1e9 if t > 0 else None, "frac": bytes_ / (t * 1e-3) / 1e9 / peak if t > 0 else None,
+                         "share_of_iteration": ms / sum(v[2] for v in kernels.values()), "traffic": traffic_tab.get(k)}
+    dom = max(per_kernel, key=lambda k: per_kernel[k]["share_of_iteration"])
+    roof = {"bound": "hbm", "kernel": dom, "achieved": per_kernel[dom]["achieved"], "peak": peak, "unit": "GB/s",
+            "frac": per_kernel[dom]["frac"], "traffic": per_kernel[dom]["traffic"],
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
-            "algorithmic_bytes_per_launch": alg_flux, "kernel_ms": flux_ms,
-            "phase_ms_per_iteration": prof,
+            "algorithmic_bytes_per_launch": per_kernel[dom]["algorithmic_bytes_per_launch"], "kernel_ms": per_kernel[dom]["kernel_ms"],
+            "kernels": per_kernel, "phase_ms_per_iteration": prof,
             "iteration": {"algorithmic_bytes": alg_iter, "achieved": alg_iter / (t_ms / a.steps * 1e-3) / 1e9,
                           "frac": alg_iter / (t_ms / a.steps * 1e-3) / 1e9 / peak}}
 

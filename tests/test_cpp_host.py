@@ -107,7 +107,10 @@ def test_cli_fails_loudly_without_gpu(afx, exes, tmp_path):
 def test_cli_polar_sweep_matches_reference_fmg(afx, gpu, exes, tmp_path):
     """BASELINE config 1: the conf.ini airfoil case (implicit, FMG coarse -> mid, alpha sweep) through rans::Rans::solve_airfoil
     on the GPU against the reference's own run, both driven to 1e-10 so that the converged CL/CD/CM are comparable."""
-    gold = np.load(os.path.join(H.GOLDEN, "sweep_naca0012q_fmg.npz"))
+    path = os.path.join(H.GOLDEN, "sweep_naca0012q_fmg.npz")
+    if not os.path.exists(path):
+        pytest.skip("golden FMG sweep not generated (oracle/make_golden_fmg.py)")
+    gold = np.load(path)
     H.product_mesh(afx, H.load("naca0012q_coarse_euler_gg_o2")).write_msh(tmp_path / "naca0012q_coarse.msh")
     H.product_mesh(afx, H.load("naca0012q_mid_mesh")).write_msh(tmp_path / "naca0012q_mid.msh")
     ini = tmp_path / "conf.ini"
