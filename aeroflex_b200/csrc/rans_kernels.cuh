@@ -65,10 +65,9 @@ __global__ void __launch_bounds__(256, 3) k_dt_grad(DevMesh m, d4* __restrict__ 
         if (cfv == CF_NONE) continue;
         const uint32_t f = cfv & CF_ID;
         const bool side = cfv & CF_SIDE;
-        const uint2 fc = m.fcells[f];
+        const uint32_t j = m.cnb[(size_t)s * m.N + i];
         const d4 gA = m.fgA[f];
-        const int kind = m.fkind[f];
-        const uint32_t j = side ? fc.x : fc.y;
+        const int kind = (cfv & CF_BND) ? (int)m.fkind[f] : K_INTERNAL;
         const bool wall_ghost = walls && (cfv & CF_BND) && (kind == K_SLIPWALL || kind == K_WALL);
         if (wall_ghost) q[j] = qi;  // ghost <- owner (set_walls_from_internal)
         const d4 qj = wall_ghost ? qi : q[j];
@@ -157,16 +156,24 @@ __global__ void __launch_bounds__(256, AFX_LIM_MINB) k_limiter(DevMesh m, const 
     if (i >= m.n_grad) return;
     const d4 qi = qk[i];
     d4 lo = qi, hi = qi;
-    uint32_t cfs[4];
+    uint32_t nbs[4];
+    double2 dxy[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {  // independent coalesced loads first
+        nbs[s] = m.cnb[(size_t)s * m.N + i];
+        dxy[s] = m.cdxy[(size_t)s * m.N + i];
+    }
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
-        const uint32_t cfv = m.cf[(size_t)s * m.N + i];
-        cfs[s] = cfv;
-        if (cfv == CF_NONE) continue;
-        const uint2 fc = m.fcells[cfv & CF_ID];
+        const uint32_t j = nbs[s];
+        if (j == CF_NONE) continue;
         // a wall ghost holds its owner's state (set_walls_from_internal): no need to read it
-        const bool wall_ghost = walls && (cfv & CF_BND) && (m.fkind[cfv & CF_ID] == K_SLIPWALL || m.fkind[cfv & CF_ID] == K_WALL);
-        const d4 qj = wall_ghost ? qi : qk[(cfv & CF_SIDE) ? fc.x : fc.y];
+        bool wall_ghost = false;
+        if (walls && j >= m.N) {
+            const int kind = m.fkind[m.cf[(size_t)s * m.N + i] & CF_ID];
+            wall_ghost = (kind == K_SLIPWALL || kind == K_WALL);
+        }
+        const d4 qj = wall_ghost ? qi : qk[j];
         lo.x = fmin(lo.x, qj.x); lo.y = fmin(lo.y, qj.y); lo.z = fmin(lo.z, qj.z); lo.w = fmin(lo.w, qj.w);
         hi.x = fmax(hi.x, qj.x); hi.y = fmax(hi.y, qj.y); hi.z = fmax(hi.z, qj.z); hi.w = fmax(hi.w, qj.w);
     }
@@ -183,10 +190,8 @@ __global__ void __launch_bounds__(256, AFX_LIM_MINB) k_limiter(DevMesh m, const 
     d4 pmax = mk4(0, 0, 0, 0), pmin = mk4(0, 0, 0, 0);
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
-        const uint32_t cfv = cfs[s];
-        if (cfv == CF_NONE) continue;
-        const d4 gB = m.fgB[cfv & CF_ID];
-        const double dx = (cfv & CF_SIDE) ? gB.z : gB.x, dy = (cfv & CF_SIDE) ? gB.w : gB.y;
+        if (nbs[s] == CF_NONE) continue;
+        const double dx = dxy[s].x, dy = dxy[s].y;
         const double p0 = gxi.x * dx + gyi.x * dy, p1 = gxi.y * dx + gyi.y * dy, p2 = gxi.z * dx + gyi.z * dy, p3 = gxi.w * dx + gyi.w * dy;
         pmax.x = fmax(pmax.x, p0); pmax.y = fmax(pmax.y, p1); pmax.z = fmax(pmax.z, p2); pmax.w = fmax(pmax.w, p3);
         pmin.x = fmin(pmin.x, p0); pmin.y = fmin(pmin.y, p1); pmin.z = fmin(pmin.z, p2); pmin.w = fmin(pmin.w, p3);
@@ -200,10 +205,8 @@ __global__ void __launch_bounds__(256, AFX_LIM_MINB) k_limiter(DevMesh m, const 
 #endif
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
-        const uint32_t cfv = cfs[s];
-        if (cfv == CF_NONE) continue;
-        const d4 gB = m.fgB[cfv & CF_ID];
-        const double dx = (cfv & CF_SIDE) ? gB.z : gB.x, dy = (cfv & CF_SIDE) ? gB.w : gB.y;
+        if (nbs[s] == CF_NONE) continue;
+        const double dx = dxy[s].x, dy = dxy[s].y;
         l.x = fmin(l.x, venkat(gxi.x * dx + gyi.x * dy, dmax.x, dmin.x, K3a));
         l.y = fmin(l.y, venkat(gxi.y * dx + gyi.y * dy, dmax.y, dmin.y, K3a));
         l.z = fmin(l.z, venkat(gxi.z * dx + gyi.z * dy, dmax.z, dmin.z, K3a));

@@ -129,7 +129,7 @@ struct Solver {
     bool bcs_set = false;
 
     // device geometry
-    DBuf<uint2> fcells; DBuf<d4> fgA, fgB, ftij; DBuf<uint8_t> fkind; DBuf<uint32_t> cf; DBuf<double> area;
+    DBuf<uint2> fcells; DBuf<d4> fgA, fgB, ftij; DBuf<uint8_t> fkind; DBuf<uint32_t> cf, cnb; DBuf<double2> cdxy; DBuf<double> area;
     DBuf<double> lsqM; DBuf<uint16_t> lsq_perm;
     DBuf<uint32_t> bface, bghost, bowner; DBuf<int32_t> bpatch; DBuf<d4> bstate; DBuf<double> bcx, bcy;
     DBuf<uint32_t> perm_c_new2old, perm_c_old2new;
@@ -331,7 +331,8 @@ void Solver::create(const afx_mesh_desc& m, const afx_gas& g, int visc, int dev,
         h_t[n] = d4{t0, t1, l, 0.};
     }
     // ---- cell -> face lists, slots in ascending ORIGINAL edge id ----
-    std::vector<uint32_t> h_cf((size_t)4 * N, CF_NONE);
+    std::vector<uint32_t> h_cf((size_t)4 * N, CF_NONE), h_cnb((size_t)4 * N, CF_NONE);
+    std::vector<double2> h_cdxy((size_t)4 * N, make_double2(0., 0.));
     std::vector<uint16_t> h_perm(N, 0);
     std::vector<double> h_area(NT);
     for (uint32_t n = 0; n < NT; ++n) h_area[n] = m.cells_area[c_new2old[n]];
@@ -351,6 +352,10 @@ void Solver::create(const afx_mesh_desc& m, const afx_gas& g, int visc, int dev,
             if (m.edges_cells[2 * (size_t)e] != o) v |= CF_SIDE;
             if (is_bnd[e]) v |= CF_BND;
             h_cf[(size_t)slot * N + n] = v;
+            const bool is_c1 = (m.edges_cells[2 * (size_t)e] != o);
+            h_cnb[(size_t)slot * N + n] = c_old2new[m.edges_cells[2 * (size_t)e + (is_c1 ? 0 : 1)]];
+            // the reference's own subtraction (solver.h:541-542): face centre minus this cell's centre
+            h_cdxy[(size_t)slot * N + n] = make_double2(m.edges_cx[e] - m.cells_cx[o], m.edges_cy[e] - m.cells_cy[o]);
             perm |= (uint16_t)(slot << (2 * order[slot]));  // local side order[slot] lives in this slot
         }
         h_perm[n] = perm;
@@ -373,7 +378,7 @@ void Solver::create(const afx_mesh_desc& m, const afx_gas& g, int visc, int dev,
     if (viscous_type == 1) ftij.upload(h_t, st);
     std::vector<uint8_t> h_kind(E, 0);
     fkind.upload(h_kind, st);
-    cf.upload(h_cf, st); area.upload(h_area, st); lsq_perm.upload(h_perm, st);
+    cf.upload(h_cf, st); cnb.upload(h_cnb, st); cdxy.upload(h_cdxy, st); area.upload(h_area, st); lsq_perm.upload(h_perm, st);
     bface.upload(h_bnd_face, st); bghost.upload(h_bghost, st); bowner.upload(h_bowner, st);
     bpatch.upload(h_bnd_patch, st); bcx.upload(h_bcx, st); bcy.upload(h_bcy, st);
     bstate.alloc(G ? G : 1);
@@ -416,7 +421,7 @@ void Solver::create(const afx_mesh_desc& m, const afx_gas& g, int visc, int dev,
     dm.N = N; dm.G = G; dm.E = E; dm.NT = NT;
     dm.n_upd = n_upd; dm.n_grad = n_grad; dm.e_flux = e_flux;
     dm.fcells = fcells.p; dm.fgA = fgA.p; dm.fgB = fgB.p; dm.ftij = ftij.p; dm.fkind = fkind.p;
-    dm.cf = cf.p; dm.area = area.p; dm.lsqM = lsqM.p; dm.lsq_perm = lsq_perm.p;
+    dm.cf = cf.p; dm.cnb = cnb.p; dm.cdxy = cdxy.p; dm.area = area.p; dm.lsqM = lsqM.p; dm.lsq_perm = lsq_perm.p;
 }
 
 // solver::set_bcs, solver.h:200-247

@@ -35,6 +35,8 @@ struct DevMesh {
     const d4* ftij;              // [E] t0, t1, l, - (laminar face-gradient direction, solver.h:369-376)
     const uint8_t* fkind;        // [E]
     const uint32_t* cf;          // [4][N]
+    const uint32_t* cnb;         // [4][N] the cell across slot s (same slots as cf; CF_NONE where empty): one indirection less
+    const double2* cdxy;         // [4][N] face centre minus this cell's centre for slot s (the fgB half this cell needs)
     const double* area;          // [NT]
     const double* lsqM;          // [8][N]  (M * dT) rows in cellsEdges order, LSQ only
     const uint16_t* lsq_perm;    // [N] bits 0-7: slot of local side j (2 bits each), bits 8-10: number of sides
