@@ -150,10 +150,13 @@ __device__ __forceinline__ double venkat(double dqg, double dmax, double dmin, d
 }
 
 __global__ void __launch_bounds__(256, AFX_LIM_MINB) k_limiter(DevMesh m, const d4* __restrict__ qk, const d4* __restrict__ gx,
-                                                 const d4* __restrict__ gy, d4* __restrict__ lim, double limiter_k, int walls)
+                                                 const d4* __restrict__ gy, d4* __restrict__ lim, double limiter_k, int walls,
+                                                 uint32_t lo1, uint32_t n1, uint32_t lo2, uint32_t n2)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m.n_grad) return;
+    // cells [lo1, lo1+n1) and [lo2, lo2+n2): a partitioned run limits its interior cells while the halo is in flight
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n1 + n2) return;
+    const uint32_t i = t < n1 ? lo1 + t : lo2 + (t - n1);
     const d4 qi = qk[i];
     d4 lo = qi, hi = qi;
     uint32_t nbs[4];
@@ -563,9 +566,11 @@ static void dt_grad(int grad, const DevMesh& m, d4* q, double* dt, d4* gx, d4* g
     if (grad == 0) k_dt_grad<0><<<nblk(m.n_grad), 256, 0, st>>>(m, q, dt, gx, gy, prm, gam, want_grad, walls);
     else k_dt_grad<1><<<nblk(m.n_grad), 256, 0, st>>>(m, q, dt, gx, gy, prm, gam, want_grad, walls);
 }
-static void limiter(const DevMesh& m, const d4* qk, const d4* gx, const d4* gy, d4* lim, double k, int walls, cudaStream_t st)
+static void limiter(const DevMesh& m, const d4* qk, const d4* gx, const d4* gy, d4* lim, double k, int walls, uint32_t lo1, uint32_t n1,
+                    uint32_t lo2, uint32_t n2, cudaStream_t st)
 {
-    k_limiter<<<nblk(m.n_grad), 256, 0, st>>>(m, qk, gx, gy, lim, k, walls);
+    if (n1 + n2 == 0) return;
+    k_limiter<<<nblk(n1 + n2), 256, 0, st>>>(m, qk, gx, gy, lim, k, walls, lo1, n1, lo2, n2);
 }
 static void flux(int second, int visc, int uniform, const DevMesh& m, const d4* qk, const d4* q0, const d4* gx, const d4* gy,
                  const d4* lim, d4* fl, const GasC& g, d4 qfar, cudaStream_t st)

@@ -190,6 +190,8 @@ struct Solver {
     void create(const afx_mesh_desc& m, const afx_gas& g, int visc, int dev, const Partition* part = nullptr);
     void init_halo(const Partition& part, const char* nccl_id);
     void exchange(d4* field, cudaStream_t stream);
+    bool halo_pending = false;
+    void ensure_halo() { if (halo_pending) { CK(cudaStreamWaitEvent(st, ev_halo, 0)); halo_pending = false; } }
     void reduce_norms(double* v, int n);
     void set_bcs(int n_patch, const uint8_t* kinds, const afx_bvars* vars);
     void set_options(int so, int grad, double k);
@@ -469,18 +471,30 @@ void Solver::push_params(double relax, bool keep_qW)
 
 void Solver::launch_dt_grad(bool want_grad, bool walls)
 {
+    ensure_halo();
     kt->dt_grad(gradient_scheme == AFX_GRAD_GREEN_GAUSS ? 0 : 1, dm, q.p, dt.p, gx.p, gy.p, prm.p, gas.gamma, want_grad, walls, st);
     ++launches;
 }
 
 void Solver::launch_limiter(const d4* qk)
 {
-    kt->limiter(dm, qk, gx.p, gy.p, lim.p, limiter_k, (visc_not_inviscid || second_order) ? 1 : 0, st);
+    const int walls = (visc_not_inviscid || second_order) ? 1 : 0;
+    if (halo_pending && n_front > 0 && n_front < n_upd) {
+        // owned cells farther than two hops from any foreign cell do not see the halo: limit them while it is in flight
+        kt->limiter(dm, qk, gx.p, gy.p, lim.p, limiter_k, walls, n_front, n_upd - n_front, 0, 0, st);
+        ensure_halo();
+        kt->limiter(dm, qk, gx.p, gy.p, lim.p, limiter_k, walls, 0, n_front, n_upd, n_grad - n_upd, st);
+        launches += 2;
+        return;
+    }
+    ensure_halo();
+    kt->limiter(dm, qk, gx.p, gy.p, lim.p, limiter_k, walls, 0, n_grad, 0, 0, st);
     ++launches;
 }
 
 void Solver::launch_flux(const d4* qk, bool uniform, d4 qfar)
 {
+    ensure_halo();
     kt->flux(second_order, viscous_type, uniform ? 1 : 0, dm, qk, q.p, gx.p, gy.p, lim.p, flux.p, gas, qfar, st);
     ++launches;
 }
@@ -500,7 +514,7 @@ void Solver::launch_gather(const d4* qk_in, d4* qk_out, d4* vec_out, double alph
         CK(cudaEventRecord(ev_halo, cs));
         no.blk_off = b0;
         kt->gather(MODE, LAST, dm, n_front, n_upd, flux.p, q.p, qk_in, qk_out, dt.p, vec_out, alpha, prm.p, walls ? 1 : 0, no, st);
-        CK(cudaStreamWaitEvent(st, ev_halo, 0));
+        halo_pending = true;  // joined by the first kernel that reads halo cells (ensure_halo)
         launches += 2;
         return;
     }
@@ -524,6 +538,7 @@ void Solver::explicit_iteration()
         if (s < 2) launch_gather<0, 0>(in[s], out[s], qW.p, alpha[s], grads);
         else launch_gather<0, 1>(in[s], out[s], qW.p, alpha[s], grads);
     }
+    ensure_halo();  // the halo stream joins before the iteration (and its graph) ends
 }
 
 // NCCL halo: the ring cells' states come from their owners after every stage
@@ -588,6 +603,7 @@ void Solver::reduce_norms(double* v, int n)
 
 double Solver::fetch_last_norm()
 {
+    ensure_halo();
     unsigned int* h_idx = reinterpret_cast<unsigned int*>(h_pinned + 8);
     CK(cudaMemcpyAsync(h_idx, counters.p + 1, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -1338,6 +1354,7 @@ int afx_rans_profile_explicit(afx_rans* s, double relaxation, int n_iter, double
                 CK(cudaEventRecord(ev[e++], S.st));
                 CK(cudaEventRecord(ev[e++], S.st));
             }
+            S.ensure_halo();
             CK(cudaStreamSynchronize(S.st));
             float ms;
             CK(cudaEventElapsedTime(&ms, ev[0], ev[1])); out_ms[0] += ms;
