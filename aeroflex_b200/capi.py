@@ -34,7 +34,7 @@ EXPORTED_SYMBOLS = [
     "afx_rans_create", "afx_rans_destroy", "afx_rans_set_bcs", "afx_rans_set_options", "afx_rans_set_cfl",
     "afx_rans_set_math_mode", "afx_rans_get_math_mode",
     "afx_rans_init", "afx_rans_refill_bcs", "afx_rans_bcs_from_internal", "afx_rans_set_q", "afx_rans_get_q",
-    "afx_rans_get_field", "afx_rans_boundary_variables", "afx_rans_uniform_residual", "afx_rans_step_explicit",
+    "afx_rans_set_q_local", "afx_rans_get_q_local", "afx_rans_get_field", "afx_rans_boundary_variables", "afx_rans_uniform_residual", "afx_rans_step_explicit",
     "afx_rans_run_explicit", "afx_rans_phase_dt_gradients", "afx_rans_phase_limiters", "afx_rans_phase_residual",
     "afx_rans_residual", "afx_rans_fill_jacobian", "afx_rans_get_jacobian_blocks", "afx_rans_step_implicit", "afx_rans_compute",
     "afx_rans_set_linear_solver", "afx_rans_last_linear_iterations",
@@ -168,6 +168,8 @@ def load_library():
     L.afx_rans_set_q.argtypes = [vp, vp]
     L.afx_rans_get_q.argtypes = [vp, vp]
     L.afx_rans_get_field.argtypes = [vp, C.c_int, vp]
+    L.afx_rans_set_q_local.argtypes = [vp, vp]
+    L.afx_rans_get_q_local.argtypes = [vp, vp]
     L.afx_rans_boundary_variables.argtypes = [vp, C.POINTER(BVars)]
     L.afx_rans_uniform_residual.argtypes = [vp, dp]
     L.afx_rans_step_explicit.argtypes = [vp, C.c_double, dp]
@@ -430,6 +432,22 @@ class GpuSolver:
     def get_q(self, out=None):
         out = np.empty(self.n4) if out is None else out
         _check(self.L.afx_rans_get_q(self.h, _ptr(out)))
+        return out
+
+    # a partitioned solver's own piece (owned | ring 1 | ring 2 | ghosts), no host-side gather through the global vector
+    def local_size4(self):
+        p = getattr(self, "partition", None)
+        return 4 * (p.N + p.G) if p is not None else self.n4
+
+    def set_q_local(self, q):
+        q = np.ascontiguousarray(q, np.float64)
+        if q.size != self.local_size4():
+            raise ValueError("local state has the wrong length")
+        _check(self.L.afx_rans_set_q_local(self.h, _ptr(q)))
+
+    def get_q_local(self, out=None):
+        out = np.empty(self.local_size4()) if out is None else out
+        _check(self.L.afx_rans_get_q_local(self.h, _ptr(out)))
         return out
 
     def get(self, name):

@@ -1104,6 +1104,23 @@ int afx_rans_get_q(afx_rans* s, double* q)
     });
 }
 
+int afx_rans_set_q_local(afx_rans* s, const double* q_local)
+{
+    return guard([&] {
+        auto& S = s->s;
+        S.use();
+        S.from_ref_order4(q_local, S.q.p);
+        S.sync_ghost_rows();
+        CK(cudaStreamSynchronize(S.st));
+        S.jac_valid = false;
+    });
+}
+
+int afx_rans_get_q_local(afx_rans* s, double* q_local)
+{
+    return guard([&] { s->s.use(); s->s.to_ref_order4(s->s.q.p, q_local); });
+}
+
 int afx_rans_get_field(afx_rans* s, int field, double* out)
 {
     return guard([&] {

@@ -240,28 +240,27 @@ def main():
                           "frac": alg_iter / (t_ms / a.steps * 1e-3) / 1e9 / peak}}
 
     # end to end through the C ABI with host-resident state, pinned buffers
-    nq4 = 4 * (N + G)
+    # (a partitioned rank moves ITS piece: owned + halo + ghost rows, in its own numbering)
+    nq4 = s.local_size4()
     hq = afx.pinned_array(nq4)
-    hq[:] = q0
-    s.get_q(hq)
+    s.get_q_local(hq)
     for _ in range(2):
-        s.set_q(hq); s.solve(RELAX); s.get_q(hq)
+        s.set_q_local(hq); s.solve(RELAX); s.get_q_local(hq)
     barrier()
     te = time.perf_counter()
     for _ in range(a.e2e_steps):
-        s.set_q(hq)
+        s.set_q_local(hq)
         nr = s.solve(RELAX)
-        s.get_q(hq)
+        s.get_q_local(hq)
     barrier()
     e2e_s = time.perf_counter() - te
     if dist is not None:
         t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    loc4 = nq4 if part is None else 4 * (part.N + part.G) * world  # every rank moves its piece (owned + halo + ghosts)
-    e2e = {"value": N * a.e2e_steps / e2e_s, "unit": "cell-updates/s", "h2d_bytes_per_step": 8 * loc4,
-           "d2h_bytes_per_step": 8 * loc4 + 8, "steps": a.e2e_steps, "ms_per_step": e2e_s / a.e2e_steps * 1e3,
-           "path": "afx_rans_set_q(pinned host) -> afx_rans_step_explicit -> afx_rans_get_q(pinned host) + norm"}
+    e2e = {"value": N * a.e2e_steps / e2e_s, "unit": "cell-updates/s", "h2d_bytes_per_step": 8 * nq4 * world,
+           "d2h_bytes_per_step": 8 * nq4 * world + 8, "steps": a.e2e_steps, "ms_per_step": e2e_s / a.e2e_steps * 1e3,
+           "path": "afx_rans_set_q[_local](pinned host) -> afx_rans_step_explicit -> afx_rans_get_q[_local](pinned host) + norm"}
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:

@@ -173,6 +173,11 @@ int afx_rans_bcs_from_internal(afx_rans* s);
 /* solver::get_q as value transfer: q has 4*(N+G) doubles in reference order */
 int afx_rans_set_q(afx_rans* s, const double* q);
 int afx_rans_get_q(afx_rans* s, double* q);
+/* the same for a partitioned handle in ITS OWN numbering: 4*(local cells + local ghosts) doubles in the order of
+ * afx_partition_get_desc (owned | ring 1 | ring 2 | boundary ghosts) -- what a distributed host program holds.
+ * On a single-GPU handle they are set_q / get_q. */
+int afx_rans_set_q_local(afx_rans* s, const double* q_local);
+int afx_rans_get_q_local(afx_rans* s, double* q_local);
 /* one of AFX_F_*: 4*(N+G) doubles (N+G for AFX_F_DT) in reference order */
 int afx_rans_get_field(afx_rans* s, int field, double* out);
 /* solver::get_boundary_variables (solver.h:597-611); returns 1 if a far-field patch was found, else 0 (defaults) */
