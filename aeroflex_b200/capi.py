@@ -31,6 +31,7 @@ EXPORTED_SYMBOLS = [
     "afx_mesh_write_msh",
     "afx_partition_create", "afx_partition_free", "afx_partition_get_desc", "afx_partition_info", "afx_partition_cell_l2g",
     "afx_partition_edge_l2g", "afx_partition_peer", "afx_nccl_unique_id", "afx_rans_create_partitioned",
+    "afx_rans_p2p_export", "afx_rans_p2p_connect", "afx_rans_halo_mode",
     "afx_rans_create", "afx_rans_destroy", "afx_rans_set_bcs", "afx_rans_set_options", "afx_rans_set_cfl",
     "afx_rans_set_math_mode", "afx_rans_get_math_mode",
     "afx_rans_init", "afx_rans_refill_bcs", "afx_rans_bcs_from_internal", "afx_rans_set_q", "afx_rans_get_q",
@@ -155,6 +156,9 @@ def load_library():
     L.afx_partition_edge_l2g.argtypes = [vp]
     L.afx_partition_peer.argtypes = [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(u32p), u32p, C.POINTER(u32p), u32p]
     L.afx_nccl_unique_id.argtypes = [C.c_char_p]
+    L.afx_rans_p2p_export.argtypes = [vp, vp, C.POINTER(C.c_size_t)]
+    L.afx_rans_p2p_connect.argtypes = [vp, C.c_char_p, C.c_size_t, C.c_int]
+    L.afx_rans_halo_mode.argtypes = [vp]
     L.afx_rans_create_partitioned.argtypes = [C.POINTER(vp), vp, C.POINTER(Gas), C.c_int, C.c_int, C.c_char_p]
     L.afx_rans_destroy.argtypes = [vp]
     L.afx_rans_set_bcs.argtypes = [vp, C.c_int, vp, C.POINTER(BVars)]
@@ -433,6 +437,21 @@ class GpuSolver:
         out = np.empty(self.n4) if out is None else out
         _check(self.L.afx_rans_get_q(self.h, _ptr(out)))
         return out
+
+    # peer-memory halo (CUDA IPC): blob = p2p_export(); all-gather the blobs in rank order; p2p_connect(blobs)
+    def p2p_export(self):
+        n = C.c_size_t()
+        _check(self.L.afx_rans_p2p_export(self.h, None, C.byref(n)))
+        buf = C.create_string_buffer(n.value)
+        _check(self.L.afx_rans_p2p_export(self.h, buf, C.byref(n)))
+        return buf.raw
+
+    def p2p_connect(self, blobs):
+        joined = b"".join(blobs)
+        _check(self.L.afx_rans_p2p_connect(self.h, joined, len(blobs[0]), len(blobs)))
+
+    def halo_mode(self):
+        return {0: "none", 1: "nccl", 2: "p2p"}[self.L.afx_rans_halo_mode(self.h)]
 
     # a partitioned solver's own piece (owned | ring 1 | ring 2 | ghosts), no host-side gather through the global vector
     def local_size4(self):

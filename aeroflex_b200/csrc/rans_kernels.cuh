@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(256) k_gather_update(DevMesh m, const d4* __re
                                                        const d4* q, const d4* qk_in,
                                                        d4* qk_out, const double* __restrict__ dt,
                                                        d4* __restrict__ qW, double alpha, const double* __restrict__ prm,
-                                                       int walls, NormOut no, uint32_t lo, uint32_t hi)
+                                                       int walls, NormOut no, uint32_t lo, uint32_t hi, PushArgs push)
 {
     const uint32_t i = lo + blockIdx.x * blockDim.x + threadIdx.x;
     double nrm = 0;
@@ -361,6 +361,14 @@ __global__ void __launch_bounds__(256) k_gather_update(DevMesh m, const d4* __re
             o.z = q0.z + r.z * dti * alpha * relax;
             o.w = q0.w + r.w * dti * alpha * relax;
             qk_out[i] = o;
+            if (push.enabled && i < push.n_front) {  // halo push: straight into the peers' receive buffers over NVLink
+                const unsigned long long par = (*push.epoch) & 1ull;
+                for (uint32_t k = push.dst_ptr[i]; k < push.dst_ptr[i + 1]; ++k) {
+                    const uint32_t d = push.dst[k], p = d >> 28, slot = d & 0x0FFFFFFFu;
+                    push.peer_buf[p][par * push.peer_stride[p] + slot] = o;
+                }
+                __threadfence_system();
+            }
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
                 const uint32_t cfv = bnd[s];
@@ -520,6 +528,37 @@ __global__ void __launch_bounds__(256) k_wall_forces(WallArgs a, DevMesh m, cons
     }
 }
 
+// Halo hand-off between GPUs of one node (peer-mapped memory, no collective library on the data path) ---------------
+// after the send-layer update: publish "my data of exchange #epoch+1 is in your buffer" to every peer
+__global__ void k_halo_signal(SignalArgs a)
+{
+    __threadfence_system();
+    const unsigned long long e = *a.epoch + 1ull;
+    if ((int)threadIdx.x < a.n_peers) {
+        *reinterpret_cast<volatile unsigned long long*>(a.peer_flag[threadIdx.x]) = e;
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *a.epoch = e;
+}
+// wait until every peer has delivered exchange #epoch, then copy the receive buffer of that parity into the halo cells
+__global__ void __launch_bounds__(256) k_halo_wait_scatter(WaitArgs a, d4* __restrict__ field)
+{
+    const unsigned long long e = *a.epoch;
+    if (threadIdx.x == 0) {
+        for (int p = 0; p < a.n_peers; ++p)
+            while (*reinterpret_cast<const volatile unsigned long long*>(a.flag[p]) < e) { }
+        __threadfence_system();
+    }
+    __syncthreads();
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= a.n_recv) return;
+    const d4* src = a.recv_buf + ((e - 1ull) & 1ull) * a.n_recv + k;
+    d4 v;  // written by a peer GPU: read past L1
+    v.x = __ldcg(&src->x); v.y = __ldcg(&src->y); v.z = __ldcg(&src->z); v.w = __ldcg(&src->w);
+    field[a.recv_idx[k]] = v;
+}
+
 // small utilities -----------------------------------------------------------
 __global__ void k_fill_cells(d4* __restrict__ q, uint32_t n, d4 v)
 {
@@ -584,12 +623,15 @@ static void flux(int second, int visc, int uniform, const DevMesh& m, const d4* 
 }
 static unsigned gather_blocks(uint32_t n_cells) { return nblk(n_cells); }
 static void gather(int mode, int last, const DevMesh& m, uint32_t lo, uint32_t hi, const d4* fl, const d4* q, const d4* qk_in, d4* qk_out,
-                   const double* dt, d4* vec_out, double alpha, const double* prm, int walls, NormOut no, cudaStream_t st)
+                   const double* dt, d4* vec_out, double alpha, const double* prm, int walls, NormOut no, const PushArgs* push_in,
+                   cudaStream_t st)
 {
     if (hi <= lo) return;
+    PushArgs push{};
+    if (push_in) push = *push_in;
     const unsigned nb = nblk(hi - lo);
     if (no.blk_total == 0) { no.blk_off = 0; no.blk_total = nb; }
-#define AFX_G(M, L) k_gather_update<M, L><<<nb, 256, 0, st>>>(m, fl, q, qk_in, qk_out, dt, vec_out, alpha, prm, walls, no, lo, hi)
+#define AFX_G(M, L) k_gather_update<M, L><<<nb, 256, 0, st>>>(m, fl, q, qk_in, qk_out, dt, vec_out, alpha, prm, walls, no, lo, hi, push)
     if (mode == 0) { if (last) AFX_G(0, 1); else AFX_G(0, 0); }
     else if (mode == 1) AFX_G(1, 1);
     else AFX_G(2, 1);
@@ -611,6 +653,11 @@ static void ghost_fill(d4* q, const uint32_t* bghost, const uint32_t* bowner, co
     k_ghost_fill<<<nblk(G), 256, 0, st>>>(q, bghost, bowner, bstate, G, from_owner);
 }
 static void permute4(const d4* src, d4* dst, const uint32_t* idx, uint32_t n, cudaStream_t st) { k_permute4<<<nblk(n), 256, 0, st>>>(src, dst, idx, n); }
+static void halo_signal(const SignalArgs& a, cudaStream_t st) { k_halo_signal<<<1, 32, 0, st>>>(a); }
+static void halo_wait_scatter(const WaitArgs& a, d4* field, cudaStream_t st)
+{
+    k_halo_wait_scatter<<<nblk(a.n_recv ? a.n_recv : 1), 256, 0, st>>>(a, field);
+}
 static void scatter4(const d4* src, d4* dst, const uint32_t* idx, uint32_t n, cudaStream_t st) { k_scatter4<<<nblk(n), 256, 0, st>>>(src, dst, idx, n); }
 static void permute1(const double* src, double* dst, const uint32_t* idx, uint32_t n, uint32_t nsrc, cudaStream_t st)
 {

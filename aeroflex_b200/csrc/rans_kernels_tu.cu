@@ -15,7 +15,8 @@ const KernelTable& table()
 #else
         "strict",
 #endif
-        launch::dt_grad, launch::limiter, launch::flux, launch::gather, launch::gather_blocks, launch::jacobian, launch::jac_diag,
+        launch::dt_grad, launch::limiter, launch::flux, launch::gather, launch::halo_signal, launch::halo_wait_scatter, launch::gather_blocks,
+        launch::jacobian, launch::jac_diag,
         launch::wall_forces, launch::fill_cells, launch::ghost_fill, launch::permute4, launch::permute1, launch::scatter4,
         launch::spmv, launch::jacobi_sweep, launch::invert_blocks, launch::multi_dot, launch::multi_axpy, launch::scale_from, launch::sub,
         launch::axpy_state};

@@ -94,7 +94,21 @@ struct Halo {
     // global patch extents for the force integrals
     std::vector<double> patch_xmin, patch_xmax, patch_ysum;
     std::vector<uint32_t> patch_count;
-    ~Halo() { if (comm) NcclApi::get().CommDestroy(comm); }
+    // peer-memory path (CUDA IPC): one exported block = [flags: 1024 B][receive buffer: 2 parities x n_recv cells]
+    bool p2p = false;
+    void* ipc_block = nullptr;
+    std::vector<void*> opened;            // peer blocks mapped into this process
+    DBuf<uint32_t> dst_ptr, dst;          // CSR: send-layer cell -> (peer slot, position in its receive list)
+    DBuf<unsigned long long> epoch;
+    PushArgs push{};
+    SignalArgs sig{};
+    WaitArgs wait{};
+    ~Halo()
+    {
+        for (void* p : opened) cudaIpcCloseMemHandle(p);
+        if (ipc_block) cudaFree(ipc_block);
+        if (comm) NcclApi::get().CommDestroy(comm);
+    }
 };
 
 struct Solver {
@@ -189,6 +203,8 @@ struct Solver {
 
     void create(const afx_mesh_desc& m, const afx_gas& g, int visc, int dev, const Partition* part = nullptr);
     void init_halo(const Partition& part, const char* nccl_id);
+    size_t p2p_export(void* blob);
+    void p2p_connect(const void* blobs, size_t blob_size, int nranks);
     void exchange(d4* field, cudaStream_t stream);
     bool halo_pending = false;
     void ensure_halo() { if (halo_pending) { CK(cudaStreamWaitEvent(st, ev_halo, 0)); halo_pending = false; } }
@@ -507,18 +523,29 @@ void Solver::launch_gather(const d4* qk_in, d4* qk_out, d4* vec_out, double alph
         NormOut no = norm_out();
         const unsigned b0 = kt->gather_blocks(n_front), b1 = kt->gather_blocks(n_upd - n_front);
         no.blk_off = 0; no.blk_total = b0 + b1;
-        kt->gather(MODE, LAST, dm, 0, n_front, flux.p, q.p, qk_in, qk_out, dt.p, vec_out, alpha, prm.p, walls ? 1 : 0, no, st);
-        CK(cudaEventRecord(ev_front, st));
-        CK(cudaStreamWaitEvent(cs, ev_front, 0));
-        exchange(qk_out, cs);
+        if (halo->p2p) {
+            // fused: the update kernel stores the send layer straight into the peers' receive buffers (NVLink), a
+            // one-warp kernel raises the peers' flags, and the halo stream waits for OUR flags and fills our halo
+            kt->gather(MODE, LAST, dm, 0, n_front, flux.p, q.p, qk_in, qk_out, dt.p, vec_out, alpha, prm.p, walls ? 1 : 0, no, &halo->push, st);
+            kt->halo_signal(halo->sig, st);
+            CK(cudaEventRecord(ev_front, st));
+            CK(cudaStreamWaitEvent(cs, ev_front, 0));
+            kt->halo_wait_scatter(halo->wait, qk_out, cs);
+            launches += 2;
+        } else {
+            kt->gather(MODE, LAST, dm, 0, n_front, flux.p, q.p, qk_in, qk_out, dt.p, vec_out, alpha, prm.p, walls ? 1 : 0, no, nullptr, st);
+            CK(cudaEventRecord(ev_front, st));
+            CK(cudaStreamWaitEvent(cs, ev_front, 0));
+            exchange(qk_out, cs);
+        }
         CK(cudaEventRecord(ev_halo, cs));
         no.blk_off = b0;
-        kt->gather(MODE, LAST, dm, n_front, n_upd, flux.p, q.p, qk_in, qk_out, dt.p, vec_out, alpha, prm.p, walls ? 1 : 0, no, st);
+        kt->gather(MODE, LAST, dm, n_front, n_upd, flux.p, q.p, qk_in, qk_out, dt.p, vec_out, alpha, prm.p, walls ? 1 : 0, no, nullptr, st);
         halo_pending = true;  // joined by the first kernel that reads halo cells (ensure_halo)
         launches += 2;
         return;
     }
-    kt->gather(MODE, LAST, dm, 0, n_upd, flux.p, q.p, qk_in, qk_out, dt.p, vec_out, alpha, prm.p, walls ? 1 : 0, norm_out(), st);
+    kt->gather(MODE, LAST, dm, 0, n_upd, flux.p, q.p, qk_in, qk_out, dt.p, vec_out, alpha, prm.p, walls ? 1 : 0, norm_out(), nullptr, st);
     ++launches;
     if (halo && MODE == 0) exchange(qk_out, st);
 }
@@ -586,6 +613,80 @@ void Solver::exchange(d4* field, cudaStream_t st)
     }
     NK(NcclApi::get().GroupEnd());
     if (h.n_recv) { kt->scatter4(h.recv_buf.p, field, h.recv_idx.p, h.n_recv, st); ++launches; }
+}
+
+// ---- peer-memory halo: export this rank's receive block, map the peers' ----
+struct P2PBlobPeer { int32_t rank; uint32_t recv_off, recv_cnt; };
+struct P2PBlob {
+    cudaIpcMemHandle_t handle;
+    uint32_t n_recv, n_peers;
+    P2PBlobPeer peers[16];
+};
+constexpr size_t P2P_FLAG_BYTES = 1024;
+
+size_t Solver::p2p_export(void* blob)
+{
+    if (!halo) throw InvalidArg("not a partitioned solver");
+    Halo& h = *halo;
+    if (h.peers.size() > P2P_MAX_PEERS) throw InvalidArg("too many halo peers for the peer-memory path");
+    if (!h.ipc_block) {
+        const size_t bytes = P2P_FLAG_BYTES + 2 * (size_t)std::max<uint32_t>(h.n_recv, 1) * sizeof(d4);
+        CK(cudaMalloc(&h.ipc_block, bytes));
+        CK(cudaMemset(h.ipc_block, 0, bytes));
+        h.epoch.alloc(1);
+        CK(cudaMemset(h.epoch.p, 0, sizeof(unsigned long long)));
+    }
+    P2PBlob b{};
+    CK(cudaIpcGetMemHandle(&b.handle, h.ipc_block));
+    b.n_recv = h.n_recv; b.n_peers = (uint32_t)h.peers.size();
+    for (size_t k = 0; k < h.peers.size(); ++k) { b.peers[k].rank = h.peers[k].rank; b.peers[k].recv_off = h.peers[k].recv_off; b.peers[k].recv_cnt = h.peers[k].recv_cnt; }
+    if (blob) std::memcpy(blob, &b, sizeof b);
+    return sizeof b;
+}
+
+void Solver::p2p_connect(const void* blobs, size_t blob_size, int nranks)
+{
+    if (!halo || !halo->ipc_block) throw InvalidArg("afx_rans_p2p_export must be called first");
+    Halo& h = *halo;
+    if (blob_size != sizeof(P2PBlob) || nranks != h.nranks) throw InvalidArg("peer blobs do not match this build / communicator");
+    use();
+    const P2PBlob* all = static_cast<const P2PBlob*>(blobs);
+    h.push = PushArgs{}; h.sig = SignalArgs{}; h.wait = WaitArgs{};
+    std::vector<std::vector<uint32_t>> per_cell(n_front);
+    std::vector<uint32_t> si(h.n_send);
+    if (h.n_send) CK(cudaMemcpy(si.data(), h.send_idx.p, (size_t)h.n_send * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    for (size_t k = 0; k < h.peers.size(); ++k) {
+        const auto& pk = h.peers[k];
+        const P2PBlob& pb = all[pk.rank];
+        void* base = nullptr;
+        CK(cudaIpcOpenMemHandle(&base, pb.handle, cudaIpcMemLazyEnablePeerAccess));
+        h.opened.push_back(base);
+        const P2PBlobPeer* mine = nullptr;
+        for (uint32_t j = 0; j < pb.n_peers; ++j) if (pb.peers[j].rank == h.rank) mine = &pb.peers[j];
+        if (!mine || mine->recv_cnt != pk.send_cnt) throw InvalidArg("halo plans of two ranks disagree");
+        h.push.peer_buf[k] = reinterpret_cast<d4*>(static_cast<char*>(base) + P2P_FLAG_BYTES) + mine->recv_off;
+        h.push.peer_stride[k] = pb.n_recv;
+        h.sig.peer_flag[k] = reinterpret_cast<unsigned long long*>(base) + h.rank;
+        h.wait.flag[k] = reinterpret_cast<const unsigned long long*>(h.ipc_block) + pk.rank;
+        for (uint32_t j = 0; j < pk.send_cnt; ++j) {
+            const uint32_t cell = si[pk.send_off + j];
+            if (cell >= n_front) throw InvalidArg("send-layer cell outside the front range");
+            per_cell[cell].push_back(((uint32_t)k << 28) | j);
+        }
+    }
+    std::vector<uint32_t> ptr(n_front + 1, 0), dst;
+    for (uint32_t c = 0; c < n_front; ++c) { ptr[c] = (uint32_t)dst.size(); dst.insert(dst.end(), per_cell[c].begin(), per_cell[c].end()); }
+    ptr[n_front] = (uint32_t)dst.size();
+    if (dst.empty()) dst.push_back(0);
+    h.dst_ptr.upload(ptr, st); h.dst.upload(dst, st);
+    CK(cudaStreamSynchronize(st));
+    h.push.enabled = 1; h.push.n_front = n_front; h.push.dst_ptr = h.dst_ptr.p; h.push.dst = h.dst.p; h.push.epoch = h.epoch.p;
+    h.sig.n_peers = (int)h.peers.size(); h.sig.epoch = h.epoch.p;
+    h.wait.n_peers = (int)h.peers.size(); h.wait.epoch = h.epoch.p;
+    h.wait.recv_buf = reinterpret_cast<const d4*>(static_cast<char*>(h.ipc_block) + P2P_FLAG_BYTES);
+    h.wait.recv_idx = h.recv_idx.p; h.wait.n_recv = h.n_recv;
+    h.p2p = (n_front > 0 && n_front < n_upd);
+    invalidate_graph();
 }
 
 // partitioned runs keep per-rank sums of squares: add them over the ranks, then take the root
@@ -978,6 +1079,18 @@ int afx_nccl_unique_id(char out[128])
         std::memcpy(out, &id, 128);
     });
 }
+
+int afx_rans_p2p_export(afx_rans* s, void* blob, size_t* size)
+{
+    return guard([&] { const size_t n = s->s.p2p_export(blob); if (size) *size = n; });
+}
+
+int afx_rans_p2p_connect(afx_rans* s, const void* blobs, size_t blob_size, int nranks)
+{
+    return guard([&] { s->s.p2p_connect(blobs, blob_size, nranks); });
+}
+
+int afx_rans_halo_mode(afx_rans* s) { return !s->s.halo ? 0 : (s->s.halo->p2p ? 2 : 1); }
 
 int afx_rans_create_partitioned(afx_rans** out, const afx_partition* part, const afx_gas* gas, int viscosity_model, int device,
                                 const char nccl_id[128])

@@ -52,6 +52,32 @@ struct NormOut {
     unsigned int blk_total; // blocks of all launches of the phase; the block that arrives last finishes the sum
 };
 
+// Halo push over NVLink peer memory, fused into the update kernel: an advanced cell that a peer needs is stored straight
+// into that peer's receive buffer (double-buffered by stage parity) from the kernel that computes it.
+constexpr int P2P_MAX_PEERS = 8;
+struct PushArgs {
+    int enabled;                                  // 0: no push (single GPU, NCCL halo, or cells outside the send layer)
+    uint32_t n_front;                             // cells [0, n_front) have destinations
+    const uint32_t* dst_ptr;                      // [n_front+1] CSR over the send-layer cells
+    const uint32_t* dst;                          // (peer slot << 28) | position in that peer's receive list
+    d4* peer_buf[P2P_MAX_PEERS];                  // peer's receive buffer at my offset (parity 0), a peer-mapped pointer
+    unsigned long long peer_stride[P2P_MAX_PEERS];// elements between the two parity buffers of that peer
+    const unsigned long long* epoch;              // completed exchanges of this rank (device counter)
+};
+struct SignalArgs {
+    int n_peers;
+    unsigned long long* peer_flag[P2P_MAX_PEERS]; // peer's flag slot for my rank (peer-mapped)
+    unsigned long long* epoch;
+};
+struct WaitArgs {
+    int n_peers;
+    const unsigned long long* flag[P2P_MAX_PEERS]; // my flag slots, one per peer I receive from
+    const unsigned long long* epoch;
+    const d4* recv_buf;                           // [2][n_recv]
+    const uint32_t* recv_idx;                     // [n_recv] halo cells to fill
+    uint32_t n_recv;
+};
+
 struct WallArgs {
     const uint32_t* bface; const int32_t* bpatch; uint32_t G; int patch;
     const double* bcx; const double* bcy;
@@ -71,7 +97,10 @@ struct KernelTable {
                  const d4* lim, d4* flux, const GasC& g, d4 qfar, cudaStream_t st);
     // cells [lo, hi); `no` carries the block bookkeeping when the phase is split into several launches
     void (*gather)(int mode, int last, const DevMesh& m, uint32_t lo, uint32_t hi, const d4* flux, const d4* q, const d4* qk_in,
-                   d4* qk_out, const double* dt, d4* vec_out, double alpha, const double* prm, int walls, NormOut no, cudaStream_t st);
+                   d4* qk_out, const double* dt, d4* vec_out, double alpha, const double* prm, int walls, NormOut no,
+                   const PushArgs* push, cudaStream_t st);
+    void (*halo_signal)(const SignalArgs& a, cudaStream_t st);               // tell the peers my send layer is in their buffers
+    void (*halo_wait_scatter)(const WaitArgs& a, d4* field, cudaStream_t st); // wait for the peers, then fill my halo cells
     unsigned (*gather_blocks)(uint32_t n_cells);
     void (*jacobian)(int visc, const DevMesh& m, const d4* q, const d4* gx, const d4* gy, d4* J, const GasC& g, cudaStream_t st);
     void (*jac_diag)(const DevMesh& m, const d4* J, const double* dt, double* D, cudaStream_t st);

@@ -162,6 +162,10 @@ def main():
         ids = [afx.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         s = afx.GpuSolver(part, viscosity=VISC, device=local, math=a.math, nccl_id=ids[0])
+        if os.environ.get("AFX_HALO", "p2p") == "p2p":  # halo through NVLink peer memory, fused into the update kernel
+            blobs = [None] * world
+            dist.all_gather_object(blobs, s.p2p_export())
+            s.p2p_connect(blobs)
     else:
         s = afx.GpuSolver(mesh, viscosity=VISC, device=local, math=a.math)
     config["math"] = a.math + (" (shared reciprocals + FMA; parity 1e-10 tested)" if a.math == "fast" else " (bit-identical to the CPU reference)")
@@ -172,8 +176,8 @@ def main():
     s.set_q(q0)
     config.update({"cells": N, "edges": E, "ghost_cells": G,
                    "parallelism": "1 GPU" if world == 1 else
-                   "domain decomposition: %d Hilbert-curve partitions, 2-layer halo, one NCCL send/recv group per RK stage "
-                   "(this rank: %d owned + %d halo cells, %d peers)" % (world, part.n_own, part.n_r1 + part.n_r2, part.n_peers)})
+                   "domain decomposition: %d Hilbert-curve partitions, 2-layer halo refreshed every RK stage, halo=%s "
+                   "(this rank: %d owned + %d halo cells, %d peers)" % (world, s.halo_mode(), part.n_own, part.n_r1 + part.n_r2, part.n_peers)})
 
     def barrier():
         torch.cuda.synchronize()

@@ -157,6 +157,15 @@ int afx_nccl_unique_id(char out[128]);
 int afx_rans_create_partitioned(afx_rans** out, const afx_partition* part, const afx_gas* gas, int viscosity_model,
                                 int device, const char nccl_id[128]);
 
+/* Halo over NVLink peer memory instead of NCCL (one node, one process per GPU, CUDA IPC): every rank exports a
+ * blob (size returned in *size; pass blob = NULL to query), the host program all-gathers the blobs in rank order
+ * and hands them to connect.  After that the update kernel itself stores the send layer into the peers' receive
+ * buffers and a flag hand-off replaces the NCCL send/recv group; norms and forces still use NCCL all-reduce. */
+int afx_rans_p2p_export(afx_rans* s, void* blob, size_t* size);
+int afx_rans_p2p_connect(afx_rans* s, const void* blobs, size_t blob_size, int nranks);
+/* 0 single GPU, 1 NCCL halo, 2 peer-memory halo */
+int afx_rans_halo_mode(afx_rans* s);
+
 /* solver::set_bcs (solver.h:200-247): kind and far-field variables per patch id */
 int afx_rans_set_bcs(afx_rans* s, int n_patch, const uint8_t* patch_kind, const afx_bvars* patch_vars);
 /* set_second_order / set_gradient_scheme / set_limiter_k (solver.h:135,149-152,162) */

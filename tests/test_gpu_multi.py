@@ -26,7 +26,7 @@ def _q0(afx, mesh):
     return s, q
 
 
-def _worker(rank, world, port, n_iter, out_dir, math):
+def _worker(rank, world, port, n_iter, out_dir, math, halo):
     import torch.distributed as dist
     import aeroflex_b200 as afx
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
@@ -36,6 +36,11 @@ def _worker(rank, world, port, n_iter, out_dir, math):
     ids = [afx.nccl_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(ids, src=0)
     s = afx.GpuSolver(part, viscosity="spallart-allmaras", math=math, device=rank, nccl_id=ids[0])
+    if halo == "p2p":  # NVLink peer-memory halo: all-gather the IPC blobs, map the peers' receive buffers
+        blobs = [None] * world
+        dist.all_gather_object(blobs, s.p2p_export())
+        s.p2p_connect(blobs)
+    assert s.halo_mode() == halo
     s.set_bcs(BCS); s.set_options(True, "green-gauss", 5.0, 1.4); s.init(); s.refill_bcs()
     q0 = np.load(os.path.join(out_dir, "q0.npy"))
     s.set_q(q0)
@@ -48,12 +53,12 @@ def _worker(rank, world, port, n_iter, out_dir, math):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,math", [(2, "strict"), (2, "fast")])
-def test_partitioned_run_matches_single_gpu(afx, gpu, tmp_path, world, math):
+@pytest.mark.parametrize("world,math,halo", [(2, "strict", "nccl"), (2, "strict", "p2p"), (2, "fast", "p2p")])
+def test_partitioned_run_matches_single_gpu(afx, gpu, tmp_path, world, math, halo):
     if gpu < world:
         pytest.skip("needs %d GPUs, %d visible" % (world, gpu))
     import torch.multiprocessing as mp
-    n_iter = 6
+    n_iter = 25
     mesh = afx.Mesh.synth_omesh(*DIMS, 150.0)
     single, q0 = _q0(afx, mesh)
     np.save(tmp_path / "q0.npy", q0)
@@ -63,7 +68,7 @@ def test_partitioned_run_matches_single_gpu(afx, gpu, tmp_path, world, math):
     Q = single.get_q().reshape(-1, 4)
     F = np.array(single.wall_forces("wall"))
     del single
-    mp.spawn(_worker, args=(world, _free_port(), n_iter, str(tmp_path), math), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), n_iter, str(tmp_path), math, halo), nprocs=world, join=True)
     seen = 0
     for r in range(world):
         d = np.load(tmp_path / ("r%d.npz" % r))
