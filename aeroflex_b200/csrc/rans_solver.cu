@@ -207,6 +207,7 @@ struct Solver {
     void p2p_connect(const void* blobs, size_t blob_size, int nranks);
     void exchange(d4* field, cudaStream_t stream);
     bool halo_pending = false;
+    bool halo_overlap = false;  // AFX_HALO_OVERLAP=1: exchange on a second stream under the interior update (needed for the NCCL halo)
     void ensure_halo() { if (halo_pending) { CK(cudaStreamWaitEvent(st, ev_halo, 0)); halo_pending = false; } }
     void reduce_norms(double* v, int n);
     void set_bcs(int n_patch, const uint8_t* kinds, const afx_bvars* vars);
@@ -268,6 +269,7 @@ void Solver::create(const afx_mesh_desc& m, const afx_gas& g, int visc, int dev,
     for (auto& e : evp) CK(cudaEventCreate(&e));
     CK(cudaMallocHost(&h_pinned, 64 * sizeof(double)));
     if (const char* e = getenv("AFX_NO_GRAPH")) use_graph = !(e[0] == '1');
+    if (const char* e = getenv("AFX_HALO_OVERLAP")) halo_overlap = (e[0] == '1');
     if (const char* e = getenv("AFX_MATH")) kt = (std::string(e) == "strict") ? &strict::table() : &fast::table();
 
     N = m.n_cells; G = m.n_ghost; E = m.n_edges; NT = N + G;
@@ -518,6 +520,15 @@ void Solver::launch_flux(const d4* qk, bool uniform, d4 qfar)
 template <int MODE, int LAST>
 void Solver::launch_gather(const d4* qk_in, d4* qk_out, d4* vec_out, double alpha, bool walls)
 {
+    if (halo && MODE == 0 && halo->p2p && !halo_overlap) {
+        // one launch advances everything and pushes the send layer into the peers' buffers; a flag hand-off and a
+        // small wait+scatter kernel complete the halo on the same stream (no fork/join, no split launches)
+        kt->gather(MODE, LAST, dm, 0, n_upd, flux.p, q.p, qk_in, qk_out, dt.p, vec_out, alpha, prm.p, walls ? 1 : 0, norm_out(), &halo->push, st);
+        kt->halo_signal(halo->sig, st);
+        kt->halo_wait_scatter(halo->wait, qk_out, st);
+        launches += 3;
+        return;
+    }
     if (halo && MODE == 0 && n_front > 0 && n_front < n_upd) {
         // send layer first, then the exchange on the halo stream while the interior cells are advanced
         NormOut no = norm_out();

@@ -15,6 +15,9 @@
 
 namespace rans {
 
+// CUDA device new solvers are created on (one process per GPU: set it once from LOCAL_RANK / --device)
+inline int& default_device() { static int d = 0; return d; }
+
 class solver {
 protected:
     struct Deleter { void operator()(afx_rans* s) const { afx_rans_destroy(s); } };
@@ -53,8 +56,8 @@ public:
     std::map<std::string, boundary_condition> bcs;
 
     solver() {}
-    solver(const mesh& m_in, const gas& g_in, std::string viscosity_model_, int device = 0)
-        : g(g_in), m(m_in), viscosity_model(std::move(viscosity_model_)), device_(device) { create(); }
+    solver(const mesh& m_in, const gas& g_in, std::string viscosity_model_, int device = -1)
+        : g(g_in), m(m_in), viscosity_model(std::move(viscosity_model_)), device_(device < 0 ? default_device() : device) { create(); }
     // like the reference (solver.h:112-116): a copy is a fresh solver on the same mesh with the same bcs, not a state copy
     solver(const solver& s) : solver(s.get_cmesh(), s.get_gas(), s.get_viscosity_model(), s.device_) {
         bcs = s.get_bcs(); print_interval = s.get_print_interval(); second_order = s.second_order;
@@ -130,7 +133,7 @@ public:
 
 class explicitSolver : public solver {  // solver.h:721-742
 public:
-    explicitSolver(const mesh& m_in, const gas& g_in, std::string viscosity_model_, int device = 0) : solver(m_in, g_in, viscosity_model_, device) {}
+    explicitSolver(const mesh& m_in, const gas& g_in, std::string viscosity_model_, int device = -1) : solver(m_in, g_in, viscosity_model_, device) {}
     explicitSolver(const explicitSolver& s) : explicitSolver(s.get_cmesh(), s.get_gas(), s.get_viscosity_model(), s.device_) {}
     void fill() override {}
     int compute() override { return 0; }
@@ -152,7 +155,7 @@ public:
 
 class implicitSolver : public solver {  // solver.h:852-970
 public:
-    implicitSolver(const mesh& m_in, const gas& g_in, std::string viscosity_model_, int device = 0) : solver(m_in, g_in, viscosity_model_, device) {}
+    implicitSolver(const mesh& m_in, const gas& g_in, std::string viscosity_model_, int device = -1) : solver(m_in, g_in, viscosity_model_, device) {}
     implicitSolver(const implicitSolver& s) : implicitSolver(s.get_cmesh(), s.get_gas(), s.get_viscosity_model(), s.device_) {}
     void fill() override { check(afx_rans_fill_jacobian(h_.get())); }  // fillRhoLHS, solver.h:973-976
     int compute() override {                                            // solver.h:1160-1167
