@@ -112,6 +112,28 @@ def reference_cpu(steps, warmup):
                       % (CPU_SAMPLE, rm.N, rm.E, steps, threads, dt)}, dt / steps * 1e3
 
 
+def port_cpu(steps):
+    """The restated oracle, threaded variant (-O3 -march=native -fopenmp), on all host cores: the strongest CPU number
+    we can produce for this path (bit-identical to the serial restatement; the reference itself cannot thread its face loops)."""
+    import aeroflex_b200 as afx
+    from oracle import orc
+    ni, nj, nq = WORKLOADS[CPU_SAMPLE]
+    m = afx.Mesh.synth_omesh(ni, nj, nq, 150.0)
+    x, y, cells, b0, b1 = m.elements()
+    om = orc.OracleMesh(x, y, cells, m.is_tri, b0, b1, m.bnd_patch, m.patch_names, fast=True)
+    o = orc.OracleSolver(om, viscosity=VISC, fast=True)
+    o.set_bcs(BCS); o.set_options(SECOND, GRAD, LIMK, CFL); o.init(); o.refill_bcs()
+    o.q[:] = perturbed(o.q.copy(), m.N)
+    o.explicit_solve_omp(RELAX)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        o.explicit_solve_omp(RELAX)
+    dt = time.perf_counter() - t0
+    threads = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
+    return {"value": m.N * steps / dt, "unit": "cell-updates/s", "cores": threads, "kind": "port",
+            "sample": "%s: %d iterations of oracle/rans_oracle.c orc_explicit_solve_omp, %d threads, %.1f s" % (CPU_SAMPLE, steps, threads, dt)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -269,6 +291,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         cpu, _ = reference_cpu(20, 1)
+        cpu_port = port_cpu(60)
     if rank == 0:
         out = {"metric": "RANS cell-updates/s", "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": a.steps, "warmup": W,
                "ms_per_step": t_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -276,6 +299,7 @@ def main():
                "wall_ms_per_step": wall_ms / a.steps, "final_residual_norm": float(norms[-1])}
         if cpu is not None:
             out["cpu_baseline"] = cpu
+            out["cpu_port"] = cpu_port
         print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()

@@ -51,7 +51,8 @@ class Solver(C.Structure):
                 ("bnd_vars", C.POINTER(BVars)),
                 ("viscous_type", C.c_int), ("visc_not_inviscid", C.c_int), ("second_order", C.c_int),
                 ("gradient_scheme", C.c_int), ("limiter_k", C.c_double), ("cfl", C.c_double)] + \
-               [(n, C.POINTER(C.c_double)) for n in ("q", "qk", "qW", "gx", "gy", "lim", "qmin", "qmax", "rhs", "dt", "lsq")]
+               [(n, C.POINTER(C.c_double)) for n in ("q", "qk", "qW", "gx", "gy", "lim", "qmin", "qmax", "rhs", "dt", "lsq")] + \
+               [("cf_sorted", C.POINTER(C.c_uint32)), ("fluxbuf", C.POINTER(C.c_double))]
 
 
 _libs = {}

@@ -432,7 +432,7 @@ void orc_solver_free(orc_solver *s)
 {
     free(s->q); free(s->qk); free(s->qW); free(s->gx); free(s->gy); free(s->lim);
     free(s->qmin); free(s->qmax); free(s->rhs); free(s->dt);
-    free(s->edge_kind); free(s->bnd_kind); free(s->bnd_vars); free(s->lsq);
+    free(s->edge_kind); free(s->bnd_kind); free(s->bnd_vars); free(s->lsq); free(s->cf_sorted); free(s->fluxbuf);
     memset(s, 0, sizeof *s);
 }
 
@@ -876,4 +876,162 @@ int orc_wall_forces(const orc_solver *s, int patch, double out[3])
     out[0] = -fx * sin(aoa) + fy * cos(aoa);
     out[2] = cm;
     return 0;
+}
+
+/* ------------------------------------------------------------------ */
+/* Threaded variant for TIMING the port on all host cores.  The reference's face loops are serial scatters
+ * (solver.h:313,432,522,535,751); here every phase is a gather over cells (or a map over faces), with each
+ * cell's faces visited in ascending edge id, so every sum has the reference's order and the result is
+ * bit-identical to orc_explicit_solve.  Green-Gauss or least-squares, any flux kind.
+ * ------------------------------------------------------------------ */
+static void build_cf_(orc_solver *s)
+{
+    const orc_mesh *m = &s->m;
+    s->cf_sorted = (uint32_t *)malloc(4 * (size_t)m->N * sizeof(uint32_t));
+    s->fluxbuf = (double *)malloc(4 * (size_t)m->E * sizeof(double));
+    for (uint32_t i = 0; i < m->N; ++i) {
+        uint32_t e[4];
+        const uint32_t sz = m->is_tri[i] ? 3 : 4;
+        for (uint32_t k = 0; k < 4; ++k) e[k] = k < sz ? m->cell_edges[4 * (size_t)i + k] : ORC_EDGE_NULL;
+        for (int a = 1; a < 4; ++a)
+            for (int b = a; b > 0 && e[b] < e[b - 1]; --b) { const uint32_t t = e[b]; e[b] = e[b - 1]; e[b - 1] = t; }
+        memcpy(s->cf_sorted + 4 * (size_t)i, e, sizeof e);
+    }
+}
+
+static double spectral_(const double *q, double nx, double ny, double gam)
+{
+    const double V = (q[1] * nx + q[2] * ny) / q[0];
+    const double p = (gam - 1) * (q[3] - 0.5 / q[0] * (q[1] * q[1] + q[2] * q[2]));
+    return sqrt(p * gam / q[0]) + fabs(V);
+}
+
+double orc_explicit_solve_omp(orc_solver *s, double relaxation)
+{
+    static const double alpha[3] = {0.25, 0.5, 1.};
+    const orc_mesh *m = &s->m;
+    const size_t NT = (size_t)m->N + m->G, n4 = 4 * NT;
+    const double gam = s->g.gamma;
+    if (!s->cf_sorted) build_cf_(s);
+    const double *q = s->q;
+    /* calc_dt */
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < (long)m->N; ++i) {
+        double sum = 0;
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t e = s->cf_sorted[4 * i + k];
+            if (e == ORC_EDGE_NULL) break;
+            const uint32_t c0 = m->edge_cells[2 * (size_t)e], c1 = m->edge_cells[2 * (size_t)e + 1];
+            const double eL = spectral_(q + 4 * (size_t)c0, m->enx[e], m->eny[e], gam);
+            double eig = eL;
+            if (two_sided_(s->edge_kind[e])) { const double eR = spectral_(q + 4 * (size_t)c1, m->enx[e], m->eny[e], gam); eig = (eL < eR) ? eR : eL; }
+            sum += eig * m->elen[e];
+        }
+        s->dt[i] = s->cfl * m->area[i] / sum;
+    }
+    memcpy(s->qk, s->q, n4 * sizeof(double));
+    for (int st = 0; st < 3; ++st) {
+        double *qk = s->qk;
+        if (s->visc_not_inviscid | s->second_order) {
+            orc_set_walls_from_internal(s, qk);
+            if (s->gradient_scheme == ORC_GREEN_GAUSS) {
+#pragma omp parallel for schedule(static)
+                for (long i = 0; i < (long)m->N; ++i) {
+                    double ax[4] = {0, 0, 0, 0}, ay[4] = {0, 0, 0, 0};
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t e = s->cf_sorted[4 * i + k];
+                        if (e == ORC_EDGE_NULL) break;
+                        const uint32_t c0 = m->edge_cells[2 * (size_t)e], c1 = m->edge_cells[2 * (size_t)e + 1];
+                        const double dxif = m->ecx[e] - m->ccx[c0], dyif = m->ecy[e] - m->ccy[c0];
+                        const double dxij = m->ccx[c0] - m->ccx[c1], dyij = m->ccy[c0] - m->ccy[c1];
+                        const double w = sqrt(dxif * dxif + dyif * dyif) / sqrt(dxij * dxij + dyij * dyij);
+                        const double *qL = q + 4 * (size_t)c0;
+                        double qR[4];
+                        orc_bc_vars(s->edge_kind[e], &s->g, m->enx[e], m->eny[e], qL, q + 4 * (size_t)c1, qR);
+                        for (int c = 0; c < 4; ++c) {
+                            const double fk = (qL[c] * (1.0 - w) + qR[c] * w) * m->elen[e];
+                            if ((uint32_t)i == c0) { ax[c] += fk * m->enx[e]; ay[c] += fk * m->eny[e]; }
+                            else { ax[c] -= fk * m->enx[e]; ay[c] -= fk * m->eny[e]; }
+                        }
+                    }
+                    for (int c = 0; c < 4; ++c) { s->gx[4 * i + c] = ax[c] / m->area[i]; s->gy[4 * i + c] = ay[c] / m->area[i]; }
+                }
+                for (size_t i = 4 * (size_t)m->N; i < n4; ++i) { s->gx[i] = 0; s->gy[i] = 0; }
+            } else {
+                orc_calc_gradients(s);  /* least squares is already a loop over cells in the reference */
+            }
+            if (s->second_order) {
+#pragma omp parallel for schedule(static)
+                for (long i = 0; i < (long)m->N; ++i) {
+                    double lo[4], hi[4], l[4] = {1, 1, 1, 1};
+                    for (int c = 0; c < 4; ++c) lo[c] = hi[c] = qk[4 * i + c];
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t e = s->cf_sorted[4 * i + k];
+                        if (e == ORC_EDGE_NULL) break;
+                        const uint32_t c0 = m->edge_cells[2 * (size_t)e], c1 = m->edge_cells[2 * (size_t)e + 1];
+                        const double *qn = qk + 4 * (size_t)((uint32_t)i == c0 ? c1 : c0);
+                        for (int c = 0; c < 4; ++c) { lo[c] = fmin(lo[c], qn[c]); hi[c] = fmax(hi[c], qn[c]); }
+                    }
+                    const double Ka = s->limiter_k * sqrt(m->area[i]), K3a = Ka * Ka * Ka;
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t e = s->cf_sorted[4 * i + k];
+                        if (e == ORC_EDGE_NULL) break;
+                        const double dx = m->ecx[e] - m->ccx[i], dy = m->ecy[e] - m->ccy[i];
+                        for (int c = 0; c < 4; ++c) {
+                            const double dqg = s->gx[4 * i + c] * dx + s->gy[4 * i + c] * dy;
+                            const double dmax = hi[c] - qk[4 * i + c], dmin = lo[c] - qk[4 * i + c];
+                            double v = 1.0;
+                            if (dqg > 1e-16) v = 1 / dqg * ((dmax * dmax + K3a) * dqg + 2 * dqg * dqg * dmax) / (dmax * dmax + 2 * dqg * dqg + dmax * dqg + K3a);
+                            else if (dqg < -1e-16) v = 1 / dqg * ((dmin * dmin + K3a) * dqg + 2 * dqg * dqg * dmin) / (dmin * dmin + 2 * dqg * dqg + dmin * dqg + K3a);
+                            l[c] = fmin(l[c], v);
+                        }
+                    }
+                    for (int c = 0; c < 4; ++c) s->lim[4 * i + c] = l[c];
+                }
+                for (size_t i = 4 * (size_t)m->N; i < n4; ++i) s->lim[i] = 1;
+            }
+        }
+        /* face fluxes, once per face */
+#pragma omp parallel for schedule(static)
+        for (long e = 0; e < (long)m->E; ++e) {
+            const uint32_t c0 = m->edge_cells[2 * e], c1 = m->edge_cells[2 * e + 1];
+            const size_t k0 = 4 * (size_t)c0, k1 = 4 * (size_t)c1;
+            double gradx[4], grady[4], f[4], qL[4], qR[4];
+            orc_average_gradients(s, c0, c1, gradx, grady);
+            for (int c = 0; c < 4; ++c) { qL[c] = qk[k0 + c]; qR[c] = qk[k1 + c]; }
+            if (s->second_order) {
+                const double d0x = m->ecx[e] - m->ccx[c0], d0y = m->ecy[e] - m->ccy[c0];
+                const double d1x = m->ecx[e] - m->ccx[c1], d1y = m->ecy[e] - m->ccy[c1];
+                for (int c = 0; c < 4; ++c) {
+                    qL[c] = qk[k0 + c] + (s->gx[k0 + c] * d0x + s->gy[k0 + c] * d0y) * s->lim[k0 + c];
+                    qR[c] = qk[k1 + c] + (s->gx[k1 + c] * d1x + s->gy[k1 + c] * d1y) * s->lim[k1 + c];
+                }
+            }
+            orc_flux(s->edge_kind[e], &s->g, s->viscous_type, m->enx[e], m->eny[e], qL, qR, gradx, grady, f);
+            for (int c = 0; c < 4; ++c) s->fluxbuf[4 * (size_t)e + c] = f[c] * m->elen[e];
+        }
+        /* gather, residual, stage update */
+        memset(s->qW + 4 * (size_t)m->N, 0, 4 * (size_t)m->G * sizeof(double));
+#pragma omp parallel for schedule(static)
+        for (long i = 0; i < (long)m->N; ++i) {
+            double r[4] = {0, 0, 0, 0};
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t e = s->cf_sorted[4 * i + k];
+                if (e == ORC_EDGE_NULL) break;
+                const double *f = s->fluxbuf + 4 * (size_t)e;
+                if (m->edge_cells[2 * (size_t)e] == (uint32_t)i) for (int c = 0; c < 4; ++c) r[c] -= f[c];
+                else for (int c = 0; c < 4; ++c) r[c] += f[c];
+            }
+            for (int c = 0; c < 4; ++c) {
+                s->qW[4 * i + c] = r[c] / m->area[i];
+                qk[4 * i + c] = s->q[4 * i + c] + s->qW[4 * i + c] * s->dt[i] * alpha[st] * relaxation;
+            }
+        }
+        for (uint32_t b = 0; b < m->G; ++b) {  /* ghost rows of qW for two-sided boundary faces */
+            const uint32_t e = m->bnd_edge[b];
+            if (two_sided_(s->edge_kind[e])) for (int c = 0; c < 4; ++c) s->qW[4 * ((size_t)m->N + b) + c] = s->fluxbuf[4 * (size_t)e + c];
+        }
+    }
+    memcpy(s->q, s->qk, n4 * sizeof(double));
+    return orc_norm(s->qW, n4);
 }

@@ -73,6 +73,9 @@ typedef struct {
     double *q, *qk, *qW, *gx, *gy, *lim, *qmin, *qmax, *rhs;
     double *dt; /* [N+G] */
     double *lsq; /* [N][4] row-major 2x2 (dT d)^-1, solver.h:402-422 */
+    /* scratch of the threaded variant (orc_explicit_solve_omp): faces of a cell in ascending edge id, face fluxes */
+    uint32_t *cf_sorted; /* [N][4] */
+    double *fluxbuf; /* [E][4] */
 } orc_solver;
 
 /* ---- physics.h ---- */

@@ -90,3 +90,19 @@ def test_sanity_anchors_independent_of_any_oracle():
     touches_bnd = np.zeros(m.N, bool)
     touches_bnd[m.edge_cells[m.bnd_edge, 0]] = True
     assert np.abs(qW[~touches_bnd]).max() < 1e-9 * np.abs(qW).max() + 1e-9
+
+
+@pytest.mark.parametrize("tag", ["naca0012q_coarse_euler_gg_o2", "naca0012_coarse_laminar_lsq_o2", "naca0012_coarse_sa_gg_o1"])
+def test_threaded_port_is_bit_identical_to_the_serial_restatement(tag):
+    """orc_explicit_solve_omp (the multi-core CPU baseline of bench.py) = orc_explicit_solve, bit for bit."""
+    d = H.load(tag)
+    meta = d["meta"]
+    m = H.oracle_mesh(d, fast=True)
+    a = orc.OracleSolver(m, viscosity=meta["viscosity"], fast=True); b = orc.OracleSolver(m, viscosity=meta["viscosity"], fast=True)
+    for s in (a, b):
+        H.setup_solver(s, meta)
+        s.q[:] = d["q0"]
+    na = [a.explicit_solve(meta["relax"]) for _ in range(5)]
+    nb = [b.explicit_solve_omp(meta["relax"]) for _ in range(5)]
+    assert np.array_equal(a.q, b.q) and np.array_equal(a.qW, b.qW)
+    np.testing.assert_allclose(na, nb, rtol=1e-14)
