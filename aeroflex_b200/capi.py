@@ -33,7 +33,7 @@ EXPORTED_SYMBOLS = [
     "afx_partition_edge_l2g", "afx_partition_peer", "afx_nccl_unique_id", "afx_rans_create_partitioned",
     "afx_rans_p2p_export", "afx_rans_p2p_connect", "afx_rans_halo_mode",
     "afx_rans_create", "afx_rans_destroy", "afx_rans_set_bcs", "afx_rans_set_options", "afx_rans_set_cfl",
-    "afx_rans_set_math_mode", "afx_rans_get_math_mode",
+    "afx_rans_set_math_mode", "afx_rans_get_math_mode", "afx_rans_set_fused", "afx_rans_tile_info",
     "afx_rans_init", "afx_rans_refill_bcs", "afx_rans_bcs_from_internal", "afx_rans_set_q", "afx_rans_get_q",
     "afx_rans_set_q_local", "afx_rans_get_q_local", "afx_rans_get_field", "afx_rans_boundary_variables", "afx_rans_uniform_residual", "afx_rans_step_explicit",
     "afx_rans_run_explicit", "afx_rans_phase_dt_gradients", "afx_rans_phase_limiters", "afx_rans_phase_residual",
@@ -83,6 +83,7 @@ UNITS = [("rans_kernels_tu.cu", "kernels_strict.o", ["-DAFX_FAST=0", "-fmad=fals
          ("rans_solver.cu", "rans_solver.o", ["-fmad=false"]),
          ("mesh_host.cpp", "mesh_host.o", []),
          ("ordering.cpp", "ordering.o", []),
+         ("tiling.cpp", "tiling.o", []),
          ("partition.cpp", "partition.o", []),
          ("mesh_capi.cpp", "mesh_capi.o", [])]
 
@@ -165,6 +166,8 @@ def load_library():
     L.afx_rans_set_options.argtypes = [vp, C.c_int, C.c_int, C.c_double]
     L.afx_rans_set_cfl.argtypes = [vp, C.c_double]
     L.afx_rans_set_math_mode.argtypes = [vp, C.c_int]
+    L.afx_rans_set_fused.argtypes = [vp, C.c_int]
+    L.afx_rans_tile_info.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.afx_rans_get_math_mode.argtypes = [vp]
     for n in ("afx_rans_init", "afx_rans_refill_bcs", "afx_rans_bcs_from_internal", "afx_rans_phase_dt_gradients",
               "afx_rans_phase_limiters", "afx_rans_fill_jacobian"):
@@ -564,6 +567,16 @@ class GpuSolver:
         return int(self.L.afx_rans_launch_count(self.h))
 
     def profile_explicit(self, n_iter=5, relaxation=1.0):
-        out = np.zeros(5)
+        out = np.zeros(6)
         _check(self.L.afx_rans_profile_explicit(self.h, relaxation, n_iter, _ptr(out)))
-        return dict(dt_grad=out[0], limiter=out[1], flux=out[2], gather_update=out[3], halo_exchange=out[4])
+        return dict(dt_grad=out[0], limiter=out[1], flux=out[2], gather_update=out[3], halo_exchange=out[4], stage=out[5])
+
+    def set_fused(self, on):
+        """One fused kernel per Runge-Kutta stage (default) or limiter / flux / gather+update as three kernels."""
+        _check(self.L.afx_rans_set_fused(self.h, 1 if on else 0))
+
+    def tile_info(self):
+        out = (C.c_uint64 * 8)()
+        _check(self.L.afx_rans_tile_info(self.h, out))
+        return dict(fused=bool(out[0]), tiles=out[1], tile_cells=out[2], smem_bytes=out[3], ctas_per_sm=out[4], max_local_cells=out[5],
+                    max_local_faces=out[6], local_cells=out[7])

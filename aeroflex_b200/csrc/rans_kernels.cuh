@@ -149,6 +149,47 @@ __device__ __forceinline__ double venkat(double dqg, double dmax, double dmin, d
     return 1.0;
 }
 
+// limiter of one cell from its state, the min/max over its neighbours, its gradient and the face offsets of its slots
+// (solver.h:538-592); `valid` bit s = slot s holds a face.  Shared by k_limiter and the fused k_stage.
+__device__ __forceinline__ d4 limiter_value(const d4& qi, const d4& lo, const d4& hi, const d4& gxi, const d4& gyi, const double2 (&dxy)[4],
+                                            unsigned valid, double area, double limiter_k)
+{
+    const double Ka = limiter_k * sqrt(area);
+    const double K3a = Ka * Ka * Ka;
+    const d4 dmax = mk4(hi.x - qi.x, hi.y - qi.y, hi.z - qi.z, hi.w - qi.w);
+    const d4 dmin = mk4(lo.x - qi.x, lo.y - qi.y, lo.z - qi.z, lo.w - qi.w);
+    d4 l = mk4(1, 1, 1, 1);
+#if AFX_FAST
+    // Where the limiter function is below 1 it decreases monotonically with |dqg| (d phi/d dqg < 0 for dqg > dm/2), and
+    // values above 1 never survive the min with 1: the minimum over the faces is attained at the largest positive and
+    // the most negative projected increment -> 2 evaluations per component instead of one per face.
+    d4 pmax = mk4(0, 0, 0, 0), pmin = mk4(0, 0, 0, 0);
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        if (!(valid & (1u << s))) continue;
+        const double dx = dxy[s].x, dy = dxy[s].y;
+        const double p0 = gxi.x * dx + gyi.x * dy, p1 = gxi.y * dx + gyi.y * dy, p2 = gxi.z * dx + gyi.z * dy, p3 = gxi.w * dx + gyi.w * dy;
+        pmax.x = fmax(pmax.x, p0); pmax.y = fmax(pmax.y, p1); pmax.z = fmax(pmax.z, p2); pmax.w = fmax(pmax.w, p3);
+        pmin.x = fmin(pmin.x, p0); pmin.y = fmin(pmin.y, p1); pmin.z = fmin(pmin.z, p2); pmin.w = fmin(pmin.w, p3);
+    }
+    l.x = fmin(fmin(1.0, venkat(pmax.x, dmax.x, dmin.x, K3a)), venkat(pmin.x, dmax.x, dmin.x, K3a));
+    l.y = fmin(fmin(1.0, venkat(pmax.y, dmax.y, dmin.y, K3a)), venkat(pmin.y, dmax.y, dmin.y, K3a));
+    l.z = fmin(fmin(1.0, venkat(pmax.z, dmax.z, dmin.z, K3a)), venkat(pmin.z, dmax.z, dmin.z, K3a));
+    l.w = fmin(fmin(1.0, venkat(pmax.w, dmax.w, dmin.w, K3a)), venkat(pmin.w, dmax.w, dmin.w, K3a));
+#else
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        if (!(valid & (1u << s))) continue;
+        const double dx = dxy[s].x, dy = dxy[s].y;
+        l.x = fmin(l.x, venkat(gxi.x * dx + gyi.x * dy, dmax.x, dmin.x, K3a));
+        l.y = fmin(l.y, venkat(gxi.y * dx + gyi.y * dy, dmax.y, dmin.y, K3a));
+        l.z = fmin(l.z, venkat(gxi.z * dx + gyi.z * dy, dmax.z, dmin.z, K3a));
+        l.w = fmin(l.w, venkat(gxi.w * dx + gyi.w * dy, dmax.w, dmin.w, K3a));
+    }
+#endif
+    return l;
+}
+
 __global__ void __launch_bounds__(256, AFX_LIM_MINB) k_limiter(DevMesh m, const d4* __restrict__ qk, const d4* __restrict__ gx,
                                                  const d4* __restrict__ gy, d4* __restrict__ lim, double limiter_k, int walls,
                                                  uint32_t lo1, uint32_t n1, uint32_t lo2, uint32_t n2)
@@ -166,10 +207,12 @@ __global__ void __launch_bounds__(256, AFX_LIM_MINB) k_limiter(DevMesh m, const 
         nbs[s] = m.cnb[(size_t)s * m.N + i];
         dxy[s] = m.cdxy[(size_t)s * m.N + i];
     }
+    unsigned valid = 0;
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
         const uint32_t j = nbs[s];
         if (j == CF_NONE) continue;
+        valid |= 1u << s;
         // a wall ghost holds its owner's state (set_walls_from_internal): no need to read it
         bool wall_ghost = false;
         if (walls && j >= m.N) {
@@ -180,42 +223,7 @@ __global__ void __launch_bounds__(256, AFX_LIM_MINB) k_limiter(DevMesh m, const 
         lo.x = fmin(lo.x, qj.x); lo.y = fmin(lo.y, qj.y); lo.z = fmin(lo.z, qj.z); lo.w = fmin(lo.w, qj.w);
         hi.x = fmax(hi.x, qj.x); hi.y = fmax(hi.y, qj.y); hi.z = fmax(hi.z, qj.z); hi.w = fmax(hi.w, qj.w);
     }
-    const d4 gxi = gx[i], gyi = gy[i];
-    const double Ka = limiter_k * sqrt(m.area[i]);
-    const double K3a = Ka * Ka * Ka;
-    const d4 dmax = mk4(hi.x - qi.x, hi.y - qi.y, hi.z - qi.z, hi.w - qi.w);
-    const d4 dmin = mk4(lo.x - qi.x, lo.y - qi.y, lo.z - qi.z, lo.w - qi.w);
-    d4 l = mk4(1, 1, 1, 1);
-#if AFX_FAST
-    // Where the limiter function is below 1 it decreases monotonically with |dqg| (d phi/d dqg < 0 for dqg > dm/2), and
-    // values above 1 never survive the min with 1: the minimum over the faces is attained at the largest positive and
-    // the most negative projected increment -> 2 evaluations per component instead of one per face.
-    d4 pmax = mk4(0, 0, 0, 0), pmin = mk4(0, 0, 0, 0);
-#pragma unroll
-    for (int s = 0; s < 4; ++s) {
-        if (nbs[s] == CF_NONE) continue;
-        const double dx = dxy[s].x, dy = dxy[s].y;
-        const double p0 = gxi.x * dx + gyi.x * dy, p1 = gxi.y * dx + gyi.y * dy, p2 = gxi.z * dx + gyi.z * dy, p3 = gxi.w * dx + gyi.w * dy;
-        pmax.x = fmax(pmax.x, p0); pmax.y = fmax(pmax.y, p1); pmax.z = fmax(pmax.z, p2); pmax.w = fmax(pmax.w, p3);
-        pmin.x = fmin(pmin.x, p0); pmin.y = fmin(pmin.y, p1); pmin.z = fmin(pmin.z, p2); pmin.w = fmin(pmin.w, p3);
-    }
-    l.x = fmin(fmin(1.0, venkat(pmax.x, dmax.x, dmin.x, K3a)), venkat(pmin.x, dmax.x, dmin.x, K3a));
-    l.y = fmin(fmin(1.0, venkat(pmax.y, dmax.y, dmin.y, K3a)), venkat(pmin.y, dmax.y, dmin.y, K3a));
-    l.z = fmin(fmin(1.0, venkat(pmax.z, dmax.z, dmin.z, K3a)), venkat(pmin.z, dmax.z, dmin.z, K3a));
-    l.w = fmin(fmin(1.0, venkat(pmax.w, dmax.w, dmin.w, K3a)), venkat(pmin.w, dmax.w, dmin.w, K3a));
-    lim[i] = l;
-    return;
-#endif
-#pragma unroll
-    for (int s = 0; s < 4; ++s) {
-        if (nbs[s] == CF_NONE) continue;
-        const double dx = dxy[s].x, dy = dxy[s].y;
-        l.x = fmin(l.x, venkat(gxi.x * dx + gyi.x * dy, dmax.x, dmin.x, K3a));
-        l.y = fmin(l.y, venkat(gxi.y * dx + gyi.y * dy, dmax.y, dmin.y, K3a));
-        l.z = fmin(l.z, venkat(gxi.z * dx + gyi.z * dy, dmax.z, dmin.z, K3a));
-        l.w = fmin(l.w, venkat(gxi.w * dx + gyi.w * dy, dmax.w, dmin.w, K3a));
-    }
-    lim[i] = l;
+    lim[i] = limiter_value(qi, lo, hi, gx[i], gy[i], dxy, valid, m.area[i], limiter_k);
 }
 
 // ---------------------------------------------------------------------------

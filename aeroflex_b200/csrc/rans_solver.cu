@@ -27,6 +27,7 @@
 #include "ordering.h"
 #include "partition.h"
 #include "rans_types.h"
+#include "tiling.h"
 
 namespace afx {
 
@@ -145,6 +146,19 @@ struct Solver {
     // device geometry
     DBuf<uint2> fcells; DBuf<d4> fgA, fgB, ftij; DBuf<uint8_t> fkind; DBuf<uint32_t> cf, cnb; DBuf<double2> cdxy; DBuf<double> area;
     DBuf<double> lsqM; DBuf<uint16_t> lsq_perm;
+    // shared-memory tiles of the fused stage kernel (tiling.h)
+    DBuf<uint4> t_head, t_ctab; DBuf<uint32_t> t_halo, t_face; DBuf<double> t_area; DBuf<double2> t_dxy; DBuf<d4> t_fgeo;
+    TileTab tt{};
+    uint32_t n_tiles = 0, tile_cells = 0;
+    size_t stage_smem = 0, n_tile_faces = 0;
+    int stage_ctas_per_sm = 0;
+    unsigned stage_grid = 0;
+    bool tiles_ready = false, use_fused = true;
+    uint64_t tile_local_cells = 0;
+    void build_tile_tables(const std::vector<uint32_t>& h_cf, const std::vector<uint32_t>& h_cnb, const std::vector<double2>& h_cdxy,
+                           const std::vector<double>& h_area, const std::vector<d4>& h_gA);
+    bool fused_stage() const { return tiles_ready && use_fused && second_order && viscous_type == 0 && !(halo && halo_overlap); }
+    void launch_stage(int s, const d4* qk_in, d4* qk_out, double alpha);
     DBuf<uint32_t> bface, bghost, bowner; DBuf<int32_t> bpatch; DBuf<d4> bstate; DBuf<double> bcx, bcy;
     DBuf<uint32_t> perm_c_new2old, perm_c_old2new;
     // device state
@@ -393,6 +407,8 @@ void Solver::create(const afx_mesh_desc& m, const afx_gas& g, int visc, int dev,
         h_bcx[b] = m.edges_cx[e]; h_bcy[b] = m.edges_cy[e];
     }
 
+    build_tile_tables(h_cf, h_cnb, h_cdxy, h_area, h_gA);
+
     // ---- upload ----
     fcells.upload(h_fc, st); fgA.upload(h_gA, st); fgB.upload(h_gB, st);
     if (viscous_type == 1) ftij.upload(h_t, st);
@@ -407,7 +423,7 @@ void Solver::create(const afx_mesh_desc& m, const afx_gas& g, int visc, int dev,
     for (DBuf<d4>* b : {&q, &qkA, &qkB, &gx, &gy, &lim, &qW, &rhs, &stage}) { b->alloc(NT); b->zero(st); }
     flux.alloc(E); flux.zero(st);
     dt.alloc(NT); dt.zero(st); dt_ref.alloc(NT);
-    partial.alloc(blocks(NT) + 1); norms.alloc(NORM_RING); norms.zero(st);
+    partial.alloc(std::max<size_t>(blocks(NT), stage_grid) + 4); norms.alloc(NORM_RING); norms.zero(st);
     prm.alloc(8); prm.zero(st); counters.alloc(4); counters.zero(st); scratch.alloc(16);
     // limiters start at 1 (ghost rows keep that value, solver.h:519)
     kt->fill_cells(lim.p, NT, d4{1, 1, 1, 1}, st);
@@ -463,6 +479,7 @@ void Solver::set_bcs(int n_patch, const uint8_t* kinds, const afx_bvars* vars)
     }
     fkind.upload(h_kind, st);
     bstate.upload(h_state, st);
+    if (tiles_ready) { kt->tile_face_kinds(t_fgeo.p, t_face.p, fkind.p, n_tile_faces, st); ++launches; }
     CK(cudaStreamSynchronize(st));
     dm.fkind = fkind.p;
     bcs_set = true;
@@ -561,6 +578,88 @@ void Solver::launch_gather(const d4* qk_in, d4* qk_out, d4* vec_out, double alph
     if (halo && MODE == 0) exchange(qk_out, st);
 }
 
+// Tiles of the fused stage kernel.  AFX_FUSED=0 keeps the three-kernel stage; AFX_TILE sets the cells per tile (the
+// largest size whose staging fits the shared memory of one SM is used otherwise), AFX_STAGE_CTAS the resident CTAs per SM.
+void Solver::build_tile_tables(const std::vector<uint32_t>& h_cf, const std::vector<uint32_t>& h_cnb, const std::vector<double2>& h_cdxy,
+                               const std::vector<double>& h_area, const std::vector<d4>& h_gA)
+{
+    tiles_ready = false;
+    if (const char* e = getenv("AFX_FUSED")) if (e[0] == '0') return;
+    uint32_t T = 384;
+    if (const char* e = getenv("AFX_TILE")) T = (uint32_t)std::max(64, std::min(1024, atoi(e)));
+    int ctas = 1;
+    if (const char* e = getenv("AFX_STAGE_CTAS")) ctas = std::max(1, std::min(4, atoi(e)));
+    int smem_max = 0;
+    CK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    const size_t budget = (size_t)(smem_max - 1024) / ctas - (ctas > 1 ? 1024 : 0);
+    TilePlan plan;
+    StageSmem L{};
+    for (;; T = (T > 96 ? T - 32 : T / 2)) {
+        bool ok = true;
+        try { plan = build_tiles(N, n_upd, n_front, n_grad, h_cf.data(), h_cnb.data(), T); }
+        catch (const std::invalid_argument&) { ok = false; }  // cells not ordered compactly enough for this tile size
+        if (ok) {
+            L = stage_smem_layout(plan.max_loc, plan.max_n1, plan.max_nf, plan.max_nc, plan.max_halo);
+            if (L.total <= budget) break;
+        }
+        if (T <= 32) return;  // no tiling fits: three-kernel stage
+    }
+    static_assert(sizeof(TileHead) == 32 && sizeof(TileCell) == 16, "tile tables are read as uint4");
+    tile_cells = T; n_tiles = (uint32_t)plan.head.size(); stage_smem = L.total; tile_local_cells = plan.local_cells;
+    // static geometry packed per tile: face offsets and areas of the own + ring-1 cells, normals / lengths of the local faces
+    const size_t n_cell_rec = plan.ctab.size();
+    n_tile_faces = plan.face.size();
+    std::vector<double> h_ta(n_cell_rec, 1.0);
+    std::vector<double2> h_td(4 * n_cell_rec, make_double2(0., 0.));
+    std::vector<d4> h_tf(n_tile_faces);
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t t = 0; t < (int64_t)n_tiles; ++t) {
+        const TileHead& h = plan.head[t];
+        const uint32_t n1 = h.nc + h.h1, n1p = (n1 + 1u) & ~1u;
+        for (uint32_t l = 0; l < n1; ++l) {
+            const uint32_t c = l < h.nc ? h.cell0 + l : plan.halo[h.off_halo + l - h.nc];
+            h_ta[h.off_cell + l] = h_area[c];
+            for (int s = 0; s < 4; ++s) h_td[4 * (size_t)h.off_cell + (size_t)s * n1p + l] = h_cdxy[(size_t)s * N + c];
+        }
+        for (uint32_t lf = 0; lf < h.nf; ++lf) {
+            const d4& a = h_gA[plan.face[h.off_face + lf]];
+            h_tf[h.off_face + lf] = d4{a.x, a.y, a.z, 0.0};  // kind: set_bcs
+        }
+    }
+    auto up = [&](auto& dbuf, const auto& host) {
+        using T_ = std::remove_pointer_t<decltype(dbuf.p)>;
+        dbuf.alloc(std::max<size_t>(1, host.size() * sizeof(host[0]) / sizeof(T_)));
+        if (!host.empty()) CK(cudaMemcpyAsync(dbuf.p, host.data(), host.size() * sizeof(host[0]), cudaMemcpyHostToDevice, st));
+    };
+    up(t_head, plan.head); up(t_halo, plan.halo); up(t_ctab, plan.ctab); up(t_face, plan.face); up(t_area, h_ta); up(t_dxy, h_td); up(t_fgeo, h_tf);
+    CK(cudaStreamSynchronize(st));
+    tt = TileTab{t_head.p, t_halo.p, t_ctab.p, t_area.p, t_dxy.p, t_fgeo.p, n_tiles, plan.max_loc, plan.max_n1, plan.max_nf, plan.max_nc, plan.max_halo};
+    const int a = strict::table().stage_prepare(stage_smem), b = fast::table().stage_prepare(stage_smem);
+    if (a < 1 || b < 1) return;  // the kernel does not fit: three-kernel stage
+    stage_ctas_per_sm = std::min(a, b);
+    cudaDeviceProp prop{};
+    CK(cudaGetDeviceProperties(&prop, device));
+    stage_grid = std::min<unsigned>(n_tiles, (unsigned)prop.multiProcessorCount * (unsigned)stage_ctas_per_sm);
+    tiles_ready = true;
+}
+
+// One fused stage: limiter + MUSCL + flux + gather + update on shared-memory tiles, then the halo hand-off.
+void Solver::launch_stage(int s, const d4* qk_in, d4* qk_out, double alpha)
+{
+    ensure_halo();
+    const PushArgs* push = (halo && halo->p2p) ? &halo->push : nullptr;
+    kt->stage(s == 2, dm, tt, stage_grid, stage_smem, qk_in, q.p, qk_out, gx.p, gy.p, dt.p, qW.p, lim.p, alpha, prm.p, limiter_k, gas, norm_out(), push, st);
+    ++launches;
+    if (!halo) return;
+    if (halo->p2p) {  // the kernel stored the send layer into the peers' buffers: flags, then fill our halo cells
+        kt->halo_signal(halo->sig, st);
+        kt->halo_wait_scatter(halo->wait, qk_out, st);
+        launches += 2;
+    } else {
+        exchange(qk_out, st);
+    }
+}
+
 // explicitSolver::solve, solver.h:802-828.  Stage 0 reads q in place of qk (they
 // are equal), stage 2 writes q in place; qkA/qkB carry the intermediate stages.
 void Solver::explicit_iteration()
@@ -571,6 +670,7 @@ void Solver::explicit_iteration()
     d4* out[3] = {qkA.p, qkB.p, q.p};
     const double alpha[3] = {0.25, 0.5, 1.};  // solver.h:723
     for (int s = 0; s < 3; ++s) {
+        if (fused_stage()) { launch_stage(s, in[s], out[s], alpha[s]); continue; }
         if (second_order) launch_limiter(in[s]);
         launch_flux(in[s], false, d4{0, 0, 0, 0});
         if (s < 2) launch_gather<0, 0>(in[s], out[s], qW.p, alpha[s], grads);
@@ -1138,6 +1238,19 @@ int afx_rans_set_math_mode(afx_rans* s, int mode)
     return guard([&] { s->s.set_math_mode(mode); });
 }
 
+int afx_rans_set_fused(afx_rans* s, int on)
+{
+    return guard([&] { if (s->s.use_fused != (on != 0)) { s->s.use_fused = (on != 0); s->s.invalidate_graph(); } });
+}
+
+int afx_rans_tile_info(afx_rans* s, uint64_t out[8])
+{
+    const auto& S = s->s;
+    out[0] = S.fused_stage() ? 1 : 0; out[1] = S.n_tiles; out[2] = S.tile_cells; out[3] = S.stage_smem; out[4] = (uint64_t)S.stage_ctas_per_sm;
+    out[5] = S.tt.max_loc; out[6] = S.tt.max_nf; out[7] = S.tile_local_cells;
+    return AFX_OK;
+}
+
 int afx_rans_get_math_mode(afx_rans* s) { return s->s.kt == &afx::strict::table() ? AFX_MATH_STRICT : AFX_MATH_FAST; }
 
 int afx_rans_set_cfl(afx_rans* s, double cfl)
@@ -1466,15 +1579,16 @@ int afx_rans_wall_cp(afx_rans* s, int patch, double* cp)
 int afx_rans_last_device_ms(afx_rans* s, double* ms) { *ms = s->s.last_ms; return AFX_OK; }
 int64_t afx_rans_launch_count(afx_rans* s) { return s->s.launches; }
 
-int afx_rans_profile_explicit(afx_rans* s, double relaxation, int n_iter, double out_ms[5])
+int afx_rans_profile_explicit(afx_rans* s, double relaxation, int n_iter, double out_ms[6])
 {
     return guard([&] {
         auto& S = s->s;
         S.use();
         if (!S.bcs_set) throw afx::InvalidArg("set_bcs has not been called");
         S.push_params(relaxation);
-        for (int k = 0; k < 5; ++k) out_ms[k] = 0;
+        for (int k = 0; k < 6; ++k) out_ms[k] = 0;
         const bool grads = S.visc_not_inviscid || S.second_order;
+        const bool fused = S.fused_stage();
         const afx::d4* in[3] = {S.q.p, S.qkA.p, S.qkB.p};
         afx::d4* outp[3] = {S.qkA.p, S.qkB.p, S.q.p};
         const double alpha[3] = {0.25, 0.5, 1.};
@@ -1486,6 +1600,14 @@ int afx_rans_profile_explicit(afx_rans* s, double relaxation, int n_iter, double
             S.launch_dt_grad(grads, grads);
             CK(cudaEventRecord(ev[e++], S.st));
             for (int st = 0; st < 3; ++st) {
+                if (fused) {
+                    CK(cudaEventRecord(ev[e++], S.st));
+                    CK(cudaEventRecord(ev[e++], S.st));
+                    S.launch_stage(st, in[st], outp[st], alpha[st]);
+                    CK(cudaEventRecord(ev[e++], S.st));
+                    CK(cudaEventRecord(ev[e++], S.st));
+                    continue;
+                }
                 if (S.second_order) S.launch_limiter(in[st]);
                 CK(cudaEventRecord(ev[e++], S.st));
                 S.launch_flux(in[st], false, afx::d4{0, 0, 0, 0});
@@ -1500,6 +1622,7 @@ int afx_rans_profile_explicit(afx_rans* s, double relaxation, int n_iter, double
             float ms;
             CK(cudaEventElapsedTime(&ms, ev[0], ev[1])); out_ms[0] += ms;
             for (int st = 0; st < 3; ++st) {
+                if (fused) { CK(cudaEventElapsedTime(&ms, ev[3 + 4 * st], ev[4 + 4 * st])); out_ms[5] += ms; continue; }
                 CK(cudaEventElapsedTime(&ms, ev[1 + 4 * st], ev[2 + 4 * st])); out_ms[1] += ms;
                 CK(cudaEventElapsedTime(&ms, ev[2 + 4 * st], ev[3 + 4 * st])); out_ms[2] += ms;
                 CK(cudaEventElapsedTime(&ms, ev[3 + 4 * st], ev[4 + 4 * st])); out_ms[3] += ms;
@@ -1507,7 +1630,7 @@ int afx_rans_profile_explicit(afx_rans* s, double relaxation, int n_iter, double
             }
         }
         for (auto& e : ev) cudaEventDestroy(e);
-        for (int k = 0; k < 5; ++k) out_ms[k] /= n_iter;
+        for (int k = 0; k < 6; ++k) out_ms[k] /= n_iter;
         S.jac_valid = false;
     });
 }

@@ -1,0 +1,350 @@
+// rans_stage.cuh -- one Runge-Kutta stage of explicitSolver::solve (solver.h:808-822) as ONE persistent kernel on
+// shared-memory tiles, fed by the copy engine.
+//
+// A tile is a run of consecutive (Hilbert-ordered) cells plus its ring-1 cells (their limiter is recomputed here) plus
+// the cells those read (tiling.h).  One CTA per SM walks the tiles blockIdx.x, blockIdx.x + gridDim.x, ...  For each tile:
+//   P1  one thread per own/ring-1 cell: min/max over the neighbours, Venkatakrishnan limiter (calc_limiters,
+//       solver.h:517-593), MUSCL face states q + lim*(g.d) (solver.h:774-781) stored per local face side
+//   P2  one thread per local face: Roe / boundary flux (physics.h:160-530) times the face length, stored over the
+//       left face state
+//   P3  one thread per own cell: owner-computes gather in slot (= ascending reference edge) order, /area, stage update
+//       (solver.h:787-798, 818-821), wall ghosts of the next stage, residual norm, halo push
+// The phases read shared memory only.  Their inputs form three groups -- (1) states, gradients, face offsets, areas and
+// local connectivity of the cells, (2) face normals/lengths/kinds, (3) iteration-start state and time step -- and a
+// group is requested as soon as the phase that reads it has finished with the previous tile: contiguous pieces by bulk
+// copies (cp.async.bulk, completion on an mbarrier), the ring cells' states and gradients by 16-byte cp.async gathers.
+// So the copies of tile k+1 fly under the arithmetic of tile k and the kernel is bound by the fp64 pipe / HBM, not by
+// load latency.
+// The limiter and flux arrays of the three-kernel stage never exist.  Faces cut by a tile boundary are evaluated by both
+// tiles (identical inputs -> identical bits), ring-1 limiters are recomputed; every per-cell sum keeps the reference's
+// order, so in strict mode the state is bit-identical to the unfused kernels and to the CPU reference.
+#pragma once
+#include <algorithm>
+
+#include "rans_kernels.cuh"
+
+#ifndef AFX_STAGE_THREADS
+#define AFX_STAGE_THREADS 512
+#endif
+#ifndef AFX_STAGE_MINB
+#define AFX_STAGE_MINB 1
+#endif
+
+namespace afx {
+namespace AFX_NS {
+
+// ---- copy-engine and mbarrier primitives (PTX) ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+// global -> shared bulk copy; bytes is a multiple of 16, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+struct TileView {  // one tile's header, unpacked
+    uint32_t cell0, nc, n1, n1p, nf, nh, nhp, off_halo, off_cell, off_face;
+};
+__device__ __forceinline__ TileView tile_view(const TileTab& tt, uint32_t tile)
+{
+    const uint4 a = tt.head[2 * (size_t)tile], b = tt.head[2 * (size_t)tile + 1];
+    TileView v;
+    v.cell0 = a.x; v.nc = a.y; v.n1 = a.y + a.z; v.n1p = (v.n1 + 1u) & ~1u; v.nh = a.z + a.w; v.nhp = (v.nh + 3u) & ~3u;
+    v.nf = b.x; v.off_halo = b.y; v.off_cell = b.z; v.off_face = b.w;
+    return v;
+}
+
+template <int LAST>
+__global__ void __launch_bounds__(AFX_STAGE_THREADS, AFX_STAGE_MINB)
+k_stage(DevMesh m, TileTab tt, const d4* __restrict__ qk_in, const d4* q0, d4* qk_out, const d4* __restrict__ gx,
+        const d4* __restrict__ gy, const double* __restrict__ dt, d4* __restrict__ qW, d4* __restrict__ lim, double alpha,
+        const double* __restrict__ prm, double limiter_k, GasC g, NormOut no, PushArgs push)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    const StageSmem L = stage_smem_layout(tt.max_loc, tt.max_n1, tt.max_nf, tt.max_nc, tt.max_halo);
+    d4* const sq = reinterpret_cast<d4*>(smem + L.sq);
+    d4* const sgx = reinterpret_cast<d4*>(smem + L.sgx);
+    d4* const sgy = reinterpret_cast<d4*>(smem + L.sgy);
+    double2* const sdxy = reinterpret_cast<double2*>(smem + L.sdxy);
+    double* const sarea = reinterpret_cast<double*>(smem + L.sarea);
+    uint4* const sctab = reinterpret_cast<uint4*>(smem + L.sctab);
+    d4* const sfg = reinterpret_cast<d4*>(smem + L.sfg);
+    d4* const srec = reinterpret_cast<d4*>(smem + L.srec);
+    d4* const sq0 = reinterpret_cast<d4*>(smem + L.sq0);
+    double* const sdt = reinterpret_cast<double*>(smem + L.sdt);
+    double* const sarea3 = reinterpret_cast<double*>(smem + L.sarea3);
+    uint4* const sctab3 = reinterpret_cast<uint4*>(smem + L.sctab3);
+    uint32_t* const shalo = reinterpret_cast<uint32_t*>(smem + L.shalo);
+    const uint32_t bar1 = smem_u32(smem + L.bars), bar2 = bar1 + 8, bar3 = bar1 + 16;
+    const uint32_t tid = threadIdx.x;
+    const bool q0_is_in = (q0 == qk_in);  // stage 0: the stage state IS the iteration-start state
+
+    if (tid == 0) { mbar_init(bar1, 1); mbar_init(bar2, 1); mbar_init(bar3, 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+
+    // ---- requests ----
+    // group 1 of tile v (its ring ids are in shalo[buf]); also the ring ids of the tile after it into the other buffer
+    auto request_g1 = [&](const TileView& v, uint32_t buf, bool has_next, const TileView& nx) {
+        if (tid == 0) {
+            const uint32_t bytes = 32u * v.nc * 3u + 64u * v.n1p + 8u * v.n1p + 16u * v.n1p + (has_next ? 4u * nx.nhp : 0u);
+            mbar_expect_tx(bar1, bytes);
+            bulk_g2s(smem_u32(sq), qk_in + v.cell0, 32u * v.nc, bar1);
+            bulk_g2s(smem_u32(sgx), gx + v.cell0, 32u * v.nc, bar1);
+            bulk_g2s(smem_u32(sgy), gy + v.cell0, 32u * v.nc, bar1);
+            bulk_g2s(smem_u32(sdxy), tt.dxy_t + 4 * (size_t)v.off_cell, 64u * v.n1p, bar1);
+            bulk_g2s(smem_u32(sarea), tt.area_t + v.off_cell, 8u * v.n1p, bar1);
+            bulk_g2s(smem_u32(sctab), tt.ctab + v.off_cell, 16u * v.n1p, bar1);
+            if (has_next && nx.nhp) bulk_g2s(smem_u32(shalo + (buf ^ 1u) * tt.max_halo), tt.halo + nx.off_halo, 4u * nx.nhp, bar1);
+        }
+        const uint32_t* ids = shalo + buf * tt.max_halo;
+        for (uint32_t k = tid; k < v.nh; k += AFX_STAGE_THREADS) {  // ring cells: states, and gradients of ring 1
+            const uint32_t gid = ids[k], l = v.nc + k;
+            const char* s = reinterpret_cast<const char*>(qk_in + gid);
+            cp_async16(smem_u32(sq + l), s); cp_async16(smem_u32(sq + l) + 16, s + 16);
+            if (l < v.n1) {
+                const char* a = reinterpret_cast<const char*>(gx + gid);
+                const char* b = reinterpret_cast<const char*>(gy + gid);
+                cp_async16(smem_u32(sgx + l), a); cp_async16(smem_u32(sgx + l) + 16, a + 16);
+                cp_async16(smem_u32(sgy + l), b); cp_async16(smem_u32(sgy + l) + 16, b + 16);
+            }
+        }
+        cp_async_commit();
+    };
+    auto request_g2 = [&](const TileView& v) {
+        if (tid == 0) {
+            mbar_expect_tx(bar2, 32u * v.nf);
+            bulk_g2s(smem_u32(sfg), tt.fgeo_t + v.off_face, 32u * v.nf, bar2);
+        }
+    };
+    auto request_g3 = [&](const TileView& v) {
+        if (!q0_is_in && tid == 0) {
+            mbar_expect_tx(bar3, 32u * v.nc);
+            bulk_g2s(smem_u32(sq0), q0 + v.cell0, 32u * v.nc, bar3);
+        }
+        for (uint32_t l = tid; l < v.nc; l += AFX_STAGE_THREADS) cp_async8(smem_u32(sdt + l), dt + v.cell0 + l);
+        cp_async_commit();
+    };
+
+    double nrm = 0;
+    uint32_t tile = blockIdx.x, it = 0;
+    TileView cur{}, nxt{};
+    if (tile < tt.n_tiles) {
+        cur = tile_view(tt, tile);
+        for (uint32_t k = tid; k < cur.nhp; k += AFX_STAGE_THREADS) shalo[k] = tt.halo[cur.off_halo + k];  // first tile: ids by plain loads
+        __syncthreads();
+        const bool has_next = tile + gridDim.x < tt.n_tiles;
+        if (has_next) nxt = tile_view(tt, tile + gridDim.x);
+        request_g1(cur, 0, has_next, nxt);
+        request_g2(cur);
+    }
+    const d4 zero = mk4(0, 0, 0, 0);
+    for (; tile < tt.n_tiles; tile += gridDim.x, ++it) {
+        const uint32_t par = it & 1u;
+        const bool has_next = tile + gridDim.x < tt.n_tiles;
+        const bool has_next2 = tile + 2 * gridDim.x < tt.n_tiles;
+        TileView nx2{};
+        if (has_next2) nx2 = tile_view(tt, tile + 2 * gridDim.x);
+
+        // ---- P1: limiter and MUSCL face states of the own and ring-1 cells ----
+        cp_async_wait<0>();      // my gathers of group 1
+        mbar_wait(bar1, par);
+        __syncthreads();         // everybody's gathers; P3 of the previous tile is over
+        request_g3(cur);         // group 3 of THIS tile: P3 of the previous tile read these buffers until the barrier above
+        for (uint32_t l = tid; l < cur.n1; l += AFX_STAGE_THREADS) {
+            const uint4 tc = sctab[l];
+            const uint32_t nb[4] = {tc.x & 0xFFFFu, tc.x >> 16, tc.y & 0xFFFFu, tc.y >> 16};
+            const uint32_t fs[4] = {tc.z & 0xFFFFu, tc.z >> 16, tc.w & 0xFFFFu, tc.w >> 16};
+            double2 dxy[4];
+#pragma unroll
+            for (int s = 0; s < 4; ++s) dxy[s] = sdxy[s * cur.n1p + l];
+            const d4 gxi = sgx[l], gyi = sgy[l];
+            const double area = sarea[l];
+            const d4 qi = sq[l];
+            d4 lo = qi, hi = qi;
+            unsigned valid = 0;
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                if (nb[s] == 0xFFFFu) continue;
+                valid |= 1u << s;
+                const d4 qj = sq[nb[s]];  // wall ghosts hold their owner's state (written by the previous stage / k_dt_grad)
+                lo.x = fmin(lo.x, qj.x); lo.y = fmin(lo.y, qj.y); lo.z = fmin(lo.z, qj.z); lo.w = fmin(lo.w, qj.w);
+                hi.x = fmax(hi.x, qj.x); hi.y = fmax(hi.y, qj.y); hi.z = fmax(hi.z, qj.z); hi.w = fmax(hi.w, qj.w);
+                // the cell across an own cell's face is own, ring 1 or a ghost; a ghost cell has zero gradient and
+                // limiter 1, so its face state is its state
+                if (nb[s] >= cur.n1 && fs[s] != 0xFFFFu) srec[2 * (fs[s] & 0x7FFFu) + 1] = qj;
+            }
+            const d4 lm = limiter_value(qi, lo, hi, gxi, gyi, dxy, valid, area, limiter_k);
+            if (l < cur.nc) {  // what P3 needs after group 1 has been overwritten by the next tile
+                sarea3[l] = area; sctab3[l] = tc;
+                if (q0_is_in) sq0[l] = qi;
+                if (LAST && prm[2] != 0.0) lim[cur.cell0 + l] = lm;  // kept, like qW, for the last iteration of a run only
+            }
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                if (fs[s] == 0xFFFFu) continue;
+                const double dx = dxy[s].x, dy = dxy[s].y;
+                d4 r;  // solver.h:774-781
+                r.x = qi.x + (gxi.x * dx + gyi.x * dy) * lm.x;
+                r.y = qi.y + (gxi.y * dx + gyi.y * dy) * lm.y;
+                r.z = qi.z + (gxi.z * dx + gyi.z * dy) * lm.z;
+                r.w = qi.w + (gxi.w * dx + gyi.w * dy) * lm.w;
+                srec[2 * (fs[s] & 0x7FFFu) + (fs[s] >> 15)] = r;
+            }
+        }
+        __syncthreads();
+        if (has_next) request_g1(nxt, par ^ 1u, has_next2, nx2); else cp_async_commit();
+
+        // ---- P2: one flux per local face ----
+        mbar_wait(bar2, par);
+        for (uint32_t lf = tid; lf < cur.nf; lf += AFX_STAGE_THREADS) {
+            const d4 gA = sfg[lf];
+            const d4 qL = srec[2 * lf], qR = srec[2 * lf + 1];
+            d4 fl = face_flux<0>((int)gA.w, qL, qR, zero, zero, gA.x, gA.y, g);
+            fl.x *= gA.z; fl.y *= gA.z; fl.z *= gA.z; fl.w *= gA.z;
+            srec[2 * lf] = fl;
+            srec[2 * lf + 1].x = gA.w;  // P3 needs the kind of boundary faces after group 2 has been overwritten
+        }
+        __syncthreads();
+        if (has_next) request_g2(nxt);
+
+        // ---- P3: gather, update, ghosts, norm ----
+        cp_async_wait<1>();      // my time steps (group 1 of the next tile may still be in flight)
+        if (!q0_is_in) mbar_wait(bar3, par);
+        for (uint32_t l = tid; l < cur.nc; l += AFX_STAGE_THREADS) {
+            const uint32_t i = cur.cell0 + l;
+            const uint4 tc = sctab3[l];
+            const uint32_t nb[4] = {tc.x & 0xFFFFu, tc.x >> 16, tc.y & 0xFFFFu, tc.y >> 16};
+            const uint32_t fs[4] = {tc.z & 0xFFFFu, tc.z >> 16, tc.w & 0xFFFFu, tc.w >> 16};
+            d4 r = zero;
+            uint32_t wall_ghost[4] = {CF_NONE, CF_NONE, CF_NONE, CF_NONE};
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                if (fs[s] == 0xFFFFu) continue;
+                const uint32_t lf = fs[s] & 0x7FFFu;
+                const d4 fl = srec[2 * lf];
+                if (fs[s] >> 15) { r.x += fl.x; r.y += fl.y; r.z += fl.z; r.w += fl.w; }
+                else { r.x -= fl.x; r.y -= fl.y; r.z -= fl.z; r.w -= fl.w; }
+                if (nb[s] >= cur.n1) {  // boundary face (rare)
+                    const int kind = (int)srec[2 * lf + 1].x;
+                    if (LAST && kind == K_INTERNAL)  // two-sided boundary face: the ghost row of qW holds +flux
+                        nrm += fl.x * fl.x + fl.y * fl.y + fl.z * fl.z + fl.w * fl.w;
+                    if (kind == K_SLIPWALL || kind == K_WALL) wall_ghost[s] = tt.halo[cur.off_halo + nb[s] - cur.nc];
+                }
+            }
+            const double A = sarea3[l];
+            r.x /= A; r.y /= A; r.z /= A; r.w /= A;
+            const d4 qs = sq0[l];
+            const double dti = sdt[l];
+            const double relax = prm[1];
+            d4 o;
+            o.x = qs.x + r.x * dti * alpha * relax;
+            o.y = qs.y + r.y * dti * alpha * relax;
+            o.z = qs.z + r.z * dti * alpha * relax;
+            o.w = qs.w + r.w * dti * alpha * relax;
+            qk_out[i] = o;
+            if (push.enabled && i < push.n_front) {  // halo push: straight into the peers' receive buffers over NVLink
+                const unsigned long long pr = (*push.epoch) & 1ull;
+                for (uint32_t k = push.dst_ptr[i]; k < push.dst_ptr[i + 1]; ++k) {
+                    const uint32_t d = push.dst[k], p = d >> 28, slot = d & 0x0FFFFFFFu;
+                    push.peer_buf[p][pr * push.peer_stride[p] + slot] = o;
+                }
+                __threadfence_system();
+            }
+            // wall ghosts of the next stage follow their owner; after the last stage the ghost keeps the state its owner
+            // had when the stage started (solver.h:811 ran before the update)
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+                if (wall_ghost[s] != CF_NONE) qk_out[wall_ghost[s]] = LAST ? (q0_is_in ? qs : qk_in[i]) : o;
+            if (LAST) {
+                if (prm[2] != 0.0) qW[i] = r;  // prm[2]: keep qW (only the last iteration of a run needs it)
+                nrm += r.x * r.x + r.y * r.y + r.z * r.z + r.w * r.w;
+            }
+        }
+        cur = nxt; nxt = nx2;
+    }
+    cp_async_wait<0>();
+    if (LAST) block_norm_accumulate(nrm, no);
+}
+
+// kinds of the tiles' local faces (fgeo_t.w) from the face kinds set by set_bcs
+__global__ void k_tile_face_kinds(d4* __restrict__ fgeo_t, const uint32_t* __restrict__ tile_face, const uint8_t* __restrict__ fkind, size_t n)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) fgeo_t[i].w = (double)fkind[tile_face[i]];
+}
+
+namespace launch {
+
+static int stage_threads() { return AFX_STAGE_THREADS; }
+
+static int stage_prepare(size_t smem)
+{
+    // opt in to the device maximum once: the attribute belongs to the function, not to a solver handle
+    int dev = 0, smem_max = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    cudaFuncAttributes fa0{}, fa1{};  // static shared memory (the norm reduction) counts against the same limit
+    if (cudaFuncGetAttributes(&fa0, k_stage<0>) != cudaSuccess || cudaFuncGetAttributes(&fa1, k_stage<1>) != cudaSuccess) { cudaGetLastError(); return -1; }
+    const int dyn_max = smem_max - (int)std::max(fa0.sharedSizeBytes, fa1.sharedSizeBytes);
+    if ((int)smem > dyn_max) return -1;
+    if (cudaFuncSetAttribute(k_stage<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max) != cudaSuccess) { cudaGetLastError(); return -1; }
+    if (cudaFuncSetAttribute(k_stage<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max) != cudaSuccess) { cudaGetLastError(); return -1; }
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_stage<0>, AFX_STAGE_THREADS, smem) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return nb;
+}
+
+static void stage(int last, const DevMesh& m, const TileTab& tt, unsigned grid, size_t smem, const d4* qk_in, const d4* q0, d4* qk_out,
+                  const d4* gx, const d4* gy, const double* dt, d4* qW, d4* lim, double alpha, const double* prm, double limiter_k,
+                  const GasC& g, NormOut no, const PushArgs* push_in, cudaStream_t st)
+{
+    if (!grid || !tt.n_tiles) return;
+    PushArgs push{};
+    if (push_in) push = *push_in;
+    if (no.blk_total == 0) { no.blk_off = 0; no.blk_total = grid; }
+    if (last) k_stage<1><<<grid, AFX_STAGE_THREADS, smem, st>>>(m, tt, qk_in, q0, qk_out, gx, gy, dt, qW, lim, alpha, prm, limiter_k, g, no, push);
+    else k_stage<0><<<grid, AFX_STAGE_THREADS, smem, st>>>(m, tt, qk_in, q0, qk_out, gx, gy, dt, qW, lim, alpha, prm, limiter_k, g, no, push);
+}
+
+static void tile_face_kinds(d4* fgeo_t, const uint32_t* tile_face, const uint8_t* fkind, size_t n, cudaStream_t st)
+{
+    if (n) k_tile_face_kinds<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(fgeo_t, tile_face, fkind, n);
+}
+
+}  // namespace launch
+}  // namespace AFX_NS
+}  // namespace afx

@@ -42,6 +42,47 @@ struct DevMesh {
     const uint16_t* lsq_perm;    // [N] bits 0-7: slot of local side j (2 bits each), bits 8-10: number of sides
 };
 
+// Device view of the shared-memory tiles (tiling.h): tile t owns cells [cell0, cell0+nc) and stages, with LOCAL 16-bit
+// indices, its ring-1 cells (limiter recomputed), the state-only cells around them and every face with an end in the
+// tile.  Static geometry is packed per tile so that everything but the ring cells' states arrives by bulk copies.
+struct TileTab {
+    const uint4* head;       // [n_tiles][2]: {cell0, nc, h1, h2}, {nf, off_halo, off_cell, off_face}
+    const uint32_t* halo;    // [off_halo + k]: global ids of the local cells nc.. (ring 1, then state-only cells); padded to 4
+    const uint4* ctab;       // [off_cell + l], l < nc+h1: 4 x u16 local neighbour, 4 x u16 local face | side bit (0xFFFF none)
+    const double* area_t;    // [off_cell + l]: cell areas, tile-local order (off_cell and the per-tile count are even)
+    const double2* dxy_t;    // [4*off_cell + s*n1p + l]: face centre minus cell centre of slot s (n1p = nc+h1 rounded up to even)
+    const d4* fgeo_t;        // [off_face + lf]: {nx, ny, len, kind} of the local face
+    uint32_t n_tiles;
+    uint32_t max_loc, max_n1, max_nf, max_nc, max_halo;  // shared-memory carve-up (stage_smem_layout)
+};
+
+// Shared-memory carve-up of k_stage, byte offsets; the same function sizes the launch on the host.
+struct StageSmem {
+    uint32_t sq, sgx, sgy, sdxy, sarea, sctab;   // group 1: inputs of the limiter / reconstruction phase
+    uint32_t sfg;                                // group 2: face geometry
+    uint32_t srec;                               // face states, then fluxes
+    uint32_t sq0, sdt, sarea3, sctab3;           // group 3: inputs of the gather / update phase
+    uint32_t shalo;                              // [2][max_halo] global ids of the ring cells, double buffered
+    uint32_t bars;                               // 3 mbarriers
+    uint32_t total;
+};
+__host__ __device__ inline uint32_t stage_smem_take(uint32_t& o, uint32_t bytes) { const uint32_t at = o; o += (bytes + 31u) & ~31u; return at; }
+__host__ __device__ inline StageSmem stage_smem_layout(uint32_t max_loc, uint32_t max_n1, uint32_t max_nf, uint32_t max_nc, uint32_t max_halo)
+{
+    StageSmem L;
+    uint32_t o = 0;
+    L.sq = stage_smem_take(o, 32u * max_loc); L.sgx = stage_smem_take(o, 32u * max_n1); L.sgy = stage_smem_take(o, 32u * max_n1);
+    L.sdxy = stage_smem_take(o, 64u * max_n1); L.sarea = stage_smem_take(o, 8u * max_n1); L.sctab = stage_smem_take(o, 16u * max_n1);
+    L.sfg = stage_smem_take(o, 32u * max_nf);
+    L.srec = stage_smem_take(o, 64u * max_nf);
+    L.sq0 = stage_smem_take(o, 32u * max_nc); L.sdt = stage_smem_take(o, 8u * max_nc); L.sarea3 = stage_smem_take(o, 8u * max_nc);
+    L.sctab3 = stage_smem_take(o, 16u * max_nc);
+    L.shalo = stage_smem_take(o, 8u * max_halo);
+    L.bars = stage_smem_take(o, 32u);
+    L.total = o;
+    return L;
+}
+
 struct NormOut {
     double* partial;        // [gridDim.x]
     unsigned int* counter;  // block counter
@@ -99,6 +140,13 @@ struct KernelTable {
     void (*gather)(int mode, int last, const DevMesh& m, uint32_t lo, uint32_t hi, const d4* flux, const d4* q, const d4* qk_in,
                    d4* qk_out, const double* dt, d4* vec_out, double alpha, const double* prm, int walls, NormOut no,
                    const PushArgs* push, cudaStream_t st);
+    // fused stage on shared-memory tiles: limiter + MUSCL + flux + gather + update in one persistent kernel of `grid` CTAs
+    void (*stage)(int last, const DevMesh& m, const TileTab& tt, unsigned grid, size_t smem, const d4* qk_in, const d4* q0,
+                  d4* qk_out, const d4* gx, const d4* gy, const double* dt, d4* qW, d4* lim, double alpha, const double* prm, double limiter_k,
+                  const GasC& g, NormOut no, const PushArgs* push, cudaStream_t st);
+    int (*stage_prepare)(size_t smem);  // opt in to the dynamic shared memory on the current device; resident CTAs per SM or <0
+    int (*stage_threads)();
+    void (*tile_face_kinds)(d4* fgeo_t, const uint32_t* tile_face, const uint8_t* fkind, size_t n, cudaStream_t st);  // refresh after set_bcs
     void (*halo_signal)(const SignalArgs& a, cudaStream_t st);               // tell the peers my send layer is in their buffers
     void (*halo_wait_scatter)(const WaitArgs& a, d4* field, cudaStream_t st); // wait for the peers, then fill my halo cells
     unsigned (*gather_blocks)(uint32_t n_cells);

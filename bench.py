@@ -144,6 +144,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--math", default="fast", choices=["fast", "strict"])
+    ap.add_argument("--fused", type=int, default=1, help="1: one fused kernel per RK stage on shared-memory tiles; 0: limiter / flux / gather kernels")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -192,6 +193,11 @@ def main():
         s = afx.GpuSolver(mesh, viscosity=VISC, device=local, math=a.math)
     config["math"] = a.math + (" (shared reciprocals + FMA; parity 1e-10 tested)" if a.math == "fast" else " (bit-identical to the CPU reference)")
     s.set_bcs(BCS); s.set_options(SECOND, GRAD, LIMK, CFL); s.init(); s.refill_bcs()
+    s.set_fused(a.fused)
+    tiles = s.tile_info()
+    config["stage_kernel"] = ("fused k_stage: %d tiles of <= %d cells, %d B shared memory, %d CTAs/SM, staging overhead %.2fx"
+                              % (tiles["tiles"], tiles["tile_cells"], tiles["smem_bytes"], tiles["ctas_per_sm"],
+                                 tiles["local_cells"] / max(1, (N if part is None else part.n_own)))) if tiles["fused"] else "k_limiter + k_flux + k_gather_update"
     base = np.zeros(4 * (N + G))
     s.get_q(base)  # a partitioned solver fills its own entries of the global vector
     q0 = perturbed(base, N)
@@ -234,10 +240,15 @@ def main():
     n_loc = N if part is None else part.n_own
     share = n_loc / N  # this rank's share of the cells
     # algorithmic bytes per launch (DESIGN.md section 5 / SURVEY.md 8d), launches per iteration, phase time per iteration
-    kernels = {"k_flux": ((144.0 * N + 48.0 * E) * share, 3, prof["flux"]),
-               "k_limiter": ((152.0 * N + 24.0 * E) * share, 3, prof["limiter"]),
-               "k_gather_update": ((144.0 * N + 32.0 * E) * share, 3, prof["gather_update"]),
-               "k_dt_grad": ((168.0 * N + 80.0 * E) * share, 1, prof["dt_grad"])}
+    if tiles["fused"]:
+        # one stage = limiter (152N+24E) + residual loop (184N+48E) + stage update (104N), SURVEY.md 8d
+        kernels = {"k_stage": ((440.0 * N + 72.0 * E) * share, 3, prof["stage"]),
+                   "k_dt_grad": ((168.0 * N + 80.0 * E) * share, 1, prof["dt_grad"])}
+    else:
+        kernels = {"k_flux": ((144.0 * N + 48.0 * E) * share, 3, prof["flux"]),
+                   "k_limiter": ((152.0 * N + 24.0 * E) * share, 3, prof["limiter"]),
+                   "k_gather_update": ((144.0 * N + 32.0 * E) * share, 3, prof["gather_update"]),
+                   "k_dt_grad": ((168.0 * N + 80.0 * E) * share, 1, prof["dt_grad"])}
     alg_iter = (1488.0 * N + 296.0 * E) * share
     peaks = {}
     try:

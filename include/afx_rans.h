@@ -173,6 +173,14 @@ int afx_rans_set_options(afx_rans* s, int second_order, int gradient_scheme, dou
 /* arithmetic mode (AFX_MATH_*); the environment variable AFX_MATH=strict|fast sets the default at creation */
 int afx_rans_set_math_mode(afx_rans* s, int mode);
 int afx_rans_get_math_mode(afx_rans* s);
+/* Stage kernels of the explicit iteration: 1 (default; AFX_FUSED=0 at creation turns it off) = ONE kernel per
+ * Runge-Kutta stage on shared-memory tiles (limiter + MUSCL + flux + gather + update; second-order non-laminar runs),
+ * 0 = limiter / face flux / gather+update as three kernels.  Strict-mode states are bit-identical either way. */
+int afx_rans_set_fused(afx_rans* s, int on);
+/* out[0] = 1 if the fused stage kernel is in use, out[1] = tiles, out[2] = cells per tile, out[3] = dynamic shared
+ * memory per CTA (bytes), out[4] = resident CTAs per SM, out[5] = largest local cell count, out[6] = largest local
+ * face count, out[7] = total local cells of all tiles (own + ring 1 + state-only; / n_cells = staging overhead) */
+int afx_rans_tile_info(afx_rans* s, uint64_t out[8]);
 /* solver::set_cfl (solver.h:250-252) */
 int afx_rans_set_cfl(afx_rans* s, double cfl);
 /* solver::init / refill_bcs / bcs_from_internal (solver.h:615-631, 259-287) */
@@ -236,8 +244,8 @@ int afx_rans_last_device_ms(afx_rans* s, double* ms);
 int64_t afx_rans_launch_count(afx_rans* s);
 /* per-phase device milliseconds of one explicit iteration, timed with CUDA events between the phases:
  * out[0]=dt+gradients, out[1]=limiter (3 stages), out[2]=face flux (3 stages), out[3]=gather+update (3 stages),
- * out[4]=halo exchange (3 stages; 0 on one GPU) */
-int afx_rans_profile_explicit(afx_rans* s, double relaxation, int n_iter, double out_ms[5]);
+ * out[4]=halo exchange (3 stages; 0 on one GPU), out[5]=fused stage kernel (3 stages; then out[1..3] are 0) */
+int afx_rans_profile_explicit(afx_rans* s, double relaxation, int n_iter, double out_ms[6]);
 
 #ifdef __cplusplus
 }
