@@ -32,10 +32,10 @@ namespace AFX_NS {
 __device__ __forceinline__ double spectral_radius(const d4& q, double nx, double ny, double gam)
 {
 #if AFX_FAST
-    const double r = 1.0 / q.x;
+    const double r = fast_rcp(q.x);
     const double V = (q.y * nx + q.z * ny) * r;
     const double p = (gam - 1) * (q.w - 0.5 * r * (q.y * q.y + q.z * q.z));
-    return sqrt(p * gam * r) + fabs(V);
+    return fast_sqrt(p * gam * r) + fabs(V);
 #else
     const double V = (q.y * nx + q.z * ny) / q.x;
     const double p = (gam - 1) * (q.w - 0.5 / q.x * (q.y * q.y + q.z * q.z));
@@ -101,8 +101,14 @@ __global__ void __launch_bounds__(256, 3) k_dt_grad(DevMesh m, d4* __restrict__ 
     dt[i] = prm[0] * A / dsum;  // prm[0] = cfl
     if (!want_grad) return;
     if (GRAD == 0) {
+#if AFX_FAST
+        const double rA = fast_rcp(A);
+        ax.x *= rA; ax.y *= rA; ax.z *= rA; ax.w *= rA;
+        ay.x *= rA; ay.y *= rA; ay.z *= rA; ay.w *= rA;
+#else
         ax.x /= A; ax.y /= A; ax.z /= A; ax.w /= A;
         ay.x /= A; ay.y /= A; ay.z /= A; ay.w /= A;
+#endif
     } else {  // least squares, rows in cellsEdges order, solver.h:471-508
         const uint32_t perm = m.lsq_perm[i];  // bits 0-7: slot of local side j (2 bits each); bits 8-10: number of sides
         const int nside = (int)(perm >> 8);
@@ -135,13 +141,6 @@ __global__ void __launch_bounds__(256, 3) k_dt_grad(DevMesh m, d4* __restrict__ 
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ double venkat(double dqg, double dmax, double dmin, double K3a)
 {
-#if AFX_FAST
-    // one division: the reference's 1/dqg * num / den with the common factor dqg cancelled analytically
-    const double dm = dqg > 0 ? dmax : dmin;
-    const double num = dm * dm + K3a + 2 * dqg * dm;
-    const double den = dm * dm + 2 * dqg * dqg + dm * dqg + K3a;
-    return (dqg > 1e-16 || dqg < -1e-16) ? num / den : 1.0;
-#endif
     if (dqg > 1e-16)
         return 1 / dqg * ((dmax * dmax + K3a) * dqg + 2 * dqg * dqg * dmax) / (dmax * dmax + 2 * dqg * dqg + dmax * dqg + K3a);
     if (dqg < -1e-16)
@@ -149,20 +148,39 @@ __device__ __forceinline__ double venkat(double dqg, double dmax, double dmin, d
     return 1.0;
 }
 
+// K^3 a of the Venkatakrishnan function, solver.h:551-552
+__device__ __forceinline__ double limiter_k3a(double area, double limiter_k)
+{
+    const double Ka = limiter_k * sqrt(area);
+    return Ka * Ka * Ka;
+}
+
+#if AFX_FAST
+// min(1, phi(pmax), phi(pmin)) with ONE reciprocal: both denominators are positive (dm and the increment have the same
+// sign), so the smaller fraction is found by cross-multiplying
+__device__ __forceinline__ double venkat_pair(double pmax, double pmin, double dmax, double dmin, double K3a)
+{
+    double n1 = 1.0, d1 = 1.0, n2 = 1.0, d2 = 1.0;
+    if (pmax > 1e-16) { n1 = dmax * dmax + K3a + 2 * pmax * dmax; d1 = dmax * dmax + 2 * pmax * pmax + dmax * pmax + K3a; }
+    if (pmin < -1e-16) { n2 = dmin * dmin + K3a + 2 * pmin * dmin; d2 = dmin * dmin + 2 * pmin * pmin + dmin * pmin + K3a; }
+    const bool first = n1 * d2 < n2 * d1;
+    const double n = first ? n1 : n2, d = first ? d1 : d2;
+    return n >= d ? 1.0 : n * fast_rcp(d);
+}
+#endif
+
 // limiter of one cell from its state, the min/max over its neighbours, its gradient and the face offsets of its slots
 // (solver.h:538-592); `valid` bit s = slot s holds a face.  Shared by k_limiter and the fused k_stage.
 __device__ __forceinline__ d4 limiter_value(const d4& qi, const d4& lo, const d4& hi, const d4& gxi, const d4& gyi, const double2 (&dxy)[4],
-                                            unsigned valid, double area, double limiter_k)
+                                            unsigned valid, double K3a)
 {
-    const double Ka = limiter_k * sqrt(area);
-    const double K3a = Ka * Ka * Ka;
     const d4 dmax = mk4(hi.x - qi.x, hi.y - qi.y, hi.z - qi.z, hi.w - qi.w);
     const d4 dmin = mk4(lo.x - qi.x, lo.y - qi.y, lo.z - qi.z, lo.w - qi.w);
     d4 l = mk4(1, 1, 1, 1);
 #if AFX_FAST
     // Where the limiter function is below 1 it decreases monotonically with |dqg| (d phi/d dqg < 0 for dqg > dm/2), and
     // values above 1 never survive the min with 1: the minimum over the faces is attained at the largest positive and
-    // the most negative projected increment -> 2 evaluations per component instead of one per face.
+    // the most negative projected increment -> one pair of evaluations per component instead of one per face.
     d4 pmax = mk4(0, 0, 0, 0), pmin = mk4(0, 0, 0, 0);
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
@@ -172,10 +190,10 @@ __device__ __forceinline__ d4 limiter_value(const d4& qi, const d4& lo, const d4
         pmax.x = fmax(pmax.x, p0); pmax.y = fmax(pmax.y, p1); pmax.z = fmax(pmax.z, p2); pmax.w = fmax(pmax.w, p3);
         pmin.x = fmin(pmin.x, p0); pmin.y = fmin(pmin.y, p1); pmin.z = fmin(pmin.z, p2); pmin.w = fmin(pmin.w, p3);
     }
-    l.x = fmin(fmin(1.0, venkat(pmax.x, dmax.x, dmin.x, K3a)), venkat(pmin.x, dmax.x, dmin.x, K3a));
-    l.y = fmin(fmin(1.0, venkat(pmax.y, dmax.y, dmin.y, K3a)), venkat(pmin.y, dmax.y, dmin.y, K3a));
-    l.z = fmin(fmin(1.0, venkat(pmax.z, dmax.z, dmin.z, K3a)), venkat(pmin.z, dmax.z, dmin.z, K3a));
-    l.w = fmin(fmin(1.0, venkat(pmax.w, dmax.w, dmin.w, K3a)), venkat(pmin.w, dmax.w, dmin.w, K3a));
+    l.x = venkat_pair(pmax.x, pmin.x, dmax.x, dmin.x, K3a);
+    l.y = venkat_pair(pmax.y, pmin.y, dmax.y, dmin.y, K3a);
+    l.z = venkat_pair(pmax.z, pmin.z, dmax.z, dmin.z, K3a);
+    l.w = venkat_pair(pmax.w, pmin.w, dmax.w, dmin.w, K3a);
 #else
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
@@ -223,7 +241,7 @@ __global__ void __launch_bounds__(256, AFX_LIM_MINB) k_limiter(DevMesh m, const 
         lo.x = fmin(lo.x, qj.x); lo.y = fmin(lo.y, qj.y); lo.z = fmin(lo.z, qj.z); lo.w = fmin(lo.w, qj.w);
         hi.x = fmax(hi.x, qj.x); hi.y = fmax(hi.y, qj.y); hi.z = fmax(hi.z, qj.z); hi.w = fmax(hi.w, qj.w);
     }
-    lim[i] = limiter_value(qi, lo, hi, gx[i], gy[i], dxy, valid, m.area[i], limiter_k);
+    lim[i] = limiter_value(qi, lo, hi, gx[i], gy[i], dxy, valid, limiter_k3a(m.area[i], limiter_k));
 }
 
 // ---------------------------------------------------------------------------
@@ -359,7 +377,12 @@ __global__ void __launch_bounds__(256) k_gather_update(DevMesh m, const d4* __re
         }
         if (MODE == 0) {
             const double A = m.area[i];
+#if AFX_FAST
+            const double rA = fast_rcp(A);
+            r.x *= rA; r.y *= rA; r.z *= rA; r.w *= rA;
+#else
             r.x /= A; r.y /= A; r.z /= A; r.w /= A;
+#endif
             const d4 q0 = q[i];
             const double dti = dt[i];
             d4 o;

@@ -38,11 +38,41 @@ __device__ __forceinline__ double sabs(double x) { return sqrt(x * x + 1e-4); }
 __device__ __forceinline__ double entropy_fix(double l, double d) { return l > d ? l : (l * l + d * d) / (2 * d); }
 
 #if AFX_FAST
-// Roe flux, physics.h:180-228, with 4 divisions (1/rhoL, 1/rhoR, 1/(sL+sR), 1/c^2) instead of 19
+// Fast-mode reciprocal / square roots: the 20-bit hardware seed (MUFU.RCP64H / MUFU.RSQ64H) plus two Newton steps in
+// FMA arithmetic, ~1-2 ulp for normal positive arguments, no special-case branch (the states here are densities,
+// sound speeds and positive denominators).  The IEEE division / sqrt sequences of strict mode cost 3-4x as many
+// instructions, most of them integer fix-up.
+__device__ __forceinline__ double fast_rcp(double a)
+{
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
+    double e = fma(-a, x, 1.0); x = fma(x, e, x);
+    e = fma(-a, x, 1.0); x = fma(x, e, x);
+    return x;
+}
+__device__ __forceinline__ double fast_rsqrt(double a)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    double e = fma(-(a * y), y, 1.0); y = fma(0.5 * y, e, y);
+    e = fma(-(a * y), y, 1.0); y = fma(0.5 * y, e, y);
+    return y;
+}
+__device__ __forceinline__ double fast_sqrt(double a)
+{
+    const double y = fast_rsqrt(a);
+    const double g = a * y;
+    return fma(0.5 * y, fma(-g, g, a), g);  // one more correction of the product
+}
+__device__ __forceinline__ double sabs_fast(double x) { return fast_sqrt(fma(x, x, 1e-4)); }
+
+// Roe flux, physics.h:180-228: one reciprocal square root per density gives 1/rho and sqrt(rho), one for c^2 gives c
+// and 1/c^2; one reciprocal for 1/(sL+sR) -- instead of the reference's 19 divisions and 6 square roots
 __device__ __forceinline__ d4 roe_flux(const d4& qL, const d4& qR, double nx, double ny, double gam)
 {
     const double gm1 = gam - 1;
-    const double rL = 1.0 / qL.x, rR = 1.0 / qR.x;
+    const double yL = fast_rsqrt(qL.x), yR = fast_rsqrt(qR.x);
+    const double rL = yL * yL, rR = yR * yR;
     const double uL = qL.y * rL, vL = qL.z * rL, uR = qR.y * rR, vR = qR.z * rR;
     const double VL = uL * nx + vL * ny, VR = uR * nx + vR * ny;
     const double pL = gm1 * (qL.w - 0.5 * (qL.y * uL + qL.z * vL));
@@ -53,20 +83,21 @@ __device__ __forceinline__ d4 roe_flux(const d4& qL, const d4& qR, double nx, do
     f.z = (VL * qL.z + VR * qR.z + (pL + pR) * ny) * 0.5;
     f.w = (VL * (qL.w + pL) + VR * (qR.w + pR)) * 0.5;
 
-    const double sL = sqrt(qL.x), sR = sqrt(qR.x);
+    const double sL = qL.x * yL, sR = qR.x * yR;
     const double rho = sR * sL;
-    const double rs = 1.0 / (sL + sR);
+    const double rs = fast_rcp(sL + sR);
     const double wL = sL * rs, wR = sR * rs;
     const double u = uL * wL + uR * wR;
     const double v = vL * wL + vR * wR;
     const double h = (qL.w + pL) * rL * wL + (qR.w + pR) * rR * wR;
     const double q2 = u * u + v * v;
     const double c2 = gm1 * (h - 0.5 * q2);
-    const double c = sqrt(c2);
-    const double rc2 = 1.0 / c2;
+    const double yc = fast_rsqrt(c2);
+    const double c = c2 * yc;
+    const double rc2 = yc * yc;
     const double V = u * nx + v * ny;
-    const double d = 0.05 * c, hd = 10.0 * c * rc2;  // 1/(2d) = 10/c
-    const double a_cm = sabs(V - c), a_c = sabs(V), a_cp = sabs(V + c);
+    const double d = 0.05 * c, hd = 10.0 * yc;  // 1/(2d) = 10/c
+    const double a_cm = sabs_fast(V - c), a_c = sabs_fast(V), a_cp = sabs_fast(V + c);
     const double l_cm = a_cm > d ? a_cm : (a_cm * a_cm + d * d) * hd;
     const double l_c = a_c > d ? a_c : (a_c * a_c + d * d) * hd;
     const double l_cp = a_cp > d ? a_cp : (a_cp * a_cp + d * d) * hd;

@@ -147,10 +147,12 @@ struct Solver {
     DBuf<uint2> fcells; DBuf<d4> fgA, fgB, ftij; DBuf<uint8_t> fkind; DBuf<uint32_t> cf, cnb; DBuf<double2> cdxy; DBuf<double> area;
     DBuf<double> lsqM; DBuf<uint16_t> lsq_perm;
     // shared-memory tiles of the fused stage kernel (tiling.h)
-    DBuf<uint4> t_head, t_ctab; DBuf<uint32_t> t_halo, t_face; DBuf<double> t_area; DBuf<double2> t_dxy; DBuf<d4> t_fgeo;
+    DBuf<uint4> t_head, t_ctab; DBuf<uint32_t> t_halo, t_face; DBuf<double> t_area, t_k3a; DBuf<double2> t_dxy; DBuf<d4> t_fgeo;
     TileTab tt{};
     uint32_t n_tiles = 0, tile_cells = 0;
-    size_t stage_smem = 0, n_tile_faces = 0;
+    size_t stage_smem = 0, n_tile_faces = 0, n_tile_cells = 0;
+    double k3a_for = -1;  // limiter_k the tiles' K^3 a table was computed for
+    void refresh_tile_k3a();
     int stage_ctas_per_sm = 0;
     unsigned stage_grid = 0;
     bool tiles_ready = false, use_fused = true;
@@ -608,6 +610,7 @@ void Solver::build_tile_tables(const std::vector<uint32_t>& h_cf, const std::vec
     tile_cells = T; n_tiles = (uint32_t)plan.head.size(); stage_smem = L.total; tile_local_cells = plan.local_cells;
     // static geometry packed per tile: face offsets and areas of the own + ring-1 cells, normals / lengths of the local faces
     const size_t n_cell_rec = plan.ctab.size();
+    n_tile_cells = n_cell_rec;
     n_tile_faces = plan.face.size();
     std::vector<double> h_ta(n_cell_rec, 1.0);
     std::vector<double2> h_td(4 * n_cell_rec, make_double2(0., 0.));
@@ -632,8 +635,9 @@ void Solver::build_tile_tables(const std::vector<uint32_t>& h_cf, const std::vec
         if (!host.empty()) CK(cudaMemcpyAsync(dbuf.p, host.data(), host.size() * sizeof(host[0]), cudaMemcpyHostToDevice, st));
     };
     up(t_head, plan.head); up(t_halo, plan.halo); up(t_ctab, plan.ctab); up(t_face, plan.face); up(t_area, h_ta); up(t_dxy, h_td); up(t_fgeo, h_tf);
+    t_k3a.alloc(std::max<size_t>(1, n_cell_rec));
     CK(cudaStreamSynchronize(st));
-    tt = TileTab{t_head.p, t_halo.p, t_ctab.p, t_area.p, t_dxy.p, t_fgeo.p, n_tiles, plan.max_loc, plan.max_n1, plan.max_nf, plan.max_nc, plan.max_halo};
+    tt = TileTab{t_head.p, t_halo.p, t_ctab.p, t_k3a.p, t_dxy.p, t_fgeo.p, n_tiles, plan.max_loc, plan.max_n1, plan.max_nf, plan.max_nc, plan.max_halo};
     const int a = strict::table().stage_prepare(stage_smem), b = fast::table().stage_prepare(stage_smem);
     if (a < 1 || b < 1) return;  // the kernel does not fit: three-kernel stage
     stage_ctas_per_sm = std::min(a, b);
@@ -643,12 +647,22 @@ void Solver::build_tile_tables(const std::vector<uint32_t>& h_cf, const std::vec
     tiles_ready = true;
 }
 
+// the tiles' K^3 a table follows limiter_k; always computed by the strict kernels (IEEE sqrt, no contraction)
+void Solver::refresh_tile_k3a()
+{
+    if (!tiles_ready || k3a_for == limiter_k) return;
+    strict::table().tile_k3a(t_area.p, t_k3a.p, n_tile_cells, limiter_k, st);
+    ++launches;
+    CK(cudaStreamSynchronize(st));
+    k3a_for = limiter_k;
+}
+
 // One fused stage: limiter + MUSCL + flux + gather + update on shared-memory tiles, then the halo hand-off.
 void Solver::launch_stage(int s, const d4* qk_in, d4* qk_out, double alpha)
 {
     ensure_halo();
     const PushArgs* push = (halo && halo->p2p) ? &halo->push : nullptr;
-    kt->stage(s == 2, dm, tt, stage_grid, stage_smem, qk_in, q.p, qk_out, gx.p, gy.p, dt.p, qW.p, lim.p, alpha, prm.p, limiter_k, gas, norm_out(), push, st);
+    kt->stage(s == 2, dm, tt, stage_grid, stage_smem, qk_in, q.p, qk_out, gx.p, gy.p, dt.p, qW.p, lim.p, alpha, prm.p, gas, norm_out(), push, st);
     ++launches;
     if (!halo) return;
     if (halo->p2p) {  // the kernel stored the send layer into the peers' buffers: flags, then fill our halo cells
@@ -835,6 +849,7 @@ void Solver::run_explicit(double relax, int n_iter, double* norms_out)
     if (!bcs_set) throw InvalidArg("set_bcs has not been called");
     if (n_iter <= 0) return;
     push_params(relax, n_iter == 1);  // qW is kept for the last iteration of the call only
+    refresh_tile_k3a();
     h_pinned[35] = 1.0;               // constant source of the "keep qW" flag, never rewritten
     CK(cudaEventRecord(ev0, st));
     int done = 0;
@@ -1586,6 +1601,7 @@ int afx_rans_profile_explicit(afx_rans* s, double relaxation, int n_iter, double
         S.use();
         if (!S.bcs_set) throw afx::InvalidArg("set_bcs has not been called");
         S.push_params(relaxation);
+        S.refresh_tile_k3a();
         for (int k = 0; k < 6; ++k) out_ms[k] = 0;
         const bool grads = S.visc_not_inviscid || S.second_order;
         const bool fused = S.fused_stage();

@@ -89,7 +89,7 @@ template <int LAST>
 __global__ void __launch_bounds__(AFX_STAGE_THREADS, AFX_STAGE_MINB)
 k_stage(DevMesh m, TileTab tt, const d4* __restrict__ qk_in, const d4* q0, d4* qk_out, const d4* __restrict__ gx,
         const d4* __restrict__ gy, const double* __restrict__ dt, d4* __restrict__ qW, d4* __restrict__ lim, double alpha,
-        const double* __restrict__ prm, double limiter_k, GasC g, NormOut no, PushArgs push)
+        const double* __restrict__ prm, GasC g, NormOut no, PushArgs push)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const StageSmem L = stage_smem_layout(tt.max_loc, tt.max_n1, tt.max_nf, tt.max_nc, tt.max_halo);
@@ -97,7 +97,7 @@ k_stage(DevMesh m, TileTab tt, const d4* __restrict__ qk_in, const d4* q0, d4* q
     d4* const sgx = reinterpret_cast<d4*>(smem + L.sgx);
     d4* const sgy = reinterpret_cast<d4*>(smem + L.sgy);
     double2* const sdxy = reinterpret_cast<double2*>(smem + L.sdxy);
-    double* const sarea = reinterpret_cast<double*>(smem + L.sarea);
+    double* const sk3a = reinterpret_cast<double*>(smem + L.sarea);
     uint4* const sctab = reinterpret_cast<uint4*>(smem + L.sctab);
     d4* const sfg = reinterpret_cast<d4*>(smem + L.sfg);
     d4* const srec = reinterpret_cast<d4*>(smem + L.srec);
@@ -124,7 +124,7 @@ k_stage(DevMesh m, TileTab tt, const d4* __restrict__ qk_in, const d4* q0, d4* q
             bulk_g2s(smem_u32(sgx), gx + v.cell0, 32u * v.nc, bar1);
             bulk_g2s(smem_u32(sgy), gy + v.cell0, 32u * v.nc, bar1);
             bulk_g2s(smem_u32(sdxy), tt.dxy_t + 4 * (size_t)v.off_cell, 64u * v.n1p, bar1);
-            bulk_g2s(smem_u32(sarea), tt.area_t + v.off_cell, 8u * v.n1p, bar1);
+            bulk_g2s(smem_u32(sk3a), tt.k3a_t + v.off_cell, 8u * v.n1p, bar1);
             bulk_g2s(smem_u32(sctab), tt.ctab + v.off_cell, 16u * v.n1p, bar1);
             if (has_next && nx.nhp) bulk_g2s(smem_u32(shalo + (buf ^ 1u) * tt.max_halo), tt.halo + nx.off_halo, 4u * nx.nhp, bar1);
         }
@@ -153,7 +153,10 @@ k_stage(DevMesh m, TileTab tt, const d4* __restrict__ qk_in, const d4* q0, d4* q
             mbar_expect_tx(bar3, 32u * v.nc);
             bulk_g2s(smem_u32(sq0), q0 + v.cell0, 32u * v.nc, bar3);
         }
-        for (uint32_t l = tid; l < v.nc; l += AFX_STAGE_THREADS) cp_async8(smem_u32(sdt + l), dt + v.cell0 + l);
+        for (uint32_t l = tid; l < v.nc; l += AFX_STAGE_THREADS) {
+            cp_async8(smem_u32(sdt + l), dt + v.cell0 + l);
+            cp_async8(smem_u32(sarea3 + l), m.area + v.cell0 + l);
+        }
         cp_async_commit();
     };
 
@@ -190,7 +193,7 @@ k_stage(DevMesh m, TileTab tt, const d4* __restrict__ qk_in, const d4* q0, d4* q
 #pragma unroll
             for (int s = 0; s < 4; ++s) dxy[s] = sdxy[s * cur.n1p + l];
             const d4 gxi = sgx[l], gyi = sgy[l];
-            const double area = sarea[l];
+            const double K3a = sk3a[l];
             const d4 qi = sq[l];
             d4 lo = qi, hi = qi;
             unsigned valid = 0;
@@ -205,9 +208,9 @@ k_stage(DevMesh m, TileTab tt, const d4* __restrict__ qk_in, const d4* q0, d4* q
                 // limiter 1, so its face state is its state
                 if (nb[s] >= cur.n1 && fs[s] != 0xFFFFu) srec[2 * (fs[s] & 0x7FFFu) + 1] = qj;
             }
-            const d4 lm = limiter_value(qi, lo, hi, gxi, gyi, dxy, valid, area, limiter_k);
+            const d4 lm = limiter_value(qi, lo, hi, gxi, gyi, dxy, valid, K3a);
             if (l < cur.nc) {  // what P3 needs after group 1 has been overwritten by the next tile
-                sarea3[l] = area; sctab3[l] = tc;
+                sctab3[l] = tc;
                 if (q0_is_in) sq0[l] = qi;
                 if (LAST && prm[2] != 0.0) lim[cur.cell0 + l] = lm;  // kept, like qW, for the last iteration of a run only
             }
@@ -264,7 +267,12 @@ k_stage(DevMesh m, TileTab tt, const d4* __restrict__ qk_in, const d4* q0, d4* q
                 }
             }
             const double A = sarea3[l];
+#if AFX_FAST
+            const double rA = fast_rcp(A);
+            r.x *= rA; r.y *= rA; r.z *= rA; r.w *= rA;
+#else
             r.x /= A; r.y /= A; r.z /= A; r.w /= A;
+#endif
             const d4 qs = sq0[l];
             const double dti = sdt[l];
             const double relax = prm[1];
@@ -298,6 +306,13 @@ k_stage(DevMesh m, TileTab tt, const d4* __restrict__ qk_in, const d4* q0, d4* q
     if (LAST) block_norm_accumulate(nrm, no);
 }
 
+// K^3 a of every tile-local cell record from its area (solver.h:551-552); run when limiter_k changes
+__global__ void k_tile_k3a(const double* __restrict__ area_t, double* __restrict__ k3a_t, size_t n, double limiter_k)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) k3a_t[i] = limiter_k3a(area_t[i], limiter_k);
+}
+
 // kinds of the tiles' local faces (fgeo_t.w) from the face kinds set by set_bcs
 __global__ void k_tile_face_kinds(d4* __restrict__ fgeo_t, const uint32_t* __restrict__ tile_face, const uint8_t* __restrict__ fkind, size_t n)
 {
@@ -329,15 +344,20 @@ static int stage_prepare(size_t smem)
 }
 
 static void stage(int last, const DevMesh& m, const TileTab& tt, unsigned grid, size_t smem, const d4* qk_in, const d4* q0, d4* qk_out,
-                  const d4* gx, const d4* gy, const double* dt, d4* qW, d4* lim, double alpha, const double* prm, double limiter_k,
+                  const d4* gx, const d4* gy, const double* dt, d4* qW, d4* lim, double alpha, const double* prm,
                   const GasC& g, NormOut no, const PushArgs* push_in, cudaStream_t st)
 {
     if (!grid || !tt.n_tiles) return;
     PushArgs push{};
     if (push_in) push = *push_in;
     if (no.blk_total == 0) { no.blk_off = 0; no.blk_total = grid; }
-    if (last) k_stage<1><<<grid, AFX_STAGE_THREADS, smem, st>>>(m, tt, qk_in, q0, qk_out, gx, gy, dt, qW, lim, alpha, prm, limiter_k, g, no, push);
-    else k_stage<0><<<grid, AFX_STAGE_THREADS, smem, st>>>(m, tt, qk_in, q0, qk_out, gx, gy, dt, qW, lim, alpha, prm, limiter_k, g, no, push);
+    if (last) k_stage<1><<<grid, AFX_STAGE_THREADS, smem, st>>>(m, tt, qk_in, q0, qk_out, gx, gy, dt, qW, lim, alpha, prm, g, no, push);
+    else k_stage<0><<<grid, AFX_STAGE_THREADS, smem, st>>>(m, tt, qk_in, q0, qk_out, gx, gy, dt, qW, lim, alpha, prm, g, no, push);
+}
+
+static void tile_k3a(const double* area_t, double* k3a_t, size_t n, double limiter_k, cudaStream_t st)
+{
+    if (n) k_tile_k3a<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(area_t, k3a_t, n, limiter_k);
 }
 
 static void tile_face_kinds(d4* fgeo_t, const uint32_t* tile_face, const uint8_t* fkind, size_t n, cudaStream_t st)

@@ -49,7 +49,7 @@ struct TileTab {
     const uint4* head;       // [n_tiles][2]: {cell0, nc, h1, h2}, {nf, off_halo, off_cell, off_face}
     const uint32_t* halo;    // [off_halo + k]: global ids of the local cells nc.. (ring 1, then state-only cells); padded to 4
     const uint4* ctab;       // [off_cell + l], l < nc+h1: 4 x u16 local neighbour, 4 x u16 local face | side bit (0xFFFF none)
-    const double* area_t;    // [off_cell + l]: cell areas, tile-local order (off_cell and the per-tile count are even)
+    const double* k3a_t;     // [off_cell + l]: (limiter_k sqrt(area))^3 of the cell, tile-local order (off_cell and the per-tile count are even)
     const double2* dxy_t;    // [4*off_cell + s*n1p + l]: face centre minus cell centre of slot s (n1p = nc+h1 rounded up to even)
     const d4* fgeo_t;        // [off_face + lf]: {nx, ny, len, kind} of the local face
     uint32_t n_tiles;
@@ -142,10 +142,11 @@ struct KernelTable {
                    const PushArgs* push, cudaStream_t st);
     // fused stage on shared-memory tiles: limiter + MUSCL + flux + gather + update in one persistent kernel of `grid` CTAs
     void (*stage)(int last, const DevMesh& m, const TileTab& tt, unsigned grid, size_t smem, const d4* qk_in, const d4* q0,
-                  d4* qk_out, const d4* gx, const d4* gy, const double* dt, d4* qW, d4* lim, double alpha, const double* prm, double limiter_k,
+                  d4* qk_out, const d4* gx, const d4* gy, const double* dt, d4* qW, d4* lim, double alpha, const double* prm,
                   const GasC& g, NormOut no, const PushArgs* push, cudaStream_t st);
     int (*stage_prepare)(size_t smem);  // opt in to the dynamic shared memory on the current device; resident CTAs per SM or <0
     int (*stage_threads)();
+    void (*tile_k3a)(const double* area_t, double* k3a_t, size_t n, double limiter_k, cudaStream_t st);  // refresh after set_options
     void (*tile_face_kinds)(d4* fgeo_t, const uint32_t* tile_face, const uint8_t* fkind, size_t n, cudaStream_t st);  // refresh after set_bcs
     void (*halo_signal)(const SignalArgs& a, cudaStream_t st);               // tell the peers my send layer is in their buffers
     void (*halo_wait_scatter)(const WaitArgs& a, d4* field, cudaStream_t st); // wait for the peers, then fill my halo cells
