@@ -50,4 +50,92 @@ std::vector<uint32_t> hilbert_order(const double* x, const double* y, const std:
     return out;
 }
 
+namespace {
+
+struct Bisector {
+    const uint32_t* nb;
+    std::vector<uint32_t>& cells;
+    std::vector<uint32_t> label;              // subset / visit marks, one fresh id per use
+    uint32_t next_id = 1;
+    uint32_t T;
+    std::vector<std::pair<uint32_t, uint32_t>> leaves;  // (start, size)
+
+    uint32_t fresh()
+    {
+        uint32_t v;
+#pragma omp atomic capture
+        v = next_id++;
+        return v;
+    }
+    // breadth-first order of cells[lo,hi) (all labelled `in`) from `start`, relabelled `out`; components not reached
+    // from `start` follow, each from its first cell in array order.  Returns the last cell of the FIRST component.
+    uint32_t bfs(uint32_t lo, uint32_t hi, uint32_t start, uint32_t in, uint32_t out, std::vector<uint32_t>& ord)
+    {
+        ord.clear();
+        uint32_t last_first = start, scan = lo;
+        bool first = true;
+        for (uint32_t seed = start;;) {
+            size_t head = ord.size();
+            label[seed] = out; ord.push_back(seed);
+            while (head < ord.size()) {
+                const uint32_t c = ord[head++];
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t j = nb[4 * (size_t)c + k];
+                    if (j != 0xFFFFFFFFu && label[j] == in) { label[j] = out; ord.push_back(j); }
+                }
+            }
+            if (first) { last_first = ord.back(); first = false; }
+            if (ord.size() == hi - lo) break;
+            while (label[cells[scan]] != in) ++scan;
+            seed = cells[scan];
+        }
+        return last_first;
+    }
+    void split(uint32_t lo, uint32_t hi, uint32_t k)
+    {
+        const uint32_t n = hi - lo;
+        std::vector<uint32_t> ord;
+        ord.reserve(n);
+        const uint32_t a = fresh(), b = fresh(), c = fresh();
+        for (uint32_t i = lo; i < hi; ++i) label[cells[i]] = a;
+        uint32_t far = bfs(lo, hi, cells[lo], a, b, ord);
+        if (k > 1) {  // a second sweep from the far end: a better pseudo-peripheral start, levels along the long axis
+            const uint32_t d = fresh();
+            far = bfs(lo, hi, far, b, d, ord);
+            bfs(lo, hi, far, d, c, ord);
+        }
+        std::copy(ord.begin(), ord.end(), cells.begin() + lo);
+        if (k == 1) {
+#pragma omp critical(afx_bisect_leaves)
+            leaves.emplace_back(lo, n);
+            return;
+        }
+        const uint32_t kl = k / 2;
+        const uint32_t nl = (uint32_t)((uint64_t)n * kl / k);
+        std::vector<uint32_t>().swap(ord);
+#pragma omp task default(shared) if (n > 65536)
+        split(lo, lo + nl, kl);
+#pragma omp task default(shared) if (n > 65536)
+        split(lo + nl, hi, k - kl);
+#pragma omp taskwait
+    }
+};
+
+}  // namespace
+
+std::vector<uint32_t> graph_tile_order(uint32_t n_total, const uint32_t* nb, std::vector<uint32_t> cells, uint32_t tile_cells,
+                                       std::vector<uint32_t>& tile_sizes)
+{
+    if (cells.empty()) return cells;
+    Bisector B{nb, cells, std::vector<uint32_t>(n_total, 0u), 1u, tile_cells, {}};
+    const uint32_t n = (uint32_t)cells.size();
+    const uint32_t k = (n + tile_cells - 1) / tile_cells;
+#pragma omp parallel
+#pragma omp single
+    B.split(0, n, k);
+    std::sort(B.leaves.begin(), B.leaves.end());
+    for (const auto& l : B.leaves) tile_sizes.push_back(l.second);
+    return cells;
+}
+
 }  // namespace afx

@@ -28,18 +28,33 @@
 namespace afx {
 namespace AFX_NS {
 
-// spectral radius c + |V.n| of one state, solver.h:329-336
-__device__ __forceinline__ double spectral_radius(const d4& q, double nx, double ny, double gam)
+// spectral radius c + |V.n| of one state, solver.h:329-336, split into the part that belongs to the cell -- the speed
+// of sound, one square root (and in strict mode the division 0.5/rho) -- and the part that belongs to the face.  The
+// split evaluates exactly the reference's expressions, so the sum is bit-identical to computing both per face.
+struct CellSound {
+    double c;   // sqrt(gamma p / rho)
+    double r;   // fast mode: 1/rho, shared with the normal velocity
+};
+__device__ __forceinline__ CellSound cell_sound(const d4& q, double gam)
+{
+    CellSound s;
+#if AFX_FAST
+    s.r = fast_rcp(q.x);
+    const double p = (gam - 1) * (q.w - 0.5 * s.r * (q.y * q.y + q.z * q.z));
+    s.c = fast_sqrt(p * gam * s.r);
+#else
+    const double p = (gam - 1) * (q.w - 0.5 / q.x * (q.y * q.y + q.z * q.z));
+    s.c = sqrt(p * gam / q.x);
+    s.r = 0;
+#endif
+    return s;
+}
+__device__ __forceinline__ double spectral_radius(const d4& q, const CellSound& s, double nx, double ny)
 {
 #if AFX_FAST
-    const double r = fast_rcp(q.x);
-    const double V = (q.y * nx + q.z * ny) * r;
-    const double p = (gam - 1) * (q.w - 0.5 * r * (q.y * q.y + q.z * q.z));
-    return fast_sqrt(p * gam * r) + fabs(V);
+    return s.c + fabs((q.y * nx + q.z * ny) * s.r);
 #else
-    const double V = (q.y * nx + q.z * ny) / q.x;
-    const double p = (gam - 1) * (q.w - 0.5 / q.x * (q.y * q.y + q.z * q.z));
-    return sqrt(p * gam / q.x) + fabs(V);
+    return s.c + fabs((q.y * nx + q.z * ny) / q.x);
 #endif
 }
 
@@ -57,6 +72,7 @@ __global__ void __launch_bounds__(256, 3) k_dt_grad(DevMesh m, d4* __restrict__ 
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m.n_grad) return;
     const d4 qi = q[i];
+    const CellSound si = cell_sound(qi, gam);  // once per cell instead of once per face
     double dsum = 0;
     d4 ax = mk4(0, 0, 0, 0), ay = mk4(0, 0, 0, 0);
 #pragma unroll
@@ -74,10 +90,11 @@ __global__ void __launch_bounds__(256, 3) k_dt_grad(DevMesh m, d4* __restrict__ 
         const d4 qL = side ? qj : qi, qR = side ? qi : qj;  // states of cell0 / cell1
         const double nx = gA.x, ny = gA.y, len = gA.z;
         // spectral radius, solver.h:328-345
-        const double eig_L = spectral_radius(qL, nx, ny, gam);
-        double eig = eig_L;
+        // cell0's radius alone at one-sided (boundary) faces, where this cell is always cell0
+        double eig = spectral_radius(qi, si, nx, ny);
         if (kind == K_INTERNAL) {
-            const double eig_R = spectral_radius(qR, nx, ny, gam);
+            const double eig_j = spectral_radius(qj, cell_sound(qj, gam), nx, ny);
+            const double eig_L = side ? eig_j : eig, eig_R = side ? eig : eig_j;
             eig = (eig_L < eig_R) ? eig_R : eig_L;
         }
         dsum += eig * len;
@@ -187,8 +204,8 @@ __device__ __forceinline__ d4 limiter_value(const d4& qi, const d4& lo, const d4
         if (!(valid & (1u << s))) continue;
         const double dx = dxy[s].x, dy = dxy[s].y;
         const double p0 = gxi.x * dx + gyi.x * dy, p1 = gxi.y * dx + gyi.y * dy, p2 = gxi.z * dx + gyi.z * dy, p3 = gxi.w * dx + gyi.w * dy;
-        pmax.x = fmax(pmax.x, p0); pmax.y = fmax(pmax.y, p1); pmax.z = fmax(pmax.z, p2); pmax.w = fmax(pmax.w, p3);
-        pmin.x = fmin(pmin.x, p0); pmin.y = fmin(pmin.y, p1); pmin.z = fmin(pmin.z, p2); pmin.w = fmin(pmin.w, p3);
+        pmax.x = dmax2(pmax.x, p0); pmax.y = dmax2(pmax.y, p1); pmax.z = dmax2(pmax.z, p2); pmax.w = dmax2(pmax.w, p3);
+        pmin.x = dmin2(pmin.x, p0); pmin.y = dmin2(pmin.y, p1); pmin.z = dmin2(pmin.z, p2); pmin.w = dmin2(pmin.w, p3);
     }
     l.x = venkat_pair(pmax.x, pmin.x, dmax.x, dmin.x, K3a);
     l.y = venkat_pair(pmax.y, pmin.y, dmax.y, dmin.y, K3a);
@@ -199,10 +216,10 @@ __device__ __forceinline__ d4 limiter_value(const d4& qi, const d4& lo, const d4
     for (int s = 0; s < 4; ++s) {
         if (!(valid & (1u << s))) continue;
         const double dx = dxy[s].x, dy = dxy[s].y;
-        l.x = fmin(l.x, venkat(gxi.x * dx + gyi.x * dy, dmax.x, dmin.x, K3a));
-        l.y = fmin(l.y, venkat(gxi.y * dx + gyi.y * dy, dmax.y, dmin.y, K3a));
-        l.z = fmin(l.z, venkat(gxi.z * dx + gyi.z * dy, dmax.z, dmin.z, K3a));
-        l.w = fmin(l.w, venkat(gxi.w * dx + gyi.w * dy, dmax.w, dmin.w, K3a));
+        l.x = dmin2(l.x, venkat(gxi.x * dx + gyi.x * dy, dmax.x, dmin.x, K3a));
+        l.y = dmin2(l.y, venkat(gxi.y * dx + gyi.y * dy, dmax.y, dmin.y, K3a));
+        l.z = dmin2(l.z, venkat(gxi.z * dx + gyi.z * dy, dmax.z, dmin.z, K3a));
+        l.w = dmin2(l.w, venkat(gxi.w * dx + gyi.w * dy, dmax.w, dmin.w, K3a));
     }
 #endif
     return l;
@@ -238,8 +255,8 @@ __global__ void __launch_bounds__(256, AFX_LIM_MINB) k_limiter(DevMesh m, const 
             wall_ghost = (kind == K_SLIPWALL || kind == K_WALL);
         }
         const d4 qj = wall_ghost ? qi : qk[j];
-        lo.x = fmin(lo.x, qj.x); lo.y = fmin(lo.y, qj.y); lo.z = fmin(lo.z, qj.z); lo.w = fmin(lo.w, qj.w);
-        hi.x = fmax(hi.x, qj.x); hi.y = fmax(hi.y, qj.y); hi.z = fmax(hi.z, qj.z); hi.w = fmax(hi.w, qj.w);
+        lo.x = dmin2(lo.x, qj.x); lo.y = dmin2(lo.y, qj.y); lo.z = dmin2(lo.z, qj.z); lo.w = dmin2(lo.w, qj.w);
+        hi.x = dmax2(hi.x, qj.x); hi.y = dmax2(hi.y, qj.y); hi.z = dmax2(hi.z, qj.z); hi.w = dmax2(hi.w, qj.w);
     }
     lim[i] = limiter_value(qi, lo, hi, gx[i], gy[i], dxy, valid, limiter_k3a(m.area[i], limiter_k));
 }

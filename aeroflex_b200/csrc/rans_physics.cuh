@@ -26,6 +26,11 @@ namespace AFX_NS {
 
 __device__ __forceinline__ d4 mk4(double a, double b, double c, double d) { d4 r; r.x = a; r.y = b; r.z = c; r.w = d; return r; }
 
+// min / max as one compare and select.  fmin()/fmax() add NaN quieting (compare + two selects + a fix-up per half
+// word, ~7 instructions for a double on sm_100); the limiter takes 64 of them per cell.
+__device__ __forceinline__ double dmin2(double a, double b) { return b < a ? b : a; }
+__device__ __forceinline__ double dmax2(double a, double b) { return a < b ? b : a; }
+
 // physics.h:48-53
 __device__ __forceinline__ double pressure(const d4& q, double gam)
 {

@@ -150,6 +150,8 @@ struct Solver {
     DBuf<uint4> t_head, t_ctab; DBuf<uint32_t> t_halo, t_face; DBuf<double> t_area, t_k3a; DBuf<double2> t_dxy; DBuf<d4> t_fgeo;
     TileTab tt{};
     uint32_t n_tiles = 0, tile_cells = 0;
+    std::vector<uint32_t> tile_sizes;  // runs of consecutive cells that become tiles (graph bisection leaves)
+    uint32_t n_front_runs = 0;
     size_t stage_smem = 0, n_tile_faces = 0, n_tile_cells = 0;
     double k3a_for = -1;  // limiter_k the tiles' K^3 a table was computed for
     void refresh_tile_k3a();
@@ -217,7 +219,8 @@ struct Solver {
     void use() { CK(cudaSetDevice(device)); }
     static unsigned blocks(size_t n, unsigned bs = 256) { return (unsigned)((n + bs - 1) / bs); }
 
-    void create(const afx_mesh_desc& m, const afx_gas& g, int visc, int dev, const Partition* part = nullptr);
+    struct DryRun { uint32_t tile_cells; TileLimits limits; TilePlan plan; std::string check; };  // host-only: renumber, tile, verify (no device)
+    void create(const afx_mesh_desc& m, const afx_gas& g, int visc, int dev, const Partition* part = nullptr, DryRun* dry = nullptr);
     void init_halo(const Partition& part, const char* nccl_id);
     size_t p2p_export(void* blob);
     void p2p_connect(const void* blobs, size_t blob_size, int nranks);
@@ -269,21 +272,23 @@ bool Solver::boundary_variables(afx_bvars* out) const
     return false;
 }
 
-void Solver::create(const afx_mesh_desc& m, const afx_gas& g, int visc, int dev, const Partition* part)
+void Solver::create(const afx_mesh_desc& m, const afx_gas& g, int visc, int dev, const Partition* part, DryRun* dry)
 {
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
-        throw CudaError("no CUDA device available: libaeroflex_rans_b200 has no CPU fallback");
-    if (dev < 0 || dev >= ndev) throw InvalidArg("device ordinal out of range");
-    device = dev;
-    use();
-    cudaDeviceProp prop{};
-    CK(cudaGetDeviceProperties(&prop, dev));
-    if (prop.major < 10) throw CudaError(std::string("device '") + prop.name + "' is not sm_100 class; this library is built for sm_100a only");
-    CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
-    for (auto& e : evp) CK(cudaEventCreate(&e));
-    CK(cudaMallocHost(&h_pinned, 64 * sizeof(double)));
+    if (!dry) {
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+            throw CudaError("no CUDA device available: libaeroflex_rans_b200 has no CPU fallback");
+        if (dev < 0 || dev >= ndev) throw InvalidArg("device ordinal out of range");
+        device = dev;
+        use();
+        cudaDeviceProp prop{};
+        CK(cudaGetDeviceProperties(&prop, dev));
+        if (prop.major < 10) throw CudaError(std::string("device '") + prop.name + "' is not sm_100 class; this library is built for sm_100a only");
+        CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
+        for (auto& e : evp) CK(cudaEventCreate(&e));
+        CK(cudaMallocHost(&h_pinned, 64 * sizeof(double)));
+    }
     if (const char* e = getenv("AFX_NO_GRAPH")) use_graph = !(e[0] == '1');
     if (const char* e = getenv("AFX_HALO_OVERLAP")) halo_overlap = (e[0] == '1');
     if (const char* e = getenv("AFX_MATH")) kt = (std::string(e) == "strict") ? &strict::table() : &fast::table();
@@ -298,10 +303,21 @@ void Solver::create(const afx_mesh_desc& m, const afx_gas& g, int visc, int dev,
     viscous_type = (visc == AFX_VISC_LAMINAR) ? 1 : 0;   // solver.h:203-208 ("SA" never matches)
     visc_not_inviscid = (visc != AFX_VISC_INVISCID);
 
-    // ---- cell renumbering: Hilbert curve over rank coordinates ----
+    // ---- cell renumbering ----
+    // Hilbert curve over rank coordinates (coalescing, compact partitions); with the fused stage kernel the advanced
+    // cells are then regrouped by recursive graph bisection so that consecutive runs are compact patches of the cell
+    // graph: those runs are the kernel's shared-memory tiles (AFX_ORDER=hilbert keeps the curve and cuts it evenly).
     c_old2new.resize(NT); c_new2old.resize(NT);
     const char* ord = getenv("AFX_ORDER");
     const bool hilbert = !(ord && std::string(ord) == "none");
+    // AFX_FUSED=1 opts in to the fused stage kernel (measured at parity with the three-kernel stage)
+    bool want_tiles = false;
+    if (const char* e = getenv("AFX_FUSED")) want_tiles = (e[0] == '1');
+    if (dry) want_tiles = true;
+    tile_cells = dry ? dry->tile_cells : 192;
+    if (const char* e = getenv("AFX_TILE")) if (!dry) tile_cells = (uint32_t)std::max(32, std::min(1024, atoi(e)));
+    const bool graph_tiles = want_tiles && !(ord && (std::string(ord) == "hilbert" || std::string(ord) == "none"));
+    tile_sizes.clear(); n_front_runs = 0;
     {
         std::vector<uint32_t> idx(N);
         std::iota(idx.begin(), idx.end(), 0u);
@@ -312,6 +328,32 @@ void Solver::create(const afx_mesh_desc& m, const afx_gas& g, int visc, int dev,
             for (const auto& p : part->peers) for (uint32_t c : p.send) front[c] = 1;
             std::stable_partition(idx.begin(), idx.begin() + n_upd, [&](uint32_t c) { return front[c] != 0; });
             n_front = (uint32_t)std::count(front.begin(), front.begin() + n_upd, (uint8_t)1);
+        }
+        const bool split_front = n_front > 0 && n_front < n_upd;
+        if (graph_tiles) {
+            std::vector<uint32_t> nbr((size_t)4 * N, 0xFFFFFFFFu);  // cell -> neighbour cells, reference numbering
+#pragma omp parallel for schedule(static)
+            for (int64_t c = 0; c < (int64_t)N; ++c) {
+                const uint32_t sz = m.cells_is_tri[c] ? 3u : 4u;
+                for (uint32_t k = 0; k < sz; ++k) {
+                    const uint32_t e = m.cells_edges[4 * (size_t)c + k];
+                    if (e >= E) continue;
+                    const uint32_t a = m.edges_cells[2 * (size_t)e], b = m.edges_cells[2 * (size_t)e + 1];
+                    const uint32_t j = (a == (uint32_t)c) ? b : a;
+                    if (j < N) nbr[4 * (size_t)c + k] = j;
+                }
+            }
+            auto regroup = [&](uint32_t lo, uint32_t hi) {
+                if (hi <= lo) return;
+                std::vector<uint32_t> sub(idx.begin() + lo, idx.begin() + hi);
+                sub = graph_tile_order(N, nbr.data(), std::move(sub), tile_cells, tile_sizes);
+                std::copy(sub.begin(), sub.end(), idx.begin() + lo);
+            };
+            if (split_front) { regroup(0, n_front); n_front_runs = (uint32_t)tile_sizes.size(); regroup(n_front, n_upd); }
+            else regroup(0, n_upd);
+        } else if (want_tiles) {  // even cuts of the curve
+            if (split_front) { tile_sizes.push_back(n_front); n_front_runs = 1; tile_sizes.push_back(n_upd - n_front); }
+            else tile_sizes.push_back(n_upd);
         }
         for (uint32_t n = 0; n < N; ++n) { c_new2old[n] = idx[n]; c_old2new[idx[n]] = n; }
         // ghosts follow their owners
@@ -409,6 +451,11 @@ void Solver::create(const afx_mesh_desc& m, const afx_gas& g, int visc, int dev,
         h_bcx[b] = m.edges_cx[e]; h_bcy[b] = m.edges_cy[e];
     }
 
+    if (dry) {  // the host half only: tile the renumbered mesh and verify the plan against the connectivity
+        dry->plan = build_tiles(N, n_grad, h_cf.data(), h_cnb.data(), tile_sizes, n_front_runs, tile_cells, dry->limits);
+        dry->check = check_tiles(dry->plan, N, n_upd, h_cf.data(), h_cnb.data());
+        return;
+    }
     build_tile_tables(h_cf, h_cnb, h_cdxy, h_area, h_gA);
 
     // ---- upload ----
@@ -580,32 +627,45 @@ void Solver::launch_gather(const d4* qk_in, d4* qk_out, d4* vec_out, double alph
     if (halo && MODE == 0) exchange(qk_out, st);
 }
 
-// Tiles of the fused stage kernel.  AFX_FUSED=0 keeps the three-kernel stage; AFX_TILE sets the cells per tile (the
-// largest size whose staging fits the shared memory of one SM is used otherwise), AFX_STAGE_CTAS the resident CTAs per SM.
+// Tiles of the fused stage kernel (AFX_FUSED=1).  AFX_TILE sets the cells per tile,
+// AFX_STAGE_CTAS the resident CTAs per SM the shared-memory budget is divided by.
 void Solver::build_tile_tables(const std::vector<uint32_t>& h_cf, const std::vector<uint32_t>& h_cnb, const std::vector<double2>& h_cdxy,
                                const std::vector<double>& h_area, const std::vector<d4>& h_gA)
 {
     tiles_ready = false;
-    if (const char* e = getenv("AFX_FUSED")) if (e[0] == '0') return;
-    uint32_t T = 384;
-    if (const char* e = getenv("AFX_TILE")) T = (uint32_t)std::max(64, std::min(1024, atoi(e)));
-    int ctas = 1;
+    if (tile_sizes.empty()) return;  // not asked for
+    int ctas = 2;
     if (const char* e = getenv("AFX_STAGE_CTAS")) ctas = std::max(1, std::min(4, atoi(e)));
     int smem_max = 0;
     CK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     const size_t budget = (size_t)(smem_max - 1024) / ctas - (ctas > 1 ? 1024 : 0);
-    TilePlan plan;
+    // staging limits of one tile: typical ratios of a compact patch (local cells 1.6x, own + ring 1 1.35x, faces 2.2x,
+    // ring ids 0.7x the own cells) scaled up as far as the shared memory allows; the few tiles beyond them are cut in two
+    uint32_t T = tile_cells;
+    TileLimits lim;
     StageSmem L{};
-    for (;; T = (T > 96 ? T - 32 : T / 2)) {
-        bool ok = true;
-        try { plan = build_tiles(N, n_upd, n_front, n_grad, h_cf.data(), h_cnb.data(), T); }
-        catch (const std::invalid_argument&) { ok = false; }  // cells not ordered compactly enough for this tile size
-        if (ok) {
-            L = stage_smem_layout(plan.max_loc, plan.max_n1, plan.max_nf, plan.max_nc, plan.max_halo);
-            if (L.total <= budget) break;
+    auto limits_for = [&](uint32_t t, double f) {
+        TileLimits l;
+        l.max_loc = (uint32_t)(1.6 * f * t); l.max_n1 = ((uint32_t)(1.35 * f * t) + 1u) & ~1u; l.max_nf = (uint32_t)(2.2 * f * t);
+        l.max_halo = ((uint32_t)(0.7 * f * t) + 3u) & ~3u;
+        return l;
+    };
+    for (;; T = T * 7 / 8) {
+        double f = 1.0;
+        while (f < 3.0) {
+            const TileLimits l = limits_for(T, f + 0.05);
+            if (stage_smem_layout(l.max_loc, l.max_n1, l.max_nf, (T + 1u) & ~1u, l.max_halo).total > budget) break;
+            f += 0.05;
         }
-        if (T <= 32) return;  // no tiling fits: three-kernel stage
+        lim = limits_for(T, f);
+        if (stage_smem_layout(lim.max_loc, lim.max_n1, lim.max_nf, (T + 1u) & ~1u, lim.max_halo).total <= budget) break;
+        if (T <= 16) return;  // no tiling fits: three-kernel stage
     }
+    TilePlan plan;
+    try { plan = build_tiles(N, n_grad, h_cf.data(), h_cnb.data(), tile_sizes, n_front_runs, T, lim); }
+    catch (const std::invalid_argument&) { return; }  // three-kernel stage
+    L = stage_smem_layout(plan.max_loc, plan.max_n1, plan.max_nf, plan.max_nc, plan.max_halo);
+    if (L.total > budget) return;
     static_assert(sizeof(TileHead) == 32 && sizeof(TileCell) == 16, "tile tables are read as uint4");
     tile_cells = T; n_tiles = (uint32_t)plan.head.size(); stage_smem = L.total; tile_local_cells = plan.local_cells;
     // static geometry packed per tile: face offsets and areas of the own + ring-1 cells, normals / lengths of the local faces
@@ -1251,6 +1311,27 @@ int afx_rans_set_options(afx_rans* s, int second_order, int gradient_scheme, dou
 int afx_rans_set_math_mode(afx_rans* s, int mode)
 {
     return guard([&] { s->s.set_math_mode(mode); });
+}
+
+int afx_tiling_plan(const afx_mesh_desc* mesh, uint32_t tile_cells, const uint32_t* limits, uint32_t* n_tiles, uint32_t* per_tile, uint32_t cap,
+                    uint64_t* smem_bytes)
+{
+    return guard([&] {
+        if (!mesh || !n_tiles) throw afx::InvalidArg("null argument");
+        afx::Solver S;
+        afx::Solver::DryRun dry{tile_cells, afx::TileLimits{}, {}, {}};
+        if (limits) dry.limits = afx::TileLimits{limits[0], limits[1], limits[2], limits[3]};
+        const afx_gas g{1.4, 1., 0., 1., 1.};
+        S.create(*mesh, g, 0, 0, nullptr, &dry);
+        if (!dry.check.empty()) throw afx::InvalidArg("tile plan inconsistent: " + dry.check);
+        const auto& P = dry.plan;
+        *n_tiles = (uint32_t)P.head.size();
+        if (smem_bytes) *smem_bytes = afx::stage_smem_layout(P.max_loc, P.max_n1, P.max_nf, P.max_nc, P.max_halo).total;
+        if (per_tile)
+            for (uint32_t t = 0; t < P.head.size() && t < cap; ++t) {
+                per_tile[4 * t] = P.head[t].nc; per_tile[4 * t + 1] = P.head[t].h1; per_tile[4 * t + 2] = P.head[t].h2; per_tile[4 * t + 3] = P.head[t].nf;
+            }
+    });
 }
 
 int afx_rans_set_fused(afx_rans* s, int on)

@@ -23,11 +23,12 @@
 
 #include "rans_kernels.cuh"
 
+// measured best on B200 (profiles/): two CTAs of 256 threads per SM, tiles of 192 cells
 #ifndef AFX_STAGE_THREADS
-#define AFX_STAGE_THREADS 512
+#define AFX_STAGE_THREADS 256
 #endif
 #ifndef AFX_STAGE_MINB
-#define AFX_STAGE_MINB 1
+#define AFX_STAGE_MINB 2
 #endif
 
 namespace afx {
@@ -73,6 +74,50 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// shared-memory accesses by 32-bit shared-window address: no generic-address arithmetic in the inner loops
+__device__ __forceinline__ d4 lds_d4(uint32_t a)
+{
+    d4 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a) : "memory");
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+16];" : "=d"(v.z), "=d"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_d4(uint32_t a, const d4& v)
+{
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v.x), "d"(v.y) : "memory");
+    asm volatile("st.shared.v2.f64 [%0+16], {%1, %2};" ::"r"(a), "d"(v.z), "d"(v.w) : "memory");
+}
+__device__ __forceinline__ double2 lds_d2(uint32_t a)
+{
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ double lds_d(uint32_t a)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_d(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+__device__ __forceinline__ uint4 lds_u4(uint32_t a)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u4(uint32_t a, const uint4& v)
+{
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
 struct TileView {  // one tile's header, unpacked
     uint32_t cell0, nc, n1, n1p, nf, nh, nhp, off_halo, off_cell, off_face;
 };
@@ -93,20 +138,12 @@ k_stage(DevMesh m, TileTab tt, const d4* __restrict__ qk_in, const d4* q0, d4* q
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const StageSmem L = stage_smem_layout(tt.max_loc, tt.max_n1, tt.max_nf, tt.max_nc, tt.max_halo);
-    d4* const sq = reinterpret_cast<d4*>(smem + L.sq);
-    d4* const sgx = reinterpret_cast<d4*>(smem + L.sgx);
-    d4* const sgy = reinterpret_cast<d4*>(smem + L.sgy);
-    double2* const sdxy = reinterpret_cast<double2*>(smem + L.sdxy);
-    double* const sk3a = reinterpret_cast<double*>(smem + L.sarea);
-    uint4* const sctab = reinterpret_cast<uint4*>(smem + L.sctab);
-    d4* const sfg = reinterpret_cast<d4*>(smem + L.sfg);
-    d4* const srec = reinterpret_cast<d4*>(smem + L.srec);
-    d4* const sq0 = reinterpret_cast<d4*>(smem + L.sq0);
-    double* const sdt = reinterpret_cast<double*>(smem + L.sdt);
-    double* const sarea3 = reinterpret_cast<double*>(smem + L.sarea3);
-    uint4* const sctab3 = reinterpret_cast<uint4*>(smem + L.sctab3);
-    uint32_t* const shalo = reinterpret_cast<uint32_t*>(smem + L.shalo);
-    const uint32_t bar1 = smem_u32(smem + L.bars), bar2 = bar1 + 8, bar3 = bar1 + 16;
+    const uint32_t sb = smem_u32(smem);
+    // shared-window addresses of the staging arrays (rans_types.h: StageSmem)
+    const uint32_t a_sq = sb + L.sq, a_gx = sb + L.sgx, a_gy = sb + L.sgy, a_dxy = sb + L.sdxy, a_k3a = sb + L.sarea, a_ctab = sb + L.sctab;
+    const uint32_t a_fg = sb + L.sfg, a_rec = sb + L.srec;
+    const uint32_t a_q0 = sb + L.sq0, a_dt = sb + L.sdt, a_area3 = sb + L.sarea3, a_ctab3 = sb + L.sctab3, a_halo = sb + L.shalo;
+    const uint32_t bar1 = sb + L.bars, bar2 = bar1 + 8, bar3 = bar1 + 16;
     const uint32_t tid = threadIdx.x;
     const bool q0_is_in = (q0 == qk_in);  // stage 0: the stage state IS the iteration-start state
 
@@ -115,29 +152,29 @@ k_stage(DevMesh m, TileTab tt, const d4* __restrict__ qk_in, const d4* q0, d4* q
     __syncthreads();
 
     // ---- requests ----
-    // group 1 of tile v (its ring ids are in shalo[buf]); also the ring ids of the tile after it into the other buffer
+    // group 1 of tile v (its ring ids are in halo buffer `buf`); also the ring ids of the tile after it into the other buffer
     auto request_g1 = [&](const TileView& v, uint32_t buf, bool has_next, const TileView& nx) {
         if (tid == 0) {
             const uint32_t bytes = 32u * v.nc * 3u + 64u * v.n1p + 8u * v.n1p + 16u * v.n1p + (has_next ? 4u * nx.nhp : 0u);
             mbar_expect_tx(bar1, bytes);
-            bulk_g2s(smem_u32(sq), qk_in + v.cell0, 32u * v.nc, bar1);
-            bulk_g2s(smem_u32(sgx), gx + v.cell0, 32u * v.nc, bar1);
-            bulk_g2s(smem_u32(sgy), gy + v.cell0, 32u * v.nc, bar1);
-            bulk_g2s(smem_u32(sdxy), tt.dxy_t + 4 * (size_t)v.off_cell, 64u * v.n1p, bar1);
-            bulk_g2s(smem_u32(sk3a), tt.k3a_t + v.off_cell, 8u * v.n1p, bar1);
-            bulk_g2s(smem_u32(sctab), tt.ctab + v.off_cell, 16u * v.n1p, bar1);
-            if (has_next && nx.nhp) bulk_g2s(smem_u32(shalo + (buf ^ 1u) * tt.max_halo), tt.halo + nx.off_halo, 4u * nx.nhp, bar1);
+            bulk_g2s(a_sq, qk_in + v.cell0, 32u * v.nc, bar1);
+            bulk_g2s(a_gx, gx + v.cell0, 32u * v.nc, bar1);
+            bulk_g2s(a_gy, gy + v.cell0, 32u * v.nc, bar1);
+            bulk_g2s(a_dxy, tt.dxy_t + 4 * (size_t)v.off_cell, 64u * v.n1p, bar1);
+            bulk_g2s(a_k3a, tt.k3a_t + v.off_cell, 8u * v.n1p, bar1);
+            bulk_g2s(a_ctab, tt.ctab + v.off_cell, 16u * v.n1p, bar1);
+            if (has_next && nx.nhp) bulk_g2s(a_halo + (buf ^ 1u) * 4u * tt.max_halo, tt.halo + nx.off_halo, 4u * nx.nhp, bar1);
         }
-        const uint32_t* ids = shalo + buf * tt.max_halo;
+        const uint32_t ids = a_halo + buf * 4u * tt.max_halo;
         for (uint32_t k = tid; k < v.nh; k += AFX_STAGE_THREADS) {  // ring cells: states, and gradients of ring 1
-            const uint32_t gid = ids[k], l = v.nc + k;
+            const uint32_t gid = lds_u32(ids + 4u * k), l = v.nc + k;
             const char* s = reinterpret_cast<const char*>(qk_in + gid);
-            cp_async16(smem_u32(sq + l), s); cp_async16(smem_u32(sq + l) + 16, s + 16);
+            cp_async16(a_sq + 32u * l, s); cp_async16(a_sq + 32u * l + 16, s + 16);
             if (l < v.n1) {
                 const char* a = reinterpret_cast<const char*>(gx + gid);
                 const char* b = reinterpret_cast<const char*>(gy + gid);
-                cp_async16(smem_u32(sgx + l), a); cp_async16(smem_u32(sgx + l) + 16, a + 16);
-                cp_async16(smem_u32(sgy + l), b); cp_async16(smem_u32(sgy + l) + 16, b + 16);
+                cp_async16(a_gx + 32u * l, a); cp_async16(a_gx + 32u * l + 16, a + 16);
+                cp_async16(a_gy + 32u * l, b); cp_async16(a_gy + 32u * l + 16, b + 16);
             }
         }
         cp_async_commit();
@@ -145,17 +182,17 @@ k_stage(DevMesh m, TileTab tt, const d4* __restrict__ qk_in, const d4* q0, d4* q
     auto request_g2 = [&](const TileView& v) {
         if (tid == 0) {
             mbar_expect_tx(bar2, 32u * v.nf);
-            bulk_g2s(smem_u32(sfg), tt.fgeo_t + v.off_face, 32u * v.nf, bar2);
+            bulk_g2s(a_fg, tt.fgeo_t + v.off_face, 32u * v.nf, bar2);
         }
     };
     auto request_g3 = [&](const TileView& v) {
         if (!q0_is_in && tid == 0) {
             mbar_expect_tx(bar3, 32u * v.nc);
-            bulk_g2s(smem_u32(sq0), q0 + v.cell0, 32u * v.nc, bar3);
+            bulk_g2s(a_q0, q0 + v.cell0, 32u * v.nc, bar3);
         }
         for (uint32_t l = tid; l < v.nc; l += AFX_STAGE_THREADS) {
-            cp_async8(smem_u32(sdt + l), dt + v.cell0 + l);
-            cp_async8(smem_u32(sarea3 + l), m.area + v.cell0 + l);
+            cp_async8(a_dt + 8u * l, dt + v.cell0 + l);
+            cp_async8(a_area3 + 8u * l, m.area + v.cell0 + l);
         }
         cp_async_commit();
     };
@@ -165,7 +202,7 @@ k_stage(DevMesh m, TileTab tt, const d4* __restrict__ qk_in, const d4* q0, d4* q
     TileView cur{}, nxt{};
     if (tile < tt.n_tiles) {
         cur = tile_view(tt, tile);
-        for (uint32_t k = tid; k < cur.nhp; k += AFX_STAGE_THREADS) shalo[k] = tt.halo[cur.off_halo + k];  // first tile: ids by plain loads
+        for (uint32_t k = tid; k < cur.nhp; k += AFX_STAGE_THREADS) sts_u32(a_halo + 4u * k, tt.halo[cur.off_halo + k]);  // first tile: ids by plain loads
         __syncthreads();
         const bool has_next = tile + gridDim.x < tt.n_tiles;
         if (has_next) nxt = tile_view(tt, tile + gridDim.x);
@@ -186,32 +223,34 @@ k_stage(DevMesh m, TileTab tt, const d4* __restrict__ qk_in, const d4* q0, d4* q
         __syncthreads();         // everybody's gathers; P3 of the previous tile is over
         request_g3(cur);         // group 3 of THIS tile: P3 of the previous tile read these buffers until the barrier above
         for (uint32_t l = tid; l < cur.n1; l += AFX_STAGE_THREADS) {
-            const uint4 tc = sctab[l];
-            const uint32_t nb[4] = {tc.x & 0xFFFFu, tc.x >> 16, tc.y & 0xFFFFu, tc.y >> 16};
+            const uint4 tc = lds_u4(a_ctab + 16u * l);
+            const uint32_t nb[4] = {tc.x & 0xFFFFu, tc.x >> 16, tc.y & 0xFFFFu, tc.y >> 16};  // an empty slot points at l itself
             const uint32_t fs[4] = {tc.z & 0xFFFFu, tc.z >> 16, tc.w & 0xFFFFu, tc.w >> 16};
-            double2 dxy[4];
+            double2 dxy[4];  // (0, 0) in empty slots
 #pragma unroll
-            for (int s = 0; s < 4; ++s) dxy[s] = sdxy[s * cur.n1p + l];
-            const d4 gxi = sgx[l], gyi = sgy[l];
-            const double K3a = sk3a[l];
-            const d4 qi = sq[l];
+            for (int s = 0; s < 4; ++s) dxy[s] = lds_d2(a_dxy + 16u * (s * cur.n1p + l));
+            const d4 gxi = lds_d4(a_gx + 32u * l), gyi = lds_d4(a_gy + 32u * l);
+            const double K3a = lds_d(a_k3a + 8u * l);
+            const d4 qi = lds_d4(a_sq + 32u * l);
             d4 lo = qi, hi = qi;
             unsigned valid = 0;
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
-                if (nb[s] == 0xFFFFu) continue;
-                valid |= 1u << s;
-                const d4 qj = sq[nb[s]];  // wall ghosts hold their owner's state (written by the previous stage / k_dt_grad)
-                lo.x = fmin(lo.x, qj.x); lo.y = fmin(lo.y, qj.y); lo.z = fmin(lo.z, qj.z); lo.w = fmin(lo.w, qj.w);
-                hi.x = fmax(hi.x, qj.x); hi.y = fmax(hi.y, qj.y); hi.z = fmax(hi.z, qj.z); hi.w = fmax(hi.w, qj.w);
+                valid |= (nb[s] != l ? 1u : 0u) << s;
+                const d4 qj = lds_d4(a_sq + 32u * nb[s]);  // wall ghosts hold their owner's state (previous stage / k_dt_grad)
+                lo.x = dmin2(lo.x, qj.x); lo.y = dmin2(lo.y, qj.y); lo.z = dmin2(lo.z, qj.z); lo.w = dmin2(lo.w, qj.w);
+                hi.x = dmax2(hi.x, qj.x); hi.y = dmax2(hi.y, qj.y); hi.z = dmax2(hi.z, qj.z); hi.w = dmax2(hi.w, qj.w);
                 // the cell across an own cell's face is own, ring 1 or a ghost; a ghost cell has zero gradient and
                 // limiter 1, so its face state is its state
-                if (nb[s] >= cur.n1 && fs[s] != 0xFFFFu) srec[2 * (fs[s] & 0x7FFFu) + 1] = qj;
+                if (nb[s] >= cur.n1 && fs[s] != 0xFFFFu) sts_d4(a_rec + 64u * (fs[s] & 0x7FFFu) + 32u, qj);
             }
+#if AFX_FAST
+            valid = 0xFu;  // empty slots project to 0 and change neither pmax nor pmin
+#endif
             const d4 lm = limiter_value(qi, lo, hi, gxi, gyi, dxy, valid, K3a);
             if (l < cur.nc) {  // what P3 needs after group 1 has been overwritten by the next tile
-                sctab3[l] = tc;
-                if (q0_is_in) sq0[l] = qi;
+                sts_u4(a_ctab3 + 16u * l, tc);
+                if (q0_is_in) sts_d4(a_q0 + 32u * l, qi);
                 if (LAST && prm[2] != 0.0) lim[cur.cell0 + l] = lm;  // kept, like qW, for the last iteration of a run only
             }
 #pragma unroll
@@ -223,7 +262,7 @@ k_stage(DevMesh m, TileTab tt, const d4* __restrict__ qk_in, const d4* q0, d4* q
                 r.y = qi.y + (gxi.y * dx + gyi.y * dy) * lm.y;
                 r.z = qi.z + (gxi.z * dx + gyi.z * dy) * lm.z;
                 r.w = qi.w + (gxi.w * dx + gyi.w * dy) * lm.w;
-                srec[2 * (fs[s] & 0x7FFFu) + (fs[s] >> 15)] = r;
+                sts_d4(a_rec + 32u * (2u * (fs[s] & 0x7FFFu) + (fs[s] >> 15)), r);
             }
         }
         __syncthreads();
@@ -232,22 +271,22 @@ k_stage(DevMesh m, TileTab tt, const d4* __restrict__ qk_in, const d4* q0, d4* q
         // ---- P2: one flux per local face ----
         mbar_wait(bar2, par);
         for (uint32_t lf = tid; lf < cur.nf; lf += AFX_STAGE_THREADS) {
-            const d4 gA = sfg[lf];
-            const d4 qL = srec[2 * lf], qR = srec[2 * lf + 1];
+            const d4 gA = lds_d4(a_fg + 32u * lf);
+            const d4 qL = lds_d4(a_rec + 64u * lf), qR = lds_d4(a_rec + 64u * lf + 32u);
             d4 fl = face_flux<0>((int)gA.w, qL, qR, zero, zero, gA.x, gA.y, g);
             fl.x *= gA.z; fl.y *= gA.z; fl.z *= gA.z; fl.w *= gA.z;
-            srec[2 * lf] = fl;
-            srec[2 * lf + 1].x = gA.w;  // P3 needs the kind of boundary faces after group 2 has been overwritten
+            sts_d4(a_rec + 64u * lf, fl);
+            sts_d(a_rec + 64u * lf + 32u, gA.w);  // P3 needs the kind of boundary faces after group 2 has been overwritten
         }
         __syncthreads();
         if (has_next) request_g2(nxt);
 
         // ---- P3: gather, update, ghosts, norm ----
-        cp_async_wait<1>();      // my time steps (group 1 of the next tile may still be in flight)
+        cp_async_wait<1>();      // my time steps and areas (group 1 of the next tile may still be in flight)
         if (!q0_is_in) mbar_wait(bar3, par);
         for (uint32_t l = tid; l < cur.nc; l += AFX_STAGE_THREADS) {
             const uint32_t i = cur.cell0 + l;
-            const uint4 tc = sctab3[l];
+            const uint4 tc = lds_u4(a_ctab3 + 16u * l);
             const uint32_t nb[4] = {tc.x & 0xFFFFu, tc.x >> 16, tc.y & 0xFFFFu, tc.y >> 16};
             const uint32_t fs[4] = {tc.z & 0xFFFFu, tc.z >> 16, tc.w & 0xFFFFu, tc.w >> 16};
             d4 r = zero;
@@ -256,25 +295,25 @@ k_stage(DevMesh m, TileTab tt, const d4* __restrict__ qk_in, const d4* q0, d4* q
             for (int s = 0; s < 4; ++s) {
                 if (fs[s] == 0xFFFFu) continue;
                 const uint32_t lf = fs[s] & 0x7FFFu;
-                const d4 fl = srec[2 * lf];
+                const d4 fl = lds_d4(a_rec + 64u * lf);
                 if (fs[s] >> 15) { r.x += fl.x; r.y += fl.y; r.z += fl.z; r.w += fl.w; }
                 else { r.x -= fl.x; r.y -= fl.y; r.z -= fl.z; r.w -= fl.w; }
                 if (nb[s] >= cur.n1) {  // boundary face (rare)
-                    const int kind = (int)srec[2 * lf + 1].x;
+                    const int kind = (int)lds_d(a_rec + 64u * lf + 32u);
                     if (LAST && kind == K_INTERNAL)  // two-sided boundary face: the ghost row of qW holds +flux
                         nrm += fl.x * fl.x + fl.y * fl.y + fl.z * fl.z + fl.w * fl.w;
                     if (kind == K_SLIPWALL || kind == K_WALL) wall_ghost[s] = tt.halo[cur.off_halo + nb[s] - cur.nc];
                 }
             }
-            const double A = sarea3[l];
+            const double A = lds_d(a_area3 + 8u * l);
 #if AFX_FAST
             const double rA = fast_rcp(A);
             r.x *= rA; r.y *= rA; r.z *= rA; r.w *= rA;
 #else
             r.x /= A; r.y /= A; r.z /= A; r.w /= A;
 #endif
-            const d4 qs = sq0[l];
-            const double dti = sdt[l];
+            const d4 qs = lds_d4(a_q0 + 32u * l);
+            const double dti = lds_d(a_dt + 8u * l);
             const double relax = prm[1];
             d4 o;
             o.x = qs.x + r.x * dti * alpha * relax;

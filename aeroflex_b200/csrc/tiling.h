@@ -15,6 +15,7 @@
 // reference's ascending edge order, so results do not depend on the tiling.
 #pragma once
 #include <cstdint>
+#include <string>
 #include <vector>
 
 namespace afx {
@@ -32,7 +33,7 @@ struct TileHead {            // 32 bytes, read by every thread of the CTA
 };
 
 struct TileCell {            // 16 bytes per own / ring-1 cell
-    uint16_t nb[4];          // local index of the cell across slot s (TL_NONE where the slot is empty)
+    uint16_t nb[4];          // local index of the cell across slot s (the cell's own index where the slot is empty)
     uint16_t fs[4];          // local face of slot s | TL_SIDE, TL_NONE if the face has no end in the tile
 };
 
@@ -47,9 +48,21 @@ struct TilePlan {
     uint64_t local_cells = 0;          // sum of nc+h1+h2 over the tiles
 };
 
+struct TileLimits {  // a tile whose staging would exceed one of these is cut in two (0 = no limit)
+    uint32_t max_loc = 0, max_n1 = 0, max_nf = 0, max_halo = 0;
+};
+
 // cf / cnb: [4][N] slot-major tables of the solver (valid for cells < n_grad); N real cells.
-// Tiles never straddle n_front (the send layer of a partitioned run is advanced by its own tiles).
-TilePlan build_tiles(uint32_t N, uint32_t n_upd, uint32_t n_front, uint32_t n_grad, const uint32_t* cf, const uint32_t* cnb,
-                     uint32_t tile_cells);
+// `sizes`: consecutive runs of cells starting at cell 0 (ordering.h: graph_tile_order), the first `n_front_tiles` of
+// them cover the send layer of a partitioned run.  Runs longer than tile_cells are cut into pieces of tile_cells.
+TilePlan build_tiles(uint32_t N, uint32_t n_grad, const uint32_t* cf, const uint32_t* cnb, const std::vector<uint32_t>& sizes,
+                     uint32_t n_front_tiles, uint32_t tile_cells, const TileLimits& lim = TileLimits());
+
+
+// Verifies a plan against the connectivity it was built from: every advanced cell is owned by exactly one tile, the
+// local neighbour / face indices of every own and ring-1 cell point at the right global cell / face with the right
+// side bit, every face of an own cell is a local face and ring-1 cells list exactly the faces they share with the
+// tile.  Returns an empty string or the first inconsistency.
+std::string check_tiles(const TilePlan& P, uint32_t N, uint32_t n_upd, const uint32_t* cf, const uint32_t* cnb);
 
 }  // namespace afx

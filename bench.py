@@ -144,7 +144,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--math", default="fast", choices=["fast", "strict"])
-    ap.add_argument("--fused", type=int, default=1, help="1: one fused kernel per RK stage on shared-memory tiles; 0: limiter / flux / gather kernels")
+    ap.add_argument("--fused", type=int, default=0, help="1: one fused kernel per RK stage on shared-memory tiles; 0 (default): limiter / flux / gather kernels")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -167,6 +167,8 @@ def main():
                                                        "d2h_bytes_per_step": 0}}))
         return
 
+    if a.fused:
+        os.environ["AFX_FUSED"] = "1"  # the tiles (and the graph-bisection numbering) are built at creation
     import torch
     import aeroflex_b200 as afx
     if afx.device_count() <= 0:

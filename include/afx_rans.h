@@ -173,14 +173,21 @@ int afx_rans_set_options(afx_rans* s, int second_order, int gradient_scheme, dou
 /* arithmetic mode (AFX_MATH_*); the environment variable AFX_MATH=strict|fast sets the default at creation */
 int afx_rans_set_math_mode(afx_rans* s, int mode);
 int afx_rans_get_math_mode(afx_rans* s);
-/* Stage kernels of the explicit iteration: 1 (default; AFX_FUSED=0 at creation turns it off) = ONE kernel per
- * Runge-Kutta stage on shared-memory tiles (limiter + MUSCL + flux + gather + update; second-order non-laminar runs),
- * 0 = limiter / face flux / gather+update as three kernels.  Strict-mode states are bit-identical either way. */
+/* Stage kernels of the explicit iteration: 0 (default) = limiter / face flux / gather+update as three kernels;
+ * 1 = ONE persistent kernel per Runge-Kutta stage on shared-memory tiles (limiter + MUSCL + flux + gather + update;
+ * second-order non-laminar runs).  The tiles are built at creation only if the environment has AFX_FUSED=1 (the cells
+ * are then numbered by recursive graph bisection); without them this call leaves the three-kernel stage in place.
+ * Strict-mode states are bit-identical either way. */
 int afx_rans_set_fused(afx_rans* s, int on);
 /* out[0] = 1 if the fused stage kernel is in use, out[1] = tiles, out[2] = cells per tile, out[3] = dynamic shared
  * memory per CTA (bytes), out[4] = resident CTAs per SM, out[5] = largest local cell count, out[6] = largest local
  * face count, out[7] = total local cells of all tiles (own + ring 1 + state-only; / n_cells = staging overhead) */
 int afx_rans_tile_info(afx_rans* s, uint64_t out[8]);
+/* Host-only (no device needed): renumber `mesh` as afx_rans_create would, cut it into tiles of at most `tile_cells`
+ * cells and verify the plan against the connectivity.  n_tiles out; per_tile[4*t..] = own cells, ring-1 cells,
+ * state-only cells, local faces of tile t (up to `cap` tiles); smem_bytes = dynamic shared memory k_stage would need. */
+int afx_tiling_plan(const afx_mesh_desc* mesh, uint32_t tile_cells, const uint32_t* limits /* NULL or {max local cells, max own+ring1,
+                    max faces, max ring ids}: tiles beyond are cut in two */, uint32_t* n_tiles, uint32_t* per_tile, uint32_t cap, uint64_t* smem_bytes);
 /* solver::set_cfl (solver.h:250-252) */
 int afx_rans_set_cfl(afx_rans* s, double cfl);
 /* solver::init / refill_bcs / bcs_from_internal (solver.h:615-631, 259-287) */
