@@ -33,7 +33,7 @@ EXPORTED_SYMBOLS = [
     "afx_partition_edge_l2g", "afx_partition_peer", "afx_nccl_unique_id", "afx_rans_create_partitioned",
     "afx_rans_p2p_export", "afx_rans_p2p_connect", "afx_rans_halo_mode",
     "afx_rans_create", "afx_rans_destroy", "afx_rans_set_bcs", "afx_rans_set_options", "afx_rans_set_cfl",
-    "afx_rans_set_math_mode", "afx_rans_get_math_mode", "afx_rans_set_fused", "afx_rans_tile_info", "afx_tiling_plan",
+    "afx_rans_set_math_mode", "afx_rans_get_math_mode", "afx_rans_set_fused", "afx_rans_tile_info", "afx_tiling_plan", "afx_tiling_plan_partition",
     "afx_rans_init", "afx_rans_refill_bcs", "afx_rans_bcs_from_internal", "afx_rans_set_q", "afx_rans_get_q",
     "afx_rans_set_q_local", "afx_rans_get_q_local", "afx_rans_get_field", "afx_rans_boundary_variables", "afx_rans_uniform_residual", "afx_rans_step_explicit",
     "afx_rans_run_explicit", "afx_rans_phase_dt_gradients", "afx_rans_phase_limiters", "afx_rans_phase_residual",
@@ -167,6 +167,7 @@ def load_library():
     L.afx_rans_set_cfl.argtypes = [vp, C.c_double]
     L.afx_rans_set_math_mode.argtypes = [vp, C.c_int]
     L.afx_tiling_plan.argtypes = [C.POINTER(MeshDesc), C.c_uint32, vp, C.POINTER(C.c_uint32), vp, C.c_uint32, C.POINTER(C.c_uint64)]
+    L.afx_tiling_plan_partition.argtypes = [vp, C.c_uint32, vp, C.POINTER(C.c_uint32), vp, C.c_uint32, C.POINTER(C.c_uint64)]
     L.afx_rans_set_fused.argtypes = [vp, C.c_int]
     L.afx_rans_tile_info.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.afx_rans_get_math_mode.argtypes = [vp]
@@ -375,8 +376,11 @@ def tiling_plan(mesh, tile_cells, limits=None):
     smem = C.c_uint64()
     per = np.zeros((cap, 4), dtype=np.uint32)
     lim = np.asarray(limits, dtype=np.uint32) if limits is not None else None
-    _check(L.afx_tiling_plan(C.byref(mesh.d), tile_cells, lim.ctypes.data_as(C.c_void_p) if lim is not None else None, C.byref(n),
-                             per.ctypes.data_as(C.c_void_p), cap, C.byref(smem)))
+    limp = lim.ctypes.data_as(C.c_void_p) if lim is not None else None
+    if isinstance(mesh, Partition):
+        _check(L.afx_tiling_plan_partition(mesh.h, tile_cells, limp, C.byref(n), per.ctypes.data_as(C.c_void_p), cap, C.byref(smem)))
+    else:
+        _check(L.afx_tiling_plan(C.byref(mesh.d), tile_cells, limp, C.byref(n), per.ctypes.data_as(C.c_void_p), cap, C.byref(smem)))
     return per[:n.value].copy(), int(smem.value)
 
 

@@ -620,6 +620,19 @@ __global__ void k_ghost_fill(d4* __restrict__ q, const uint32_t* __restrict__ bg
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b < G) q[bghost[b]] = from_owner ? q[bowner[b]] : bstate[b];
 }
+// wall ghosts of cells [lo, N) follow their owners (set_walls_from_internal, solver.h:289-305).  The stage kernels do this
+// for the cells they advance; a partitioned run with the fused stage kernel needs it for its ring-1 halo cells too, whose
+// limiters that kernel recomputes from the staged ghost states.
+__global__ void k_ghost_follow(d4* __restrict__ q, const uint32_t* __restrict__ bghost, const uint32_t* __restrict__ bowner,
+                               const uint32_t* __restrict__ bface, const uint8_t* __restrict__ fkind, uint32_t G, uint32_t lo)
+{
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= G) return;
+    const uint32_t o = bowner[b];
+    const int kind = fkind[bface[b]];
+    if (o >= lo && (kind == K_SLIPWALL || kind == K_WALL)) q[bghost[b]] = q[o];
+}
+
 // permuted copies between reference order (host layout) and internal order
 __global__ void k_permute4(const d4* __restrict__ src, d4* __restrict__ dst, const uint32_t* __restrict__ idx, uint32_t n)
 {
@@ -699,6 +712,11 @@ static void fill_cells(d4* q, uint32_t n, d4 v, cudaStream_t st) { k_fill_cells<
 static void ghost_fill(d4* q, const uint32_t* bghost, const uint32_t* bowner, const d4* bstate, uint32_t G, int from_owner, cudaStream_t st)
 {
     k_ghost_fill<<<nblk(G), 256, 0, st>>>(q, bghost, bowner, bstate, G, from_owner);
+}
+static void ghost_follow(d4* q, const uint32_t* bghost, const uint32_t* bowner, const uint32_t* bface, const uint8_t* fkind, uint32_t G, uint32_t lo,
+                         cudaStream_t st)
+{
+    if (G) k_ghost_follow<<<nblk(G), 256, 0, st>>>(q, bghost, bowner, bface, fkind, G, lo);
 }
 static void permute4(const d4* src, d4* dst, const uint32_t* idx, uint32_t n, cudaStream_t st) { k_permute4<<<nblk(n), 256, 0, st>>>(src, dst, idx, n); }
 static void halo_signal(const SignalArgs& a, cudaStream_t st) { k_halo_signal<<<1, 32, 0, st>>>(a); }

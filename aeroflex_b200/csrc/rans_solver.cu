@@ -732,6 +732,8 @@ void Solver::launch_stage(int s, const d4* qk_in, d4* qk_out, double alpha)
     } else {
         exchange(qk_out, st);
     }
+    // the next stage recomputes the limiters of this rank's ring-1 halo cells from staged states: their wall ghosts follow them
+    if (s < 2 && G) { kt->ghost_follow(qk_out, bghost.p, bowner.p, bface.p, fkind.p, G, n_upd, st); ++launches; }
 }
 
 // explicitSolver::solve, solver.h:802-828.  Stage 0 reads q in place of qk (they
@@ -1313,24 +1315,41 @@ int afx_rans_set_math_mode(afx_rans* s, int mode)
     return guard([&] { s->s.set_math_mode(mode); });
 }
 
+static void tiling_plan_impl(const afx_mesh_desc& mesh, const afx::Partition* part, uint32_t tile_cells, const uint32_t* limits, uint32_t* n_tiles,
+                             uint32_t* per_tile, uint32_t cap, uint64_t* smem_bytes)
+{
+    if (!n_tiles) throw afx::InvalidArg("null argument");
+    afx::Solver S;
+    afx::Solver::DryRun dry{tile_cells, afx::TileLimits{}, {}, {}};
+    if (limits) dry.limits = afx::TileLimits{limits[0], limits[1], limits[2], limits[3]};
+    const afx_gas g{1.4, 1., 0., 1., 1.};
+    S.create(mesh, g, 0, 0, part, &dry);
+    if (!dry.check.empty()) throw afx::InvalidArg("tile plan inconsistent: " + dry.check);
+    const auto& P = dry.plan;
+    *n_tiles = (uint32_t)P.head.size();
+    if (smem_bytes) *smem_bytes = afx::stage_smem_layout(P.max_loc, P.max_n1, P.max_nf, P.max_nc, P.max_halo).total;
+    if (per_tile)
+        for (uint32_t t = 0; t < P.head.size() && t < cap; ++t) {
+            per_tile[4 * t] = P.head[t].nc; per_tile[4 * t + 1] = P.head[t].h1; per_tile[4 * t + 2] = P.head[t].h2; per_tile[4 * t + 3] = P.head[t].nf;
+        }
+}
+
 int afx_tiling_plan(const afx_mesh_desc* mesh, uint32_t tile_cells, const uint32_t* limits, uint32_t* n_tiles, uint32_t* per_tile, uint32_t cap,
                     uint64_t* smem_bytes)
 {
     return guard([&] {
-        if (!mesh || !n_tiles) throw afx::InvalidArg("null argument");
-        afx::Solver S;
-        afx::Solver::DryRun dry{tile_cells, afx::TileLimits{}, {}, {}};
-        if (limits) dry.limits = afx::TileLimits{limits[0], limits[1], limits[2], limits[3]};
-        const afx_gas g{1.4, 1., 0., 1., 1.};
-        S.create(*mesh, g, 0, 0, nullptr, &dry);
-        if (!dry.check.empty()) throw afx::InvalidArg("tile plan inconsistent: " + dry.check);
-        const auto& P = dry.plan;
-        *n_tiles = (uint32_t)P.head.size();
-        if (smem_bytes) *smem_bytes = afx::stage_smem_layout(P.max_loc, P.max_n1, P.max_nf, P.max_nc, P.max_halo).total;
-        if (per_tile)
-            for (uint32_t t = 0; t < P.head.size() && t < cap; ++t) {
-                per_tile[4 * t] = P.head[t].nc; per_tile[4 * t + 1] = P.head[t].h1; per_tile[4 * t + 2] = P.head[t].h2; per_tile[4 * t + 3] = P.head[t].nf;
-            }
+        if (!mesh) throw afx::InvalidArg("null argument");
+        tiling_plan_impl(*mesh, nullptr, tile_cells, limits, n_tiles, per_tile, cap, smem_bytes);
+    });
+}
+
+int afx_tiling_plan_partition(const afx_partition* part, uint32_t tile_cells, const uint32_t* limits, uint32_t* n_tiles, uint32_t* per_tile,
+                              uint32_t cap, uint64_t* smem_bytes)
+{
+    return guard([&] {
+        if (!part) throw afx::InvalidArg("null argument");
+        const afx_mesh_desc d = part->p.desc();
+        tiling_plan_impl(d, &part->p, tile_cells, limits, n_tiles, per_tile, cap, smem_bytes);
     });
 }
 

@@ -156,6 +156,8 @@ struct KernelTable {
     void (*wall_forces)(const WallArgs& a, const DevMesh& m, const d4* q, cudaStream_t st);
     void (*fill_cells)(d4* q, uint32_t n, d4 v, cudaStream_t st);
     void (*ghost_fill)(d4* q, const uint32_t* bghost, const uint32_t* bowner, const d4* bstate, uint32_t G, int from_owner, cudaStream_t st);
+    void (*ghost_follow)(d4* q, const uint32_t* bghost, const uint32_t* bowner, const uint32_t* bface, const uint8_t* fkind, uint32_t G, uint32_t lo,
+                         cudaStream_t st);  // wall ghosts of cells >= lo take their owner's state
     void (*permute4)(const d4* src, d4* dst, const uint32_t* idx, uint32_t n, cudaStream_t st);
     void (*permute1)(const double* src, double* dst, const uint32_t* idx, uint32_t n, uint32_t nsrc, cudaStream_t st);
     void (*scatter4)(const d4* src, d4* dst, const uint32_t* idx, uint32_t n, cudaStream_t st);  // dst[idx[i]] = src[i]

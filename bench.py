@@ -37,6 +37,7 @@ WORKLOADS = {  # name: (ni, nj, n_quad_layers) -> SURVEY.md 8d
     "synthetic-4M-mixed-omesh": (2048, 1280, 512),
     "synthetic-8M-mixed-omesh": (4096, 1280, 512),
     "synthetic-16M-mixed-omesh": (4096, 2560, 1024),
+    "synthetic-64M-mixed-omesh": (8192, 5120, 2048),
 }
 # weak scaling: 2^20 cells per GPU, the whole mesh cut into N pieces along a Hilbert curve, 2-layer halo over NCCL
 WEAK = {1: "synthetic-1M-mixed-omesh", 2: "synthetic-2M-mixed-omesh", 4: "synthetic-4M-mixed-omesh", 8: "synthetic-8M-mixed-omesh"}
@@ -150,6 +151,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     W = max(a.warmup, 3) if a.impl == "b200" else a.warmup
     workload = a.workload or WEAK.get(world, "synthetic-1M-mixed-omesh")
+    scaling = "weak" if a.workload is None else "strong (fixed mesh: %s)" % workload  # an explicit workload is cut into N pieces
     config = {"workload": workload, "scheme": "explicit 3-stage RK, 2nd order MUSCL, Green-Gauss, Venkatakrishnan k=5",
               "viscosity": "spallart-allmaras (reference semantics: Roe flux + no-slip wall + gradients, SURVEY F1/F2)",
               "cfl": CFL, "relaxation": RELAX, "l2": "working set > 126 MB L2 (inputs larger than L2, no flush)"}
@@ -307,7 +309,7 @@ def main():
         cpu_port = port_cpu(60)
     if rank == 0:
         out = {"metric": "RANS cell-updates/s", "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": a.steps, "warmup": W,
-               "ms_per_step": t_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+               "ms_per_step": t_ms / a.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
                "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
                "wall_ms_per_step": wall_ms / a.steps, "final_residual_norm": float(norms[-1])}
         if cpu is not None:

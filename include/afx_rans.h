@@ -188,6 +188,9 @@ int afx_rans_tile_info(afx_rans* s, uint64_t out[8]);
  * state-only cells, local faces of tile t (up to `cap` tiles); smem_bytes = dynamic shared memory k_stage would need. */
 int afx_tiling_plan(const afx_mesh_desc* mesh, uint32_t tile_cells, const uint32_t* limits /* NULL or {max local cells, max own+ring1,
                     max faces, max ring ids}: tiles beyond are cut in two */, uint32_t* n_tiles, uint32_t* per_tile, uint32_t cap, uint64_t* smem_bytes);
+/* the same for one rank's piece of a partitioned mesh: only the owned cells are tiled, the send layer by its own tiles */
+int afx_tiling_plan_partition(const afx_partition* part, uint32_t tile_cells, const uint32_t* limits, uint32_t* n_tiles, uint32_t* per_tile,
+                              uint32_t cap, uint64_t* smem_bytes);
 /* solver::set_cfl (solver.h:250-252) */
 int afx_rans_set_cfl(afx_rans* s, double cfl);
 /* solver::init / refill_bcs / bcs_from_internal (solver.h:615-631, 259-287) */

@@ -26,9 +26,11 @@ def _q0(afx, mesh):
     return s, q
 
 
-def _worker(rank, world, port, n_iter, out_dir, math, halo):
+def _worker(rank, world, port, n_iter, out_dir, math, halo, fused):
     import torch.distributed as dist
     import aeroflex_b200 as afx
+    if fused:
+        os.environ["AFX_FUSED"] = "1"  # tiles + graph-bisection numbering at creation: the fused stage kernel pushes the halo itself
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     mesh = afx.Mesh.synth_omesh(*DIMS, 150.0)
@@ -41,6 +43,7 @@ def _worker(rank, world, port, n_iter, out_dir, math, halo):
         dist.all_gather_object(blobs, s.p2p_export())
         s.p2p_connect(blobs)
     assert s.halo_mode() == halo
+    assert s.tile_info()["fused"] == bool(fused)
     s.set_bcs(BCS); s.set_options(True, "green-gauss", 5.0, 1.4); s.init(); s.refill_bcs()
     q0 = np.load(os.path.join(out_dir, "q0.npy"))
     s.set_q(q0)
@@ -53,8 +56,9 @@ def _worker(rank, world, port, n_iter, out_dir, math, halo):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,math,halo", [(2, "strict", "nccl"), (2, "strict", "p2p"), (2, "fast", "p2p")])
-def test_partitioned_run_matches_single_gpu(afx, gpu, tmp_path, world, math, halo):
+@pytest.mark.parametrize("world,math,halo,fused", [(2, "strict", "nccl", 0), (2, "strict", "p2p", 0), (2, "fast", "p2p", 0),
+                                                   (2, "strict", "p2p", 1), (2, "strict", "nccl", 1), (4, "strict", "p2p", 1)])
+def test_partitioned_run_matches_single_gpu(afx, gpu, tmp_path, world, math, halo, fused):
     if gpu < world:
         pytest.skip("needs %d GPUs, %d visible" % (world, gpu))
     import torch.multiprocessing as mp
@@ -68,7 +72,7 @@ def test_partitioned_run_matches_single_gpu(afx, gpu, tmp_path, world, math, hal
     Q = single.get_q().reshape(-1, 4)
     F = np.array(single.wall_forces("wall"))
     del single
-    mp.spawn(_worker, args=(world, _free_port(), n_iter, str(tmp_path), math, halo), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), n_iter, str(tmp_path), math, halo, fused), nprocs=world, join=True)
     seen = 0
     for r in range(world):
         d = np.load(tmp_path / ("r%d.npz" % r))
