@@ -71,7 +71,9 @@ struct DBuf {
         if (h.size() != n) alloc(h.size());
         if (n) CK(cudaMemcpyAsync(p, h.data(), n * sizeof(T), cudaMemcpyHostToDevice, st));
     }
-    void free() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void view(T* base, size_t n_) { free(); p = base; n = n_; borrowed = true; }  // a slice of another allocation
+    void free() { if (p && !borrowed) cudaFree(p); p = nullptr; n = 0; borrowed = false; }
+    bool borrowed = false;
     ~DBuf() { free(); }
 };
 
@@ -167,6 +169,8 @@ struct Solver {
     DBuf<uint32_t> perm_c_new2old, perm_c_old2new;
     // device state
     DBuf<d4> q, qkA, qkB, gx, gy, lim, qW, rhs, flux, stage;
+    DBuf<d4> grad;  // [gx | gy] in one allocation: one L2 access-policy window covers both
+    void set_l2_window();
     DBuf<double> dt, dt_ref;
     DBuf<d4> J; DBuf<double> D;   // Jacobian face blocks [E][16] d4 and diagonal blocks [NT][16]
     // implicit step: block-Jacobi preconditioned restarted GMRES on the device
@@ -469,7 +473,10 @@ void Solver::create(const afx_mesh_desc& m, const afx_gas& g, int visc, int dev,
     bstate.alloc(G ? G : 1);
     perm_c_new2old.upload(c_new2old, st); perm_c_old2new.upload(c_old2new, st);
 
-    for (DBuf<d4>* b : {&q, &qkA, &qkB, &gx, &gy, &lim, &qW, &rhs, &stage}) { b->alloc(NT); b->zero(st); }
+    grad.alloc(2 * (size_t)NT); grad.zero(st);
+    gx.view(grad.p, NT); gy.view(grad.p + NT, NT);
+    for (DBuf<d4>* b : {&q, &qkA, &qkB, &lim, &qW, &rhs, &stage}) { b->alloc(NT); b->zero(st); }
+    set_l2_window();
     flux.alloc(E); flux.zero(st);
     dt.alloc(NT); dt.zero(st); dt_ref.alloc(NT);
     partial.alloc(std::max<size_t>(blocks(NT), stage_grid) + 4); norms.alloc(NORM_RING); norms.zero(st);
@@ -507,6 +514,26 @@ void Solver::create(const afx_mesh_desc& m, const afx_gas& g, int visc, int dev,
     dm.n_upd = n_upd; dm.n_grad = n_grad; dm.e_flux = e_flux;
     dm.fcells = fcells.p; dm.fgA = fgA.p; dm.fgB = fgB.p; dm.ftij = ftij.p; dm.fkind = fkind.p;
     dm.cf = cf.p; dm.cnb = cnb.p; dm.cdxy = cdxy.p; dm.area = area.p; dm.lsqM = lsqM.p; dm.lsq_perm = lsq_perm.p;
+}
+
+// The gradients are written once per iteration and read by the limiter and the flux kernel of all three stages: where
+// both arrays fit the part of the 126 MB L2 that may be set aside for persisting lines, every kernel on the solver's
+// stream (and every node captured from it) keeps them resident.  Larger meshes stream as before.  AFX_L2_PERSIST=0 disables.
+void Solver::set_l2_window()
+{
+    if (const char* e = getenv("AFX_L2_PERSIST")) if (e[0] == '0') return;
+    cudaDeviceProp prop{};
+    CK(cudaGetDeviceProperties(&prop, device));
+    const size_t bytes = grad.n * sizeof(d4);
+    if (prop.persistingL2CacheMaxSize <= 0 || bytes == 0 || bytes > (size_t)prop.persistingL2CacheMaxSize || bytes > (size_t)prop.accessPolicyMaxWindowSize) return;
+    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, bytes) != cudaSuccess) { cudaGetLastError(); return; }
+    cudaStreamAttrValue a{};
+    a.accessPolicyWindow.base_ptr = grad.p;
+    a.accessPolicyWindow.num_bytes = bytes;
+    a.accessPolicyWindow.hitRatio = 1.0f;
+    a.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    a.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &a) != cudaSuccess) cudaGetLastError();
 }
 
 // solver::set_bcs, solver.h:200-247
