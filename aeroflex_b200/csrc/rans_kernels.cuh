@@ -75,16 +75,22 @@ __global__ void __launch_bounds__(256, 3) k_dt_grad(DevMesh m, d4* __restrict__ 
     const CellSound si = cell_sound(qi, gam);  // once per cell instead of once per face
     double dsum = 0;
     d4 ax = mk4(0, 0, 0, 0), ay = mk4(0, 0, 0, 0);
+    uint32_t nbv[4];
+    d4 geo[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {  // independent coalesced loads first: neighbour | flags and the slot's face geometry
+        nbv[s] = m.cnb[(size_t)s * m.N + i];
+        geo[s] = m.cgeo[(size_t)s * m.N + i];
+    }
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
-        const uint32_t cfv = m.cf[(size_t)s * m.N + i];
-        if (cfv == CF_NONE) continue;
-        const uint32_t f = cfv & CF_ID;
-        const bool side = cfv & CF_SIDE;
-        const uint32_t j = m.cnb[(size_t)s * m.N + i];
-        const d4 gA = m.fgA[f];
-        const int kind = (cfv & CF_BND) ? (int)m.fkind[f] : K_INTERNAL;
-        const bool wall_ghost = walls && (cfv & CF_BND) && (kind == K_SLIPWALL || kind == K_WALL);
+        const uint32_t v = nbv[s];
+        if (v == CF_NONE) continue;
+        const bool side = v & CF_SIDE;
+        const uint32_t j = v & CF_ID;
+        const d4 gA = geo[s];
+        const int kind = (v & CF_BND) ? (int)m.fkind[m.cf[(size_t)s * m.N + i] & CF_ID] : K_INTERNAL;
+        const bool wall_ghost = walls && (v & CF_BND) && (kind == K_SLIPWALL || kind == K_WALL);
         if (wall_ghost) q[j] = qi;  // ghost <- owner (set_walls_from_internal)
         const d4 qj = wall_ghost ? qi : q[j];
         const d4 qL = side ? qj : qi, qR = side ? qi : qj;  // states of cell0 / cell1
@@ -245,12 +251,12 @@ __global__ void __launch_bounds__(256, AFX_LIM_MINB) k_limiter(DevMesh m, const 
     unsigned valid = 0;
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
-        const uint32_t j = nbs[s];
-        if (j == CF_NONE) continue;
+        if (nbs[s] == CF_NONE) continue;
+        const uint32_t j = nbs[s] & CF_ID;
         valid |= 1u << s;
         // a wall ghost holds its owner's state (set_walls_from_internal): no need to read it
         bool wall_ghost = false;
-        if (walls && j >= m.N) {
+        if (walls && (nbs[s] & CF_BND)) {
             const int kind = m.fkind[m.cf[(size_t)s * m.N + i] & CF_ID];
             wall_ghost = (kind == K_SLIPWALL || kind == K_WALL);
         }

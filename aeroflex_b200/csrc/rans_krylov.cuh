@@ -35,7 +35,7 @@ __device__ __forceinline__ d4 row_Ax(const DevMesh& m, const d4* __restrict__ J,
         if (cfv == CF_NONE) continue;
         const uint32_t f = cfv & CF_ID;
         const bool side = cfv & CF_SIDE;
-        const d4 t = blk_mul(J + (size_t)f * 16 + (side ? 8 : 4), x[m.cnb[(size_t)s * m.N + i]]);
+        const d4 t = blk_mul(J + (size_t)f * 16 + (side ? 8 : 4), x[m.cnb[(size_t)s * m.N + i] & CF_ID]);
         y.x += t.x; y.y += t.y; y.z += t.z; y.w += t.w;
     }
     return y;

@@ -146,7 +146,7 @@ struct Solver {
     bool bcs_set = false;
 
     // device geometry
-    DBuf<uint2> fcells; DBuf<d4> fgA, fgB, ftij; DBuf<uint8_t> fkind; DBuf<uint32_t> cf, cnb; DBuf<double2> cdxy; DBuf<double> area;
+    DBuf<uint2> fcells; DBuf<d4> fgA, fgB, ftij; DBuf<uint8_t> fkind; DBuf<uint32_t> cf, cnb; DBuf<d4> cgeo; DBuf<double2> cdxy; DBuf<double> area;
     DBuf<double> lsqM; DBuf<uint16_t> lsq_perm;
     // shared-memory tiles of the fused stage kernel (tiling.h)
     DBuf<uint4> t_head, t_ctab; DBuf<uint32_t> t_halo, t_face; DBuf<double> t_area, t_k3a; DBuf<double2> t_dxy; DBuf<d4> t_fgeo;
@@ -467,7 +467,16 @@ void Solver::create(const afx_mesh_desc& m, const afx_gas& g, int visc, int dev,
     if (viscous_type == 1) ftij.upload(h_t, st);
     std::vector<uint8_t> h_kind(E, 0);
     fkind.upload(h_kind, st);
-    cf.upload(h_cf, st); cnb.upload(h_cnb, st); cdxy.upload(h_cdxy, st); area.upload(h_area, st); lsq_perm.upload(h_perm, st);
+    {   // device copy of the neighbour table carries the side / boundary flags of cf; per-slot face geometry beside it
+        if (NT > CF_ID) throw InvalidArg("too many cells for the 30-bit neighbour index");
+        std::vector<uint32_t> h_cnbf(h_cnb);
+        std::vector<d4> h_cgeo((size_t)4 * N, d4{0., 0., 0., 0.});
+#pragma omp parallel for schedule(static)
+        for (int64_t k = 0; k < (int64_t)h_cnbf.size(); ++k)
+            if (h_cf[k] != CF_NONE) { h_cnbf[k] |= h_cf[k] & (CF_SIDE | CF_BND); h_cgeo[k] = h_gA[h_cf[k] & CF_ID]; }
+        cnb.upload(h_cnbf, st); cgeo.upload(h_cgeo, st);
+    }
+    cf.upload(h_cf, st); cdxy.upload(h_cdxy, st); area.upload(h_area, st); lsq_perm.upload(h_perm, st);
     bface.upload(h_bnd_face, st); bghost.upload(h_bghost, st); bowner.upload(h_bowner, st);
     bpatch.upload(h_bnd_patch, st); bcx.upload(h_bcx, st); bcy.upload(h_bcy, st);
     bstate.alloc(G ? G : 1);
@@ -513,7 +522,7 @@ void Solver::create(const afx_mesh_desc& m, const afx_gas& g, int visc, int dev,
     dm.N = N; dm.G = G; dm.E = E; dm.NT = NT;
     dm.n_upd = n_upd; dm.n_grad = n_grad; dm.e_flux = e_flux;
     dm.fcells = fcells.p; dm.fgA = fgA.p; dm.fgB = fgB.p; dm.ftij = ftij.p; dm.fkind = fkind.p;
-    dm.cf = cf.p; dm.cnb = cnb.p; dm.cdxy = cdxy.p; dm.area = area.p; dm.lsqM = lsqM.p; dm.lsq_perm = lsq_perm.p;
+    dm.cf = cf.p; dm.cnb = cnb.p; dm.cgeo = cgeo.p; dm.cdxy = cdxy.p; dm.area = area.p; dm.lsqM = lsqM.p; dm.lsq_perm = lsq_perm.p;
 }
 
 // The gradients are written once per iteration and read by the limiter and the flux kernel of all three stages: where

@@ -35,7 +35,8 @@ struct DevMesh {
     const d4* ftij;              // [E] t0, t1, l, - (laminar face-gradient direction, solver.h:369-376)
     const uint8_t* fkind;        // [E]
     const uint32_t* cf;          // [4][N]
-    const uint32_t* cnb;         // [4][N] the cell across slot s (same slots as cf; CF_NONE where empty): one indirection less
+    const uint32_t* cnb;         // [4][N] the cell across slot s (same slots as cf; CF_NONE where empty) | CF_SIDE | CF_BND like cf
+    const d4* cgeo;              // [4][N] {nx, ny, len, w_gg} of the face in slot s: the dt/gradient kernel reads no face record
     const double2* cdxy;         // [4][N] face centre minus this cell's centre for slot s (the fgB half this cell needs)
     const double* area;          // [NT]
     const double* lsqM;          // [8][N]  (M * dT) rows in cellsEdges order, LSQ only
