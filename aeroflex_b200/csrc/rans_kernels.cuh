@@ -24,6 +24,12 @@
 #ifndef AFX_LIM_MINB
 #define AFX_LIM_MINB 4
 #endif
+#ifndef AFX_DTG_THREADS
+#define AFX_DTG_THREADS 256
+#endif
+#ifndef AFX_DTG_MINB
+#define AFX_DTG_MINB 3
+#endif
 
 namespace afx {
 namespace AFX_NS {
@@ -65,7 +71,7 @@ __device__ __forceinline__ double spectral_radius(const d4& q, const CellSound& 
 // least-squares (470-513).  Source state is the iteration-start q.
 // ---------------------------------------------------------------------------
 template <int GRAD>
-__global__ void __launch_bounds__(256, 3) k_dt_grad(DevMesh m, d4* __restrict__ q, double* __restrict__ dt,
+__global__ void __launch_bounds__(AFX_DTG_THREADS, AFX_DTG_MINB) k_dt_grad(DevMesh m, d4* __restrict__ q, double* __restrict__ dt,
                                                  d4* __restrict__ gx, d4* __restrict__ gy, const double* __restrict__ prm,
                                                  double gam, int want_grad, int walls)
 {
@@ -669,8 +675,8 @@ inline unsigned nblk(size_t n, unsigned bs = 256) { return (unsigned)((n + bs - 
 static void dt_grad(int grad, const DevMesh& m, d4* q, double* dt, d4* gx, d4* gy, const double* prm, double gam, int want_grad,
                     int walls, cudaStream_t st)
 {
-    if (grad == 0) k_dt_grad<0><<<nblk(m.n_grad), 256, 0, st>>>(m, q, dt, gx, gy, prm, gam, want_grad, walls);
-    else k_dt_grad<1><<<nblk(m.n_grad), 256, 0, st>>>(m, q, dt, gx, gy, prm, gam, want_grad, walls);
+    if (grad == 0) k_dt_grad<0><<<nblk(m.n_grad, AFX_DTG_THREADS), AFX_DTG_THREADS, 0, st>>>(m, q, dt, gx, gy, prm, gam, want_grad, walls);
+    else k_dt_grad<1><<<nblk(m.n_grad, AFX_DTG_THREADS), AFX_DTG_THREADS, 0, st>>>(m, q, dt, gx, gy, prm, gam, want_grad, walls);
 }
 static void limiter(const DevMesh& m, const d4* qk, const d4* gx, const d4* gy, d4* lim, double k, int walls, uint32_t lo1, uint32_t n1,
                     uint32_t lo2, uint32_t n2, cudaStream_t st)

@@ -154,7 +154,8 @@ def main():
     scaling = "weak" if a.workload is None else "strong (fixed mesh: %s)" % workload  # an explicit workload is cut into N pieces
     config = {"workload": workload, "scheme": "explicit 3-stage RK, 2nd order MUSCL, Green-Gauss, Venkatakrishnan k=5",
               "viscosity": "spallart-allmaras (reference semantics: Roe flux + no-slip wall + gradients, SURVEY F1/F2)",
-              "cfl": CFL, "relaxation": RELAX, "l2": "working set > 126 MB L2 (inputs larger than L2, no flush)"}
+              "cfl": CFL, "relaxation": RELAX,
+              "l2": "working set > 126 MB L2 (inputs larger than L2, no flush); the solver pins its gradient arrays in L2 when they fit (1M cells: 64 MB)"}
 
     if a.impl == "reference":
         if rank != 0:
