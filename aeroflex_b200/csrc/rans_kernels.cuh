@@ -34,6 +34,16 @@
 namespace afx {
 namespace AFX_NS {
 
+// Programmatic dependent launch: the four kernels of the explicit iteration are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so the CTAs of kernel k+1 start as the last wave of kernel k
+// drains, read their STATIC inputs (connectivity, geometry) and only then wait for kernel k to complete.  Anything a
+// predecessor writes is read after pdl_wait() and through plain (coherent) loads: the pointers to solver state carry
+// no __restrict__ in these kernels, because a dependent CTA can be resident while an older kernel still runs on its SM and
+// ld.global.nc may then serve lines that were cached before the predecessor's writes.  Kernels launched without the
+// attribute see both calls as no-ops.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // spectral radius c + |V.n| of one state, solver.h:329-336, split into the part that belongs to the cell -- the speed
 // of sound, one square root (and in strict mode the division 0.5/rho) -- and the part that belongs to the face.  The
 // split evaluates exactly the reference's expressions, so the sum is bit-identical to computing both per face.
@@ -71,16 +81,13 @@ __device__ __forceinline__ double spectral_radius(const d4& q, const CellSound& 
 // least-squares (470-513).  Source state is the iteration-start q.
 // ---------------------------------------------------------------------------
 template <int GRAD>
-__global__ void __launch_bounds__(AFX_DTG_THREADS, AFX_DTG_MINB) k_dt_grad(DevMesh m, d4* __restrict__ q, double* __restrict__ dt,
-                                                 d4* __restrict__ gx, d4* __restrict__ gy, const double* __restrict__ prm,
+__global__ void __launch_bounds__(AFX_DTG_THREADS, AFX_DTG_MINB) k_dt_grad(DevMesh m, d4* q, double* dt,
+                                                 d4* gx, d4* gy, const double* __restrict__ prm,
                                                  double gam, int want_grad, int walls)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m.n_grad) return;
-    const d4 qi = q[i];
-    const CellSound si = cell_sound(qi, gam);  // once per cell instead of once per face
-    double dsum = 0;
-    d4 ax = mk4(0, 0, 0, 0), ay = mk4(0, 0, 0, 0);
+    pdl_launch_dependents();
     uint32_t nbv[4];
     d4 geo[4];
 #pragma unroll
@@ -88,6 +95,11 @@ __global__ void __launch_bounds__(AFX_DTG_THREADS, AFX_DTG_MINB) k_dt_grad(DevMe
         nbv[s] = m.cnb[(size_t)s * m.N + i];
         geo[s] = m.cgeo[(size_t)s * m.N + i];
     }
+    pdl_wait();  // the state comes from the previous kernel
+    const d4 qi = q[i];
+    const CellSound si = cell_sound(qi, gam);  // once per cell instead of once per face
+    double dsum = 0;
+    d4 ax = mk4(0, 0, 0, 0), ay = mk4(0, 0, 0, 0);
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
         const uint32_t v = nbv[s];
@@ -237,16 +249,15 @@ __device__ __forceinline__ d4 limiter_value(const d4& qi, const d4& lo, const d4
     return l;
 }
 
-__global__ void __launch_bounds__(256, AFX_LIM_MINB) k_limiter(DevMesh m, const d4* __restrict__ qk, const d4* __restrict__ gx,
-                                                 const d4* __restrict__ gy, d4* __restrict__ lim, double limiter_k, int walls,
+__global__ void __launch_bounds__(256, AFX_LIM_MINB) k_limiter(DevMesh m, const d4* qk, const d4* gx,
+                                                 const d4* gy, d4* lim, double limiter_k, int walls,
                                                  uint32_t lo1, uint32_t n1, uint32_t lo2, uint32_t n2)
 {
     // cells [lo1, lo1+n1) and [lo2, lo2+n2): a partitioned run limits its interior cells while the halo is in flight
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n1 + n2) return;
     const uint32_t i = t < n1 ? lo1 + t : lo2 + (t - n1);
-    const d4 qi = qk[i];
-    d4 lo = qi, hi = qi;
+    pdl_launch_dependents();
     uint32_t nbs[4];
     double2 dxy[4];
 #pragma unroll
@@ -254,6 +265,10 @@ __global__ void __launch_bounds__(256, AFX_LIM_MINB) k_limiter(DevMesh m, const 
         nbs[s] = m.cnb[(size_t)s * m.N + i];
         dxy[s] = m.cdxy[(size_t)s * m.N + i];
     }
+    const double area_i = m.area[i];
+    pdl_wait();  // stage state and gradients come from the previous kernels
+    const d4 qi = qk[i];
+    d4 lo = qi, hi = qi;
     unsigned valid = 0;
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
@@ -270,7 +285,7 @@ __global__ void __launch_bounds__(256, AFX_LIM_MINB) k_limiter(DevMesh m, const 
         lo.x = dmin2(lo.x, qj.x); lo.y = dmin2(lo.y, qj.y); lo.z = dmin2(lo.z, qj.z); lo.w = dmin2(lo.w, qj.w);
         hi.x = dmax2(hi.x, qj.x); hi.y = dmax2(hi.y, qj.y); hi.z = dmax2(hi.z, qj.z); hi.w = dmax2(hi.w, qj.w);
     }
-    lim[i] = limiter_value(qi, lo, hi, gx[i], gy[i], dxy, valid, limiter_k3a(m.area[i], limiter_k));
+    lim[i] = limiter_value(qi, lo, hi, gx[i], gy[i], dxy, valid, limiter_k3a(area_i, limiter_k));
 }
 
 // ---------------------------------------------------------------------------
@@ -281,22 +296,25 @@ __global__ void __launch_bounds__(256, AFX_LIM_MINB) k_limiter(DevMesh m, const 
 // iteration-start q.
 // ---------------------------------------------------------------------------
 template <int SECOND, int VISC, int UNIFORM>
-__global__ void __launch_bounds__(256, AFX_FLUX_MINB) k_flux(DevMesh m, const d4* __restrict__ qk, const d4* __restrict__ q0,
-                                              const d4* __restrict__ gx, const d4* __restrict__ gy,
-                                              const d4* __restrict__ lim, d4* __restrict__ flux, GasC g, d4 qfar)
+__global__ void __launch_bounds__(256, AFX_FLUX_MINB) k_flux(DevMesh m, const d4* qk, const d4* q0,
+                                              const d4* gx, const d4* gy,
+                                              const d4* lim, d4* flux, GasC g, d4 qfar)
 {
     const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= m.e_flux) return;
+    pdl_launch_dependents();
     const uint2 fc = m.fcells[f];
     const d4 gA = m.fgA[f];
     const int kind = m.fkind[f];
+    d4 gB = mk4(0, 0, 0, 0);
+    if (SECOND && !UNIFORM) gB = m.fgB[f];
+    pdl_wait();  // states, gradients, limiters come from the previous kernels
     d4 qL, qR;
     if (UNIFORM) { qL = qfar; qR = qfar; }
     else { qL = qk[fc.x]; qR = qk[fc.y]; }
     d4 gL0, gL1, gR0, gR1;
     if ((SECOND && !UNIFORM) || VISC == 1) { gL0 = gx[fc.x]; gL1 = gy[fc.x]; gR0 = gx[fc.y]; gR1 = gy[fc.y]; }
     if (SECOND && !UNIFORM) {  // solver.h:774-781
-        const d4 gB = m.fgB[f];
         const d4 lL = lim[fc.x], lR = lim[fc.y];
         qL.x = qL.x + (gL0.x * gB.x + gL1.x * gB.y) * lL.x;
         qL.y = qL.y + (gL0.y * gB.x + gL1.y * gB.y) * lL.y;
@@ -382,21 +400,26 @@ __device__ __forceinline__ void block_norm_accumulate(double v, const NormOut& n
 // and stores the vector (qW or rhs).
 // ---------------------------------------------------------------------------
 template <int MODE, int LAST>
-__global__ void __launch_bounds__(256) k_gather_update(DevMesh m, const d4* __restrict__ flux,
+__global__ void __launch_bounds__(256) k_gather_update(DevMesh m, const d4* flux,
                                                        const d4* q, const d4* qk_in,
-                                                       d4* qk_out, const double* __restrict__ dt,
-                                                       d4* __restrict__ qW, double alpha, const double* __restrict__ prm,
+                                                       d4* qk_out, const double* dt,
+                                                       d4* qW, double alpha, const double* __restrict__ prm,
                                                        int walls, NormOut no, uint32_t lo, uint32_t hi, PushArgs push)
 {
     const uint32_t i = lo + blockIdx.x * blockDim.x + threadIdx.x;
     double nrm = 0;
+    pdl_launch_dependents();
+    uint32_t bnd[4] = {CF_NONE, CF_NONE, CF_NONE, CF_NONE};
+    if (i < hi) {
+#pragma unroll
+        for (int s = 0; s < 4; ++s) bnd[s] = m.cf[(size_t)s * m.N + i];
+    }
+    pdl_wait();  // the fluxes come from the previous kernel
     if (i < hi) {
         d4 r = mk4(0, 0, 0, 0);
-        uint32_t bnd[4];
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
-            const uint32_t cfv = m.cf[(size_t)s * m.N + i];
-            bnd[s] = cfv;
+            const uint32_t cfv = bnd[s];
             if (cfv == CF_NONE) continue;
             const d4 fl = flux[cfv & CF_ID];
             if (cfv & CF_SIDE) { r.x += fl.x; r.y += fl.y; r.z += fl.z; r.w += fl.w; }
@@ -672,23 +695,41 @@ namespace launch {
 
 inline unsigned nblk(size_t n, unsigned bs = 256) { return (unsigned)((n + bs - 1) / bs); }
 
+// AFX_PDL=0 turns programmatic dependent launch off (plain stream order between the kernels)
+inline bool pdl_on()
+{
+    static const bool on = [] { const char* e = getenv("AFX_PDL"); return !(e && e[0] == '0'); }();
+    return on;
+}
+template <class... KArgs, class... Args>
+static void launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, cudaStream_t st, Args&&... args)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_on() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 static void dt_grad(int grad, const DevMesh& m, d4* q, double* dt, d4* gx, d4* gy, const double* prm, double gam, int want_grad,
                     int walls, cudaStream_t st)
 {
-    if (grad == 0) k_dt_grad<0><<<nblk(m.n_grad, AFX_DTG_THREADS), AFX_DTG_THREADS, 0, st>>>(m, q, dt, gx, gy, prm, gam, want_grad, walls);
-    else k_dt_grad<1><<<nblk(m.n_grad, AFX_DTG_THREADS), AFX_DTG_THREADS, 0, st>>>(m, q, dt, gx, gy, prm, gam, want_grad, walls);
+    if (grad == 0) launch_pdl(k_dt_grad<0>, nblk(m.n_grad, AFX_DTG_THREADS), AFX_DTG_THREADS, st, m, q, dt, gx, gy, prm, gam, want_grad, walls);
+    else launch_pdl(k_dt_grad<1>, nblk(m.n_grad, AFX_DTG_THREADS), AFX_DTG_THREADS, st, m, q, dt, gx, gy, prm, gam, want_grad, walls);
 }
 static void limiter(const DevMesh& m, const d4* qk, const d4* gx, const d4* gy, d4* lim, double k, int walls, uint32_t lo1, uint32_t n1,
                     uint32_t lo2, uint32_t n2, cudaStream_t st)
 {
     if (n1 + n2 == 0) return;
-    k_limiter<<<nblk(n1 + n2), 256, 0, st>>>(m, qk, gx, gy, lim, k, walls, lo1, n1, lo2, n2);
+    launch_pdl(k_limiter, nblk(n1 + n2), 256, st, m, qk, gx, gy, lim, k, walls, lo1, n1, lo2, n2);
 }
 static void flux(int second, int visc, int uniform, const DevMesh& m, const d4* qk, const d4* q0, const d4* gx, const d4* gy,
                  const d4* lim, d4* fl, const GasC& g, d4 qfar, cudaStream_t st)
 {
     const unsigned nb = nblk(m.e_flux);
-#define AFX_FLUX(S, V, U) k_flux<S, V, U><<<nb, 256, 0, st>>>(m, qk, q0, gx, gy, lim, fl, g, qfar)
+#define AFX_FLUX(S, V, U) launch_pdl(k_flux<S, V, U>, nb, 256, st, m, qk, q0, gx, gy, lim, fl, g, qfar)
     if (uniform) { if (visc) AFX_FLUX(0, 1, 1); else AFX_FLUX(0, 0, 1); }
     else if (second) { if (visc) AFX_FLUX(1, 1, 0); else AFX_FLUX(1, 0, 0); }
     else { if (visc) AFX_FLUX(0, 1, 0); else AFX_FLUX(0, 0, 0); }
@@ -704,7 +745,7 @@ static void gather(int mode, int last, const DevMesh& m, uint32_t lo, uint32_t h
     if (push_in) push = *push_in;
     const unsigned nb = nblk(hi - lo);
     if (no.blk_total == 0) { no.blk_off = 0; no.blk_total = nb; }
-#define AFX_G(M, L) k_gather_update<M, L><<<nb, 256, 0, st>>>(m, fl, q, qk_in, qk_out, dt, vec_out, alpha, prm, walls, no, lo, hi, push)
+#define AFX_G(M, L) launch_pdl(k_gather_update<M, L>, nb, 256, st, m, fl, q, qk_in, qk_out, dt, vec_out, alpha, prm, walls, no, lo, hi, push)
     if (mode == 0) { if (last) AFX_G(0, 1); else AFX_G(0, 0); }
     else if (mode == 1) AFX_G(1, 1);
     else AFX_G(2, 1);
