@@ -34,8 +34,12 @@ struct Prolongation {  // rows of the sparse (4m x 4n) mapper, one weight per (f
 };
 
 // inverse-distance prolongation, multigrid.h:100-178: coarse cell j contributes to fine cell i when
-// d2 < 2 A_j, weight 1/max(0.1 sqrt(A_j), d), rows normalised by their sum (accumulated over ascending j)
-inline Prolongation make_prolongation(const mesh& coarse, const mesh& fine) {
+// d2 < 2 A_j, weight 1/max(0.1 sqrt(A_j), d), rows normalised by their sum (accumulated over ascending j).
+// The reference tests all m x n pairs; make_prolongation finds the same pairs through a k-d tree over the coarse
+// centres whose nodes carry their bounding box and the largest 2 A_j below them: a node is skipped when the
+// point is at least that far from the box, which -- rounding being monotonic -- never drops a pair the reference keeps.
+// Rows are sorted by j and summed in that order, so weights and q_fine are bit-identical to the reference's.
+inline Prolongation make_prolongation_bruteforce(const mesh& coarse, const mesh& fine) {
     const long m = (long)fine.cellsAreas.size(), n = (long)coarse.cellsAreas.size();
     std::vector<std::vector<std::pair<uint32_t, double>>> rows((size_t)m);
 #pragma omp parallel for schedule(dynamic, 64)
@@ -54,6 +58,96 @@ inline Prolongation make_prolongation(const mesh& coarse, const mesh& fine) {
             }
         }
         for (auto& e : r) e.second = e.second / scale;
+    }
+    Prolongation P;
+    P.rows.resize((size_t)m);
+    for (long i = 0; i < m; ++i) {
+        P.rows[(size_t)i].begin = (uint32_t)P.col.size();
+        for (auto& e : rows[(size_t)i]) { P.col.push_back(e.first); P.w.push_back(e.second); }
+        P.rows[(size_t)i].end = (uint32_t)P.col.size();
+    }
+    return P;
+}
+
+struct CoarseTree {  // k-d tree over the coarse cell centres
+    struct Node { double x0, x1, y0, y1, r2max; uint32_t lo, hi; int left, right; };
+    std::vector<uint32_t> idx;
+    std::vector<Node> nodes;
+    const mesh& c;
+    explicit CoarseTree(const mesh& coarse) : c(coarse) {
+        idx.resize(c.cellsAreas.size());
+        for (size_t k = 0; k < idx.size(); ++k) idx[k] = (uint32_t)k;
+        nodes.reserve(idx.size() / 4 + 16);
+        if (!idx.empty()) build(0, (uint32_t)idx.size());
+    }
+    int build(uint32_t lo, uint32_t hi) {
+        Node nd{1e300, -1e300, 1e300, -1e300, 0., lo, hi, -1, -1};
+        for (uint32_t k = lo; k < hi; ++k) {
+            const uint32_t j = idx[k];
+            nd.x0 = std::min(nd.x0, c.cellsCentersX[j]); nd.x1 = std::max(nd.x1, c.cellsCentersX[j]);
+            nd.y0 = std::min(nd.y0, c.cellsCentersY[j]); nd.y1 = std::max(nd.y1, c.cellsCentersY[j]);
+            nd.r2max = std::max(nd.r2max, 2 * c.cellsAreas[j]);
+        }
+        const int me = (int)nodes.size();
+        nodes.push_back(nd);
+        if (hi - lo > 16) {
+            const bool by_x = (nd.x1 - nd.x0) >= (nd.y1 - nd.y0);
+            const uint32_t mid = lo + (hi - lo) / 2;
+            std::nth_element(idx.begin() + lo, idx.begin() + mid, idx.begin() + hi, [&](uint32_t a, uint32_t b) {
+                return by_x ? c.cellsCentersX[a] < c.cellsCentersX[b] : c.cellsCentersY[a] < c.cellsCentersY[b];
+            });
+            const int l = build(lo, mid), r = build(mid, hi);
+            nodes[(size_t)me].left = l; nodes[(size_t)me].right = r;
+        }
+        return me;
+    }
+    // every coarse cell j with |x - x_j|^2 < 2 A_j, unordered
+    void query(double x, double y, std::vector<uint32_t>& out) const {
+        if (nodes.empty()) return;
+        int stack[64], top = 0;
+        stack[top++] = 0;
+        while (top) {
+            const Node& nd = nodes[(size_t)stack[--top]];
+            const double dx = x < nd.x0 ? nd.x0 - x : (x > nd.x1 ? x - nd.x1 : 0.), dy = y < nd.y0 ? nd.y0 - y : (y > nd.y1 ? y - nd.y1 : 0.);
+            if (dx * dx + dy * dy >= nd.r2max) continue;
+            if (nd.left < 0) {
+                for (uint32_t k = nd.lo; k < nd.hi; ++k) {
+                    const uint32_t j = idx[k];
+                    const double xj = c.cellsCentersX[j], yj = c.cellsCentersY[j];
+                    const double d2 = (x - xj) * (x - xj) + (y - yj) * (y - yj);
+                    if (d2 < 2 * c.cellsAreas[j]) out.push_back(j);
+                }
+            } else { stack[top++] = nd.left; stack[top++] = nd.right; }
+        }
+    }
+};
+
+inline Prolongation make_prolongation(const mesh& coarse, const mesh& fine) {
+    const long m = (long)fine.cellsAreas.size();
+    const CoarseTree tree(coarse);
+    std::vector<std::vector<std::pair<uint32_t, double>>> rows((size_t)m);
+#pragma omp parallel
+    {
+        std::vector<uint32_t> js;
+#pragma omp for schedule(dynamic, 256)
+        for (long i = 0; i < m; ++i) {
+            const double xi = fine.cellsCentersX[(size_t)i], yi = fine.cellsCentersY[(size_t)i];
+            js.clear();
+            tree.query(xi, yi, js);
+            std::sort(js.begin(), js.end());  // the reference's j loop is ascending: same summation order
+            double scale = 0;
+            auto& r = rows[(size_t)i];
+            r.reserve(js.size());
+            for (const uint32_t j : js) {
+                const double xj = coarse.cellsCentersX[j], yj = coarse.cellsCentersY[j];
+                const double d2 = (xi - xj) * (xi - xj) + (yi - yj) * (yi - yj);
+                const double r2 = coarse.cellsAreas[j];
+                const double si = 1 / std::max(0.1 * std::sqrt(r2), std::sqrt(d2));
+                scale += si;
+                r.emplace_back(j, si);
+            }
+            for (auto& e : r) e.second = e.second / scale;
+        }
     }
     Prolongation P;
     P.rows.resize((size_t)m);

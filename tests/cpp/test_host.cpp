@@ -1,6 +1,7 @@
 // CPU-side checks of the C++ host adapter (no GPU needed): conf.ini parsing and the FMG prolongation.
 //   test_host conf <conf.ini> <roundtrip.ini>         -> prints the parsed rans settings
 //   test_host prolong <coarse.msh> <fine.msh> <q.bin> <out.bin>
+//   test_host prolong_check <coarse.msh> <fine.msh>   -> tree search vs all-pairs search
 #include <cstdio>
 #include <fstream>
 #include <iostream>
@@ -46,6 +47,14 @@ int main(int argc, char** argv) {
             std::ofstream(argv[5], std::ios::binary).write(reinterpret_cast<const char*>(qf.data()), (std::streamsize)(qf.size() * sizeof(double)));
             std::printf("prolong rows=%zu nnz=%zu\n", P.rows.size(), P.w.size());
             return 0;
+        }
+        if (mode == "prolong_check" && argc > 3) {  // k-d tree search against the reference's all-pairs loop: identical rows
+            rans::mesh coarse(argv[2]), fine(argv[3]);
+            const rans::Prolongation A = rans::make_prolongation(coarse, fine), B = rans::make_prolongation_bruteforce(coarse, fine);
+            bool same = A.col == B.col && A.w == B.w && A.rows.size() == B.rows.size();
+            for (size_t i = 0; same && i < A.rows.size(); ++i) same = A.rows[i].begin == B.rows[i].begin && A.rows[i].end == B.rows[i].end;
+            std::printf("prolong_check rows=%zu nnz=%zu identical=%d\n", A.rows.size(), A.w.size(), (int)same);
+            return same ? 0 : 1;
         }
     } catch (std::exception& e) {
         std::printf("EXCEPTION %s\n", e.what());

@@ -91,6 +91,16 @@ def test_fmg_prolongation_matches_reference(afx, exes, tmp_path):
     assert np.array_equal(qf, g["q_fine"])
 
 
+def test_fmg_prolongation_tree_search_equals_all_pairs(afx, exes, tmp_path):
+    """the k-d tree search must find exactly the pairs of the reference's O(m n) loop, in the same order."""
+    for k, dims in enumerate([(64, 40, 16), (128, 80, 32), (96, 60, 0)]):
+        afx.Mesh.synth_omesh(*dims, 150.0).write_msh(str(tmp_path / ("p%d.msh" % k)))
+    for a, b in ((0, 1), (2, 1), (1, 0)):  # coarse -> fine, quads -> mixed, and fine -> coarse for good measure
+        r = subprocess.run([exes["test_host"], "prolong_check", str(tmp_path / ("p%d.msh" % a)), str(tmp_path / ("p%d.msh" % b))],
+                           capture_output=True, text=True)
+        assert r.returncode == 0 and "identical=1" in r.stdout, r.stdout
+
+
 def test_cli_fails_loudly_without_gpu(afx, exes, tmp_path):
     if afx.device_count() > 0:
         pytest.skip("a GPU is visible")
