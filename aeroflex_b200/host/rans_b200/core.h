@@ -44,6 +44,24 @@ struct boundary_condition {  // core.h:112-115
     boundary_variables vars_far;
 };
 
+class solution {  // core.h:119-164: primitive variables of cell i from the conservative state
+    const std::vector<double>& q;
+    const gas& g;
+public:
+    solution(const std::vector<double>& q_, const gas& g_) : q(q_), g(g_) {}
+    double gamma() const { return g.gamma; }
+    double rho(int i) const { return q[4 * (size_t)i]; }
+    double rhou(int i) const { return q[4 * (size_t)i + 1]; }
+    double rhov(int i) const { return q[4 * (size_t)i + 2]; }
+    double rhoe(int i) const { return q[4 * (size_t)i + 3]; }
+    double p(int i) const { return (g.gamma - 1) * (rhoe(i) - 0.5 / rho(i) * (rhou(i) * rhou(i) + rhov(i) * rhov(i))); }
+    double u(int i) const { return rhou(i) / rho(i); }
+    double v(int i) const { return rhov(i) / rho(i); }
+    double T(int i) const { return p(i) / (g.R * rho(i)); }
+    double c(int i) const { return std::sqrt(g.gamma * p(i) / rho(i)); }
+    double mach(int i) const { return std::sqrt(rhou(i) * rhou(i) + rhov(i) * rhov(i)) / (rho(i) * c(i)); }
+};
+
 struct Settings {  // core.h:166-232
     gas g;
     std::vector<std::string> meshes;

@@ -104,6 +104,7 @@ public:
 
     // host mirror of the state vector, 4 doubles per cell, real cells then ghosts (solver.h:255-257)
     std::vector<double>& get_q() { check(afx_rans_get_q(h_.get(), q_host_.data())); return q_host_; }
+    solution get_solution() { return solution(get_q(), g); }  // solver.h:693-697, on the refreshed host mirror
     void set_q(const std::vector<double>& q) {
         if (q.size() != q_host_.size()) throw std::invalid_argument("state vector has the wrong length");
         check(afx_rans_set_q(h_.get(), q.data()));

@@ -20,6 +20,10 @@ public:
     // where <airfoil>_coarse.msh / <airfoil>_mid.msh live; the reference hard-codes this relative path (rans.h:84-85)
     std::string mesh_dir = "../../../../examples/rans/";
     bool verbose = true;
+    // the reference writes <airfoil>_<alpha>.vtu into the working directory after every angle (rans.h:103); off by default
+    // here (a 64-angle sweep is 64 files), on with save_vtu -- same file names, under vtu_dir
+    bool save_vtu = false;
+    std::string vtu_dir = "";
 
     explicit Rans(GUIHandler& gui) : gui(gui) {}
 
@@ -52,6 +56,7 @@ public:
             db.cl.push_back(wp.cl);
             db.cd.push_back(wp.cd);
             db.cmy.push_back(wp.cm);
+            if (save_vtu) save(vtu_dir + airfoil + "_" + std::to_string(alpha) + ".vtu", s);  // rans.h:103
             if (gui.signal.stop) break;
         }
     }
@@ -60,6 +65,20 @@ public:
         iters = 0;
         if (settings.solver_type() == "implicit") run_airfoil<implicitSolver>(airfoil, db);
         else if (settings.solver_type() == "explicit") run_airfoil<explicitSolver>(airfoil, db);
+    }
+
+    template <class T>
+    void run() {  // rans.h:68-76: multigrid over settings.meshes, then the VTU file
+        input();
+        multigrid<T> multi(ms, settings, gui, residuals, iters, profile);
+        multi.verbose = verbose;
+        rans::solver& s = multi.run(true);
+        save(settings.outfilename, s);
+        std::cout << "Saved results to file " << settings.outfilename << "\n" << std::endl;
+    }
+    void solve() {  // rans.h:108-114
+        if (settings.solver_type() == "implicit") run<implicitSolver>();
+        else if (settings.solver_type() == "explicit") run<explicitSolver>();
     }
 
     template <class T>

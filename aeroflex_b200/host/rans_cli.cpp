@@ -1,5 +1,5 @@
 // rans_cli.cpp -- the RANS leg of AeroFLEX's CLI mode (reference: src/aeroflex/src/app.cpp:168-176, 829-854):
-//   rans_cli -i conf.ini [-m mesh_dir] [-a airfoil] [--math strict|fast] [--device d] [--shard i/n] [-q]
+//   rans_cli -i conf.ini [-m mesh_dir] [-a airfoil] [--math strict|fast] [--device d] [--shard i/n] [--vtu dir/] [-q]
 // --shard i/n solves the i-th of n contiguous chunks of the alpha list (BASELINE config 5: a 64-angle polar sweep is
 // n independent warm-start chains, one per GPU, no communication; scripts/polar_sweep.sh launches them).
 // reads the [rans-*] sections of an AeroFLEX conf.ini, runs rans.compute_alphas() and rans.solve_airfoil() on the GPU
@@ -14,6 +14,7 @@
 int main(int argc, char** argv) {
     std::string conf, mesh_dir = "../../../../examples/rans/", airfoil = "naca0012q", math;
     bool quiet = false;
+    std::string vtu_dir;
     int shard_i = 0, shard_n = 1;
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
@@ -22,6 +23,7 @@ int main(int argc, char** argv) {
         else if (a == "-a" && i + 1 < argc) airfoil = argv[++i];
         else if (a == "--math" && i + 1 < argc) math = argv[++i];
         else if (a == "-q") quiet = true;
+        else if (a == "--vtu" && i + 1 < argc) vtu_dir = argv[++i];  // write <airfoil>_<alpha>.vtu per angle (rans.h:103) into this directory
         else if (a == "--device" && i + 1 < argc) rans::default_device() = std::atoi(argv[++i]);
         else if (a == "--shard" && i + 1 < argc) { if (std::sscanf(argv[++i], "%d/%d", &shard_i, &shard_n) != 2 || shard_n < 1 || shard_i < 0 || shard_i >= shard_n) { std::fprintf(stderr, "bad --shard\n"); return 2; } }
     }
@@ -36,6 +38,7 @@ int main(int argc, char** argv) {
         rans.settings.import_config_file(io);
         rans.mesh_dir = mesh_dir;
         rans.verbose = !quiet;
+        if (!vtu_dir.empty()) { rans.save_vtu = true; rans.vtu_dir = vtu_dir; }
         rans.compute_alphas();
         database::airfoil db;
         {  // this process's contiguous chunk of the alpha list

@@ -1,6 +1,7 @@
 // CPU-side checks of the C++ host adapter (no GPU needed): conf.ini parsing and the FMG prolongation.
 //   test_host conf <conf.ini> <roundtrip.ini>         -> prints the parsed rans settings
 //   test_host prolong <coarse.msh> <fine.msh> <q.bin> <out.bin>
+//   test_host walldist <mesh.msh> [wall bc_type]      -> tree search vs all-pairs scan
 //   test_host prolong_check <coarse.msh> <fine.msh>   -> tree search vs all-pairs search
 #include <cstdio>
 #include <fstream>
@@ -54,6 +55,33 @@ int main(int argc, char** argv) {
             bool same = A.col == B.col && A.w == B.w && A.rows.size() == B.rows.size();
             for (size_t i = 0; same && i < A.rows.size(); ++i) same = A.rows[i].begin == B.rows[i].begin && A.rows[i].end == B.rows[i].end;
             std::printf("prolong_check rows=%zu nnz=%zu identical=%d\n", A.rows.size(), A.w.size(), (int)same);
+            return same ? 0 : 1;
+        }
+        if (mode == "walldist" && argc > 2) {  // k-d tree wall distance against the reference's all-pairs scan (mesh.h:794-830)
+            rans::mesh m(argv[2]);
+            std::map<std::string, rans::boundary_condition> bcs;
+            bcs["wall"].bc_type = argc > 3 ? argv[3] : "wall";
+            bcs["farfield"].bc_type = "farfield";
+            m.compute_wall_dist(bcs);
+            bool same = true;
+            double dmax = 0;
+            for (size_t i = 0; i < m.cellsAreas.size(); ++i) {
+                double mind = 1;
+                bool first = true;
+                for (size_t j = 0; j < m.boundaryEdges.size(); ++j) {
+                    const std::string& t = bcs.at(m.boundaryEdgesPhysicals[j]).bc_type;
+                    if (t == "wall" || t == "slip-wall") {
+                        const double dx = m.cellsCentersX[i] - m.edgesCentersX[m.boundaryEdges[j]], dy = m.cellsCentersY[i] - m.edgesCentersY[m.boundaryEdges[j]];
+                        const double d = std::sqrt(dx * dx + dy * dy);
+                        mind = first ? d : std::min(mind, d);
+                        first = false;
+                    }
+                }
+                same = same && mind == m.wall_dist[i];
+                dmax = std::max(dmax, m.wall_dist[i]);
+            }
+            std::printf("walldist cells=%zu nodes=%zu max=%.6g identical=%d tri0=%d n0=%u,%u,%u,%u\n", m.cellsAreas.size(), m.nodesX.size(), dmax, (int)same,
+                        (int)m.cellsIsTriangle[0], m.cellsNodes(0, 0), m.cellsNodes(0, 1), m.cellsNodes(0, 2), m.cellsNodes(0, 3));
             return same ? 0 : 1;
         }
     } catch (std::exception& e) {

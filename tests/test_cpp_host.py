@@ -101,6 +101,15 @@ def test_fmg_prolongation_tree_search_equals_all_pairs(afx, exes, tmp_path):
         assert r.returncode == 0 and "identical=1" in r.stdout, r.stdout
 
 
+def test_wall_distance_tree_search_equals_all_pairs(afx, exes, tmp_path):
+    """mesh::compute_wall_dist (mesh.h:794-830) through the k-d tree: bit-identical to the reference's N x G scan; no wall -> 1."""
+    afx.Mesh.synth_omesh(128, 80, 32, 150.0).write_msh(str(tmp_path / "w.msh"))
+    r = subprocess.run([exes["test_host"], "walldist", str(tmp_path / "w.msh"), "slip-wall"], capture_output=True, text=True)
+    assert r.returncode == 0 and "identical=1" in r.stdout, r.stdout
+    r = subprocess.run([exes["test_host"], "walldist", str(tmp_path / "w.msh"), "inlet"], capture_output=True, text=True)
+    assert r.returncode == 0 and "identical=1" in r.stdout and "max=1 " in r.stdout, r.stdout
+
+
 def test_cli_fails_loudly_without_gpu(afx, exes, tmp_path):
     if afx.device_count() > 0:
         pytest.skip("a GPU is visible")
@@ -145,3 +154,25 @@ def test_cli_explicit_mode_runs(afx, gpu, exes, tmp_path):
     assert r.returncode == 0, r.stdout[-2000:]
     rows = [[float(v) for v in l.split()[1:]] for l in r.stdout.splitlines() if l.startswith("POLAR")]
     assert len(rows) == 1 and 0.05 < rows[0][1] < 0.2  # CL at 1 degree
+
+
+@pytest.mark.gpu
+def test_cli_writes_reference_layout_vtu(afx, gpu, exes, tmp_path):
+    """save() (post.h:58-180): one <airfoil>_<alpha>.vtu per angle with the reference's arrays, sized by the mid mesh."""
+    H.product_mesh(afx, H.load("naca0012q_coarse_euler_gg_o2")).write_msh(tmp_path / "naca0012q_coarse.msh")
+    mid = H.product_mesh(afx, H.load("naca0012q_mid_mesh"))
+    mid.write_msh(tmp_path / "naca0012q_mid.msh")
+    ini = tmp_path / "conf.ini"
+    ini.write_text(CONF % dict(solver="implicit", tol="1e-4", max_it=50, alpha_end="1.0", start_cfl="40.0"))
+    out = tmp_path / "vtu"
+    out.mkdir()
+    r = subprocess.run([exes["cli"], "-i", str(ini), "-m", str(tmp_path) + "/", "-q", "--vtu", str(out) + "/"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:]
+    files = sorted(os.listdir(out))
+    assert files == ["naca0012q_1.000000.vtu"]  # std::to_string(alpha), rans.h:103
+    txt = (out / files[0]).read_text()
+    assert 'NumberOfCells="%d"' % mid.N in txt
+    for name in ("connectivity", "offsets", "types", "Wall Distance", "Mach", "Density", "Pressure", "Temperature", "Velocity"):
+        assert 'Name="%s"' % name in txt
+    mach = txt.split('Name="Mach" Format="ascii">')[1].split("</DataArray>")[0].split()
+    assert len(mach) == mid.N and 0.0 < min(map(float, mach)) and max(map(float, mach)) < 1.0
