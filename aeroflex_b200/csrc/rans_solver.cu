@@ -1105,9 +1105,7 @@ bool Solver::gmres(const d4* b, d4* x)
 {
     const int m = gmres_restart;
     const size_t stride = NT;
-    double* hh = h_pinned + 48;  // never more than m+2 <= 16?  -> use a heap buffer
     std::vector<double> hbuf((size_t)m + 4);
-    (void)hh;
     CK(cudaMemsetAsync(x, 0, (size_t)NT * sizeof(d4), st));
     last_linear_iters = 0;
     // r = M^-1 b
