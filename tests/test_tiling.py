@@ -54,3 +54,18 @@ def test_tiles_beyond_the_limits_are_cut_in_two(afx, order_env):
     assert len(cut) > len(free) and cut[:, 0].sum() == m.N
     assert (cut[:, 0] + cut[:, 1] + cut[:, 2]).max() <= lim[0] and (cut[:, 0] + cut[:, 1]).max() <= lim[1]
     assert smem_cut < smem_free
+
+
+@pytest.mark.parametrize("nranks", [2, 3])
+def test_tile_plan_of_partitioned_meshes(afx, order_env, nranks):
+    """A rank's tiles cover exactly its owned cells; the send layer (cells some peer needs) is tiled apart from the
+    interior so that it can be advanced and pushed first.  The plan is verified against the local connectivity."""
+    os.environ["AFX_ORDER"] = "graph"
+    mesh = afx.Mesh.synth_omesh(128, 80, 32, 150.0)
+    for r in range(nranks):
+        p = afx.Partition(mesh, nranks, r)
+        per, smem = afx.tiling_plan(p, 96)
+        assert per[:, 0].sum() == p.n_own and per[:, 0].max() <= 96
+        n_front = len(np.unique(np.concatenate([send for (_, send, _) in p.peers])))
+        # the first tiles hold the send layer and nothing else: some prefix of the tile sizes sums to it
+        assert n_front in np.cumsum(per[:, 0])
