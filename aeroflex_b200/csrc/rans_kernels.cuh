@@ -303,11 +303,13 @@ __global__ void __launch_bounds__(256, AFX_FLUX_MINB) k_flux(DevMesh m, const d4
     const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= m.e_flux) return;
     pdl_launch_dependents();
-    const uint2 fc = m.fcells[f];
-    const d4 gA = m.fgA[f];
-    const int kind = m.fkind[f];
-    d4 gB = mk4(0, 0, 0, 0);
-    if (SECOND && !UNIFORM) gB = m.fgB[f];
+    // one 64-byte record per face: normal, length, both centre offsets, the two cells and the kind
+    const d4 r0 = m.frec[2 * (size_t)f], r1 = m.frec[2 * (size_t)f + 1];
+    const unsigned long long cw = (unsigned long long)__double_as_longlong(r1.w);
+    const uint2 fc = make_uint2((uint32_t)cw & CF_ID, (uint32_t)(cw >> 32));
+    const int kind = (int)(((uint32_t)cw) >> 30);
+    const d4 gA = mk4(r0.x, r0.y, r0.z, 0.);
+    const d4 gB = mk4(r0.w, r1.x, r1.y, r1.z);
     pdl_wait();  // states, gradients, limiters come from the previous kernels
     d4 qL, qR;
     if (UNIFORM) { qL = qfar; qR = qfar; }
@@ -642,6 +644,16 @@ __global__ void __launch_bounds__(256) k_halo_wait_scatter(WaitArgs a, d4* __res
     field[a.recv_idx[k]] = v;
 }
 
+// kind bits of the face records from the face kinds set by set_bcs
+__global__ void k_face_record_kinds(d4* __restrict__ frec, const uint8_t* __restrict__ fkind, uint32_t E)
+{
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= E) return;
+    unsigned long long cw = (unsigned long long)__double_as_longlong(frec[2 * (size_t)f + 1].w);
+    cw = (cw & ~(3ull << 30)) | ((unsigned long long)(fkind[f] & 3u) << 30);
+    frec[2 * (size_t)f + 1].w = __longlong_as_double((long long)cw);
+}
+
 // small utilities -----------------------------------------------------------
 __global__ void k_fill_cells(d4* __restrict__ q, uint32_t n, d4 v)
 {
@@ -765,6 +777,10 @@ static void fill_cells(d4* q, uint32_t n, d4 v, cudaStream_t st) { k_fill_cells<
 static void ghost_fill(d4* q, const uint32_t* bghost, const uint32_t* bowner, const d4* bstate, uint32_t G, int from_owner, cudaStream_t st)
 {
     k_ghost_fill<<<nblk(G), 256, 0, st>>>(q, bghost, bowner, bstate, G, from_owner);
+}
+static void face_record_kinds(d4* frec, const uint8_t* fkind, uint32_t E, cudaStream_t st)
+{
+    if (E) k_face_record_kinds<<<nblk(E), 256, 0, st>>>(frec, fkind, E);
 }
 static void ghost_follow(d4* q, const uint32_t* bghost, const uint32_t* bowner, const uint32_t* bface, const uint8_t* fkind, uint32_t G, uint32_t lo,
                          cudaStream_t st)

@@ -146,7 +146,7 @@ struct Solver {
     bool bcs_set = false;
 
     // device geometry
-    DBuf<uint2> fcells; DBuf<d4> fgA, fgB, ftij; DBuf<uint8_t> fkind; DBuf<uint32_t> cf, cnb; DBuf<d4> cgeo; DBuf<double2> cdxy; DBuf<double> area;
+    DBuf<uint2> fcells; DBuf<d4> fgA, fgB, ftij, frec; DBuf<uint8_t> fkind; DBuf<uint32_t> cf, cnb; DBuf<d4> cgeo; DBuf<double2> cdxy; DBuf<double> area;
     DBuf<double> lsqM; DBuf<uint16_t> lsq_perm;
     // shared-memory tiles of the fused stage kernel (tiling.h)
     DBuf<uint4> t_head, t_ctab; DBuf<uint32_t> t_halo, t_face; DBuf<double> t_area, t_k3a; DBuf<double2> t_dxy; DBuf<d4> t_fgeo;
@@ -462,6 +462,19 @@ void Solver::create(const afx_mesh_desc& m, const afx_gas& g, int visc, int dev,
     }
     build_tile_tables(h_cf, h_cnb, h_cdxy, h_area, h_gA);
 
+    {   // the face kernel's 64-byte records (kind bits: set_bcs)
+        std::vector<d4> h_rec((size_t)2 * E);
+#pragma omp parallel for schedule(static)
+        for (int64_t n = 0; n < (int64_t)E; ++n) {
+            const unsigned long long cw = (unsigned long long)h_fc[n].x | ((unsigned long long)h_fc[n].y << 32);
+            double cwd;
+            std::memcpy(&cwd, &cw, 8);
+            h_rec[2 * (size_t)n] = d4{h_gA[n].x, h_gA[n].y, h_gA[n].z, h_gB[n].x};
+            h_rec[2 * (size_t)n + 1] = d4{h_gB[n].y, h_gB[n].z, h_gB[n].w, cwd};
+        }
+        frec.upload(h_rec, st);
+    }
+
     // ---- upload ----
     fcells.upload(h_fc, st); fgA.upload(h_gA, st); fgB.upload(h_gB, st);
     if (viscous_type == 1) ftij.upload(h_t, st);
@@ -521,7 +534,7 @@ void Solver::create(const afx_mesh_desc& m, const afx_gas& g, int visc, int dev,
 
     dm.N = N; dm.G = G; dm.E = E; dm.NT = NT;
     dm.n_upd = n_upd; dm.n_grad = n_grad; dm.e_flux = e_flux;
-    dm.fcells = fcells.p; dm.fgA = fgA.p; dm.fgB = fgB.p; dm.ftij = ftij.p; dm.fkind = fkind.p;
+    dm.fcells = fcells.p; dm.fgA = fgA.p; dm.fgB = fgB.p; dm.ftij = ftij.p; dm.fkind = fkind.p; dm.frec = frec.p;
     dm.cf = cf.p; dm.cnb = cnb.p; dm.cgeo = cgeo.p; dm.cdxy = cdxy.p; dm.area = area.p; dm.lsqM = lsqM.p; dm.lsq_perm = lsq_perm.p;
 }
 
@@ -564,6 +577,7 @@ void Solver::set_bcs(int n_patch, const uint8_t* kinds, const afx_bvars* vars)
     }
     fkind.upload(h_kind, st);
     bstate.upload(h_state, st);
+    kt->face_record_kinds(frec.p, fkind.p, E, st); ++launches;
     if (tiles_ready) { kt->tile_face_kinds(t_fgeo.p, t_face.p, fkind.p, n_tile_faces, st); ++launches; }
     CK(cudaStreamSynchronize(st));
     dm.fkind = fkind.p;

@@ -34,6 +34,7 @@ struct DevMesh {
     const d4* fgB;               // [E] d0x, d0y, d1x, d1y
     const d4* ftij;              // [E] t0, t1, l, - (laminar face-gradient direction, solver.h:369-376)
     const uint8_t* fkind;        // [E]
+    const d4* frec;              // [E][2] the face kernel's record: {nx, ny, len, d0x}, {d0y, d1x, d1y, bits(cell0 | kind << 30, cell1)}
     const uint32_t* cf;          // [4][N]
     const uint32_t* cnb;         // [4][N] the cell across slot s (same slots as cf; CF_NONE where empty) | CF_SIDE | CF_BND like cf
     const d4* cgeo;              // [4][N] {nx, ny, len, w_gg} of the face in slot s: the dt/gradient kernel reads no face record
@@ -148,6 +149,7 @@ struct KernelTable {
     int (*stage_prepare)(size_t smem);  // opt in to the dynamic shared memory on the current device; resident CTAs per SM or <0
     int (*stage_threads)();
     void (*tile_k3a)(const double* area_t, double* k3a_t, size_t n, double limiter_k, cudaStream_t st);  // refresh after set_options
+    void (*face_record_kinds)(d4* frec, const uint8_t* fkind, uint32_t E, cudaStream_t st);  // refresh after set_bcs
     void (*tile_face_kinds)(d4* fgeo_t, const uint32_t* tile_face, const uint8_t* fkind, size_t n, cudaStream_t st);  // refresh after set_bcs
     void (*halo_signal)(const SignalArgs& a, cudaStream_t st);               // tell the peers my send layer is in their buffers
     void (*halo_wait_scatter)(const WaitArgs& a, d4* field, cudaStream_t st); // wait for the peers, then fill my halo cells
