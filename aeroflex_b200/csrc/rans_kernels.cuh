@@ -74,112 +74,7 @@ __device__ __forceinline__ double spectral_radius(const d4& q, const CellSound& 
 #endif
 }
 
-// ---------------------------------------------------------------------------
-// Local time step + gradients of q, one thread per real cell.
-// calc_dt (solver.h:308-356), set_walls_from_internal (289-305, folded in: the
-// owner writes its wall ghosts), calc_gradients Green-Gauss (428-469) or
-// least-squares (470-513).  Source state is the iteration-start q (SURVEY F5).
-// ---------------------------------------------------------------------------
-template <int GRAD>
-__global__ void __launch_bounds__(AFX_DTG_THREADS, AFX_DTG_MINB) k_dt_grad(DevMesh m, d4* q, double* dt,
-                                                 d4* gx, d4* gy, const double* __restrict__ prm,
-                                                 double gam, int want_grad, int walls)
-{
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m.n_grad) return;
-    pdl_launch_dependents();
-    uint32_t nbv[4];
-    d4 geo[4];
-#pragma unroll
-    for (int s = 0; s < 4; ++s) {  // independent coalesced loads first: neighbour | flags and the slot's face geometry
-        nbv[s] = m.cnb[(size_t)s * m.N + i];
-        geo[s] = m.cgeo[(size_t)s * m.N + i];
-    }
-    pdl_wait();  // the state comes from the previous kernel
-    const d4 qi = q[i];
-    const CellSound si = cell_sound(qi, gam);  // once per cell instead of once per face
-    double dsum = 0;
-    d4 ax = mk4(0, 0, 0, 0), ay = mk4(0, 0, 0, 0);
-#pragma unroll
-    for (int s = 0; s < 4; ++s) {
-        const uint32_t v = nbv[s];
-        if (v == CF_NONE) continue;
-        const bool side = v & CF_SIDE;
-        const uint32_t j = v & CF_ID;
-        const d4 gA = geo[s];
-        const int kind = (v & CF_BND) ? (int)m.fkind[m.cf[(size_t)s * m.N + i] & CF_ID] : K_INTERNAL;
-        const bool wall_ghost = walls && (v & CF_BND) && (kind == K_SLIPWALL || kind == K_WALL);
-        if (wall_ghost) q[j] = qi;  // ghost <- owner (set_walls_from_internal)
-        const d4 qj = wall_ghost ? qi : q[j];
-        const d4 qL = side ? qj : qi, qR = side ? qi : qj;  // states of cell0 / cell1
-        const double nx = gA.x, ny = gA.y, len = gA.z;
-        // spectral radius, solver.h:328-345
-        // cell0's radius alone at one-sided (boundary) faces, where this cell is always cell0
-        double eig = spectral_radius(qi, si, nx, ny);
-        if (kind == K_INTERNAL) {
-            const double eig_j = spectral_radius(qj, cell_sound(qj, gam), nx, ny);
-            const double eig_L = side ? eig_j : eig, eig_R = side ? eig : eig_j;
-            eig = (eig_L < eig_R) ? eig_R : eig_L;
-        }
-        dsum += eig * len;
-        if (GRAD == 0 && want_grad) {  // Green-Gauss face value, solver.h:444-457
-            const d4 qv = bc_vars(kind, qL, qR, nx, ny, gam);
-            const double w = gA.w;
-            const double f0 = (qL.x * (1.0 - w) + qv.x * w) * len;
-            const double f1 = (qL.y * (1.0 - w) + qv.y * w) * len;
-            const double f2 = (qL.z * (1.0 - w) + qv.z * w) * len;
-            const double f3 = (qL.w * (1.0 - w) + qv.w * w) * len;
-            if (!side) {
-                ax.x += f0 * nx; ax.y += f1 * nx; ax.z += f2 * nx; ax.w += f3 * nx;
-                ay.x += f0 * ny; ay.y += f1 * ny; ay.z += f2 * ny; ay.w += f3 * ny;
-            } else {
-                ax.x -= f0 * nx; ax.y -= f1 * nx; ax.z -= f2 * nx; ax.w -= f3 * nx;
-                ay.x -= f0 * ny; ay.y -= f1 * ny; ay.z -= f2 * ny; ay.w -= f3 * ny;
-            }
-        }
-    }
-    const double A = m.area[i];
-    dt[i] = prm[0] * A / dsum;  // prm[0] = cfl
-    if (!want_grad) return;
-    if (GRAD == 0) {
-#if AFX_FAST
-        const double rA = fast_rcp(A);
-        ax.x *= rA; ax.y *= rA; ax.z *= rA; ax.w *= rA;
-        ay.x *= rA; ay.y *= rA; ay.z *= rA; ay.w *= rA;
-#else
-        ax.x /= A; ax.y /= A; ax.z /= A; ax.w /= A;
-        ay.x /= A; ay.y /= A; ay.z /= A; ay.w /= A;
-#endif
-    } else {  // least squares, rows in cellsEdges order, solver.h:471-508
-        const uint32_t perm = m.lsq_perm[i];  // bits 0-7: slot of local side j (2 bits each); bits 8-10: number of sides
-        const int nside = (int)(perm >> 8);
-#pragma unroll
-        for (int jrow = 0; jrow < 4; ++jrow) {
-            if (jrow >= nside) break;
-            const int s = (perm >> (2 * jrow)) & 3;
-            const uint32_t cfv = m.cf[(size_t)s * m.N + i];
-            const uint32_t f = cfv & CF_ID;
-            const uint2 fc = m.fcells[f];
-            const d4 gA = m.fgA[f];
-            const int kind = m.fkind[f];
-            const uint32_t j = (cfv & CF_SIDE) ? fc.x : fc.y;
-            const d4 qn = q[j];
-            const d4 qv = bc_vars(kind, qi, qn, gA.x, gA.y, gam);  // (q_p, q_n) whatever the orientation
-            const double d0 = qi.x - qv.x, d1 = qi.y - qv.y, d2 = qi.z - qv.z, d3 = qi.w - qv.w;
-            const double m0 = m.lsqM[(size_t)jrow * m.N + i], m1 = m.lsqM[(size_t)(4 + jrow) * m.N + i];
-            ax.x += m0 * d0; ax.y += m0 * d1; ax.z += m0 * d2; ax.w += m0 * d3;
-            ay.x += m1 * d0; ay.y += m1 * d1; ay.z += m1 * d2; ay.w += m1 * d3;
-        }
-    }
-    gx[i] = ax;
-    gy[i] = ay;
-}
-
-// ---------------------------------------------------------------------------
-// Venkatakrishnan limiter, one thread per real cell.  calc_limiters
-// (solver.h:517-593): min/max over the edge neighbours (ghosts included) of the
-// stage state, then the minimum of the limiter function over the cell's faces.
-// ---------------------------------------------------------------------------
+// ---- Venkatakrishnan limiter function (used by k_dt_grad<.,1>, k_limiter and the fused k_stage) ----
 __device__ __forceinline__ double venkat(double dqg, double dmax, double dmin, double K3a)
 {
     if (dqg > 1e-16)
@@ -249,6 +144,138 @@ __device__ __forceinline__ d4 limiter_value(const d4& qi, const d4& lo, const d4
     return l;
 }
 
+// ---------------------------------------------------------------------------
+// Local time step + gradients of q, one thread per real cell.
+// calc_dt (solver.h:308-356), set_walls_from_internal (289-305, folded in: the
+// owner writes its wall ghosts), calc_gradients Green-Gauss (428-469) or
+// least-squares (470-513).  Source state is the iteration-start q (SURVEY F5).
+// ---------------------------------------------------------------------------
+// LIM = 1 also writes the limiters of the FIRST Runge-Kutta stage (calc_limiters, solver.h:517-593): that stage limits
+// the iteration-start state, whose neighbour states this kernel has just read and whose gradient it has just computed,
+// so the first k_limiter launch of the iteration -- a second pass over q, gx, gy, the neighbour table and the areas --
+// is saved.  Same limiter_value() on the same inputs in the same order: the bits are those of k_limiter.
+template <int GRAD, int LIM>
+__global__ void __launch_bounds__(AFX_DTG_THREADS, AFX_DTG_MINB) k_dt_grad(DevMesh m, d4* q, double* dt,
+                                                 d4* gx, d4* gy, const double* __restrict__ prm,
+                                                 double gam, int want_grad, int walls, d4* lim, double limiter_k)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m.n_grad) return;
+    pdl_launch_dependents();
+    uint32_t nbv[4];
+    d4 geo[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {  // independent coalesced loads first: neighbour | flags and the slot's face geometry
+        nbv[s] = m.cnb[(size_t)s * m.N + i];
+        geo[s] = m.cgeo[(size_t)s * m.N + i];
+    }
+    pdl_wait();  // the state comes from the previous kernel
+    const d4 qi = q[i];
+    const CellSound si = cell_sound(qi, gam);  // once per cell instead of once per face
+    double dsum = 0;
+    d4 ax = mk4(0, 0, 0, 0), ay = mk4(0, 0, 0, 0);
+    unsigned wall_slots = 0;  // LIM: slots whose neighbour is a wall ghost (it holds this cell's state)
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const uint32_t v = nbv[s];
+        if (v == CF_NONE) continue;
+        const bool side = v & CF_SIDE;
+        const uint32_t j = v & CF_ID;
+        const d4 gA = geo[s];
+        const int kind = (v & CF_BND) ? (int)m.fkind[m.cf[(size_t)s * m.N + i] & CF_ID] : K_INTERNAL;
+        const bool wall_ghost = walls && (v & CF_BND) && (kind == K_SLIPWALL || kind == K_WALL);
+        if (wall_ghost) q[j] = qi;  // ghost <- owner (set_walls_from_internal)
+        const d4 qj = wall_ghost ? qi : q[j];
+        if (LIM && wall_ghost) wall_slots |= 1u << s;
+        const d4 qL = side ? qj : qi, qR = side ? qi : qj;  // states of cell0 / cell1
+        const double nx = gA.x, ny = gA.y, len = gA.z;
+        // spectral radius, solver.h:328-345
+        // cell0's radius alone at one-sided (boundary) faces, where this cell is always cell0
+        double eig = spectral_radius(qi, si, nx, ny);
+        if (kind == K_INTERNAL) {
+            const double eig_j = spectral_radius(qj, cell_sound(qj, gam), nx, ny);
+            const double eig_L = side ? eig_j : eig, eig_R = side ? eig : eig_j;
+            eig = (eig_L < eig_R) ? eig_R : eig_L;
+        }
+        dsum += eig * len;
+        if (GRAD == 0 && want_grad) {  // Green-Gauss face value, solver.h:444-457
+            const d4 qv = bc_vars(kind, qL, qR, nx, ny, gam);
+            const double w = gA.w;
+            const double f0 = (qL.x * (1.0 - w) + qv.x * w) * len;
+            const double f1 = (qL.y * (1.0 - w) + qv.y * w) * len;
+            const double f2 = (qL.z * (1.0 - w) + qv.z * w) * len;
+            const double f3 = (qL.w * (1.0 - w) + qv.w * w) * len;
+            if (!side) {
+                ax.x += f0 * nx; ax.y += f1 * nx; ax.z += f2 * nx; ax.w += f3 * nx;
+                ay.x += f0 * ny; ay.y += f1 * ny; ay.z += f2 * ny; ay.w += f3 * ny;
+            } else {
+                ax.x -= f0 * nx; ax.y -= f1 * nx; ax.z -= f2 * nx; ax.w -= f3 * nx;
+                ay.x -= f0 * ny; ay.y -= f1 * ny; ay.z -= f2 * ny; ay.w -= f3 * ny;
+            }
+        }
+    }
+    const double A = m.area[i];
+    dt[i] = prm[0] * A / dsum;  // prm[0] = cfl
+    if (!want_grad) return;
+    if (GRAD == 0) {
+#if AFX_FAST
+        const double rA = fast_rcp(A);
+        ax.x *= rA; ax.y *= rA; ax.z *= rA; ax.w *= rA;
+        ay.x *= rA; ay.y *= rA; ay.z *= rA; ay.w *= rA;
+#else
+        ax.x /= A; ax.y /= A; ax.z /= A; ax.w /= A;
+        ay.x /= A; ay.y /= A; ay.z /= A; ay.w /= A;
+#endif
+    } else {  // least squares, rows in cellsEdges order, solver.h:471-508
+        const uint32_t perm = m.lsq_perm[i];  // bits 0-7: slot of local side j (2 bits each); bits 8-10: number of sides
+        const int nside = (int)(perm >> 8);
+#pragma unroll
+        for (int jrow = 0; jrow < 4; ++jrow) {
+            if (jrow >= nside) break;
+            const int s = (perm >> (2 * jrow)) & 3;
+            const uint32_t cfv = m.cf[(size_t)s * m.N + i];
+            const uint32_t f = cfv & CF_ID;
+            const uint2 fc = m.fcells[f];
+            const d4 gA = m.fgA[f];
+            const int kind = m.fkind[f];
+            const uint32_t j = (cfv & CF_SIDE) ? fc.x : fc.y;
+            const d4 qn = q[j];
+            const d4 qv = bc_vars(kind, qi, qn, gA.x, gA.y, gam);  // (q_p, q_n) whatever the orientation
+            const double d0 = qi.x - qv.x, d1 = qi.y - qv.y, d2 = qi.z - qv.z, d3 = qi.w - qv.w;
+            const double m0 = m.lsqM[(size_t)jrow * m.N + i], m1 = m.lsqM[(size_t)(4 + jrow) * m.N + i];
+            ax.x += m0 * d0; ax.y += m0 * d1; ax.z += m0 * d2; ax.w += m0 * d3;
+            ay.x += m1 * d0; ay.y += m1 * d1; ay.z += m1 * d2; ay.w += m1 * d3;
+        }
+    }
+    gx[i] = ax;
+    gy[i] = ay;
+    if (LIM) {
+        // min / max over the edge neighbours (solver.h:524-536) in an epilogue of its own: the neighbour states are read a
+        // second time, from L1, instead of carrying eight more accumulators through the gradient loop
+        double2 dxy[4];
+#pragma unroll
+        for (int s = 0; s < 4; ++s) dxy[s] = m.cdxy[(size_t)s * m.N + i];
+        d4 lo = qi, hi = qi;
+        unsigned valid = 0;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const uint32_t v = nbv[s];
+            if (v == CF_NONE) continue;
+            valid |= 1u << s;
+            if (wall_slots & (1u << s)) continue;  // the ghost holds qi: neither bound moves
+            const d4 qj = q[v & CF_ID];
+            lo.x = dmin2(lo.x, qj.x); lo.y = dmin2(lo.y, qj.y); lo.z = dmin2(lo.z, qj.z); lo.w = dmin2(lo.w, qj.w);
+            hi.x = dmax2(hi.x, qj.x); hi.y = dmax2(hi.y, qj.y); hi.z = dmax2(hi.z, qj.z); hi.w = dmax2(hi.w, qj.w);
+        }
+        lim[i] = limiter_value(qi, lo, hi, ax, ay, dxy, valid, limiter_k3a(A, limiter_k));
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Venkatakrishnan limiter, one thread per real cell.  calc_limiters
+// (solver.h:517-593): min/max over the edge neighbours (ghosts included) of the
+// stage state, then the minimum of the limiter function over the cell's faces.
+// ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256, AFX_LIM_MINB) k_limiter(DevMesh m, const d4* qk, const d4* gx,
                                                  const d4* gy, d4* lim, double limiter_k, int walls,
                                                  uint32_t lo1, uint32_t n1, uint32_t lo2, uint32_t n2)
@@ -725,11 +752,15 @@ static void launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, 
     cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
+// lim != nullptr: also write the first stage's limiters (needs want_grad)
 static void dt_grad(int grad, const DevMesh& m, d4* q, double* dt, d4* gx, d4* gy, const double* prm, double gam, int want_grad,
-                    int walls, cudaStream_t st)
+                    int walls, d4* lim, double limiter_k, cudaStream_t st)
 {
-    if (grad == 0) launch_pdl(k_dt_grad<0>, nblk(m.n_grad, AFX_DTG_THREADS), AFX_DTG_THREADS, st, m, q, dt, gx, gy, prm, gam, want_grad, walls);
-    else launch_pdl(k_dt_grad<1>, nblk(m.n_grad, AFX_DTG_THREADS), AFX_DTG_THREADS, st, m, q, dt, gx, gy, prm, gam, want_grad, walls);
+    const unsigned nb = nblk(m.n_grad, AFX_DTG_THREADS);
+#define AFX_DTG(G, L) launch_pdl(k_dt_grad<G, L>, nb, AFX_DTG_THREADS, st, m, q, dt, gx, gy, prm, gam, want_grad, walls, lim, limiter_k)
+    if (lim && want_grad) { if (grad == 0) AFX_DTG(0, 1); else AFX_DTG(1, 1); }
+    else { if (grad == 0) AFX_DTG(0, 0); else AFX_DTG(1, 0); }
+#undef AFX_DTG
 }
 static void limiter(const DevMesh& m, const d4* qk, const d4* gx, const d4* gy, d4* lim, double k, int walls, uint32_t lo1, uint32_t n1,
                     uint32_t lo2, uint32_t n2, cudaStream_t st)

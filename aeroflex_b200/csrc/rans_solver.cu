@@ -236,7 +236,10 @@ struct Solver {
     void set_bcs(int n_patch, const uint8_t* kinds, const afx_bvars* vars);
     void set_options(int so, int grad, double k);
     void push_params(double relax, bool keep_qW = true);
-    void launch_dt_grad(bool want_grad, bool walls);
+    void launch_dt_grad(bool want_grad, bool walls, bool with_lim = false);
+    bool fuse_lim0 = true;  // AFX_FUSE_LIM0=0: keep the first stage's limiter in its own k_limiter launch
+    // the first stage limits the iteration-start state: k_dt_grad can do it from the neighbour states it has just read
+    bool lim0_in_dt_grad() const { return fuse_lim0 && second_order && !fused_stage(); }
     void launch_limiter(const d4* qk);
     void launch_flux(const d4* qk, bool uniform, d4 qfar);
     template <int MODE, int LAST>
@@ -295,6 +298,7 @@ void Solver::create(const afx_mesh_desc& m, const afx_gas& g, int visc, int dev,
     }
     if (const char* e = getenv("AFX_NO_GRAPH")) use_graph = !(e[0] == '1');
     if (const char* e = getenv("AFX_HALO_OVERLAP")) halo_overlap = (e[0] == '1');
+    if (const char* e = getenv("AFX_FUSE_LIM0")) fuse_lim0 = !(e[0] == '0');
     if (const char* e = getenv("AFX_MATH")) kt = (std::string(e) == "strict") ? &strict::table() : &fast::table();
 
     N = m.n_cells; G = m.n_ghost; E = m.n_edges; NT = N + G;
@@ -603,10 +607,11 @@ void Solver::push_params(double relax, bool keep_qW)
     relax_dev = relax; cfl_dev = cfl; keep_dev = kq;
 }
 
-void Solver::launch_dt_grad(bool want_grad, bool walls)
+void Solver::launch_dt_grad(bool want_grad, bool walls, bool with_lim)
 {
     ensure_halo();
-    kt->dt_grad(gradient_scheme == AFX_GRAD_GREEN_GAUSS ? 0 : 1, dm, q.p, dt.p, gx.p, gy.p, prm.p, gas.gamma, want_grad, walls, st);
+    kt->dt_grad(gradient_scheme == AFX_GRAD_GREEN_GAUSS ? 0 : 1, dm, q.p, dt.p, gx.p, gy.p, prm.p, gas.gamma, want_grad, walls,
+                (with_lim && want_grad) ? lim.p : nullptr, limiter_k, st);
     ++launches;
 }
 
@@ -791,13 +796,14 @@ void Solver::launch_stage(int s, const d4* qk_in, d4* qk_out, double alpha)
 void Solver::explicit_iteration()
 {
     const bool grads = visc_not_inviscid || second_order;  // solver.h:810
-    launch_dt_grad(grads, grads);
+    const bool lim0 = lim0_in_dt_grad();  // second_order => grads
+    launch_dt_grad(grads, grads, lim0);
     const d4* in[3] = {q.p, qkA.p, qkB.p};
     d4* out[3] = {qkA.p, qkB.p, q.p};
     const double alpha[3] = {0.25, 0.5, 1.};  // solver.h:723
     for (int s = 0; s < 3; ++s) {
         if (fused_stage()) { launch_stage(s, in[s], out[s], alpha[s]); continue; }
-        if (second_order) launch_limiter(in[s]);
+        if (second_order && !(s == 0 && lim0)) launch_limiter(in[s]);
         launch_flux(in[s], false, d4{0, 0, 0, 0});
         if (s < 2) launch_gather<0, 0>(in[s], out[s], qW.p, alpha[s], grads);
         else launch_gather<0, 1>(in[s], out[s], qW.p, alpha[s], grads);
@@ -1033,8 +1039,9 @@ double Solver::residual_rhs()
     if (!bcs_set) throw InvalidArg("set_bcs has not been called");
     push_params(relax_dev < 0 ? 1.0 : relax_dev);
     const bool grads = second_order || visc_not_inviscid;  // solver.h:1083
-    launch_dt_grad(grads, grads);
-    if (second_order) launch_limiter(q.p);
+    const bool lim0 = fuse_lim0 && second_order;
+    launch_dt_grad(grads, grads, lim0);
+    if (second_order && !lim0) launch_limiter(q.p);
     launch_flux(q.p, false, d4{0, 0, 0, 0});
     launch_gather<1, 1>(q.p, nullptr, rhs.p, 0., false);
     CK(cudaGetLastError());
@@ -1761,7 +1768,8 @@ int afx_rans_profile_explicit(afx_rans* s, double relaxation, int n_iter, double
         for (int it = 0; it < n_iter; ++it) {
             int e = 0;
             CK(cudaEventRecord(ev[e++], S.st));
-            S.launch_dt_grad(grads, grads);
+            const bool lim0 = S.lim0_in_dt_grad();
+            S.launch_dt_grad(grads, grads, lim0);
             CK(cudaEventRecord(ev[e++], S.st));
             for (int st = 0; st < 3; ++st) {
                 if (fused) {
@@ -1772,7 +1780,7 @@ int afx_rans_profile_explicit(afx_rans* s, double relaxation, int n_iter, double
                     CK(cudaEventRecord(ev[e++], S.st));
                     continue;
                 }
-                if (S.second_order) S.launch_limiter(in[st]);
+                if (S.second_order && !(st == 0 && lim0)) S.launch_limiter(in[st]);
                 CK(cudaEventRecord(ev[e++], S.st));
                 S.launch_flux(in[st], false, afx::d4{0, 0, 0, 0});
                 CK(cudaEventRecord(ev[e++], S.st));

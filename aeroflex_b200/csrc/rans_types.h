@@ -131,8 +131,9 @@ struct WallArgs {
 // Launchers of one arithmetic mode.  Every function enqueues exactly one kernel on `st`.
 struct KernelTable {
     const char* name;
+    // lim != nullptr (and want_grad): the kernel also writes the limiters of the first stage (state q), saving that k_limiter launch
     void (*dt_grad)(int grad_scheme, const DevMesh& m, d4* q, double* dt, d4* gx, d4* gy, const double* prm, double gam,
-                    int want_grad, int walls, cudaStream_t st);
+                    int want_grad, int walls, d4* lim, double limiter_k, cudaStream_t st);
     // cells [lo1, lo1+n1) and [lo2, lo2+n2)
     void (*limiter)(const DevMesh& m, const d4* qk, const d4* gx, const d4* gy, d4* lim, double limiter_k, int walls, uint32_t lo1, uint32_t n1,
                     uint32_t lo2, uint32_t n2, cudaStream_t st);

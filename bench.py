@@ -145,6 +145,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--math", default="fast", choices=["fast", "strict"])
+    ap.add_argument("--fuse-lim0", type=int, default=1, help="1 (default): k_dt_grad also writes the first stage's limiters (9 kernels per iteration); 0: separate k_limiter launch (10)")
     ap.add_argument("--fused", type=int, default=0, help="1: one fused kernel per RK stage on shared-memory tiles; 0 (default): limiter / flux / gather kernels")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -172,6 +173,7 @@ def main():
 
     if a.fused:
         os.environ["AFX_FUSED"] = "1"  # the tiles (and the graph-bisection numbering) are built at creation
+    os.environ["AFX_FUSE_LIM0"] = "1" if a.fuse_lim0 else "0"
     import torch
     import aeroflex_b200 as afx
     if afx.device_count() <= 0:
@@ -202,7 +204,7 @@ def main():
     tiles = s.tile_info()
     config["stage_kernel"] = ("fused k_stage: %d tiles of <= %d cells, %d B shared memory, %d CTAs/SM, staging overhead %.2fx"
                               % (tiles["tiles"], tiles["tile_cells"], tiles["smem_bytes"], tiles["ctas_per_sm"],
-                                 tiles["local_cells"] / max(1, (N if part is None else part.n_own)))) if tiles["fused"] else "k_limiter + k_flux + k_gather_update"
+                                 tiles["local_cells"] / max(1, (N if part is None else part.n_own)))) if tiles["fused"] else ("k_dt_grad writes the first stage's limiters; k_limiter (stages 2, 3) + k_flux + k_gather_update" if (a.fuse_lim0 and SECOND) else "k_limiter + k_flux + k_gather_update")
     base = np.zeros(4 * (N + G))
     s.get_q(base)  # a partitioned solver fills its own entries of the global vector
     q0 = perturbed(base, N)
@@ -250,10 +252,11 @@ def main():
         kernels = {"k_stage": ((440.0 * N + 72.0 * E) * share, 3, prof["stage"]),
                    "k_dt_grad": ((168.0 * N + 80.0 * E) * share, 1, prof["dt_grad"])}
     else:
+        lim0 = 1 if (a.fuse_lim0 and SECOND) else 0  # the first stage's limiter phase runs inside k_dt_grad
         kernels = {"k_flux": ((144.0 * N + 48.0 * E) * share, 3, prof["flux"]),
-                   "k_limiter": ((152.0 * N + 24.0 * E) * share, 3, prof["limiter"]),
+                   "k_limiter": ((152.0 * N + 24.0 * E) * share, 3 - lim0, prof["limiter"]),
                    "k_gather_update": ((144.0 * N + 32.0 * E) * share, 3, prof["gather_update"]),
-                   "k_dt_grad": ((168.0 * N + 80.0 * E) * share, 1, prof["dt_grad"])}
+                   "k_dt_grad": ((168.0 * N + 80.0 * E + lim0 * (152.0 * N + 24.0 * E)) * share, 1, prof["dt_grad"])}
     alg_iter = (1488.0 * N + 296.0 * E) * share
     peaks = {}
     try:

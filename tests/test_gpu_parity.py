@@ -306,4 +306,33 @@ def test_implicit_converged_forces_match_reference(afx, gpu, math):
     assert cl == pytest.approx(float(g["cl"][0]), rel=1e-7)
     assert cd == pytest.approx(float(g["cd"][0]), rel=1e-6)
     assert cm == pytest.approx(float(g["cm"][0]), rel=1e-6)
-    print("implicit outer iterations:", len(hist), "last linear iterations:", s.last_linear_iterations())
+    print("implicit outer iterations:", len(hist), "last linear iterations:", s.last_linear_iterations())@pytest.mark.gpu
+@pytest.mark.parametrize("grad,visc,math", [("green-gauss", "inviscid", "strict"), ("least-squares", "laminar", "strict"), ("green-gauss", "spallart-allmaras", "fast")])
+def test_first_stage_limiter_inside_dt_grad_is_bit_identical(afx, gpu, monkeypatch, grad, visc, math):
+    """k_dt_grad<.,1> writes the first stage's limiters itself (one k_limiter launch less per iteration): same
+    limiter_value() on the same inputs, so state, norms and the residual RHS have the bits of the separate launch,
+    in both arithmetic modes."""
+    m = afx.Mesh.synth_omesh(160, 80, 24, 100.0)
+    bcs = {"farfield": ("farfield", dict(mach=0.25, angle=0.03, T=1.0, p=1.0)), "wall": ("wall" if visc != "inviscid" else "slip-wall", None)}
+    outs = []
+    for fuse in ("1", "0"):
+        monkeypatch.setenv("AFX_FUSE_LIM0", fuse)
+        s = afx.GpuSolver(m, viscosity=visc, math=math)
+        s.set_bcs(bcs); s.set_options(True, grad, 5.0, 1.5); s.init(); s.refill_bcs()
+        s.set_q(H.synth_state(m.N, s.get_q()))
+        l0 = s.launch_count()
+        norms = s.run(6, 0.9)
+        per_iter = (s.launch_count() - l0) / 6.0
+        rhs_norm = s.residual()
+        outs.append((norms, s.get_q(), per_iter, rhs_norm, s.get("rhs"), s.get("limiters")))
+    if math == "strict":
+        assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+        assert outs[0][3] == outs[1][3] and np.array_equal(outs[0][4], outs[1][4]) and np.array_equal(outs[0][5], outs[1][5])
+    else:  # FMA contraction may differ between the two inlining contexts
+        np.testing.assert_allclose(outs[0][0], outs[1][0], rtol=1e-11)
+        np.testing.assert_allclose(outs[0][1], outs[1][1], rtol=1e-11, atol=1e-14)
+        np.testing.assert_allclose(outs[0][4], outs[1][4], rtol=1e-9, atol=1e-12)
+    assert outs[0][2] == 9 and outs[1][2] == 10  # kernels per explicit iteration
+
+
+
