@@ -27,8 +27,14 @@
 #ifndef AFX_DTG_THREADS
 #define AFX_DTG_THREADS 256
 #endif
+// k_dt_grad: AFX_DTG_PRELOAD=1 requests the four neighbour states together (5 gathers in flight per thread) and needs
+// ~128 registers to hold them without spilling a value that is still in flight -> 2 CTAs per SM.  AFX_DTG_PRELOAD=0 with
+// AFX_DTG_MINB=3 is the earlier kernel (one gather at a time, 80 registers, 24 warps per SM).
+#ifndef AFX_DTG_PRELOAD
+#define AFX_DTG_PRELOAD 1
+#endif
 #ifndef AFX_DTG_MINB
-#define AFX_DTG_MINB 3
+#define AFX_DTG_MINB (AFX_DTG_PRELOAD ? 2 : 3)
 #endif
 
 namespace afx {
@@ -171,10 +177,28 @@ __global__ void __launch_bounds__(AFX_DTG_THREADS, AFX_DTG_MINB) k_dt_grad(DevMe
     }
     pdl_wait();  // the state comes from the previous kernel
     const d4 qi = q[i];
-    const CellSound si = cell_sound(qi, gam);  // once per cell instead of once per face
     double dsum = 0;
     d4 ax = mk4(0, 0, 0, 0), ay = mk4(0, 0, 0, 0);
-    unsigned wall_slots = 0;  // LIM: slots whose neighbour is a wall ghost (it holds this cell's state)
+    unsigned wall_slots = 0;  // slots whose neighbour is a wall ghost (it takes this cell's state)
+#if AFX_DTG_PRELOAD
+    // All four neighbour states are requested before any of them is used, and the wall ghosts are written after the last
+    // read: a ghost store between two gathers would order them (the compiler must assume the addresses may coincide), and
+    // this kernel is bound by the latency of exactly these gathers.  A wall ghost is read by its owner only.
+    d4 qn[4];
+    unsigned kinds = 0;  // 2 bits per slot
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const uint32_t v = nbv[s];
+        qn[s] = mk4(0, 0, 0, 0);
+        if (v == CF_NONE) continue;
+        const int kind = (v & CF_BND) ? (int)m.fkind[m.cf[(size_t)s * m.N + i] & CF_ID] : K_INTERNAL;
+        const bool wall_ghost = walls && (v & CF_BND) && (kind == K_SLIPWALL || kind == K_WALL);
+        kinds |= (unsigned)kind << (2 * s);
+        if (wall_ghost) wall_slots |= 1u << s;
+        else qn[s] = q[v & CF_ID];
+    }
+#endif
+    const CellSound si = cell_sound(qi, gam);  // once per cell instead of once per face
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
         const uint32_t v = nbv[s];
@@ -182,11 +206,17 @@ __global__ void __launch_bounds__(AFX_DTG_THREADS, AFX_DTG_MINB) k_dt_grad(DevMe
         const bool side = v & CF_SIDE;
         const uint32_t j = v & CF_ID;
         const d4 gA = geo[s];
+#if AFX_DTG_PRELOAD
+        const int kind = (int)((kinds >> (2 * s)) & 3u);
+        const d4 qj = (wall_slots & (1u << s)) ? qi : qn[s];
+        (void)j;
+#else
         const int kind = (v & CF_BND) ? (int)m.fkind[m.cf[(size_t)s * m.N + i] & CF_ID] : K_INTERNAL;
         const bool wall_ghost = walls && (v & CF_BND) && (kind == K_SLIPWALL || kind == K_WALL);
         if (wall_ghost) q[j] = qi;  // ghost <- owner (set_walls_from_internal)
         const d4 qj = wall_ghost ? qi : q[j];
         if (LIM && wall_ghost) wall_slots |= 1u << s;
+#endif
         const d4 qL = side ? qj : qi, qR = side ? qi : qj;  // states of cell0 / cell1
         const double nx = gA.x, ny = gA.y, len = gA.z;
         // spectral radius, solver.h:328-345
@@ -214,6 +244,13 @@ __global__ void __launch_bounds__(AFX_DTG_THREADS, AFX_DTG_MINB) k_dt_grad(DevMe
             }
         }
     }
+#if AFX_DTG_PRELOAD
+    if (wall_slots) {  // ghost <- owner (set_walls_from_internal)
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+            if (wall_slots & (1u << s)) q[nbv[s] & CF_ID] = qi;
+    }
+#endif
     const double A = m.area[i];
     dt[i] = prm[0] * A / dsum;  // prm[0] = cfl
     if (!want_grad) return;
