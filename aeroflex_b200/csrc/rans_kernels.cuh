@@ -24,17 +24,26 @@
 #ifndef AFX_LIM_MINB
 #define AFX_LIM_MINB 4
 #endif
+// k_dt_grad tuning, measured on B200 at 1M cells with the first-stage limiter inside the kernel (profiles/r01_s3_ab_*.jsonl,
+// ms per explicit iteration): 128 threads x 6 CTAs 0.405 | 256 x 3 0.411-0.417 | + L2 prefetch of the limiter's face
+// offsets 0.407-0.408 | offsets loaded before the dependency wait 0.425 | 64 registers (256 x 4) 0.441 | neighbour preload:
+// 128 registers (256 x 2) 0.415, + prefetch 0.405, capped at 80 registers 0.428.
+//   AFX_DTG_PRELOAD=1 requests the four neighbour states together and writes the wall ghosts after the last read; it needs
+//   ~128 registers to hold them without spilling a value that is still in flight, and the limiter epilogue then runs at
+//   16 warps per SM: no gain over one gather at a time at 24 warps (the kernel is not bound by gather latency alone).
+//   AFX_DTG_DXY: where the first-stage limiter gets its face offsets: 0 loads them in its epilogue, 1 also prefetches them
+//   into L2 at kernel start, 2 loads them before the dependency wait (8 more registers through the gradient loop).
 #ifndef AFX_DTG_THREADS
-#define AFX_DTG_THREADS 256
+#define AFX_DTG_THREADS 128
 #endif
-// k_dt_grad: AFX_DTG_PRELOAD=1 requests the four neighbour states together (5 gathers in flight per thread) and needs
-// ~128 registers to hold them without spilling a value that is still in flight -> 2 CTAs per SM.  AFX_DTG_PRELOAD=0 with
-// AFX_DTG_MINB=3 is the earlier kernel (one gather at a time, 80 registers, 24 warps per SM).
 #ifndef AFX_DTG_PRELOAD
-#define AFX_DTG_PRELOAD 1
+#define AFX_DTG_PRELOAD 0
 #endif
 #ifndef AFX_DTG_MINB
-#define AFX_DTG_MINB (AFX_DTG_PRELOAD ? 2 : 3)
+#define AFX_DTG_MINB (AFX_DTG_PRELOAD ? 512 / AFX_DTG_THREADS : 768 / AFX_DTG_THREADS)
+#endif
+#ifndef AFX_DTG_DXY
+#define AFX_DTG_DXY 0
 #endif
 
 namespace afx {
@@ -49,6 +58,7 @@ namespace AFX_NS {
 // attribute see both calls as no-ops.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // spectral radius c + |V.n| of one state, solver.h:329-336, split into the part that belongs to the cell -- the speed
 // of sound, one square root (and in strict mode the division 0.5/rho) -- and the part that belongs to the face.  The
@@ -175,6 +185,18 @@ __global__ void __launch_bounds__(AFX_DTG_THREADS, AFX_DTG_MINB) k_dt_grad(DevMe
         nbv[s] = m.cnb[(size_t)s * m.N + i];
         geo[s] = m.cgeo[(size_t)s * m.N + i];
     }
+#if AFX_DTG_DXY == 1
+    if (LIM) {  // the limiter epilogue's face offsets: on their way to L2 while the gradients are computed, no register held
+#pragma unroll
+        for (int s = 0; s < 4; ++s) prefetch_l2(&m.cdxy[(size_t)s * m.N + i]);
+    }
+#elif AFX_DTG_DXY == 2
+    double2 dxy_early[4];
+    if (LIM) {
+#pragma unroll
+        for (int s = 0; s < 4; ++s) dxy_early[s] = m.cdxy[(size_t)s * m.N + i];
+    }
+#endif
     pdl_wait();  // the state comes from the previous kernel
     const d4 qi = q[i];
     double dsum = 0;
@@ -291,7 +313,13 @@ __global__ void __launch_bounds__(AFX_DTG_THREADS, AFX_DTG_MINB) k_dt_grad(DevMe
         // second time, from L1, instead of carrying eight more accumulators through the gradient loop
         double2 dxy[4];
 #pragma unroll
-        for (int s = 0; s < 4; ++s) dxy[s] = m.cdxy[(size_t)s * m.N + i];
+        for (int s = 0; s < 4; ++s) {
+#if AFX_DTG_DXY == 2
+            dxy[s] = dxy_early[s];
+#else
+            dxy[s] = m.cdxy[(size_t)s * m.N + i];
+#endif
+        }
         d4 lo = qi, hi = qi;
         unsigned valid = 0;
 #pragma unroll

@@ -1,0 +1,26 @@
+#!/usr/bin/env python
+"""Build tuning variants of the CUDA library next to the default one (for A/B runs with AFX_LIB=...)."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import aeroflex_b200 as afx  # noqa: E402
+
+VARIANTS = {
+    # the k_dt_grad of sessions 1-2: one neighbour gather at a time, 80 registers, 3 CTAs per SM
+    "nopreload": ["-DAFX_DTG_PRELOAD=0"],
+    "nopreload_pf": ["-DAFX_DTG_PRELOAD=0", "-DAFX_DTG_DXY=1"],
+    "nopreload_early": ["-DAFX_DTG_PRELOAD=0", "-DAFX_DTG_DXY=2"],
+    "nopreload_minb4": ["-DAFX_DTG_PRELOAD=0", "-DAFX_DTG_MINB=4"],
+    "preload_pf": ["-DAFX_DTG_PRELOAD=1", "-DAFX_DTG_DXY=1"],
+    "preload_minb3": ["-DAFX_DTG_PRELOAD=1", "-DAFX_DTG_MINB=3"],
+    "preload_minb3_pf": ["-DAFX_DTG_PRELOAD=1", "-DAFX_DTG_MINB=3", "-DAFX_DTG_DXY=1"],
+    "nopreload_t128": ["-DAFX_DTG_PRELOAD=0", "-DAFX_DTG_THREADS=128", "-DAFX_DTG_MINB=6"],
+    "nopreload_t128_pf": ["-DAFX_DTG_PRELOAD=0", "-DAFX_DTG_THREADS=128", "-DAFX_DTG_MINB=6", "-DAFX_DTG_DXY=1"],
+}
+for name, defs in VARIANTS.items():
+    if len(sys.argv) > 1 and name not in sys.argv[1:]:
+        continue
+    out = os.path.join(ROOT, "aeroflex_b200", "lib", "libaeroflex_rans_b200_%s.so" % name)
+    print(afx.build_library(force=True, defines=defs, out=out))
