@@ -17,12 +17,24 @@
 #pragma once
 #include "rans_physics.cuh"
 
-// resident CTAs per SM asked of ptxas for the two heavy kernels (register cap = 65536 / (256 * n))
+// CTA size and resident CTAs per SM asked of ptxas for the stage kernels (register cap = 65536 / (threads * n)).
+// Measured on B200 at 1M cells (profiles/r01_s3_ab_stage_threads.jsonl): 128-thread CTAs for k_flux and k_limiter
+// 0.3953 ms per iteration (flux phase 0.161, limiter 0.093) against 0.4030 with 256 (0.173, 0.097); k_gather_update is
+// better at 256 (0.114-0.118 against 0.135 at 128).
+#ifndef AFX_FLUX_THREADS
+#define AFX_FLUX_THREADS 128
+#endif
+#ifndef AFX_LIM_THREADS
+#define AFX_LIM_THREADS 128
+#endif
+#ifndef AFX_GATHER_THREADS
+#define AFX_GATHER_THREADS 256
+#endif
 #ifndef AFX_FLUX_MINB
-#define AFX_FLUX_MINB 4
+#define AFX_FLUX_MINB (1024 / AFX_FLUX_THREADS)
 #endif
 #ifndef AFX_LIM_MINB
-#define AFX_LIM_MINB 4
+#define AFX_LIM_MINB (1024 / AFX_LIM_THREADS)
 #endif
 // k_dt_grad tuning, measured on B200 at 1M cells with the first-stage limiter inside the kernel (profiles/r01_s3_ab_*.jsonl,
 // ms per explicit iteration): 128 threads x 6 CTAs 0.405 | 256 x 3 0.411-0.417 | + L2 prefetch of the limiter's face
@@ -341,7 +353,7 @@ __global__ void __launch_bounds__(AFX_DTG_THREADS, AFX_DTG_MINB) k_dt_grad(DevMe
 // (solver.h:517-593): min/max over the edge neighbours (ghosts included) of the
 // stage state, then the minimum of the limiter function over the cell's faces.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, AFX_LIM_MINB) k_limiter(DevMesh m, const d4* qk, const d4* gx,
+__global__ void __launch_bounds__(AFX_LIM_THREADS, AFX_LIM_MINB) k_limiter(DevMesh m, const d4* qk, const d4* gx,
                                                  const d4* gy, d4* lim, double limiter_k, int walls,
                                                  uint32_t lo1, uint32_t n1, uint32_t lo2, uint32_t n2)
 {
@@ -388,7 +400,7 @@ __global__ void __launch_bounds__(256, AFX_LIM_MINB) k_limiter(DevMesh m, const 
 // iteration-start q.
 // ---------------------------------------------------------------------------
 template <int SECOND, int VISC, int UNIFORM>
-__global__ void __launch_bounds__(256, AFX_FLUX_MINB) k_flux(DevMesh m, const d4* qk, const d4* q0,
+__global__ void __launch_bounds__(AFX_FLUX_THREADS, AFX_FLUX_MINB) k_flux(DevMesh m, const d4* qk, const d4* q0,
                                               const d4* gx, const d4* gy,
                                               const d4* lim, d4* flux, GasC g, d4 qfar)
 {
@@ -494,7 +506,7 @@ __device__ __forceinline__ void block_norm_accumulate(double v, const NormOut& n
 // and stores the vector (qW or rhs).
 // ---------------------------------------------------------------------------
 template <int MODE, int LAST>
-__global__ void __launch_bounds__(256) k_gather_update(DevMesh m, const d4* flux,
+__global__ void __launch_bounds__(AFX_GATHER_THREADS) k_gather_update(DevMesh m, const d4* flux,
                                                        const d4* q, const d4* qk_in,
                                                        d4* qk_out, const double* dt,
                                                        d4* qW, double alpha, const double* __restrict__ prm,
@@ -831,19 +843,19 @@ static void limiter(const DevMesh& m, const d4* qk, const d4* gx, const d4* gy, 
                     uint32_t lo2, uint32_t n2, cudaStream_t st)
 {
     if (n1 + n2 == 0) return;
-    launch_pdl(k_limiter, nblk(n1 + n2), 256, st, m, qk, gx, gy, lim, k, walls, lo1, n1, lo2, n2);
+    launch_pdl(k_limiter, nblk(n1 + n2, AFX_LIM_THREADS), AFX_LIM_THREADS, st, m, qk, gx, gy, lim, k, walls, lo1, n1, lo2, n2);
 }
 static void flux(int second, int visc, int uniform, const DevMesh& m, const d4* qk, const d4* q0, const d4* gx, const d4* gy,
                  const d4* lim, d4* fl, const GasC& g, d4 qfar, cudaStream_t st)
 {
-    const unsigned nb = nblk(m.e_flux);
-#define AFX_FLUX(S, V, U) launch_pdl(k_flux<S, V, U>, nb, 256, st, m, qk, q0, gx, gy, lim, fl, g, qfar)
+    const unsigned nb = nblk(m.e_flux, AFX_FLUX_THREADS);
+#define AFX_FLUX(S, V, U) launch_pdl(k_flux<S, V, U>, nb, AFX_FLUX_THREADS, st, m, qk, q0, gx, gy, lim, fl, g, qfar)
     if (uniform) { if (visc) AFX_FLUX(0, 1, 1); else AFX_FLUX(0, 0, 1); }
     else if (second) { if (visc) AFX_FLUX(1, 1, 0); else AFX_FLUX(1, 0, 0); }
     else { if (visc) AFX_FLUX(0, 1, 0); else AFX_FLUX(0, 0, 0); }
 #undef AFX_FLUX
 }
-static unsigned gather_blocks(uint32_t n_cells) { return nblk(n_cells); }
+static unsigned gather_blocks(uint32_t n_cells) { return nblk(n_cells, AFX_GATHER_THREADS); }
 static void gather(int mode, int last, const DevMesh& m, uint32_t lo, uint32_t hi, const d4* fl, const d4* q, const d4* qk_in, d4* qk_out,
                    const double* dt, d4* vec_out, double alpha, const double* prm, int walls, NormOut no, const PushArgs* push_in,
                    cudaStream_t st)
@@ -851,9 +863,9 @@ static void gather(int mode, int last, const DevMesh& m, uint32_t lo, uint32_t h
     if (hi <= lo) return;
     PushArgs push{};
     if (push_in) push = *push_in;
-    const unsigned nb = nblk(hi - lo);
+    const unsigned nb = nblk(hi - lo, AFX_GATHER_THREADS);
     if (no.blk_total == 0) { no.blk_off = 0; no.blk_total = nb; }
-#define AFX_G(M, L) launch_pdl(k_gather_update<M, L>, nb, 256, st, m, fl, q, qk_in, qk_out, dt, vec_out, alpha, prm, walls, no, lo, hi, push)
+#define AFX_G(M, L) launch_pdl(k_gather_update<M, L>, nb, AFX_GATHER_THREADS, st, m, fl, q, qk_in, qk_out, dt, vec_out, alpha, prm, walls, no, lo, hi, push)
     if (mode == 0) { if (last) AFX_G(0, 1); else AFX_G(0, 0); }
     else if (mode == 1) AFX_G(1, 1);
     else AFX_G(2, 1);

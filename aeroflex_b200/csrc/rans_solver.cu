@@ -505,7 +505,7 @@ void Solver::create(const afx_mesh_desc& m, const afx_gas& g, int visc, int dev,
     set_l2_window();
     flux.alloc(E); flux.zero(st);
     dt.alloc(NT); dt.zero(st); dt_ref.alloc(NT);
-    partial.alloc(std::max<size_t>(blocks(NT), stage_grid) + 4); norms.alloc(NORM_RING); norms.zero(st);
+    partial.alloc(std::max<size_t>(kt->gather_blocks(NT), stage_grid) + 4); norms.alloc(NORM_RING); norms.zero(st);
     prm.alloc(8); prm.zero(st); counters.alloc(4); counters.zero(st); scratch.alloc(16);
     // limiters start at 1 (ghost rows keep that value, solver.h:519)
     kt->fill_cells(lim.p, NT, d4{1, 1, 1, 1}, st);
