@@ -59,3 +59,9 @@ def test_one_cta_walks_many_tiles_under_emulation(emu_lib):
     # one emulated SM: a single persistent CTA pair walks every tile, so every buffer hand-over of the pipeline is exercised
     tail = run_gpu_tests_under_emulation(emu_lib, ["test_gpu_fused.py"], "bit_identical and (48 or 192)", extra_env={"AFX_EMU_SMS": "1"})
     assert " passed" in tail
+
+
+def test_edge_cases_under_emulation(emu_lib):
+    # supersonic / transonic boundary branches, meshes smaller than a CTA, limiter extremes, NaN handling
+    tail = run_gpu_tests_under_emulation(emu_lib, ["test_gpu_edge_cases.py"], "not ring_wraps")  # 120 000 iterations: GPU only
+    assert " passed" in tail
