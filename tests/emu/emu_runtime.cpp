@@ -9,12 +9,21 @@
 //   cp.async when the issuing thread's wait_group covers it -- a read before the wait sees the old bytes.
 // * Streams execute in submission order; a capturing stream records closures and a graph launch replays them.
 #include <cuda_runtime.h>
+#include <nccl.h>
+#include <dlfcn.h>
+#include <fcntl.h>
 #include <omp.h>
+#include <sched.h>
 #include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <map>
+#include <mutex>
+#include <string>
 
 thread_local uint3 threadIdx, blockIdx;
 thread_local dim3 blockDim, gridDim;
@@ -234,10 +243,23 @@ double rsqrt_seed(double a) { return upper_word(1.0 / std::sqrt(a)); }
 
 void submit(cudaStream_t st, std::function<void()> op);
 
+const char* self_path()
+{
+    static std::string path = [] {
+        Dl_info info{};
+        if (!dladdr(reinterpret_cast<void*>(&rcp_seed), &info) || !info.dli_fname) { fprintf(stderr, "afx_emu: dladdr failed\n"); abort(); }
+        return std::string(info.dli_fname);
+    }();
+    return path.c_str();
+}
+
 }  // namespace afx_emu
 
 // ---- runtime API ---------------------------------------------------------------------------------------------------
-struct afx_emu_graph { std::vector<std::function<void()>> ops; };
+struct afx_emu_graph {
+    std::vector<std::function<void()>> ops;
+    std::vector<afx_emu_stream*> forked;  // streams that joined the capture through an event (fork / join pattern)
+};
 struct afx_emu_stream { afx_emu_graph* capture = nullptr; };
 
 void afx_emu::submit(cudaStream_t st, std::function<void()> op)
@@ -248,9 +270,12 @@ void afx_emu::submit(cudaStream_t st, std::function<void()> op)
 
 const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : (e == cudaErrorNotSupported ? "not supported by the host emulation" : "emulated CUDA error"); }
 cudaError_t cudaGetLastError() { return cudaSuccess; }
-cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
-cudaError_t cudaSetDevice(int d) { return d == 0 ? cudaSuccess : cudaErrorInvalidValue; }
-cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
+// AFX_EMU_DEVICES "devices" (default 1): the multi-rank tests give every rank (= process) its own ordinal
+static int emu_devices() { const char* e = getenv("AFX_EMU_DEVICES"); const int n = e ? atoi(e) : 1; return n > 0 ? n : 1; }
+static thread_local int g_device = 0;
+cudaError_t cudaGetDeviceCount(int* n) { *n = emu_devices(); return cudaSuccess; }
+cudaError_t cudaSetDevice(int d) { if (d < 0 || d >= emu_devices()) return cudaErrorInvalidValue; g_device = d; return cudaSuccess; }
+cudaError_t cudaGetDevice(int* d) { *d = g_device; return cudaSuccess; }
 cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int)
 {
     memset(p, 0, sizeof *p);
@@ -267,14 +292,45 @@ cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr a, int)
 }
 cudaError_t cudaDeviceSetLimit(cudaLimit, size_t) { return cudaSuccess; }
 cudaError_t cudaDeviceGetStreamPriorityRange(int* lo, int* hi) { *lo = 0; *hi = -1; return cudaSuccess; }
+// "Device" memory is memfd-backed shared mappings, so that cudaIpcGetMemHandle / cudaIpcOpenMemHandle can map an allocation
+// of another rank's process (through /proc/<pid>/fd/<fd>) exactly like CUDA IPC maps a peer's buffer.
+namespace {
+struct Alloc { size_t bytes; int fd; };
+std::mutex g_alloc_mu;
+std::map<char*, Alloc> g_allocs;   // cudaMalloc'ed blocks of this process
+std::map<void*, size_t> g_opened;  // peer blocks mapped here (base -> bytes)
+struct IpcHandle { int pid, fd; unsigned long long bytes, offset; };
+static_assert(sizeof(IpcHandle) <= sizeof(cudaIpcMemHandle_t), "IPC handle fits");
+}  // namespace
 cudaError_t afx_emu_malloc(void** p, size_t bytes)
 {
-    *p = aligned_alloc(256, (bytes + 255) & ~(size_t)255);
-    if (!*p) return cudaErrorInvalidValue;
-    memset(*p, 0xCD, bytes);  // fresh device memory is not zero: poison it
+    const size_t rounded = (bytes + 4095) & ~(size_t)4095;
+    const int fd = memfd_create("afx_emu_dev", 0);
+    if (fd < 0 || ftruncate(fd, (off_t)(rounded ? rounded : 4096)) != 0) { if (fd >= 0) close(fd); return cudaErrorInvalidValue; }
+    void* m = mmap(nullptr, rounded ? rounded : 4096, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    if (m == MAP_FAILED) { close(fd); return cudaErrorInvalidValue; }
+    memset(m, 0xCD, bytes);  // fresh device memory is not zero: poison it
+    std::lock_guard<std::mutex> g(g_alloc_mu);
+    g_allocs[static_cast<char*>(m)] = Alloc{rounded ? rounded : 4096, fd};
+    *p = m;
     return cudaSuccess;
 }
-cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
+cudaError_t afx_emu_malloc_host(void** p, size_t bytes)
+{
+    *p = aligned_alloc(256, (bytes + 255) & ~(size_t)255);
+    return *p ? cudaSuccess : cudaErrorInvalidValue;
+}
+cudaError_t cudaFree(void* p)
+{
+    if (!p) return cudaSuccess;
+    std::lock_guard<std::mutex> g(g_alloc_mu);
+    auto it = g_allocs.find(static_cast<char*>(p));
+    if (it == g_allocs.end()) return cudaErrorInvalidValue;
+    munmap(p, it->second.bytes);
+    close(it->second.fd);
+    g_allocs.erase(it);
+    return cudaSuccess;
+}
 cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
 cudaError_t cudaMemcpy(void* dst, const void* src, size_t n, cudaMemcpyKind) { memmove(dst, src, n); return cudaSuccess; }
 cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t n, cudaMemcpyKind, cudaStream_t st)
@@ -292,7 +348,16 @@ cudaError_t cudaStreamCreateWithFlags(cudaStream_t* st, unsigned) { *st = new af
 cudaError_t cudaStreamCreateWithPriority(cudaStream_t* st, unsigned, int) { *st = new afx_emu_stream; return cudaSuccess; }
 cudaError_t cudaStreamDestroy(cudaStream_t st) { delete st; return cudaSuccess; }
 cudaError_t cudaStreamSynchronize(cudaStream_t st) { return (st && st->capture) ? cudaErrorInvalidValue : cudaSuccess; }
-cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
+cudaError_t cudaStreamWaitEvent(cudaStream_t st, cudaEvent_t ev, unsigned)
+{
+    // an event recorded in a capturing stream pulls the waiting stream into the same capture: what that stream is given
+    // afterwards is recorded in submission order (a valid topological order of the graph) instead of running now
+    if (st && ev && ev->captured_in && !st->capture) {
+        st->capture = static_cast<afx_emu_graph*>(ev->captured_in);
+        st->capture->forked.push_back(st);
+    }
+    return cudaSuccess;
+}
 cudaError_t cudaStreamSetAttribute(cudaStream_t, cudaStreamAttrID, const cudaStreamAttrValue*) { return cudaSuccess; }
 cudaError_t cudaStreamBeginCapture(cudaStream_t st, cudaStreamCaptureMode)
 {
@@ -304,6 +369,8 @@ cudaError_t cudaStreamEndCapture(cudaStream_t st, cudaGraph_t* g)
 {
     if (!st || !st->capture) return cudaErrorInvalidValue;
     *g = st->capture;
+    for (afx_emu_stream* f : st->capture->forked) f->capture = nullptr;
+    st->capture->forked.clear();
     st->capture = nullptr;
     return cudaSuccess;
 }
@@ -316,16 +383,184 @@ cudaError_t cudaGraphLaunch(cudaGraphExec_t e, cudaStream_t)
     return cudaSuccess;
 }
 static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
-cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new afx_emu_event{0.}; return cudaSuccess; }
-cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = new afx_emu_event{0.}; return cudaSuccess; }
+cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new afx_emu_event{0., nullptr}; return cudaSuccess; }
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = new afx_emu_event{0., nullptr}; return cudaSuccess; }
 cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
 cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t st)
 {
+    e->captured_in = (st && st->capture) ? st->capture : nullptr;
     afx_emu::submit(st, [=] { e->t_ms = now_ms(); });
     return cudaSuccess;
 }
 cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) { *ms = (float)(b->t_ms - a->t_ms); return cudaSuccess; }
-cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t*, void*) { return cudaErrorNotSupported; }
-cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
-cudaError_t cudaIpcCloseMemHandle(void*) { return cudaErrorNotSupported; }
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p)
+{
+    std::lock_guard<std::mutex> g(g_alloc_mu);
+    auto it = g_allocs.upper_bound(static_cast<char*>(p));
+    if (it == g_allocs.begin()) return cudaErrorInvalidValue;
+    --it;
+    if (static_cast<char*>(p) >= it->first + it->second.bytes) return cudaErrorInvalidValue;
+    IpcHandle ih{(int)getpid(), it->second.fd, it->second.bytes, (unsigned long long)(static_cast<char*>(p) - it->first)};
+    memset(h, 0, sizeof *h);
+    memcpy(h, &ih, sizeof ih);
+    return cudaSuccess;
+}
+cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned)
+{
+    IpcHandle ih;
+    memcpy(&ih, &h, sizeof ih);
+    char path[64];
+    snprintf(path, sizeof path, "/proc/%d/fd/%d", ih.pid, ih.fd);
+    const int fd = open(path, O_RDWR);
+    if (fd < 0) return cudaErrorNotSupported;
+    void* m = mmap(nullptr, ih.bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (m == MAP_FAILED) return cudaErrorInvalidValue;
+    std::lock_guard<std::mutex> g(g_alloc_mu);
+    g_opened[m] = ih.bytes;
+    *p = static_cast<char*>(m) + ih.offset;
+    return cudaSuccess;
+}
+cudaError_t cudaIpcCloseMemHandle(void* p)
+{
+    std::lock_guard<std::mutex> g(g_alloc_mu);
+    for (auto it = g_opened.begin(); it != g_opened.end(); ++it)
+        if (static_cast<char*>(p) >= static_cast<char*>(it->first) && static_cast<char*>(p) < static_cast<char*>(it->first) + it->second) {
+            munmap(it->first, it->second);
+            g_opened.erase(it);
+            return cudaSuccess;
+        }
+    return cudaErrorInvalidValue;
+}
+
+// ---- the NCCL entry points nccl_dl.h binds (build_emu.py points it at these): ranks are processes, the "fabric" is one
+// POSIX shared-memory segment per communicator (named by the unique id) holding a barrier, an all-reduce slot per rank and
+// a mailbox per ordered pair of ranks.  Operations are submitted to their stream like kernels, so they are captured into
+// graphs and replayed with them.
+namespace {
+constexpr size_t NCCL_SLOT_DOUBLES = 1 << 16;       // all-reduce chunk
+constexpr size_t NCCL_MAILBOX_BYTES = 4u << 20;     // one halo message
+struct NcclHeader { std::atomic<int> arrived; std::atomic<int> generation; std::atomic<int> attached; };
+struct EmuComm {
+    char* base; size_t bytes; int nranks, rank; std::string name;
+    struct Op { bool send; void* buf; size_t bytes; int peer; };
+    std::vector<Op> group;
+    NcclHeader* hdr() { return reinterpret_cast<NcclHeader*>(base); }
+    double* slot(int r) { return reinterpret_cast<double*>(base + 4096) + (size_t)r * NCCL_SLOT_DOUBLES; }
+    char* mailbox(int src, int dst) { return base + 4096 + (size_t)nranks * NCCL_SLOT_DOUBLES * 8 + ((size_t)src * nranks + dst) * NCCL_MAILBOX_BYTES; }
+    void barrier()
+    {
+        NcclHeader* h = hdr();
+        const int gen = h->generation.load();
+        if (h->arrived.fetch_add(1) + 1 == nranks) { h->arrived.store(0); h->generation.fetch_add(1); }
+        else while (h->generation.load() == gen) sched_yield();
+    }
+};
+}  // namespace
+extern "C" {
+ncclResult_t afx_emu_ncclGetUniqueId(ncclUniqueId* id)
+{
+    static std::atomic<int> counter{0};
+    memset(id, 0, sizeof *id);
+    snprintf(id->internal, sizeof id->internal, "/afx_emu_nccl_%d_%d_%lld", (int)getpid(), counter.fetch_add(1),
+             (long long)std::chrono::steady_clock::now().time_since_epoch().count());
+    return ncclSuccess;
+}
+ncclResult_t afx_emu_ncclCommInitRank(ncclComm_t* comm, int nranks, ncclUniqueId id, int rank)
+{
+    EmuComm* c = new EmuComm;
+    c->nranks = nranks; c->rank = rank; c->name = id.internal;
+    c->bytes = 4096 + (size_t)nranks * NCCL_SLOT_DOUBLES * 8 + (size_t)nranks * nranks * NCCL_MAILBOX_BYTES;
+    const int fd = shm_open(c->name.c_str(), O_CREAT | O_RDWR, 0600);
+    if (fd < 0 || ftruncate(fd, (off_t)c->bytes) != 0) { if (fd >= 0) close(fd); delete c; return ncclSystemError; }
+    void* m = mmap(nullptr, c->bytes, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_NORESERVE, fd, 0);
+    close(fd);
+    if (m == MAP_FAILED) { delete c; return ncclSystemError; }
+    c->base = static_cast<char*>(m);
+    c->hdr()->attached.fetch_add(1);
+    c->barrier();                                   // everybody has the segment: the name can go
+    if (rank == 0) shm_unlink(c->name.c_str());
+    *comm = reinterpret_cast<ncclComm_t>(c);
+    return ncclSuccess;
+}
+ncclResult_t afx_emu_ncclCommDestroy(ncclComm_t comm)
+{
+    EmuComm* c = reinterpret_cast<EmuComm*>(comm);
+    munmap(c->base, c->bytes);
+    delete c;
+    return ncclSuccess;
+}
+ncclResult_t afx_emu_ncclAllReduce(const void* send, void* recv, size_t count, ncclDataType_t dt, ncclRedOp_t op, ncclComm_t comm, cudaStream_t st)
+{
+    if (dt != ncclDouble || op != ncclSum) return ncclInternalError;
+    EmuComm* c = reinterpret_cast<EmuComm*>(comm);
+    afx_emu::submit(st, [=] {
+        const double* s = static_cast<const double*>(send);
+        double* r = static_cast<double*>(recv);
+        for (size_t o = 0; o < count; o += NCCL_SLOT_DOUBLES) {
+            const size_t n = std::min(NCCL_SLOT_DOUBLES, count - o);
+            memcpy(c->slot(c->rank), s + o, n * 8);
+            c->barrier();
+            for (size_t k = 0; k < n; ++k) {
+                double acc = 0;
+                for (int q = 0; q < c->nranks; ++q) acc += c->slot(q)[k];  // rank order on every rank: identical sums
+                r[o + k] = acc;
+            }
+            c->barrier();
+        }
+    });
+    return ncclSuccess;
+}
+ncclResult_t afx_emu_ncclGroupStart() { return ncclSuccess; }
+static thread_local EmuComm* g_group_comm = nullptr;
+static thread_local cudaStream_t g_group_stream = nullptr;
+ncclResult_t afx_emu_ncclSend(const void* buf, size_t count, ncclDataType_t dt, int peer, ncclComm_t comm, cudaStream_t st)
+{
+    if (dt != ncclDouble || count * 8 > NCCL_MAILBOX_BYTES) return ncclInternalError;
+    EmuComm* c = reinterpret_cast<EmuComm*>(comm);
+    c->group.push_back(EmuComm::Op{true, const_cast<void*>(buf), count * 8, peer});
+    g_group_comm = c; g_group_stream = st;
+    return ncclSuccess;
+}
+ncclResult_t afx_emu_ncclRecv(void* buf, size_t count, ncclDataType_t dt, int peer, ncclComm_t comm, cudaStream_t st)
+{
+    if (dt != ncclDouble || count * 8 > NCCL_MAILBOX_BYTES) return ncclInternalError;
+    EmuComm* c = reinterpret_cast<EmuComm*>(comm);
+    c->group.push_back(EmuComm::Op{false, buf, count * 8, peer});
+    g_group_comm = c; g_group_stream = st;
+    return ncclSuccess;
+}
+ncclResult_t afx_emu_ncclGroupEnd()
+{
+    EmuComm* c = g_group_comm;
+    if (!c) return ncclSuccess;  // an empty group (a rank without peers): nothing to wait for -- pairs synchronise below
+    std::vector<EmuComm::Op> ops;
+    ops.swap(c->group);
+    cudaStream_t st = g_group_stream;
+    g_group_comm = nullptr; g_group_stream = nullptr;
+    // point-to-point hand-off per ordered pair: the sender fills the pair's mailbox and raises its sequence number, the
+    // receiver waits for it, copies, and acknowledges; no collective barrier (ranks have different peer sets)
+    afx_emu::submit(st, [c, ops] {
+        struct Box { std::atomic<unsigned long long> filled, drained; };
+        auto box = [&](int src, int dst) { return reinterpret_cast<Box*>(c->mailbox(src, dst)); };
+        for (const auto& o : ops)
+            if (o.send) {
+                Box* b = box(c->rank, o.peer);
+                while (b->filled.load() != b->drained.load()) sched_yield();  // previous message still unread
+                memcpy(reinterpret_cast<char*>(b) + 64, o.buf, o.bytes);
+                b->filled.fetch_add(1);
+            }
+        for (const auto& o : ops)
+            if (!o.send) {
+                Box* b = box(o.peer, c->rank);
+                while (b->filled.load() == b->drained.load()) sched_yield();
+                memcpy(o.buf, reinterpret_cast<char*>(b) + 64, o.bytes);
+                b->drained.fetch_add(1);
+            }
+    });
+    return ncclSuccess;
+}
+const char* afx_emu_ncclGetErrorString(ncclResult_t r) { return r == ncclSuccess ? "no error" : "emulated NCCL error"; }
+ncclResult_t afx_emu_ncclGetVersion(int* v) { *v = 22809; return ncclSuccess; }
+}  // extern "C"

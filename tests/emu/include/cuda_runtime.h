@@ -60,6 +60,7 @@ void cpasync_commit();
 void cpasync_wait(int leave_pending);
 double rcp_seed(double a);    // MUFU.RCP64H: the upper word of 1/a, lower word zero
 double rsqrt_seed(double a);  // MUFU.RSQ64H
+const char* self_path();      // file name of the emulation library (nccl_dl.h binds the emulated NCCL entry points in it)
 }  // namespace afx_emu
 
 // set by the scheduler whenever a fiber is resumed (one fiber runs at a time per host thread)
@@ -92,7 +93,7 @@ enum { cudaSuccess = 0, cudaErrorInvalidValue = 1, cudaErrorNotSupported = 801, 
 struct afx_emu_stream;
 struct afx_emu_graph;
 typedef afx_emu_stream* cudaStream_t;
-struct afx_emu_event { double t_ms; };
+struct afx_emu_event { double t_ms; void* captured_in; };
 typedef afx_emu_event* cudaEvent_t;
 typedef afx_emu_graph* cudaGraph_t;
 typedef afx_emu_graph* cudaGraphExec_t;
@@ -130,8 +131,9 @@ cudaError_t cudaDeviceGetStreamPriorityRange(int* lo, int* hi);
 cudaError_t afx_emu_malloc(void** p, size_t bytes);
 template <class T>
 static inline cudaError_t cudaMalloc(T** p, size_t bytes) { return afx_emu_malloc(reinterpret_cast<void**>(p), bytes); }
+cudaError_t afx_emu_malloc_host(void** p, size_t bytes);
 template <class T>
-static inline cudaError_t cudaMallocHost(T** p, size_t bytes) { return afx_emu_malloc(reinterpret_cast<void**>(p), bytes); }
+static inline cudaError_t cudaMallocHost(T** p, size_t bytes) { return afx_emu_malloc_host(reinterpret_cast<void**>(p), bytes); }
 cudaError_t cudaFree(void* p);
 cudaError_t cudaFreeHost(void* p);
 cudaError_t cudaMemcpy(void* dst, const void* src, size_t n, cudaMemcpyKind k);

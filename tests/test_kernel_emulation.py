@@ -65,3 +65,21 @@ def test_edge_cases_under_emulation(emu_lib):
     # supersonic / transonic boundary branches, meshes smaller than a CTA, limiter extremes, NaN handling
     tail = run_gpu_tests_under_emulation(emu_lib, ["test_gpu_edge_cases.py"], "not ring_wraps")  # 120 000 iterations: GPU only
     assert " passed" in tail
+
+
+MULTI_ENV = {"AFX_EMU_DEVICES": "4", "OMP_NUM_THREADS": "3", "OMP_WAIT_POLICY": "passive"}
+
+
+def test_partitioned_runs_under_emulation(emu_lib):
+    """Ranks are processes, peer memory is a shared mapping of the other process's "device" allocation, NCCL is a
+    shared-memory segment: the halo push from the update kernel, the flag hand-off, the split launches of the NCCL mode
+    (captured across two streams) and the partition-aware k_dt_grad / k_limiter ranges run for real.  Strict mode:
+    bit-identical to the single-device run."""
+    tail = run_gpu_tests_under_emulation(emu_lib, ["test_gpu_multi.py"], "2-strict-p2p-0 or 2-strict-nccl-0 or 4-strict-p2p-1", extra_env=MULTI_ENV)
+    assert "3 passed" in tail
+
+
+def test_overlapped_peer_memory_halo_under_emulation(emu_lib):
+    # AFX_HALO_OVERLAP=1: send layer first, exchange on the halo stream under the interior update, interior limiter first
+    tail = run_gpu_tests_under_emulation(emu_lib, ["test_gpu_multi.py"], "2-strict-p2p-0", extra_env=dict(MULTI_ENV, AFX_HALO_OVERLAP="1"))
+    assert "1 passed" in tail
