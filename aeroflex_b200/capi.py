@@ -19,7 +19,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "lib")
 LIBNAME = "libaeroflex_rans_b200.so"
 
-BC_KINDS = {"farfield": 1, "slip-wall": 2, "wall": 3}          # solver.h:220-227; anything else -> 0 (internal)
+BC_KINDS = {"farfield": 1, "slip-wall": 2, "wall": 3, "inlet-outlet": 4}  # solver.h:220-227, 603-606; anything else -> 0 (internal)
 VISCOSITY = {"inviscid": 0, "laminar": 1, "spallart-allmaras": 2}  # core.h:176 (spelling is the reference's)
 GRADIENT = {"green-gauss": 0, "least-squares": 1}               # core.h:175
 FIELDS = {"q": 0, "qW": 1, "gx": 2, "gy": 3, "limiters": 4, "dt": 5, "rhs": 6}

@@ -138,4 +138,23 @@ std::vector<uint32_t> graph_tile_order(uint32_t n_total, const uint32_t* nb, std
     return cells;
 }
 
+// k pieces of (almost) equal size by the same recursive level-structure bisection: piece p = cells [start_p, start_p + size_p)
+// of the returned order.  This is the graph-growing bisection METIS uses for its initial partitions, applied recursively to
+// the cell graph itself (no coarsening / refinement passes): pieces are connected fronts of the face-neighbour graph, whatever
+// the cell shapes and sizes.
+std::vector<uint32_t> graph_partition_order(uint32_t n_total, const uint32_t* nb, std::vector<uint32_t> cells, uint32_t k,
+                                            std::vector<uint32_t>& piece_sizes)
+{
+    piece_sizes.clear();
+    if (cells.empty() || k == 0) return cells;
+    Bisector B{nb, cells, std::vector<uint32_t>(n_total, 0u), 1u, 0u, {}};
+    const uint32_t n = (uint32_t)cells.size();
+#pragma omp parallel
+#pragma omp single
+    B.split(0, n, std::min(k, n));
+    std::sort(B.leaves.begin(), B.leaves.end());
+    for (const auto& l : B.leaves) piece_sizes.push_back(l.second);
+    return cells;
+}
+
 }  // namespace afx

@@ -23,4 +23,9 @@ std::vector<uint32_t> hilbert_order(const double* x, const double* y, const std:
 std::vector<uint32_t> graph_tile_order(uint32_t n_total, const uint32_t* nb, std::vector<uint32_t> cells, uint32_t tile_cells,
                                        std::vector<uint32_t>& tile_sizes);
 
+// The same bisection cut into exactly k pieces of (almost) equal size: a METIS-style graph partition of the cell graph
+// (recursive graph-growing bisection, no multilevel refinement).  piece_sizes[p] consecutive cells of the result form piece p.
+std::vector<uint32_t> graph_partition_order(uint32_t n_total, const uint32_t* nb, std::vector<uint32_t> cells, uint32_t k,
+                                            std::vector<uint32_t>& piece_sizes);
+
 }  // namespace afx

@@ -2,6 +2,7 @@
 #include "partition.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <numeric>
 #include <stdexcept>
 #include <string>
@@ -38,14 +39,34 @@ void Partition::build(const afx_mesh_desc& g, int nranks_, int rank_)
     if ((uint32_t)nranks > N) throw std::invalid_argument("more ranks than cells");
     n_global_cells = N; n_global_ghost = G; n_global_edges = E;
 
-    // 1. global curve order and ownership
+    // 1. global order and ownership: rank r owns cells order[cut[r] .. cut[r+1])
+    //    default: Hilbert curve over rank coordinates, cut evenly;
+    //    AFX_PARTITION=graph: recursive graph bisection of the face-neighbour graph into nranks pieces (METIS-style graph
+    //    partition; pieces in breadth-first order).  Every rank computes the same deterministic result.
     std::vector<uint32_t> all(N);
     std::iota(all.begin(), all.end(), 0u);
-    const std::vector<uint32_t> order = hilbert_order(g.cells_cx, g.cells_cy, all);
+    std::vector<uint32_t> order;
+    std::vector<uint32_t> cut(nranks + 1);
+    const char* pm = getenv("AFX_PARTITION");
+    if (pm && std::string(pm) == "graph") {
+        std::vector<uint32_t> nbr((size_t)4 * N, 0xFFFFFFFFu);
+        for (uint32_t c = 0; c < N; ++c) {
+            uint32_t k = 0;
+            for_neighbours(g, c, [&](uint32_t n) { nbr[4 * (size_t)c + k++] = n; });
+        }
+        std::vector<uint32_t> sizes;
+        order = graph_partition_order(N, nbr.data(), std::move(all), (uint32_t)nranks, sizes);
+        if ((int)sizes.size() != nranks) throw std::logic_error("partition: graph bisection returned a wrong number of pieces");
+        cut[0] = 0;
+        for (int r = 0; r < nranks; ++r) cut[r + 1] = cut[r] + sizes[r];
+    } else if (pm && std::string(pm) != "hilbert" && pm[0]) {
+        throw std::invalid_argument("AFX_PARTITION must be hilbert or graph");
+    } else {
+        order = hilbert_order(g.cells_cx, g.cells_cy, all);
+        for (int r = 0; r <= nranks; ++r) cut[r] = (uint32_t)((uint64_t)r * N / nranks);
+    }
     std::vector<uint32_t> pos(N);
     for (uint32_t k = 0; k < N; ++k) pos[order[k]] = k;
-    std::vector<uint32_t> cut(nranks + 1);
-    for (int r = 0; r <= nranks; ++r) cut[r] = (uint32_t)((uint64_t)r * N / nranks);
     auto owner_of = [&](uint32_t c) { return (int)(std::upper_bound(cut.begin(), cut.end(), pos[c]) - cut.begin()) - 1; };
 
     // 2. classes: 0 owned, 1 ring 1, 2 ring 2, 255 absent
@@ -152,10 +173,12 @@ void Partition::build(const afx_mesh_desc& g, int nranks_, int rank_)
     int npatch = 0;
     for (uint32_t b = 0; b < G; ++b) npatch = std::max(npatch, g.boundary_patch[b] + 1);
     patch_xmin.assign(npatch, 0.); patch_xmax.assign(npatch, 0.); patch_ysum.assign(npatch, 0.); patch_count.assign(npatch, 0);
+    patch_order.clear();
     for (uint32_t b = 0; b < G; ++b) {
         const int p = g.boundary_patch[b];
         if (p < 0) continue;
         const uint32_t e = g.boundary_edges[b];
+        if (!patch_count[p]) patch_order.push_back(p);
         if (!patch_count[p]) { patch_xmin[p] = patch_xmax[p] = g.edges_cx[e]; patch_ysum[p] = g.edges_cy[e]; }
         else { patch_xmin[p] = std::min(patch_xmin[p], g.edges_cx[e]); patch_xmax[p] = std::max(patch_xmax[p], g.edges_cx[e]); patch_ysum[p] += g.edges_cy[e]; }
         ++patch_count[p];

@@ -2,7 +2,9 @@
 //
 // Cells are ordered along a Hilbert curve and cut into `nranks` contiguous
 // chunks (compact pieces, short interfaces; the same curve gives each GPU its
-// coalescing-friendly numbering).  Rank r keeps, in this local order,
+// coalescing-friendly numbering) -- or, with AFX_PARTITION=graph, by recursive
+// graph bisection of the face-neighbour graph (METIS-style graph partition,
+// ordering.h).  Rank r keeps, in this local order,
 //   [ owned | ring 1 | ring 2 | boundary ghosts ]
 // ring k = real cells of other ranks at graph distance k from an owned cell.
 // With both rings' STATES received after every stage update, a rank can
@@ -41,6 +43,9 @@ struct Partition {
     // global extents of every patch, for force coefficients (post.h:314-338)
     std::vector<double> patch_xmin, patch_xmax, patch_ysum;
     std::vector<uint32_t> patch_count;
+    // patch ids in the order of their first edge in the GLOBAL boundary list: solver::get_boundary_variables
+    // (solver.h:597-611) takes the far-field state of the first far-field edge of the whole mesh, which a rank may not hold
+    std::vector<int32_t> patch_order;
 
     void build(const afx_mesh_desc& g, int nranks, int rank);
     afx_mesh_desc desc() const;

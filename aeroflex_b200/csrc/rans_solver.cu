@@ -143,6 +143,9 @@ struct Solver {
     std::vector<uint8_t> h_bnd_kind;          // [G]
     std::vector<afx_bvars> h_bnd_vars;        // [G]
     std::vector<double> h_bcx, h_bcy;         // [G] boundary edge centres
+    std::vector<int32_t> patch_order;         // patch ids by first edge in the (global) boundary list
+    std::vector<uint8_t> patch_kinds;         // as given to set_bcs
+    std::vector<afx_bvars> patch_vars;
     bool bcs_set = false;
 
     // device geometry
@@ -273,9 +276,15 @@ void Solver::conservative(const afx_bvars& b, double q4[4]) const
 // solver.h:597-611
 bool Solver::boundary_variables(afx_bvars* out) const
 {
+    // The reference walks the boundary edges of the WHOLE mesh and stops at the first far-field one (or at the first
+    // "inlet-outlet" one, whose variables are the defaults).  Per patch in order of first appearance that is the same
+    // search, and it does not depend on which boundary edges this rank happens to hold.
     *out = afx_bvars{0.2, 0., 1., 1.};
-    for (uint32_t b = 0; b < G; ++b)
-        if (h_bnd_kind[b] == AFX_BC_FARFIELD) { *out = h_bnd_vars[b]; return true; }
+    for (int32_t p : patch_order) {
+        if (p < 0 || p >= (int32_t)patch_kinds.size()) continue;
+        if (patch_kinds[p] == AFX_BC_FARFIELD) { *out = patch_vars[p]; return true; }
+        if (patch_kinds[p] == AFX_BC_INLET_OUTLET) return false;
+    }
     return false;
 }
 
@@ -447,6 +456,17 @@ void Solver::create(const afx_mesh_desc& m, const afx_gas& g, int visc, int dev,
         h_perm[n] = perm;
     }
     // ---- boundary tables (reference boundary order) ----
+    patch_order.clear();
+    if (part) patch_order = part->patch_order;
+    else {
+        std::vector<uint8_t> seen;
+        for (uint32_t b = 0; b < G; ++b) {
+            const int32_t p = m.boundary_patch[b];
+            if (p < 0) continue;
+            if ((size_t)p >= seen.size()) seen.resize((size_t)p + 1, 0);
+            if (!seen[p]) { seen[p] = 1; patch_order.push_back(p); }
+        }
+    }
     h_bnd_face.resize(G); h_bnd_patch.assign(m.boundary_patch, m.boundary_patch + G);
     h_bnd_kind.assign(G, 0); h_bnd_vars.assign(G, afx_bvars{0.2, 0., 1., 1.});
     h_bcx.resize(G); h_bcy.resize(G);
@@ -568,10 +588,15 @@ void Solver::set_bcs(int n_patch, const uint8_t* kinds, const afx_bvars* vars)
     use();
     std::vector<uint8_t> h_kind(E, 0);
     std::vector<d4> h_state(G ? G : 1);
+    if (n_patch < 0 || (n_patch > 0 && (!kinds || !vars))) throw InvalidArg("null argument");
+    for (int32_t p : patch_order)  // a partition may hold no edge of a patch of the whole mesh: bcs.at still needs it
+        if (p >= n_patch) throw InvalidArg("boundary patch " + std::to_string(p) + " has no boundary condition (bcs.at)");
+    patch_kinds.assign(kinds, kinds + n_patch);
+    patch_vars.assign(vars, vars + n_patch);
     for (uint32_t b = 0; b < G; ++b) {
         const int p = h_bnd_patch[b];
         if (p < 0 || p >= n_patch) throw InvalidArg("boundary patch " + std::to_string(p) + " has no boundary condition (bcs.at)");
-        const uint8_t k = kinds[p] <= 3 ? kinds[p] : 0;
+        const uint8_t k = kinds[p] <= 3 ? kinds[p] : 0;  // anything else (AFX_BC_INLET_OUTLET included) keeps the internal flux
         h_bnd_kind[b] = k;
         h_bnd_vars[b] = (k == AFX_BC_FARFIELD) ? vars[p] : afx_bvars{0.2, 0., 1., 1.};  // solver.h:219-229
         h_kind[h_bnd_face[b]] = k;

@@ -89,7 +89,7 @@ public:
         for (int p = 0; p < np; ++p) {
             if (!used[(size_t)p]) continue;
             const boundary_condition& bc = bcs.at(m.patch_name(p));  // std::out_of_range like the reference
-            kind[(size_t)p] = bc.bc_type == "farfield" ? AFX_BC_FARFIELD : bc.bc_type == "slip-wall" ? AFX_BC_SLIPWALL : bc.bc_type == "wall" ? AFX_BC_WALL : AFX_BC_INTERNAL;
+            kind[(size_t)p] = bc.bc_type == "farfield" ? AFX_BC_FARFIELD : bc.bc_type == "slip-wall" ? AFX_BC_SLIPWALL : bc.bc_type == "wall" ? AFX_BC_WALL : bc.bc_type == "inlet-outlet" ? AFX_BC_INLET_OUTLET : AFX_BC_INTERNAL;
             vars[(size_t)p] = afx_bvars{bc.vars_far.mach, bc.vars_far.angle, bc.vars_far.T, bc.vars_far.p};
         }
         check(afx_rans_set_bcs(h_.get(), np, kind.data(), vars.data()));

@@ -44,7 +44,10 @@ typedef enum {
 } afx_status;
 
 /* edge flux kinds chosen by solver::set_bcs (solver.h:216-246) */
-enum { AFX_BC_INTERNAL = 0, AFX_BC_FARFIELD = 1, AFX_BC_SLIPWALL = 2, AFX_BC_WALL = 3 };
+enum { AFX_BC_INTERNAL = 0, AFX_BC_FARFIELD = 1, AFX_BC_SLIPWALL = 2, AFX_BC_WALL = 3,
+       /* the literal type "inlet-outlet": like every unknown type it keeps the internal flux against the ghost cell, but
+        * solver::get_boundary_variables (solver.h:597-611) stops its search at such an edge and returns the defaults */
+       AFX_BC_INLET_OUTLET = 4 };
 /* Settings::viscosity_options (core.h:176) */
 enum { AFX_VISC_INVISCID = 0, AFX_VISC_LAMINAR = 1, AFX_VISC_SA = 2 };
 /* Settings::gradient_options (core.h:175), by meaning not by index */

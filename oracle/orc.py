@@ -19,7 +19,7 @@ f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
 
 INTERNAL, FARFIELD, SLIPWALL, WALL = 0, 1, 2, 3
 GREEN_GAUSS, LEAST_SQUARES = 0, 1
-KIND_OF = {"farfield": FARFIELD, "slip-wall": SLIPWALL, "wall": WALL}
+KIND_OF = {"farfield": FARFIELD, "slip-wall": SLIPWALL, "wall": WALL, "inlet-outlet": 4}  # 4: solver.h:603-606
 VISC_OF = {"inviscid": 0, "laminar": 1, "spallart-allmaras": 2}
 
 

@@ -447,7 +447,7 @@ void orc_set_bcs(orc_solver *s, int npatch, const uint8_t *patch_kind, const orc
         orc_bvars dflt = {0.2, 0, 1, 1.}; /* core.h:62-65 */
         s->bnd_kind[b] = kind;
         s->bnd_vars[b] = (kind == ORC_FARFIELD) ? patch_vars[p] : dflt; /* solver.h:219-229 */
-        s->edge_kind[m->bnd_edge[b]] = kind;
+        s->edge_kind[m->bnd_edge[b]] = kind <= ORC_WALL ? kind : ORC_INTERNAL; /* "inlet-outlet" has no flux class: solver.h:237-245 */
     }
 }
 
@@ -488,8 +488,10 @@ int orc_boundary_variables(const orc_solver *s, orc_bvars *out)
 {
     orc_bvars dflt = {0.2, 0, 1, 1.};
     *out = dflt;
-    for (uint32_t b = 0; b < s->m.G; ++b)
+    for (uint32_t b = 0; b < s->m.G; ++b) {
         if (s->bnd_kind[b] == ORC_FARFIELD) { *out = s->bnd_vars[b]; return 1; }
+        if (s->bnd_kind[b] == ORC_INLET_OUTLET) { *out = s->bnd_vars[b]; return 0; } /* solver.h:603-606: the defaults */
+    }
     return 0;
 }
 

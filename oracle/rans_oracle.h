@@ -31,7 +31,8 @@ extern "C" {
 #define ORC_EDGE_NULL 0xFFFFFFFFu /* mesh.h:35 */
 
 /* edge flux kinds, solver.h:203-246 */
-enum { ORC_INTERNAL = 0, ORC_FARFIELD = 1, ORC_SLIPWALL = 2, ORC_WALL = 3 };
+enum { ORC_INTERNAL = 0, ORC_FARFIELD = 1, ORC_SLIPWALL = 2, ORC_WALL = 3,
+       ORC_INLET_OUTLET = 4 /* flux of an unknown type (internal), but get_boundary_variables stops here: solver.h:603-606 */ };
 /* gradient schemes, solver.h:428,470 */
 enum { ORC_GREEN_GAUSS = 0, ORC_LEAST_SQUARES = 1 };
 

@@ -137,3 +137,20 @@ def test_residual_history_ring_wraps(afx, gpu):
     for norms, q in outs[1:]:
         assert np.array_equal(norms, outs[0][0]) and np.array_equal(q, outs[0][1])
     assert np.all(np.isfinite(outs[0][0])) and outs[0][0][-1] < outs[0][0][0]
+
+
+@pytest.mark.parametrize("tag,typ", [("inlet_outlet", "inlet-outlet"), ("unknown", "something-else")])
+def test_boundary_variables_search_vs_reference_golden(afx, gpu, tag, typ):
+    """solver.h:597-611 through the C ABI (AFX_BC_INLET_OUTLET): init(), the uniform-flow residual and the force rotation
+    take the far-field state of the first far-field edge unless an "inlet-outlet" edge comes first."""
+    g = H.load("bc_quirks")
+    d = H.load("naca0012q_coarse_euler_gg_o2")
+    m = H.product_mesh(afx, d)
+    s = afx.GpuSolver(m, math="strict")
+    s.set_bcs({"farfield": (typ, None), "wall": ("farfield", dict(mach=0.3, angle=0.05, T=1.0, p=1.0))})
+    s.set_options(True, "green-gauss", 5.0, 1.2); s.init(); s.refill_bcs()
+    assert np.array_equal(s.get_q(), g[tag + "_q_init"])
+    assert s.get_uniform_residual() == pytest.approx(float(g[tag + "_uniform_residual"]), rel=NORM_RTOL)
+    norms = s.run(3, 0.9)
+    np.testing.assert_allclose(norms, g[tag + "_norms"], rtol=NORM_RTOL)
+    assert np.array_equal(s.get_q(), g[tag + "_q"])

@@ -45,6 +45,8 @@ def _worker(rank, world, port, n_iter, out_dir, math, halo, fused):
     assert s.halo_mode() == halo
     assert s.tile_info()["fused"] == bool(fused)
     s.set_bcs(BCS); s.set_options(True, "green-gauss", 5.0, 1.4); s.init(); s.refill_bcs()
+    qi = np.full(4 * (mesh.N + mesh.G), np.nan)
+    s.get_q(qi)  # init() + refill_bcs() of this rank's piece, in global numbering
     q0 = np.load(os.path.join(out_dir, "q0.npy"))
     s.set_q(q0)
     ur = s.get_uniform_residual()
@@ -52,7 +54,8 @@ def _worker(rank, world, port, n_iter, out_dir, math, halo, fused):
     out = np.full(4 * (mesh.N + mesh.G), np.nan)
     s.get_q(out)
     forces = s.wall_forces("wall")
-    np.savez(os.path.join(out_dir, "r%d.npz" % rank), q=out, norms=norms, forces=np.array(forces), owned=part.cell_l2g[:part.n_own], ur=ur)
+    np.savez(os.path.join(out_dir, "r%d.npz" % rank), q=out, norms=norms, forces=np.array(forces), owned=part.cell_l2g[:part.n_own], ur=ur,
+             q_init=qi)
     dist.destroy_process_group()
 
 
@@ -65,6 +68,7 @@ def test_partitioned_run_matches_single_gpu(afx, gpu, tmp_path, world, math, hal
     n_iter = 25
     mesh = afx.Mesh.synth_omesh(*DIMS, 150.0)
     single, q0 = _q0(afx, mesh)
+    q_init = single.get_q().reshape(-1, 4)  # init() + refill_bcs() on one GPU
     np.save(tmp_path / "q0.npy", q0)
     single.set_q(q0)
     ur = single.get_uniform_residual()
@@ -78,6 +82,8 @@ def test_partitioned_run_matches_single_gpu(afx, gpu, tmp_path, world, math, hal
         d = np.load(tmp_path / ("r%d.npz" % r))
         own = d["owned"]
         got = d["q"].reshape(-1, 4)[own]
+        # a rank that holds no far-field edge still initialises with the far-field state of the whole mesh (solver.h:597-631)
+        assert np.array_equal(d["q_init"].reshape(-1, 4)[own], q_init[own])
         if math == "strict":
             assert np.array_equal(got, Q[own])  # bit-identical to the single-GPU strict run (itself bit-identical to the oracle)
             np.testing.assert_allclose(d["norms"], ref_norms, rtol=1e-12)

@@ -83,3 +83,9 @@ def test_overlapped_peer_memory_halo_under_emulation(emu_lib):
     # AFX_HALO_OVERLAP=1: send layer first, exchange on the halo stream under the interior update, interior limiter first
     tail = run_gpu_tests_under_emulation(emu_lib, ["test_gpu_multi.py"], "2-strict-p2p-0", extra_env=dict(MULTI_ENV, AFX_HALO_OVERLAP="1"))
     assert "1 passed" in tail
+
+
+def test_graph_partitioned_run_under_emulation(emu_lib):
+    # AFX_PARTITION=graph: recursive graph bisection instead of Hilbert chunks; same bit-identity to the single-device run
+    tail = run_gpu_tests_under_emulation(emu_lib, ["test_gpu_multi.py"], "2-strict-p2p-0 or 4-strict-p2p-1", extra_env=dict(MULTI_ENV, AFX_PARTITION="graph"))
+    assert "2 passed" in tail

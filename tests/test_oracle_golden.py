@@ -106,3 +106,19 @@ def test_threaded_port_is_bit_identical_to_the_serial_restatement(tag):
     nb = [b.explicit_solve_omp(meta["relax"]) for _ in range(5)]
     assert np.array_equal(a.q, b.q) and np.array_equal(a.qW, b.qW)
     np.testing.assert_allclose(na, nb, rtol=1e-14)
+
+
+@pytest.mark.parametrize("tag,typ", [("inlet_outlet", "inlet-outlet"), ("unknown", "something-else")])
+def test_boundary_variables_search_matches_reference(tag, typ):
+    """solver.h:597-611: the far-field state is that of the first "farfield" boundary edge, unless an edge of the literal
+    type "inlet-outlet" comes first (then the defaults).  Golden vectors from the unmodified reference headers
+    (oracle/make_golden_bc_quirks.py)."""
+    g = H.load("bc_quirks")
+    d = H.load("naca0012q_coarse_euler_gg_o2")
+    o = orc.OracleSolver(H.oracle_mesh(d))
+    o.set_bcs({"farfield": (typ, None), "wall": ("farfield", dict(mach=0.3, angle=0.05, T=1.0, p=1.0))})
+    o.set_options(True, "green-gauss", 5.0, 1.2); o.init(); o.refill_bcs()
+    assert np.array_equal(o.q, g[tag + "_q_init"])
+    assert o.uniform_residual() == float(g[tag + "_uniform_residual"])
+    norms = [o.explicit_solve(0.9) for _ in range(3)]
+    assert np.array_equal(norms, g[tag + "_norms"]) and np.array_equal(o.q, g[tag + "_q"])

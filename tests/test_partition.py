@@ -22,8 +22,12 @@ def neighbours(mesh):
     return nb
 
 
+@pytest.mark.parametrize("method", ["hilbert", "graph"])
 @pytest.mark.parametrize("nranks", [2, 3, 8])
-def test_partition_plan_is_consistent(afx, nranks):
+def test_partition_plan_is_consistent(afx, monkeypatch, nranks, method):
+    """AFX_PARTITION=hilbert (default): even cuts of the Hilbert curve; =graph: recursive graph bisection of the
+    face-neighbour graph (METIS-style).  Same plan contract for both."""
+    monkeypatch.setenv("AFX_PARTITION", method)
     mesh = afx.Mesh.synth_omesh(64, 40, 16, 40.0)
     N = mesh.N
     nb = neighbours(mesh)
@@ -112,6 +116,33 @@ def _worker(rank, world, port, n_iter, out_dir):
     np.savez(os.path.join(out_dir, "rank%d.npz" % rank), q=o.q.reshape(-1, 4)[:n_own], cells=part.cell_l2g[:n_own], norms=np.array(norms),
              ghosts_q=o.q.reshape(-1, 4)[NL:], ghosts=part.cell_l2g[NL:])
     dist.destroy_process_group()
+
+
+def test_graph_partition_pieces_are_connected_and_cut_less_than_the_curve(afx, monkeypatch):
+    """Each piece of the graph partition is one connected component of the cell graph, and on the stretched O-mesh its halo
+    is no larger than that of the Hilbert chunks (2 ranks: 512 against 640 ring cells on the 65 536-cell mesh)."""
+    mesh = afx.Mesh.synth_omesh(256, 160, 64, 150.0)
+    nb = neighbours(mesh)
+    halo = {}
+    for method in ("hilbert", "graph"):
+        monkeypatch.setenv("AFX_PARTITION", method)
+        parts = [afx.Partition(mesh, 2, r) for r in range(2)]
+        halo[method] = max(p.n_r1 + p.n_r2 for p in parts)
+        if method == "graph":
+            for p in parts:
+                own = set(int(c) for c in p.cell_l2g[:p.n_own])
+                seen, stack = set(), [next(iter(own))]
+                while stack:
+                    c = stack.pop()
+                    if c in seen:
+                        continue
+                    seen.add(c)
+                    stack.extend(n for n in nb[c] if n in own and n not in seen)
+                assert seen == own
+    assert halo["graph"] <= halo["hilbert"]
+    monkeypatch.setenv("AFX_PARTITION", "metis")
+    with pytest.raises(afx.AfxError):
+        afx.Partition(mesh, 2, 0)
 
 
 def test_two_rank_gloo_run_reproduces_single_domain(afx, tmp_path):
