@@ -60,7 +60,8 @@ def _worker(rank, world, port, n_iter, out_dir, math, halo, fused):
 
 
 @pytest.mark.parametrize("world,math,halo,fused", [(2, "strict", "nccl", 0), (2, "strict", "p2p", 0), (2, "fast", "p2p", 0),
-                                                   (2, "strict", "p2p", 1), (2, "strict", "nccl", 1), (4, "strict", "p2p", 1)])
+                                                   (2, "strict", "p2p", 1), (2, "strict", "nccl", 1), (4, "strict", "p2p", 1),
+                                                   (8, "strict", "p2p", 0), (8, "fast", "p2p", 1)])
 def test_partitioned_run_matches_single_gpu(afx, gpu, tmp_path, world, math, halo, fused):
     if gpu < world:
         pytest.skip("needs %d GPUs, %d visible" % (world, gpu))
