@@ -17,16 +17,16 @@ def _free_port():
     return port
 
 
-def _q0(afx, mesh):
-    s = afx.GpuSolver(mesh, viscosity="spallart-allmaras", math="strict", device=0)
-    s.set_bcs(BCS); s.set_options(True, "green-gauss", 5.0, 1.4); s.init(); s.refill_bcs()
+def _q0(afx, mesh, visc="spallart-allmaras", grad="green-gauss", so=True):
+    s = afx.GpuSolver(mesh, viscosity=visc, math="strict", device=0)
+    s.set_bcs(BCS); s.set_options(so, grad, 5.0, 1.4); s.init(); s.refill_bcs()
     q = s.get_q()
     rng = np.random.default_rng(77)
     q[:4 * mesh.N] *= 1 + 1e-3 * rng.uniform(-1, 1, 4 * mesh.N)
     return s, q
 
 
-def _worker(rank, world, port, n_iter, out_dir, math, halo, fused):
+def _worker(rank, world, port, n_iter, out_dir, math, halo, fused, visc="spallart-allmaras", grad="green-gauss", so=True):
     import torch.distributed as dist
     import aeroflex_b200 as afx
     if fused:
@@ -37,14 +37,14 @@ def _worker(rank, world, port, n_iter, out_dir, math, halo, fused):
     part = afx.Partition(mesh, world, rank)
     ids = [afx.nccl_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(ids, src=0)
-    s = afx.GpuSolver(part, viscosity="spallart-allmaras", math=math, device=rank, nccl_id=ids[0])
+    s = afx.GpuSolver(part, viscosity=visc, math=math, device=rank, nccl_id=ids[0])
     if halo == "p2p":  # NVLink peer-memory halo: all-gather the IPC blobs, map the peers' receive buffers
         blobs = [None] * world
         dist.all_gather_object(blobs, s.p2p_export())
         s.p2p_connect(blobs)
     assert s.halo_mode() == halo
     assert s.tile_info()["fused"] == bool(fused)
-    s.set_bcs(BCS); s.set_options(True, "green-gauss", 5.0, 1.4); s.init(); s.refill_bcs()
+    s.set_bcs(BCS); s.set_options(so, grad, 5.0, 1.4); s.init(); s.refill_bcs()
     qi = np.full(4 * (mesh.N + mesh.G), np.nan)
     s.get_q(qi)  # init() + refill_bcs() of this rank's piece, in global numbering
     q0 = np.load(os.path.join(out_dir, "q0.npy"))
@@ -54,8 +54,12 @@ def _worker(rank, world, port, n_iter, out_dir, math, halo, fused):
     out = np.full(4 * (mesh.N + mesh.G), np.nan)
     s.get_q(out)
     forces = s.wall_forces("wall")
+    rhs_norm = s.residual()  # implicitSolver::fillRhoRHS on the partitioned state: norm all-reduced, vector per rank
+    rhs = np.full(4 * (mesh.N + mesh.G), np.nan)
+    loc = s.get("rhs").reshape(-1, 4)
+    rhs.reshape(-1, 4)[part.cell_l2g[:part.n_own]] = loc[:part.n_own]
     np.savez(os.path.join(out_dir, "r%d.npz" % rank), q=out, norms=norms, forces=np.array(forces), owned=part.cell_l2g[:part.n_own], ur=ur,
-             q_init=qi)
+             q_init=qi, rhs=rhs, rhs_norm=rhs_norm)
     dist.destroy_process_group()
 
 
@@ -96,3 +100,36 @@ def test_partitioned_run_matches_single_gpu(afx, gpu, tmp_path, world, math, hal
             np.testing.assert_allclose(d["forces"], F, rtol=1e-8, atol=1e-12)
         seen += len(own)
     assert seen == mesh.N
+
+
+@pytest.mark.parametrize("world,visc,grad,so,halo", [(3, "laminar", "least-squares", True, "p2p"), (2, "laminar", "green-gauss", True, "nccl"),
+                                                      (3, "inviscid", "green-gauss", False, "p2p"), (5, "spallart-allmaras", "least-squares", True, "p2p")])
+def test_partitioned_variants_match_single_gpu(afx, gpu, tmp_path, world, visc, grad, so, halo):
+    """Odd rank counts, the laminar face-gradient path (ftij, iteration-start state), least-squares gradients and first-order
+    runs in a partitioned solver; also the implicit right-hand side (afx_rans_residual) of a partitioned state."""
+    if gpu < world:
+        pytest.skip("needs %d GPUs, %d visible" % (world, gpu))
+    import torch.multiprocessing as mp
+    n_iter = 8
+    mesh = afx.Mesh.synth_omesh(*DIMS, 150.0)
+    single, q0 = _q0(afx, mesh, visc, grad, so)
+    if visc == "laminar":  # keep the perturbation small enough for the viscous terms at this CFL
+        base = single.get_q()
+        q0 = base + 0.1 * (q0 - base)
+    np.save(tmp_path / "q0.npy", q0)
+    single.set_q(q0)
+    ref_norms = single.run(n_iter, 0.9)
+    Q = single.get_q().reshape(-1, 4)
+    F = np.array(single.wall_forces("wall"))
+    rhs_norm = single.residual()
+    RHS = single.get("rhs").reshape(-1, 4)
+    del single
+    mp.spawn(_worker, args=(world, _free_port(), n_iter, str(tmp_path), "strict", halo, 0, visc, grad, so), nprocs=world, join=True)
+    for r in range(world):
+        d = np.load(tmp_path / ("r%d.npz" % r))
+        own = d["owned"]
+        assert np.array_equal(d["q"].reshape(-1, 4)[own], Q[own])
+        np.testing.assert_allclose(d["norms"], ref_norms, rtol=1e-12)
+        np.testing.assert_allclose(d["forces"], F, rtol=1e-12, atol=1e-15)
+        assert np.array_equal(d["rhs"].reshape(-1, 4)[own], RHS[own])
+        assert float(d["rhs_norm"]) == pytest.approx(rhs_norm, rel=1e-12)

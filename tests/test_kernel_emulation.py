@@ -90,3 +90,9 @@ def test_graph_partitioned_run_under_emulation(emu_lib):
     # AFX_PARTITION=graph: recursive graph bisection instead of Hilbert chunks; same bit-identity to the single-device run
     tail = run_gpu_tests_under_emulation(emu_lib, ["test_gpu_multi.py"], "2-strict-p2p-0 or 4-strict-p2p-1", extra_env=dict(MULTI_ENV, AFX_PARTITION="graph"))
     assert "2 passed" in tail
+
+
+def test_partitioned_variants_under_emulation(emu_lib):
+    # 3 ranks, laminar face gradients + least squares; 3 ranks first order; partitioned implicit right-hand side
+    tail = run_gpu_tests_under_emulation(emu_lib, ["test_gpu_multi.py"], "variants and (3-laminar or 3-inviscid)", extra_env=MULTI_ENV)
+    assert "2 passed" in tail
