@@ -48,9 +48,9 @@ limiter_k = 5.0
 
 
 def _build(afx, src, out):
-    lib_dir = os.path.dirname(afx.library_path())
+    lib = os.path.realpath(afx.library_path())  # linked by file name: AFX_LIB may name a differently tuned build
     subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-fopenmp", "-Wall", "-Werror", "-I" + HOST, "-o", str(out), src,
-                    "-L" + lib_dir, "-laeroflex_rans_b200", "-Wl,-rpath," + lib_dir], check=True)
+                    "-L" + os.path.dirname(lib), "-l:" + os.path.basename(lib), "-Wl,-rpath," + os.path.dirname(lib)], check=True)
     return str(out)
 
 

@@ -96,3 +96,9 @@ def test_partitioned_variants_under_emulation(emu_lib):
     # 3 ranks, laminar face gradients + least squares; 3 ranks first order; partitioned implicit right-hand side
     tail = run_gpu_tests_under_emulation(emu_lib, ["test_gpu_multi.py"], "variants and (3-laminar or 3-inviscid)", extra_env=MULTI_ENV)
     assert "2 passed" in tail
+
+
+def test_cpp_adapter_cli_under_emulation(emu_lib):
+    # the C++ host adapter end to end (rans::Rans::solve_airfoil -> multigrid<gpuSolver> FMG, explicit) linked against the emulation
+    tail = run_gpu_tests_under_emulation(emu_lib, ["test_cpp_host.py"], "explicit_mode")
+    assert "1 passed" in tail
