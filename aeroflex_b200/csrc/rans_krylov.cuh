@@ -11,7 +11,10 @@
 namespace afx {
 namespace AFX_NS {
 
-constexpr int KRY_BLOCKS = 592;  // 4 CTAs per SM on 148 SMs: the reduction grid
+#ifndef AFX_KRY_BLOCKS
+#define AFX_KRY_BLOCKS 592  // 4 CTAs per SM on 148 SMs: the reduction grid
+#endif
+constexpr int KRY_BLOCKS = AFX_KRY_BLOCKS;
 
 __device__ __forceinline__ d4 blk_mul(const d4* __restrict__ B, const d4& x)
 {

@@ -306,7 +306,9 @@ def test_implicit_converged_forces_match_reference(afx, gpu, math):
     assert cl == pytest.approx(float(g["cl"][0]), rel=1e-7)
     assert cd == pytest.approx(float(g["cd"][0]), rel=1e-6)
     assert cm == pytest.approx(float(g["cm"][0]), rel=1e-6)
-    print("implicit outer iterations:", len(hist), "last linear iterations:", s.last_linear_iterations())@pytest.mark.gpu
+    print("implicit outer iterations:", len(hist), "last linear iterations:", s.last_linear_iterations())
+
+
 @pytest.mark.parametrize("grad,visc,math", [("green-gauss", "inviscid", "strict"), ("least-squares", "laminar", "strict"), ("green-gauss", "spallart-allmaras", "fast")])
 def test_first_stage_limiter_inside_dt_grad_is_bit_identical(afx, gpu, monkeypatch, grad, visc, math):
     """k_dt_grad<.,1> writes the first stage's limiters itself (one k_limiter launch less per iteration): same
