@@ -39,7 +39,7 @@ EXPORTED_SYMBOLS = [
     "afx_rans_run_explicit", "afx_rans_phase_dt_gradients", "afx_rans_phase_limiters", "afx_rans_phase_residual",
     "afx_rans_residual", "afx_rans_fill_jacobian", "afx_rans_get_jacobian_blocks", "afx_rans_step_implicit", "afx_rans_compute",
     "afx_rans_set_linear_solver", "afx_rans_last_linear_iterations",
-    "afx_rans_wall_forces", "afx_rans_wall_cp", "afx_rans_last_device_ms", "afx_rans_launch_count",
+    "afx_rans_wall_forces", "afx_rans_wall_cp", "afx_rans_sweep", "afx_rans_last_device_ms", "afx_rans_launch_count",
     "afx_rans_profile_explicit",
 ]
 
@@ -56,6 +56,11 @@ class Gas(C.Structure):
 
 class BVars(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("mach", "angle", "T", "p")]
+
+
+class SweepSettings(C.Structure):
+    _fields_ = [("implicit", C.c_int), ("relaxation", C.c_double), ("start_cfl", C.c_double), ("slope_cfl", C.c_double),
+                ("max_cfl", C.c_double), ("tolerance", C.c_double), ("rhs_iterations", C.c_int), ("max_iterations", C.c_int)]
 
 
 class MeshDesc(C.Structure):
@@ -192,6 +197,7 @@ def load_library():
     L.afx_rans_last_linear_iterations.argtypes = [vp]
     L.afx_rans_wall_forces.argtypes = [vp, C.c_int, vp]
     L.afx_rans_wall_cp.argtypes = [vp, C.c_int, vp]
+    L.afx_rans_sweep.argtypes = [vp, C.POINTER(SweepSettings), C.c_int, C.c_int, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp]
     L.afx_rans_last_device_ms.argtypes = [vp, dp]
     L.afx_rans_launch_count.restype = C.c_int64
     L.afx_rans_launch_count.argtypes = [vp]
@@ -569,6 +575,21 @@ class GpuSolver:
         p = self.mesh.patch_names.index(patch_name) if patch_name in self.mesh.patch_names else -1
         _check(self.L.afx_rans_wall_forces(self.h, p, _ptr(out)))
         return tuple(out)  # cl, cd, cm
+
+    def sweep(self, alphas_deg, implicit=True, relaxation=0.9, start_cfl=40.0, slope_cfl=50.0, max_cfl=100.0, tolerance=1e-4,
+              rhs_iterations=5, max_iterations=300, farfield="farfield", wall="wall", reinit=True):
+        """Rans::run_airfoil's angle loop on this mesh level (rans.h:86-104): returns dict(cl, cd, cm, iterations, residual)."""
+        al = np.ascontiguousarray(alphas_deg, dtype=np.float64)
+        n = len(al)
+        st = SweepSettings(int(bool(implicit)), relaxation, start_cfl, slope_cfl, max_cfl, tolerance, rhs_iterations, max_iterations)
+        cl, cd, cm, res = (np.full(n, np.nan) for _ in range(4))
+        it = np.zeros(n, np.int32)
+        names = self.mesh.patch_names
+        rc = self.L.afx_rans_sweep(self.h, C.byref(st), names.index(farfield), names.index(wall), _ptr(al), n, int(bool(reinit)),
+                                   _ptr(cl), _ptr(cd), _ptr(cm), _ptr(it), _ptr(res))
+        if rc not in (0, -3):
+            _check(rc)
+        return dict(cl=cl, cd=cd, cm=cm, iterations=it, residual=res, status=rc)
 
     def wall_cp(self, patch_name):
         p = self.mesh.patch_names.index(patch_name)

@@ -1771,6 +1771,61 @@ int afx_rans_wall_cp(afx_rans* s, int patch, double* cp)
     return rc ? rc : count;
 }
 
+int afx_rans_sweep(afx_rans* s, const afx_sweep_settings* st, int farfield_patch, int wall_patch, const double* alphas_deg, int n_alpha,
+                   int reinit, double* cl, double* cd, double* cm, int* iterations, double* residual)
+{
+    if (!s || !st || (n_alpha > 0 && !alphas_deg)) { afx::set_error("null argument"); return AFX_ERR_INVALID; }
+    auto& S = s->s;
+    if (!S.bcs_set) { afx::set_error("set_bcs has not been called"); return AFX_ERR_INVALID; }
+    if (farfield_patch < 0 || farfield_patch >= (int)S.patch_kinds.size() || S.patch_kinds[(size_t)farfield_patch] != AFX_BC_FARFIELD) {
+        afx::set_error("farfield_patch is not a far-field patch of the last set_bcs");
+        return AFX_ERR_INVALID;
+    }
+    if (st->implicit && S.halo) { afx::set_error("the implicit step is single-GPU in this version"); return AFX_ERR_INVALID; }
+    if (n_alpha <= 0) return AFX_OK;
+    int rc = AFX_OK;
+    // rans.h:86-88: the first angle is in place when the field is initialised
+    auto apply_alpha = [&](double alpha_deg) {
+        std::vector<uint8_t> kinds(S.patch_kinds);
+        std::vector<afx_bvars> vars(S.patch_vars);
+        vars[(size_t)farfield_patch].angle = alpha_deg * 0.01745;
+        return afx_rans_set_bcs(s, (int)kinds.size(), kinds.data(), vars.data());
+    };
+    if ((rc = apply_alpha(alphas_deg[0])) != AFX_OK) return rc;
+    if (reinit && (rc = afx_rans_init(s)) != AFX_OK) return rc;
+    for (int a = 0; a < n_alpha; ++a) {
+        if ((rc = apply_alpha(alphas_deg[a])) != AFX_OK) return rc;            // rans.h:94-97
+        if ((rc = afx_rans_refill_bcs(s)) != AFX_OK) return rc;                // multigrid.h:303
+        double err_0 = 0, err = 0, cfl = st->start_cfl;
+        if ((rc = afx_rans_uniform_residual(s, &err_0)) != AFX_OK) return rc;
+        int i = 0;
+        do {                                                                   // multigrid.h:190-236 / 247-292
+            afx_rans_set_cfl(s, cfl);
+            if (st->implicit) {
+                if ((rc = afx_rans_fill_jacobian(s)) != AFX_OK) return rc;
+                rc = afx_rans_compute(s);
+                if (rc == AFX_OK) rc = afx_rans_step_implicit(s, st->relaxation, err_0 * st->tolerance, st->rhs_iterations, &err);
+            } else {
+                rc = afx_rans_step_explicit(s, st->relaxation, &err);
+            }
+            if (rc == AFX_ERR_NUMERIC) { if (iterations) iterations[a] = i + 1; if (residual) residual[a] = -1; return rc; }
+            if (rc != AFX_OK) return rc;
+            if (i == 0 && err > 2 * err_0) err_0 = err;
+            err /= err_0;
+            if (st->implicit) cfl = std::min(st->start_cfl + (i + 1) * st->slope_cfl, st->max_cfl);
+            ++i;
+        } while (err > st->tolerance && i < st->max_iterations);
+        double f[3];
+        if ((rc = afx_rans_wall_forces(s, wall_patch, f)) != AFX_OK) return rc;  // rans.h:99-102
+        if (cl) cl[a] = f[0];
+        if (cd) cd[a] = f[1];
+        if (cm) cm[a] = f[2];
+        if (iterations) iterations[a] = i;
+        if (residual) residual[a] = err;
+    }
+    return AFX_OK;
+}
+
 int afx_rans_last_device_ms(afx_rans* s, double* ms) { *ms = s->s.last_ms; return AFX_OK; }
 int64_t afx_rans_launch_count(afx_rans* s) { return s->s.launches; }
 

@@ -252,6 +252,24 @@ int afx_rans_wall_forces(afx_rans* s, int patch, double out_cl_cd_cm[3]);
 int afx_rans_wall_cp(afx_rans* s, int patch, double* cp);
 
 /* device time of the kernels of the last step/run call, milliseconds (CUDA events on the solver's stream) */
+/* Warm-started angle-of-attack sweep on one mesh level -- the per-angle body of Rans::run_airfoil (rans.h:86-104) with
+ * multigrid<T>::run_solver (multigrid.h:182-293) inside the library: the far-field angle of `farfield_patch` is set to
+ * alpha * 0.01745 (the reference's deg -> rad literal, rans.h:94) and set_bcs is applied; init() runs once before the
+ * first angle if `reinit`; then per angle refill_bcs(), the pseudo-time loop (explicit: constant CFL start_cfl; implicit:
+ * fill + compute + solve with the CFL ramp start_cfl + (i+1) slope_cfl <= max_cfl and rhs_iterations sub-iterations)
+ * until residual / uniform-flow residual <= tolerance or max_iterations, and get_wall_profile of `wall_patch`
+ * (post.h:301-387).  cl/cd/cm/iterations/residual have n_alpha entries (any may be NULL).  A chain of angles per GPU is
+ * how the polar database of the VLM viscous correction is sharded (BASELINE config 5: no communication between chains).
+ * Returns AFX_ERR_NUMERIC where the reference's run_solver returns 1 (the angles done so far are filled in).
+ * Partitioned handles: explicit only, called by every rank. */
+typedef struct afx_sweep_settings {
+    int implicit;            /* 0: explicitSolver, 1: implicitSolver */
+    double relaxation, start_cfl, slope_cfl, max_cfl, tolerance;
+    int rhs_iterations, max_iterations;
+} afx_sweep_settings;
+int afx_rans_sweep(afx_rans* s, const afx_sweep_settings* settings, int farfield_patch, int wall_patch, const double* alphas_deg,
+                   int n_alpha, int reinit, double* cl, double* cd, double* cm, int* iterations, double* residual);
+
 int afx_rans_last_device_ms(afx_rans* s, double* ms);
 /* kernels launched by this handle since creation (bench.py's gpu_launches) */
 int64_t afx_rans_launch_count(afx_rans* s);

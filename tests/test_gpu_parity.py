@@ -338,3 +338,50 @@ def test_first_stage_limiter_inside_dt_grad_is_bit_identical(afx, gpu, monkeypat
 
 
 
+
+
+def test_sweep_entry_point_matches_reference_polar_and_the_primitive_calls(afx, gpu):
+    """afx_rans_sweep = the angle loop of Rans::run_airfoil (rans.h:86-104) + multigrid::run_solver (multigrid.h:182-293) on
+    one level.  Implicit, both sides driven to 1e-10: the converged CL/CD/CM of the reference's own sweep
+    (golden sweep_naca0012q_coarse.npz).  Explicit: identical, to the bit, to the same loop written with the primitive
+    ABI calls (as the C++ adapter does)."""
+    g = H.load("sweep_naca0012q_coarse")
+    d = H.load("naca0012q_coarse_euler_gg_o2")
+    m = H.product_mesh(afx, d)
+    bcs = {"farfield": ("farfield", dict(mach=0.2, angle=0.0, T=1.0, p=1.0)), "wall": ("slip-wall", None)}
+    s = afx.GpuSolver(m, math="strict")
+    s.set_bcs(bcs); s.set_options(True, "green-gauss", 5.0, 40.0)
+    r = s.sweep(g["alphas"], implicit=True, tolerance=1e-10, max_iterations=400)
+    assert r["status"] == 0 and np.all(r["residual"] <= 1e-10) and np.all(r["iterations"] < 400)
+    np.testing.assert_allclose(r["cl"], g["cl"], rtol=1e-7)
+    np.testing.assert_allclose(r["cd"], g["cd"], rtol=1e-6)
+    np.testing.assert_allclose(r["cm"], g["cm"], rtol=1e-6)
+    # explicit, loose tolerance, against the primitive calls
+    alphas = [1.0, 2.5]
+    a = afx.GpuSolver(m, math="strict")
+    a.set_bcs(bcs); a.set_options(True, "green-gauss", 5.0, 1.5)
+    ra = a.sweep(alphas, implicit=False, relaxation=0.9, start_cfl=1.5, tolerance=0.2, max_iterations=150)
+    b = afx.GpuSolver(m, math="strict")
+    b.set_options(True, "green-gauss", 5.0, 1.5)
+    forces, iters = [], []
+    for k, al in enumerate(alphas):
+        bb = dict(bcs); bb["farfield"] = ("farfield", dict(mach=0.2, angle=al * 0.01745, T=1.0, p=1.0))
+        b.set_bcs(bb)
+        if k == 0:
+            b.init()
+        b.refill_bcs()
+        err_0 = b.get_uniform_residual()
+        i = 0
+        while True:
+            b.set_cfl(1.5)
+            err = b.solve(0.9)
+            if i == 0 and err > 2 * err_0:
+                err_0 = err
+            err /= err_0
+            i += 1
+            if not (err > 0.2 and i < 150):
+                break
+        forces.append(b.wall_forces("wall")); iters.append(i)
+    assert list(ra["iterations"]) == iters
+    assert np.array_equal(np.array(forces), np.stack([ra["cl"], ra["cd"], ra["cm"]], axis=1))
+    assert np.array_equal(a.get_q(), b.get_q())
