@@ -154,3 +154,22 @@ def test_boundary_variables_search_vs_reference_golden(afx, gpu, tag, typ):
     norms = s.run(3, 0.9)
     np.testing.assert_allclose(norms, g[tag + "_norms"], rtol=NORM_RTOL)
     assert np.array_equal(s.get_q(), g[tag + "_q"])
+
+
+@pytest.mark.parametrize("tag", ["transonic_slip", "supersonic_slip", "supersonic_wall"])
+def test_transonic_and_supersonic_histories_vs_reference_golden(afx, gpu, tag):
+    """The same regimes against the reference's own histories (tests/golden/regimes.npz): strict mode to the bit, fast mode
+    within the north-star tolerance."""
+    from tests.test_oracle_golden import REGIMES, regime_start
+    g = H.load("regimes")
+    d = H.load("naca0012q_coarse_euler_gg_o2")
+    m = H.product_mesh(afx, d)
+    s = afx.GpuSolver(m, viscosity=REGIMES[tag][3], math="strict")
+    s.set_q(regime_start(s, tag))
+    norms = s.run(12, 0.9)
+    np.testing.assert_allclose(norms, g[tag + "_norms"], rtol=NORM_RTOL, atol=0)
+    assert H.sha(s.get_q()) == str(g[tag + "_q_sha256"])
+    assert H.sha(s.get("limiters")[:4 * m.N]) == str(g[tag + "_lim_sha256"])
+    f = afx.GpuSolver(m, viscosity=REGIMES[tag][3], math="fast")
+    f.set_q(regime_start(f, tag))
+    np.testing.assert_allclose(f.run(12, 0.9), g[tag + "_norms"], rtol=1e-9, atol=0)  # shocks forming: a decade of slack on 1e-10
