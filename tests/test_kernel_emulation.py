@@ -45,7 +45,7 @@ def test_package_never_picks_the_emulation_library(afx, emu_lib):
 
 def test_three_kernel_stage_sources_match_reference_under_emulation(emu_lib):
     # explicit histories / single phases / synthetic mixed meshes / RHS and Jacobian blocks / BC handling / graph replay
-    tail = run_gpu_tests_under_emulation(emu_lib, ["test_gpu_parity.py"], "not implicit_converged and not full_size")
+    tail = run_gpu_tests_under_emulation(emu_lib, ["test_gpu_parity.py"], "not implicit_converged and not full_size and not sweep_entry")  # the implicit end-to-end cases take ~1 min each: GPU only
     assert " passed" in tail
 
 
@@ -88,14 +88,14 @@ def test_overlapped_peer_memory_halo_under_emulation(emu_lib):
 
 def test_graph_partitioned_run_under_emulation(emu_lib):
     # AFX_PARTITION=graph: recursive graph bisection instead of Hilbert chunks; same bit-identity to the single-device run
-    tail = run_gpu_tests_under_emulation(emu_lib, ["test_gpu_multi.py"], "2-strict-p2p-0 or 4-strict-p2p-1", extra_env=dict(MULTI_ENV, AFX_PARTITION="graph"))
-    assert "2 passed" in tail
+    tail = run_gpu_tests_under_emulation(emu_lib, ["test_gpu_multi.py"], "4-strict-p2p-1", extra_env=dict(MULTI_ENV, AFX_PARTITION="graph"))
+    assert "1 passed" in tail
 
 
 def test_partitioned_variants_under_emulation(emu_lib):
     # 3 ranks, laminar face gradients + least squares; 3 ranks first order; partitioned implicit right-hand side
-    tail = run_gpu_tests_under_emulation(emu_lib, ["test_gpu_multi.py"], "variants and (3-laminar or 3-inviscid)", extra_env=MULTI_ENV)
-    assert "2 passed" in tail
+    tail = run_gpu_tests_under_emulation(emu_lib, ["test_gpu_multi.py"], "variants and 3-laminar", extra_env=MULTI_ENV)
+    assert "1 passed" in tail
 
 
 def test_cpp_adapter_cli_under_emulation(emu_lib):
