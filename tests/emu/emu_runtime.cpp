@@ -295,7 +295,7 @@ cudaError_t cudaDeviceGetStreamPriorityRange(int* lo, int* hi) { *lo = 0; *hi = 
 // "Device" memory is memfd-backed shared mappings, so that cudaIpcGetMemHandle / cudaIpcOpenMemHandle can map an allocation
 // of another rank's process (through /proc/<pid>/fd/<fd>) exactly like CUDA IPC maps a peer's buffer.
 namespace {
-struct Alloc { size_t bytes; int fd; };
+struct Alloc { size_t bytes; int fd; char* map; };  // bytes = length of the whole mapping, guard page included
 std::mutex g_alloc_mu;
 std::map<char*, Alloc> g_allocs;   // cudaMalloc'ed blocks of this process
 std::map<void*, size_t> g_opened;  // peer blocks mapped here (base -> bytes)
@@ -304,15 +304,20 @@ static_assert(sizeof(IpcHandle) <= sizeof(cudaIpcMemHandle_t), "IPC handle fits"
 }  // namespace
 cudaError_t afx_emu_malloc(void** p, size_t bytes)
 {
-    const size_t rounded = (bytes + 4095) & ~(size_t)4095;
+    // The block ENDS (up to the 256-byte allocation granularity) at a page boundary followed by an inaccessible guard page:
+    // a kernel that reads or writes past the end of an array faults at once instead of touching a neighbour's bytes.
+    const size_t used = std::max<size_t>((bytes + 255) & ~(size_t)255, 256);
+    const size_t data = (used + 4095) & ~(size_t)4095, total = data + 4096;
     const int fd = memfd_create("afx_emu_dev", 0);
-    if (fd < 0 || ftruncate(fd, (off_t)(rounded ? rounded : 4096)) != 0) { if (fd >= 0) close(fd); return cudaErrorInvalidValue; }
-    void* m = mmap(nullptr, rounded ? rounded : 4096, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    if (fd < 0 || ftruncate(fd, (off_t)total) != 0) { if (fd >= 0) close(fd); return cudaErrorInvalidValue; }
+    void* m = mmap(nullptr, total, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
     if (m == MAP_FAILED) { close(fd); return cudaErrorInvalidValue; }
-    memset(m, 0xCD, bytes);  // fresh device memory is not zero: poison it
+    char* start = static_cast<char*>(m) + (data - used);
+    memset(m, 0xCD, data);  // fresh device memory is not zero: poison it
+    mprotect(static_cast<char*>(m) + data, 4096, PROT_NONE);
     std::lock_guard<std::mutex> g(g_alloc_mu);
-    g_allocs[static_cast<char*>(m)] = Alloc{rounded ? rounded : 4096, fd};
-    *p = m;
+    g_allocs[start] = Alloc{total, fd, static_cast<char*>(m)};
+    *p = start;
     return cudaSuccess;
 }
 cudaError_t afx_emu_malloc_host(void** p, size_t bytes)
@@ -326,7 +331,7 @@ cudaError_t cudaFree(void* p)
     std::lock_guard<std::mutex> g(g_alloc_mu);
     auto it = g_allocs.find(static_cast<char*>(p));
     if (it == g_allocs.end()) return cudaErrorInvalidValue;
-    munmap(p, it->second.bytes);
+    munmap(it->second.map, it->second.bytes);
     close(it->second.fd);
     g_allocs.erase(it);
     return cudaSuccess;
@@ -400,8 +405,8 @@ cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p)
     auto it = g_allocs.upper_bound(static_cast<char*>(p));
     if (it == g_allocs.begin()) return cudaErrorInvalidValue;
     --it;
-    if (static_cast<char*>(p) >= it->first + it->second.bytes) return cudaErrorInvalidValue;
-    IpcHandle ih{(int)getpid(), it->second.fd, it->second.bytes, (unsigned long long)(static_cast<char*>(p) - it->first)};
+    if (static_cast<char*>(p) >= it->second.map + it->second.bytes - 4096) return cudaErrorInvalidValue;
+    IpcHandle ih{(int)getpid(), it->second.fd, it->second.bytes - 4096, (unsigned long long)(static_cast<char*>(p) - it->second.map)};
     memset(h, 0, sizeof *h);
     memcpy(h, &ih, sizeof ih);
     return cudaSuccess;
