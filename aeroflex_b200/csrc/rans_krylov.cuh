@@ -144,6 +144,75 @@ __global__ void __launch_bounds__(256) k_multi_dot_final(int nblocks, const doub
     const double t = block_sum(acc);
     if (threadIdx.x == 0) out[blockIdx.x] = t;
 }
+
+// The same final sums without a second launch: the block that finishes last (device-wide counter) adds the partials of
+// every j exactly as k_multi_dot_final does -- same strided order per thread, same block_sum tree -- so the results carry
+// the same bits.  The Krylov iteration of the shipped meshes is bound by launches, not by bytes.
+__device__ __forceinline__ void dot_finish_by_last_block(int k, const double* partial, double* out, unsigned int* counter)
+{
+    __shared__ bool last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!last) return;
+    for (int j = 0; j < k; ++j) {
+        double acc = 0;
+        for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) acc += __ldcg(&partial[(size_t)j * gridDim.x + b]);
+        const double t = block_sum(acc);
+        if (threadIdx.x == 0) out[j] = t;
+    }
+    if (threadIdx.x == 0) *counter = 0;
+}
+
+// multi_dot in one launch
+__global__ void __launch_bounds__(256) k_multi_dot(uint32_t n, const d4* __restrict__ V, size_t stride, int k, const d4* __restrict__ w,
+                                                   double* partial, double* out, unsigned int* counter)
+{
+    for (int j = 0; j < k; ++j) {
+        const d4* __restrict__ vj = V + (size_t)j * stride;
+        double acc = 0;
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+            const d4 a = vj[i], b = w[i];
+            acc += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+        }
+        const double t = block_sum(acc);
+        if (threadIdx.x == 0) partial[(size_t)j * gridDim.x + blockIdx.x] = t;
+    }
+    dot_finish_by_last_block(k, partial, out, counter);
+}
+
+// w -= sum_j c[j] V_j followed by ||w||^2 -> out[0], one launch (classical Gram-Schmidt step + the norm of the result):
+// the update is k_multi_axpy's arithmetic per cell, the norm k_multi_dot's (same grid-stride partition, same trees)
+__global__ void __launch_bounds__(256) k_axpy_norm(uint32_t n, const d4* __restrict__ V, size_t stride, int k, const double* __restrict__ c,
+                                                   double sign, d4* w, double* partial, double* out, unsigned int* counter)
+{
+    double acc = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        d4 a = w[i];
+        for (int j = 0; j < k; ++j) {
+            const double cj = sign * c[j];
+            const d4 v = V[(size_t)j * stride + i];
+            a.x += cj * v.x; a.y += cj * v.y; a.z += cj * v.z; a.w += cj * v.w;
+        }
+        w[i] = a;
+        acc += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+    }
+    const double t = block_sum(acc);
+    if (threadIdx.x == 0) partial[blockIdx.x] = t;
+    dot_finish_by_last_block(1, partial, out, counter);
+}
+
+// r = A x and z = Dinv r (the first block-Jacobi sweep from a zero start) in one launch: k_spmv + k_jacobi_sweep(first)
+__global__ void __launch_bounds__(256) k_spmv_sweep0(DevMesh m, const d4* __restrict__ J, const d4* __restrict__ D, const d4* __restrict__ Dinv,
+                                                     const d4* __restrict__ x, d4* __restrict__ r, d4* __restrict__ z)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m.NT) return;
+    const d4 ri = row_Ax(m, J, D, x, i);
+    r[i] = ri;
+    z[i] = (i >= m.N) ? ri : blk_mul(Dinv + (size_t)i * 4, ri);
+}
 // w += sign * sum_j c[j] V_j
 __global__ void __launch_bounds__(256) k_multi_axpy(uint32_t n, const d4* __restrict__ V, size_t stride, int k, const double* __restrict__ c,
                                                     double sign, d4* __restrict__ w)
@@ -207,6 +276,20 @@ static void multi_dot(uint32_t n, const d4* V, size_t stride, int k, const d4* w
 {
     k_multi_dot_partial<<<KRY_BLOCKS, 256, 0, st>>>(n, V, stride, k, w, partial);
     k_multi_dot_final<<<k, 256, 0, st>>>(KRY_BLOCKS, partial, out);
+}
+// one-launch forms (counter: a zeroed device word, reset by the kernel)
+static void multi_dot1(uint32_t n, const d4* V, size_t stride, int k, const d4* w, double* partial, double* out, unsigned int* counter, cudaStream_t st)
+{
+    k_multi_dot<<<KRY_BLOCKS, 256, 0, st>>>(n, V, stride, k, w, partial, out, counter);
+}
+static void axpy_norm(uint32_t n, const d4* V, size_t stride, int k, const double* c, double sign, d4* w, double* partial, double* out,
+                      unsigned int* counter, cudaStream_t st)
+{
+    k_axpy_norm<<<KRY_BLOCKS, 256, 0, st>>>(n, V, stride, k, c, sign, w, partial, out, counter);
+}
+static void spmv_sweep0(const DevMesh& m, const d4* J, const double* D, const double* Dinv, const d4* x, d4* r, d4* z, cudaStream_t st)
+{
+    k_spmv_sweep0<<<(m.NT + 255) / 256, 256, 0, st>>>(m, J, reinterpret_cast<const d4*>(D), reinterpret_cast<const d4*>(Dinv), x, r, z);
 }
 static void multi_axpy(uint32_t n, const d4* V, size_t stride, int k, const double* c, double sign, d4* w, cudaStream_t st)
 {

@@ -177,13 +177,14 @@ struct Solver {
     DBuf<double> dt, dt_ref;
     DBuf<d4> J; DBuf<double> D;   // Jacobian face blocks [E][16] d4 and diagonal blocks [NT][16]
     // implicit step: block-Jacobi preconditioned restarted GMRES on the device
-    DBuf<double> Dinv, kry_partial, kry_h; DBuf<d4> kry_V, kry_w, kry_z, kry_t, kry_x; DBuf<int> kry_flag;
+    DBuf<double> Dinv, kry_partial, kry_h; DBuf<d4> kry_V, kry_w, kry_z, kry_t, kry_x; DBuf<int> kry_flag; DBuf<unsigned int> kry_counter;
     int gmres_restart = 30, gmres_max_iter = 500, precond_sweeps = 4;
     double gmres_tol = 1e-2;
     int last_linear_iters = 0;
     bool precond_valid = false;
     int compute_preconditioner();
     void apply_preconditioner(const d4* r, d4* z);
+    void precondition_Ax(const d4* x, d4* r_buf, d4* z);  // r_buf = A x, z = M^-1 r_buf; the product and the first sweep share a launch
     bool gmres(const d4* b, d4* x);
     double step_implicit(double relax, double tol, int rhs_iterations);
     DBuf<double> partial, norms, prm, scratch;
@@ -1117,6 +1118,7 @@ int Solver::compute_preconditioner()
         Dinv.alloc((size_t)NT * 16); kry_flag.alloc(1);
         kry_V.alloc((size_t)(gmres_restart + 1) * NT); kry_w.alloc(NT); kry_z.alloc(NT); kry_t.alloc(NT); kry_x.alloc(NT);
         kry_partial.alloc((size_t)(gmres_restart + 2) * 1024); kry_h.alloc(gmres_restart + 4);
+        kry_counter.alloc(1); kry_counter.zero(st);
     }
     kry_flag.zero(st);
     kt->invert_blocks(NT, D.p, Dinv.p, kry_flag.p, st);
@@ -1144,6 +1146,20 @@ void Solver::apply_preconditioner(const d4* r, d4* z)
     }
 }
 
+void Solver::precondition_Ax(const d4* x, d4* r_buf, d4* z)
+{
+    d4* a = z; d4* b = kry_t.p;
+    const int sweeps = std::max(1, precond_sweeps);
+    if ((sweeps - 1) % 2) std::swap(a, b);
+    kt->spmv_sweep0(dm, J.p, D.p, Dinv.p, x, r_buf, a, st);
+    ++launches;
+    for (int k = 1; k < sweeps; ++k) {
+        kt->jacobi_sweep(dm, J.p, D.p, Dinv.p, r_buf, a, b, 0, st);
+        ++launches;
+        std::swap(a, b);
+    }
+}
+
 // Left-preconditioned restarted GMRES, zero initial guess, stop on ||M^-1 (b - A x)|| <= tol ||M^-1 b||
 // (the criterion of Eigen::GMRES used at solver.h:886,906-910).  Arnoldi by classical Gram-Schmidt with all
 // inner products of a step in one reduction; the Givens recurrence runs on the host (one small D2H per step).
@@ -1157,7 +1173,7 @@ bool Solver::gmres(const d4* b, d4* x)
     // r = M^-1 b
     d4* V0 = kry_V.p;
     apply_preconditioner(b, kry_w.p);
-    kt->multi_dot(NT, kry_w.p, stride, 1, kry_w.p, kry_partial.p, kry_h.p, st); launches += 2;
+    kt->multi_dot1(NT, kry_w.p, stride, 1, kry_w.p, kry_partial.p, kry_h.p, kry_counter.p, st); ++launches;
     CK(cudaMemcpyAsync(hbuf.data(), kry_h.p, sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     const double r0 = std::sqrt(hbuf[0]);
@@ -1173,13 +1189,12 @@ bool Solver::gmres(const d4* b, d4* x)
         bool done = false;
         for (; k < m && last_linear_iters < gmres_max_iter; ++k) {
             ++last_linear_iters;
-            // w = M^-1 A v_k
-            kt->spmv(dm, J.p, D.p, kry_V.p + (size_t)k * stride, kry_z.p, st); ++launches;
-            apply_preconditioner(kry_z.p, kry_w.p);
+            // w = M^-1 A v_k   (7 launches per Arnoldi step: product + first sweep, 3 sweeps, dots, update + norm, scaling;
+            // the unfused sequence was 11 -- on the shipped meshes the step is bound by launches)
+            precondition_Ax(kry_V.p + (size_t)k * stride, kry_z.p, kry_w.p);
             // h = V^T w ; w -= V h ; ||w||^2
-            kt->multi_dot(NT, kry_V.p, stride, k + 1, kry_w.p, kry_partial.p, kry_h.p, st); launches += 2;
-            kt->multi_axpy(NT, kry_V.p, stride, k + 1, kry_h.p, -1.0, kry_w.p, st); ++launches;
-            kt->multi_dot(NT, kry_w.p, stride, 1, kry_w.p, kry_partial.p, kry_h.p + (k + 1), st); launches += 2;
+            kt->multi_dot1(NT, kry_V.p, stride, k + 1, kry_w.p, kry_partial.p, kry_h.p, kry_counter.p, st); ++launches;
+            kt->axpy_norm(NT, kry_V.p, stride, k + 1, kry_h.p, -1.0, kry_w.p, kry_partial.p, kry_h.p + (k + 1), kry_counter.p, st); ++launches;
             CK(cudaMemcpyAsync(hbuf.data(), kry_h.p, (size_t)(k + 2) * sizeof(double), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             const double hn = std::sqrt(hbuf[k + 1]);
@@ -1214,7 +1229,7 @@ bool Solver::gmres(const d4* b, d4* x)
         kt->spmv(dm, J.p, D.p, x, kry_z.p, st); ++launches;
         kt->sub(NT, b, kry_z.p, kry_z.p, st); ++launches;
         apply_preconditioner(kry_z.p, kry_w.p);
-        kt->multi_dot(NT, kry_w.p, stride, 1, kry_w.p, kry_partial.p, kry_h.p, st); launches += 2;
+        kt->multi_dot1(NT, kry_w.p, stride, 1, kry_w.p, kry_partial.p, kry_h.p, kry_counter.p, st); ++launches;
         CK(cudaMemcpyAsync(hbuf.data(), kry_h.p, sizeof(double), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         beta = std::sqrt(hbuf[0]);
