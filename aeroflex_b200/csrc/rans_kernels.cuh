@@ -573,6 +573,21 @@ __global__ void __launch_bounds__(AFX_GATHER_THREADS) k_gather_update(DevMesh m,
             nrm += r.x * r.x + r.y * r.y + r.z * r.z + r.w * r.w;
         }
     }
+    if (MODE == 0 && push.early_signal && blockIdx.x < push.n_front_blocks) {  // uniform per CTA
+        // every store of this CTA into the peers' buffers has been issued and fenced (system scope) by its thread
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            if (atomicAdd(push.front_done, 1u) == push.n_front_blocks - 1) {  // the whole send layer is on its way
+                *push.front_done = 0;
+                __threadfence_system();
+                const unsigned long long e = *push.epoch_rw + 1ull;
+                for (int p = 0; p < push.n_peers; ++p) *reinterpret_cast<volatile unsigned long long*>(push.peer_flag[p]) = e;
+                __threadfence_system();
+                *push.epoch_rw = e;  // read next by k_halo_wait_scatter (a later kernel of this stream)
+            }
+        }
+    }
     if (LAST) block_norm_accumulate(nrm, no);
 }
 

@@ -103,6 +103,8 @@ struct Halo {
     std::vector<void*> opened;            // peer blocks mapped into this process
     DBuf<uint32_t> dst_ptr, dst;          // CSR: send-layer cell -> (peer slot, position in its receive list)
     DBuf<unsigned long long> epoch;
+    DBuf<unsigned int> front_done;
+    bool early_signal = false;            // AFX_HALO_EARLY_SIGNAL=1
     PushArgs push{};
     SignalArgs sig{};
     WaitArgs wait{};
@@ -670,6 +672,17 @@ void Solver::launch_gather(const d4* qk_in, d4* qk_out, d4* vec_out, double alph
     if (halo && MODE == 0 && halo->p2p && !halo_overlap) {
         // one launch advances everything and pushes the send layer into the peers' buffers; a flag hand-off and a
         // small wait+scatter kernel complete the halo on the same stream (no fork/join, no split launches)
+        if (halo->early_signal) {
+            // the last CTA of the send layer raises the peers' flags from inside the update kernel: the hand-off travels
+            // while the interior cells are still being advanced, and the signalling launch disappears
+            PushArgs pa = halo->push;
+            pa.early_signal = 1;
+            pa.n_front_blocks = kt->gather_blocks(n_front);
+            kt->gather(MODE, LAST, dm, 0, n_upd, flux.p, q.p, qk_in, qk_out, dt.p, vec_out, alpha, prm.p, walls ? 1 : 0, norm_out(), &pa, st);
+            kt->halo_wait_scatter(halo->wait, qk_out, st);
+            launches += 2;
+            return;
+        }
         kt->gather(MODE, LAST, dm, 0, n_upd, flux.p, q.p, qk_in, qk_out, dt.p, vec_out, alpha, prm.p, walls ? 1 : 0, norm_out(), &halo->push, st);
         kt->halo_signal(halo->sig, st);
         kt->halo_wait_scatter(halo->wait, qk_out, st);
@@ -954,6 +967,12 @@ void Solver::p2p_connect(const void* blobs, size_t blob_size, int nranks)
     h.wait.n_peers = (int)h.peers.size(); h.wait.epoch = h.epoch.p;
     h.wait.recv_buf = reinterpret_cast<const d4*>(static_cast<char*>(h.ipc_block) + P2P_FLAG_BYTES);
     h.wait.recv_idx = h.recv_idx.p; h.wait.n_recv = h.n_recv;
+    h.front_done.alloc(1);
+    CK(cudaMemset(h.front_done.p, 0, sizeof(unsigned int)));
+    h.push.early_signal = 0; h.push.n_front_blocks = 0; h.push.front_done = h.front_done.p; h.push.epoch_rw = h.epoch.p;
+    h.push.n_peers = (int)h.peers.size();
+    for (size_t k = 0; k < h.peers.size(); ++k) h.push.peer_flag[k] = h.sig.peer_flag[k];
+    if (const char* e = getenv("AFX_HALO_EARLY_SIGNAL")) h.early_signal = (e[0] == '1');
     h.p2p = (n_front > 0 && n_front < n_upd);
     invalidate_graph();
 }

@@ -106,6 +106,14 @@ struct PushArgs {
     d4* peer_buf[P2P_MAX_PEERS];                  // peer's receive buffer at my offset (parity 0), a peer-mapped pointer
     unsigned long long peer_stride[P2P_MAX_PEERS];// elements between the two parity buffers of that peer
     const unsigned long long* epoch;              // completed exchanges of this rank (device counter)
+    // early hand-off (AFX_HALO_EARLY_SIGNAL=1): the send layer lives in the first n_front_blocks CTAs of the update kernel; the
+    // one that finishes last raises the peers' flags itself, while the rest of the kernel still advances interior cells
+    int early_signal;
+    unsigned int n_front_blocks;
+    unsigned int* front_done;                     // device counter, zero between launches
+    unsigned long long* epoch_rw;                 // the same counter as `epoch`, advanced by the signalling CTA
+    int n_peers;
+    unsigned long long* peer_flag[P2P_MAX_PEERS]; // peer's flag slot for my rank (peer-mapped)
 };
 struct SignalArgs {
     int n_peers;

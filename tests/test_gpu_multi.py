@@ -133,3 +133,11 @@ def test_partitioned_variants_match_single_gpu(afx, gpu, tmp_path, world, visc, 
         np.testing.assert_allclose(d["forces"], F, rtol=1e-12, atol=1e-15)
         assert np.array_equal(d["rhs"].reshape(-1, 4)[own], RHS[own])
         assert float(d["rhs_norm"]) == pytest.approx(rhs_norm, rel=1e-12)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_early_halo_signal_matches_single_gpu(afx, gpu, tmp_path, monkeypatch, world):
+    """AFX_HALO_EARLY_SIGNAL=1: the last send-layer CTA of the update kernel raises the peers' flags itself (no signalling
+    launch, the hand-off overlaps the interior update).  Same data, same bits."""
+    monkeypatch.setenv("AFX_HALO_EARLY_SIGNAL", "1")
+    test_partitioned_run_matches_single_gpu(afx, gpu, tmp_path, world, "strict", "p2p", 0)

@@ -102,3 +102,9 @@ def test_cpp_adapter_cli_under_emulation(emu_lib):
     # the C++ host adapter end to end (rans::Rans::solve_airfoil -> multigrid<gpuSolver> FMG, explicit) linked against the emulation
     tail = run_gpu_tests_under_emulation(emu_lib, ["test_cpp_host.py"], "explicit_mode")
     assert "1 passed" in tail
+
+
+def test_early_halo_signal_under_emulation(emu_lib):
+    # AFX_HALO_EARLY_SIGNAL=1 (opt-in): flags raised by the last send-layer CTA of the update kernel, 4 ranks as processes
+    tail = run_gpu_tests_under_emulation(emu_lib, ["test_gpu_multi.py"], "early_halo and 4", extra_env=MULTI_ENV)
+    assert "1 passed" in tail
