@@ -72,7 +72,16 @@ struct Fiber {
 };
 struct MBar { uint32_t phase = 0; std::vector<Copy> pending; };
 
+// Shadow of the dynamic shared memory, one entry per 4 bytes (the race check of emu_stage_ptx.h accesses):
+//   * between two block barriers ("epoch") a word written by one thread may not be read or written by another;
+//   * a word that an asynchronous copy (cp.async / cp.async.bulk) is still in flight to may not be touched at all.
+// Words filled by a landed copy belong to nobody: whoever waited for the copy may read them.
+struct Shadow { uint32_t epoch; int16_t writer, reader; uint16_t inflight; };
+constexpr int16_t NOBODY = -1, MANY = -2;
+
 struct Worker {  // one per host thread
+    std::vector<Shadow> shadow;
+    uint32_t epoch = 1;
     char* stacks = nullptr;
     unsigned char* smem = nullptr;
     Fiber fib[MAX_THREADS];
@@ -87,6 +96,7 @@ struct Worker {  // one per host thread
         stacks = static_cast<char*>(mmap(nullptr, STACK_BYTES * MAX_THREADS, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0));
         if (stacks == MAP_FAILED) { perror("afx_emu: mmap"); abort(); }
         smem = static_cast<unsigned char*>(aligned_alloc(1024, DYN_SMEM_BYTES));
+        shadow.assign(DYN_SMEM_BYTES / 4, Shadow{0, NOBODY, NOBODY, 0});
     }
 };
 thread_local Worker* g_w = nullptr;
@@ -101,8 +111,9 @@ void fiber_main()
     Worker& w = *g_w;
     (*w.body)();
     Fiber& f = w.fib[w.cur];
-    if (!f.open.empty() || !f.groups.empty()) {  // copies never waited for are lost with the thread: land them (the data is simply unused)
-        f.open.clear(); f.groups.clear();
+    if (!f.open.empty() || !f.groups.empty()) {  // copies never waited for: a kernel must drain its cp.async groups before it exits
+        fprintf(stderr, "afx_emu: thread %u of block %u exits with cp.async copies it never waited for\n", threadIdx.x, blockIdx.x);
+        abort();
     }
     f.state = DONE;
     void* dummy;
@@ -122,6 +133,8 @@ void run_block(Worker& w, unsigned n)
 {
     w.nthreads = n;
     w.bars.clear();
+    ++w.epoch;
+    for (auto& e : w.shadow) e.inflight = 0;
     for (unsigned t = 0; t < n; ++t) {
         Fiber& f = w.fib[t];
         char* top = w.stacks + STACK_BYTES * (size_t)(t + 1);
@@ -151,6 +164,7 @@ void run_block(Worker& w, unsigned n)
         if (alive && at_block == alive) {
             for (unsigned t = 0; t < n; ++t) if (w.fib[t].state == WAIT_BLOCK) w.fib[t].state = RUNNABLE;
             progressed = true;
+            ++w.epoch;  // accesses before and after a __syncthreads() are ordered
         }
         for (unsigned w0 = 0; w0 < n; w0 += 32) {
             unsigned live = 0, waiting = 0;
@@ -203,11 +217,67 @@ void run_grid(dim3 grid, dim3 block, size_t smem, const std::function<void()>& b
     }
 }
 
+// ---- shared-memory race check ---------------------------------------------------------------------------------------
+static const bool g_racecheck = [] { const char* e = getenv("AFX_EMU_RACECHECK"); return !(e && e[0] == '0'); }();
+[[noreturn]] static void race(const char* what, uint32_t off, int other)
+{
+    fprintf(stderr, "afx_emu: shared-memory hazard: %s at byte offset %u of the dynamic shared memory (block %u, thread %u, other thread %d)\n",
+            what, off, blockIdx.x, threadIdx.x, other);
+    abort();
+}
+void smem_access(uint32_t off, uint32_t bytes, bool write)
+{
+    if (!g_racecheck) return;
+    Worker& w = *g_w;
+    const int16_t me = (int16_t)w.cur;
+    for (uint32_t k = off / 4; k <= (off + bytes - 1) / 4; ++k) {
+        Shadow& e = w.shadow[k];
+        if (e.inflight) race(write ? "write to a word an asynchronous copy is in flight to" : "read of a word an asynchronous copy is in flight to", k * 4, -1);
+        if (e.epoch != w.epoch) { e.epoch = w.epoch; e.writer = NOBODY; e.reader = NOBODY; }
+        if (write) {
+            if (e.writer != NOBODY && e.writer != me) race("two threads write the same word without a barrier between them", k * 4, e.writer);
+            if (e.reader != NOBODY && e.reader != me) race("a thread writes a word another thread has read since the last barrier", k * 4, e.reader);
+            e.writer = me;
+        } else {
+            if (e.writer != NOBODY && e.writer != me) race("a thread reads a word another thread has written since the last barrier", k * 4, e.writer);
+            e.reader = (e.reader == NOBODY || e.reader == me) ? me : MANY;
+        }
+    }
+}
+static void smem_copy_mark(void* dst, uint32_t bytes, int delta)
+{
+    if (!g_racecheck || !g_w || !g_w->smem) return;
+    Worker& w = *g_w;
+    const ptrdiff_t off = static_cast<unsigned char*>(dst) - w.smem;
+    if (off < 0 || (size_t)off + bytes > DYN_SMEM_BYTES) return;
+    for (size_t k = (size_t)off / 4; k <= ((size_t)off + bytes - 1) / 4; ++k) {
+        Shadow& e = w.shadow[k];
+        if (delta > 0) {
+            // the copy may start at once: nobody may have touched the destination since the last barrier ... unless it is the
+            // issuing thread itself (program order) -- a read by ANOTHER thread in this epoch is the classic buffer-reuse bug
+            if (e.epoch == w.epoch && ((e.reader != NOBODY && e.reader != (int16_t)w.cur) || (e.writer != NOBODY && e.writer != (int16_t)w.cur)))
+                race("an asynchronous copy is issued into a word another thread has used since the last barrier", (uint32_t)k * 4,
+                     e.reader != NOBODY ? e.reader : e.writer);
+            ++e.inflight;
+        } else {
+            if (e.inflight) --e.inflight;
+            e.epoch = 0;  // landed data belongs to nobody
+        }
+    }
+}
+
 // ---- deferred asynchronous copies ----------------------------------------------------------------------------------
-static void land(const std::vector<Copy>& cs) { for (const Copy& c : cs) memcpy(c.dst, c.src, c.bytes); }
+static void land(const std::vector<Copy>& cs)
+{
+    for (const Copy& c : cs) { memcpy(c.dst, c.src, c.bytes); smem_copy_mark(c.dst, c.bytes, -1); }
+}
 void mbar_init(uint32_t bar) { g_w->bars[bar] = MBar{}; }
 void mbar_expect(uint32_t, uint32_t) {}
-void mbar_queue(uint32_t bar, void* dst, const void* src, uint32_t bytes) { g_w->bars[bar].pending.push_back(Copy{dst, src, bytes}); }
+void mbar_queue(uint32_t bar, void* dst, const void* src, uint32_t bytes)
+{
+    smem_copy_mark(dst, bytes, +1);
+    g_w->bars[bar].pending.push_back(Copy{dst, src, bytes});
+}
 void mbar_wait(uint32_t bar, uint32_t parity)
 {
     MBar& b = g_w->bars[bar];
@@ -216,7 +286,11 @@ void mbar_wait(uint32_t bar, uint32_t parity)
     b.pending.clear();
     b.phase ^= 1u;
 }
-void cpasync_queue(void* dst, const void* src, uint32_t bytes) { g_w->fib[g_w->cur].open.push_back(Copy{dst, src, bytes}); }
+void cpasync_queue(void* dst, const void* src, uint32_t bytes)
+{
+    smem_copy_mark(dst, bytes, +1);
+    g_w->fib[g_w->cur].open.push_back(Copy{dst, src, bytes});
+}
 void cpasync_commit()
 {
     Fiber& f = g_w->fib[g_w->cur];

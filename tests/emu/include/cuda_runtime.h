@@ -58,6 +58,7 @@ void mbar_wait(uint32_t bar, uint32_t parity);
 void cpasync_queue(void* dst, const void* src, uint32_t bytes);
 void cpasync_commit();
 void cpasync_wait(int leave_pending);
+void smem_access(uint32_t offset, uint32_t bytes, bool write);  // race check of a shared-memory access (emu_runtime.cpp)
 double rcp_seed(double a);    // MUFU.RCP64H: the upper word of 1/a, lower word zero
 double rsqrt_seed(double a);  // MUFU.RSQ64H
 const char* self_path();      // file name of the emulation library (nccl_dl.h binds the emulated NCCL entry points in it)

@@ -14,6 +14,8 @@ __device__ __forceinline__ unsigned char* emu_sp(uint32_t a, uint32_t bytes, uin
     emu_need(((a - 1024u) & (align - 1u)) == 0, "misaligned shared-memory access");
     return ::afx_emu::g_dyn_smem + (a - 1024u);
 }
+__device__ __forceinline__ unsigned char* emu_ld(uint32_t a, uint32_t bytes, uint32_t align) { unsigned char* p = emu_sp(a, bytes, align); ::afx_emu::smem_access(a - 1024u, bytes, false); return p; }
+__device__ __forceinline__ unsigned char* emu_st(uint32_t a, uint32_t bytes, uint32_t align) { unsigned char* p = emu_sp(a, bytes, align); ::afx_emu::smem_access(a - 1024u, bytes, true); return p; }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t) { emu_sp(bar, 8, 8); ::afx_emu::mbar_init(bar); }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) { ::afx_emu::mbar_expect(bar, bytes); }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) { ::afx_emu::mbar_wait(bar, parity); }
@@ -36,13 +38,13 @@ __device__ __forceinline__ void cp_async_commit() { ::afx_emu::cpasync_commit();
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { ::afx_emu::cpasync_wait(N); }
 
-__device__ __forceinline__ d4 lds_d4(uint32_t a) { d4 v; memcpy(&v, emu_sp(a, 32, 16), 32); return v; }
-__device__ __forceinline__ void sts_d4(uint32_t a, const d4& v) { memcpy(emu_sp(a, 32, 16), &v, 32); }
-__device__ __forceinline__ double2 lds_d2(uint32_t a) { double2 v; memcpy(&v, emu_sp(a, 16, 16), 16); return v; }
-__device__ __forceinline__ double lds_d(uint32_t a) { double v; memcpy(&v, emu_sp(a, 8, 8), 8); return v; }
-__device__ __forceinline__ void sts_d(uint32_t a, double v) { memcpy(emu_sp(a, 8, 8), &v, 8); }
-__device__ __forceinline__ uint4 lds_u4(uint32_t a) { uint4 v; memcpy(&v, emu_sp(a, 16, 16), 16); return v; }
-__device__ __forceinline__ void sts_u4(uint32_t a, const uint4& v) { memcpy(emu_sp(a, 16, 16), &v, 16); }
-__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; memcpy(&v, emu_sp(a, 4, 4), 4); return v; }
-__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { memcpy(emu_sp(a, 4, 4), &v, 4); }
+__device__ __forceinline__ d4 lds_d4(uint32_t a) { d4 v; memcpy(&v, emu_ld(a, 32, 16), 32); return v; }
+__device__ __forceinline__ void sts_d4(uint32_t a, const d4& v) { memcpy(emu_st(a, 32, 16), &v, 32); }
+__device__ __forceinline__ double2 lds_d2(uint32_t a) { double2 v; memcpy(&v, emu_ld(a, 16, 16), 16); return v; }
+__device__ __forceinline__ double lds_d(uint32_t a) { double v; memcpy(&v, emu_ld(a, 8, 8), 8); return v; }
+__device__ __forceinline__ void sts_d(uint32_t a, double v) { memcpy(emu_st(a, 8, 8), &v, 8); }
+__device__ __forceinline__ uint4 lds_u4(uint32_t a) { uint4 v; memcpy(&v, emu_ld(a, 16, 16), 16); return v; }
+__device__ __forceinline__ void sts_u4(uint32_t a, const uint4& v) { memcpy(emu_st(a, 16, 16), &v, 16); }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; memcpy(&v, emu_ld(a, 4, 4), 4); return v; }
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { memcpy(emu_st(a, 4, 4), &v, 4); }
 
