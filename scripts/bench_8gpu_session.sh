@@ -21,6 +21,10 @@ tr() { # name nproc args...
 }
 for n in 2 4 8; do tr m8_strong16M_$n $n --steps 50 --warmup 5 --e2e-steps 3 --workload synthetic-16M-mixed-omesh; done
 tr m8_weak1M_8 8 --steps 100 --warmup 10
+# session-3 experiments that no multi-GPU box has timed yet: flags raised from inside the update kernel; graph partition
+AFX_HALO_EARLY_SIGNAL=1 tr m8_weak1M_8_early_signal 8 --steps 100 --warmup 10
+AFX_HALO_EARLY_SIGNAL=1 tr m8_strong16M_8_early_signal 8 --steps 50 --warmup 5 --e2e-steps 3 --workload synthetic-16M-mixed-omesh
+AFX_PARTITION=graph tr m8_weak1M_8_graph_partition 8 --steps 100 --warmup 10
 timeout 300 python scripts/polar_sweep_bench.py 8 > gpurun_out/m8_polar_8gpu.json 2> gpurun_out/m8_polar.err
 python - <<PY
 import json

@@ -16,6 +16,8 @@ VARIANTS = {
     "preload_pf": ["-DAFX_DTG_PRELOAD=1", "-DAFX_DTG_DXY=1"],
     "preload_minb3": ["-DAFX_DTG_PRELOAD=1", "-DAFX_DTG_MINB=3"],
     "preload_minb3_pf": ["-DAFX_DTG_PRELOAD=1", "-DAFX_DTG_MINB=3", "-DAFX_DTG_DXY=1"],
+    "fl64": ["-DAFX_FLUX_THREADS=64", "-DAFX_LIM_THREADS=64"],      # untried in session 3
+    "g512": ["-DAFX_GATHER_THREADS=512"],                              # untried in session 3
     "st128": ["-DAFX_FLUX_THREADS=128", "-DAFX_LIM_THREADS=128", "-DAFX_GATHER_THREADS=128"],
     "fl128": ["-DAFX_FLUX_THREADS=128", "-DAFX_LIM_THREADS=128"],
     "nopreload_t128": ["-DAFX_DTG_PRELOAD=0", "-DAFX_DTG_THREADS=128", "-DAFX_DTG_MINB=6"],

@@ -8,6 +8,11 @@ timeout 150 python bench.py --impl reference --steps 20 --warmup 2 > gpurun_out/
 timeout 120 python bench.py --steps 200 --warmup 10 --math strict --no-cpu-baseline > gpurun_out/f_bench_1gpu_strict.json 2> gpurun_out/f_bench_1gpu_strict.err
 timeout 240 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --e2e-steps 3 --workload synthetic-16M-mixed-omesh > gpurun_out/f_bench_16M.json 2> gpurun_out/f_bench_16M.err
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/f_launches.csv python bench.py --steps 4 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/f_ncu_list.log 2>&1
+# CTA sizes session 3 could not try (scripts/build_variants.py builds them next to the default library on the CPU side first)
+for v in fl64 g512; do
+  [ -f aeroflex_b200/lib/libaeroflex_rans_b200_$v.so ] && AFX_LIB=$PWD/aeroflex_b200/lib/libaeroflex_rans_b200_$v.so QUICK_AB_FUSE=1 timeout 30 python scripts/quick_ab.py >> gpurun_out/f_ab_cta.jsonl 2>> gpurun_out/f_ab_cta.err
+done
+QUICK_AB_FUSE=1,0 timeout 30 python scripts/quick_ab.py >> gpurun_out/f_ab_cta.jsonl 2>> gpurun_out/f_ab_cta.err
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:"k_flux|k_limiter|k_gather_update|k_dt_grad" -s 20 -c 8 -o gpurun_out/f_prof -f python bench.py --steps 4 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/f_ncu_full.log 2>&1
 python - <<PY
 import json
