@@ -671,7 +671,7 @@ __global__ void __launch_bounds__(256) k_jac_diag(DevMesh m, const double* __res
     double d[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) d[k] = 0;
-    if (i >= m.N) {
+    if (i >= m.n_upd) {  // ghost rows, and the halo rows of a partition (they belong to another rank)
         d[0] = d[5] = d[10] = d[15] = 1;
     } else {
         const double t = m.area[i] / dt[i];

@@ -30,7 +30,9 @@ __device__ __forceinline__ d4 blk_mul(const d4* __restrict__ B, const d4& x)
 __device__ __forceinline__ d4 row_Ax(const DevMesh& m, const d4* __restrict__ J, const d4* __restrict__ D, const d4* __restrict__ x, uint32_t i)
 {
     const d4 xi = x[i];
-    if (i >= m.N) return xi;  // ghost rows are the identity (solver.h:1062-1070)
+    // ghost rows are the identity (solver.h:1062-1070); so are the halo rows of a partition, which belong to another rank and
+    // are refreshed from it before they are read
+    if (i >= m.n_upd) return xi;
     d4 y = blk_mul(D + (size_t)i * 4, xi);
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
@@ -58,7 +60,7 @@ __global__ void __launch_bounds__(256) k_jacobi_sweep(DevMesh m, const d4* __res
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m.NT) return;
     const d4 ri = r[i];
-    if (i >= m.N) { z_out[i] = ri; return; }
+    if (i >= m.n_upd) { z_out[i] = ri; return; }
     if (first) { z_out[i] = blk_mul(Dinv + (size_t)i * 4, ri); return; }
     const d4 az = row_Ax(m, J, D, z_in, i);
     const d4 d = blk_mul(Dinv + (size_t)i * 4, mk4(ri.x - az.x, ri.y - az.y, ri.z - az.z, ri.w - az.w));
@@ -211,7 +213,7 @@ __global__ void __launch_bounds__(256) k_spmv_sweep0(DevMesh m, const d4* __rest
     if (i >= m.NT) return;
     const d4 ri = row_Ax(m, J, D, x, i);
     r[i] = ri;
-    z[i] = (i >= m.N) ? ri : blk_mul(Dinv + (size_t)i * 4, ri);
+    z[i] = (i >= m.n_upd) ? ri : blk_mul(Dinv + (size_t)i * 4, ri);
 }
 // w += sign * sum_j c[j] V_j
 __global__ void __launch_bounds__(256) k_multi_axpy(uint32_t n, const d4* __restrict__ V, size_t stride, int k, const double* __restrict__ c,

@@ -186,7 +186,12 @@ struct Solver {
     bool precond_valid = false;
     int compute_preconditioner();
     void apply_preconditioner(const d4* r, d4* z);
-    void precondition_Ax(const d4* x, d4* r_buf, d4* z);  // r_buf = A x, z = M^-1 r_buf; the product and the first sweep share a launch
+    void precondition_Ax(const d4* x, d4* r_buf, d4* z);
+    // partitioned implicit step: inner products run over the owned rows and are summed over the ranks; a vector whose
+    // neighbour rows are about to be read (matrix-vector product, Jacobi sweep) gets its halo rows from their owners first
+    uint32_t n_dot() const { return halo ? n_upd : NT; }
+    void halo_refresh(d4* field) { if (halo) exchange(field, st); }
+    void allreduce_sum(double* dev, int n) { if (halo && n > 0) NK(NcclApi::get().AllReduce(dev, dev, (size_t)n, ncclDouble, ncclSum, halo->comm, st)); }  // r_buf = A x, z = M^-1 r_buf; the product and the first sweep share a launch
     bool gmres(const d4* b, d4* x);
     double step_implicit(double relax, double tol, int rhs_iterations);
     DBuf<double> partial, norms, prm, scratch;
@@ -1159,6 +1164,7 @@ void Solver::apply_preconditioner(const d4* r, d4* z)
     kt->jacobi_sweep(dm, J.p, D.p, Dinv.p, r, nullptr, a, 1, st);
     ++launches;
     for (int k = 1; k < sweeps; ++k) {
+        halo_refresh(a);
         kt->jacobi_sweep(dm, J.p, D.p, Dinv.p, r, a, b, 0, st);
         ++launches;
         std::swap(a, b);
@@ -1170,9 +1176,10 @@ void Solver::precondition_Ax(const d4* x, d4* r_buf, d4* z)
     d4* a = z; d4* b = kry_t.p;
     const int sweeps = std::max(1, precond_sweeps);
     if ((sweeps - 1) % 2) std::swap(a, b);
-    kt->spmv_sweep0(dm, J.p, D.p, Dinv.p, x, r_buf, a, st);
+    kt->spmv_sweep0(dm, J.p, D.p, Dinv.p, x, r_buf, a, st);  // the caller keeps the halo rows of x current
     ++launches;
     for (int k = 1; k < sweeps; ++k) {
+        halo_refresh(a);
         kt->jacobi_sweep(dm, J.p, D.p, Dinv.p, r_buf, a, b, 0, st);
         ++launches;
         std::swap(a, b);
@@ -1191,8 +1198,10 @@ bool Solver::gmres(const d4* b, d4* x)
     last_linear_iters = 0;
     // r = M^-1 b
     d4* V0 = kry_V.p;
+    const uint32_t nd = n_dot();
     apply_preconditioner(b, kry_w.p);
-    kt->multi_dot1(NT, kry_w.p, stride, 1, kry_w.p, kry_partial.p, kry_h.p, kry_counter.p, st); ++launches;
+    kt->multi_dot1(nd, kry_w.p, stride, 1, kry_w.p, kry_partial.p, kry_h.p, kry_counter.p, st); ++launches;
+    allreduce_sum(kry_h.p, 1);
     CK(cudaMemcpyAsync(hbuf.data(), kry_h.p, sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     const double r0 = std::sqrt(hbuf[0]);
@@ -1203,6 +1212,7 @@ bool Solver::gmres(const d4* b, d4* x)
     while (last_linear_iters < gmres_max_iter) {
         // V0 = r / beta   (kry_h[0] holds beta^2)
         kt->scale_from(NT, kry_w.p, kry_h.p, 1, 1, V0, st); ++launches;
+        halo_refresh(V0);
         std::fill(g.begin(), g.end(), 0.0); g[0] = beta;
         int k = 0;
         bool done = false;
@@ -1212,8 +1222,10 @@ bool Solver::gmres(const d4* b, d4* x)
             // the unfused sequence was 11 -- on the shipped meshes the step is bound by launches)
             precondition_Ax(kry_V.p + (size_t)k * stride, kry_z.p, kry_w.p);
             // h = V^T w ; w -= V h ; ||w||^2
-            kt->multi_dot1(NT, kry_V.p, stride, k + 1, kry_w.p, kry_partial.p, kry_h.p, kry_counter.p, st); ++launches;
-            kt->axpy_norm(NT, kry_V.p, stride, k + 1, kry_h.p, -1.0, kry_w.p, kry_partial.p, kry_h.p + (k + 1), kry_counter.p, st); ++launches;
+            kt->multi_dot1(nd, kry_V.p, stride, k + 1, kry_w.p, kry_partial.p, kry_h.p, kry_counter.p, st); ++launches;
+            allreduce_sum(kry_h.p, k + 1);
+            kt->axpy_norm(nd, kry_V.p, stride, k + 1, kry_h.p, -1.0, kry_w.p, kry_partial.p, kry_h.p + (k + 1), kry_counter.p, st); ++launches;
+            allreduce_sum(kry_h.p + (k + 1), 1);
             CK(cudaMemcpyAsync(hbuf.data(), kry_h.p, (size_t)(k + 2) * sizeof(double), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             const double hn = std::sqrt(hbuf[k + 1]);
@@ -1231,6 +1243,7 @@ bool Solver::gmres(const d4* b, d4* x)
             const double err = std::fabs(g[k + 1]) / r0;
             if (hn != 0 && k + 1 < m + 1) {  // v_{k+1} = w / ||w||   (kry_h[k+1] holds ||w||^2)
                 kt->scale_from(NT, kry_w.p, kry_h.p + (k + 1), 1, 1, kry_V.p + (size_t)(k + 1) * stride, st); ++launches;
+                halo_refresh(kry_V.p + (size_t)(k + 1) * stride);
             }
             if (err < gmres_tol || hn == 0) { ++k; done = true; break; }
         }
@@ -1245,10 +1258,12 @@ bool Solver::gmres(const d4* b, d4* x)
         CK(cudaStreamSynchronize(st));  // y is reused
         if (done) return true;
         // restart: r = M^-1 (b - A x)
+        halo_refresh(x);
         kt->spmv(dm, J.p, D.p, x, kry_z.p, st); ++launches;
         kt->sub(NT, b, kry_z.p, kry_z.p, st); ++launches;
         apply_preconditioner(kry_z.p, kry_w.p);
-        kt->multi_dot1(NT, kry_w.p, stride, 1, kry_w.p, kry_partial.p, kry_h.p, kry_counter.p, st); ++launches;
+        kt->multi_dot1(nd, kry_w.p, stride, 1, kry_w.p, kry_partial.p, kry_h.p, kry_counter.p, st); ++launches;
+        allreduce_sum(kry_h.p, 1);
         CK(cudaMemcpyAsync(hbuf.data(), kry_h.p, sizeof(double), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         beta = std::sqrt(hbuf[0]);
@@ -1269,14 +1284,16 @@ double Solver::step_implicit(double relax, double tol, int rhs_iterations)
     if (err < tol) return err;
     const double err_ini = err;
     if (!gmres(rhs.p, kry_x.p)) return -1;
-    kt->axpy_state(NT, relax, kry_x.p, q.p, st); ++launches;
+    kt->axpy_state(n_dot(), relax, kry_x.p, q.p, st); ++launches;
+    halo_refresh(q.p);
     for (int i = 0; i < rhs_iterations; ++i) {
         err = residual_rhs();
         if (!(err == err)) return -1;
         if (err < tol) return err;
         if (err > 10 * err_ini) return err;
         if (!gmres(rhs.p, kry_x.p)) return -1;
-        kt->axpy_state(NT, relax, kry_x.p, q.p, st); ++launches;
+        kt->axpy_state(n_dot(), relax, kry_x.p, q.p, st); ++launches;
+        halo_refresh(q.p);
     }
     err = residual_rhs();
     sync_ghost_rows();
@@ -1723,7 +1740,6 @@ int afx_rans_step_implicit(afx_rans* s, double relaxation, double tol, int rhs_i
 {
     double v = -1;
     const int rc = guard([&] {
-        if (s->s.halo) throw afx::InvalidArg("the implicit step is single-GPU in this version");
         v = s->s.step_implicit(relaxation, tol, rhs_iterations);
     });
     if (norm) *norm = v;
@@ -1815,7 +1831,6 @@ int afx_rans_sweep(afx_rans* s, const afx_sweep_settings* st, int farfield_patch
         afx::set_error("farfield_patch is not a far-field patch of the last set_bcs");
         return AFX_ERR_INVALID;
     }
-    if (st->implicit && S.halo) { afx::set_error("the implicit step is single-GPU in this version"); return AFX_ERR_INVALID; }
     if (n_alpha <= 0) return AFX_OK;
     int rc = AFX_OK;
     // rans.h:86-88: the first angle is in place when the field is initialised

@@ -240,7 +240,9 @@ int afx_rans_compute(afx_rans* s);
 /* implicitSolver::solve (solver.h:1170-1213): RHS, left-preconditioned restarted GMRES on the device with the
  * frozen Jacobian, q += relaxation * dq, up to 1 + rhs_iterations times with the reference's early exits;
  * *norm = final ||RhoVector||_2.  AFX_ERR_NUMERIC (and *norm = -1) where the reference returns -1.  The linear
- * solver is NOT Eigen's: per-iteration histories of the implicit path are "parity unpinned" (DESIGN.md). */
+ * solver is NOT Eigen's: per-iteration histories of the implicit path are "parity unpinned" (DESIGN.md).
+ * Partitioned handles: every rank calls it; the halo rows of the Krylov vectors are fetched from their owners before
+ * each matrix-vector product and Jacobi sweep, inner products are summed over the ranks. */
 int afx_rans_step_implicit(afx_rans* s, double relaxation, double tol, int rhs_iterations, double* norm);
 /* defaults mirror solver.h:906-910 (restart 30, 500 iterations, tolerance 1e-2); precond_sweeps block-Jacobi sweeps */
 int afx_rans_set_linear_solver(afx_rans* s, int restart, int max_iterations, double tolerance, int precond_sweeps);
@@ -261,7 +263,7 @@ int afx_rans_wall_cp(afx_rans* s, int patch, double* cp);
  * (post.h:301-387).  cl/cd/cm/iterations/residual have n_alpha entries (any may be NULL).  A chain of angles per GPU is
  * how the polar database of the VLM viscous correction is sharded (BASELINE config 5: no communication between chains).
  * Returns AFX_ERR_NUMERIC where the reference's run_solver returns 1 (the angles done so far are filled in).
- * Partitioned handles: explicit only, called by every rank. */
+ * Partitioned handles: called by every rank with the same arguments (explicit and implicit). */
 typedef struct afx_sweep_settings {
     int implicit;            /* 0: explicitSolver, 1: implicitSolver */
     double relaxation, start_cfl, slope_cfl, max_cfl, tolerance;
