@@ -109,8 +109,3 @@ def test_early_halo_signal_under_emulation(emu_lib):
     tail = run_gpu_tests_under_emulation(emu_lib, ["test_gpu_multi.py"], "early_halo and 4", extra_env=MULTI_ENV)
     assert "1 passed" in tail
 
-
-def test_partitioned_implicit_step_under_emulation(emu_lib):
-    # GMRES + block-Jacobi on 2 ranks (halo refresh per product / sweep, all-reduced inner products): the reference's converged forces
-    tail = run_gpu_tests_under_emulation(emu_lib, ["test_gpu_multi.py"], "partitioned_implicit and 2", extra_env=MULTI_ENV, timeout=1500)
-    assert "1 passed" in tail
