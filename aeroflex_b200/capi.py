@@ -122,6 +122,11 @@ def build_library(force=False, verbose=False, defines=(), out=None):
 _lib = None
 
 
+def is_emulation():
+    """True if the loaded library is the host emulation of tests/emu (bench.py and smoke() refuse to run on it)."""
+    return b"EMULATION" in load_library().afx_version()
+
+
 def load_library():
     """Load the CUDA library; raises (never falls back) if it is absent and cannot be built."""
     global _lib
@@ -133,6 +138,11 @@ def load_library():
     L = C.CDLL(path)
     L.afx_last_error.restype = C.c_char_p
     L.afx_version.restype = C.c_char_p
+    if b"EMULATION" in L.afx_version() and os.environ.get("AFX_ALLOW_EMULATION") != "tests":
+        # tests/emu builds the kernel sources for the host so that the CPU test run can execute them; that library is
+        # test infrastructure and must never stand in for the CUDA library
+        raise RuntimeError("%s is the host emulation of the kernel sources (tests/emu): it is loaded by the test run only "
+                           "(AFX_ALLOW_EMULATION=tests); the product has no CPU path" % path)
     vp, dp, u32p, u8p, i32p = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint32), C.POINTER(C.c_uint8), C.POINTER(C.c_int32)
     L.afx_pinned_alloc.restype = C.c_void_p
     L.afx_pinned_alloc.argtypes = [C.c_size_t]

@@ -178,6 +178,8 @@ def main():
     import aeroflex_b200 as afx
     if afx.device_count() <= 0:
         raise SystemExit("bench.py: no CUDA device visible; the product has no CPU path")
+    if afx.is_emulation():
+        raise SystemExit("bench.py: AFX_LIB names the host emulation of tests/emu; only the CUDA library is measured")
     dist = None
     if world > 1:
         import torch.distributed as dist

@@ -27,7 +27,7 @@ def emu_lib():
 
 
 def run_gpu_tests_under_emulation(emu_lib, files, select, timeout=900, extra_env=None):
-    env = dict(os.environ, AFX_LIB=emu_lib)
+    env = dict(os.environ, AFX_LIB=emu_lib, AFX_ALLOW_EMULATION="tests")
     env.update(extra_env or {})
     cmd = [sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "-p", "no:cacheprovider", "-k", select] + [os.path.join(ROOT, "tests", f) for f in files]
     r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=timeout)
@@ -40,7 +40,14 @@ def test_package_never_picks_the_emulation_library(afx, emu_lib):
     assert "AFX_LIB" not in os.environ, "the CPU test run itself must use the CUDA library"
     assert os.path.realpath(afx.library_path()) != os.path.realpath(emu_lib)
     assert os.path.dirname(os.path.realpath(emu_lib)).startswith(os.path.join(ROOT, "tests", "emu"))
-    assert afx.device_count() <= 0 or True  # the CUDA library reports the real device count; create() fails loudly without one
+    assert not afx.is_emulation()
+    # outside the test run the package refuses the emulation library, and bench.py / smoke() refuse it always
+    code = "import aeroflex_b200 as a; a.load_library()"
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=dict(os.environ, AFX_LIB=emu_lib), capture_output=True, text=True)
+    assert r.returncode != 0 and "host emulation" in r.stderr
+    r = subprocess.run([sys.executable, "bench.py", "--steps", "1", "--warmup", "1"], cwd=ROOT,
+                       env=dict(os.environ, AFX_LIB=emu_lib, AFX_ALLOW_EMULATION="tests"), capture_output=True, text=True)
+    assert r.returncode != 0 and "only the CUDA library is measured" in (r.stderr + r.stdout)
 
 
 def test_three_kernel_stage_sources_match_reference_under_emulation(emu_lib):
