@@ -32,6 +32,7 @@ EXPORTED_SYMBOLS = [
     "afx_partition_create", "afx_partition_free", "afx_partition_get_desc", "afx_partition_info", "afx_partition_cell_l2g",
     "afx_partition_edge_l2g", "afx_partition_peer", "afx_nccl_unique_id", "afx_rans_create_partitioned",
     "afx_rans_p2p_export", "afx_rans_p2p_connect", "afx_rans_halo_mode",
+    "afx_group_create", "afx_group_free", "afx_group_abort", "afx_rans_create_partitioned_group",
     "afx_rans_create", "afx_rans_destroy", "afx_rans_set_bcs", "afx_rans_set_options", "afx_rans_set_cfl",
     "afx_rans_set_math_mode", "afx_rans_get_math_mode", "afx_rans_set_fused", "afx_rans_tile_info", "afx_tiling_plan", "afx_tiling_plan_partition",
     "afx_rans_init", "afx_rans_refill_bcs", "afx_rans_bcs_from_internal", "afx_rans_set_q", "afx_rans_get_q",
@@ -176,6 +177,10 @@ def load_library():
     L.afx_rans_p2p_connect.argtypes = [vp, C.c_char_p, C.c_size_t, C.c_int]
     L.afx_rans_halo_mode.argtypes = [vp]
     L.afx_rans_create_partitioned.argtypes = [C.POINTER(vp), vp, C.POINTER(Gas), C.c_int, C.c_int, C.c_char_p]
+    L.afx_group_create.argtypes = [C.POINTER(vp), C.c_int]
+    L.afx_group_free.argtypes = [vp]
+    L.afx_group_abort.argtypes = [vp]
+    L.afx_rans_create_partitioned_group.argtypes = [C.POINTER(vp), vp, C.POINTER(Gas), C.c_int, C.c_int, vp]
     L.afx_rans_destroy.argtypes = [vp]
     L.afx_rans_set_bcs.argtypes = [vp, C.c_int, vp, C.POINTER(BVars)]
     L.afx_rans_set_options.argtypes = [vp, C.c_int, C.c_int, C.c_double]
@@ -400,12 +405,55 @@ def tiling_plan(mesh, tile_cells, limits=None):
     return per[:n.value].copy(), int(smem.value)
 
 
+class Group:
+    """In-process communicator for N partitioned solvers of this process (one host thread per solver): stands where NCCL
+    stands, so that all ranks can share one device."""
+
+    def __init__(self, nranks):
+        self.L = load_library()
+        self.h = C.c_void_p()
+        self.nranks = nranks
+        _check(self.L.afx_group_create(C.byref(self.h), nranks))
+
+    def abort(self):
+        self.L.afx_group_abort(self.h)
+
+    def __del__(self):
+        try:
+            self.L.afx_group_free(self.h)
+        except Exception:
+            pass
+
+
+def run_ranks(fns):
+    """Run one callable per rank, each on its own host thread (ctypes releases the GIL inside the library), and re-raise
+    the first failure.  The collective calls of an in-process group meet this way."""
+    import threading
+    errs = [None] * len(fns)
+    outs = [None] * len(fns)
+
+    def go(i):
+        try:
+            outs[i] = fns[i]()
+        except BaseException as e:  # noqa: BLE001 -- handed to the caller
+            errs[i] = e
+    ts = [threading.Thread(target=go, args=(i,)) for i in range(len(fns))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    for e in errs:
+        if e is not None:
+            raise e
+    return outs
+
+
 class GpuSolver:
     """rans::solver on one B200 through the C ABI."""
 
-    def __init__(self, mesh, gas=None, viscosity="inviscid", device=0, math=None, nccl_id=None):
+    def __init__(self, mesh, gas=None, viscosity="inviscid", device=0, math=None, nccl_id=None, group=None):
         """math: "strict" (bit-identical to the CPU reference), "fast" (default; shared reciprocals + FMA) or None
-        (library default / AFX_MATH)."""
+        (library default / AFX_MATH).  group: an in-process Group instead of NCCL (mesh = Partition)."""
         self.L = load_library()
         self.mesh = mesh
         g = gas or {}
@@ -416,7 +464,11 @@ class GpuSolver:
         if isinstance(mesh, Partition):
             # one piece of a partitioned mesh: mesh = Partition, nccl_id = the 128-byte id made on rank 0
             self.partition = mesh
-            _check(self.L.afx_rans_create_partitioned(C.byref(self.h), mesh.h, C.byref(self.gas), VISCOSITY[viscosity], device, nccl_id))
+            self.group = group  # keeps the communicator alive as long as a member
+            if group is not None:
+                _check(self.L.afx_rans_create_partitioned_group(C.byref(self.h), mesh.h, C.byref(self.gas), VISCOSITY[viscosity], device, group.h))
+            else:
+                _check(self.L.afx_rans_create_partitioned(C.byref(self.h), mesh.h, C.byref(self.gas), VISCOSITY[viscosity], device, nccl_id))
             mesh = mesh.global_mesh
             self.mesh = mesh
         else:

@@ -556,7 +556,8 @@ __global__ void __launch_bounds__(AFX_GATHER_THREADS) k_gather_update(DevMesh m,
                     const uint32_t d = push.dst[k], p = d >> 28, slot = d & 0x0FFFFFFFu;
                     push.peer_buf[p][par * push.peer_stride[p] + slot] = o;
                 }
-                __threadfence_system();
+                // no fence per thread: the flags are raised after a system-scope fence that follows all of these stores --
+                // in k_halo_signal (a later kernel of this stream) or, with the early hand-off, once per front CTA below
             }
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
@@ -574,7 +575,8 @@ __global__ void __launch_bounds__(AFX_GATHER_THREADS) k_gather_update(DevMesh m,
         }
     }
     if (MODE == 0 && push.early_signal && blockIdx.x < push.n_front_blocks) {  // uniform per CTA
-        // every store of this CTA into the peers' buffers has been issued and fenced (system scope) by its thread
+        // every store of this CTA into the peers' buffers has been issued: one system-scope fence per CTA (cumulative over
+        // the stores the barrier has ordered before it), not one per thread
         __syncthreads();
         if (threadIdx.x == 0) {
             __threadfence_system();
@@ -705,12 +707,12 @@ __global__ void __launch_bounds__(256) k_wall_forces(WallArgs a, DevMesh m, cons
     for (uint32_t b = threadIdx.x; b < G; b += blockDim.x) {
         if (bpatch[b] != patch) continue;
         const uint32_t f = bface[b];
-        if (m.fcells[f].x >= m.n_upd) continue;  // the wall face of a halo cell belongs to another rank
         const d4 qc = q[m.fcells[f].x];
         const d4 gA = m.fgA[f];
         const double p = (gam - 1) * (qc.w - 0.5 / qc.x * (qc.y * qc.y + qc.z * qc.z));
         const double cp = 2. / (gam * mach_inf * mach_inf) * (p / p_inf - 1.);
-        if (cp_out) cp_out[b] = cp;
+        if (cp_out) cp_out[b] = cp;  // halo cells carry their owners' states: every wall edge this rank holds gets its cp
+        if (m.fcells[f].x >= m.n_upd) continue;  // ...but the FORCE of a halo cell's wall face belongs to another rank
         const double fxi = cp * gA.x * gA.z / (xmax - xmin);
         const double fyi = cp * gA.y * gA.z / (xmax - xmin);
         const double mi = (bcx[b] - x_moment) / (xmax - xmin) * fyi - (bcy[b] - y_moment) / (xmax - xmin) * fxi;
@@ -746,12 +748,34 @@ __global__ void k_halo_signal(SignalArgs a)
     if (threadIdx.x == 0) *a.epoch = e;
 }
 // wait until every peer has delivered exchange #epoch, then copy the receive buffer of that parity into the halo cells
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// The wait is BOUNDED: a peer that died, threw, or chose another halo mode never raises its flag, and an unbounded spin
+// would leave an unkillable kernel on every surviving GPU.  After a.timeout_ns the waiting thread records 1 + the peer's
+// slot in *a.err (host-visible), gives up on all peers, and the host turns that into AFX_ERR_COMM after the run.
 __global__ void __launch_bounds__(256) k_halo_wait_scatter(WaitArgs a, d4* __restrict__ field)
 {
     const unsigned long long e = *a.epoch;
     if (threadIdx.x == 0) {
-        for (int p = 0; p < a.n_peers; ++p)
-            while (*reinterpret_cast<const volatile unsigned long long*>(a.flag[p]) < e) { }
+        bool dead = a.err && *reinterpret_cast<volatile int*>(a.err) != 0;  // an earlier exchange already failed: do not wait again
+        unsigned long long t0 = 0;
+        for (int p = 0; p < a.n_peers && !dead; ++p) {
+            unsigned spins = 0;
+            while (*reinterpret_cast<const volatile unsigned long long*>(a.flag[p]) < e) {
+                if (++spins < 64u) continue;           // the flag usually arrives within a microsecond or two
+                if (t0 == 0) t0 = global_timer_ns();
+                __nanosleep(200);
+                if (a.timeout_ns && global_timer_ns() - t0 > a.timeout_ns) {
+                    if (a.err) *reinterpret_cast<volatile int*>(a.err) = 1 + p;
+                    dead = true;
+                    break;
+                }
+            }
+        }
         __threadfence_system();
     }
     __syncthreads();

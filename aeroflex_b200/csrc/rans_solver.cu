@@ -11,8 +11,13 @@
 // per call.
 #include <cuda_runtime.h>
 
+#include <unistd.h>
+
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <condition_variable>
+#include <mutex>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -85,9 +90,52 @@ struct DBuf {
                                    std::to_string(__LINE__) + ")");                                  \
     } while (0)
 
-// halo exchange of one partitioned solver: one NCCL communicator, packed sends, scattered receives
+struct Solver;
+
+// In-process communicator: the partitioned solvers of ONE host process, one host thread per handle, on one device or
+// several.  It stands where NCCL stands -- the staged halo exchange and the small all-reduces -- so that a box with a
+// single GPU (where NCCL refuses two ranks on one device) can run every partition plan on hardware, and a single-process
+// driver of several GPUs needs no collective library.  Every collective call is a rendezvous of all ranks; a rank that
+// never arrives breaks the group after `timeout_s` and every waiter gets AFX_ERR_COMM instead of hanging.
+struct LocalGroup {
+    explicit LocalGroup(int n_) : n(n_), member((size_t)n_, nullptr), slot((size_t)n_) {}
+    const int n;
+    std::mutex mu;
+    std::condition_variable cv;
+    int arrived = 0;
+    uint64_t gen = 0;
+    bool broken = false;
+    double timeout_s = 120.;
+    std::vector<Solver*> member;              // set by init_halo, read between barriers
+    std::vector<std::vector<double>> slot;    // all-reduce operands, one per rank
+    void barrier()
+    {
+        std::unique_lock<std::mutex> lk(mu);
+        if (broken) throw CommError("in-process group is broken (a rank failed or never arrived)");
+        const uint64_t g = gen;
+        if (++arrived == n) { arrived = 0; ++gen; cv.notify_all(); return; }
+        const bool ok = cv.wait_for(lk, std::chrono::duration<double>(timeout_s), [&] { return gen != g || broken; });
+        if (!ok || broken) { broken = true; cv.notify_all(); throw CommError("in-process group: a rank did not reach the rendezvous"); }
+    }
+    void abort_group() { std::lock_guard<std::mutex> lk(mu); broken = true; cv.notify_all(); }
+    // sum over the ranks in rank order on every rank: the same bits everywhere
+    void allreduce_sum(int rank, double* v, int cnt)
+    {
+        slot[(size_t)rank].assign(v, v + cnt);
+        barrier();
+        for (int i = 0; i < cnt; ++i) {
+            double t = 0;
+            for (int r = 0; r < n; ++r) t += slot[(size_t)r][(size_t)i];
+            v[i] = t;
+        }
+        barrier();  // nobody overwrites a slot that is still being read
+    }
+};
+
+// halo exchange of one partitioned solver: one NCCL communicator (or the in-process group), packed sends, scattered receives
 struct Halo {
     ncclComm_t comm = nullptr;
+    std::shared_ptr<LocalGroup> grp;      // in-process communicator instead of NCCL
     int rank = 0, nranks = 1;
     struct Peer { int rank; uint32_t send_off, send_cnt, recv_off, recv_cnt; };
     std::vector<Peer> peers;
@@ -104,12 +152,15 @@ struct Halo {
     DBuf<uint32_t> dst_ptr, dst;          // CSR: send-layer cell -> (peer slot, position in its receive list)
     DBuf<unsigned long long> epoch;
     DBuf<unsigned int> front_done;
+    DBuf<double> red;                     // device scratch of the all-reduces (norm chunks, forces)
+    bool can_p2p = true;                  // this rank's plan fits the peer-memory path (agreed over all ranks at connect)
     bool early_signal = false;            // AFX_HALO_EARLY_SIGNAL=1
     PushArgs push{};
     SignalArgs sig{};
     WaitArgs wait{};
     ~Halo()
     {
+        if (grp) { std::lock_guard<std::mutex> lk(grp->mu); if (rank >= 0 && rank < grp->n) grp->member[(size_t)rank] = nullptr; }
         for (void* p : opened) cudaIpcCloseMemHandle(p);
         if (ipc_block) cudaFree(ipc_block);
         if (comm) NcclApi::get().CommDestroy(comm);
@@ -191,7 +242,7 @@ struct Solver {
     // neighbour rows are about to be read (matrix-vector product, Jacobi sweep) gets its halo rows from their owners first
     uint32_t n_dot() const { return halo ? n_upd : NT; }
     void halo_refresh(d4* field) { if (halo) exchange(field, st); }
-    void allreduce_sum(double* dev, int n) { if (halo && n > 0) NK(NcclApi::get().AllReduce(dev, dev, (size_t)n, ncclDouble, ncclSum, halo->comm, st)); }  // r_buf = A x, z = M^-1 r_buf; the product and the first sweep share a launch
+    void allreduce_sum(double* dev, int n) { if (halo && n > 0) comm_allreduce(dev, n); }  // r_buf = A x, z = M^-1 r_buf; the product and the first sweep share a launch
     bool gmres(const d4* b, d4* x);
     double step_implicit(double relax, double tol, int rhs_iterations);
     DBuf<double> partial, norms, prm, scratch;
@@ -236,7 +287,10 @@ struct Solver {
 
     struct DryRun { uint32_t tile_cells; TileLimits limits; TilePlan plan; std::string check; };  // host-only: renumber, tile, verify (no device)
     void create(const afx_mesh_desc& m, const afx_gas& g, int visc, int dev, const Partition* part = nullptr, DryRun* dry = nullptr);
-    void init_halo(const Partition& part, const char* nccl_id);
+    void init_halo(const Partition& part, const char* nccl_id, std::shared_ptr<LocalGroup> group = nullptr);
+    void comm_allreduce(double* dev, int n);   // sum over the ranks, in place, on the solver's stream
+    void check_comm();                         // AFX_ERR_COMM if a halo wait gave up on a peer
+    int* comm_err_word() { return reinterpret_cast<int*>(h_pinned + 48); }
     size_t p2p_export(void* blob);
     void p2p_connect(const void* blobs, size_t blob_size, int nranks);
     void exchange(d4* field, cudaStream_t stream);
@@ -307,11 +361,16 @@ void Solver::create(const afx_mesh_desc& m, const afx_gas& g, int visc, int dev,
         use();
         cudaDeviceProp prop{};
         CK(cudaGetDeviceProperties(&prop, dev));
-        if (prop.major < 10) throw CudaError(std::string("device '") + prop.name + "' is not sm_100 class; this library is built for sm_100a only");
+        // the kernels are built as arch=compute_100a,code=sm_100a: arch-specific, no forward compatibility (sm_103 / sm_110 / sm_120
+        // parts would fail at the first launch with "no kernel image")
+        if (prop.major != 10 || prop.minor != 0)
+            throw CudaError(std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                            "; this library is built for sm_100a (B200) only");
         CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
         for (auto& e : evp) CK(cudaEventCreate(&e));
         CK(cudaMallocHost(&h_pinned, 64 * sizeof(double)));
+        std::memset(h_pinned, 0, 64 * sizeof(double));
     }
     if (const char* e = getenv("AFX_NO_GRAPH")) use_graph = !(e[0] == '1');
     if (const char* e = getenv("AFX_HALO_OVERLAP")) halo_overlap = (e[0] == '1');
@@ -674,7 +733,8 @@ void Solver::launch_flux(const d4* qk, bool uniform, d4 qfar)
 template <int MODE, int LAST>
 void Solver::launch_gather(const d4* qk_in, d4* qk_out, d4* vec_out, double alpha, bool walls)
 {
-    if (halo && MODE == 0 && halo->p2p && !halo_overlap) {
+    const bool split_front = n_front > 0 && n_front < n_upd;
+    if (halo && MODE == 0 && halo->p2p && !(halo_overlap && split_front)) {
         // one launch advances everything and pushes the send layer into the peers' buffers; a flag hand-off and a
         // small wait+scatter kernel complete the halo on the same stream (no fork/join, no split launches)
         if (halo->early_signal) {
@@ -694,7 +754,7 @@ void Solver::launch_gather(const d4* qk_in, d4* qk_out, d4* vec_out, double alph
         launches += 3;
         return;
     }
-    if (halo && MODE == 0 && n_front > 0 && n_front < n_upd) {
+    if (halo && MODE == 0 && split_front && !(halo->grp && !halo->p2p)) {
         // send layer first, then the exchange on the halo stream while the interior cells are advanced
         NormOut no = norm_out();
         const unsigned b0 = kt->gather_blocks(n_front), b1 = kt->gather_blocks(n_upd - n_front);
@@ -856,7 +916,7 @@ void Solver::explicit_iteration()
 }
 
 // NCCL halo: the ring cells' states come from their owners after every stage
-void Solver::init_halo(const Partition& part, const char* nccl_id)
+void Solver::init_halo(const Partition& part, const char* nccl_id, std::shared_ptr<LocalGroup> group)
 {
     halo.reset(new Halo);
     Halo& h = *halo;
@@ -881,10 +941,19 @@ void Solver::init_halo(const Partition& part, const char* nccl_id)
     h.send_idx.upload(si, st); h.recv_idx.upload(ri, st);
     h.send_buf.alloc(si.size()); h.recv_buf.alloc(ri.size());
     CK(cudaStreamSynchronize(st));
-    ncclUniqueId id;
-    static_assert(sizeof(id) == 128, "ncclUniqueId is 128 bytes");
-    std::memcpy(&id, nccl_id, sizeof(id));
-    NK(NcclApi::get().CommInitRank(&h.comm, h.nranks, id, h.rank));
+    h.red.alloc(64);
+    if (group) {
+        if (group->n != h.nranks) throw InvalidArg("the in-process group was created for another number of ranks");
+        h.grp = group;
+        std::lock_guard<std::mutex> lk(group->mu);
+        if (group->member[(size_t)h.rank]) throw InvalidArg("rank already present in the in-process group");
+        group->member[(size_t)h.rank] = this;
+    } else {
+        ncclUniqueId id;
+        static_assert(sizeof(id) == 128, "ncclUniqueId is 128 bytes");
+        std::memcpy(&id, nccl_id, sizeof(id));
+        NK(NcclApi::get().CommInitRank(&h.comm, h.nranks, id, h.rank));
+    }
     cell_l2g = part.cell_l2g;
     n_global = part.n_global_cells + part.n_global_ghost;
 }
@@ -893,6 +962,29 @@ void Solver::exchange(d4* field, cudaStream_t st)
 {
     Halo& h = *halo;
     if (h.n_send) { kt->permute4(field, h.send_buf.p, h.send_idx.p, h.n_send, st); ++launches; }
+    if (h.grp) {
+        // staged exchange of the in-process group: every rank packs, all meet, every rank copies its peers' packed
+        // layers into its receive buffer (device to device, across devices if the handles live on several), all meet again
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        CK(cudaStreamIsCapturing(st, &cap));
+        if (cap != cudaStreamCaptureStatusNone) throw InvalidArg("the staged in-process halo cannot be captured into a graph");
+        CK(cudaStreamSynchronize(st));
+        h.grp->barrier();
+        for (const auto& p : h.peers) {
+            if (!p.recv_cnt) continue;
+            const Solver* P = h.grp->member[(size_t)p.rank];
+            if (!P || !P->halo) throw CommError("in-process group: peer rank " + std::to_string(p.rank) + " is missing");
+            const Halo::Peer* mine = nullptr;
+            for (const auto& q : P->halo->peers) if (q.rank == h.rank) mine = &q;
+            if (!mine || mine->send_cnt != p.recv_cnt) throw CommError("halo plans of two ranks disagree");
+            CK(cudaMemcpyPeerAsync(h.recv_buf.p + p.recv_off, device, P->halo->send_buf.p + mine->send_off, P->device,
+                                   (size_t)p.recv_cnt * sizeof(d4), st));
+        }
+        if (h.n_recv) { kt->scatter4(h.recv_buf.p, field, h.recv_idx.p, h.n_recv, st); ++launches; }
+        CK(cudaStreamSynchronize(st));
+        h.grp->barrier();  // nobody repacks while a peer still reads
+        return;
+    }
     NK(NcclApi::get().GroupStart());
     for (const auto& p : h.peers) {
         if (p.send_cnt) NK(NcclApi::get().Send(h.send_buf.p + p.send_off, (size_t)p.send_cnt * 4, ncclDouble, p.rank, h.comm, st));
@@ -908,6 +1000,10 @@ struct P2PBlob {
     cudaIpcMemHandle_t handle;
     uint32_t n_recv, n_peers;
     P2PBlobPeer peers[16];
+    int64_t pid;            // exporter's process: an importer in the same process uses raw_ptr (CUDA IPC cannot map a block
+    uint64_t raw_ptr;       // into the process that owns it)
+    int32_t device;
+    int32_t can_p2p;        // the exporter's plan fits the peer-memory path; every rank must, or all stay on the collective halo
 };
 constexpr size_t P2P_FLAG_BYTES = 1024;
 
@@ -915,7 +1011,7 @@ size_t Solver::p2p_export(void* blob)
 {
     if (!halo) throw InvalidArg("not a partitioned solver");
     Halo& h = *halo;
-    if (h.peers.size() > P2P_MAX_PEERS) throw InvalidArg("too many halo peers for the peer-memory path");
+    h.can_p2p = h.peers.size() <= (size_t)P2P_MAX_PEERS && h.peers.size() <= 16;
     if (!h.ipc_block) {
         const size_t bytes = P2P_FLAG_BYTES + 2 * (size_t)std::max<uint32_t>(h.n_recv, 1) * sizeof(d4);
         CK(cudaMalloc(&h.ipc_block, bytes));
@@ -925,8 +1021,9 @@ size_t Solver::p2p_export(void* blob)
     }
     P2PBlob b{};
     CK(cudaIpcGetMemHandle(&b.handle, h.ipc_block));
-    b.n_recv = h.n_recv; b.n_peers = (uint32_t)h.peers.size();
-    for (size_t k = 0; k < h.peers.size(); ++k) { b.peers[k].rank = h.peers[k].rank; b.peers[k].recv_off = h.peers[k].recv_off; b.peers[k].recv_cnt = h.peers[k].recv_cnt; }
+    b.n_recv = h.n_recv; b.n_peers = (uint32_t)std::min<size_t>(h.peers.size(), 16);
+    b.pid = (int64_t)getpid(); b.raw_ptr = (uint64_t)(uintptr_t)h.ipc_block; b.device = device; b.can_p2p = h.can_p2p ? 1 : 0;
+    for (size_t k = 0; k < h.peers.size() && k < 16; ++k) { b.peers[k].rank = h.peers[k].rank; b.peers[k].recv_off = h.peers[k].recv_off; b.peers[k].recv_cnt = h.peers[k].recv_cnt; }
     if (blob) std::memcpy(blob, &b, sizeof b);
     return sizeof b;
 }
@@ -939,6 +1036,11 @@ void Solver::p2p_connect(const void* blobs, size_t blob_size, int nranks)
     use();
     const P2PBlob* all = static_cast<const P2PBlob*>(blobs);
     h.push = PushArgs{}; h.sig = SignalArgs{}; h.wait = WaitArgs{};
+    // the ranks never talk about the halo mode again: it is decided here, from data every rank sees identically.  One rank
+    // on the collective exchange while its peers push and spin on flags would be a silent deadlock.
+    bool all_can = true;
+    for (int r = 0; r < nranks; ++r) all_can = all_can && all[r].can_p2p != 0;
+    if (!all_can) { h.p2p = false; invalidate_graph(); return; }
     std::vector<std::vector<uint32_t>> per_cell(n_front);
     std::vector<uint32_t> si(h.n_send);
     if (h.n_send) CK(cudaMemcpy(si.data(), h.send_idx.p, (size_t)h.n_send * sizeof(uint32_t), cudaMemcpyDeviceToHost));
@@ -946,8 +1048,17 @@ void Solver::p2p_connect(const void* blobs, size_t blob_size, int nranks)
         const auto& pk = h.peers[k];
         const P2PBlob& pb = all[pk.rank];
         void* base = nullptr;
-        CK(cudaIpcOpenMemHandle(&base, pb.handle, cudaIpcMemLazyEnablePeerAccess));
-        h.opened.push_back(base);
+        if (pb.pid == (int64_t)getpid()) {  // a handle of this process (in-process group): its block is addressable as it is
+            base = reinterpret_cast<void*>((uintptr_t)pb.raw_ptr);
+            if (pb.device != device) {
+                const cudaError_t e = cudaDeviceEnablePeerAccess(pb.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
+                cudaGetLastError();
+            }
+        } else {
+            CK(cudaIpcOpenMemHandle(&base, pb.handle, cudaIpcMemLazyEnablePeerAccess));
+            h.opened.push_back(base);
+        }
         const P2PBlobPeer* mine = nullptr;
         for (uint32_t j = 0; j < pb.n_peers; ++j) if (pb.peers[j].rank == h.rank) mine = &pb.peers[j];
         if (!mine || mine->recv_cnt != pk.send_cnt) throw InvalidArg("halo plans of two ranks disagree");
@@ -972,13 +1083,18 @@ void Solver::p2p_connect(const void* blobs, size_t blob_size, int nranks)
     h.wait.n_peers = (int)h.peers.size(); h.wait.epoch = h.epoch.p;
     h.wait.recv_buf = reinterpret_cast<const d4*>(static_cast<char*>(h.ipc_block) + P2P_FLAG_BYTES);
     h.wait.recv_idx = h.recv_idx.p; h.wait.n_recv = h.n_recv;
+    double timeout_ms = 20000.;  // AFX_HALO_TIMEOUT_MS: how long a halo wait spins for a peer before it gives up (0: for ever)
+    if (const char* e = getenv("AFX_HALO_TIMEOUT_MS")) timeout_ms = atof(e);
+    h.wait.timeout_ns = (unsigned long long)(timeout_ms * 1e6);
+    *comm_err_word() = 0;
+    h.wait.err = comm_err_word();  // pinned host memory, addressable from the device (unified addressing)
     h.front_done.alloc(1);
     CK(cudaMemset(h.front_done.p, 0, sizeof(unsigned int)));
     h.push.early_signal = 0; h.push.n_front_blocks = 0; h.push.front_done = h.front_done.p; h.push.epoch_rw = h.epoch.p;
     h.push.n_peers = (int)h.peers.size();
     for (size_t k = 0; k < h.peers.size(); ++k) h.push.peer_flag[k] = h.sig.peer_flag[k];
     if (const char* e = getenv("AFX_HALO_EARLY_SIGNAL")) h.early_signal = (e[0] == '1');
-    h.p2p = (n_front > 0 && n_front < n_upd);
+    h.p2p = true;  // every rank can: the single-launch path works for any front size (an all-front or empty send layer included)
     invalidate_graph();
 }
 
@@ -986,13 +1102,42 @@ void Solver::p2p_connect(const void* blobs, size_t blob_size, int nranks)
 void Solver::reduce_norms(double* v, int n)
 {
     if (!halo || n <= 0) return;
-    DBuf<double> d;
-    d.alloc((size_t)n);
-    CK(cudaMemcpyAsync(d.p, v, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
-    NK(NcclApi::get().AllReduce(d.p, d.p, (size_t)n, ncclDouble, ncclSum, halo->comm, st));
-    CK(cudaMemcpyAsync(v, d.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    Halo& h = *halo;
+    if (h.grp) {  // host values already: sum them in rank order
+        h.grp->allreduce_sum(h.rank, v, n);
+    } else {
+        if (h.red.n < (size_t)n) h.red.alloc((size_t)n);  // persistent scratch: no allocation (a device-wide sync) per call
+        CK(cudaMemcpyAsync(h.red.p, v, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+        NK(NcclApi::get().AllReduce(h.red.p, h.red.p, (size_t)n, ncclDouble, ncclSum, h.comm, st));
+        CK(cudaMemcpyAsync(v, h.red.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
     for (int i = 0; i < n; ++i) v[i] = std::sqrt(v[i]);
+}
+
+// sum of a small device vector over the ranks, in place, ordered on the solver's stream
+void Solver::comm_allreduce(double* dev, int n)
+{
+    if (!halo || n <= 0) return;
+    Halo& h = *halo;
+    if (!h.grp) { NK(NcclApi::get().AllReduce(dev, dev, (size_t)n, ncclDouble, ncclSum, h.comm, st)); return; }
+    std::vector<double> tmp((size_t)n);
+    CK(cudaMemcpyAsync(tmp.data(), dev, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    h.grp->allreduce_sum(h.rank, tmp.data(), n);
+    CK(cudaMemcpyAsync(dev, tmp.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));  // tmp goes out of scope
+}
+
+void Solver::check_comm()
+{
+    if (!halo || !halo->p2p) return;
+    const int e = *reinterpret_cast<volatile int*>(comm_err_word());
+    if (e == 0) return;
+    const int slot = e - 1;
+    const int peer = (slot >= 0 && slot < (int)halo->peers.size()) ? halo->peers[(size_t)slot].rank : -1;
+    throw CommError("halo wait timed out: rank " + std::to_string(peer) + " did not deliver its send layer (peer dead, or on another halo mode); "
+                    "the state of this solver is no longer valid");
 }
 
 double Solver::fetch_last_norm()
@@ -1006,6 +1151,7 @@ double Solver::fetch_last_norm()
     CK(cudaMemcpyAsync(h_pinned, norms.p + ((k - 1) % NORM_RING), sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     norm_idx_host = k;
+    check_comm();
     double v = h_pinned[0];
     reduce_norms(&v, 1);
     return v;
@@ -1028,7 +1174,7 @@ void Solver::run_explicit(double relax, int n_iter, double* norms_out)
         CK(cudaMemcpyAsync(h_idx, counters.p + 1, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         const unsigned int k0 = *h_idx;
-        if (use_graph) {
+        if (use_graph && !(halo && halo->grp && !halo->p2p)) {  // the staged in-process halo meets on the host: no capture
             if (!graph_exec) {
                 cudaGraph_t g = nullptr;
                 const int64_t l0 = launches;
@@ -1069,6 +1215,7 @@ void Solver::run_explicit(double relax, int n_iter, double* norms_out)
                 it += n;
             }
             CK(cudaStreamSynchronize(st));
+            check_comm();
             reduce_norms(tmp.data(), chunk);
             std::copy(tmp.begin(), tmp.end(), norms_out + done);
         }
@@ -1080,6 +1227,7 @@ void Solver::run_explicit(double relax, int n_iter, double* norms_out)
     CK(cudaEventElapsedTime(&ms, ev0, ev1));
     last_ms = ms;
     jac_valid = false;
+    check_comm();
 }
 
 // implicitSolver::fillRhoRHS, solver.h:1079-1152
@@ -1429,6 +1577,34 @@ int afx_rans_create_partitioned(afx_rans** out, const afx_partition* part, const
     return AFX_OK;
 }
 
+struct afx_group_impl;
+int afx_group_create(afx_group** out, int nranks)
+{
+    if (!out || nranks < 1) { afx::set_error("bad argument"); return AFX_ERR_INVALID; }
+    *out = reinterpret_cast<afx_group*>(new std::shared_ptr<afx::LocalGroup>(std::make_shared<afx::LocalGroup>(nranks)));
+    return AFX_OK;
+}
+void afx_group_free(afx_group* g) { delete reinterpret_cast<std::shared_ptr<afx::LocalGroup>*>(g); }
+void afx_group_abort(afx_group* g) { if (g) (*reinterpret_cast<std::shared_ptr<afx::LocalGroup>*>(g))->abort_group(); }
+
+int afx_rans_create_partitioned_group(afx_rans** out, const afx_partition* part, const afx_gas* gas, int viscosity_model, int device,
+                                      afx_group* group)
+{
+    if (!out || !part || !gas || !group) { afx::set_error("null argument"); return AFX_ERR_INVALID; }
+    *out = nullptr;
+    afx_rans* h = nullptr;
+    const int rc = guard([&] {
+        if (viscosity_model < 0 || viscosity_model > 2) throw afx::InvalidArg("viscosity model must be 0, 1 or 2");
+        h = new afx_rans;
+        const afx_mesh_desc d = part->p.desc();
+        h->s.create(d, *gas, viscosity_model, device, &part->p);
+        h->s.init_halo(part->p, nullptr, *reinterpret_cast<std::shared_ptr<afx::LocalGroup>*>(group));
+    });
+    if (rc) { delete h; return rc; }
+    *out = h;
+    return AFX_OK;
+}
+
 void afx_rans_destroy(afx_rans* s) { delete s; }
 
 int afx_rans_set_bcs(afx_rans* s, int n_patch, const uint8_t* patch_kind, const afx_bvars* patch_vars)
@@ -1501,6 +1677,7 @@ int afx_rans_get_math_mode(afx_rans* s) { return s->s.kt == &afx::strict::table(
 
 int afx_rans_set_cfl(afx_rans* s, double cfl)
 {
+    if (!s) { afx::set_error("null argument"); return AFX_ERR_INVALID; }
     s->s.cfl = cfl;
     return AFX_OK;
 }
@@ -1787,7 +1964,7 @@ int afx_rans_wall_forces(afx_rans* s, int patch, double out[3])
                                         S.scratch.p, nullptr}, S.dm, S.q.p, S.st);
         ++S.launches;
         CK(cudaGetLastError());
-        if (S.halo) NK(afx::NcclApi::get().AllReduce(S.scratch.p, S.scratch.p, 3, ncclDouble, ncclSum, S.halo->comm, S.st));
+        S.comm_allreduce(S.scratch.p, 3);
         CK(cudaMemcpyAsync(S.h_pinned + 16, S.scratch.p, 3 * sizeof(double), cudaMemcpyDeviceToHost, S.st));
         CK(cudaStreamSynchronize(S.st));
         const double fx = S.h_pinned[16], fy = S.h_pinned[17], cm = S.h_pinned[18], aoa = far.angle;
@@ -1809,6 +1986,7 @@ int afx_rans_wall_cp(afx_rans* s, int patch, double* cp)
         S.boundary_variables(&far);
         afx::DBuf<double> d_cp;
         d_cp.alloc(S.G);
+        d_cp.zero(S.st);
         S.kt->wall_forces(afx::WallArgs{S.bface.p, S.bpatch.p, S.G, patch, S.bcx.p, S.bcy.p, S.gas.gamma, far.p, far.mach, 0., 1., 0., 0.,
                                         S.scratch.p, d_cp.p}, S.dm, S.q.p, S.st);
         ++S.launches;
@@ -1875,8 +2053,13 @@ int afx_rans_sweep(afx_rans* s, const afx_sweep_settings* st, int farfield_patch
     return AFX_OK;
 }
 
-int afx_rans_last_device_ms(afx_rans* s, double* ms) { *ms = s->s.last_ms; return AFX_OK; }
-int64_t afx_rans_launch_count(afx_rans* s) { return s->s.launches; }
+int afx_rans_last_device_ms(afx_rans* s, double* ms)
+{
+    if (!s || !ms) { afx::set_error("null argument"); return AFX_ERR_INVALID; }
+    *ms = s->s.last_ms;
+    return AFX_OK;
+}
+int64_t afx_rans_launch_count(afx_rans* s) { return s ? s->s.launches : 0; }
 
 int afx_rans_profile_explicit(afx_rans* s, double relaxation, int n_iter, double out_ms[6])
 {

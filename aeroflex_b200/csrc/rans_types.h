@@ -127,6 +127,8 @@ struct WaitArgs {
     const d4* recv_buf;                           // [2][n_recv]
     const uint32_t* recv_idx;                     // [n_recv] halo cells to fill
     uint32_t n_recv;
+    unsigned long long timeout_ns;                // give up on a peer after this long (0: wait for ever)
+    int* err;                                     // host-visible word: 1 + slot of the peer that never delivered
 };
 
 struct WallArgs {

@@ -160,13 +160,31 @@ int afx_nccl_unique_id(char out[128]);
 int afx_rans_create_partitioned(afx_rans** out, const afx_partition* part, const afx_gas* gas, int viscosity_model,
                                 int device, const char nccl_id[128]);
 
+/* In-process group: the partitioned solvers of ONE host process (one host thread per handle; all ranks on one device, or
+ * one device each).  It stands where NCCL stands: the halo is exchanged by device-to-device copies between two host
+ * rendezvous (the "staged" halo, no CUDA graph), the norms and forces are summed on the host in rank order.  This is what
+ * lets a box with a single GPU run every partition plan on hardware (NCCL refuses two ranks on one device), and what a
+ * single-process driver of several GPUs uses.  afx_rans_p2p_export / _connect work on group members too (the blobs then
+ * carry plain device pointers): the peer-memory push, its flag hand-off and the captured graph run exactly as between
+ * processes.  Every collective call must be made by all ranks, each from its own host thread; a rank that never arrives
+ * breaks the group after 120 s and the waiting ranks return AFX_ERR_COMM.  afx_group_abort breaks it at once. */
+typedef struct afx_group afx_group;
+int afx_group_create(afx_group** out, int nranks);
+void afx_group_free(afx_group* g);   /* after the last member solver is destroyed */
+void afx_group_abort(afx_group* g);
+int afx_rans_create_partitioned_group(afx_rans** out, const afx_partition* part, const afx_gas* gas, int viscosity_model,
+                                      int device, afx_group* group);
+
 /* Halo over NVLink peer memory instead of NCCL (one node, one process per GPU, CUDA IPC): every rank exports a
  * blob (size returned in *size; pass blob = NULL to query), the host program all-gathers the blobs in rank order
  * and hands them to connect.  After that the update kernel itself stores the send layer into the peers' receive
  * buffers and a flag hand-off replaces the NCCL send/recv group; norms and forces still use NCCL all-reduce. */
 int afx_rans_p2p_export(afx_rans* s, void* blob, size_t* size);
 int afx_rans_p2p_connect(afx_rans* s, const void* blobs, size_t blob_size, int nranks);
-/* 0 single GPU, 1 NCCL halo, 2 peer-memory halo */
+/* A halo wait that sees no flag from a peer within AFX_HALO_TIMEOUT_MS (default 20000; 0 = wait for ever) gives up: the
+ * run that contains it returns AFX_ERR_COMM and the solver's state is no longer valid.  The peer-memory path is used only
+ * if EVERY rank's plan fits it (<= 8 peers); otherwise all ranks stay on the collective exchange.
+ * 0 single GPU, 1 NCCL (or staged in-process) halo, 2 peer-memory halo */
 int afx_rans_halo_mode(afx_rans* s);
 
 /* solver::set_bcs (solver.h:200-247): kind and far-field variables per patch id */

@@ -4,6 +4,9 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# tests/test_gpu_group.py runs up to 8 partitioned solvers of this process on one GPU, each with its own streams and with kernels
+# that wait for flags raised by another solver's kernels: give every stream its own hardware queue (read at CUDA initialisation)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 

@@ -417,6 +417,9 @@ cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t n, cudaMemcpyKind
     afx_emu::submit(st, [=] { memmove(dst, src, n); });
     return cudaSuccess;
 }
+cudaError_t cudaMemcpyPeerAsync(void* dst, int, const void* src, int, size_t n, cudaStream_t st) { return cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToDevice, st); }
+cudaError_t cudaStreamIsCapturing(cudaStream_t st, cudaStreamCaptureStatus* s) { *s = (st && st->capture) ? cudaStreamCaptureStatusActive : cudaStreamCaptureStatusNone; return cudaSuccess; }
+cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
 cudaError_t cudaMemset(void* dst, int v, size_t n) { memset(dst, v, n); return cudaSuccess; }
 cudaError_t cudaMemsetAsync(void* dst, int v, size_t n, cudaStream_t st)
 {

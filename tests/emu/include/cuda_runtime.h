@@ -71,6 +71,10 @@ extern thread_local dim3 blockDim, gridDim;
 static inline void __syncthreads() { ::afx_emu::sync_block(); }
 static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+#include <time.h>
+#include <sched.h>
+static inline void __nanosleep(unsigned) { sched_yield(); }
+namespace afx_emu { static inline unsigned long long global_timer_ns() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return (unsigned long long)ts.tv_sec * 1000000000ull + (unsigned long long)ts.tv_nsec; } }
 [[noreturn]] static inline void __trap() { abort(); }
 static inline double __shfl_down_sync(unsigned, double v, int delta)
 {
@@ -90,7 +94,8 @@ static inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v
 
 // ---- runtime API ---------------------------------------------------------------------------------------------------
 typedef int cudaError_t;
-enum { cudaSuccess = 0, cudaErrorInvalidValue = 1, cudaErrorNotSupported = 801, cudaErrorNoDevice = 100 };
+enum { cudaSuccess = 0, cudaErrorInvalidValue = 1, cudaErrorNotSupported = 801, cudaErrorNoDevice = 100, cudaErrorPeerAccessAlreadyEnabled = 704 };
+enum cudaStreamCaptureStatus { cudaStreamCaptureStatusNone = 0, cudaStreamCaptureStatusActive = 1 };
 struct afx_emu_stream;
 struct afx_emu_graph;
 typedef afx_emu_stream* cudaStream_t;
@@ -139,6 +144,9 @@ cudaError_t cudaFree(void* p);
 cudaError_t cudaFreeHost(void* p);
 cudaError_t cudaMemcpy(void* dst, const void* src, size_t n, cudaMemcpyKind k);
 cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t n, cudaMemcpyKind k, cudaStream_t st);
+cudaError_t cudaMemcpyPeerAsync(void* dst, int dst_dev, const void* src, int src_dev, size_t n, cudaStream_t st);
+cudaError_t cudaStreamIsCapturing(cudaStream_t st, cudaStreamCaptureStatus* s);
+cudaError_t cudaDeviceEnablePeerAccess(int peer, unsigned flags);
 cudaError_t cudaMemset(void* dst, int v, size_t n);
 cudaError_t cudaMemsetAsync(void* dst, int v, size_t n, cudaStream_t st);
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t* st, unsigned flags);
