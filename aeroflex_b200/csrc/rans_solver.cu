@@ -10,6 +10,7 @@
 // residual norm is reduced on the device into a ring that the host reads once
 // per call.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>  // header-only; the ranges cost nothing unless a profiler injects itself
 
 #include <unistd.h>
 
@@ -50,6 +51,13 @@ struct NumericError : std::runtime_error {
 };
 struct CommError : std::runtime_error {
     using std::runtime_error::runtime_error;
+};
+
+// NVTX range over a scope (tracing): visible in nsys / ncu --nvtx timelines as "afx:<name>"
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
 };
 
 #define CK(call)                                                                                       \
@@ -352,6 +360,7 @@ bool Solver::boundary_variables(afx_bvars* out) const
 
 void Solver::create(const afx_mesh_desc& m, const afx_gas& g, int visc, int dev, const Partition* part, DryRun* dry)
 {
+    NvtxRange nvtx_("afx:create (renumber, tables, upload)");
     if (!dry) {
         int ndev = 0;
         if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -960,6 +969,7 @@ void Solver::init_halo(const Partition& part, const char* nccl_id, std::shared_p
 
 void Solver::exchange(d4* field, cudaStream_t st)
 {
+    NvtxRange nvtx_("afx:halo exchange (collective)");
     Halo& h = *halo;
     if (h.n_send) { kt->permute4(field, h.send_buf.p, h.send_idx.p, h.n_send, st); ++launches; }
     if (h.grp) {
@@ -1159,6 +1169,7 @@ double Solver::fetch_last_norm()
 
 void Solver::run_explicit(double relax, int n_iter, double* norms_out)
 {
+    NvtxRange nvtx_("afx:run_explicit");
     use();
     if (!bcs_set) throw InvalidArg("set_bcs has not been called");
     if (n_iter <= 0) return;
@@ -1233,6 +1244,7 @@ void Solver::run_explicit(double relax, int n_iter, double* norms_out)
 // implicitSolver::fillRhoRHS, solver.h:1079-1152
 double Solver::residual_rhs()
 {
+    NvtxRange nvtx_("afx:residual_rhs (fillRhoRHS)");
     use();
     if (!bcs_set) throw InvalidArg("set_bcs has not been called");
     push_params(relax_dev < 0 ? 1.0 : relax_dev);
@@ -1266,6 +1278,7 @@ double Solver::uniform_residual()
 // implicitSolver::fillRhoLHS, solver.h:979-1071
 void Solver::fill_jacobian()
 {
+    NvtxRange nvtx_("afx:fill_jacobian (fillRhoLHS)");
     use();
     if (!bcs_set) throw InvalidArg("set_bcs has not been called");
     push_params(relax_dev < 0 ? 1.0 : relax_dev);
@@ -1339,6 +1352,7 @@ void Solver::precondition_Ax(const d4* x, d4* r_buf, d4* z)
 // inner products of a step in one reduction; the Givens recurrence runs on the host (one small D2H per step).
 bool Solver::gmres(const d4* b, d4* x)
 {
+    NvtxRange nvtx_("afx:gmres");
     const int m = gmres_restart;
     const size_t stride = NT;
     std::vector<double> hbuf((size_t)m + 4);
@@ -1451,6 +1465,7 @@ double Solver::step_implicit(double relax, double tol, int rhs_iterations)
 
 void Solver::to_ref_order4(const d4* dev_new, double* host_out)
 {
+    NvtxRange nvtx_("afx:get (permute + D2H)");
     // stage[old] = dev_new[old2new[old]]
     kt->permute4(dev_new, stage.p, perm_c_old2new.p, NT, st);
     ++launches;
@@ -1460,6 +1475,7 @@ void Solver::to_ref_order4(const d4* dev_new, double* host_out)
 
 void Solver::from_ref_order4(const double* host_in, d4* dev_new)
 {
+    NvtxRange nvtx_("afx:set (H2D + permute)");
     CK(cudaMemcpyAsync(stage.p, host_in, (size_t)NT * sizeof(d4), cudaMemcpyHostToDevice, st));
     // dev_new[new] = stage[new2old[new]]
     kt->permute4(stage.p, dev_new, perm_c_new2old.p, NT, st);

@@ -5,9 +5,13 @@ Contract (driver): python bench.py --gpus N --steps K --warmup W  (torchrun for 
 
 A "step" is one explicitSolver::solve() (local dt + 3 RK stages, each = wall-ghost copy, limiter, face flux,
 gather + update; the gradients of the iteration-start state are computed once) over the whole mesh.
-Workload at N=1: BASELINE.json configs[1], the synthetic 1M-cell mixed tri/quad NACA0012 O-mesh, "RANS-SA"
-(which in the reference is the Roe flux + no-slip wall + always-on gradients), second order,
-Green-Gauss, limiter_k 5, relaxation 0.9, CFL 1.5, perturbed free stream (default_rng(12345), 1e-3).
+Workload: BASELINE.json configs[2], the synthetic 16M-cell mixed tri/quad NACA0012 O-mesh (the mesh the metric and the
+">= 60 % of the HBM roofline" target are quoted on), "RANS-SA" (which in the reference is the Roe flux + no-slip wall +
+always-on gradients), second order, Green-Gauss, limiter_k 5, relaxation 0.9, CFL 1.5, perturbed free
+stream (default_rng(12345), 1e-3).  --gpus N cuts the SAME 16M mesh into N pieces (strong scaling, configs[2]);
+--scaling weak runs 8M cells per GPU (configs[3]: 64M cells on 8 GPUs); --workload synthetic-1M-mixed-omesh is configs[1].
+Every N > 1 run carries a parity probe: rank 0 also runs the first 10 iterations of the same mesh un-partitioned and the
+residual-norm histories must agree to 1e-10 relative ("parity" in the JSON line).
 
  value      cell-updates/s, state resident in HBM, CUDA events on the solver's stream around the K steps
  e2e        the same metric through the C ABI with HOST state every step: afx_rans_set_q (pinned H2D) ->
@@ -37,10 +41,13 @@ WORKLOADS = {  # name: (ni, nj, n_quad_layers) -> SURVEY.md 8d
     "synthetic-4M-mixed-omesh": (2048, 1280, 512),
     "synthetic-8M-mixed-omesh": (4096, 1280, 512),
     "synthetic-16M-mixed-omesh": (4096, 2560, 1024),
+    "synthetic-32M-mixed-omesh": (8192, 2560, 1024),
     "synthetic-64M-mixed-omesh": (8192, 5120, 2048),
 }
-# weak scaling: 2^20 cells per GPU, the whole mesh cut into N pieces along a Hilbert curve, 2-layer halo over NCCL
-WEAK = {1: "synthetic-1M-mixed-omesh", 2: "synthetic-2M-mixed-omesh", 4: "synthetic-4M-mixed-omesh", 8: "synthetic-8M-mixed-omesh"}
+HEADLINE = "synthetic-16M-mixed-omesh"  # BASELINE.json configs[2]: 1/2/4/8 GPUs on this one mesh (strong scaling)
+# --scaling weak, BASELINE.json configs[3]: 8M cells per GPU (64M cells on 8 GPUs)
+WEAK = {1: "synthetic-8M-mixed-omesh", 2: "synthetic-16M-mixed-omesh", 4: "synthetic-32M-mixed-omesh", 8: "synthetic-64M-mixed-omesh"}
+PARITY_ITERS, PARITY_RTOL = 10, 1e-10
 BCS = {"farfield": ("farfield", dict(mach=0.2, angle=1.0 * 0.01745, T=1.0, p=1.0)), "wall": ("wall", None)}
 VISC, GRAD, SECOND, LIMK, CFL, RELAX = "spallart-allmaras", "green-gauss", True, 5.0, 1.5, 0.9
 CPU_SAMPLE = "synthetic-64k-mixed-omesh"
@@ -86,12 +93,12 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
-def reference_cpu(steps, warmup):
+def reference_cpu(steps, warmup, sample=CPU_SAMPLE):
     """The reference's own explicitSolver on the host cores (oracle/_ref), bounded sample of the workload."""
     import aeroflex_b200 as afx
     from oracle import ref
     import tempfile
-    ni, nj, nq = WORKLOADS[CPU_SAMPLE]
+    ni, nj, nq = WORKLOADS[sample]
     m = afx.Mesh.synth_omesh(ni, nj, nq, 150.0)
     with tempfile.TemporaryDirectory() as td:
         path = os.path.join(td, "sample.msh")
@@ -108,9 +115,10 @@ def reference_cpu(steps, warmup):
     dt = time.perf_counter() - t0
     threads = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
     return {"value": rm.N * steps / dt, "unit": "cell-updates/s", "cores": threads, "kind": "reference",
-            "sample": "%s (N=%d, E=%d): %d explicit iterations of the unmodified reference headers (Eigen-API stand-in, -O3 -fopenmp, "
-                      "OMP_NUM_THREADS=%d; the reference's face loops are serial, so 1 core does the hot loops), %.1f s"
-                      % (CPU_SAMPLE, rm.N, rm.E, steps, threads, dt)}, dt / steps * 1e3
+            "sample": "%s (N=%d, E=%d): %d explicit iterations (after %d warm-up) of the unmodified reference headers (Eigen-API stand-in, "
+                      "-O3 -fopenmp, OMP_NUM_THREADS=%d; the reference's face loops are serial, so 1 core does the hot loops), %.1f s; "
+                      "cell-updates/s is size-normalised: the serial reference does not get faster per cell on a larger mesh"
+                      % (sample, rm.N, rm.E, steps, warmup, threads, dt)}, dt / steps * 1e3
 
 
 def port_cpu(steps):
@@ -135,38 +143,53 @@ def port_cpu(steps):
             "sample": "%s: %d iterations of oracle/rans_oracle.c orc_explicit_solve_omp, %d threads, %.1f s" % (CPU_SAMPLE, steps, threads, dt)}
 
 
+def shared_config(workload, world, weak):
+    """The part of `config` BOTH arms print, so that the two lines describe one configuration by construction."""
+    ni, nj, nq = WORKLOADS[workload]
+    return {"workload": workload, "cells": ni * (nq + 2 * (nj - nq)), "mesh": "NACA0012 O-mesh %d x %d, inner %d layers quads, outer layers split into triangles" % (ni, nj, nq),
+            "scheme": "explicit 3-stage RK, 2nd order MUSCL, Green-Gauss, Venkatakrishnan k=5",
+            "viscosity": "spallart-allmaras (reference semantics: Roe flux + no-slip wall + gradients, SURVEY F1/F2)",
+            "cfl": CFL, "relaxation": RELAX, "gpus": world, "scaling": "weak (8M cells per GPU)" if weak else "strong (one mesh cut into N pieces)",
+            "cpu_arms": "the CPU reference (--impl reference, cpu_baseline) is timed on a bounded sample of the same mesh family (%s) -- its mesh "
+                        "reader and serial face loops need minutes per iteration at this size; cell-updates/s is size-normalised" % CPU_SAMPLE,
+            "l2": "working set far larger than the 126 MB L2 (inputs larger than L2, no flush needed)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default=None)
+    ap.add_argument("--workload", default=None, help="default: %s (BASELINE.json configs[2]); any key of WORKLOADS" % HEADLINE)
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"], help="strong: the workload cut into N pieces; weak: 8M cells per GPU (configs[3])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--no-parity-probe", action="store_true", help="N > 1: skip the un-partitioned 10-iteration run on rank 0")
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--math", default="fast", choices=["fast", "strict"])
-    ap.add_argument("--fuse-lim0", type=int, default=1, help="1 (default): k_dt_grad also writes the first stage's limiters (9 kernels per iteration); 0: separate k_limiter launch (10)")
+    ap.add_argument("--fuse-lim0", type=int, default=1, help="1 (default): k_dt_grad also writes the first stage's limiters; 0: separate k_limiter launch")
     ap.add_argument("--fused", type=int, default=0, help="1: one fused kernel per RK stage on shared-memory tiles; 0 (default): limiter / flux / gather kernels")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     W = max(a.warmup, 3) if a.impl == "b200" else a.warmup
-    workload = a.workload or WEAK.get(world, "synthetic-1M-mixed-omesh")
-    scaling = "weak" if a.workload is None else "strong (fixed mesh: %s)" % workload  # an explicit workload is cut into N pieces
-    config = {"workload": workload, "scheme": "explicit 3-stage RK, 2nd order MUSCL, Green-Gauss, Venkatakrishnan k=5",
-              "viscosity": "spallart-allmaras (reference semantics: Roe flux + no-slip wall + gradients, SURVEY F1/F2)",
-              "cfl": CFL, "relaxation": RELAX,
-              "l2": "working set > 126 MB L2 (inputs larger than L2, no flush); the solver pins its gradient arrays in L2 when they fit (1M cells: 64 MB)"}
+    weak = a.scaling == "weak" and a.workload is None
+    workload = a.workload or (WEAK.get(world) if weak else HEADLINE)
+    if workload not in WORKLOADS:
+        raise SystemExit("bench.py: unknown workload %r" % workload)
+    scaling = "weak" if weak else "strong"
+    config = shared_config(workload, world, weak)
 
     if a.impl == "reference":
         if rank != 0:
             return
-        steps = max(1, min(a.steps, 40))  # bounded: ~0.7 s per iteration on the 64k sample
-        cpu, ms = reference_cpu(steps, min(a.warmup, 2))
-        config["workload"] = workload + " (CPU arm timed on the bounded sample named in cpu_baseline.sample)"
+        # K steps after W warm-up steps exactly as asked; every step is one explicit iteration of the unmodified reference on
+        # the bounded sample (~0.2 s per iteration on 64k cells)
+        steps = max(1, a.steps)
+        cpu, ms = reference_cpu(steps, a.warmup)
         print(json.dumps({"impl": "reference", "metric": "RANS cell-updates/s", "value": cpu["value"], "unit": "cell-updates/s",
-                          "n_gpus": a.gpus, "steps": steps, "warmup": min(a.warmup, 2), "ms_per_step": ms, "higher_is_better": True,
-                          "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                          "n_gpus": a.gpus, "steps": steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True,
+                          "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                           "cpu_baseline": cpu, "e2e": {"value": cpu["value"], "unit": "cell-updates/s", "h2d_bytes_per_step": 0,
                                                        "d2h_bytes_per_step": 0}}))
         return
@@ -185,6 +208,7 @@ def main():
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    t_setup = time.perf_counter()
     ni, nj, nq = WORKLOADS[workload]
     mesh = afx.Mesh.synth_omesh(ni, nj, nq, 150.0)
     N, G, E = mesh.N, mesh.G, mesh.E
@@ -200,27 +224,37 @@ def main():
             s.p2p_connect(blobs)
     else:
         s = afx.GpuSolver(mesh, viscosity=VISC, device=local, math=a.math)
-    config["math"] = a.math + (" (shared reciprocals + FMA; parity 1e-10 tested)" if a.math == "fast" else " (bit-identical to the CPU reference)")
     s.set_bcs(BCS); s.set_options(SECOND, GRAD, LIMK, CFL); s.init(); s.refill_bcs()
     s.set_fused(a.fused)
     tiles = s.tile_info()
-    config["stage_kernel"] = ("fused k_stage: %d tiles of <= %d cells, %d B shared memory, %d CTAs/SM, staging overhead %.2fx"
-                              % (tiles["tiles"], tiles["tile_cells"], tiles["smem_bytes"], tiles["ctas_per_sm"],
-                                 tiles["local_cells"] / max(1, (N if part is None else part.n_own)))) if tiles["fused"] else ("k_dt_grad writes the first stage's limiters; k_limiter (stages 2, 3) + k_flux + k_gather_update" if (a.fuse_lim0 and SECOND) else "k_limiter + k_flux + k_gather_update")
+    details = {"math": a.math + (" (shared reciprocals + FMA; parity 1e-10 tested)" if a.math == "fast" else " (bit-identical to the CPU reference)"),
+               "edges": E, "ghost_cells": G, "setup_s": None}
+    details["stage_kernel"] = ("fused k_stage: %d tiles of <= %d cells, %d B shared memory, %d CTAs/SM, staging overhead %.2fx"
+                               % (tiles["tiles"], tiles["tile_cells"], tiles["smem_bytes"], tiles["ctas_per_sm"],
+                                  tiles["local_cells"] / max(1, (N if part is None else part.n_own)))) if tiles["fused"] else ("k_dt_grad writes the first stage's limiters; k_limiter (stages 2, 3) + k_flux + k_gather_update" if (a.fuse_lim0 and SECOND) else "k_limiter + k_flux + k_gather_update")
     base = np.zeros(4 * (N + G))
     s.get_q(base)  # a partitioned solver fills its own entries of the global vector
-    q0 = perturbed(base, N)
-    s.set_q(q0)
-    config.update({"cells": N, "edges": E, "ghost_cells": G,
-                   "parallelism": "1 GPU" if world == 1 else
-                   "domain decomposition: %d Hilbert-curve partitions, 2-layer halo refreshed every RK stage, halo=%s "
-                   "(this rank: %d owned + %d halo cells, %d peers)" % (world, s.halo_mode(), part.n_own, part.n_r1 + part.n_r2, part.n_peers)})
+    q0 = perturbed(base, N)  # multiplicative, by GLOBAL index: every rank perturbs its own entries exactly as one GPU would
+    del base
+    details["parallelism"] = "1 GPU" if world == 1 else \
+        "domain decomposition: %d %s partitions, 2-layer halo refreshed every RK stage, halo=%s (this rank: %d owned + %d halo cells, %d peers)" \
+        % (world, os.environ.get("AFX_PARTITION", "hilbert"), s.halo_mode(), part.n_own, part.n_r1 + part.n_r2, part.n_peers)
 
     def barrier():
         torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
             torch.cuda.synchronize()
+
+    # parity probe, part 1 (N > 1): the first PARITY_ITERS iterations of the PARTITIONED run from q0
+    parity = None
+    probe = world > 1 and not a.no_parity_probe
+    if probe:
+        s.set_q(q0)
+        probe_norms = s.run(PARITY_ITERS, RELAX)
+        probe_forces = np.array(s.wall_forces("wall"))
+    s.set_q(q0)
+    details["setup_s"] = time.perf_counter() - t_setup
 
     s.run(W, RELAX)
     sampler = ClockSampler(local)
@@ -248,18 +282,21 @@ def main():
     prof = s.profile_explicit(5, RELAX)
     n_loc = N if part is None else part.n_own
     share = n_loc / N  # this rank's share of the cells
-    # algorithmic bytes per launch (DESIGN.md section 5 / SURVEY.md 8d), launches per iteration, phase time per iteration
+    # ALGORITHMIC bytes per launch (they sum to 1488 N + 296 E per iteration however the phases are fused):
+    #   dt 48N+32E, Green-Gauss 120N+48E, limiter 152N+24E, residual loop 184N+48E, stage update 104N.
+    # The face kernel carries the residual loop's reads (144N+48E); the gather/update kernel the residual's qW + area (40N) and
+    # the update (104N).  The flux buffer between them is an implementation temporary: it shows up in `traffic`, not here.
     if tiles["fused"]:
-        # one stage = limiter (152N+24E) + residual loop (184N+48E) + stage update (104N), SURVEY.md 8d
         kernels = {"k_stage": ((440.0 * N + 72.0 * E) * share, 3, prof["stage"]),
                    "k_dt_grad": ((168.0 * N + 80.0 * E) * share, 1, prof["dt_grad"])}
     else:
         lim0 = 1 if (a.fuse_lim0 and SECOND) else 0  # the first stage's limiter phase runs inside k_dt_grad
         kernels = {"k_flux": ((144.0 * N + 48.0 * E) * share, 3, prof["flux"]),
                    "k_limiter": ((152.0 * N + 24.0 * E) * share, 3 - lim0, prof["limiter"]),
-                   "k_gather_update": ((144.0 * N + 32.0 * E) * share, 3, prof["gather_update"]),
+                   "k_gather_update": (144.0 * N * share, 3, prof["gather_update"]),
                    "k_dt_grad": ((168.0 * N + 80.0 * E + lim0 * (152.0 * N + 24.0 * E)) * share, 1, prof["dt_grad"])}
     alg_iter = (1488.0 * N + 296.0 * E) * share
+    assert abs(sum(b * n for b, n, _ in kernels.values()) - alg_iter) < 1e-6 * alg_iter
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -284,7 +321,8 @@ def main():
             "algorithmic_bytes_per_launch": per_kernel[dom]["algorithmic_bytes_per_launch"], "kernel_ms": per_kernel[dom]["kernel_ms"],
             "kernels": per_kernel, "phase_ms_per_iteration": prof,
             "iteration": {"algorithmic_bytes": alg_iter, "achieved": alg_iter / (t_ms / a.steps * 1e-3) / 1e9,
-                          "frac": alg_iter / (t_ms / a.steps * 1e-3) / 1e9 / peak}}
+                          "frac": alg_iter / (t_ms / a.steps * 1e-3) / 1e9 / peak,
+                          "frac_of_nominal_8TBs": alg_iter / (t_ms / a.steps * 1e-3) / 1e9 / 8000.0}}
 
     # end to end through the C ABI with host-resident state, pinned buffers
     # (a partitioned rank moves ITS piece: owned + halo + ghost rows, in its own numbering)
@@ -309,15 +347,36 @@ def main():
            "d2h_bytes_per_step": 8 * nq4 * world + 8, "steps": a.e2e_steps, "ms_per_step": e2e_s / a.e2e_steps * 1e3,
            "path": "afx_rans_set_q[_local](pinned host) -> afx_rans_step_explicit -> afx_rans_get_q[_local](pinned host) + norm"}
 
+    # parity probe, part 2: rank 0 runs the same iterations on the un-partitioned mesh (its GPU holds both solvers)
+    if probe:
+        del hq
+        if rank == 0:
+            t1 = time.perf_counter()
+            one = afx.GpuSolver(mesh, viscosity=VISC, device=local, math=a.math)
+            one.set_bcs(BCS); one.set_options(SECOND, GRAD, LIMK, CFL); one.init(); one.refill_bcs()
+            one.set_q(perturbed(one.get_q(), N))  # init() is bit-identical on every piece (tested): the same q0, now whole
+            ref_norms = one.run(PARITY_ITERS, RELAX)
+            ref_forces = np.array(one.wall_forces("wall"))
+            del one
+            rel = float(np.max(np.abs(probe_norms - ref_norms) / np.abs(ref_norms)))
+            frel = float(np.max(np.abs(probe_forces - ref_forces) / np.maximum(np.abs(ref_forces), 1e-300)))
+            parity = {"what": "first %d residual norms of the %d-GPU run vs the same mesh un-partitioned on rank 0's GPU (same math mode), "
+                              "and CL/CD/CM after those iterations" % (PARITY_ITERS, world),
+                      "norm_rtol": PARITY_RTOL, "norm_max_rel_diff": rel, "forces_max_rel_diff": frel,
+                      "ok": bool(rel <= PARITY_RTOL and frel <= 1e-8), "probe_s": time.perf_counter() - t1}
+        barrier()
+
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        cpu, _ = reference_cpu(20, 1)
+        cpu, _ = reference_cpu(20, 2)
         cpu_port = port_cpu(60)
     if rank == 0:
         out = {"metric": "RANS cell-updates/s", "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": a.steps, "warmup": W,
                "ms_per_step": t_ms / a.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
-               "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
-               "wall_ms_per_step": wall_ms / a.steps, "final_residual_norm": float(norms[-1])}
+               "data": "synthetic", "config": config, "details": details, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+               "roofline": roof, "wall_ms_per_step": wall_ms / a.steps, "final_residual_norm": float(norms[-1])}
+        if parity is not None:
+            out["parity"] = parity
         if cpu is not None:
             out["cpu_baseline"] = cpu
             out["cpu_port"] = cpu_port
