@@ -34,7 +34,7 @@ EXPORTED_SYMBOLS = [
     "afx_rans_p2p_export", "afx_rans_p2p_connect", "afx_rans_halo_mode",
     "afx_group_create", "afx_group_free", "afx_group_abort", "afx_rans_create_partitioned_group",
     "afx_rans_create", "afx_rans_destroy", "afx_rans_set_bcs", "afx_rans_set_options", "afx_rans_set_cfl",
-    "afx_rans_set_math_mode", "afx_rans_get_math_mode", "afx_rans_set_fused", "afx_rans_tile_info", "afx_tiling_plan", "afx_tiling_plan_partition",
+    "afx_rans_set_math_mode", "afx_rans_get_math_mode", "afx_rans_set_fused", "afx_rans_tile_info", "afx_rans_set_pipelined", "afx_rans_pipe_info", "afx_tiling_plan", "afx_tiling_plan_partition",
     "afx_rans_init", "afx_rans_refill_bcs", "afx_rans_bcs_from_internal", "afx_rans_set_q", "afx_rans_get_q",
     "afx_rans_set_q_local", "afx_rans_get_q_local", "afx_rans_get_field", "afx_rans_boundary_variables", "afx_rans_uniform_residual", "afx_rans_step_explicit",
     "afx_rans_run_explicit", "afx_rans_phase_dt_gradients", "afx_rans_phase_limiters", "afx_rans_phase_residual",
@@ -190,6 +190,8 @@ def load_library():
     L.afx_tiling_plan_partition.argtypes = [vp, C.c_uint32, vp, C.POINTER(C.c_uint32), vp, C.c_uint32, C.POINTER(C.c_uint64)]
     L.afx_rans_set_fused.argtypes = [vp, C.c_int]
     L.afx_rans_tile_info.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.afx_rans_set_pipelined.argtypes = [vp, C.c_int]
+    L.afx_rans_pipe_info.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.afx_rans_get_math_mode.argtypes = [vp]
     for n in ("afx_rans_init", "afx_rans_refill_bcs", "afx_rans_bcs_from_internal", "afx_rans_phase_dt_gradients",
               "afx_rans_phase_limiters", "afx_rans_fill_jacobian"):
@@ -676,6 +678,16 @@ class GpuSolver:
     def set_fused(self, on):
         """One fused kernel per Runge-Kutta stage (default) or limiter / flux / gather+update as three kernels."""
         _check(self.L.afx_rans_set_fused(self.h, 1 if on else 0))
+
+    def set_pipelined(self, on):
+        """One persistent kernel per Runge-Kutta stage sweeping L2-resident chunks, or limiter / flux / gather+update as three kernels."""
+        _check(self.L.afx_rans_set_pipelined(self.h, 1 if on else 0))
+
+    def pipe_info(self):
+        out = (C.c_uint64 * 8)()
+        _check(self.L.afx_rans_pipe_info(self.h, out))
+        return dict(active=bool(out[0]), chunk_cells=int(out[1]), chunks=int(out[2]), items=int(out[3]), far_faces=int(out[4]), far_cells=int(out[5]),
+                    lag_flux=int(out[6] >> 32), lag_update=int(out[6] & 0xFFFFFFFF), ctas=int(out[7]))
 
     def tile_info(self):
         out = (C.c_uint64 * 8)()

@@ -353,24 +353,30 @@ __global__ void __launch_bounds__(AFX_DTG_THREADS, AFX_DTG_MINB) k_dt_grad(DevMe
 // (solver.h:517-593): min/max over the edge neighbours (ghosts included) of the
 // stage state, then the minimum of the limiter function over the cell's faces.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(AFX_LIM_THREADS, AFX_LIM_MINB) k_limiter(DevMesh m, const d4* qk, const d4* gx,
-                                                 const d4* gy, d4* lim, double limiter_k, int walls,
-                                                 uint32_t lo1, uint32_t n1, uint32_t lo2, uint32_t n2)
-{
-    // cells [lo1, lo1+n1) and [lo2, lo2+n2): a partitioned run limits its interior cells while the halo is in flight
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n1 + n2) return;
-    const uint32_t i = t < n1 ? lo1 + t : lo2 + (t - n1);
-    pdl_launch_dependents();
+// static inputs of one cell's limiter (connectivity, geometry): loaded before anything the kernel has to wait for
+struct LimCell {
     uint32_t nbs[4];
     double2 dxy[4];
+    double area;
+};
+__device__ __forceinline__ LimCell limiter_load_static(const DevMesh& m, uint32_t i)
+{
+    LimCell c;
 #pragma unroll
-    for (int s = 0; s < 4; ++s) {  // independent coalesced loads first
-        nbs[s] = m.cnb[(size_t)s * m.N + i];
-        dxy[s] = m.cdxy[(size_t)s * m.N + i];
+    for (int s = 0; s < 4; ++s) {  // independent coalesced loads
+        c.nbs[s] = m.cnb[(size_t)s * m.N + i];
+        c.dxy[s] = m.cdxy[(size_t)s * m.N + i];
     }
-    const double area_i = m.area[i];
-    pdl_wait();  // stage state and gradients come from the previous kernels
+    c.area = m.area[i];
+    return c;
+}
+// the limiter of cell i from the stage state and the gradients (shared by k_limiter and the pipelined stage kernel k_pipe)
+__device__ __forceinline__ void limiter_cell(const DevMesh& m, uint32_t i, const LimCell& c, const d4* qk, const d4* gx, const d4* gy, d4* lim,
+                                             double limiter_k, int walls)
+{
+    const uint32_t (&nbs)[4] = c.nbs;
+    const double2 (&dxy)[4] = c.dxy;
+    const double area_i = c.area;
     const d4 qi = qk[i];
     d4 lo = qi, hi = qi;
     unsigned valid = 0;
@@ -392,6 +398,20 @@ __global__ void __launch_bounds__(AFX_LIM_THREADS, AFX_LIM_MINB) k_limiter(DevMe
     lim[i] = limiter_value(qi, lo, hi, gx[i], gy[i], dxy, valid, limiter_k3a(area_i, limiter_k));
 }
 
+__global__ void __launch_bounds__(AFX_LIM_THREADS, AFX_LIM_MINB) k_limiter(DevMesh m, const d4* qk, const d4* gx,
+                                                 const d4* gy, d4* lim, double limiter_k, int walls,
+                                                 uint32_t lo1, uint32_t n1, uint32_t lo2, uint32_t n2)
+{
+    // cells [lo1, lo1+n1) and [lo2, lo2+n2): a partitioned run limits its interior cells while the halo is in flight
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n1 + n2) return;
+    const uint32_t i = t < n1 ? lo1 + t : lo2 + (t - n1);
+    pdl_launch_dependents();
+    const LimCell c = limiter_load_static(m, i);
+    pdl_wait();  // stage state and gradients come from the previous kernels
+    limiter_cell(m, i, c, qk, gx, gy, lim, limiter_k, walls);
+}
+
 // ---------------------------------------------------------------------------
 // Face loop, one thread per face: MUSCL reconstruction + flux, written once.
 // explicitSolver::calc_residual (solver.h:751-786) / fillRhoRHS (1097-1134) /
@@ -399,29 +419,50 @@ __global__ void __launch_bounds__(AFX_LIM_THREADS, AFX_LIM_MINB) k_limiter(DevMe
 // average_gradients (solver.h:359-398) feeds the laminar term with the
 // iteration-start q.
 // ---------------------------------------------------------------------------
-template <int SECOND, int VISC, int UNIFORM>
-__global__ void __launch_bounds__(AFX_FLUX_THREADS, AFX_FLUX_MINB) k_flux(DevMesh m, const d4* qk, const d4* q0,
-                                              const d4* gx, const d4* gy,
-                                              const d4* lim, d4* flux, GasC g, d4 qfar)
+// 256-bit loads that are cached in L2 only: for data written by OTHER CTAs of the running kernel (k_pipe), which a line
+// this SM's L1 has kept from an earlier read would hide
+__device__ __forceinline__ d4 ld_cg4(const d4* p)
 {
-    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= m.e_flux) return;
-    pdl_launch_dependents();
-    // one 64-byte record per face: normal, length, both centre offsets, the two cells and the kind
+    d4 v;
+    asm volatile("ld.global.cg.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+    return v;
+}
+template <int CG>
+__device__ __forceinline__ d4 ld4(const d4* p) { if (CG) return ld_cg4(p); return *p; }
+
+// one 64-byte record per face: normal, length, both centre offsets, the two cells and the kind
+struct FaceRec {
+    d4 gA, gB;
+    uint2 fc;
+    int kind;
+};
+__device__ __forceinline__ FaceRec face_load_static(const DevMesh& m, uint32_t f)
+{
     const d4 r0 = m.frec[2 * (size_t)f], r1 = m.frec[2 * (size_t)f + 1];
     const unsigned long long cw = (unsigned long long)__double_as_longlong(r1.w);
-    const uint2 fc = make_uint2((uint32_t)cw & CF_ID, (uint32_t)(cw >> 32));
-    const int kind = (int)(((uint32_t)cw) >> 30);
-    const d4 gA = mk4(r0.x, r0.y, r0.z, 0.);
-    const d4 gB = mk4(r0.w, r1.x, r1.y, r1.z);
-    pdl_wait();  // states, gradients, limiters come from the previous kernels
+    FaceRec r;
+    r.fc = make_uint2((uint32_t)cw & CF_ID, (uint32_t)(cw >> 32));
+    r.kind = (int)(((uint32_t)cw) >> 30);
+    r.gA = mk4(r0.x, r0.y, r0.z, 0.);
+    r.gB = mk4(r0.w, r1.x, r1.y, r1.z);
+    return r;
+}
+// MUSCL reconstruction + flux of face f, written once (shared by k_flux and k_pipe; CG: the limiters were written by
+// other CTAs of the running kernel)
+template <int SECOND, int VISC, int UNIFORM, int CG>
+__device__ __forceinline__ void flux_face(const DevMesh& m, uint32_t f, const FaceRec& rec, const d4* qk, const d4* q0, const d4* gx, const d4* gy,
+                                          const d4* lim, d4* flux, const GasC& g, const d4& qfar)
+{
+    const uint2 fc = rec.fc;
+    const int kind = rec.kind;
+    const d4 gA = rec.gA, gB = rec.gB;
     d4 qL, qR;
     if (UNIFORM) { qL = qfar; qR = qfar; }
     else { qL = qk[fc.x]; qR = qk[fc.y]; }
     d4 gL0, gL1, gR0, gR1;
     if ((SECOND && !UNIFORM) || VISC == 1) { gL0 = gx[fc.x]; gL1 = gy[fc.x]; gR0 = gx[fc.y]; gR1 = gy[fc.y]; }
     if (SECOND && !UNIFORM) {  // solver.h:774-781
-        const d4 lL = lim[fc.x], lR = lim[fc.y];
+        const d4 lL = ld4<CG>(lim + fc.x), lR = ld4<CG>(lim + fc.y);
         qL.x = qL.x + (gL0.x * gB.x + gL1.x * gB.y) * lL.x;
         qL.y = qL.y + (gL0.y * gB.x + gL1.y * gB.y) * lL.y;
         qL.z = qL.z + (gL0.z * gB.x + gL1.z * gB.y) * lL.z;
@@ -451,12 +492,25 @@ __global__ void __launch_bounds__(AFX_FLUX_THREADS, AFX_FLUX_MINB) k_flux(DevMes
     flux[f] = fl;
 }
 
+template <int SECOND, int VISC, int UNIFORM>
+__global__ void __launch_bounds__(AFX_FLUX_THREADS, AFX_FLUX_MINB) k_flux(DevMesh m, const d4* qk, const d4* q0,
+                                              const d4* gx, const d4* gy,
+                                              const d4* lim, d4* flux, GasC g, d4 qfar)
+{
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= m.e_flux) return;
+    pdl_launch_dependents();
+    const FaceRec rec = face_load_static(m, f);
+    pdl_wait();  // states, gradients, limiters come from the previous kernels
+    flux_face<SECOND, VISC, UNIFORM, 0>(m, f, rec, qk, q0, gx, gy, lim, flux, g, qfar);
+}
+
 // ---------------------------------------------------------------------------
 // Block-level deterministic sum of one double per thread -> partial[blockIdx];
 // the last block to finish adds the partials in index order and stores the
 // square root (residual L2 norm, solver.h:827 / 1178).
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void block_norm_accumulate(double v, const NormOut& no)
+__device__ __forceinline__ void block_norm_accumulate(double v, const NormOut& no, unsigned int slot)
 {
     double* partial = no.partial; unsigned int* counter = no.counter; double* norms = no.norms; unsigned int* norm_idx = no.norm_idx;
     __shared__ double sh[32];
@@ -471,7 +525,7 @@ __device__ __forceinline__ void block_norm_accumulate(double v, const NormOut& n
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
         if (lane == 0) {
-            partial[no.blk_off + blockIdx.x] = t;
+            partial[no.blk_off + slot] = t;
             __threadfence();
             last = (atomicAdd(counter, 1u) == no.blk_total - 1);
         }
@@ -505,6 +559,68 @@ __device__ __forceinline__ void block_norm_accumulate(double v, const NormOut& n
 // faces count in the norm.  LAST adds the squared entries to the residual norm
 // and stores the vector (qW or rhs).
 // ---------------------------------------------------------------------------
+// gather + update of cell i; returns the cell's share of the squared residual norm (LAST).  Shared by k_gather_update and the
+// pipelined stage kernel k_pipe (CG: the fluxes were written by other CTAs of the running kernel).
+template <int MODE, int LAST, int CG>
+__device__ __forceinline__ double gather_cell(const DevMesh& m, uint32_t i, const uint32_t (&bnd)[4], const d4* flux, const d4* q, const d4* qk_in,
+                                              d4* qk_out, const double* dt, d4* qW, double alpha, const double* __restrict__ prm, int walls,
+                                              const PushArgs& push)
+{
+    double nrm = 0;
+    d4 r = mk4(0, 0, 0, 0);
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const uint32_t cfv = bnd[s];
+        if (cfv == CF_NONE) continue;
+        const d4 fl = ld4<CG>(flux + (cfv & CF_ID));
+        if (cfv & CF_SIDE) { r.x += fl.x; r.y += fl.y; r.z += fl.z; r.w += fl.w; }
+        else { r.x -= fl.x; r.y -= fl.y; r.z -= fl.z; r.w -= fl.w; }
+        if (LAST && MODE != 1 && (cfv & CF_BND) && m.fkind[cfv & CF_ID] == K_INTERNAL)  // two-sided boundary face: the ghost row of qW holds +flux
+            nrm += fl.x * fl.x + fl.y * fl.y + fl.z * fl.z + fl.w * fl.w;
+    }
+    if (MODE == 0) {
+        const double A = m.area[i];
+#if AFX_FAST
+        const double rA = fast_rcp(A);
+        r.x *= rA; r.y *= rA; r.z *= rA; r.w *= rA;
+#else
+        r.x /= A; r.y /= A; r.z /= A; r.w /= A;
+#endif
+        const d4 q0 = q[i];
+        const double dti = dt[i];
+        d4 o;
+        const double relax = prm[1];
+        o.x = q0.x + r.x * dti * alpha * relax;
+        o.y = q0.y + r.y * dti * alpha * relax;
+        o.z = q0.z + r.z * dti * alpha * relax;
+        o.w = q0.w + r.w * dti * alpha * relax;
+        qk_out[i] = o;
+        if (push.enabled && i < push.n_front) {  // halo push: straight into the peers' receive buffers over NVLink
+            const unsigned long long par = (*push.epoch) & 1ull;
+            for (uint32_t k = push.dst_ptr[i]; k < push.dst_ptr[i + 1]; ++k) {
+                const uint32_t d = push.dst[k], p = d >> 28, slot = d & 0x0FFFFFFFu;
+                push.peer_buf[p][par * push.peer_stride[p] + slot] = o;
+            }
+            // no fence per thread: the flags are raised after a system-scope fence that follows all of these stores --
+            // in k_halo_signal (a later kernel of this stream) or, with the early hand-off, once per front CTA below
+        }
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const uint32_t cfv = bnd[s];
+            if (!walls || cfv == CF_NONE || !(cfv & CF_BND)) continue;
+            const int kind = m.fkind[cfv & CF_ID];
+            // wall ghosts of the next stage follow their owner; after the last stage the ghost keeps the state its
+            // owner had when the stage started (solver.h:811 ran before the update)
+            if (kind == K_SLIPWALL || kind == K_WALL) qk_out[m.fcells[cfv & CF_ID].y] = LAST ? qk_in[i] : o;
+        }
+    }
+    if (LAST) {
+        if (MODE != 0 || prm[2] != 0.0) qW[i] = r;  // prm[2]: keep qW (only the last iteration of a run needs it)
+        nrm += r.x * r.x + r.y * r.y + r.z * r.z + r.w * r.w;
+    }
+    return nrm;
+}
+
 template <int MODE, int LAST>
 __global__ void __launch_bounds__(AFX_GATHER_THREADS) k_gather_update(DevMesh m, const d4* flux,
                                                        const d4* q, const d4* qk_in,
@@ -521,59 +637,7 @@ __global__ void __launch_bounds__(AFX_GATHER_THREADS) k_gather_update(DevMesh m,
         for (int s = 0; s < 4; ++s) bnd[s] = m.cf[(size_t)s * m.N + i];
     }
     pdl_wait();  // the fluxes come from the previous kernel
-    if (i < hi) {
-        d4 r = mk4(0, 0, 0, 0);
-#pragma unroll
-        for (int s = 0; s < 4; ++s) {
-            const uint32_t cfv = bnd[s];
-            if (cfv == CF_NONE) continue;
-            const d4 fl = flux[cfv & CF_ID];
-            if (cfv & CF_SIDE) { r.x += fl.x; r.y += fl.y; r.z += fl.z; r.w += fl.w; }
-            else { r.x -= fl.x; r.y -= fl.y; r.z -= fl.z; r.w -= fl.w; }
-            if (LAST && MODE != 1 && (cfv & CF_BND) && m.fkind[cfv & CF_ID] == K_INTERNAL)  // two-sided boundary face: the ghost row of qW holds +flux
-                nrm += fl.x * fl.x + fl.y * fl.y + fl.z * fl.z + fl.w * fl.w;
-        }
-        if (MODE == 0) {
-            const double A = m.area[i];
-#if AFX_FAST
-            const double rA = fast_rcp(A);
-            r.x *= rA; r.y *= rA; r.z *= rA; r.w *= rA;
-#else
-            r.x /= A; r.y /= A; r.z /= A; r.w /= A;
-#endif
-            const d4 q0 = q[i];
-            const double dti = dt[i];
-            d4 o;
-            const double relax = prm[1];
-            o.x = q0.x + r.x * dti * alpha * relax;
-            o.y = q0.y + r.y * dti * alpha * relax;
-            o.z = q0.z + r.z * dti * alpha * relax;
-            o.w = q0.w + r.w * dti * alpha * relax;
-            qk_out[i] = o;
-            if (push.enabled && i < push.n_front) {  // halo push: straight into the peers' receive buffers over NVLink
-                const unsigned long long par = (*push.epoch) & 1ull;
-                for (uint32_t k = push.dst_ptr[i]; k < push.dst_ptr[i + 1]; ++k) {
-                    const uint32_t d = push.dst[k], p = d >> 28, slot = d & 0x0FFFFFFFu;
-                    push.peer_buf[p][par * push.peer_stride[p] + slot] = o;
-                }
-                // no fence per thread: the flags are raised after a system-scope fence that follows all of these stores --
-                // in k_halo_signal (a later kernel of this stream) or, with the early hand-off, once per front CTA below
-            }
-#pragma unroll
-            for (int s = 0; s < 4; ++s) {
-                const uint32_t cfv = bnd[s];
-                if (!walls || cfv == CF_NONE || !(cfv & CF_BND)) continue;
-                const int kind = m.fkind[cfv & CF_ID];
-                // wall ghosts of the next stage follow their owner; after the last stage the ghost keeps the state its
-                // owner had when the stage started (solver.h:811 ran before the update)
-                if (kind == K_SLIPWALL || kind == K_WALL) qk_out[m.fcells[cfv & CF_ID].y] = LAST ? qk_in[i] : o;
-            }
-        }
-        if (LAST) {
-            if (MODE != 0 || prm[2] != 0.0) qW[i] = r;  // prm[2]: keep qW (only the last iteration of a run needs it)
-            nrm += r.x * r.x + r.y * r.y + r.z * r.z + r.w * r.w;
-        }
-    }
+    if (i < hi) nrm = gather_cell<MODE, LAST, 0>(m, i, bnd, flux, q, qk_in, qk_out, dt, qW, alpha, prm, walls, push);
     if (MODE == 0 && push.early_signal && blockIdx.x < push.n_front_blocks) {  // uniform per CTA
         // every store of this CTA into the peers' buffers has been issued: one system-scope fence per CTA (cumulative over
         // the stores the barrier has ordered before it), not one per thread
@@ -590,7 +654,7 @@ __global__ void __launch_bounds__(AFX_GATHER_THREADS) k_gather_update(DevMesh m,
             }
         }
     }
-    if (LAST) block_norm_accumulate(nrm, no);
+    if (LAST) block_norm_accumulate(nrm, no, blockIdx.x);
 }
 
 // ---------------------------------------------------------------------------

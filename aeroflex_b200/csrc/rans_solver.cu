@@ -229,6 +229,15 @@ struct Solver {
                            const std::vector<double>& h_area, const std::vector<d4>& h_gA);
     bool fused_stage() const { return tiles_ready && use_fused && second_order && viscous_type == 0 && !(halo && halo_overlap); }
     void launch_stage(int s, const d4* qk_in, d4* qk_out, double alpha);
+    // pipelined stage kernel on L2-resident chunks (rans_pipe.cuh); [0] without, [1] with the limiter phase
+    DBuf<uint4> p_steps[2]; DBuf<uint32_t> p_face_start, p_uslot, p_far_faces, p_far_cells, p_far_mask; DBuf<unsigned int> p_ctr;
+    PipeTab pipe_tab[2] = {};
+    bool pipe_ready = false, use_pipe = false;
+    unsigned pipe_grid = 0;
+    void build_pipe_tables();
+    bool pipe_stage() const { return pipe_ready && use_pipe && viscous_type == 0 && !(halo && halo_overlap) && !fused_stage(); }
+    void launch_pipe(int s, const d4* qk_in, d4* qk_out, double alpha, bool has_l);
+    int* pipe_err_word() { return reinterpret_cast<int*>(h_pinned + 49); }
     DBuf<uint32_t> bface, bghost, bowner; DBuf<int32_t> bpatch; DBuf<d4> bstate; DBuf<double> bcx, bcy;
     DBuf<uint32_t> perm_c_new2old, perm_c_old2new;
     // device state
@@ -312,7 +321,7 @@ struct Solver {
     void launch_dt_grad(bool want_grad, bool walls, bool with_lim = false);
     bool fuse_lim0 = true;  // AFX_FUSE_LIM0=0: keep the first stage's limiter in its own k_limiter launch
     // the first stage limits the iteration-start state: k_dt_grad can do it from the neighbour states it has just read
-    bool lim0_in_dt_grad() const { return fuse_lim0 && second_order && !fused_stage(); }
+    bool lim0_in_dt_grad() const { return fuse_lim0 && second_order && !fused_stage(); }  // also ahead of the pipelined stage
     void launch_limiter(const d4* qk);
     void launch_flux(const d4* qk, bool uniform, d4 qfar);
     template <int MODE, int LAST>
@@ -601,7 +610,9 @@ void Solver::create(const afx_mesh_desc& m, const afx_gas& g, int visc, int dev,
     set_l2_window();
     flux.alloc(E); flux.zero(st);
     dt.alloc(NT); dt.zero(st); dt_ref.alloc(NT);
-    partial.alloc(std::max<size_t>(kt->gather_blocks(NT), stage_grid) + 4); norms.alloc(NORM_RING); norms.zero(st);
+    build_pipe_tables();
+    partial.alloc(std::max<size_t>(std::max<size_t>(kt->gather_blocks(NT), stage_grid), (size_t)pipe_tab[0].nU_near_items + pipe_tab[0].n_farU_items) + 4);
+    norms.alloc(NORM_RING); norms.zero(st);
     prm.alloc(8); prm.zero(st); counters.alloc(4); counters.zero(st); scratch.alloc(16);
     // limiters start at 1 (ghost rows keep that value, solver.h:519)
     kt->fill_cells(lim.p, NT, d4{1, 1, 1, 1}, st);
@@ -885,6 +896,111 @@ void Solver::refresh_tile_k3a()
     k3a_for = limiter_k;
 }
 
+// Work list of the pipelined stage kernel (PipeTab, rans_types.h): chunks of 2^shift cells along the cell order, the sweep's
+// steps, and the far faces / cells that are done after the sweep.  AFX_PIPE=0|1, AFX_PIPE_SHIFT, AFX_PIPE_LAGF, AFX_PIPE_LAGU.
+void Solver::build_pipe_tables()
+{
+    pipe_ready = false;
+    if (const char* e = getenv("AFX_PIPE")) use_pipe = (e[0] == '1');
+    uint32_t shift = 15, lagF = 2, lagU = 2;
+    if (const char* e = getenv("AFX_PIPE_SHIFT")) shift = (uint32_t)std::max(8, std::min(24, atoi(e)));
+    if (const char* e = getenv("AFX_PIPE_LAGF")) lagF = (uint32_t)std::max(1, std::min(16, atoi(e)));
+    if (const char* e = getenv("AFX_PIPE_LAGU")) lagU = (uint32_t)std::max(0, std::min(16, atoi(e)));
+    const uint32_t T = (uint32_t)kt->pipe_threads();
+    const uint32_t csz = 1u << shift;
+    const uint32_t n_chunks = (n_grad + csz - 1) / csz;
+    if (!n_chunks || !n_upd) return;
+    auto items = [&](uint32_t n) { return (n + T - 1) / T; };
+    // faces are sorted by their lower cell: the faces of chunk c are a range
+    std::vector<uint32_t> fs(n_chunks + 1, e_flux);
+    {
+        uint32_t c = 0;
+        fs[0] = 0;
+        for (uint32_t f = 0; f < e_flux; ++f) {
+            const uint32_t lo = std::min(h_fcells[2 * (size_t)f], h_fcells[2 * (size_t)f + 1]);
+            const uint32_t cf_ = lo >> shift;
+            if (cf_ >= n_chunks) throw InvalidArg("face outside the chunks of the pipelined stage");
+            while (c < cf_) fs[++c] = f;
+        }
+        while (c < n_chunks) fs[++c] = e_flux;
+    }
+    std::vector<uint32_t> far_f, far_c, mask((n_upd + 31) / 32 + 1, 0u);
+    for (uint32_t f = 0; f < e_flux; ++f) {
+        const uint32_t a = h_fcells[2 * (size_t)f], b = h_fcells[2 * (size_t)f + 1];
+        if (b >= N) continue;  // boundary face: the ghost's limiter and gradient never change
+        const uint32_t ca = a >> shift, cb = b >> shift;
+        if (ca > cb + 1 || cb > ca + 1) {
+            far_f.push_back(f);
+            if (a < n_upd) mask[a >> 5] |= 1u << (a & 31);
+            if (b < n_upd) mask[b >> 5] |= 1u << (b & 31);
+        }
+    }
+    for (uint32_t i = 0; i < n_upd; ++i) if ((mask[i >> 5] >> (i & 31)) & 1u) far_c.push_back(i);
+    const uint32_t n_far_f = (uint32_t)far_f.size(), n_far_c = (uint32_t)far_c.size();
+    std::vector<uint32_t> uslot(n_chunks, 0);
+    uint32_t nU = 0, nLtot = 0, nFnear = 0;
+    auto cellsL = [&](uint32_t c) { return std::min((c + 1) << shift, n_grad) - (c << shift); };
+    auto cellsU = [&](uint32_t c) { const uint32_t lo = c << shift; return lo >= n_upd ? 0u : std::min((c + 1) << shift, n_upd) - lo; };
+    for (uint32_t c = 0; c < n_chunks; ++c) { uslot[c] = nU; nU += items(cellsU(c)); nLtot += items(cellsL(c)); nFnear += items(fs[c + 1] - fs[c]); }
+    const uint32_t n_steps = n_chunks + lagF + lagU;
+    std::vector<uint4> steps[2];
+    uint32_t n_main[2] = {0, 0};
+    for (int hl = 0; hl < 2; ++hl) {
+        steps[hl].resize(n_steps);
+        uint32_t at = 0;
+        for (uint32_t k = 0; k < n_steps; ++k) {
+            const uint32_t nl = (hl && k < n_chunks) ? items(cellsL(k)) : 0u;
+            const uint32_t nf = (k >= lagF && k - lagF < n_chunks) ? items(fs[k - lagF + 1] - fs[k - lagF]) : 0u;
+            const uint32_t nu = (k >= lagF + lagU && k - lagF - lagU < n_chunks) ? items(cellsU(k - lagF - lagU)) : 0u;
+            steps[hl][k] = make_uint4(at, nl, nf, nu);
+            at += nl + nf + nu;
+        }
+        n_main[hl] = at;
+        p_steps[hl].upload(steps[hl], st);
+    }
+    if (far_f.empty()) far_f.push_back(0);
+    if (far_c.empty()) far_c.push_back(0);
+    p_face_start.upload(fs, st); p_uslot.upload(uslot, st); p_far_faces.upload(far_f, st); p_far_cells.upload(far_c, st); p_far_mask.upload(mask, st);
+    p_ctr.alloc(4 + 2 * (size_t)n_chunks); p_ctr.zero(st);
+    *pipe_err_word() = 0;
+    for (int hl = 0; hl < 2; ++hl) {
+        PipeTab& t = pipe_tab[hl];
+        t = PipeTab{};
+        t.shift = shift; t.n_chunks = n_chunks; t.n_steps = n_steps; t.lagF = lagF; t.lagU = lagU;
+        t.n_main = n_main[hl]; t.n_farF_items = items(n_far_f); t.n_farU_items = items(n_far_c);
+        t.n_items = t.n_main + t.n_farF_items + t.n_farU_items;
+        t.n_far_faces = n_far_f; t.n_far_cells = n_far_c;
+        t.nL_total = hl ? nLtot : 0u; t.nF_total = nFnear + t.n_farF_items; t.nU_near_items = nU;
+        t.steps = p_steps[hl].p; t.face_start = p_face_start.p; t.u_slot0 = p_uslot.p;
+        t.far_faces = p_far_faces.p; t.far_cells = p_far_cells.p; t.far_mask = p_far_mask.p;
+        t.ctr = p_ctr.p; t.err = pipe_err_word();
+    }
+    cudaDeviceProp prop{};
+    CK(cudaGetDeviceProperties(&prop, device));
+    pipe_grid = (unsigned)prop.multiProcessorCount * (unsigned)kt->pipe_ctas_per_sm();
+    pipe_ready = true;
+}
+
+// One pipelined stage: (limiter +) flux + gather + update, chunk by chunk through the L2, then the halo hand-off.
+void Solver::launch_pipe(int s, const d4* qk_in, d4* qk_out, double alpha, bool has_l)
+{
+    ensure_halo();
+    const int walls = (visc_not_inviscid || second_order) ? 1 : 0;
+    const PushArgs* push = (halo && halo->p2p) ? &halo->push : nullptr;
+    const PipeTab& pt = pipe_tab[has_l ? 1 : 0];
+    kt->pipe(second_order, viscous_type, s == 2, has_l ? 1 : 0, dm, pt, std::min<unsigned>(pipe_grid, pt.n_items), qk_in, q.p, qk_out, gx.p, gy.p, lim.p,
+             flux.p, dt.p, qW.p, alpha, prm.p, gas, limiter_k, walls, norm_out(), push, st);
+    ++launches;
+    if (!halo) return;
+    if (halo->p2p) {  // the update items stored the send layer into the peers' buffers: flags, then fill our halo cells
+        kt->halo_signal(halo->sig, st);
+        kt->halo_wait_scatter(halo->wait, qk_out, st);
+        launches += 2;
+    } else {
+        exchange(qk_out, st);
+    }
+}
+
 // One fused stage: limiter + MUSCL + flux + gather + update on shared-memory tiles, then the halo hand-off.
 void Solver::launch_stage(int s, const d4* qk_in, d4* qk_out, double alpha)
 {
@@ -916,6 +1032,7 @@ void Solver::explicit_iteration()
     const double alpha[3] = {0.25, 0.5, 1.};  // solver.h:723
     for (int s = 0; s < 3; ++s) {
         if (fused_stage()) { launch_stage(s, in[s], out[s], alpha[s]); continue; }
+        if (pipe_stage()) { launch_pipe(s, in[s], out[s], alpha[s], second_order && !(s == 0 && lim0)); continue; }
         if (second_order && !(s == 0 && lim0)) launch_limiter(in[s]);
         launch_flux(in[s], false, d4{0, 0, 0, 0});
         if (s < 2) launch_gather<0, 0>(in[s], out[s], qW.p, alpha[s], grads);
@@ -1141,6 +1258,8 @@ void Solver::comm_allreduce(double* dev, int n)
 
 void Solver::check_comm()
 {
+    if (*reinterpret_cast<volatile int*>(pipe_err_word()) != 0)
+        throw CudaError("pipelined stage kernel: a dependency wait ran into its bound (internal error); the state of this solver is no longer valid");
     if (!halo || !halo->p2p) return;
     const int e = *reinterpret_cast<volatile int*>(comm_err_word());
     if (e == 0) return;
@@ -1689,6 +1808,24 @@ int afx_rans_tile_info(afx_rans* s, uint64_t out[8])
     return AFX_OK;
 }
 
+int afx_rans_set_pipelined(afx_rans* s, int on)
+{
+    return guard([&] {
+        if (!s) throw afx::InvalidArg("null argument");
+        if (s->s.use_pipe != (on != 0)) { s->s.use_pipe = (on != 0); s->s.invalidate_graph(); }
+    });
+}
+
+int afx_rans_pipe_info(afx_rans* s, uint64_t out[8])
+{
+    if (!s || !out) { afx::set_error("null argument"); return AFX_ERR_INVALID; }
+    const auto& S = s->s;
+    const afx::PipeTab& t = S.pipe_tab[1];
+    out[0] = S.pipe_stage() ? 1 : 0; out[1] = 1ull << t.shift; out[2] = t.n_chunks; out[3] = t.n_items; out[4] = t.n_far_faces; out[5] = t.n_far_cells;
+    out[6] = ((uint64_t)t.lagF << 32) | t.lagU; out[7] = S.pipe_grid;
+    return AFX_OK;
+}
+
 int afx_rans_get_math_mode(afx_rans* s) { return s->s.kt == &afx::strict::table() ? AFX_MATH_STRICT : AFX_MATH_FAST; }
 
 int afx_rans_set_cfl(afx_rans* s, double cfl)
@@ -2087,7 +2224,7 @@ int afx_rans_profile_explicit(afx_rans* s, double relaxation, int n_iter, double
         S.refresh_tile_k3a();
         for (int k = 0; k < 6; ++k) out_ms[k] = 0;
         const bool grads = S.visc_not_inviscid || S.second_order;
-        const bool fused = S.fused_stage();
+        const bool fused = S.fused_stage() || S.pipe_stage();  // one kernel per stage: its time goes to out_ms[5]
         const afx::d4* in[3] = {S.q.p, S.qkA.p, S.qkB.p};
         afx::d4* outp[3] = {S.qkA.p, S.qkB.p, S.q.p};
         const double alpha[3] = {0.25, 0.5, 1.};
@@ -2103,7 +2240,8 @@ int afx_rans_profile_explicit(afx_rans* s, double relaxation, int n_iter, double
                 if (fused) {
                     CK(cudaEventRecord(ev[e++], S.st));
                     CK(cudaEventRecord(ev[e++], S.st));
-                    S.launch_stage(st, in[st], outp[st], alpha[st]);
+                    if (S.fused_stage()) S.launch_stage(st, in[st], outp[st], alpha[st]);
+                    else S.launch_pipe(st, in[st], outp[st], alpha[st], S.second_order && !(st == 0 && lim0));
                     CK(cudaEventRecord(ev[e++], S.st));
                     CK(cudaEventRecord(ev[e++], S.st));
                     continue;

@@ -85,6 +85,33 @@ __host__ __device__ inline StageSmem stage_smem_layout(uint32_t max_loc, uint32_
     return L;
 }
 
+// Work list of the pipelined stage kernel k_pipe (rans_pipe.cuh).  The cells [0, n_grad) are cut into chunks of 2^shift
+// consecutive cells (compact patches of the mesh along the space-filling curve); ONE persistent kernel per Runge-Kutta stage
+// walks the chunks with three phases a fixed number of steps apart -- limiter of chunk k, face fluxes of chunk k - lagF,
+// gather + update of chunk k - lagF - lagU -- so that what one phase writes (limiters, fluxes) and what two phases read
+// (states, gradients) is still in the 126 MB L2 when the next phase asks for it.  Items (one CTA-load of cells or faces) are
+// handed out in step order from a device counter; an item waits on per-chunk completion counters of the items it reads from,
+// all of which were handed out before it.  Faces joining two chunks more than one apart, and the cells that touch them
+// ("far", a few per cent), are done after the sweep from two index lists.
+struct PipeTab {
+    uint32_t shift, n_chunks, n_steps;
+    uint32_t lagF, lagU;
+    uint32_t n_items, n_main;            // all items; items of the sweep (then: far-face items, then far-cell items)
+    uint32_t n_farF_items, n_farU_items;
+    uint32_t n_far_faces, n_far_cells;
+    uint32_t nL_total, nF_total;         // limiter items; flux items (sweep + far)
+    uint32_t nU_near_items;              // norm slots of the sweep's update items; the far items' slots follow
+    const uint4* steps;                  // [n_steps] {first item, limiter items, flux items, update items}
+    const uint32_t* face_start;          // [n_chunks + 1] first face whose lower cell lies in chunk c (capped at e_flux)
+    const uint32_t* u_slot0;             // [n_chunks] first norm slot of chunk c's update items
+    const uint32_t* far_faces;           // [n_far_faces]
+    const uint32_t* far_cells;           // [n_far_cells]
+    const uint32_t* far_mask;            // bit i: advanced cell i touches a far face
+    unsigned int* ctr;                   // [0] next item, [1] CTAs that left, [2] limiter items done, [3] flux items done,
+                                         // [4 + c] limiter items of chunk c done, [4 + n_chunks + c] flux items of chunk c done
+    int* err;                            // host-visible: a dependency wait ran into its bound (internal error, never expected)
+};
+
 struct NormOut {
     double* partial;        // [gridDim.x]
     unsigned int* counter;  // block counter
@@ -157,6 +184,12 @@ struct KernelTable {
     void (*stage)(int last, const DevMesh& m, const TileTab& tt, unsigned grid, size_t smem, const d4* qk_in, const d4* q0,
                   d4* qk_out, const d4* gx, const d4* gy, const double* dt, d4* qW, d4* lim, double alpha, const double* prm,
                   const GasC& g, NormOut no, const PushArgs* push, cudaStream_t st);
+    // pipelined stage on L2-resident chunks: (limiter +) flux + gather + update in one persistent kernel
+    void (*pipe)(int second, int visc, int last, int has_l, const DevMesh& m, const PipeTab& pt, unsigned grid, const d4* qk_in, const d4* q0,
+                 d4* qk_out, const d4* gx, const d4* gy, d4* lim, d4* flux, const double* dt, d4* qW, double alpha, const double* prm,
+                 const GasC& g, double limiter_k, int walls, NormOut no, const PushArgs* push, cudaStream_t st);
+    int (*pipe_threads)();
+    int (*pipe_ctas_per_sm)();
     int (*stage_prepare)(size_t smem);  // opt in to the dynamic shared memory on the current device; resident CTAs per SM or <0
     int (*stage_threads)();
     void (*tile_k3a)(const double* area_t, double* k3a_t, size_t n, double limiter_k, cudaStream_t st);  // refresh after set_options

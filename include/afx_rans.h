@@ -204,6 +204,13 @@ int afx_rans_set_fused(afx_rans* s, int on);
  * memory per CTA (bytes), out[4] = resident CTAs per SM, out[5] = largest local cell count, out[6] = largest local
  * face count, out[7] = total local cells of all tiles (own + ring 1 + state-only; / n_cells = staging overhead) */
 int afx_rans_tile_info(afx_rans* s, uint64_t out[8]);
+/* Pipelined stage kernel (default for inviscid / "spallart-allmaras" runs; AFX_PIPE=0 or on = 0 selects the three-kernel stage):
+ * ONE persistent kernel per Runge-Kutta stage sweeps the mesh in chunks with limiter, face-flux and gather/update phases a
+ * few chunks apart, so the limiters, the flux buffer and the re-read states and gradients change hands inside the L2 instead
+ * of through HBM.  Same arithmetic, same bits as the three-kernel stage.
+ * info: {active, cells per chunk, chunks, work items per stage, far faces, far cells, lagF << 32 | lagU, CTAs} */
+int afx_rans_set_pipelined(afx_rans* s, int on);
+int afx_rans_pipe_info(afx_rans* s, uint64_t out[8]);
 /* Host-only (no device needed): renumber `mesh` as afx_rans_create would, cut it into tiles of at most `tile_cells`
  * cells and verify the plan against the connectivity.  n_tiles out; per_tile[4*t..] = own cells, ring-1 cells,
  * state-only cells, local faces of tile t (up to `cap` tiles); smem_bytes = dynamic shared memory k_stage would need. */

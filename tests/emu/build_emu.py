@@ -41,6 +41,10 @@ REWRITES = {
         ('asm volatile("griddepcontrol.wait;" ::: "memory");', "", 1),
         ('asm volatile("prefetch.global.L2 [%0];" ::"l"(p));', "(void)p;", 1),
         ('asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));', "t = ::afx_emu::global_timer_ns();", 1),
+        ('asm volatile("ld.global.cg.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));', "v = *p;", 1),
+    ],
+    "rans_pipe.cuh": [
+        ('asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");', "v = __atomic_load_n(p, __ATOMIC_ACQUIRE);", 1),
     ],
     "rans_solver.cu": [  # the library says what it is: the package refuses to load it outside the test run, bench.py and smoke() always
         ('return "aeroflex_rans_b200 0.1 (sm_100a)";', 'return "aeroflex_rans_b200 0.1 (HOST EMULATION of the sm_100a sources -- tests only, not a product path)";', 1),
@@ -58,7 +62,7 @@ REWRITES = {
 STAGE_BEGIN = "// ---- copy-engine and mbarrier primitives (PTX) ----"
 STAGE_END = "struct TileView {"
 
-SOURCES = ["rans_types.h", "rans_physics.cuh", "rans_kernels.cuh", "rans_krylov.cuh", "rans_stage.cuh", "rans_kernels_tu.cu",
+SOURCES = ["rans_types.h", "rans_physics.cuh", "rans_kernels.cuh", "rans_krylov.cuh", "rans_stage.cuh", "rans_pipe.cuh", "rans_kernels_tu.cu",
            "rans_solver.cu", "nccl_dl.h", "ordering.h", "partition.h", "tiling.h", "mesh_host.h"]
 HOST_CPP = ["mesh_host.cpp", "ordering.cpp", "tiling.cpp", "partition.cpp", "mesh_capi.cpp"]
 

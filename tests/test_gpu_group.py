@@ -42,6 +42,12 @@ def _group_run(afx, mesh, world, halo, math, visc, grad, so, n_iter, q0, ndev, f
             solvers[r] = afx.GpuSolver(parts[r], viscosity=visc, math=math, device=r % ndev, group=group)
         return f
     afx.run_ranks([make(r) for r in range(world)])
+    # Peer-memory mode makes one solver's kernel wait for a flag another solver's kernel raises.  On ONE device that needs the two
+    # streams in different hardware queues: safe for a few ranks (CUDA_DEVICE_MAX_CONNECTIONS=32, tests/conftest.py), not for 8
+    # (measured on the B200: the 8-rank case ran into the bounded wait).  More ranks than that share a device only with the staged
+    # halo; with one device per rank (the production layout) every case uses the mode it names.
+    if halo == "p2p" and world > 3 and ndev < world:
+        halo = "staged"
     if halo == "p2p":
         blobs = [s.p2p_export() for s in solvers]
         for s in solvers:
