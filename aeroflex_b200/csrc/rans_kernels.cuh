@@ -506,15 +506,12 @@ __global__ void __launch_bounds__(AFX_FLUX_THREADS, AFX_FLUX_MINB) k_flux(DevMes
 }
 
 // ---------------------------------------------------------------------------
-// Block-level deterministic sum of one double per thread -> partial[blockIdx];
-// the last block to finish adds the partials in index order and stores the
-// square root (residual L2 norm, solver.h:827 / 1178).
+// Block-level deterministic sum of one double per thread -> partial[slot];
+// k_norm_finish adds the partials in slot order.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void block_norm_accumulate(double v, const NormOut& no, unsigned int slot)
+__device__ __forceinline__ void block_norm_partial(double v, const NormOut& no, unsigned int slot)
 {
-    double* partial = no.partial; unsigned int* counter = no.counter; double* norms = no.norms; unsigned int* norm_idx = no.norm_idx;
     __shared__ double sh[32];
-    __shared__ bool last;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
@@ -524,27 +521,32 @@ __device__ __forceinline__ void block_norm_accumulate(double v, const NormOut& n
         double t = lane < nw ? sh[lane] : 0.0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
-        if (lane == 0) {
-            partial[no.blk_off + slot] = t;
-            __threadfence();
-            last = (atomicAdd(counter, 1u) == no.blk_total - 1);
-        }
+        if (lane == 0) no.partial[no.blk_off + slot] = t;
     }
+}
+
+// The partial sums of one phase, added in slot order by one block of its own (fixed shape: strided per thread, then a
+// tree), the square root stored in the residual-history ring (solver.h:827 / 1178).  It used to be the last block of the
+// producing kernel that did this, found with a fence + atomic per block -- which made EVERY block of the last update
+// kernel wait ~1.5 us for its atomic to return before it could retire: k_gather_update<0,1> took 0.63 ms against 0.35 ms
+// for k_gather_update<0,0> at 16M cells (ncu, profiles/r02a_16M_ncu_full_summary.json).  A 2 us launch is cheaper.
+__global__ void __launch_bounds__(1024) k_norm_finish(NormOut no, unsigned int total)
+{
+    __shared__ double sh[32];
+    pdl_launch_dependents();
+    pdl_wait();  // the partial sums come from the previous kernel
+    double t = 0;
+    for (unsigned int b = threadIdx.x; b < total; b += blockDim.x) t += no.partial[b];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+    if (lane == 0) sh[wid] = t;
     __syncthreads();
-    if (last) {  // fixed-order final reduction by one block
-        double t = 0;
-        for (uint32_t b = threadIdx.x; b < no.blk_total; b += blockDim.x) t += __ldcg(&partial[b]);
+    if (wid == 0) {
+        double u = lane < nw ? sh[lane] : 0.0;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
-        __syncthreads();
-        if (lane == 0) sh[wid] = t;
-        __syncthreads();
-        if (wid == 0) {
-            double u = lane < nw ? sh[lane] : 0.0;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) u += __shfl_down_sync(0xffffffffu, u, o);
-            if (lane == 0) { const unsigned int k = *norm_idx; norms[k % NORM_RING] = no.store_square ? u : sqrt(u); *norm_idx = k + 1; *counter = 0; }
-        }
+        for (int o = 16; o > 0; o >>= 1) u += __shfl_down_sync(0xffffffffu, u, o);
+        if (lane == 0) { const unsigned int k = *no.norm_idx; no.norms[k % NORM_RING] = no.store_square ? u : sqrt(u); *no.norm_idx = k + 1; }
     }
 }
 
@@ -654,7 +656,7 @@ __global__ void __launch_bounds__(AFX_GATHER_THREADS) k_gather_update(DevMesh m,
             }
         }
     }
-    if (LAST) block_norm_accumulate(nrm, no, blockIdx.x);
+    if (LAST) block_norm_partial(nrm, no, blockIdx.x);
 }
 
 // ---------------------------------------------------------------------------
@@ -959,6 +961,7 @@ static void flux(int second, int visc, int uniform, const DevMesh& m, const d4* 
 #undef AFX_FLUX
 }
 static unsigned gather_blocks(uint32_t n_cells) { return nblk(n_cells, AFX_GATHER_THREADS); }
+static void norm_finish(NormOut no, unsigned total, cudaStream_t st) { launch_pdl(k_norm_finish, 1u, 1024u, st, no, total); }
 static void gather(int mode, int last, const DevMesh& m, uint32_t lo, uint32_t hi, const d4* fl, const d4* q, const d4* qk_in, d4* qk_out,
                    const double* dt, d4* vec_out, double alpha, const double* prm, int walls, NormOut no, const PushArgs* push_in,
                    cudaStream_t st)

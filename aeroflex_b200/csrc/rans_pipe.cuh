@@ -22,6 +22,11 @@
 #ifndef AFX_PIPE_MINB
 #define AFX_PIPE_MINB (1024 / AFX_PIPE_THREADS)
 #endif
+// elements (cells or faces) per thread and work item: the claim, the dependency wait and the two barriers of an item are
+// paid once per AFX_PIPE_THREADS * AFX_PIPE_EPT elements
+#ifndef AFX_PIPE_EPT
+#define AFX_PIPE_EPT 2
+#endif
 
 namespace afx {
 namespace AFX_NS {
@@ -44,130 +49,94 @@ __device__ __forceinline__ void pipe_wait(const unsigned int* c, unsigned int wa
         if (spins > (1u << 25)) { if (err) *reinterpret_cast<volatile int*>(err) = 1; break; }
     }
 }
-// all writes of this CTA's item are done (the caller has passed a barrier): publish
-__device__ __forceinline__ void pipe_publish(unsigned int* chunk_ctr, unsigned int* total_ctr)
-{
-    __threadfence();
-    if (chunk_ctr) atomicAdd(chunk_ctr, 1u);
-    atomicAdd(total_ctr, 1u);
-}
 
-template <int SECOND, int VISC, int LAST, int HAS_L>
+enum : uint32_t { PH_L = 0, PH_F = 1, PH_U = 2, PH_FARF = 3, PH_FARU = 4 };
+
+template <int SECOND, int LAST, int HAS_L>
 __global__ void __launch_bounds__(AFX_PIPE_THREADS, AFX_PIPE_MINB) k_pipe(DevMesh m, PipeTab pt, const d4* qk_in, const d4* q0, d4* qk_out,
                                                                          const d4* gx, const d4* gy, d4* lim, d4* flux, const double* dt,
                                                                          d4* qW, double alpha, const double* __restrict__ prm, GasC g,
                                                                          double limiter_k, int walls, NormOut no, PushArgs push)
 {
     constexpr uint32_t T = AFX_PIPE_THREADS;
-    enum : uint32_t { PH_L = 0, PH_F = 1, PH_U = 2, PH_FARF = 3, PH_FARU = 4, PH_EXIT = 5 };
-    __shared__ uint32_t s_it[3];  // phase, chunk, item index inside its chunk and phase (or inside the far list)
+    __shared__ unsigned int s_next[2];  // the item this CTA works on next, double buffered (claimed one item ahead)
     __shared__ bool s_last_out;
     pdl_launch_dependents();
     pdl_wait();  // states, gradients, time steps and the zeroed work counters come from earlier kernels
     unsigned int* const Ldone = pt.ctr + 4;
     unsigned int* const Fdone = pt.ctr + 4 + pt.n_chunks;
-    uint32_t cursor = 0;
     unsigned int nxt = 0;
-    if (threadIdx.x == 0) nxt = atomicAdd(&pt.ctr[0], 1u);
-    for (;;) {
-        if (threadIdx.x == 0) {
-            const uint32_t it = nxt;
-            uint32_t ph, chunk = 0, idx = 0;
-            if (it >= pt.n_items) ph = PH_EXIT;
-            else if (it < pt.n_main) {
-                while (cursor + 1 < pt.n_steps && it >= pt.steps[cursor + 1].x) ++cursor;
-                const uint4 sp = pt.steps[cursor];
-                const uint32_t r = it - sp.x;
-                if (r < sp.y) { ph = PH_L; chunk = cursor; idx = r; }
-                else if (r < sp.y + sp.z) { ph = PH_F; chunk = cursor - pt.lagF; idx = r - sp.y; }
-                else { ph = PH_U; chunk = cursor - pt.lagF - pt.lagU; idx = r - sp.y - sp.z; }
-            } else if (it < pt.n_main + pt.n_farF_items) { ph = PH_FARF; idx = it - pt.n_main; }
-            else { ph = PH_FARU; idx = it - pt.n_main - pt.n_farF_items; }
-            s_it[0] = ph; s_it[1] = chunk; s_it[2] = idx;
-            if (ph != PH_EXIT) nxt = atomicAdd(&pt.ctr[0], 1u);  // the next claim travels while this item is worked on
-        }
-        __syncthreads();
-        const uint32_t ph = s_it[0], chunk = s_it[1], idx = s_it[2];
-        if (ph == PH_EXIT) break;
+    if (threadIdx.x == 0) s_next[0] = atomicAdd(&pt.ctr[0], 1u);
+    __syncthreads();
+    for (unsigned int n = 0;; ++n) {
+        const unsigned int it = s_next[n & 1u];
+        if (it >= pt.n_items) break;
+        if (threadIdx.x == 0) nxt = atomicAdd(&pt.ctr[0], 1u);  // the next claim travels while this item is worked on
+        const uint4 rec = pt.items[it];                          // same address for the whole CTA: one broadcast load
+        const uint32_t ph = rec.x & 7u, chunk = rec.x >> 3, first = rec.y, cnt = rec.z;
         if (ph == PH_L) {
             if (HAS_L) {
-                const uint32_t i = (chunk << pt.shift) + idx * T + threadIdx.x;
-                const uint32_t hi = umin32((chunk + 1u) << pt.shift, m.n_grad);
-                if (i < hi) {
+#pragma unroll 1
+                for (uint32_t k = threadIdx.x; k < cnt; k += T) {
+                    const uint32_t i = first + k;
                     const LimCell c = limiter_load_static(m, i);
                     limiter_cell(m, i, c, qk_in, gx, gy, lim, limiter_k, walls);
                 }
-                __syncthreads();
-                if (threadIdx.x == 0) pipe_publish(&Ldone[chunk], &pt.ctr[2]);
             }
         } else if (ph == PH_F || ph == PH_FARF) {
-            uint32_t f = 0;
-            bool active;
-            if (ph == PH_F) {
-                f = pt.face_start[chunk] + idx * T + threadIdx.x;
-                active = f < pt.face_start[chunk + 1];
-            } else {
-                const uint32_t k = idx * T + threadIdx.x;
-                active = k < pt.n_far_faces;
-                if (active) f = pt.far_faces[k];
-            }
-            FaceRec rec;
-            if (active) {
-                rec = face_load_static(m, f);
-                if (ph == PH_F && rec.fc.y < m.N) {  // a face between two chunks more than one apart waits for the far pass
-                    const uint32_t ca = rec.fc.x >> pt.shift, cb = rec.fc.y >> pt.shift;
-                    if (ca > cb + 1u || cb > ca + 1u) active = false;
-                }
-            }
             if (HAS_L) {  // the limiters of both cells: this chunk and its two neighbours (sweep), every chunk (far pass)
-                if (threadIdx.x == 0) {
-                    if (ph == PH_F) {
-                        const uint32_t c0 = chunk > 0 ? chunk - 1u : 0u, c1 = umin32(chunk + 1u, pt.n_chunks - 1u);
-                        for (uint32_t c = c0; c <= c1; ++c) {
-                            const uint32_t cells = umin32((c + 1u) << pt.shift, m.n_grad) - (c << pt.shift);
-                            pipe_wait(&Ldone[c], (cells + T - 1u) / T, pt.err);
-                        }
-                    } else pipe_wait(&pt.ctr[2], pt.nL_total, pt.err);
-                    __threadfence();
-                }
+                if (ph == PH_F) {
+                    if (threadIdx.x < 3u) {
+                        const uint32_t c = chunk + threadIdx.x;  // chunk - 1 + t
+                        if (c >= 1u && c - 1u < pt.n_chunks) pipe_wait(&Ldone[c - 1u], pt.chunk_items[c - 1u].x, pt.err);
+                        __threadfence();
+                    }
+                } else if (threadIdx.x == 0) { pipe_wait(&pt.ctr[2], pt.nL_total, pt.err); __threadfence(); }
                 __syncthreads();
             }
-            if (active) flux_face<SECOND, VISC, 0, HAS_L>(m, f, rec, qk_in, q0, gx, gy, lim, flux, g, mk4(0, 0, 0, 0));
-            __syncthreads();
-            if (threadIdx.x == 0) pipe_publish(ph == PH_F ? &Fdone[chunk] : nullptr, &pt.ctr[3]);
-        } else {  // PH_U, PH_FARU
-            uint32_t i = 0;
-            bool active;
+#pragma unroll 1
+            for (uint32_t k = threadIdx.x; k < cnt; k += T) {
+                const uint32_t f = ph == PH_F ? first + k : pt.far_faces[first + k];
+                const FaceRec fr = face_load_static(m, f);
+                if (ph == PH_F && fr.fc.y < m.N) {  // a face between two chunks more than one apart waits for the far pass
+                    const uint32_t ca = fr.fc.x >> pt.shift, cb = fr.fc.y >> pt.shift;
+                    if (ca > cb + 1u || cb > ca + 1u) continue;
+                }
+                flux_face<SECOND, 0, 0, HAS_L>(m, f, fr, qk_in, q0, gx, gy, lim, flux, g, mk4(0, 0, 0, 0));
+            }
+        } else {  // PH_U, PH_FARU: the fluxes of the cell's faces -- lower cell in this chunk or the one before (sweep)
             if (ph == PH_U) {
-                i = (chunk << pt.shift) + idx * T + threadIdx.x;
-                active = i < umin32((chunk + 1u) << pt.shift, m.n_upd);
-                if (active && ((pt.far_mask[i >> 5] >> (i & 31u)) & 1u)) active = false;  // touches a far face: far pass
-            } else {
-                const uint32_t k = idx * T + threadIdx.x;
-                active = k < pt.n_far_cells;
-                if (active) i = pt.far_cells[k];
-            }
-            uint32_t bnd[4] = {CF_NONE, CF_NONE, CF_NONE, CF_NONE};
-            if (active) {
-#pragma unroll
-                for (int s = 0; s < 4; ++s) bnd[s] = m.cf[(size_t)s * m.N + i];
-            }
-            if (threadIdx.x == 0) {  // the fluxes of the cell's faces: lower cell in this chunk or the one before (sweep)
-                if (ph == PH_U) {
-                    const uint32_t c0 = chunk > 0 ? chunk - 1u : 0u;
-                    for (uint32_t c = c0; c <= chunk; ++c) {
-                        const uint32_t nf = pt.face_start[c + 1] - pt.face_start[c];
-                        pipe_wait(&Fdone[c], (nf + T - 1u) / T, pt.err);
-                    }
-                } else pipe_wait(&pt.ctr[3], pt.nF_total, pt.err);
-                __threadfence();
-            }
+                if (threadIdx.x < 2u) {
+                    const uint32_t c = chunk + threadIdx.x;  // chunk - 1 + t
+                    if (c >= 1u) pipe_wait(&Fdone[c - 1u], pt.chunk_items[c - 1u].y, pt.err);
+                    __threadfence();
+                }
+            } else if (threadIdx.x == 0) { pipe_wait(&pt.ctr[3], pt.nF_total, pt.err); __threadfence(); }
             __syncthreads();
             double nrm = 0;
-            if (active) nrm = gather_cell<0, LAST, 1>(m, i, bnd, flux, q0, qk_in, qk_out, dt, qW, alpha, prm, walls, push);
-            if (LAST) block_norm_accumulate(nrm, no, ph == PH_U ? pt.u_slot0[chunk] + idx : pt.nU_near_items + idx);
+#pragma unroll 1
+            for (uint32_t k = threadIdx.x; k < cnt; k += T) {
+                uint32_t i;
+                if (ph == PH_U) {
+                    i = first + k;
+                    if ((pt.far_mask[i >> 5] >> (i & 31u)) & 1u) continue;  // touches a far face: far pass
+                } else i = pt.far_cells[first + k];
+                uint32_t bnd[4];
+#pragma unroll
+                for (int s = 0; s < 4; ++s) bnd[s] = m.cf[(size_t)s * m.N + i];
+                nrm += gather_cell<0, LAST, 1>(m, i, bnd, flux, q0, qk_in, qk_out, dt, qW, alpha, prm, walls, push);
+            }
+            if (LAST) block_norm_partial(nrm, no, rec.w);
         }
-        __syncthreads();  // s_it is rewritten next
+        if (threadIdx.x == 0) s_next[(n + 1u) & 1u] = nxt;
+        __syncthreads();  // every write of this item has been issued
+        if (threadIdx.x == 0 && ph != PH_U && ph != PH_FARU && (HAS_L || ph != PH_L)) {
+            // publish: the fence (cumulative over the writes the barrier has ordered before it) and the counters run while the
+            // other threads are already on the next item
+            __threadfence();
+            if (ph == PH_L) { atomicAdd(&Ldone[chunk], 1u); atomicAdd(&pt.ctr[2], 1u); }
+            else { if (ph == PH_F) atomicAdd(&Fdone[chunk], 1u); atomicAdd(&pt.ctr[3], 1u); }
+        }
     }
     // the last CTA to leave zeroes the work counters for the next launch (which starts behind griddepcontrol.wait)
     if (threadIdx.x == 0) {
@@ -182,7 +151,7 @@ __global__ void __launch_bounds__(AFX_PIPE_THREADS, AFX_PIPE_MINB) k_pipe(DevMes
 
 namespace launch {
 
-static int pipe_threads() { return AFX_PIPE_THREADS; }
+static int pipe_item_elems() { return AFX_PIPE_THREADS * AFX_PIPE_EPT; }
 static int pipe_ctas_per_sm() { return AFX_PIPE_MINB; }
 
 static void pipe(int second, int visc, int last, int has_l, const DevMesh& m, const PipeTab& pt, unsigned grid, const d4* qk_in, const d4* q0,
@@ -192,15 +161,15 @@ static void pipe(int second, int visc, int last, int has_l, const DevMesh& m, co
     if (!grid || !pt.n_items) return;
     PushArgs push{};
     if (push_in) push = *push_in;
-    if (no.blk_total == 0) { no.blk_off = 0; no.blk_total = pt.nU_near_items + pt.n_farU_items; }
-#define AFX_PIPE(S, V, L, H) launch_pdl(k_pipe<S, V, L, H>, grid, AFX_PIPE_THREADS, st, m, pt, qk_in, q0, qk_out, gx, gy, lim, flux, dt, qW, alpha, prm, g, limiter_k, walls, no, push)
-#define AFX_PIPE_LH(S, V) do { if (last) { if (has_l) AFX_PIPE(S, V, 1, 1); else AFX_PIPE(S, V, 1, 0); } else { if (has_l) AFX_PIPE(S, V, 0, 1); else AFX_PIPE(S, V, 0, 0); } } while (0)
-    // VISC = 0 only: the laminar face gradient reads the iteration-start state of BOTH cells of a face, and the last stage
-    // writes that state in place -- a later chunk's fluxes would see updated neighbours (the host keeps the three-kernel
+    if (no.blk_total == 0) { no.blk_off = 0; no.blk_total = pt.nU_items; }
+#define AFX_PIPE(S, L, H) launch_pdl(k_pipe<S, L, H>, grid, AFX_PIPE_THREADS, st, m, pt, qk_in, q0, qk_out, gx, gy, lim, flux, dt, qW, alpha, prm, g, limiter_k, walls, no, push)
+#define AFX_PIPE_LH(S) do { if (last) { if (has_l) AFX_PIPE(S, 1, 1); else AFX_PIPE(S, 1, 0); } else { if (has_l) AFX_PIPE(S, 0, 1); else AFX_PIPE(S, 0, 0); } } while (0)
+    // inviscid flux form only: the laminar face gradient reads the iteration-start state of BOTH cells of a face, and the last
+    // stage writes that state in place -- a later chunk's fluxes would see updated neighbours (the host keeps the three-kernel
     // stage for laminar runs)
     (void)visc;
-    if (second) AFX_PIPE_LH(1, 0);
-    else AFX_PIPE_LH(0, 0);
+    if (second) AFX_PIPE_LH(1);
+    else AFX_PIPE_LH(0);
 #undef AFX_PIPE_LH
 #undef AFX_PIPE
 }

@@ -113,7 +113,7 @@ struct LocalGroup {
     int arrived = 0;
     uint64_t gen = 0;
     bool broken = false;
-    double timeout_s = 120.;
+    double timeout_s = getenv("AFX_GROUP_TIMEOUT_S") ? atof(getenv("AFX_GROUP_TIMEOUT_S")) : 120.;
     std::vector<Solver*> member;              // set by init_halo, read between barriers
     std::vector<std::vector<double>> slot;    // all-reduce operands, one per rank
     void barrier()
@@ -161,6 +161,7 @@ struct Halo {
     DBuf<unsigned long long> epoch;
     DBuf<unsigned int> front_done;
     DBuf<double> red;                     // device scratch of the all-reduces (norm chunks, forces)
+    bool lockstep = false;                // in-process group with several ranks on ONE device: see halo_rendezvous()
     bool can_p2p = true;                  // this rank's plan fits the peer-memory path (agreed over all ranks at connect)
     bool early_signal = false;            // AFX_HALO_EARLY_SIGNAL=1
     PushArgs push{};
@@ -230,7 +231,7 @@ struct Solver {
     bool fused_stage() const { return tiles_ready && use_fused && second_order && viscous_type == 0 && !(halo && halo_overlap); }
     void launch_stage(int s, const d4* qk_in, d4* qk_out, double alpha);
     // pipelined stage kernel on L2-resident chunks (rans_pipe.cuh); [0] without, [1] with the limiter phase
-    DBuf<uint4> p_steps[2]; DBuf<uint32_t> p_face_start, p_uslot, p_far_faces, p_far_cells, p_far_mask; DBuf<unsigned int> p_ctr;
+    DBuf<uint4> p_items[2]; DBuf<uint2> p_chunk_items; DBuf<uint32_t> p_far_faces, p_far_cells, p_far_mask; DBuf<unsigned int> p_ctr;
     PipeTab pipe_tab[2] = {};
     bool pipe_ready = false, use_pipe = false;
     unsigned pipe_grid = 0;
@@ -306,6 +307,12 @@ struct Solver {
     void create(const afx_mesh_desc& m, const afx_gas& g, int visc, int dev, const Partition* part = nullptr, DryRun* dry = nullptr);
     void init_halo(const Partition& part, const char* nccl_id, std::shared_ptr<LocalGroup> group = nullptr);
     void comm_allreduce(double* dev, int n);   // sum over the ranks, in place, on the solver's stream
+    // Ranks of an in-process group that SHARE a device cannot rely on a kernel of one rank running while a kernel of another
+    // spins on its flag (two streams may sit in one hardware queue; measured on the B200: 3- and 8-rank runs ran into the bounded
+    // wait).  There the ranks meet on the host after their flags are raised and before anybody waits: the wait kernel finds its
+    // flags set.  Same kernels, same buffers, same epochs -- only the overlap (and the CUDA graph) is given up.
+    void halo_rendezvous(cudaStream_t s_) { if (halo && halo->lockstep) { CK(cudaStreamSynchronize(s_)); halo->grp->barrier(); } }
+    bool graph_ok() const { return use_graph && !(halo && halo->grp && (!halo->p2p || halo->lockstep)); }
     void check_comm();                         // AFX_ERR_COMM if a halo wait gave up on a peer
     int* comm_err_word() { return reinterpret_cast<int*>(h_pinned + 48); }
     size_t p2p_export(void* blob);
@@ -611,7 +618,7 @@ void Solver::create(const afx_mesh_desc& m, const afx_gas& g, int visc, int dev,
     flux.alloc(E); flux.zero(st);
     dt.alloc(NT); dt.zero(st); dt_ref.alloc(NT);
     build_pipe_tables();
-    partial.alloc(std::max<size_t>(std::max<size_t>(kt->gather_blocks(NT), stage_grid), (size_t)pipe_tab[0].nU_near_items + pipe_tab[0].n_farU_items) + 4);
+    partial.alloc(std::max<size_t>(std::max<size_t>(kt->gather_blocks(NT), stage_grid), (size_t)pipe_tab[0].nU_items) + 4);
     norms.alloc(NORM_RING); norms.zero(st);
     prm.alloc(8); prm.zero(st); counters.alloc(4); counters.zero(st); scratch.alloc(16);
     // limiters start at 1 (ghost rows keep that value, solver.h:519)
@@ -754,6 +761,8 @@ template <int MODE, int LAST>
 void Solver::launch_gather(const d4* qk_in, d4* qk_out, d4* vec_out, double alpha, bool walls)
 {
     const bool split_front = n_front > 0 && n_front < n_upd;
+    // LAST: the launches below leave one partial sum per block; one small kernel adds them (k_norm_finish)
+    auto finish = [&](unsigned blocks) { if (LAST) { kt->norm_finish(norm_out(), blocks, st); ++launches; } };
     if (halo && MODE == 0 && halo->p2p && !(halo_overlap && split_front)) {
         // one launch advances everything and pushes the send layer into the peers' buffers; a flag hand-off and a
         // small wait+scatter kernel complete the halo on the same stream (no fork/join, no split launches)
@@ -764,14 +773,16 @@ void Solver::launch_gather(const d4* qk_in, d4* qk_out, d4* vec_out, double alph
             pa.early_signal = 1;
             pa.n_front_blocks = kt->gather_blocks(n_front);
             kt->gather(MODE, LAST, dm, 0, n_upd, flux.p, q.p, qk_in, qk_out, dt.p, vec_out, alpha, prm.p, walls ? 1 : 0, norm_out(), &pa, st);
-            kt->halo_wait_scatter(halo->wait, qk_out, st);
+            halo_rendezvous(st); kt->halo_wait_scatter(halo->wait, qk_out, st);
             launches += 2;
+            finish(kt->gather_blocks(n_upd));
             return;
         }
         kt->gather(MODE, LAST, dm, 0, n_upd, flux.p, q.p, qk_in, qk_out, dt.p, vec_out, alpha, prm.p, walls ? 1 : 0, norm_out(), &halo->push, st);
         kt->halo_signal(halo->sig, st);
-        kt->halo_wait_scatter(halo->wait, qk_out, st);
+        halo_rendezvous(st); kt->halo_wait_scatter(halo->wait, qk_out, st);
         launches += 3;
+        finish(kt->gather_blocks(n_upd));
         return;
     }
     if (halo && MODE == 0 && split_front && !(halo->grp && !halo->p2p)) {
@@ -786,7 +797,7 @@ void Solver::launch_gather(const d4* qk_in, d4* qk_out, d4* vec_out, double alph
             kt->halo_signal(halo->sig, st);
             CK(cudaEventRecord(ev_front, st));
             CK(cudaStreamWaitEvent(cs, ev_front, 0));
-            kt->halo_wait_scatter(halo->wait, qk_out, cs);
+            halo_rendezvous(st); kt->halo_wait_scatter(halo->wait, qk_out, cs);
             launches += 2;
         } else {
             kt->gather(MODE, LAST, dm, 0, n_front, flux.p, q.p, qk_in, qk_out, dt.p, vec_out, alpha, prm.p, walls ? 1 : 0, no, nullptr, st);
@@ -799,10 +810,12 @@ void Solver::launch_gather(const d4* qk_in, d4* qk_out, d4* vec_out, double alph
         kt->gather(MODE, LAST, dm, n_front, n_upd, flux.p, q.p, qk_in, qk_out, dt.p, vec_out, alpha, prm.p, walls ? 1 : 0, no, nullptr, st);
         halo_pending = true;  // joined by the first kernel that reads halo cells (ensure_halo)
         launches += 2;
+        finish(b0 + b1);
         return;
     }
     kt->gather(MODE, LAST, dm, 0, n_upd, flux.p, q.p, qk_in, qk_out, dt.p, vec_out, alpha, prm.p, walls ? 1 : 0, norm_out(), nullptr, st);
     ++launches;
+    finish(kt->gather_blocks(n_upd));
     if (halo && MODE == 0) exchange(qk_out, st);
 }
 
@@ -902,15 +915,15 @@ void Solver::build_pipe_tables()
 {
     pipe_ready = false;
     if (const char* e = getenv("AFX_PIPE")) use_pipe = (e[0] == '1');
-    uint32_t shift = 15, lagF = 2, lagU = 2;
+    uint32_t shift = 15, lagF = 3, lagU = 2;
     if (const char* e = getenv("AFX_PIPE_SHIFT")) shift = (uint32_t)std::max(8, std::min(24, atoi(e)));
     if (const char* e = getenv("AFX_PIPE_LAGF")) lagF = (uint32_t)std::max(1, std::min(16, atoi(e)));
     if (const char* e = getenv("AFX_PIPE_LAGU")) lagU = (uint32_t)std::max(0, std::min(16, atoi(e)));
-    const uint32_t T = (uint32_t)kt->pipe_threads();
+    const uint32_t IT = (uint32_t)kt->pipe_item_elems();
     const uint32_t csz = 1u << shift;
     const uint32_t n_chunks = (n_grad + csz - 1) / csz;
     if (!n_chunks || !n_upd) return;
-    auto items = [&](uint32_t n) { return (n + T - 1) / T; };
+    auto n_it = [&](uint32_t n) { return (n + IT - 1) / IT; };
     // faces are sorted by their lower cell: the faces of chunk c are a range
     std::vector<uint32_t> fs(n_chunks + 1, e_flux);
     {
@@ -937,42 +950,51 @@ void Solver::build_pipe_tables()
     }
     for (uint32_t i = 0; i < n_upd; ++i) if ((mask[i >> 5] >> (i & 31)) & 1u) far_c.push_back(i);
     const uint32_t n_far_f = (uint32_t)far_f.size(), n_far_c = (uint32_t)far_c.size();
-    std::vector<uint32_t> uslot(n_chunks, 0);
-    uint32_t nU = 0, nLtot = 0, nFnear = 0;
     auto cellsL = [&](uint32_t c) { return std::min((c + 1) << shift, n_grad) - (c << shift); };
     auto cellsU = [&](uint32_t c) { const uint32_t lo = c << shift; return lo >= n_upd ? 0u : std::min((c + 1) << shift, n_upd) - lo; };
-    for (uint32_t c = 0; c < n_chunks; ++c) { uslot[c] = nU; nU += items(cellsU(c)); nLtot += items(cellsL(c)); nFnear += items(fs[c + 1] - fs[c]); }
+    std::vector<uint2> chunk_items(n_chunks);
+    uint32_t nLtot = 0, nFnear = 0;
+    for (uint32_t c = 0; c < n_chunks; ++c) {
+        chunk_items[c] = make_uint2(n_it(cellsL(c)), n_it(fs[c + 1] - fs[c]));
+        nLtot += chunk_items[c].x; nFnear += chunk_items[c].y;
+    }
+    // the sweep: step k = limiter items of chunk k, flux items of chunk k - lagF, update items of chunk k - lagF - lagU
     const uint32_t n_steps = n_chunks + lagF + lagU;
-    std::vector<uint4> steps[2];
-    uint32_t n_main[2] = {0, 0};
+    uint32_t nU_items = 0;
     for (int hl = 0; hl < 2; ++hl) {
-        steps[hl].resize(n_steps);
-        uint32_t at = 0;
+        std::vector<uint4> items;
+        uint32_t slot = 0;
+        auto emit = [&](uint32_t ph, uint32_t chunk, uint32_t first, uint32_t count, bool is_u) {
+            for (uint32_t o = 0; o < count; o += IT) {
+                items.push_back(make_uint4(ph | (chunk << 3), first + o, std::min(IT, count - o), is_u ? slot : 0u));
+                if (is_u) ++slot;
+            }
+        };
         for (uint32_t k = 0; k < n_steps; ++k) {
-            const uint32_t nl = (hl && k < n_chunks) ? items(cellsL(k)) : 0u;
-            const uint32_t nf = (k >= lagF && k - lagF < n_chunks) ? items(fs[k - lagF + 1] - fs[k - lagF]) : 0u;
-            const uint32_t nu = (k >= lagF + lagU && k - lagF - lagU < n_chunks) ? items(cellsU(k - lagF - lagU)) : 0u;
-            steps[hl][k] = make_uint4(at, nl, nf, nu);
-            at += nl + nf + nu;
+            if (hl && k < n_chunks) emit(0u, k, k << shift, cellsL(k), false);
+            if (k >= lagF && k - lagF < n_chunks) { const uint32_t c = k - lagF; emit(1u, c, fs[c], fs[c + 1] - fs[c], false); }
+            if (k >= lagF + lagU && k - lagF - lagU < n_chunks) { const uint32_t c = k - lagF - lagU; emit(2u, c, c << shift, cellsU(c), true); }
         }
-        n_main[hl] = at;
-        p_steps[hl].upload(steps[hl], st);
+        emit(3u, 0u, 0u, n_far_f, false);
+        emit(4u, 0u, 0u, n_far_c, true);
+        nU_items = slot;
+        p_items[hl].upload(items, st);
+        PipeTab& t = pipe_tab[hl];
+        t = PipeTab{};
+        t.shift = shift; t.n_chunks = n_chunks; t.lagF = lagF; t.lagU = lagU;
+        t.n_items = (uint32_t)items.size();
+        t.n_far_faces = n_far_f; t.n_far_cells = n_far_c;
+        t.nL_total = hl ? nLtot : 0u; t.nF_total = nFnear + n_it(n_far_f); t.nU_items = nU_items;
+        t.items = p_items[hl].p;
     }
     if (far_f.empty()) far_f.push_back(0);
     if (far_c.empty()) far_c.push_back(0);
-    p_face_start.upload(fs, st); p_uslot.upload(uslot, st); p_far_faces.upload(far_f, st); p_far_cells.upload(far_c, st); p_far_mask.upload(mask, st);
+    p_chunk_items.upload(chunk_items, st); p_far_faces.upload(far_f, st); p_far_cells.upload(far_c, st); p_far_mask.upload(mask, st);
     p_ctr.alloc(4 + 2 * (size_t)n_chunks); p_ctr.zero(st);
     *pipe_err_word() = 0;
     for (int hl = 0; hl < 2; ++hl) {
         PipeTab& t = pipe_tab[hl];
-        t = PipeTab{};
-        t.shift = shift; t.n_chunks = n_chunks; t.n_steps = n_steps; t.lagF = lagF; t.lagU = lagU;
-        t.n_main = n_main[hl]; t.n_farF_items = items(n_far_f); t.n_farU_items = items(n_far_c);
-        t.n_items = t.n_main + t.n_farF_items + t.n_farU_items;
-        t.n_far_faces = n_far_f; t.n_far_cells = n_far_c;
-        t.nL_total = hl ? nLtot : 0u; t.nF_total = nFnear + t.n_farF_items; t.nU_near_items = nU;
-        t.steps = p_steps[hl].p; t.face_start = p_face_start.p; t.u_slot0 = p_uslot.p;
-        t.far_faces = p_far_faces.p; t.far_cells = p_far_cells.p; t.far_mask = p_far_mask.p;
+        t.chunk_items = p_chunk_items.p; t.far_faces = p_far_faces.p; t.far_cells = p_far_cells.p; t.far_mask = p_far_mask.p;
         t.ctr = p_ctr.p; t.err = pipe_err_word();
     }
     cudaDeviceProp prop{};
@@ -991,10 +1013,11 @@ void Solver::launch_pipe(int s, const d4* qk_in, d4* qk_out, double alpha, bool 
     kt->pipe(second_order, viscous_type, s == 2, has_l ? 1 : 0, dm, pt, std::min<unsigned>(pipe_grid, pt.n_items), qk_in, q.p, qk_out, gx.p, gy.p, lim.p,
              flux.p, dt.p, qW.p, alpha, prm.p, gas, limiter_k, walls, norm_out(), push, st);
     ++launches;
+    if (s == 2) { kt->norm_finish(norm_out(), pt.nU_items, st); ++launches; }
     if (!halo) return;
     if (halo->p2p) {  // the update items stored the send layer into the peers' buffers: flags, then fill our halo cells
         kt->halo_signal(halo->sig, st);
-        kt->halo_wait_scatter(halo->wait, qk_out, st);
+        halo_rendezvous(st); kt->halo_wait_scatter(halo->wait, qk_out, st);
         launches += 2;
     } else {
         exchange(qk_out, st);
@@ -1008,10 +1031,11 @@ void Solver::launch_stage(int s, const d4* qk_in, d4* qk_out, double alpha)
     const PushArgs* push = (halo && halo->p2p) ? &halo->push : nullptr;
     kt->stage(s == 2, dm, tt, stage_grid, stage_smem, qk_in, q.p, qk_out, gx.p, gy.p, dt.p, qW.p, lim.p, alpha, prm.p, gas, norm_out(), push, st);
     ++launches;
+    if (s == 2) { kt->norm_finish(norm_out(), stage_grid, st); ++launches; }
     if (!halo) return;
     if (halo->p2p) {  // the kernel stored the send layer into the peers' buffers: flags, then fill our halo cells
         kt->halo_signal(halo->sig, st);
-        kt->halo_wait_scatter(halo->wait, qk_out, st);
+        halo_rendezvous(st); kt->halo_wait_scatter(halo->wait, qk_out, st);
         launches += 2;
     } else {
         exchange(qk_out, st);
@@ -1167,6 +1191,12 @@ void Solver::p2p_connect(const void* blobs, size_t blob_size, int nranks)
     // on the collective exchange while its peers push and spin on flags would be a silent deadlock.
     bool all_can = true;
     for (int r = 0; r < nranks; ++r) all_can = all_can && all[r].can_p2p != 0;
+    h.lockstep = false;
+    if (h.grp)
+        for (int r = 0; r < nranks; ++r)
+            for (int r2 = r + 1; r2 < nranks; ++r2)
+                if (all[r].pid == all[r2].pid && all[r].device == all[r2].device) h.lockstep = true;  // the same on every rank
+    if (const char* e = getenv("AFX_HALO_LOCKSTEP")) h.lockstep = h.grp && e[0] == '1';  // override (tests of the bounded wait itself)
     if (!all_can) { h.p2p = false; invalidate_graph(); return; }
     std::vector<std::vector<uint32_t>> per_cell(n_front);
     std::vector<uint32_t> si(h.n_send);
@@ -1304,7 +1334,7 @@ void Solver::run_explicit(double relax, int n_iter, double* norms_out)
         CK(cudaMemcpyAsync(h_idx, counters.p + 1, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         const unsigned int k0 = *h_idx;
-        if (use_graph && !(halo && halo->grp && !halo->p2p)) {  // the staged in-process halo meets on the host: no capture
+        if (graph_ok()) {  // the staged / lock-step in-process halo meets on the host: no capture
             if (!graph_exec) {
                 cudaGraph_t g = nullptr;
                 const int64_t l0 = launches;

@@ -345,7 +345,7 @@ k_stage(DevMesh m, TileTab tt, const d4* __restrict__ qk_in, const d4* q0, d4* q
         cur = nxt; nxt = nx2;
     }
     cp_async_wait<0>();
-    if (LAST) block_norm_accumulate(nrm, no, blockIdx.x);
+    if (LAST) block_norm_partial(nrm, no, blockIdx.x);
 }
 
 // K^3 a of every tile-local cell record from its area (solver.h:551-552); run when limiter_k changes

@@ -94,16 +94,14 @@ __host__ __device__ inline StageSmem stage_smem_layout(uint32_t max_loc, uint32_
 // all of which were handed out before it.  Faces joining two chunks more than one apart, and the cells that touch them
 // ("far", a few per cent), are done after the sweep from two index lists.
 struct PipeTab {
-    uint32_t shift, n_chunks, n_steps;
+    uint32_t shift, n_chunks;
     uint32_t lagF, lagU;
-    uint32_t n_items, n_main;            // all items; items of the sweep (then: far-face items, then far-cell items)
-    uint32_t n_farF_items, n_farU_items;
+    uint32_t n_items;                    // sweep items, then far-face items, then far-cell items
     uint32_t n_far_faces, n_far_cells;
     uint32_t nL_total, nF_total;         // limiter items; flux items (sweep + far)
-    uint32_t nU_near_items;              // norm slots of the sweep's update items; the far items' slots follow
-    const uint4* steps;                  // [n_steps] {first item, limiter items, flux items, update items}
-    const uint32_t* face_start;          // [n_chunks + 1] first face whose lower cell lies in chunk c (capped at e_flux)
-    const uint32_t* u_slot0;             // [n_chunks] first norm slot of chunk c's update items
+    uint32_t nU_items;                   // update items (sweep + far) = norm slots
+    const uint4* items;                  // [n_items] {phase | chunk << 3, first element (or offset into a far list), elements, norm slot}
+    const uint2* chunk_items;            // [n_chunks] {limiter items, flux items} of chunk c: what a dependent item waits for
     const uint32_t* far_faces;           // [n_far_faces]
     const uint32_t* far_cells;           // [n_far_cells]
     const uint32_t* far_mask;            // bit i: advanced cell i touches a far face
@@ -119,7 +117,7 @@ struct NormOut {
     unsigned int* norm_idx; // running index into norms
     int store_square;       // 1: store the sum of squares (partitioned runs add the ranks' sums before the root)
     unsigned int blk_off;   // this launch's first slot in partial[] (a phase may be split into several launches)
-    unsigned int blk_total; // blocks of all launches of the phase; the block that arrives last finishes the sum
+    unsigned int blk_total; // blocks (work items) of all launches of the phase: k_norm_finish adds that many partial sums
 };
 
 // Halo push over NVLink peer memory, fused into the update kernel: an advanced cell that a peer needs is stored straight
@@ -188,7 +186,7 @@ struct KernelTable {
     void (*pipe)(int second, int visc, int last, int has_l, const DevMesh& m, const PipeTab& pt, unsigned grid, const d4* qk_in, const d4* q0,
                  d4* qk_out, const d4* gx, const d4* gy, d4* lim, d4* flux, const double* dt, d4* qW, double alpha, const double* prm,
                  const GasC& g, double limiter_k, int walls, NormOut no, const PushArgs* push, cudaStream_t st);
-    int (*pipe_threads)();
+    int (*pipe_item_elems)();  // cells or faces per work item
     int (*pipe_ctas_per_sm)();
     int (*stage_prepare)(size_t smem);  // opt in to the dynamic shared memory on the current device; resident CTAs per SM or <0
     int (*stage_threads)();
@@ -198,6 +196,7 @@ struct KernelTable {
     void (*halo_signal)(const SignalArgs& a, cudaStream_t st);               // tell the peers my send layer is in their buffers
     void (*halo_wait_scatter)(const WaitArgs& a, d4* field, cudaStream_t st); // wait for the peers, then fill my halo cells
     unsigned (*gather_blocks)(uint32_t n_cells);
+    void (*norm_finish)(NormOut no, unsigned total, cudaStream_t st);  // sum the partials of a phase -> residual-history ring
     void (*jacobian)(int visc, const DevMesh& m, const d4* q, const d4* gx, const d4* gy, d4* J, const GasC& g, cudaStream_t st);
     void (*jac_diag)(const DevMesh& m, const d4* J, const double* dt, double* D, cudaStream_t st);
     void (*wall_forces)(const WallArgs& a, const DevMesh& m, const d4* q, cudaStream_t st);

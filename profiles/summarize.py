@@ -44,10 +44,19 @@ def main(rep, launches, tag):
                 vals = [float(r[col[m]].replace(",", "")) for r in rs if r[col[m]] not in ("", "n/a")]
                 if vals:
                     d[m + " [" + units[col[m]] + "]"] = sum(vals) / len(vals)
-        rd = d.get("dram__bytes_read.sum [Mbyte]"); wr = d.get("dram__bytes_write.sum [Mbyte]")
+        def unit(prefix, scale):  # ncu picks the unit per report (us / ms, Kbyte / Mbyte / Gbyte): normalise
+            for u, f in scale.items():
+                v = d.get("%s [%s]" % (prefix, u))
+                if v is not None:
+                    return v * f
+            return None
+        BYTES = {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}
+        rd = unit("dram__bytes_read.sum", BYTES); wr = unit("dram__bytes_write.sum", BYTES)
+        t = unit("gpu__time_duration.sum", {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6})
+        if t is not None:
+            d["time_us"] = t
         if rd is not None and wr is not None:
             d["dram_traffic_per_launch_MB"] = rd + wr
-            t = d.get("gpu__time_duration.sum [us]")
             if t:
                 d["dram_GBps_during_kernel"] = (rd + wr) / t * 1e3
         out[k] = d
@@ -69,7 +78,7 @@ def main(rep, launches, tag):
             f.write("ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised: compare SHARES)\n\n" + "\n".join(lines) + "\n")
         import shutil
         shutil.copy(launches, os.path.join(HERE, tag + "_launches.csv"))
-    print(json.dumps({k: {"us": v.get("gpu__time_duration.sum [us]"), "dram_MB": v.get("dram_traffic_per_launch_MB"),
+    print(json.dumps({k: {"us": v.get("time_us"), "dram_MB": v.get("dram_traffic_per_launch_MB"),
                           "dram_GBps": v.get("dram_GBps_during_kernel")} for k, v in out.items()}, indent=1))
 
 

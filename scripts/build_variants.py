@@ -21,6 +21,11 @@ VARIANTS = {
     "st128": ["-DAFX_FLUX_THREADS=128", "-DAFX_LIM_THREADS=128", "-DAFX_GATHER_THREADS=128"],
     "fl128": ["-DAFX_FLUX_THREADS=128", "-DAFX_LIM_THREADS=128"],
     "nopreload_t128": ["-DAFX_DTG_PRELOAD=0", "-DAFX_DTG_THREADS=128", "-DAFX_DTG_MINB=6"],
+    # pipelined stage kernel: elements per thread and item, CTA shape (rans_pipe.cuh)
+    "pipe_ept1": ["-DAFX_PIPE_EPT=1"],
+    "pipe_ept4": ["-DAFX_PIPE_EPT=4"],
+    "pipe_t128": ["-DAFX_PIPE_THREADS=128", "-DAFX_PIPE_MINB=8", "-DAFX_PIPE_EPT=4"],
+    "pipe_r80": ["-DAFX_PIPE_THREADS=256", "-DAFX_PIPE_MINB=3", "-DAFX_PIPE_EPT=2"],
     "nopreload_t128_pf": ["-DAFX_DTG_PRELOAD=0", "-DAFX_DTG_THREADS=128", "-DAFX_DTG_MINB=6", "-DAFX_DTG_DXY=1"],
 }
 for name, defs in VARIANTS.items():

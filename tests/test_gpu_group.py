@@ -42,12 +42,9 @@ def _group_run(afx, mesh, world, halo, math, visc, grad, so, n_iter, q0, ndev, f
             solvers[r] = afx.GpuSolver(parts[r], viscosity=visc, math=math, device=r % ndev, group=group)
         return f
     afx.run_ranks([make(r) for r in range(world)])
-    # Peer-memory mode makes one solver's kernel wait for a flag another solver's kernel raises.  On ONE device that needs the two
-    # streams in different hardware queues: safe for a few ranks (CUDA_DEVICE_MAX_CONNECTIONS=32, tests/conftest.py), not for 8
-    # (measured on the B200: the 8-rank case ran into the bounded wait).  More ranks than that share a device only with the staged
-    # halo; with one device per rank (the production layout) every case uses the mode it names.
-    if halo == "p2p" and world > 3 and ndev < world:
-        halo = "staged"
+    # Peer-memory mode on ONE device: the library detects that group members share a device and lets the ranks meet on the host
+    # between raising and waiting for the flags (no kernel ever spins on another rank's kernel); with one device per rank -- the
+    # production layout -- the same calls run the captured graph with the in-kernel wait.
     if halo == "p2p":
         blobs = [s.p2p_export() for s in solvers]
         for s in solvers:
@@ -185,6 +182,7 @@ def test_dead_peer_returns_comm_error_instead_of_hanging(afx, gpu, monkeypatch):
     """A peer that never delivers (here: it simply does not run) must not leave an unkillable kernel: the halo wait gives up
     after AFX_HALO_TIMEOUT_MS and the run returns AFX_ERR_COMM."""
     monkeypatch.setenv("AFX_HALO_TIMEOUT_MS", "300")
+    monkeypatch.setenv("AFX_HALO_LOCKSTEP", "0")  # the in-kernel wait itself, although both ranks share the device (the peer never launches anything)
     mesh = afx.Mesh.synth_omesh(64, 40, 16, 150.0)
     world = 2
     group = afx.Group(world)

@@ -334,7 +334,7 @@ def test_first_stage_limiter_inside_dt_grad_is_bit_identical(afx, gpu, monkeypat
         np.testing.assert_allclose(outs[0][0], outs[1][0], rtol=1e-11)
         np.testing.assert_allclose(outs[0][1], outs[1][1], rtol=1e-11, atol=1e-14)
         np.testing.assert_allclose(outs[0][4], outs[1][4], rtol=1e-9, atol=1e-12)
-    assert outs[0][2] == 9 and outs[1][2] == 10  # kernels per explicit iteration
+    assert outs[0][2] == 10 and outs[1][2] == 11  # kernels per explicit iteration (the last one adds up the residual norm)
 
 
 
