@@ -9,6 +9,6 @@ solver call goes to the CUDA library and raises if it is missing or no B200 is
 visible.
 """
 from .capi import (AfxError, Mesh, GpuSolver, build_library, library_path, load_library,  # noqa: F401
-                   BC_KINDS, VISCOSITY, GRADIENT, device_count, is_emulation, EXPORTED_SYMBOLS, pinned_array, Partition, nccl_unique_id, tiling_plan, Group, run_ranks)
+                   BC_KINDS, VISCOSITY, GRADIENT, device_count, is_emulation, EXPORTED_SYMBOLS, pinned_array, Partition, nccl_unique_id, tiling_plan, Group, run_ranks, Prolongation, sweep_fmg)
 
 __all__ = ["AfxError", "Mesh", "GpuSolver", "build_library", "library_path", "load_library", "device_count"]

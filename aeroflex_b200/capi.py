@@ -40,7 +40,8 @@ EXPORTED_SYMBOLS = [
     "afx_rans_run_explicit", "afx_rans_phase_dt_gradients", "afx_rans_phase_limiters", "afx_rans_phase_residual",
     "afx_rans_residual", "afx_rans_fill_jacobian", "afx_rans_get_jacobian_blocks", "afx_rans_step_implicit", "afx_rans_compute",
     "afx_rans_set_linear_solver", "afx_rans_last_linear_iterations",
-    "afx_rans_wall_forces", "afx_rans_wall_cp", "afx_rans_sweep", "afx_rans_last_device_ms", "afx_rans_launch_count",
+    "afx_rans_wall_forces", "afx_rans_wall_cp", "afx_rans_sweep", "afx_rans_sweep_fmg", "afx_prolongation_create", "afx_prolongation_free",
+    "afx_prolongation_apply", "afx_rans_last_device_ms", "afx_rans_launch_count",
     "afx_rans_profile_explicit",
 ]
 
@@ -215,6 +216,10 @@ def load_library():
     L.afx_rans_wall_forces.argtypes = [vp, C.c_int, vp]
     L.afx_rans_wall_cp.argtypes = [vp, C.c_int, vp]
     L.afx_rans_sweep.argtypes = [vp, C.POINTER(SweepSettings), C.c_int, C.c_int, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp]
+    L.afx_prolongation_create.argtypes = [C.POINTER(vp), vp, vp, vp, vp, vp]
+    L.afx_prolongation_free.argtypes = [vp]
+    L.afx_prolongation_apply.argtypes = [vp]
+    L.afx_rans_sweep_fmg.argtypes = [C.POINTER(vp), C.POINTER(vp), C.c_int, C.POINTER(SweepSettings), C.c_int, C.c_int, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp]
     L.afx_rans_last_device_ms.argtypes = [vp, dp]
     L.afx_rans_launch_count.restype = C.c_int64
     L.afx_rans_launch_count.argtypes = [vp]
@@ -382,6 +387,45 @@ class Partition:
                     cell_edges=a(d.cells_edges, 4 * N).reshape(-1, 4), is_tri=a(d.cells_is_tri, N),
                     bnd_edge=a(d.boundary_edges, self.G) if self.G else np.zeros(0, np.uint32),
                     bnd_patch=a(d.boundary_patch, self.G) if self.G else np.zeros(0, np.int32))
+
+
+class Prolongation:
+    """FMG prolongation between two GpuSolvers on the device (CSR: row_begin[n_fine+1], col, w in the meshes' reference order)."""
+
+    def __init__(self, coarse, fine, row_begin, col, w):
+        self.L = load_library()
+        self.coarse, self.fine = coarse, fine
+        rb = np.ascontiguousarray(row_begin, np.uint32); c = np.ascontiguousarray(col, np.uint32); ww = np.ascontiguousarray(w, np.float64)
+        self.h = C.c_void_p()
+        _check(self.L.afx_prolongation_create(C.byref(self.h), coarse.h, fine.h, _ptr(rb), _ptr(c), _ptr(ww)))
+
+    def apply(self):
+        _check(self.L.afx_prolongation_apply(self.h))
+
+    def __del__(self):
+        try:
+            self.L.afx_prolongation_free(self.h)
+        except Exception:
+            pass
+
+
+def sweep_fmg(levels, prolongations, alphas_deg, implicit=True, relaxation=0.9, start_cfl=40.0, slope_cfl=50.0, max_cfl=100.0, tolerance=1e-4,
+              rhs_iterations=5, max_iterations=300, farfield="farfield", wall="wall", reinit=True):
+    """Rans::run_airfoil over several mesh levels, on the device (afx_rans_sweep_fmg)."""
+    L = load_library()
+    al = np.ascontiguousarray(alphas_deg, dtype=np.float64)
+    n = len(al)
+    st = SweepSettings(int(bool(implicit)), relaxation, start_cfl, slope_cfl, max_cfl, tolerance, rhs_iterations, max_iterations)
+    cl, cd, cm, res = (np.full(n, np.nan) for _ in range(4))
+    it = np.zeros(n, np.int32)
+    names = levels[0].mesh.patch_names
+    lv = (C.c_void_p * len(levels))(*[s.h for s in levels])
+    pr = (C.c_void_p * max(1, len(prolongations)))(*[p.h for p in prolongations])
+    rc = L.afx_rans_sweep_fmg(lv, pr, len(levels), C.byref(st), names.index(farfield), names.index(wall), _ptr(al), n, int(bool(reinit)),
+                              _ptr(cl), _ptr(cd), _ptr(cm), _ptr(it), _ptr(res))
+    if rc not in (0, -3):
+        _check(rc)
+    return dict(cl=cl, cd=cd, cm=cm, iterations=it, residual=res, status=rc)
 
 
 def nccl_unique_id():

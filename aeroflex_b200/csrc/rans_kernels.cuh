@@ -863,6 +863,26 @@ __global__ void k_face_record_kinds(d4* __restrict__ frec, const uint8_t* __rest
     frec[2 * (size_t)f + 1].w = __longlong_as_double((long long)cw);
 }
 
+// FMG prolongation q_fine = P q_coarse on the device (multigrid.h:100-178 builds P, multigrid.h:308/341 applies it): P has one
+// weight per (fine cell, coarse cell) pair, rows in the FINE mesh's reference order, columns in the COARSE mesh's; both
+// states live in their solver's internal order.  Each row is summed in ascending column order from zero, which is the order
+// of the reference's sparse product, so in the strict build the result carries the reference's bits.
+__global__ void __launch_bounds__(256) k_prolongate(uint32_t n_fine, const uint32_t* __restrict__ row_begin, const uint32_t* __restrict__ col,
+                                                    const double* __restrict__ w, const uint32_t* __restrict__ fine_new2old,
+                                                    const uint32_t* __restrict__ coarse_old2new, const d4* __restrict__ qc, d4* __restrict__ qf)
+{
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n_fine) return;
+    const uint32_t row = fine_new2old[n];
+    d4 s = mk4(0, 0, 0, 0);
+    for (uint32_t p = row_begin[row]; p < row_begin[row + 1]; ++p) {
+        const double wp = w[p];
+        const d4 c = qc[coarse_old2new[col[p]]];
+        s.x += wp * c.x; s.y += wp * c.y; s.z += wp * c.z; s.w += wp * c.w;
+    }
+    qf[n] = s;
+}
+
 // small utilities -----------------------------------------------------------
 __global__ void k_fill_cells(d4* __restrict__ q, uint32_t n, d4 v)
 {
@@ -987,6 +1007,11 @@ static void jac_diag(const DevMesh& m, const d4* J, const double* dt, double* D,
     k_jac_diag<<<nblk(m.NT), 256, 0, st>>>(m, reinterpret_cast<const double*>(J), dt, D);
 }
 static void wall_forces(const WallArgs& a, const DevMesh& m, const d4* q, cudaStream_t st) { k_wall_forces<<<1, 256, 0, st>>>(a, m, q); }
+static void prolongate(uint32_t n_fine, const uint32_t* row_begin, const uint32_t* col, const double* w, const uint32_t* fine_new2old,
+                       const uint32_t* coarse_old2new, const d4* qc, d4* qf, cudaStream_t st)
+{
+    if (n_fine) k_prolongate<<<nblk(n_fine), 256, 0, st>>>(n_fine, row_begin, col, w, fine_new2old, coarse_old2new, qc, qf);
+}
 static void fill_cells(d4* q, uint32_t n, d4 v, cudaStream_t st) { k_fill_cells<<<nblk(n), 256, 0, st>>>(q, n, v); }
 static void ghost_fill(d4* q, const uint32_t* bghost, const uint32_t* bowner, const d4* bstate, uint32_t G, int from_owner, cudaStream_t st)
 {

@@ -2182,58 +2182,159 @@ int afx_rans_wall_cp(afx_rans* s, int patch, double* cp)
     return rc ? rc : count;
 }
 
-int afx_rans_sweep(afx_rans* s, const afx_sweep_settings* st, int farfield_patch, int wall_patch, const double* alphas_deg, int n_alpha,
-                   int reinit, double* cl, double* cd, double* cm, int* iterations, double* residual)
+struct afx_prolongation {
+    afx_rans* coarse = nullptr;
+    afx_rans* fine = nullptr;
+    afx::DBuf<uint32_t> row_begin, col;
+    afx::DBuf<double> w;
+    cudaEvent_t ready = nullptr;
+    ~afx_prolongation() { if (ready) cudaEventDestroy(ready); }
+};
+
+int afx_prolongation_create(afx_prolongation** out, afx_rans* coarse, afx_rans* fine, const uint32_t* row_begin, const uint32_t* col, const double* w)
 {
-    if (!s || !st || (n_alpha > 0 && !alphas_deg)) { afx::set_error("null argument"); return AFX_ERR_INVALID; }
-    auto& S = s->s;
-    if (!S.bcs_set) { afx::set_error("set_bcs has not been called"); return AFX_ERR_INVALID; }
-    if (farfield_patch < 0 || farfield_patch >= (int)S.patch_kinds.size() || S.patch_kinds[(size_t)farfield_patch] != AFX_BC_FARFIELD) {
-        afx::set_error("farfield_patch is not a far-field patch of the last set_bcs");
-        return AFX_ERR_INVALID;
+    if (!out || !coarse || !fine || !row_begin || (!col && row_begin[fine->s.NT]) || (!w && row_begin[fine->s.NT])) { afx::set_error("null argument"); return AFX_ERR_INVALID; }
+    *out = nullptr;
+    afx_prolongation* p = nullptr;
+    const int rc = guard([&] {
+        auto& F = fine->s; auto& Cs = coarse->s;
+        if (F.device != Cs.device) throw afx::InvalidArg("both mesh levels must live on the same device");
+        if (F.halo || Cs.halo) throw afx::InvalidArg("the device-resident prolongation is for un-partitioned levels");
+        F.use();
+        const size_t nnz = row_begin[F.NT];
+        for (uint32_t r = 0; r < F.NT; ++r) if (row_begin[r] > row_begin[r + 1]) throw afx::InvalidArg("row_begin is not ascending");
+        for (size_t k = 0; k < nnz; ++k) if (col[k] >= Cs.NT) throw afx::InvalidArg("prolongation column outside the coarse mesh");
+        p = new afx_prolongation;
+        p->coarse = coarse; p->fine = fine;
+        p->row_begin.upload(std::vector<uint32_t>(row_begin, row_begin + F.NT + 1), F.st);
+        p->col.upload(nnz ? std::vector<uint32_t>(col, col + nnz) : std::vector<uint32_t>(1, 0u), F.st);
+        p->w.upload(nnz ? std::vector<double>(w, w + nnz) : std::vector<double>(1, 0.0), F.st);
+        CK(cudaEventCreateWithFlags(&p->ready, cudaEventDisableTiming));
+        CK(cudaStreamSynchronize(F.st));
+    });
+    if (rc) { delete p; return rc; }
+    *out = p;
+    return AFX_OK;
+}
+void afx_prolongation_free(afx_prolongation* p) { delete p; }
+
+int afx_prolongation_apply(afx_prolongation* p)
+{
+    if (!p) { afx::set_error("null argument"); return AFX_ERR_INVALID; }
+    return guard([&] {
+        auto& F = p->fine->s; auto& Cs = p->coarse->s;
+        F.use();
+        CK(cudaEventRecord(p->ready, Cs.st));          // the coarse state as of now (its stream's order)
+        CK(cudaStreamWaitEvent(F.st, p->ready, 0));
+        // always the strict kernels: the reference's sums in the reference's order, whatever mode the stage kernels run in
+        afx::strict::table().prolongate(F.NT, p->row_begin.p, p->col.p, p->w.p, F.perm_c_new2old.p, Cs.perm_c_old2new.p, Cs.q.p, F.q.p, F.st);
+        ++F.launches;
+        F.sync_ghost_rows();
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(F.st));
+        F.jac_valid = false;
+    });
+}
+
+namespace {
+// multigrid<T>::run_solver (multigrid.h:182-293) on one level; returns AFX_OK / AFX_ERR_NUMERIC (the reference's "return 1") / an error
+int run_level(afx_rans* s, const afx_sweep_settings* st, int* iters_out, double* err_out)
+{
+    int rc = AFX_OK;
+    double err_0 = 0, err = 0, cfl = st->start_cfl;
+    if ((rc = afx_rans_uniform_residual(s, &err_0)) != AFX_OK) return rc;
+    int i = 0;
+    do {
+        afx_rans_set_cfl(s, cfl);
+        if (st->implicit) {
+            if ((rc = afx_rans_fill_jacobian(s)) != AFX_OK) return rc;
+            rc = afx_rans_compute(s);
+            if (rc == AFX_OK) rc = afx_rans_step_implicit(s, st->relaxation, err_0 * st->tolerance, st->rhs_iterations, &err);
+        } else {
+            rc = afx_rans_step_explicit(s, st->relaxation, &err);
+        }
+        if (rc == AFX_ERR_NUMERIC) { if (iters_out) *iters_out = i + 1; if (err_out) *err_out = -1; return rc; }
+        if (rc != AFX_OK) return rc;
+        if (i == 0 && err > 2 * err_0) err_0 = err;
+        err /= err_0;
+        if (st->implicit) cfl = std::min(st->start_cfl + (i + 1) * st->slope_cfl, st->max_cfl);
+        ++i;
+    } while (err > st->tolerance && i < st->max_iterations);
+    if (iters_out) *iters_out = i;
+    if (err_out) *err_out = err;
+    return AFX_OK;
+}
+}  // namespace
+
+// Rans::run_airfoil (rans.h:78-106) over multigrid<T>::run(false) (multigrid.h:295-363): per angle the whole full-multigrid
+// start-up from the coarsest level, every level warm-started -- level 0 from its own state of the previous angle, level i > 0
+// from the prolongation of level i-1.  The states never leave the device.
+int afx_rans_sweep_fmg(afx_rans* const* levels, afx_prolongation* const* prolongations, int n_levels, const afx_sweep_settings* st,
+                       int farfield_patch, int wall_patch, const double* alphas_deg, int n_alpha, int reinit, double* cl, double* cd, double* cm,
+                       int* iterations, double* residual)
+{
+    if (!levels || n_levels < 1 || !st || (n_alpha > 0 && !alphas_deg) || (n_levels > 1 && !prolongations)) { afx::set_error("null argument"); return AFX_ERR_INVALID; }
+    for (int l = 0; l < n_levels; ++l) {
+        if (!levels[l]) { afx::set_error("null level"); return AFX_ERR_INVALID; }
+        auto& S = levels[l]->s;
+        if (!S.bcs_set) { afx::set_error("set_bcs has not been called"); return AFX_ERR_INVALID; }
+        if (farfield_patch < 0 || farfield_patch >= (int)S.patch_kinds.size() || S.patch_kinds[(size_t)farfield_patch] != AFX_BC_FARFIELD) {
+            afx::set_error("farfield_patch is not a far-field patch of the last set_bcs");
+            return AFX_ERR_INVALID;
+        }
+        if (l > 0 && (!prolongations[l - 1] || prolongations[l - 1]->coarse != levels[l - 1] || prolongations[l - 1]->fine != levels[l])) {
+            afx::set_error("prolongations[l-1] must map levels[l-1] to levels[l]");
+            return AFX_ERR_INVALID;
+        }
     }
     if (n_alpha <= 0) return AFX_OK;
     int rc = AFX_OK;
-    // rans.h:86-88: the first angle is in place when the field is initialised
-    auto apply_alpha = [&](double alpha_deg) {
+    auto apply_alpha = [&](afx_rans* s, double alpha_deg) {
+        auto& S = s->s;
         std::vector<uint8_t> kinds(S.patch_kinds);
         std::vector<afx_bvars> vars(S.patch_vars);
-        vars[(size_t)farfield_patch].angle = alpha_deg * 0.01745;
+        vars[(size_t)farfield_patch].angle = alpha_deg * 0.01745;  // rans.h:94
         return afx_rans_set_bcs(s, (int)kinds.size(), kinds.data(), vars.data());
     };
-    if ((rc = apply_alpha(alphas_deg[0])) != AFX_OK) return rc;
-    if (reinit && (rc = afx_rans_init(s)) != AFX_OK) return rc;
+    // rans.h:86-88: the first angle is in place when the coarsest field is initialised
+    if ((rc = apply_alpha(levels[0], alphas_deg[0])) != AFX_OK) return rc;
+    if (reinit && (rc = afx_rans_init(levels[0])) != AFX_OK) return rc;
     for (int a = 0; a < n_alpha; ++a) {
-        if ((rc = apply_alpha(alphas_deg[a])) != AFX_OK) return rc;            // rans.h:94-97
-        if ((rc = afx_rans_refill_bcs(s)) != AFX_OK) return rc;                // multigrid.h:303
-        double err_0 = 0, err = 0, cfl = st->start_cfl;
-        if ((rc = afx_rans_uniform_residual(s, &err_0)) != AFX_OK) return rc;
-        int i = 0;
-        do {                                                                   // multigrid.h:190-236 / 247-292
-            afx_rans_set_cfl(s, cfl);
-            if (st->implicit) {
-                if ((rc = afx_rans_fill_jacobian(s)) != AFX_OK) return rc;
-                rc = afx_rans_compute(s);
-                if (rc == AFX_OK) rc = afx_rans_step_implicit(s, st->relaxation, err_0 * st->tolerance, st->rhs_iterations, &err);
-            } else {
-                rc = afx_rans_step_explicit(s, st->relaxation, &err);
+        for (int l = 0; l < n_levels; ++l) if ((rc = apply_alpha(levels[l], alphas_deg[a])) != AFX_OK) return rc;  // rans.h:94-97
+        if ((rc = afx_rans_refill_bcs(levels[0])) != AFX_OK) return rc;                                              // multigrid.h:303
+        int it_total = 0, it = 0;
+        double err = 0;
+        afx_rans* last = levels[0];
+        for (int l = 0; l < n_levels; ++l) {
+            if (l > 0) {  // multigrid.h:306-311 / 339-344
+                if ((rc = afx_rans_bcs_from_internal(levels[l - 1])) != AFX_OK) return rc;
+                if ((rc = afx_prolongation_apply(prolongations[l - 1])) != AFX_OK) return rc;
+                if ((rc = afx_rans_refill_bcs(levels[l])) != AFX_OK) return rc;
             }
-            if (rc == AFX_ERR_NUMERIC) { if (iterations) iterations[a] = i + 1; if (residual) residual[a] = -1; return rc; }
+            last = levels[l];
+            rc = run_level(levels[l], st, &it, &err);
+            it_total += it;
+            if (rc == AFX_ERR_NUMERIC) break;  // multigrid.h:313/355: the run ends on this level
             if (rc != AFX_OK) return rc;
-            if (i == 0 && err > 2 * err_0) err_0 = err;
-            err /= err_0;
-            if (st->implicit) cfl = std::min(st->start_cfl + (i + 1) * st->slope_cfl, st->max_cfl);
-            ++i;
-        } while (err > st->tolerance && i < st->max_iterations);
+        }
+        if (iterations) iterations[a] = it_total;
+        if (residual) residual[a] = err;
+        if (rc == AFX_ERR_NUMERIC) return rc;
         double f[3];
-        if ((rc = afx_rans_wall_forces(s, wall_patch, f)) != AFX_OK) return rc;  // rans.h:99-102
+        if ((rc = afx_rans_wall_forces(last, wall_patch, f)) != AFX_OK) return rc;  // rans.h:99-102
         if (cl) cl[a] = f[0];
         if (cd) cd[a] = f[1];
         if (cm) cm[a] = f[2];
-        if (iterations) iterations[a] = i;
-        if (residual) residual[a] = err;
     }
     return AFX_OK;
+}
+
+int afx_rans_sweep(afx_rans* s, const afx_sweep_settings* st, int farfield_patch, int wall_patch, const double* alphas_deg, int n_alpha,
+                   int reinit, double* cl, double* cd, double* cm, int* iterations, double* residual)
+{
+    if (!s) { afx::set_error("null argument"); return AFX_ERR_INVALID; }
+    afx_rans* one[1] = {s};
+    return afx_rans_sweep_fmg(one, nullptr, 1, st, farfield_patch, wall_patch, alphas_deg, n_alpha, reinit, cl, cd, cm, iterations, residual);
 }
 
 int afx_rans_last_device_ms(afx_rans* s, double* ms)

@@ -200,6 +200,8 @@ struct KernelTable {
     void (*jacobian)(int visc, const DevMesh& m, const d4* q, const d4* gx, const d4* gy, d4* J, const GasC& g, cudaStream_t st);
     void (*jac_diag)(const DevMesh& m, const d4* J, const double* dt, double* D, cudaStream_t st);
     void (*wall_forces)(const WallArgs& a, const DevMesh& m, const d4* q, cudaStream_t st);
+    void (*prolongate)(uint32_t n_fine, const uint32_t* row_begin, const uint32_t* col, const double* w, const uint32_t* fine_new2old,
+                       const uint32_t* coarse_old2new, const d4* qc, d4* qf, cudaStream_t st);
     void (*fill_cells)(d4* q, uint32_t n, d4 v, cudaStream_t st);
     void (*ghost_fill)(d4* q, const uint32_t* bghost, const uint32_t* bowner, const d4* bstate, uint32_t G, int from_owner, cudaStream_t st);
     void (*ghost_follow)(d4* q, const uint32_t* bghost, const uint32_t* bowner, const uint32_t* bface, const uint8_t* fkind, uint32_t G, uint32_t lo,

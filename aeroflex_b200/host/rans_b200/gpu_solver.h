@@ -61,12 +61,14 @@ public:
     // like the reference (solver.h:112-116): a copy is a fresh solver on the same mesh with the same bcs, not a state copy
     solver(const solver& s) : solver(s.get_cmesh(), s.get_gas(), s.get_viscosity_model(), s.device_) {
         bcs = s.get_bcs(); print_interval = s.get_print_interval(); second_order = s.second_order;
+        push_options();  // the fresh device solver starts from its defaults: hand it the copied second_order (as solver.h:112-116 copies it)
     }
     solver& operator=(const solver& rhs) {
         if (this == &rhs) return *this;
         g = rhs.g; m = rhs.m; viscosity_model = rhs.viscosity_model; device_ = rhs.device_;
         create();
         bcs = rhs.bcs; print_interval = rhs.print_interval; second_order = rhs.second_order;
+        push_options();
         return *this;
     }
     virtual ~solver() {}
@@ -135,7 +137,7 @@ public:
 class explicitSolver : public solver {  // solver.h:721-742
 public:
     explicitSolver(const mesh& m_in, const gas& g_in, std::string viscosity_model_, int device = -1) : solver(m_in, g_in, viscosity_model_, device) {}
-    explicitSolver(const explicitSolver& s) : explicitSolver(s.get_cmesh(), s.get_gas(), s.get_viscosity_model(), s.device_) {}
+    explicitSolver(const explicitSolver& s) : solver(s) {}  // the reference's implicit copy: solver's copy constructor (fresh state, same bcs / order)
     void fill() override {}
     int compute() override { return 0; }
     double solve(const double relaxation = 1, const double = 0, const int = 5) override {  // solver.h:802-828
@@ -157,7 +159,7 @@ public:
 class implicitSolver : public solver {  // solver.h:852-970
 public:
     implicitSolver(const mesh& m_in, const gas& g_in, std::string viscosity_model_, int device = -1) : solver(m_in, g_in, viscosity_model_, device) {}
-    implicitSolver(const implicitSolver& s) : implicitSolver(s.get_cmesh(), s.get_gas(), s.get_viscosity_model(), s.device_) {}
+    implicitSolver(const implicitSolver& s) : solver(s) {}
     void fill() override { check(afx_rans_fill_jacobian(h_.get())); }  // fillRhoLHS, solver.h:973-976
     int compute() override {                                            // solver.h:1160-1167
         const int rc = afx_rans_compute(h_.get());

@@ -8,6 +8,7 @@
 #include <chrono>
 #include <cmath>
 #include <iostream>
+#include <memory>
 #include <thread>
 
 #include "common.h"
@@ -169,6 +170,9 @@ public:
     CpProfile& profile;
     std::vector<solverType> solvers;
     std::vector<Prolongation> mappers;
+    // the same mappers resident on the GPU: level i -> i+1 without the state leaving the device (afx_prolongation_*)
+    struct ProlDeleter { void operator()(afx_prolongation* p) const { afx_prolongation_free(p); } };
+    std::vector<std::unique_ptr<afx_prolongation, ProlDeleter>> device_mappers;
     bool verbose = true;
 
     multigrid(std::vector<mesh> ms, Settings& settings, GUIHandler& gui, std::vector<double>& residuals, std::atomic<int>& iters,
@@ -188,6 +192,13 @@ public:
             mappers.resize(ms.size() - 1);
             for (uint i = 0; i < ms.size() - 1; ++i) {
                 mappers[i] = gen_mapper(i);
+                std::vector<uint32_t> row_begin(mappers[i].rows.size() + 1, 0u);
+                for (size_t r = 0; r < mappers[i].rows.size(); ++r) row_begin[r + 1] = mappers[i].rows[r].end;
+                afx_prolongation* dp = nullptr;
+                if (afx_prolongation_create(&dp, solvers[i].handle(), solvers[i + 1].handle(), row_begin.data(), mappers[i].col.data(),
+                                            mappers[i].w.data()) != AFX_OK)
+                    throw std::runtime_error(afx_last_error());
+                device_mappers.emplace_back(dp);
                 gui.msg.push("[RANS] Matrix " + std::to_string(i + 1) + " done");
             }
         }
@@ -268,7 +279,9 @@ inline solverType& multigrid<solverType>::run(const bool reinit) {
         if (verbose) std::cout << "\nMultigrid : Stage " << i + 1 << "/" << solvers.size() << "\n" << std::endl;
         if (i > 0) {  // map the last solution to the current grid
             solvers[i - 1].bcs_from_internal();
-            solvers[i].set_q(mappers[i - 1].apply(solvers[i - 1].get_q()));
+            if (i - 1 < device_mappers.size()) {  // q_fine = mapper * q_coarse on the device, the reference's sums in the reference's order
+                if (afx_prolongation_apply(device_mappers[i - 1].get()) != AFX_OK) throw std::runtime_error(afx_last_error());
+            } else solvers[i].set_q(mappers[i - 1].apply(solvers[i - 1].get_q()));
             solvers[i].refill_bcs();
         }
         const int state = run_solver(solvers[i]);

@@ -297,6 +297,25 @@ typedef struct afx_sweep_settings {
 int afx_rans_sweep(afx_rans* s, const afx_sweep_settings* settings, int farfield_patch, int wall_patch, const double* alphas_deg,
                    int n_alpha, int reinit, double* cl, double* cd, double* cm, int* iterations, double* residual);
 
+/* FMG prolongation between two mesh levels ON THE DEVICE (replaces `solvers[i].get_q() = mappers[i-1] * solvers[i-1].get_q()`,
+ * multigrid.h:308,341; the weights are those of multigrid::gen_mapper, multigrid.h:100-178).  CSR with one weight per
+ * (fine cell, coarse cell) pair: row r = fine cell r in the fine mesh's reference order (ghost rows included, n_fine_cells +
+ * n_fine_ghosts rows), col = coarse cell in the coarse mesh's reference order, columns ascending inside a row.  apply()
+ * overwrites the fine solver's state with P q_coarse, summed in column order (the reference's bits); both solvers on one
+ * device, neither partitioned. */
+typedef struct afx_prolongation afx_prolongation;
+int afx_prolongation_create(afx_prolongation** out, afx_rans* coarse, afx_rans* fine, const uint32_t* row_begin, const uint32_t* col,
+                            const double* w);
+void afx_prolongation_free(afx_prolongation* p);
+int afx_prolongation_apply(afx_prolongation* p);
+/* The whole of Rans::run_airfoil (rans.h:78-106): per angle, multigrid<T>::run(false) (multigrid.h:295-363) over `n_levels`
+ * mesh levels -- level 0 warm-started from its own state of the previous angle, level l from prolongations[l-1] applied to
+ * level l-1 after bcs_from_internal -- each level iterated by run_solver as in afx_rans_sweep; forces from the last level run.
+ * iterations[a] = iterations summed over the levels.  States never leave the device.  levels[l]: set_bcs and set_options done. */
+int afx_rans_sweep_fmg(afx_rans* const* levels, afx_prolongation* const* prolongations, int n_levels, const afx_sweep_settings* settings,
+                       int farfield_patch, int wall_patch, const double* alphas_deg, int n_alpha, int reinit, double* cl, double* cd,
+                       double* cm, int* iterations, double* residual);
+
 int afx_rans_last_device_ms(afx_rans* s, double* ms);
 /* kernels launched by this handle since creation (bench.py's gpu_launches) */
 int64_t afx_rans_launch_count(afx_rans* s);
