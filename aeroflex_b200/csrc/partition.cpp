@@ -63,7 +63,22 @@ void Partition::build(const afx_mesh_desc& g, int nranks_, int rank_)
         throw std::invalid_argument("AFX_PARTITION must be hilbert or graph");
     } else {
         order = hilbert_order(g.cells_cx, g.cells_cy, all);
-        for (int r = 0; r <= nranks; ++r) cut[r] = (uint32_t)((uint64_t)r * N / nranks);
+        // Cut by WORK, not by cell count: the face kernel's time goes with the faces, and a quadrilateral carries 4/2 of them
+        // against a triangle's 3/2.  With the per-cell and per-face times measured on one B200 at 16M cells (0.231 ns per cell
+        // and iteration in the cell kernels, 0.0876 ns per face in the face kernel) a quad costs 1.12 triangles; on the 16M
+        // O-mesh an all-quad piece of equal cell count ran 9 % longer than the average piece, and every stage ends with a
+        // halo hand-off that waits for the slowest neighbour.  AFX_PARTITION_QUAD_WEIGHT overrides (percent; 100 = by cells).
+        uint64_t wq = 112;
+        if (const char* e = getenv("AFX_PARTITION_QUAD_WEIGHT")) wq = (uint64_t)std::max(1, atoi(e));
+        std::vector<uint64_t> pre(N + 1, 0);
+        for (uint32_t k = 0; k < N; ++k) pre[k + 1] = pre[k] + (g.cells_is_tri[order[k]] ? 100u : wq);
+        cut[0] = 0; cut[nranks] = N;
+        for (int r = 1; r < nranks; ++r) {
+            const uint64_t want = pre[N] / (uint64_t)nranks * (uint64_t)r + pre[N] % (uint64_t)nranks * (uint64_t)r / (uint64_t)nranks;
+            uint32_t c = (uint32_t)(std::lower_bound(pre.begin(), pre.end(), want) - pre.begin());
+            c = std::max<uint32_t>(c, cut[r - 1] + 1);                       // every rank owns at least one cell
+            cut[r] = std::min<uint32_t>(c, N - (uint32_t)(nranks - r));
+        }
     }
     std::vector<uint32_t> pos(N);
     for (uint32_t k = 0; k < N; ++k) pos[order[k]] = k;

@@ -54,9 +54,14 @@ __global__ void __launch_bounds__(256) k_spmv(DevMesh m, const d4* __restrict__ 
 }
 
 // block-Jacobi sweep: first ? z = Dinv r : z_out = z_in + Dinv (r - A z_in)
+// `stop` (may be null): the device-side flag of the Krylov iteration.  Once k_givens_step has seen the linear residual reach the
+// tolerance, the kernels of the steps the host has already queued behind it return at once: the host looks at the iteration
+// once per batch of steps, not once per step.
 __global__ void __launch_bounds__(256) k_jacobi_sweep(DevMesh m, const d4* __restrict__ J, const d4* __restrict__ D, const d4* __restrict__ Dinv,
-                                                      const d4* __restrict__ r, const d4* __restrict__ z_in, d4* __restrict__ z_out, int first)
+                                                      const d4* __restrict__ r, const d4* __restrict__ z_in, d4* __restrict__ z_out, int first,
+                                                      const int* __restrict__ stop)
 {
+    if (stop && *stop) return;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m.NT) return;
     const d4 ri = r[i];
@@ -169,8 +174,9 @@ __device__ __forceinline__ void dot_finish_by_last_block(int k, const double* pa
 
 // multi_dot in one launch
 __global__ void __launch_bounds__(256) k_multi_dot(uint32_t n, const d4* __restrict__ V, size_t stride, int k, const d4* __restrict__ w,
-                                                   double* partial, double* out, unsigned int* counter)
+                                                   double* partial, double* out, unsigned int* counter, const int* __restrict__ stop)
 {
+    if (stop && *stop) return;
     for (int j = 0; j < k; ++j) {
         const d4* __restrict__ vj = V + (size_t)j * stride;
         double acc = 0;
@@ -187,8 +193,9 @@ __global__ void __launch_bounds__(256) k_multi_dot(uint32_t n, const d4* __restr
 // w -= sum_j c[j] V_j followed by ||w||^2 -> out[0], one launch (classical Gram-Schmidt step + the norm of the result):
 // the update is k_multi_axpy's arithmetic per cell, the norm k_multi_dot's (same grid-stride partition, same trees)
 __global__ void __launch_bounds__(256) k_axpy_norm(uint32_t n, const d4* __restrict__ V, size_t stride, int k, const double* __restrict__ c,
-                                                   double sign, d4* w, double* partial, double* out, unsigned int* counter)
+                                                   double sign, d4* w, double* partial, double* out, unsigned int* counter, const int* __restrict__ stop)
 {
+    if (stop && *stop) return;
     double acc = 0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         d4 a = w[i];
@@ -207,8 +214,9 @@ __global__ void __launch_bounds__(256) k_axpy_norm(uint32_t n, const d4* __restr
 
 // r = A x and z = Dinv r (the first block-Jacobi sweep from a zero start) in one launch: k_spmv + k_jacobi_sweep(first)
 __global__ void __launch_bounds__(256) k_spmv_sweep0(DevMesh m, const d4* __restrict__ J, const d4* __restrict__ D, const d4* __restrict__ Dinv,
-                                                     const d4* __restrict__ x, d4* __restrict__ r, d4* __restrict__ z)
+                                                     const d4* __restrict__ x, d4* __restrict__ r, d4* __restrict__ z, const int* __restrict__ stop)
 {
+    if (stop && *stop) return;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m.NT) return;
     const d4 ri = row_Ax(m, J, D, x, i);
@@ -230,8 +238,10 @@ __global__ void __launch_bounds__(256) k_multi_axpy(uint32_t n, const d4* __rest
     w[i] = a;
 }
 // y = x * (inv ? 1/s[0] : s[0]) with the scalar taken from device memory (sqrt applied first if root)
-__global__ void __launch_bounds__(256) k_scale_from(uint32_t n, const d4* __restrict__ x, const double* __restrict__ s, int root, int inv, d4* __restrict__ y)
+__global__ void __launch_bounds__(256) k_scale_from(uint32_t n, const d4* __restrict__ x, const double* __restrict__ s, int root, int inv, d4* __restrict__ y,
+                                                    const int* __restrict__ stop)
 {
+    if (stop && *stop) return;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double f = s[0];
@@ -259,16 +269,85 @@ __global__ void __launch_bounds__(256) k_axpy_state(uint32_t n, double relax, co
     q[i] = b;
 }
 
+// ---- the small dense part of GMRES on the device --------------------------------------------------------------------
+// state (doubles): H[(m+1) x m] row-major | cs[m] | sn[m] | g[m+1] | y[m] | r0, err, k_done, stop, fail   (GmresLayout)
+struct GmresLayout {
+    int m;
+    __host__ __device__ int H() const { return 0; }
+    __host__ __device__ int cs() const { return (m + 1) * m; }
+    __host__ __device__ int sn() const { return cs() + m; }
+    __host__ __device__ int g() const { return sn() + m; }
+    __host__ __device__ int y() const { return g() + m + 1; }
+    __host__ __device__ int r0() const { return y() + m; }
+    __host__ __device__ int err() const { return r0() + 1; }
+    __host__ __device__ int k_done() const { return r0() + 2; }
+    __host__ __device__ int fail() const { return r0() + 3; }
+    __host__ __device__ int total() const { return r0() + 4; }
+};
+// start of a cycle: g = (beta, 0, ...), k_done = 0; *stop = 0.  beta2 holds beta^2 (device); first: it is also r0^2.
+__global__ void k_gmres_begin(GmresLayout L, double* st, const double* __restrict__ beta2, int first, int* stop)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const double beta = sqrt(beta2[0]);
+    for (int i = 0; i <= L.m; ++i) st[L.g() + i] = 0.0;
+    st[L.g()] = beta;
+    if (first) { st[L.r0()] = beta; st[L.fail()] = (beta == beta) ? 0.0 : 1.0; }
+    st[L.k_done()] = 0.0;
+    st[L.err()] = (st[L.r0()] > 0) ? beta / st[L.r0()] : 0.0;
+    *stop = (!(beta == beta) || beta == 0.0) ? 1 : 0;
+}
+// Arnoldi step k is done (h[0..k] = V^T w, h[k+1] = ||w||^2 after orthogonalisation): new Hessenberg column, the earlier
+// rotations, the new rotation, the residual estimate |g[k+1]| / r0 -- the recurrence Solver::gmres ran on the host.
+__global__ void k_givens_step(GmresLayout L, double* st, const double* __restrict__ h, int k, double tol, int* stop)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0 || *stop) return;
+    const int m = L.m;
+    double* H = st + L.H(); double* cs = st + L.cs(); double* sn = st + L.sn(); double* g = st + L.g();
+    const double hn = sqrt(h[k + 1]);
+    for (int i = 0; i <= k; ++i) H[i * m + k] = h[i];
+    for (int i = 0; i < k; ++i) {
+        const double a = H[i * m + k], c = H[(i + 1) * m + k];
+        H[i * m + k] = cs[i] * a + sn[i] * c;
+        H[(i + 1) * m + k] = -sn[i] * a + cs[i] * c;
+    }
+    const double a = H[k * m + k], den = sqrt(a * a + hn * hn);
+    if (!(den == den)) { st[L.fail()] = 1.0; *stop = 1; return; }
+    cs[k] = den == 0 ? 1 : a / den; sn[k] = den == 0 ? 0 : hn / den;
+    H[k * m + k] = den;
+    g[k + 1] = -sn[k] * g[k]; g[k] = cs[k] * g[k];
+    const double err = fabs(g[k + 1]) / st[L.r0()];
+    st[L.err()] = err;
+    st[L.k_done()] = (double)(k + 1);
+    if (err < tol || hn == 0) *stop = 1;
+}
+// H y = g for the k columns done (back substitution), y -> out[0..k)
+__global__ void k_gmres_solve_y(GmresLayout L, const double* __restrict__ st, double* __restrict__ out)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int m = L.m, k = (int)st[L.k_done()];
+    const double* H = st + L.H(); const double* g = st + L.g();
+    for (int i = k - 1; i >= 0; --i) {
+        double s = g[i];
+        for (int j = i + 1; j < k; ++j) s -= H[i * m + j] * out[j];
+        out[i] = s / H[i * m + i];
+    }
+}
+
 namespace launch {
+
+static void gmres_begin(int m, double* st, const double* beta2, int first, int* stop, cudaStream_t s_) { k_gmres_begin<<<1, 32, 0, s_>>>(GmresLayout{m}, st, beta2, first, stop); }
+static void givens_step(int m, double* st, const double* h, int k, double tol, int* stop, cudaStream_t s_) { k_givens_step<<<1, 32, 0, s_>>>(GmresLayout{m}, st, h, k, tol, stop); }
+static void gmres_solve_y(int m, const double* st, double* out, cudaStream_t s_) { k_gmres_solve_y<<<1, 32, 0, s_>>>(GmresLayout{m}, st, out); }
+static int gmres_state_doubles(int m) { return GmresLayout{m}.total(); }
 
 static void spmv(const DevMesh& m, const d4* J, const double* D, const d4* x, d4* y, cudaStream_t st)
 {
     k_spmv<<<(m.NT + 255) / 256, 256, 0, st>>>(m, J, reinterpret_cast<const d4*>(D), x, y);
 }
 static void jacobi_sweep(const DevMesh& m, const d4* J, const double* D, const double* Dinv, const d4* r, const d4* z_in, d4* z_out, int first,
-                         cudaStream_t st)
+                         const int* stop, cudaStream_t st)
 {
-    k_jacobi_sweep<<<(m.NT + 255) / 256, 256, 0, st>>>(m, J, reinterpret_cast<const d4*>(D), reinterpret_cast<const d4*>(Dinv), r, z_in, z_out, first);
+    k_jacobi_sweep<<<(m.NT + 255) / 256, 256, 0, st>>>(m, J, reinterpret_cast<const d4*>(D), reinterpret_cast<const d4*>(Dinv), r, z_in, z_out, first, stop);
 }
 static void invert_blocks(uint32_t n, const double* D, double* Dinv, int* singular, cudaStream_t st)
 {
@@ -280,26 +359,27 @@ static void multi_dot(uint32_t n, const d4* V, size_t stride, int k, const d4* w
     k_multi_dot_final<<<k, 256, 0, st>>>(KRY_BLOCKS, partial, out);
 }
 // one-launch forms (counter: a zeroed device word, reset by the kernel)
-static void multi_dot1(uint32_t n, const d4* V, size_t stride, int k, const d4* w, double* partial, double* out, unsigned int* counter, cudaStream_t st)
+static void multi_dot1(uint32_t n, const d4* V, size_t stride, int k, const d4* w, double* partial, double* out, unsigned int* counter, const int* stop,
+                       cudaStream_t st)
 {
-    k_multi_dot<<<KRY_BLOCKS, 256, 0, st>>>(n, V, stride, k, w, partial, out, counter);
+    k_multi_dot<<<KRY_BLOCKS, 256, 0, st>>>(n, V, stride, k, w, partial, out, counter, stop);
 }
 static void axpy_norm(uint32_t n, const d4* V, size_t stride, int k, const double* c, double sign, d4* w, double* partial, double* out,
-                      unsigned int* counter, cudaStream_t st)
+                      unsigned int* counter, const int* stop, cudaStream_t st)
 {
-    k_axpy_norm<<<KRY_BLOCKS, 256, 0, st>>>(n, V, stride, k, c, sign, w, partial, out, counter);
+    k_axpy_norm<<<KRY_BLOCKS, 256, 0, st>>>(n, V, stride, k, c, sign, w, partial, out, counter, stop);
 }
-static void spmv_sweep0(const DevMesh& m, const d4* J, const double* D, const double* Dinv, const d4* x, d4* r, d4* z, cudaStream_t st)
+static void spmv_sweep0(const DevMesh& m, const d4* J, const double* D, const double* Dinv, const d4* x, d4* r, d4* z, const int* stop, cudaStream_t st)
 {
-    k_spmv_sweep0<<<(m.NT + 255) / 256, 256, 0, st>>>(m, J, reinterpret_cast<const d4*>(D), reinterpret_cast<const d4*>(Dinv), x, r, z);
+    k_spmv_sweep0<<<(m.NT + 255) / 256, 256, 0, st>>>(m, J, reinterpret_cast<const d4*>(D), reinterpret_cast<const d4*>(Dinv), x, r, z, stop);
 }
 static void multi_axpy(uint32_t n, const d4* V, size_t stride, int k, const double* c, double sign, d4* w, cudaStream_t st)
 {
     k_multi_axpy<<<(n + 255) / 256, 256, 0, st>>>(n, V, stride, k, c, sign, w);
 }
-static void scale_from(uint32_t n, const d4* x, const double* s, int root, int inv, d4* y, cudaStream_t st)
+static void scale_from(uint32_t n, const d4* x, const double* s, int root, int inv, d4* y, const int* stop, cudaStream_t st)
 {
-    k_scale_from<<<(n + 255) / 256, 256, 0, st>>>(n, x, s, root, inv, y);
+    k_scale_from<<<(n + 255) / 256, 256, 0, st>>>(n, x, s, root, inv, y, stop);
 }
 static void sub(uint32_t n, const d4* a, const d4* b, d4* y, cudaStream_t st) { k_sub<<<(n + 255) / 256, 256, 0, st>>>(n, a, b, y); }
 static void axpy_state(uint32_t n, double relax, const d4* x, d4* q, cudaStream_t st) { k_axpy_state<<<(n + 255) / 256, 256, 0, st>>>(n, relax, x, q); }

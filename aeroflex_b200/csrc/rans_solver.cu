@@ -248,14 +248,15 @@ struct Solver {
     DBuf<double> dt, dt_ref;
     DBuf<d4> J; DBuf<double> D;   // Jacobian face blocks [E][16] d4 and diagonal blocks [NT][16]
     // implicit step: block-Jacobi preconditioned restarted GMRES on the device
-    DBuf<double> Dinv, kry_partial, kry_h; DBuf<d4> kry_V, kry_w, kry_z, kry_t, kry_x; DBuf<int> kry_flag; DBuf<unsigned int> kry_counter;
+    DBuf<double> Dinv, kry_partial, kry_h, kry_state; DBuf<d4> kry_V, kry_w, kry_z, kry_t, kry_x; DBuf<int> kry_flag; DBuf<unsigned int> kry_counter;
     int gmres_restart = 30, gmres_max_iter = 500, precond_sweeps = 4;
     double gmres_tol = 1e-2;
     int last_linear_iters = 0;
     bool precond_valid = false;
     int compute_preconditioner();
     void apply_preconditioner(const d4* r, d4* z);
-    void precondition_Ax(const d4* x, d4* r_buf, d4* z);
+    void precondition_Ax(const d4* x, d4* r_buf, d4* z, const int* stop = nullptr);
+    struct GmresView { int m; int r0() const { return (m + 1) * m + 2 * m + (m + 1) + m; } };  // offset of {r0, err, k_done, fail} in kry_state (GmresLayout, rans_krylov.cuh)
     // partitioned implicit step: inner products run over the owned rows and are summed over the ranks; a vector whose
     // neighbour rows are about to be read (matrix-vector product, Jacobi sweep) gets its halo rows from their owners first
     uint32_t n_dot() const { return halo ? n_upd : NT; }
@@ -318,6 +319,8 @@ struct Solver {
     size_t p2p_export(void* blob);
     void p2p_connect(const void* blobs, size_t blob_size, int nranks);
     void exchange(d4* field, cudaStream_t stream);
+    int prof_stage = -1;  // >= 0 while afx_rans_profile_explicit runs stage `prof_stage`: the halo hand-off is bracketed by evp[8 + 2 s], evp[9 + 2 s]
+    void prof_mark(int which) { if (prof_stage >= 0 && prof_stage < 3) CK(cudaEventRecord(evp[8 + 2 * prof_stage + which], st)); }
     bool halo_pending = false;
     bool halo_overlap = false;  // AFX_HALO_OVERLAP=1: exchange on a second stream under the interior update (needed for the NCCL halo)
     void ensure_halo() { if (halo_pending) { CK(cudaStreamWaitEvent(st, ev_halo, 0)); halo_pending = false; } }
@@ -773,14 +776,18 @@ void Solver::launch_gather(const d4* qk_in, d4* qk_out, d4* vec_out, double alph
             pa.early_signal = 1;
             pa.n_front_blocks = kt->gather_blocks(n_front);
             kt->gather(MODE, LAST, dm, 0, n_upd, flux.p, q.p, qk_in, qk_out, dt.p, vec_out, alpha, prm.p, walls ? 1 : 0, norm_out(), &pa, st);
+            prof_mark(0);
             halo_rendezvous(st); kt->halo_wait_scatter(halo->wait, qk_out, st);
+            prof_mark(1);
             launches += 2;
             finish(kt->gather_blocks(n_upd));
             return;
         }
         kt->gather(MODE, LAST, dm, 0, n_upd, flux.p, q.p, qk_in, qk_out, dt.p, vec_out, alpha, prm.p, walls ? 1 : 0, norm_out(), &halo->push, st);
+        prof_mark(0);
         kt->halo_signal(halo->sig, st);
         halo_rendezvous(st); kt->halo_wait_scatter(halo->wait, qk_out, st);
+        prof_mark(1);
         launches += 3;
         finish(kt->gather_blocks(n_upd));
         return;
@@ -1250,7 +1257,10 @@ void Solver::p2p_connect(const void* blobs, size_t blob_size, int nranks)
     h.push.early_signal = 0; h.push.n_front_blocks = 0; h.push.front_done = h.front_done.p; h.push.epoch_rw = h.epoch.p;
     h.push.n_peers = (int)h.peers.size();
     for (size_t k = 0; k < h.peers.size(); ++k) h.push.peer_flag[k] = h.sig.peer_flag[k];
-    if (const char* e = getenv("AFX_HALO_EARLY_SIGNAL")) h.early_signal = (e[0] == '1');
+    // default since round 2 (measured on 8 B200s, 16M cells: 0.929 against 0.941 ms per iteration; bit-identical at 2 / 4 / 8 ranks on
+    // hardware): the last send-layer CTA of the update kernel raises the peers' flags itself.  AFX_HALO_EARLY_SIGNAL=0: separate launch.
+    h.early_signal = true;
+    if (const char* e = getenv("AFX_HALO_EARLY_SIGNAL")) h.early_signal = (e[0] != '0');
     h.p2p = true;  // every rank can: the single-launch path works for any front size (an all-front or empty send layer included)
     invalidate_graph();
 }
@@ -1449,7 +1459,8 @@ int Solver::compute_preconditioner()
     use();
     if (!jac_valid) throw InvalidArg("afx_rans_fill_jacobian has not been called for the current state");
     if (!Dinv.p) {
-        Dinv.alloc((size_t)NT * 16); kry_flag.alloc(1);
+        Dinv.alloc((size_t)NT * 16); kry_flag.alloc(2);  // [0] singular diagonal block, [1] the Krylov iteration's stop flag
+        kry_state.alloc((size_t)kt->gmres_state_doubles(gmres_restart)); kry_state.zero(st);
         kry_V.alloc((size_t)(gmres_restart + 1) * NT); kry_w.alloc(NT); kry_z.alloc(NT); kry_t.alloc(NT); kry_x.alloc(NT);
         kry_partial.alloc((size_t)(gmres_restart + 2) * 1024); kry_h.alloc(gmres_restart + 4);
         kry_counter.alloc(1); kry_counter.zero(st);
@@ -1471,26 +1482,26 @@ void Solver::apply_preconditioner(const d4* r, d4* z)
     // an even number of swaps must leave the result in z
     const int sweeps = std::max(1, precond_sweeps);
     if ((sweeps - 1) % 2) std::swap(a, b);
-    kt->jacobi_sweep(dm, J.p, D.p, Dinv.p, r, nullptr, a, 1, st);
+    kt->jacobi_sweep(dm, J.p, D.p, Dinv.p, r, nullptr, a, 1, nullptr, st);
     ++launches;
     for (int k = 1; k < sweeps; ++k) {
         halo_refresh(a);
-        kt->jacobi_sweep(dm, J.p, D.p, Dinv.p, r, a, b, 0, st);
+        kt->jacobi_sweep(dm, J.p, D.p, Dinv.p, r, a, b, 0, nullptr, st);
         ++launches;
         std::swap(a, b);
     }
 }
 
-void Solver::precondition_Ax(const d4* x, d4* r_buf, d4* z)
+void Solver::precondition_Ax(const d4* x, d4* r_buf, d4* z, const int* stop)
 {
     d4* a = z; d4* b = kry_t.p;
     const int sweeps = std::max(1, precond_sweeps);
     if ((sweeps - 1) % 2) std::swap(a, b);
-    kt->spmv_sweep0(dm, J.p, D.p, Dinv.p, x, r_buf, a, st);  // the caller keeps the halo rows of x current
+    kt->spmv_sweep0(dm, J.p, D.p, Dinv.p, x, r_buf, a, stop, st);  // the caller keeps the halo rows of x current
     ++launches;
     for (int k = 1; k < sweeps; ++k) {
         halo_refresh(a);
-        kt->jacobi_sweep(dm, J.p, D.p, Dinv.p, r_buf, a, b, 0, st);
+        kt->jacobi_sweep(dm, J.p, D.p, Dinv.p, r_buf, a, b, 0, stop, st);
         ++launches;
         std::swap(a, b);
     }
@@ -1498,88 +1509,84 @@ void Solver::precondition_Ax(const d4* x, d4* r_buf, d4* z)
 
 // Left-preconditioned restarted GMRES, zero initial guess, stop on ||M^-1 (b - A x)|| <= tol ||M^-1 b||
 // (the criterion of Eigen::GMRES used at solver.h:886,906-910).  Arnoldi by classical Gram-Schmidt with all
-// inner products of a step in one reduction; the Givens recurrence runs on the host (one small D2H per step).
+// inner products of a step in one reduction.  The small dense part -- Hessenberg column, Givens rotations, residual
+// estimate, back substitution -- runs on the device too (k_givens_step / k_gmres_solve_y): the host queues the Arnoldi steps
+// in batches and looks at the iteration once per batch; the steps queued behind the one that reached the tolerance see
+// the device-side stop flag and return at once.  (Round 1 synchronised with the host after every step.)
 bool Solver::gmres(const d4* b, d4* x)
 {
     NvtxRange nvtx_("afx:gmres");
     const int m = gmres_restart;
     const size_t stride = NT;
-    std::vector<double> hbuf((size_t)m + 4);
+    const GmresView L{m};
     CK(cudaMemsetAsync(x, 0, (size_t)NT * sizeof(d4), st));
     last_linear_iters = 0;
+    int batch = 6;
+    if (const char* e = getenv("AFX_GMRES_BATCH")) batch = std::max(1, atoi(e));
     // r = M^-1 b
     d4* V0 = kry_V.p;
     const uint32_t nd = n_dot();
+    int* stop = kry_flag.p + 1;
+    double* hstat = h_pinned + 56;  // r0, err, k_done, fail
+    auto read_status = [&] {
+        CK(cudaMemcpyAsync(hstat, kry_state.p + L.r0(), 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    };
     apply_preconditioner(b, kry_w.p);
-    kt->multi_dot1(nd, kry_w.p, stride, 1, kry_w.p, kry_partial.p, kry_h.p, kry_counter.p, st); ++launches;
+    kt->multi_dot1(nd, kry_w.p, stride, 1, kry_w.p, kry_partial.p, kry_h.p, kry_counter.p, nullptr, st); ++launches;
     allreduce_sum(kry_h.p, 1);
-    CK(cudaMemcpyAsync(hbuf.data(), kry_h.p, sizeof(double), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    const double r0 = std::sqrt(hbuf[0]);
+    kt->gmres_begin(m, kry_state.p, kry_h.p, 1, stop, st); ++launches;
+    read_status();
+    const double r0 = hstat[0];
     if (!(r0 == r0)) return false;
     if (r0 == 0) return true;
-    double beta = r0;
-    std::vector<double> H((size_t)(m + 1) * m), cs(m), sn(m), g(m + 1), y(m);
     while (last_linear_iters < gmres_max_iter) {
         // V0 = r / beta   (kry_h[0] holds beta^2)
-        kt->scale_from(NT, kry_w.p, kry_h.p, 1, 1, V0, st); ++launches;
+        kt->scale_from(NT, kry_w.p, kry_h.p, 1, 1, V0, nullptr, st); ++launches;
         halo_refresh(V0);
-        std::fill(g.begin(), g.end(), 0.0); g[0] = beta;
-        int k = 0;
+        int k = 0;        // Arnoldi steps queued in this cycle
+        int k_done = 0;   // ... and known to be complete
         bool done = false;
-        for (; k < m && last_linear_iters < gmres_max_iter; ++k) {
-            ++last_linear_iters;
-            // w = M^-1 A v_k   (7 launches per Arnoldi step: product + first sweep, 3 sweeps, dots, update + norm, scaling;
-            // the unfused sequence was 11 -- on the shipped meshes the step is bound by launches)
-            precondition_Ax(kry_V.p + (size_t)k * stride, kry_z.p, kry_w.p);
-            // h = V^T w ; w -= V h ; ||w||^2
-            kt->multi_dot1(nd, kry_V.p, stride, k + 1, kry_w.p, kry_partial.p, kry_h.p, kry_counter.p, st); ++launches;
-            allreduce_sum(kry_h.p, k + 1);
-            kt->axpy_norm(nd, kry_V.p, stride, k + 1, kry_h.p, -1.0, kry_w.p, kry_partial.p, kry_h.p + (k + 1), kry_counter.p, st); ++launches;
-            allreduce_sum(kry_h.p + (k + 1), 1);
-            CK(cudaMemcpyAsync(hbuf.data(), kry_h.p, (size_t)(k + 2) * sizeof(double), cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            const double hn = std::sqrt(hbuf[k + 1]);
-            for (int i = 0; i <= k; ++i) H[(size_t)i * m + k] = hbuf[i];
-            for (int i = 0; i < k; ++i) {
-                const double a = H[(size_t)i * m + k], c = H[(size_t)(i + 1) * m + k];
-                H[(size_t)i * m + k] = cs[i] * a + sn[i] * c;
-                H[(size_t)(i + 1) * m + k] = -sn[i] * a + cs[i] * c;
+        while (k < m && last_linear_iters + (k - k_done) < gmres_max_iter && !done) {
+            const int nb = std::min({batch, m - k, gmres_max_iter - last_linear_iters - (k - k_done)});
+            for (int j = 0; j < nb; ++j, ++k) {
+                // w = M^-1 A v_k   (product + first sweep, the other sweeps, dots, update + norm, rotation, scaling)
+                precondition_Ax(kry_V.p + (size_t)k * stride, kry_z.p, kry_w.p, stop);
+                // h = V^T w ; w -= V h ; ||w||^2
+                kt->multi_dot1(nd, kry_V.p, stride, k + 1, kry_w.p, kry_partial.p, kry_h.p, kry_counter.p, stop, st); ++launches;
+                allreduce_sum(kry_h.p, k + 1);
+                kt->axpy_norm(nd, kry_V.p, stride, k + 1, kry_h.p, -1.0, kry_w.p, kry_partial.p, kry_h.p + (k + 1), kry_counter.p, stop, st); ++launches;
+                allreduce_sum(kry_h.p + (k + 1), 1);
+                kt->givens_step(m, kry_state.p, kry_h.p, k, gmres_tol, stop, st); ++launches;
+                if (k + 1 < m) {  // v_{k+1} = w / ||w||   (kry_h[k+1] holds ||w||^2); skipped on the device once the iteration has stopped
+                    kt->scale_from(NT, kry_w.p, kry_h.p + (k + 1), 1, 1, kry_V.p + (size_t)(k + 1) * stride, stop, st); ++launches;
+                    halo_refresh(kry_V.p + (size_t)(k + 1) * stride);
+                }
             }
-            const double a = H[(size_t)k * m + k], den = std::sqrt(a * a + hn * hn);
-            if (!(den == den)) return false;
-            cs[k] = den == 0 ? 1 : a / den; sn[k] = den == 0 ? 0 : hn / den;
-            H[(size_t)k * m + k] = den;
-            g[k + 1] = -sn[k] * g[k]; g[k] = cs[k] * g[k];
-            const double err = std::fabs(g[k + 1]) / r0;
-            if (hn != 0 && k + 1 < m + 1) {  // v_{k+1} = w / ||w||   (kry_h[k+1] holds ||w||^2)
-                kt->scale_from(NT, kry_w.p, kry_h.p + (k + 1), 1, 1, kry_V.p + (size_t)(k + 1) * stride, st); ++launches;
-                halo_refresh(kry_V.p + (size_t)(k + 1) * stride);
-            }
-            if (err < gmres_tol || hn == 0) { ++k; done = true; break; }
+            read_status();
+            if (hstat[3] != 0.0) return false;  // NaN in the recurrence
+            const int kd = (int)hstat[2];
+            last_linear_iters += kd - k_done;
+            k_done = kd;
+            if (kd < k || hstat[1] < gmres_tol) done = true;  // the device stopped inside the batch (tolerance or breakdown)
         }
-        // x += V y with H y = g
-        for (int i = k - 1; i >= 0; --i) {
-            double s = g[i];
-            for (int j = i + 1; j < k; ++j) s -= H[(size_t)i * m + j] * y[j];
-            y[i] = s / H[(size_t)i * m + i];
+        // x += V y with H y = g (back substitution on the device, k_done columns)
+        if (k_done > 0) {
+            kt->gmres_solve_y(m, kry_state.p, kry_h.p, st); ++launches;
+            kt->multi_axpy(NT, kry_V.p, stride, k_done, kry_h.p, 1.0, x, st); ++launches;
         }
-        CK(cudaMemcpyAsync(kry_h.p, y.data(), (size_t)k * sizeof(double), cudaMemcpyHostToDevice, st));
-        kt->multi_axpy(NT, kry_V.p, stride, k, kry_h.p, 1.0, x, st); ++launches;
-        CK(cudaStreamSynchronize(st));  // y is reused
         if (done) return true;
         // restart: r = M^-1 (b - A x)
         halo_refresh(x);
         kt->spmv(dm, J.p, D.p, x, kry_z.p, st); ++launches;
         kt->sub(NT, b, kry_z.p, kry_z.p, st); ++launches;
         apply_preconditioner(kry_z.p, kry_w.p);
-        kt->multi_dot1(nd, kry_w.p, stride, 1, kry_w.p, kry_partial.p, kry_h.p, kry_counter.p, st); ++launches;
+        kt->multi_dot1(nd, kry_w.p, stride, 1, kry_w.p, kry_partial.p, kry_h.p, kry_counter.p, nullptr, st); ++launches;
         allreduce_sum(kry_h.p, 1);
-        CK(cudaMemcpyAsync(hbuf.data(), kry_h.p, sizeof(double), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        beta = std::sqrt(hbuf[0]);
-        if (!(beta == beta)) return false;
-        if (beta / r0 < gmres_tol) return true;
+        kt->gmres_begin(m, kry_state.p, kry_h.p, 0, stop, st); ++launches;
+        read_status();
+        if (!(hstat[1] == hstat[1])) return false;
+        if (hstat[1] < gmres_tol) return true;
     }
     return false;  // Eigen reports NoConvergence -> the reference returns -1 (solver.h:1184)
 }
@@ -2361,6 +2368,7 @@ int afx_rans_profile_explicit(afx_rans* s, double relaxation, int n_iter, double
         const double alpha[3] = {0.25, 0.5, 1.};
         cudaEvent_t ev[14];
         for (auto& e : ev) CK(cudaEventCreate(&e));
+        bool halo_split[3] = {false, false, false};
         for (int it = 0; it < n_iter; ++it) {
             int e = 0;
             CK(cudaEventRecord(ev[e++], S.st));
@@ -2381,8 +2389,12 @@ int afx_rans_profile_explicit(afx_rans* s, double relaxation, int n_iter, double
                 CK(cudaEventRecord(ev[e++], S.st));
                 S.launch_flux(in[st], false, afx::d4{0, 0, 0, 0});
                 CK(cudaEventRecord(ev[e++], S.st));
+                const bool split = S.halo && S.halo->p2p && !(S.halo_overlap && S.n_front > 0 && S.n_front < S.n_upd);
+                S.prof_stage = split ? st : -1;
                 if (st < 2) S.launch_gather<0, 0>(in[st], outp[st], S.qW.p, alpha[st], grads);
                 else S.launch_gather<0, 1>(in[st], outp[st], S.qW.p, alpha[st], grads);
+                S.prof_stage = -1;
+                halo_split[st] = split;
                 CK(cudaEventRecord(ev[e++], S.st));
                 CK(cudaEventRecord(ev[e++], S.st));
             }
@@ -2396,6 +2408,9 @@ int afx_rans_profile_explicit(afx_rans* s, double relaxation, int n_iter, double
                 CK(cudaEventElapsedTime(&ms, ev[2 + 4 * st], ev[3 + 4 * st])); out_ms[2] += ms;
                 CK(cudaEventElapsedTime(&ms, ev[3 + 4 * st], ev[4 + 4 * st])); out_ms[3] += ms;
                 CK(cudaEventElapsedTime(&ms, ev[4 + 4 * st], ev[5 + 4 * st])); out_ms[4] += ms;
+                if (halo_split[st]) {  // peer-memory halo: flag hand-off + wait + scatter, taken out of the gather/update figure
+                    CK(cudaEventElapsedTime(&ms, S.evp[8 + 2 * st], S.evp[9 + 2 * st])); out_ms[4] += ms; out_ms[3] -= ms;
+                }
             }
         }
         for (auto& e : ev) cudaEventDestroy(e);

@@ -212,16 +212,23 @@ struct KernelTable {
     // implicit step (rans_krylov.cuh)
     void (*spmv)(const DevMesh& m, const d4* J, const double* D, const d4* x, d4* y, cudaStream_t st);
     void (*jacobi_sweep)(const DevMesh& m, const d4* J, const double* D, const double* Dinv, const d4* r, const d4* z_in, d4* z_out, int first,
-                         cudaStream_t st);
+                         const int* stop, cudaStream_t st);
     void (*invert_blocks)(uint32_t n, const double* D, double* Dinv, int* singular, cudaStream_t st);
     void (*multi_dot)(uint32_t n, const d4* V, size_t stride, int k, const d4* w, double* partial, double* out, cudaStream_t st);  // 2 kernels
     void (*multi_axpy)(uint32_t n, const d4* V, size_t stride, int k, const double* c, double sign, d4* w, cudaStream_t st);
     // one-launch forms for the Arnoldi step (same arithmetic, same bits; the last block finishes the sums)
-    void (*multi_dot1)(uint32_t n, const d4* V, size_t stride, int k, const d4* w, double* partial, double* out, unsigned int* counter, cudaStream_t st);
+    // `stop`: device flag of the Krylov iteration (null = always run), see rans_krylov.cuh
+    void (*multi_dot1)(uint32_t n, const d4* V, size_t stride, int k, const d4* w, double* partial, double* out, unsigned int* counter, const int* stop,
+                       cudaStream_t st);
     void (*axpy_norm)(uint32_t n, const d4* V, size_t stride, int k, const double* c, double sign, d4* w, double* partial, double* out,
-                      unsigned int* counter, cudaStream_t st);
-    void (*spmv_sweep0)(const DevMesh& m, const d4* J, const double* D, const double* Dinv, const d4* x, d4* r, d4* z, cudaStream_t st);
-    void (*scale_from)(uint32_t n, const d4* x, const double* s, int root, int inv, d4* y, cudaStream_t st);
+                      unsigned int* counter, const int* stop, cudaStream_t st);
+    void (*spmv_sweep0)(const DevMesh& m, const d4* J, const double* D, const double* Dinv, const d4* x, d4* r, d4* z, const int* stop, cudaStream_t st);
+    void (*scale_from)(uint32_t n, const d4* x, const double* s, int root, int inv, d4* y, const int* stop, cudaStream_t st);
+    // the small dense part of GMRES on the device: Hessenberg column + Givens rotations + residual estimate, back substitution
+    void (*gmres_begin)(int m, double* state, const double* beta2, int first, int* stop, cudaStream_t st);
+    void (*givens_step)(int m, double* state, const double* h, int k, double tol, int* stop, cudaStream_t st);
+    void (*gmres_solve_y)(int m, const double* state, double* out, cudaStream_t st);
+    int (*gmres_state_doubles)(int m);
     void (*sub)(uint32_t n, const d4* a, const d4* b, d4* y, cudaStream_t st);
     void (*axpy_state)(uint32_t n, double relax, const d4* x, d4* q, cudaStream_t st);
 };

@@ -280,6 +280,10 @@ def main():
 
     # per-phase kernel times (CUDA events between the phases, same state, right after the timed region)
     prof = s.profile_explicit(5, RELAX)
+    if dist is not None:  # how even the pieces are: min / max of every phase over the ranks, faces per rank
+        allp = [None] * world
+        dist.all_gather_object(allp, dict(prof, cells=part.n_own, faces=part.E))
+        details["rank_spread"] = {k: [min(p[k] for p in allp), max(p[k] for p in allp)] for k in allp[0]}
     n_loc = N if part is None else part.n_own
     share = n_loc / N  # this rank's share of the cells
     # ALGORITHMIC bytes per launch (they sum to 1488 N + 296 E per iteration however the phases are fused):
