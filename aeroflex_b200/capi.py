@@ -42,7 +42,7 @@ EXPORTED_SYMBOLS = [
     "afx_rans_set_linear_solver", "afx_rans_last_linear_iterations",
     "afx_rans_wall_forces", "afx_rans_wall_cp", "afx_rans_sweep", "afx_rans_sweep_fmg", "afx_prolongation_create", "afx_prolongation_free",
     "afx_prolongation_apply", "afx_rans_last_device_ms", "afx_rans_launch_count",
-    "afx_rans_profile_explicit",
+    "afx_rans_profile_explicit", "afx_rans_profile_halo_ms",
 ]
 
 
@@ -224,6 +224,7 @@ def load_library():
     L.afx_rans_launch_count.restype = C.c_int64
     L.afx_rans_launch_count.argtypes = [vp]
     L.afx_rans_profile_explicit.argtypes = [vp, C.c_double, C.c_int, vp]
+    L.afx_rans_profile_halo_ms.argtypes = [vp, vp]
     _lib = L
     return L
 
@@ -718,6 +719,11 @@ class GpuSolver:
         out = np.zeros(6)
         _check(self.L.afx_rans_profile_explicit(self.h, relaxation, n_iter, _ptr(out)))
         return dict(dt_grad=out[0], limiter=out[1], flux=out[2], gather_update=out[3], halo_exchange=out[4], stage=out[5])
+
+    def profile_halo_ms(self):
+        out = np.zeros(2)
+        _check(self.L.afx_rans_profile_halo_ms(self.h, _ptr(out)))
+        return dict(signal=out[0], wait_scatter=out[1])
 
     def set_fused(self, on):
         """One fused kernel per Runge-Kutta stage (default) or limiter / flux / gather+update as three kernels."""

@@ -133,6 +133,34 @@ __device__ __forceinline__ double venkat_pair(double pmax, double pmin, double d
 }
 #endif
 
+#if AFX_FAST
+// largest positive / most negative projected increment g . (x_f - x_c) over the cell's faces, per component.  The gradients
+// are those of the iteration-start state for all three stages and the offsets are geometry: these eight numbers
+// are CONSTANT over an iteration.  k_dt_grad stores them (`pm`, 64 B per cell) and the limiter kernels of stages 2 and 3 read
+// them instead of gx, gy and the four face offsets (128 B per cell): same values, same bits, 120 B per cell and launch less.
+__device__ __forceinline__ void projected_extremes(const d4& gxi, const d4& gyi, const double2 (&dxy)[4], unsigned valid, d4& pmax, d4& pmin)
+{
+    pmax = mk4(0, 0, 0, 0); pmin = mk4(0, 0, 0, 0);
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        if (!(valid & (1u << s))) continue;
+        const double dx = dxy[s].x, dy = dxy[s].y;
+        const double p0 = gxi.x * dx + gyi.x * dy, p1 = gxi.y * dx + gyi.y * dy, p2 = gxi.z * dx + gyi.z * dy, p3 = gxi.w * dx + gyi.w * dy;
+        pmax.x = dmax2(pmax.x, p0); pmax.y = dmax2(pmax.y, p1); pmax.z = dmax2(pmax.z, p2); pmax.w = dmax2(pmax.w, p3);
+        pmin.x = dmin2(pmin.x, p0); pmin.y = dmin2(pmin.y, p1); pmin.z = dmin2(pmin.z, p2); pmin.w = dmin2(pmin.w, p3);
+    }
+}
+__device__ __forceinline__ d4 limiter_from_extremes(const d4& dmax, const d4& dmin, const d4& pmax, const d4& pmin, double K3a)
+{
+    d4 l;
+    l.x = venkat_pair(pmax.x, pmin.x, dmax.x, dmin.x, K3a);
+    l.y = venkat_pair(pmax.y, pmin.y, dmax.y, dmin.y, K3a);
+    l.z = venkat_pair(pmax.z, pmin.z, dmax.z, dmin.z, K3a);
+    l.w = venkat_pair(pmax.w, pmin.w, dmax.w, dmin.w, K3a);
+    return l;
+}
+#endif
+
 // limiter of one cell from its state, the min/max over its neighbours, its gradient and the face offsets of its slots
 // (solver.h:538-592); `valid` bit s = slot s holds a face.  Shared by k_limiter and the fused k_stage.
 __device__ __forceinline__ d4 limiter_value(const d4& qi, const d4& lo, const d4& hi, const d4& gxi, const d4& gyi, const double2 (&dxy)[4],
@@ -145,19 +173,9 @@ __device__ __forceinline__ d4 limiter_value(const d4& qi, const d4& lo, const d4
     // Where the limiter function is below 1 it decreases monotonically with |dqg| (d phi/d dqg < 0 for dqg > dm/2), and
     // values above 1 never survive the min with 1: the minimum over the faces is attained at the largest positive and
     // the most negative projected increment -> one pair of evaluations per component instead of one per face.
-    d4 pmax = mk4(0, 0, 0, 0), pmin = mk4(0, 0, 0, 0);
-#pragma unroll
-    for (int s = 0; s < 4; ++s) {
-        if (!(valid & (1u << s))) continue;
-        const double dx = dxy[s].x, dy = dxy[s].y;
-        const double p0 = gxi.x * dx + gyi.x * dy, p1 = gxi.y * dx + gyi.y * dy, p2 = gxi.z * dx + gyi.z * dy, p3 = gxi.w * dx + gyi.w * dy;
-        pmax.x = dmax2(pmax.x, p0); pmax.y = dmax2(pmax.y, p1); pmax.z = dmax2(pmax.z, p2); pmax.w = dmax2(pmax.w, p3);
-        pmin.x = dmin2(pmin.x, p0); pmin.y = dmin2(pmin.y, p1); pmin.z = dmin2(pmin.z, p2); pmin.w = dmin2(pmin.w, p3);
-    }
-    l.x = venkat_pair(pmax.x, pmin.x, dmax.x, dmin.x, K3a);
-    l.y = venkat_pair(pmax.y, pmin.y, dmax.y, dmin.y, K3a);
-    l.z = venkat_pair(pmax.z, pmin.z, dmax.z, dmin.z, K3a);
-    l.w = venkat_pair(pmax.w, pmin.w, dmax.w, dmin.w, K3a);
+    d4 pmax, pmin;
+    projected_extremes(gxi, gyi, dxy, valid, pmax, pmin);
+    l = limiter_from_extremes(dmax, dmin, pmax, pmin, K3a);
 #else
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
@@ -185,7 +203,7 @@ __device__ __forceinline__ d4 limiter_value(const d4& qi, const d4& lo, const d4
 template <int GRAD, int LIM>
 __global__ void __launch_bounds__(AFX_DTG_THREADS, AFX_DTG_MINB) k_dt_grad(DevMesh m, d4* q, double* dt,
                                                  d4* gx, d4* gy, const double* __restrict__ prm,
-                                                 double gam, int want_grad, int walls, d4* lim, double limiter_k)
+                                                 double gam, int want_grad, int walls, d4* lim, double limiter_k, d4* pm)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m.n_grad) return;
@@ -344,6 +362,17 @@ __global__ void __launch_bounds__(AFX_DTG_THREADS, AFX_DTG_MINB) k_dt_grad(DevMe
             lo.x = dmin2(lo.x, qj.x); lo.y = dmin2(lo.y, qj.y); lo.z = dmin2(lo.z, qj.z); lo.w = dmin2(lo.w, qj.w);
             hi.x = dmax2(hi.x, qj.x); hi.y = dmax2(hi.y, qj.y); hi.z = dmax2(hi.z, qj.z); hi.w = dmax2(hi.w, qj.w);
         }
+#if AFX_FAST
+        if (pm) {  // the projected extremes for the limiter kernels of the later stages (see projected_extremes)
+            d4 pmax, pmin;
+            projected_extremes(ax, ay, dxy, valid, pmax, pmin);
+            pm[2 * (size_t)i] = pmax; pm[2 * (size_t)i + 1] = pmin;
+            const d4 dmax = mk4(hi.x - qi.x, hi.y - qi.y, hi.z - qi.z, hi.w - qi.w);
+            const d4 dmin = mk4(lo.x - qi.x, lo.y - qi.y, lo.z - qi.z, lo.w - qi.w);
+            lim[i] = limiter_from_extremes(dmax, dmin, pmax, pmin, limiter_k3a(A, limiter_k));
+            return;
+        }
+#endif
         lim[i] = limiter_value(qi, lo, hi, ax, ay, dxy, valid, limiter_k3a(A, limiter_k));
     }
 }
@@ -359,20 +388,20 @@ struct LimCell {
     double2 dxy[4];
     double area;
 };
-__device__ __forceinline__ LimCell limiter_load_static(const DevMesh& m, uint32_t i)
+__device__ __forceinline__ LimCell limiter_load_static(const DevMesh& m, uint32_t i, bool want_dxy = true)
 {
     LimCell c;
 #pragma unroll
     for (int s = 0; s < 4; ++s) {  // independent coalesced loads
         c.nbs[s] = m.cnb[(size_t)s * m.N + i];
-        c.dxy[s] = m.cdxy[(size_t)s * m.N + i];
+        c.dxy[s] = want_dxy ? m.cdxy[(size_t)s * m.N + i] : make_double2(0., 0.);
     }
     c.area = m.area[i];
     return c;
 }
 // the limiter of cell i from the stage state and the gradients (shared by k_limiter and the pipelined stage kernel k_pipe)
 __device__ __forceinline__ void limiter_cell(const DevMesh& m, uint32_t i, const LimCell& c, const d4* qk, const d4* gx, const d4* gy, d4* lim,
-                                             double limiter_k, int walls)
+                                             double limiter_k, int walls, const d4* pm = nullptr)
 {
     const uint32_t (&nbs)[4] = c.nbs;
     const double2 (&dxy)[4] = c.dxy;
@@ -395,21 +424,30 @@ __device__ __forceinline__ void limiter_cell(const DevMesh& m, uint32_t i, const
         lo.x = dmin2(lo.x, qj.x); lo.y = dmin2(lo.y, qj.y); lo.z = dmin2(lo.z, qj.z); lo.w = dmin2(lo.w, qj.w);
         hi.x = dmax2(hi.x, qj.x); hi.y = dmax2(hi.y, qj.y); hi.z = dmax2(hi.z, qj.z); hi.w = dmax2(hi.w, qj.w);
     }
+#if AFX_FAST
+    if (pm) {  // extremes of the projected increments stored by k_dt_grad: neither the gradients nor the face offsets are read
+        const d4 pmax = pm[2 * (size_t)i], pmin = pm[2 * (size_t)i + 1];
+        const d4 dmax = mk4(hi.x - qi.x, hi.y - qi.y, hi.z - qi.z, hi.w - qi.w);
+        const d4 dmin = mk4(lo.x - qi.x, lo.y - qi.y, lo.z - qi.z, lo.w - qi.w);
+        lim[i] = limiter_from_extremes(dmax, dmin, pmax, pmin, limiter_k3a(area_i, limiter_k));
+        return;
+    }
+#endif
     lim[i] = limiter_value(qi, lo, hi, gx[i], gy[i], dxy, valid, limiter_k3a(area_i, limiter_k));
 }
 
 __global__ void __launch_bounds__(AFX_LIM_THREADS, AFX_LIM_MINB) k_limiter(DevMesh m, const d4* qk, const d4* gx,
                                                  const d4* gy, d4* lim, double limiter_k, int walls,
-                                                 uint32_t lo1, uint32_t n1, uint32_t lo2, uint32_t n2)
+                                                 uint32_t lo1, uint32_t n1, uint32_t lo2, uint32_t n2, const d4* pm)
 {
     // cells [lo1, lo1+n1) and [lo2, lo2+n2): a partitioned run limits its interior cells while the halo is in flight
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n1 + n2) return;
     const uint32_t i = t < n1 ? lo1 + t : lo2 + (t - n1);
     pdl_launch_dependents();
-    const LimCell c = limiter_load_static(m, i);
+    const LimCell c = limiter_load_static(m, i, !(AFX_FAST && pm));
     pdl_wait();  // stage state and gradients come from the previous kernels
-    limiter_cell(m, i, c, qk, gx, gy, lim, limiter_k, walls);
+    limiter_cell(m, i, c, qk, gx, gy, lim, limiter_k, walls, pm);
 }
 
 // ---------------------------------------------------------------------------
@@ -956,19 +994,19 @@ static void launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, 
 
 // lim != nullptr: also write the first stage's limiters (needs want_grad)
 static void dt_grad(int grad, const DevMesh& m, d4* q, double* dt, d4* gx, d4* gy, const double* prm, double gam, int want_grad,
-                    int walls, d4* lim, double limiter_k, cudaStream_t st)
+                    int walls, d4* lim, double limiter_k, d4* pm, cudaStream_t st)
 {
     const unsigned nb = nblk(m.n_grad, AFX_DTG_THREADS);
-#define AFX_DTG(G, L) launch_pdl(k_dt_grad<G, L>, nb, AFX_DTG_THREADS, st, m, q, dt, gx, gy, prm, gam, want_grad, walls, lim, limiter_k)
+#define AFX_DTG(G, L) launch_pdl(k_dt_grad<G, L>, nb, AFX_DTG_THREADS, st, m, q, dt, gx, gy, prm, gam, want_grad, walls, lim, limiter_k, pm)
     if (lim && want_grad) { if (grad == 0) AFX_DTG(0, 1); else AFX_DTG(1, 1); }
     else { if (grad == 0) AFX_DTG(0, 0); else AFX_DTG(1, 0); }
 #undef AFX_DTG
 }
 static void limiter(const DevMesh& m, const d4* qk, const d4* gx, const d4* gy, d4* lim, double k, int walls, uint32_t lo1, uint32_t n1,
-                    uint32_t lo2, uint32_t n2, cudaStream_t st)
+                    uint32_t lo2, uint32_t n2, const d4* pm, cudaStream_t st)
 {
     if (n1 + n2 == 0) return;
-    launch_pdl(k_limiter, nblk(n1 + n2, AFX_LIM_THREADS), AFX_LIM_THREADS, st, m, qk, gx, gy, lim, k, walls, lo1, n1, lo2, n2);
+    launch_pdl(k_limiter, nblk(n1 + n2, AFX_LIM_THREADS), AFX_LIM_THREADS, st, m, qk, gx, gy, lim, k, walls, lo1, n1, lo2, n2, pm);
 }
 static void flux(int second, int visc, int uniform, const DevMesh& m, const d4* qk, const d4* q0, const d4* gx, const d4* gy,
                  const d4* lim, d4* fl, const GasC& g, d4 qfar, cudaStream_t st)

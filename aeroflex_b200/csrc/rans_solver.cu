@@ -243,6 +243,9 @@ struct Solver {
     DBuf<uint32_t> perm_c_new2old, perm_c_old2new;
     // device state
     DBuf<d4> q, qkA, qkB, gx, gy, lim, qW, rhs, flux, stage;
+    DBuf<d4> pm;    // [2][NT] fast mode: extremes of the projected increments per cell, written by k_dt_grad with the first stage's limiters
+    bool pm_valid = false, use_pm = true;  // AFX_LIM_PM=0: the limiter kernels read gradients and face offsets as in strict mode
+    const d4* pm_for_limiter() const { return (pm_valid && kt == &fast::table()) ? pm.p : nullptr; }
     DBuf<d4> grad;  // [gx | gy] in one allocation: one L2 access-policy window covers both
     void set_l2_window();
     DBuf<double> dt, dt_ref;
@@ -283,7 +286,7 @@ struct Solver {
     {
         if (mode != AFX_MATH_STRICT && mode != AFX_MATH_FAST) throw InvalidArg("unknown math mode");
         const KernelTable* t = (mode == AFX_MATH_STRICT) ? &strict::table() : &fast::table();
-        if (t != kt) { kt = t; invalidate_graph(); jac_valid = false; }
+        if (t != kt) { kt = t; invalidate_graph(); jac_valid = false; pm_valid = false; }
     }
 
     ~Solver()
@@ -320,7 +323,13 @@ struct Solver {
     void p2p_connect(const void* blobs, size_t blob_size, int nranks);
     void exchange(d4* field, cudaStream_t stream);
     int prof_stage = -1;  // >= 0 while afx_rans_profile_explicit runs stage `prof_stage`: the halo hand-off is bracketed by evp[8 + 2 s], evp[9 + 2 s]
-    void prof_mark(int which) { if (prof_stage >= 0 && prof_stage < 3) CK(cudaEventRecord(evp[8 + 2 * prof_stage + which], st)); }
+    void prof_mark(int which)
+    {
+        if (prof_stage < 0 || prof_stage >= 3) return;
+        if (which < 2) CK(cudaEventRecord(evp[8 + 2 * prof_stage + which], st));
+        else CK(cudaEventRecord(evp[2 + prof_stage], st));  // after the signalling kernel (evp[2..4])
+    }
+    double prof_halo_ms[2] = {0, 0};  // last afx_rans_profile_explicit: signalling kernel, wait + scatter kernel (per iteration)
     bool halo_pending = false;
     bool halo_overlap = false;  // AFX_HALO_OVERLAP=1: exchange on a second stream under the interior update (needed for the NCCL halo)
     void ensure_halo() { if (halo_pending) { CK(cudaStreamWaitEvent(st, ev_halo, 0)); halo_pending = false; } }
@@ -617,6 +626,8 @@ void Solver::create(const afx_mesh_desc& m, const afx_gas& g, int visc, int dev,
     grad.alloc(2 * (size_t)NT); grad.zero(st);
     gx.view(grad.p, NT); gy.view(grad.p + NT, NT);
     for (DBuf<d4>* b : {&q, &qkA, &qkB, &lim, &qW, &rhs, &stage}) { b->alloc(NT); b->zero(st); }
+    if (const char* e = getenv("AFX_LIM_PM")) use_pm = !(e[0] == '0');
+    pm.alloc(2 * (size_t)NT); pm.zero(st);
     set_l2_window();
     flux.alloc(E); flux.zero(st);
     dt.alloc(NT); dt.zero(st); dt_ref.alloc(NT);
@@ -732,8 +743,11 @@ void Solver::push_params(double relax, bool keep_qW)
 void Solver::launch_dt_grad(bool want_grad, bool walls, bool with_lim)
 {
     ensure_halo();
+    const bool lim_here = with_lim && want_grad;
+    d4* pm_out = (lim_here && use_pm && kt == &fast::table()) ? pm.p : nullptr;
     kt->dt_grad(gradient_scheme == AFX_GRAD_GREEN_GAUSS ? 0 : 1, dm, q.p, dt.p, gx.p, gy.p, prm.p, gas.gamma, want_grad, walls,
-                (with_lim && want_grad) ? lim.p : nullptr, limiter_k, st);
+                lim_here ? lim.p : nullptr, limiter_k, pm_out, st);
+    pm_valid = pm_out != nullptr;  // any other gradient pass leaves the stored extremes stale
     ++launches;
 }
 
@@ -742,14 +756,14 @@ void Solver::launch_limiter(const d4* qk)
     const int walls = (visc_not_inviscid || second_order) ? 1 : 0;
     if (halo_pending && n_front > 0 && n_front < n_upd) {
         // owned cells farther than two hops from any foreign cell do not see the halo: limit them while it is in flight
-        kt->limiter(dm, qk, gx.p, gy.p, lim.p, limiter_k, walls, n_front, n_upd - n_front, 0, 0, st);
+        kt->limiter(dm, qk, gx.p, gy.p, lim.p, limiter_k, walls, n_front, n_upd - n_front, 0, 0, pm_for_limiter(), st);
         ensure_halo();
-        kt->limiter(dm, qk, gx.p, gy.p, lim.p, limiter_k, walls, 0, n_front, n_upd, n_grad - n_upd, st);
+        kt->limiter(dm, qk, gx.p, gy.p, lim.p, limiter_k, walls, 0, n_front, n_upd, n_grad - n_upd, pm_for_limiter(), st);
         launches += 2;
         return;
     }
     ensure_halo();
-    kt->limiter(dm, qk, gx.p, gy.p, lim.p, limiter_k, walls, 0, n_grad, 0, 0, st);
+    kt->limiter(dm, qk, gx.p, gy.p, lim.p, limiter_k, walls, 0, n_grad, 0, 0, pm_for_limiter(), st);
     ++launches;
 }
 
@@ -786,6 +800,7 @@ void Solver::launch_gather(const d4* qk_in, d4* qk_out, d4* vec_out, double alph
         kt->gather(MODE, LAST, dm, 0, n_upd, flux.p, q.p, qk_in, qk_out, dt.p, vec_out, alpha, prm.p, walls ? 1 : 0, norm_out(), &halo->push, st);
         prof_mark(0);
         kt->halo_signal(halo->sig, st);
+        prof_mark(2);
         halo_rendezvous(st); kt->halo_wait_scatter(halo->wait, qk_out, st);
         prof_mark(1);
         launches += 3;
@@ -2344,6 +2359,12 @@ int afx_rans_sweep(afx_rans* s, const afx_sweep_settings* st, int farfield_patch
     return afx_rans_sweep_fmg(one, nullptr, 1, st, farfield_patch, wall_patch, alphas_deg, n_alpha, reinit, cl, cd, cm, iterations, residual);
 }
 
+int afx_rans_profile_halo_ms(afx_rans* s, double out[2])
+{
+    if (!s || !out) { afx::set_error("null argument"); return AFX_ERR_INVALID; }
+    out[0] = s->s.prof_halo_ms[0]; out[1] = s->s.prof_halo_ms[1];
+    return AFX_OK;
+}
 int afx_rans_last_device_ms(afx_rans* s, double* ms)
 {
     if (!s || !ms) { afx::set_error("null argument"); return AFX_ERR_INVALID; }
@@ -2369,6 +2390,7 @@ int afx_rans_profile_explicit(afx_rans* s, double relaxation, int n_iter, double
         cudaEvent_t ev[14];
         for (auto& e : ev) CK(cudaEventCreate(&e));
         bool halo_split[3] = {false, false, false};
+        S.prof_halo_ms[0] = S.prof_halo_ms[1] = 0;
         for (int it = 0; it < n_iter; ++it) {
             int e = 0;
             CK(cudaEventRecord(ev[e++], S.st));
@@ -2410,6 +2432,11 @@ int afx_rans_profile_explicit(afx_rans* s, double relaxation, int n_iter, double
                 CK(cudaEventElapsedTime(&ms, ev[4 + 4 * st], ev[5 + 4 * st])); out_ms[4] += ms;
                 if (halo_split[st]) {  // peer-memory halo: flag hand-off + wait + scatter, taken out of the gather/update figure
                     CK(cudaEventElapsedTime(&ms, S.evp[8 + 2 * st], S.evp[9 + 2 * st])); out_ms[4] += ms; out_ms[3] -= ms;
+                    if (!S.halo->early_signal) {
+                        float a_ = 0, b_ = 0;
+                        CK(cudaEventElapsedTime(&a_, S.evp[8 + 2 * st], S.evp[2 + st])); CK(cudaEventElapsedTime(&b_, S.evp[2 + st], S.evp[9 + 2 * st]));
+                        S.prof_halo_ms[0] += a_ / n_iter; S.prof_halo_ms[1] += b_ / n_iter;
+                    }
                 }
             }
         }

@@ -168,10 +168,10 @@ struct KernelTable {
     const char* name;
     // lim != nullptr (and want_grad): the kernel also writes the limiters of the first stage (state q), saving that k_limiter launch
     void (*dt_grad)(int grad_scheme, const DevMesh& m, d4* q, double* dt, d4* gx, d4* gy, const double* prm, double gam,
-                    int want_grad, int walls, d4* lim, double limiter_k, cudaStream_t st);
+                    int want_grad, int walls, d4* lim, double limiter_k, d4* pm, cudaStream_t st);  // pm (fast mode, with lim): [2][cell] projected extremes
     // cells [lo1, lo1+n1) and [lo2, lo2+n2)
     void (*limiter)(const DevMesh& m, const d4* qk, const d4* gx, const d4* gy, d4* lim, double limiter_k, int walls, uint32_t lo1, uint32_t n1,
-                    uint32_t lo2, uint32_t n2, cudaStream_t st);
+                    uint32_t lo2, uint32_t n2, const d4* pm, cudaStream_t st);  // pm != null (fast mode): k_dt_grad's stored extremes
     void (*flux)(int second, int visc, int uniform, const DevMesh& m, const d4* qk, const d4* q0, const d4* gx, const d4* gy,
                  const d4* lim, d4* flux, const GasC& g, d4 qfar, cudaStream_t st);
     // cells [lo, hi); `no` carries the block bookkeeping when the phase is split into several launches

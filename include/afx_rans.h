@@ -321,8 +321,11 @@ int afx_rans_last_device_ms(afx_rans* s, double* ms);
 int64_t afx_rans_launch_count(afx_rans* s);
 /* per-phase device milliseconds of one explicit iteration, timed with CUDA events between the phases:
  * out[0]=dt+gradients, out[1]=limiter (3 stages), out[2]=face flux (3 stages), out[3]=gather+update (3 stages),
- * out[4]=halo exchange (3 stages; 0 on one GPU), out[5]=fused stage kernel (3 stages; then out[1..3] are 0) */
+ * out[4]=halo exchange (3 stages; 0 on one GPU; peer-memory halo: flag hand-off + wait + scatter, not counted in out[3]), out[5]=fused stage kernel (3 stages; then out[1..3] are 0) */
 int afx_rans_profile_explicit(afx_rans* s, double relaxation, int n_iter, double out_ms[6]);
+/* of the last afx_rans_profile_explicit on a peer-memory halo without the in-kernel hand-off (AFX_HALO_EARLY_SIGNAL=0):
+ * device milliseconds per iteration of the signalling kernel and of the wait + scatter kernel (3 exchanges) */
+int afx_rans_profile_halo_ms(afx_rans* s, double out[2]);
 
 #ifdef __cplusplus
 }

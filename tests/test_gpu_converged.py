@@ -1,0 +1,60 @@
+"""The north-star force tolerance, asserted: converged CL/CD/CM within 1e-8 relative of the reference CPU solver.
+
+Fixture tests/golden/converged_naca0012q_coarse_explicit.npz (oracle/make_golden_converged.py): the UNMODIFIED reference's
+explicit solver on naca0012q_coarse (Euler, slip wall, Green-Gauss, 2nd order, M = 0.2, alpha = 1 deg, CFL 1.5), iterated
+from the free stream until ||R|| / ||R_0|| <= 1e-13 -- deep enough for a 1e-8 comparison, which the implicit sweep fixtures
+are not (the reference's ILUT/GMRES iteration stagnates near 1e-11).
+
+ strict mode  the same number of iterations gives the same state to the bit (forces to 1e-12: tree reduction);
+ fast mode    the same number of iterations lands within 1e-8 on CL, CD and CM;
+ implicit     fillRhoLHS / GMRES on the device driven to 1e-12 finds the same fixed point: forces within 1e-8."""
+import numpy as np
+import pytest
+
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _fixture():
+    g = H.load("converged_naca0012q_coarse_explicit")
+    return g, g["meta"]
+
+
+def _solver(afx, g, meta, math, cfl=None):
+    m = H.product_mesh(afx, g)
+    s = afx.GpuSolver(m, viscosity=meta["viscosity"], math=math)
+    s.set_bcs(meta["bcs"]); s.set_options(meta["second_order"], meta["gradient"], 5.0, meta["cfl"] if cfl is None else cfl)
+    s.init(); s.refill_bcs()
+    return s
+
+
+def test_strict_mode_reaches_the_reference_state_bit_for_bit(afx, gpu):
+    g, meta = _fixture()
+    s = _solver(afx, g, meta, "strict")
+    n, every = int(g["n_iter"]), int(g["every"])
+    norms = s.run(n, meta["relax"])
+    np.testing.assert_allclose(norms[every - 1::every], g["norms_every"], rtol=1e-12, atol=0)
+    assert norms[-1] / norms[0] <= 1e-13
+    assert H.sha(s.get_q()) == str(g["sha_q"])
+    np.testing.assert_allclose(s.wall_forces("wall"), g["forces"], rtol=1e-12, atol=0)
+
+
+def test_fast_mode_converged_forces_within_1e8(afx, gpu):
+    g, meta = _fixture()
+    s = _solver(afx, g, meta, "fast")
+    norms = s.run(int(g["n_iter"]), meta["relax"])
+    assert norms[-1] / norms[0] <= 2e-13
+    np.testing.assert_allclose(s.wall_forces("wall"), g["forces"], rtol=1e-8, atol=0)  # the north-star tolerance
+
+
+@pytest.mark.parametrize("math", ["strict", "fast"])
+def test_implicit_path_converges_to_the_same_forces_within_1e8(afx, gpu, math):
+    """implicitSolver (fillRhoRHS / fillRhoLHS, GMRES + block-Jacobi sweeps on the device) and explicitSolver share the residual:
+    driven to 1e-12 the implicit iteration must sit on the fixed point the reference's explicit iteration found."""
+    g, meta = _fixture()
+    s = _solver(afx, g, meta, math, cfl=40.0)
+    r = s.sweep([1.0], implicit=True, tolerance=1e-12, max_iterations=400, reinit=True)
+    assert r["status"] == 0 and r["residual"][0] <= 1e-12 and r["iterations"][0] < 400
+    got = np.array([r["cl"][0], r["cd"][0], r["cm"][0]])
+    np.testing.assert_allclose(got, g["forces"], rtol=1e-8, atol=0)

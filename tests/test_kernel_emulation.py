@@ -124,3 +124,19 @@ def test_in_process_group_under_emulation(emu_lib):
     tail = run_gpu_tests_under_emulation(emu_lib, ["test_gpu_group.py"], "2-p2p-strict or 4-staged-strict or dead_peer or wall_cp or 3-inviscid",
                                          extra_env={"AFX_EMU_DEVICES": "1", "OMP_NUM_THREADS": "2", "OMP_WAIT_POLICY": "passive"})
     assert "5 passed" in tail
+
+
+def test_pipelined_stage_kernel_under_emulation(emu_lib):
+    """tests/test_gpu_pipe.py: the persistent chunk-sweeping stage kernel (work items claimed from a device counter, per-chunk
+    completion counters, far lists) -- its CTAs run on several host threads here, so the claim / wait / publish protocol is
+    exercised for real; bit-identical to the three-kernel stage and to the reference's golden history."""
+    tail = run_gpu_tests_under_emulation(emu_lib, ["test_gpu_pipe.py"], "(strict and (8-1-0 or 10-2-2)) or variants or laminar or reference_history or 2-p2p",
+                                         extra_env={"AFX_EMU_DEVICES": "1", "OMP_NUM_THREADS": "4", "OMP_WAIT_POLICY": "passive"})
+    assert " passed" in tail and "failed" not in tail
+
+
+def test_device_fmg_under_emulation(emu_lib):
+    """tests/test_gpu_fmg.py: device-resident prolongation (bit-identical to the reference's product) and afx_rans_sweep_fmg against
+    the same loop written with primitive calls and a host prolongation."""
+    tail = run_gpu_tests_under_emulation(emu_lib, ["test_gpu_fmg.py"], "not converges_to_the_reference")
+    assert "2 passed" in tail

@@ -152,3 +152,20 @@ def test_transonic_and_supersonic_histories_match_reference(tag):
     assert np.array_equal(o.q[:64], g[tag + "_q_head"])
     assert H.sha(o.q) == str(g[tag + "_q_sha256"])
     assert H.sha(o.lim[:4 * 4096]) == str(g[tag + "_lim_sha256"])
+
+
+def test_oracle_follows_the_converged_reference_run():
+    """tests/golden/converged_naca0012q_coarse_explicit.npz (the unmodified reference, ~90 000 explicit iterations to 1e-13): the
+    oracle reproduces the first checkpoints of its residual history exactly (the whole depth is run by the GPU tests)."""
+    import os
+    if not os.path.exists(os.path.join(H.GOLDEN, "converged_naca0012q_coarse_explicit.npz")):
+        pytest.skip("fixture not generated")
+    g = H.load("converged_naca0012q_coarse_explicit")
+    meta = g["meta"]
+    o = orc.OracleSolver(H.oracle_mesh(g), viscosity=meta["viscosity"])
+    o.set_bcs(meta["bcs"]); o.set_options(meta["second_order"], meta["gradient"], 5.0, meta["cfl"]); o.init(); o.refill_bcs()
+    every = int(g["every"])
+    for k in range(2):
+        for _ in range(every):
+            n = o.explicit_solve(meta["relax"])
+        assert n == g["norms_every"][k]
