@@ -51,11 +51,19 @@
 #ifndef AFX_DTG_PRELOAD
 #define AFX_DTG_PRELOAD 0
 #endif
+// Round 2 (profiles/r02k_ab_{1M,16M}.jsonl, same box, one process per build): with the stored-extremes epilogue (k_dt_grad<., 2>) the
+// kernel spills 304 B per thread at 80 registers (128 x 6); at 96 registers (128 x 5, 20 warps per SM) 20 B: 0.3812 -> 0.3702 ms per
+// iteration at 1M cells (dt/gradient phase 0.109 -> 0.101), 5.711 -> 5.679 at 16M; 128 x 4 (118 registers, no spills) 0.3746 / 5.794.
 #ifndef AFX_DTG_MINB
-#define AFX_DTG_MINB (AFX_DTG_PRELOAD ? 512 / AFX_DTG_THREADS : 768 / AFX_DTG_THREADS)
+#define AFX_DTG_MINB (AFX_DTG_PRELOAD ? 512 / AFX_DTG_THREADS : 640 / AFX_DTG_THREADS)
 #endif
 #ifndef AFX_DTG_DXY
 #define AFX_DTG_DXY 0
+#endif
+//   AFX_DTG_DEFER=1 (without the preload): the wall-ghost stores move behind the slot loop, so no store sits between two
+//   neighbour gathers and the compiler may overlap them as far as its register budget allows (same values, same bits).
+#ifndef AFX_DTG_DEFER
+#define AFX_DTG_DEFER 0
 #endif
 
 namespace afx {
@@ -265,9 +273,13 @@ __global__ void __launch_bounds__(AFX_DTG_THREADS, AFX_DTG_MINB) k_dt_grad(DevMe
 #else
         const int kind = (v & CF_BND) ? (int)m.fkind[m.cf[(size_t)s * m.N + i] & CF_ID] : K_INTERNAL;
         const bool wall_ghost = walls && (v & CF_BND) && (kind == K_SLIPWALL || kind == K_WALL);
+#if AFX_DTG_DEFER
+        if (wall_ghost) wall_slots |= 1u << s;
+#else
         if (wall_ghost) q[j] = qi;  // ghost <- owner (set_walls_from_internal)
-        const d4 qj = wall_ghost ? qi : q[j];
         if (LIM && wall_ghost) wall_slots |= 1u << s;
+#endif
+        const d4 qj = wall_ghost ? qi : q[j];
 #endif
         const d4 qL = side ? qj : qi, qR = side ? qi : qj;  // states of cell0 / cell1
         const double nx = gA.x, ny = gA.y, len = gA.z;
@@ -296,7 +308,7 @@ __global__ void __launch_bounds__(AFX_DTG_THREADS, AFX_DTG_MINB) k_dt_grad(DevMe
             }
         }
     }
-#if AFX_DTG_PRELOAD
+#if AFX_DTG_PRELOAD || AFX_DTG_DEFER
     if (wall_slots) {  // ghost <- owner (set_walls_from_internal)
 #pragma unroll
         for (int s = 0; s < 4; ++s)
@@ -363,7 +375,7 @@ __global__ void __launch_bounds__(AFX_DTG_THREADS, AFX_DTG_MINB) k_dt_grad(DevMe
             hi.x = dmax2(hi.x, qj.x); hi.y = dmax2(hi.y, qj.y); hi.z = dmax2(hi.z, qj.z); hi.w = dmax2(hi.w, qj.w);
         }
 #if AFX_FAST
-        if (pm) {  // the projected extremes for the limiter kernels of the later stages (see projected_extremes)
+        if (LIM == 2 || pm) {  // the projected extremes for the limiter kernels of the later stages (see projected_extremes); LIM == 2: known at compile time
             d4 pmax, pmin;
             projected_extremes(ax, ay, dxy, valid, pmax, pmin);
             pm[2 * (size_t)i] = pmax; pm[2 * (size_t)i + 1] = pmin;
@@ -373,6 +385,7 @@ __global__ void __launch_bounds__(AFX_DTG_THREADS, AFX_DTG_MINB) k_dt_grad(DevMe
             return;
         }
 #endif
+        if (LIM == 2) return;  // (fast mode only; the host never launches <., 2> in strict mode)
         lim[i] = limiter_value(qi, lo, hi, ax, ay, dxy, valid, limiter_k3a(A, limiter_k));
     }
 }
@@ -400,6 +413,9 @@ __device__ __forceinline__ LimCell limiter_load_static(const DevMesh& m, uint32_
     return c;
 }
 // the limiter of cell i from the stage state and the gradients (shared by k_limiter and the pipelined stage kernel k_pipe)
+// PM: 1 = the stored projected extremes are there (compile-time: k_limiter<1> carries no registers for the other path),
+//     0 = they are not, -1 = decided by `pm` at run time
+template <int PM = -1>
 __device__ __forceinline__ void limiter_cell(const DevMesh& m, uint32_t i, const LimCell& c, const d4* qk, const d4* gx, const d4* gy, d4* lim,
                                              double limiter_k, int walls, const d4* pm = nullptr)
 {
@@ -425,7 +441,7 @@ __device__ __forceinline__ void limiter_cell(const DevMesh& m, uint32_t i, const
         hi.x = dmax2(hi.x, qj.x); hi.y = dmax2(hi.y, qj.y); hi.z = dmax2(hi.z, qj.z); hi.w = dmax2(hi.w, qj.w);
     }
 #if AFX_FAST
-    if (pm) {  // extremes of the projected increments stored by k_dt_grad: neither the gradients nor the face offsets are read
+    if (PM == 1 || (PM == -1 && pm)) {  // extremes of the projected increments stored by k_dt_grad: neither the gradients nor the face offsets are read
         const d4 pmax = pm[2 * (size_t)i], pmin = pm[2 * (size_t)i + 1];
         const d4 dmax = mk4(hi.x - qi.x, hi.y - qi.y, hi.z - qi.z, hi.w - qi.w);
         const d4 dmin = mk4(lo.x - qi.x, lo.y - qi.y, lo.z - qi.z, lo.w - qi.w);
@@ -433,10 +449,15 @@ __device__ __forceinline__ void limiter_cell(const DevMesh& m, uint32_t i, const
         return;
     }
 #endif
+    if (PM == 1) return;  // (strict mode never stores extremes; the host never launches <1> there)
     lim[i] = limiter_value(qi, lo, hi, gx[i], gy[i], dxy, valid, limiter_k3a(area_i, limiter_k));
 }
 
-__global__ void __launch_bounds__(AFX_LIM_THREADS, AFX_LIM_MINB) k_limiter(DevMesh m, const d4* qk, const d4* gx,
+#ifndef AFX_LIM_PM_MINB  // resident CTAs per SM asked for the stored-extremes instantiation (it needs fewer registers)
+#define AFX_LIM_PM_MINB AFX_LIM_MINB
+#endif
+template <int PM>
+__global__ void __launch_bounds__(AFX_LIM_THREADS, PM ? AFX_LIM_PM_MINB : AFX_LIM_MINB) k_limiter(DevMesh m, const d4* qk, const d4* gx,
                                                  const d4* gy, d4* lim, double limiter_k, int walls,
                                                  uint32_t lo1, uint32_t n1, uint32_t lo2, uint32_t n2, const d4* pm)
 {
@@ -445,9 +466,9 @@ __global__ void __launch_bounds__(AFX_LIM_THREADS, AFX_LIM_MINB) k_limiter(DevMe
     if (t >= n1 + n2) return;
     const uint32_t i = t < n1 ? lo1 + t : lo2 + (t - n1);
     pdl_launch_dependents();
-    const LimCell c = limiter_load_static(m, i, !(AFX_FAST && pm));
+    const LimCell c = limiter_load_static(m, i, !PM);
     pdl_wait();  // stage state and gradients come from the previous kernels
-    limiter_cell(m, i, c, qk, gx, gy, lim, limiter_k, walls, pm);
+    limiter_cell<PM>(m, i, c, qk, gx, gy, lim, limiter_k, walls, pm);
 }
 
 // ---------------------------------------------------------------------------
@@ -998,7 +1019,8 @@ static void dt_grad(int grad, const DevMesh& m, d4* q, double* dt, d4* gx, d4* g
 {
     const unsigned nb = nblk(m.n_grad, AFX_DTG_THREADS);
 #define AFX_DTG(G, L) launch_pdl(k_dt_grad<G, L>, nb, AFX_DTG_THREADS, st, m, q, dt, gx, gy, prm, gam, want_grad, walls, lim, limiter_k, pm)
-    if (lim && want_grad) { if (grad == 0) AFX_DTG(0, 1); else AFX_DTG(1, 1); }
+    if (lim && want_grad && AFX_FAST && pm) { if (grad == 0) AFX_DTG(0, 2); else AFX_DTG(1, 2); }
+    else if (lim && want_grad) { if (grad == 0) AFX_DTG(0, 1); else AFX_DTG(1, 1); }
     else { if (grad == 0) AFX_DTG(0, 0); else AFX_DTG(1, 0); }
 #undef AFX_DTG
 }
@@ -1006,7 +1028,8 @@ static void limiter(const DevMesh& m, const d4* qk, const d4* gx, const d4* gy, 
                     uint32_t lo2, uint32_t n2, const d4* pm, cudaStream_t st)
 {
     if (n1 + n2 == 0) return;
-    launch_pdl(k_limiter, nblk(n1 + n2, AFX_LIM_THREADS), AFX_LIM_THREADS, st, m, qk, gx, gy, lim, k, walls, lo1, n1, lo2, n2, pm);
+    if (AFX_FAST && pm) launch_pdl(k_limiter<1>, nblk(n1 + n2, AFX_LIM_THREADS), AFX_LIM_THREADS, st, m, qk, gx, gy, lim, k, walls, lo1, n1, lo2, n2, pm);
+    else launch_pdl(k_limiter<0>, nblk(n1 + n2, AFX_LIM_THREADS), AFX_LIM_THREADS, st, m, qk, gx, gy, lim, k, walls, lo1, n1, lo2, n2, (const d4*)nullptr);
 }
 static void flux(int second, int visc, int uniform, const DevMesh& m, const d4* qk, const d4* q0, const d4* gx, const d4* gy,
                  const d4* lim, d4* fl, const GasC& g, d4 qfar, cudaStream_t st)

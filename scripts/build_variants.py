@@ -26,6 +26,15 @@ VARIANTS = {
     "pipe_ept4": ["-DAFX_PIPE_EPT=4"],
     "pipe_t128": ["-DAFX_PIPE_THREADS=128", "-DAFX_PIPE_MINB=8", "-DAFX_PIPE_EPT=4"],
     "pipe_r80": ["-DAFX_PIPE_THREADS=256", "-DAFX_PIPE_MINB=3", "-DAFX_PIPE_EPT=2"],
+    # round 2, final A/B: the stored-extremes limiter instantiation at more CTAs per SM, k_dt_grad at fewer (no spills), deferred wall-ghost stores
+    "lpm9": ["-DAFX_LIM_PM_MINB=9"],
+    "lpm10": ["-DAFX_LIM_PM_MINB=10"],
+    "dtg5": ["-DAFX_DTG_MINB=5"],
+    "dtg4": ["-DAFX_DTG_MINB=4"],
+    "defer": ["-DAFX_DTG_DEFER=1"],
+    "defer5": ["-DAFX_DTG_DEFER=1", "-DAFX_DTG_MINB=5"],
+    "defer4": ["-DAFX_DTG_DEFER=1", "-DAFX_DTG_MINB=4"],
+    "lpm9_defer5": ["-DAFX_LIM_PM_MINB=9", "-DAFX_DTG_DEFER=1", "-DAFX_DTG_MINB=5"],
     "nopreload_t128_pf": ["-DAFX_DTG_PRELOAD=0", "-DAFX_DTG_THREADS=128", "-DAFX_DTG_MINB=6", "-DAFX_DTG_DXY=1"],
 }
 for name, defs in VARIANTS.items():

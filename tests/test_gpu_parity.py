@@ -337,6 +337,29 @@ def test_first_stage_limiter_inside_dt_grad_is_bit_identical(afx, gpu, monkeypat
     assert outs[0][2] == 10 and outs[1][2] == 11  # kernels per explicit iteration (the last one adds up the residual norm)
 
 
+@pytest.mark.parametrize("grad,visc", [("green-gauss", "spallart-allmaras"), ("least-squares", "laminar")])
+def test_stored_limiter_extremes_match_the_gradient_reading_limiter(afx, gpu, monkeypatch, grad, visc):
+    """Fast mode: k_dt_grad<., 2> stores the largest positive / most negative projected increment of every cell and k_limiter<1>
+    (stages 2 and 3) reads those 64 bytes instead of gx, gy and the four face offsets.  The extremes are the values k_limiter<0>
+    computes from the same gradients and offsets, so limiters, state and norms agree (FMA contraction may differ between the two
+    inlining contexts: 1e-11), and both stay within the north-star 1e-10 of strict mode."""
+    m = afx.Mesh.synth_omesh(160, 80, 24, 100.0)
+    bcs = {"farfield": ("farfield", dict(mach=0.25, angle=0.03, T=1.0, p=1.0)), "wall": ("wall" if visc != "inviscid" else "slip-wall", None)}
+    outs = {}
+    for key, math, pm in (("pm", "fast", "1"), ("nopm", "fast", "0"), ("strict", "strict", "1")):
+        monkeypatch.setenv("AFX_LIM_PM", pm)
+        s = afx.GpuSolver(m, viscosity=visc, math=math)
+        s.set_bcs(bcs); s.set_options(True, grad, 5.0, 1.5); s.init(); s.refill_bcs()
+        s.set_q(H.synth_state(m.N, s.get_q()))
+        norms = s.run(8, 0.9)
+        outs[key] = (norms, s.get_q(), s.get("limiters"))
+    np.testing.assert_allclose(outs["pm"][0], outs["nopm"][0], rtol=1e-11)
+    np.testing.assert_allclose(outs["pm"][1], outs["nopm"][1], rtol=1e-11, atol=1e-14)
+    np.testing.assert_allclose(outs["pm"][2], outs["nopm"][2], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(outs["pm"][0], outs["strict"][0], rtol=1e-10)
+    assert 0.0 < outs["pm"][2].min() < 1.0  # the limiter is active somewhere: the comparison is not of ones with ones
+
+
 
 
 
