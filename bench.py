@@ -93,6 +93,34 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(local):
+    """N > 1: keep this rank -- and the pinned host buffers it allocates for the end-to-end leg -- on the CPUs next to its GPU
+    (nvmlDeviceGetCpuAffinity).  torchrun does not place its ranks: with 8 of them moving 2 x 67 MB per step at once, buffers on
+    the far socket go through the inter-socket links (round 1: e2e at N = 8 was 2.5x N = 1 for 1/8 of the bytes per rank).
+    Returns the number of CPUs the rank may use, or None when the topology cannot be read (nothing is changed then).
+    AFX_BENCH_NUMA=0 disables."""
+    if os.environ.get("AFX_BENCH_NUMA", "1") == "0":
+        return None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        idx = local
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",")]
+            if not all(v.isdigit() for v in ids):
+                return None
+            idx = int(ids[local])
+        mask = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(idx), ((os.cpu_count() or 64) + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1} & os.sched_getaffinity(0)
+        if len(cpus) < 2:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return None
+
+
 def reference_cpu(steps, warmup, sample=CPU_SAMPLE):
     """The reference's own explicitSolver on the host cores (oracle/_ref), bounded sample of the workload."""
     import aeroflex_b200 as afx
@@ -321,6 +349,7 @@ def main():
     if a.fused:
         os.environ["AFX_FUSED"] = "1"  # the tiles (and the graph-bisection numbering) are built at creation
     os.environ["AFX_FUSE_LIM0"] = "1" if a.fuse_lim0 else "0"
+    numa_cpus = bind_to_gpu_numa_node(local) if world > 1 else None  # before the library starts its OpenMP threads
     import torch
     import aeroflex_b200 as afx
     if afx.device_count() <= 0:
@@ -360,6 +389,9 @@ def main():
     s.get_q(base)  # a partitioned solver fills its own entries of the global vector
     q0 = perturbed(base, N)  # multiplicative, by GLOBAL index: every rank perturbs its own entries exactly as one GPU would
     del base
+    if world > 1:
+        details["numa"] = ("rank 0 bound to the %d CPUs next to its GPU (pinned e2e buffers allocated there)" % numa_cpus) if numa_cpus \
+            else "ranks not bound (topology unavailable or AFX_BENCH_NUMA=0)"
     details["parallelism"] = "1 GPU" if world == 1 else \
         "domain decomposition: %d %s partitions, 2-layer halo refreshed every RK stage, halo=%s (this rank: %d owned + %d halo cells, %d peers)" \
         % (world, os.environ.get("AFX_PARTITION", "hilbert"), s.halo_mode(), part.n_own, part.n_r1 + part.n_r2, part.n_peers)

@@ -122,3 +122,36 @@ def test_sweep_fmg_equals_the_loop_written_with_primitive_calls(afx, gpu, fmg_le
     assert list(ra["iterations"]) == iters
     assert np.array_equal(np.array(forces), np.stack([ra["cl"], ra["cd"], ra["cm"]], axis=1))
     assert np.array_equal(a[1].get_q(), b[1].get_q()) and np.array_equal(a[0].get_q(), b[0].get_q())
+
+
+def test_polar_chains_match_the_reference_polar(afx, gpu, fmg_levels):
+    """BASELINE configs[4] at the reference's own settings (conf.ini: implicit, FMG coarse -> mid, tolerance 1e-4, <= 300 iterations
+    per level): the 48 angles alpha = -10 ... 13.5 deg of the 64-angle polar, as the six warm-started chains of eight that
+    `bench.py --workload polar64 --gpus 8` gives to its first six ranks, against the UNMODIFIED reference's run_airfoil loop on the
+    same chains (tests/golden/polar64_reference.npz, oracle/make_golden_polar64.py; the two chains beyond 14 deg are stalled
+    inviscid flow on which the reference itself needs hours).  Both sides stop at 1e-4, with different linear solvers, so the forces
+    agree to a few 1e-4 -- this pins the polar a user of the reference gets, not the arithmetic (that is test_gpu_converged.py) --
+    and the outer iteration counts show the GMRES + block-Jacobi step is as strong as the reference's ILUT + GMRES on this case."""
+    g = np.load(H.GOLDEN + "/polar64_reference.npz")
+    mc, mm, csr = fmg_levels
+    bcs = {"farfield": ("farfield", dict(mach=0.2, angle=0.0, T=1.0, p=1.0)), "wall": ("slip-wall", None)}
+    al = g["alphas"]
+    assert len(al) % 8 == 0
+    cl, cd, cm, it = [], [], [], []
+    for k in range(len(al) // 8):
+        levels = [afx.GpuSolver(m, math="fast") for m in (mc, mm)]  # a fresh chain: its first angle starts from the free stream
+        for s in levels:
+            s.set_bcs(bcs); s.set_options(True, "green-gauss", 5.0, 40.0)
+        P = afx.Prolongation(levels[0], levels[1], *csr)
+        r = afx.sweep_fmg(levels, [P], al[8 * k:8 * k + 8], implicit=True, relaxation=0.9, start_cfl=40.0, slope_cfl=50.0, max_cfl=100.0,
+                          tolerance=1e-4, rhs_iterations=5, max_iterations=300)
+        assert r["status"] == 0 and np.all(r["residual"] <= 1e-4)
+        cl += list(r["cl"]); cd += list(r["cd"]); cm += list(r["cm"]); it += list(r["iterations"])
+    cl, cd, cm, it = map(np.array, (cl, cd, cm, it))
+    np.testing.assert_allclose(cl, g["cl"], rtol=0, atol=1e-3)   # |CL| <= 1.2: the lift curve to 1e-3
+    np.testing.assert_allclose(cd, g["cd"], rtol=0, atol=1.5e-4)
+    np.testing.assert_allclose(cm, g["cm"], rtol=0, atol=1e-4)
+    assert np.median(np.abs(cl - g["cl"])) < 1e-4
+    # as strong as the reference's linear solve: never more than 1.5x its outer iterations (+5), and not more in total
+    assert np.all(it <= 1.5 * g["iters"] + 5), (it, g["iters"])
+    assert it.sum() <= 1.15 * g["iters"].sum(), (it.sum(), g["iters"].sum())
