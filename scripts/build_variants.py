@@ -35,6 +35,12 @@ VARIANTS = {
     "defer5": ["-DAFX_DTG_DEFER=1", "-DAFX_DTG_MINB=5"],
     "defer4": ["-DAFX_DTG_DEFER=1", "-DAFX_DTG_MINB=4"],
     "lpm9_defer5": ["-DAFX_LIM_PM_MINB=9", "-DAFX_DTG_DEFER=1", "-DAFX_DTG_MINB=5"],
+    # CTA shapes never timed before the last call of round 2
+    "f64": ["-DAFX_FLUX_THREADS=64"],
+    "l64": ["-DAFX_LIM_THREADS=64"],
+    "f128x7": ["-DAFX_FLUX_MINB=7"],
+    "dtg64x10": ["-DAFX_DTG_THREADS=64", "-DAFX_DTG_MINB=10"],
+    "dtg256x2": ["-DAFX_DTG_THREADS=256", "-DAFX_DTG_MINB=2"],
     "nopreload_t128_pf": ["-DAFX_DTG_PRELOAD=0", "-DAFX_DTG_THREADS=128", "-DAFX_DTG_MINB=6", "-DAFX_DTG_DXY=1"],
 }
 for name, defs in VARIANTS.items():
