@@ -273,6 +273,13 @@ struct Solver {
     unsigned int norm_idx_host = 0;
 
     cudaGraphExec_t graph_exec = nullptr;
+    // One Arnoldi step (product + sweeps, inner products, update + norm, rotation, scaling: 8 small kernels) as a graph per step
+    // index, replayed with one call: the Krylov iteration of the shipped meshes is bound by launches.  Single-rank solvers only
+    // (a partitioned step has exchanges and all-reduces between the kernels).  AFX_KRY_GRAPH=0 disables.
+    std::vector<cudaGraphExec_t> kry_graph;
+    std::vector<int> kry_graph_launches;
+    bool use_kry_graph = true;
+    void invalidate_kry_graphs() { for (auto& g : kry_graph) if (g) cudaGraphExecDestroy(g); kry_graph.clear(); kry_graph_launches.clear(); }
     int64_t graph_per_iter = 0;  // kernels of ours in one captured iteration
     bool use_graph = true;
     int64_t launches = 0;
@@ -293,6 +300,7 @@ struct Solver {
     {
         cudaSetDevice(device);
         if (graph_exec) cudaGraphExecDestroy(graph_exec);
+        invalidate_kry_graphs();
         if (h_pinned) cudaFreeHost(h_pinned);
         for (auto& e : evp) if (e) cudaEventDestroy(e);
         if (ev0) cudaEventDestroy(ev0);
@@ -346,7 +354,7 @@ struct Solver {
     template <int MODE, int LAST>
     void launch_gather(const d4* qk_in, d4* qk_out, d4* vec_out, double alpha, bool walls);
     void explicit_iteration();
-    void invalidate_graph() { if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; } }
+    void invalidate_graph() { if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; } invalidate_kry_graphs(); }
     void run_explicit(double relax, int n_iter, double* norms_out);
     double fetch_last_norm();
     void check_norm(double v) { if (!(v == v) || std::isinf(v)) throw NumericError("residual norm is not finite"); }
@@ -627,6 +635,7 @@ void Solver::create(const afx_mesh_desc& m, const afx_gas& g, int visc, int dev,
     gx.view(grad.p, NT); gy.view(grad.p + NT, NT);
     for (DBuf<d4>* b : {&q, &qkA, &qkB, &lim, &qW, &rhs, &stage}) { b->alloc(NT); b->zero(st); }
     if (const char* e = getenv("AFX_LIM_PM")) use_pm = !(e[0] == '0');
+    if (const char* e = getenv("AFX_KRY_GRAPH")) use_kry_graph = !(e[0] == '0');
     pm.alloc(2 * (size_t)NT); pm.zero(st);
     set_l2_window();
     flux.alloc(E); flux.zero(st);
@@ -1474,6 +1483,7 @@ int Solver::compute_preconditioner()
     use();
     if (!jac_valid) throw InvalidArg("afx_rans_fill_jacobian has not been called for the current state");
     if (!Dinv.p) {
+        invalidate_kry_graphs();  // they hold the addresses of these buffers
         Dinv.alloc((size_t)NT * 16); kry_flag.alloc(2);  // [0] singular diagonal block, [1] the Krylov iteration's stop flag
         kry_state.alloc((size_t)kt->gmres_state_doubles(gmres_restart)); kry_state.zero(st);
         kry_V.alloc((size_t)(gmres_restart + 1) * NT); kry_w.alloc(NT); kry_z.alloc(NT); kry_t.alloc(NT); kry_x.alloc(NT);
@@ -1565,17 +1575,37 @@ bool Solver::gmres(const d4* b, d4* x)
         while (k < m && last_linear_iters + (k - k_done) < gmres_max_iter && !done) {
             const int nb = std::min({batch, m - k, gmres_max_iter - last_linear_iters - (k - k_done)});
             for (int j = 0; j < nb; ++j, ++k) {
-                // w = M^-1 A v_k   (product + first sweep, the other sweeps, dots, update + norm, rotation, scaling)
-                precondition_Ax(kry_V.p + (size_t)k * stride, kry_z.p, kry_w.p, stop);
-                // h = V^T w ; w -= V h ; ||w||^2
-                kt->multi_dot1(nd, kry_V.p, stride, k + 1, kry_w.p, kry_partial.p, kry_h.p, kry_counter.p, stop, st); ++launches;
-                allreduce_sum(kry_h.p, k + 1);
-                kt->axpy_norm(nd, kry_V.p, stride, k + 1, kry_h.p, -1.0, kry_w.p, kry_partial.p, kry_h.p + (k + 1), kry_counter.p, stop, st); ++launches;
-                allreduce_sum(kry_h.p + (k + 1), 1);
-                kt->givens_step(m, kry_state.p, kry_h.p, k, gmres_tol, stop, st); ++launches;
-                if (k + 1 < m) {  // v_{k+1} = w / ||w||   (kry_h[k+1] holds ||w||^2); skipped on the device once the iteration has stopped
-                    kt->scale_from(NT, kry_w.p, kry_h.p + (k + 1), 1, 1, kry_V.p + (size_t)(k + 1) * stride, stop, st); ++launches;
-                    halo_refresh(kry_V.p + (size_t)(k + 1) * stride);
+                auto arnoldi_step = [&] {
+                    // w = M^-1 A v_k   (product + first sweep, the other sweeps, dots, update + norm, rotation, scaling)
+                    precondition_Ax(kry_V.p + (size_t)k * stride, kry_z.p, kry_w.p, stop);
+                    // h = V^T w ; w -= V h ; ||w||^2
+                    kt->multi_dot1(nd, kry_V.p, stride, k + 1, kry_w.p, kry_partial.p, kry_h.p, kry_counter.p, stop, st); ++launches;
+                    allreduce_sum(kry_h.p, k + 1);
+                    kt->axpy_norm(nd, kry_V.p, stride, k + 1, kry_h.p, -1.0, kry_w.p, kry_partial.p, kry_h.p + (k + 1), kry_counter.p, stop, st); ++launches;
+                    allreduce_sum(kry_h.p + (k + 1), 1);
+                    kt->givens_step(m, kry_state.p, kry_h.p, k, gmres_tol, stop, st); ++launches;
+                    if (k + 1 < m) {  // v_{k+1} = w / ||w||   (kry_h[k+1] holds ||w||^2); skipped on the device once the iteration has stopped
+                        kt->scale_from(NT, kry_w.p, kry_h.p + (k + 1), 1, 1, kry_V.p + (size_t)(k + 1) * stride, stop, st); ++launches;
+                        halo_refresh(kry_V.p + (size_t)(k + 1) * stride);
+                    }
+                };
+                if (use_kry_graph && use_graph && !halo) {  // the same kernels with the same arguments, captured once per step index
+                    if ((int)kry_graph.size() != m) { invalidate_kry_graphs(); kry_graph.assign(m, nullptr); kry_graph_launches.assign(m, 0); }
+                    if (!kry_graph[k]) {
+                        cudaGraph_t g = nullptr;
+                        const int64_t l0 = launches;
+                        CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+                        arnoldi_step();
+                        CK(cudaStreamEndCapture(st, &g));
+                        kry_graph_launches[k] = (int)(launches - l0);
+                        launches = l0;
+                        CK(cudaGraphInstantiate(&kry_graph[k], g, 0));
+                        CK(cudaGraphDestroy(g));
+                    }
+                    CK(cudaGraphLaunch(kry_graph[k], st));
+                    launches += kry_graph_launches[k];
+                } else {
+                    arnoldi_step();
                 }
             }
             read_status();
@@ -2135,6 +2165,7 @@ int afx_rans_set_linear_solver(afx_rans* s, int restart, int max_iterations, dou
         auto& S = s->s;
         if (restart < 1 || max_iterations < 1 || tolerance <= 0 || precond_sweeps < 1) throw afx::InvalidArg("bad linear solver settings");
         if (restart != S.gmres_restart) { S.Dinv.free(); S.precond_valid = false; }  // buffers are sized by the restart length
+        if (restart != S.gmres_restart || tolerance != S.gmres_tol || precond_sweeps != S.precond_sweeps) S.invalidate_kry_graphs();  // baked into the nodes
         S.gmres_restart = restart; S.gmres_max_iter = max_iterations; S.gmres_tol = tolerance; S.precond_sweeps = precond_sweeps;
     });
 }

@@ -295,6 +295,18 @@ def polar_main(a, rank, world, local):
                           "tolerance is asserted against the explicit-path fixture (tests/golden/converged_naca0012q_coarse_explicit.npz)"}
     if rank == 0:
         flat = [x for rws in allrows for x in rws]
+        if parity is not None and len(alphas) == 64:
+            # the whole polar against the unmodified reference's own run_airfoil loop on the same angles (tests/golden/polar64_reference.npz,
+            # 8 warm-started chains of 8, both sides stopped at 1e-4 with different linear solvers): the attached-flow range only --
+            # beyond 14 deg the inviscid flow stalls and both iterations run to their limits
+            gp = np.load(os.path.join(ROOT, "tests", "golden", "polar64_reference.npz"), allow_pickle=False)
+            ref_by_alpha = {float(x): k for k, x in enumerate(gp["alphas"])}
+            sel = [(r_, ref_by_alpha[r_["alpha"]]) for r_ in flat if r_["alpha"] <= 13.5 and r_["alpha"] in ref_by_alpha]
+            parity["polar_vs_reference"] = {
+                "angles_compared": len(sel), "tolerance_both_sides": 1e-4,
+                "max_abs_diff": {k: float(max(abs(r_[k] - float(gp[k][j])) for r_, j in sel)) for k in ("cl", "cd", "cm")},
+                "iterations": {"ours": int(sum(r_["iterations"] for r_, _ in sel)), "reference": int(sum(int(gp["iters"][j]) for _, j in sel))},
+                "same_chains": world == 8}
         print(json.dumps({"metric": "airfoil polar angles/s", "value": len(alphas) / t_max, "unit": "angles/s", "n_gpus": world, "steps": len(alphas), "warmup": 1,
                           "ms_per_step": t_max / max(1, len(mine)) * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                           "data": "shipped meshes (fixtures)", "config": config, "gpu_launches": int(launches), "seconds": t_max,

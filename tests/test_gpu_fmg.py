@@ -129,14 +129,16 @@ def test_polar_chains_match_the_reference_polar(afx, gpu, fmg_levels):
     per level): the 48 angles alpha = -10 ... 13.5 deg of the 64-angle polar, as the six warm-started chains of eight that
     `bench.py --workload polar64 --gpus 8` gives to its first six ranks, against the UNMODIFIED reference's run_airfoil loop on the
     same chains (tests/golden/polar64_reference.npz, oracle/make_golden_polar64.py; the two chains beyond 14 deg are stalled
-    inviscid flow on which the reference itself needs hours).  Both sides stop at 1e-4, with different linear solvers, so the forces
+    inviscid flow on which the reference itself needs hours and hits its iteration limit).  Both sides stop at 1e-4, with different linear solvers, so the forces
     agree to a few 1e-4 -- this pins the polar a user of the reference gets, not the arithmetic (that is test_gpu_converged.py) --
     and the outer iteration counts show the GMRES + block-Jacobi step is as strong as the reference's ILUT + GMRES on this case."""
     g = np.load(H.GOLDEN + "/polar64_reference.npz")
     mc, mm, csr = fmg_levels
     bcs = {"farfield": ("farfield", dict(mach=0.2, angle=0.0, T=1.0, p=1.0)), "wall": ("slip-wall", None)}
-    al = g["alphas"]
-    assert len(al) % 8 == 0
+    n = 48  # the fixture also holds the chains beyond 14 deg as far as the reference has finished them (stalled flow: its iteration
+    #         runs to the 300-iteration limit per level from 16.5 deg on, and so does ours); they are not compared
+    al = g["alphas"][:n]
+    g = {k: g[k][:n] for k in ("cl", "cd", "cm", "iters")}
     cl, cd, cm, it = [], [], [], []
     for k in range(len(al) // 8):
         levels = [afx.GpuSolver(m, math="fast") for m in (mc, mm)]  # a fresh chain: its first angle starts from the free stream

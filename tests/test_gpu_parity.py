@@ -309,6 +309,30 @@ def test_implicit_converged_forces_match_reference(afx, gpu, math):
     print("implicit outer iterations:", len(hist), "last linear iterations:", s.last_linear_iterations())
 
 
+@pytest.mark.parametrize("math", ["strict", "fast"])
+def test_arnoldi_step_graphs_replay_the_same_kernels(afx, gpu, monkeypatch, math):
+    """The eight kernels of an Arnoldi step are captured once per step index and replayed with one call (AFX_KRY_GRAPH, default on):
+    same kernels, same arguments, same order -- the implicit iteration must be bit-identical to plain launches, linear iteration
+    counts and launch counts included."""
+    m = afx.Mesh.synth_omesh(96, 48, 16, 60.0)
+    bcs = {"farfield": ("farfield", dict(mach=0.2, angle=0.05, T=1.0, p=1.0)), "wall": ("slip-wall", None)}
+    outs = []
+    for graph in ("1", "0"):
+        monkeypatch.setenv("AFX_KRY_GRAPH", graph)
+        s = afx.GpuSolver(m, math=math)
+        s.set_bcs(bcs); s.set_options(True, "green-gauss", 5.0, 40.0); s.init(); s.refill_bcs()
+        l0 = s.launch_count()
+        hist = run_implicit(s, 1e-6, max_iter=12)
+        outs.append((np.array(hist), s.get_q(), s.last_linear_iterations(), s.launch_count() - l0))
+        s.set_linear_solver(restart=8, max_iterations=200, tolerance=1e-3, precond_sweeps=3)  # new restart length / sweeps: the cached graphs must go
+        hist2 = run_implicit(s, 1e-8, max_iter=6)
+        outs[-1] += (np.array(hist2), s.get_q())
+    a, b = outs
+    assert len(a[0]) > 3 and a[0][-1] >= 0
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == b[2] and a[3] == b[3]
+    assert np.array_equal(a[4], b[4]) and np.array_equal(a[5], b[5])
+
+
 @pytest.mark.parametrize("grad,visc,math", [("green-gauss", "inviscid", "strict"), ("least-squares", "laminar", "strict"), ("green-gauss", "spallart-allmaras", "fast")])
 def test_first_stage_limiter_inside_dt_grad_is_bit_identical(afx, gpu, monkeypatch, grad, visc, math):
     """k_dt_grad<.,1> writes the first stage's limiters itself (one k_limiter launch less per iteration): same
