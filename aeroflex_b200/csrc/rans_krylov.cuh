@@ -155,14 +155,14 @@ __global__ void __launch_bounds__(256) k_multi_dot_final(int nblocks, const doub
 // The same final sums without a second launch: the block that finishes last (device-wide counter) adds the partials of
 // every j exactly as k_multi_dot_final does -- same strided order per thread, same block_sum tree -- so the results carry
 // the same bits.  The Krylov iteration of the shipped meshes is bound by launches, not by bytes.
-__device__ __forceinline__ void dot_finish_by_last_block(int k, const double* partial, double* out, unsigned int* counter)
+__device__ __forceinline__ bool dot_finish_by_last_block(int k, const double* partial, double* out, unsigned int* counter)
 {
     __shared__ bool last;
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) last = (atomicAdd(counter, 1u) == gridDim.x - 1);
     __syncthreads();
-    if (!last) return;
+    if (!last) return false;
     for (int j = 0; j < k; ++j) {
         double acc = 0;
         for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) acc += __ldcg(&partial[(size_t)j * gridDim.x + b]);
@@ -170,6 +170,7 @@ __device__ __forceinline__ void dot_finish_by_last_block(int k, const double* pa
         if (threadIdx.x == 0) out[j] = t;
     }
     if (threadIdx.x == 0) *counter = 0;
+    return true;  // in every thread of the last block; out[] was written by its thread 0
 }
 
 // multi_dot in one launch
@@ -298,9 +299,8 @@ __global__ void k_gmres_begin(GmresLayout L, double* st, const double* __restric
 }
 // Arnoldi step k is done (h[0..k] = V^T w, h[k+1] = ||w||^2 after orthogonalisation): new Hessenberg column, the earlier
 // rotations, the new rotation, the residual estimate |g[k+1]| / r0 -- the recurrence Solver::gmres ran on the host.
-__global__ void k_givens_step(GmresLayout L, double* st, const double* __restrict__ h, int k, double tol, int* stop)
+__device__ __forceinline__ void givens_step_body(const GmresLayout& L, double* st, const double* h, int k, double tol, int* stop)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0 || *stop) return;
     const int m = L.m;
     double* H = st + L.H(); double* cs = st + L.cs(); double* sn = st + L.sn(); double* g = st + L.g();
     const double hn = sqrt(h[k + 1]);
@@ -319,6 +319,32 @@ __global__ void k_givens_step(GmresLayout L, double* st, const double* __restric
     st[L.err()] = err;
     st[L.k_done()] = (double)(k + 1);
     if (err < tol || hn == 0) *stop = 1;
+}
+__global__ void k_givens_step(GmresLayout L, double* st, const double* __restrict__ h, int k, double tol, int* stop)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0 || *stop) return;
+    givens_step_body(L, st, h, k, tol, stop);
+}
+// k_axpy_norm (Gram-Schmidt update + ||w||^2 -> h[k]) followed, in the block that finished the norm, by the rotation of step k - 1:
+// one launch instead of two.  h = [V^T w (k entries) | ||w||^2]; same arithmetic in the same order as the two kernels.
+__global__ void __launch_bounds__(256) k_axpy_norm_givens(uint32_t n, const d4* __restrict__ V, size_t stride, int k, const double* c, double sign, d4* w,
+                                                          double* partial, double* h, unsigned int* counter, GmresLayout L, double* st, double tol, int* stop)
+{
+    if (*stop) return;
+    double acc = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        d4 a = w[i];
+        for (int j = 0; j < k; ++j) {
+            const double cj = sign * c[j];
+            const d4 v = V[(size_t)j * stride + i];
+            a.x += cj * v.x; a.y += cj * v.y; a.z += cj * v.z; a.w += cj * v.w;
+        }
+        w[i] = a;
+        acc += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+    }
+    const double t = block_sum(acc);
+    if (threadIdx.x == 0) partial[blockIdx.x] = t;
+    if (dot_finish_by_last_block(1, partial, h + k, counter) && threadIdx.x == 0) givens_step_body(L, st, h, k - 1, tol, stop);
 }
 // H y = g for the k columns done (back substitution), y -> out[0..k)
 __global__ void k_gmres_solve_y(GmresLayout L, const double* __restrict__ st, double* __restrict__ out)
@@ -368,6 +394,11 @@ static void axpy_norm(uint32_t n, const d4* V, size_t stride, int k, const doubl
                       unsigned int* counter, const int* stop, cudaStream_t st)
 {
     k_axpy_norm<<<KRY_BLOCKS, 256, 0, st>>>(n, V, stride, k, c, sign, w, partial, out, counter, stop);
+}
+static void axpy_norm_givens(uint32_t n, const d4* V, size_t stride, int k, const double* c, double sign, d4* w, double* partial, double* h,
+                             unsigned int* counter, int m, double* state, double tol, int* stop, cudaStream_t st)
+{
+    k_axpy_norm_givens<<<KRY_BLOCKS, 256, 0, st>>>(n, V, stride, k, c, sign, w, partial, h, counter, GmresLayout{m}, state, tol, stop);
 }
 static void spmv_sweep0(const DevMesh& m, const d4* J, const double* D, const double* Dinv, const d4* x, d4* r, d4* z, const int* stop, cudaStream_t st)
 {

@@ -279,6 +279,7 @@ struct Solver {
     std::vector<cudaGraphExec_t> kry_graph;
     std::vector<int> kry_graph_launches;
     bool use_kry_graph = true;
+    bool fuse_givens = true;  // AFX_KRY_FUSE_GIVENS=0: the rotation in its own launch (k_givens_step), as on partitioned solvers
     void invalidate_kry_graphs() { for (auto& g : kry_graph) if (g) cudaGraphExecDestroy(g); kry_graph.clear(); kry_graph_launches.clear(); }
     int64_t graph_per_iter = 0;  // kernels of ours in one captured iteration
     bool use_graph = true;
@@ -636,6 +637,7 @@ void Solver::create(const afx_mesh_desc& m, const afx_gas& g, int visc, int dev,
     for (DBuf<d4>* b : {&q, &qkA, &qkB, &lim, &qW, &rhs, &stage}) { b->alloc(NT); b->zero(st); }
     if (const char* e = getenv("AFX_LIM_PM")) use_pm = !(e[0] == '0');
     if (const char* e = getenv("AFX_KRY_GRAPH")) use_kry_graph = !(e[0] == '0');
+    if (const char* e = getenv("AFX_KRY_FUSE_GIVENS")) fuse_givens = !(e[0] == '0');
     pm.alloc(2 * (size_t)NT); pm.zero(st);
     set_l2_window();
     flux.alloc(E); flux.zero(st);
@@ -1581,9 +1583,14 @@ bool Solver::gmres(const d4* b, d4* x)
                     // h = V^T w ; w -= V h ; ||w||^2
                     kt->multi_dot1(nd, kry_V.p, stride, k + 1, kry_w.p, kry_partial.p, kry_h.p, kry_counter.p, stop, st); ++launches;
                     allreduce_sum(kry_h.p, k + 1);
-                    kt->axpy_norm(nd, kry_V.p, stride, k + 1, kry_h.p, -1.0, kry_w.p, kry_partial.p, kry_h.p + (k + 1), kry_counter.p, stop, st); ++launches;
-                    allreduce_sum(kry_h.p + (k + 1), 1);
-                    kt->givens_step(m, kry_state.p, kry_h.p, k, gmres_tol, stop, st); ++launches;
+                    if (!halo && fuse_givens) {  // update + norm + rotation in one launch
+                        kt->axpy_norm_givens(nd, kry_V.p, stride, k + 1, kry_h.p, -1.0, kry_w.p, kry_partial.p, kry_h.p, kry_counter.p, m, kry_state.p, gmres_tol,
+                                             stop, st); ++launches;
+                    } else {
+                        kt->axpy_norm(nd, kry_V.p, stride, k + 1, kry_h.p, -1.0, kry_w.p, kry_partial.p, kry_h.p + (k + 1), kry_counter.p, stop, st); ++launches;
+                        allreduce_sum(kry_h.p + (k + 1), 1);
+                        kt->givens_step(m, kry_state.p, kry_h.p, k, gmres_tol, stop, st); ++launches;
+                    }
                     if (k + 1 < m) {  // v_{k+1} = w / ||w||   (kry_h[k+1] holds ||w||^2); skipped on the device once the iteration has stopped
                         kt->scale_from(NT, kry_w.p, kry_h.p + (k + 1), 1, 1, kry_V.p + (size_t)(k + 1) * stride, stop, st); ++launches;
                         halo_refresh(kry_V.p + (size_t)(k + 1) * stride);

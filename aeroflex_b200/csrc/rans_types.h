@@ -231,6 +231,10 @@ struct KernelTable {
     int (*gmres_state_doubles)(int m);
     void (*sub)(uint32_t n, const d4* a, const d4* b, d4* y, cudaStream_t st);
     void (*axpy_state)(uint32_t n, double relax, const d4* x, d4* q, cudaStream_t st);
+    // axpy_norm + givens_step in one launch: the block that finishes the norm also runs the rotation (single-rank solvers: a
+    // partitioned step all-reduces the norm between the two)
+    void (*axpy_norm_givens)(uint32_t n, const d4* V, size_t stride, int k, const double* c, double sign, d4* w, double* partial, double* h,
+                             unsigned int* counter, int m, double* state, double tol, int* stop, cudaStream_t st);
 };
 
 namespace strict { const KernelTable& table(); }  // -fmad=false, reference expression order: bit-identical to the CPU reference

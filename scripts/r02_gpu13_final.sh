@@ -8,6 +8,7 @@ timeout 300 python bench.py > gpurun_out/r02m_bench_16M.json 2> gpurun_out/r02m_
 timeout 120 python bench.py --workload synthetic-1M-mixed-omesh --steps 200 --warmup 10 --no-cpu-baseline > gpurun_out/r02m_bench_1M.json 2> gpurun_out/r02m_bench_1M.err; echo "bench1M rc=$?"
 timeout 120 python bench.py --workload confini-polar > gpurun_out/r02m_bench_confini_polar.json 2> gpurun_out/r02m_bench_confini_polar.err; echo "polar rc=$?"
 AFX_KRY_GRAPH=0 timeout 120 python bench.py --workload confini-polar > gpurun_out/r02m_bench_confini_polar_nograph.json 2> gpurun_out/r02m_bench_confini_polar_nograph.err; echo "polar (plain launches) rc=$?"
+AFX_KRY_FUSE_GIVENS=0 timeout 120 python bench.py --workload confini-polar > gpurun_out/r02m_bench_confini_polar_nofuse.json 2> gpurun_out/r02m_bench_confini_polar_nofuse.err; echo "polar (rotation in its own launch) rc=$?"
 AFX_GMRES_BATCH=12 timeout 120 python bench.py --workload confini-polar > gpurun_out/r02m_bench_confini_polar_batch12.json 2> gpurun_out/r02m_bench_confini_polar_batch12.err; echo "polar (batch 12) rc=$?"
 timeout 200 ncu --set full --clock-control none --import-source on -k regex:"k_flux|k_limiter|k_gather_update|k_dt_grad" -s 20 -c 9 -o gpurun_out/r02m_prof_1M -f python bench.py --workload synthetic-1M-mixed-omesh --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/r02m_ncu_full_1M.log 2>&1; echo "ncu full 1M rc=$?"
 timeout 200 ncu --set full --clock-control none --import-source on -k regex:"k_dt_grad" -s 3 -c 1 -o gpurun_out/r02m_prof_16M_dtgrad -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/r02m_ncu_full_16M_dtgrad.log 2>&1; echo "ncu dt_grad 16M rc=$?"
@@ -16,7 +17,7 @@ timeout 240 python bench.py --workload polar64 > gpurun_out/r02m_bench_polar64_1
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -s 2000 -c 6000 --csv --log-file gpurun_out/r02m_launches_polar.csv python bench.py --workload confini-polar > gpurun_out/r02m_ncu_list_polar.log 2>&1; echo "ncu list polar rc=$?"
 python - <<PY
 import json
-for n in ["r02m_bench_16M", "r02m_bench_1M", "r02m_bench_confini_polar", "r02m_bench_confini_polar_nograph", "r02m_bench_confini_polar_batch12", "r02m_bench_polar64_1gpu"]:
+for n in ["r02m_bench_16M", "r02m_bench_1M", "r02m_bench_confini_polar", "r02m_bench_confini_polar_nograph", "r02m_bench_confini_polar_nofuse", "r02m_bench_confini_polar_batch12", "r02m_bench_polar64_1gpu"]:
     try:
         d = json.loads(open("gpurun_out/%s.json" % n).read().strip().splitlines()[-1])
         r = d.get("roofline", {})

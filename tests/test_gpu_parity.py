@@ -310,27 +310,35 @@ def test_implicit_converged_forces_match_reference(afx, gpu, math):
 
 
 @pytest.mark.parametrize("math", ["strict", "fast"])
-def test_arnoldi_step_graphs_replay_the_same_kernels(afx, gpu, monkeypatch, math):
-    """The eight kernels of an Arnoldi step are captured once per step index and replayed with one call (AFX_KRY_GRAPH, default on):
-    same kernels, same arguments, same order -- the implicit iteration must be bit-identical to plain launches, linear iteration
-    counts and launch counts included."""
+def test_arnoldi_step_graphs_and_fused_rotation_are_bit_identical(afx, gpu, monkeypatch, math):
+    """The kernels of an Arnoldi step are captured once per step index and replayed with one call (AFX_KRY_GRAPH, default on), and the
+    Givens rotation runs in the block that finishes the norm of the update kernel instead of a launch of its own
+    (AFX_KRY_FUSE_GIVENS, default on): same arithmetic in the same order -- the implicit iteration must be bit-identical to plain,
+    separate launches, linear iteration counts included; only the launch count may differ, by one per Arnoldi step."""
     m = afx.Mesh.synth_omesh(96, 48, 16, 60.0)
     bcs = {"farfield": ("farfield", dict(mach=0.2, angle=0.05, T=1.0, p=1.0)), "wall": ("slip-wall", None)}
     outs = []
-    for graph in ("1", "0"):
-        monkeypatch.setenv("AFX_KRY_GRAPH", graph)
+    configs = (("1", "1"), ("0", "1"), ("1", "0"), ("0", "0"))
+    if afx.is_emulation():  # the CPU test run (tests/emu) takes ~35 s per configuration: both features on against both off
+        configs = (("1", "1"), ("0", "0"))
+    for graph, fuse in configs:
+        monkeypatch.setenv("AFX_KRY_GRAPH", graph); monkeypatch.setenv("AFX_KRY_FUSE_GIVENS", fuse)
         s = afx.GpuSolver(m, math=math)
         s.set_bcs(bcs); s.set_options(True, "green-gauss", 5.0, 40.0); s.init(); s.refill_bcs()
         l0 = s.launch_count()
         hist = run_implicit(s, 1e-6, max_iter=12)
-        outs.append((np.array(hist), s.get_q(), s.last_linear_iterations(), s.launch_count() - l0))
+        first = (np.array(hist), s.get_q(), s.last_linear_iterations(), s.launch_count() - l0)
         s.set_linear_solver(restart=8, max_iterations=200, tolerance=1e-3, precond_sweeps=3)  # new restart length / sweeps: the cached graphs must go
         hist2 = run_implicit(s, 1e-8, max_iter=6)
-        outs[-1] += (np.array(hist2), s.get_q())
-    a, b = outs
+        outs.append(first + (np.array(hist2), s.get_q()))
+    a = outs[0]
     assert len(a[0]) > 3 and a[0][-1] >= 0
-    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == b[2] and a[3] == b[3]
-    assert np.array_equal(a[4], b[4]) and np.array_equal(a[5], b[5])
+    for b in outs[1:]:
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == b[2]
+        assert np.array_equal(a[4], b[4]) and np.array_equal(a[5], b[5])
+    if len(outs) == 4:  # graphs replay the same launches; the fusion saves one per Arnoldi step
+        assert outs[0][3] == outs[1][3] and outs[2][3] == outs[3][3]
+    assert outs[-1][3] > outs[0][3]
 
 
 @pytest.mark.parametrize("grad,visc,math", [("green-gauss", "inviscid", "strict"), ("least-squares", "laminar", "strict"), ("green-gauss", "spallart-allmaras", "fast")])

@@ -52,7 +52,7 @@ def test_package_never_picks_the_emulation_library(afx, emu_lib):
 
 def test_three_kernel_stage_sources_match_reference_under_emulation(emu_lib):
     # explicit histories / single phases / synthetic mixed meshes / RHS and Jacobian blocks / BC handling / graph replay
-    tail = run_gpu_tests_under_emulation(emu_lib, ["test_gpu_parity.py"], "not implicit_converged and not full_size and not sweep_entry")  # the implicit end-to-end cases take ~1 min each: GPU only
+    tail = run_gpu_tests_under_emulation(emu_lib, ["test_gpu_parity.py"], "not implicit_converged and not full_size and not sweep_entry and not (arnoldi and fast)")  # the implicit end-to-end cases take ~1 min each: GPU only
     assert " passed" in tail
 
 
@@ -138,5 +138,5 @@ def test_pipelined_stage_kernel_under_emulation(emu_lib):
 def test_device_fmg_under_emulation(emu_lib):
     """tests/test_gpu_fmg.py: device-resident prolongation (bit-identical to the reference's product) and afx_rans_sweep_fmg against
     the same loop written with primitive calls and a host prolongation."""
-    tail = run_gpu_tests_under_emulation(emu_lib, ["test_gpu_fmg.py"], "not converges_to_the_reference")
+    tail = run_gpu_tests_under_emulation(emu_lib, ["test_gpu_fmg.py"], "not converges_to_the_reference and not polar_chains")  # 48 implicit FMG angles: GPU only
     assert "2 passed" in tail
