@@ -2313,7 +2313,8 @@ int run_level(afx_rans* s, const afx_sweep_settings* st, int* iters_out, double*
         } else {
             rc = afx_rans_step_explicit(s, st->relaxation, &err);
         }
-        if (rc == AFX_ERR_NUMERIC) { if (iters_out) *iters_out = i + 1; if (err_out) *err_out = -1; return rc; }
+        // multigrid.h:227,285: "if (err < 0) return 1" comes before the iteration is counted (iters++), with err = -1 / err_0
+        if (rc == AFX_ERR_NUMERIC) { if (iters_out) *iters_out = i; if (err_out) *err_out = -1.0 / err_0; return rc; }
         if (rc != AFX_OK) return rc;
         if (i == 0 && err > 2 * err_0) err_0 = err;
         err /= err_0;
@@ -2349,6 +2350,7 @@ int afx_rans_sweep_fmg(afx_rans* const* levels, afx_prolongation* const* prolong
     }
     if (n_alpha <= 0) return AFX_OK;
     int rc = AFX_OK;
+    bool any_failed = false;
     auto apply_alpha = [&](afx_rans* s, double alpha_deg) {
         auto& S = s->s;
         std::vector<uint8_t> kinds(S.patch_kinds);
@@ -2374,19 +2376,20 @@ int afx_rans_sweep_fmg(afx_rans* const* levels, afx_prolongation* const* prolong
             last = levels[l];
             rc = run_level(levels[l], st, &it, &err);
             it_total += it;
-            if (rc == AFX_ERR_NUMERIC) break;  // multigrid.h:313/355: the run ends on this level
+            // multigrid.h:313/355: a failed linear solve ends the run on this level and run() hands THIS level's solver back;
+            // run_airfoil takes its wall profile and goes on to the next angle (rans.h:98-104) -- so does the sweep
+            if (rc == AFX_ERR_NUMERIC) { any_failed = true; break; }
             if (rc != AFX_OK) return rc;
         }
         if (iterations) iterations[a] = it_total;
         if (residual) residual[a] = err;
-        if (rc == AFX_ERR_NUMERIC) return rc;
         double f[3];
         if ((rc = afx_rans_wall_forces(last, wall_patch, f)) != AFX_OK) return rc;  // rans.h:99-102
         if (cl) cl[a] = f[0];
         if (cd) cd[a] = f[1];
         if (cm) cm[a] = f[2];
     }
-    return AFX_OK;
+    return any_failed ? AFX_ERR_NUMERIC : AFX_OK;  // every angle is filled in either way
 }
 
 int afx_rans_sweep(afx_rans* s, const afx_sweep_settings* st, int farfield_patch, int wall_patch, const double* alphas_deg, int n_alpha,

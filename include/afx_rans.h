@@ -287,7 +287,9 @@ int afx_rans_wall_cp(afx_rans* s, int patch, double* cp);
  * until residual / uniform-flow residual <= tolerance or max_iterations, and get_wall_profile of `wall_patch`
  * (post.h:301-387).  cl/cd/cm/iterations/residual have n_alpha entries (any may be NULL).  A chain of angles per GPU is
  * how the polar database of the VLM viscous correction is sharded (BASELINE config 5: no communication between chains).
- * Returns AFX_ERR_NUMERIC where the reference's run_solver returns 1 (the angles done so far are filled in).
+ * Where the reference's run_solver returns 1 (a failed linear solve, multigrid.h:227,285) the sweep does what run_airfoil does:
+ * it takes the forces of the level the run ended on and goes on to the next angle (residual = -1 / uniform-flow residual for that
+ * angle, the failed iteration not counted); every angle is filled in and the call returns AFX_ERR_NUMERIC if any angle failed.
  * Partitioned handles: called by every rank with the same arguments (explicit and implicit). */
 typedef struct afx_sweep_settings {
     int implicit;            /* 0: explicitSolver, 1: implicitSolver */

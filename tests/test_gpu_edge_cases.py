@@ -190,3 +190,35 @@ def test_fast_mode_100_iterations_of_the_bench_configuration(afx, gpu):
         out.append((s.run(100, 0.9), np.array(s.wall_forces("wall"))))
     np.testing.assert_allclose(out[1][0], out[0][0], rtol=1e-10, atol=0)
     np.testing.assert_allclose(out[1][1], out[0][1], rtol=1e-8, atol=0)
+
+
+def test_sweep_goes_on_after_a_failed_linear_solve_like_run_airfoil(afx, gpu):
+    """multigrid.h:227,285 + rans.h:92-104: when the linear solve of an angle fails (run_solver returns 1), run() hands back the
+    solver of the level it ended on, run_airfoil takes ITS wall profile and goes on with the next angle.  A GMRES that is allowed
+    one iteration at tolerance 1e-14 fails at once: every angle must still be filled in (forces of the untouched free-stream state on
+    the coarse level, the failed iteration not counted, residual -1 / uniform-flow residual), status AFX_ERR_NUMERIC -- and with the
+    default linear solver the same handles then converge, so a failure leaves nothing behind."""
+    d = H.load("naca0012q_coarse_euler_gg_o2")
+    m = H.product_mesh(afx, d)
+    bcs = {"farfield": ("farfield", dict(mach=0.2, angle=0.0, T=1.0, p=1.0)), "wall": ("slip-wall", None)}
+    s = afx.GpuSolver(m, math="strict")
+    s.set_bcs(bcs); s.set_options(True, "green-gauss", 5.0, 40.0)
+    s.set_linear_solver(restart=2, max_iterations=1, tolerance=1e-14)
+    r = s.sweep([1.0, 2.0, 3.0], implicit=True, tolerance=1e-4, max_iterations=5)
+    assert r["status"] == -3
+    assert list(r["iterations"]) == [0, 0, 0] and np.all(r["residual"] < 0) and np.all(np.isfinite(r["residual"]))
+    assert np.all(np.isfinite(r["cl"])) and np.all(np.isfinite(r["cd"])) and np.all(np.isfinite(r["cm"]))
+    # the state was never advanced: the forces are those of the free stream of the FIRST angle (init() ran once, rans.h:88), rotated
+    # into each angle's wind axes by get_wall_profile
+    ref = afx.GpuSolver(m, math="strict")
+    for k, al in enumerate([1.0, 2.0, 3.0]):
+        b = dict(bcs); b["farfield"] = ("farfield", dict(mach=0.2, angle=al * 0.01745, T=1.0, p=1.0))
+        ref.set_bcs(b)
+        if k == 0:
+            ref.set_options(True, "green-gauss", 5.0, 40.0); ref.init()
+        ref.refill_bcs()
+        np.testing.assert_allclose([r["cl"][k], r["cd"][k], r["cm"][k]], ref.wall_forces("wall"), rtol=1e-12, atol=1e-15)
+        assert r["residual"][k] == pytest.approx(-1.0 / ref.get_uniform_residual(), rel=1e-12)
+    s.set_linear_solver()  # defaults: GMRES(30), <= 500 iterations, 1e-2, 4 sweeps
+    r2 = s.sweep([3.0], implicit=True, tolerance=1e-4, max_iterations=100, reinit=False)
+    assert r2["status"] == 0 and r2["residual"][0] <= 1e-4 and 0 < r2["iterations"][0] < 100
