@@ -33,7 +33,7 @@ EXPORTED_SYMBOLS = [
     "afx_partition_edge_l2g", "afx_partition_peer", "afx_nccl_unique_id", "afx_rans_create_partitioned",
     "afx_rans_p2p_export", "afx_rans_p2p_connect", "afx_rans_halo_mode",
     "afx_group_create", "afx_group_free", "afx_group_abort", "afx_rans_create_partitioned_group",
-    "afx_rans_create", "afx_rans_destroy", "afx_rans_set_bcs", "afx_rans_set_options", "afx_rans_set_cfl",
+    "afx_rans_create", "afx_rans_destroy", "afx_rans_set_bcs", "afx_rans_set_options", "afx_rans_set_limiter", "afx_rans_set_cfl",
     "afx_rans_set_math_mode", "afx_rans_get_math_mode", "afx_rans_set_fused", "afx_rans_tile_info", "afx_rans_set_pipelined", "afx_rans_pipe_info", "afx_tiling_plan", "afx_tiling_plan_partition",
     "afx_rans_init", "afx_rans_refill_bcs", "afx_rans_bcs_from_internal", "afx_rans_set_q", "afx_rans_get_q",
     "afx_rans_set_q_local", "afx_rans_get_q_local", "afx_rans_get_field", "afx_rans_boundary_variables", "afx_rans_uniform_residual", "afx_rans_step_explicit",
@@ -185,6 +185,7 @@ def load_library():
     L.afx_rans_destroy.argtypes = [vp]
     L.afx_rans_set_bcs.argtypes = [vp, C.c_int, vp, C.POINTER(BVars)]
     L.afx_rans_set_options.argtypes = [vp, C.c_int, C.c_int, C.c_double]
+    L.afx_rans_set_limiter.argtypes = [vp, C.c_int]
     L.afx_rans_set_cfl.argtypes = [vp, C.c_double]
     L.afx_rans_set_math_mode.argtypes = [vp, C.c_int]
     L.afx_tiling_plan.argtypes = [C.POINTER(MeshDesc), C.c_uint32, vp, C.POINTER(C.c_uint32), vp, C.c_uint32, C.POINTER(C.c_uint64)]
@@ -558,6 +559,10 @@ class GpuSolver:
         _check(self.L.afx_rans_set_options(self.h, int(bool(second_order)), GRADIENT[gradient], limiter_k))
         if cfl is not None:
             self.set_cfl(cfl)
+
+    def set_limiter(self, name="venkatakrishnan"):
+        """calc_limiters' function: "venkatakrishnan" (the reference's default build) or "michalak" (its RANS_MICHALAK_LIMITER build)."""
+        _check(self.L.afx_rans_set_limiter(self.h, {"venkatakrishnan": 0, "michalak": 1}[name]))
 
     def set_cfl(self, cfl): _check(self.L.afx_rans_set_cfl(self.h, cfl))
     def init(self): _check(self.L.afx_rans_init(self.h))

@@ -471,6 +471,75 @@ __global__ void __launch_bounds__(AFX_LIM_THREADS, PM ? AFX_LIM_PM_MINB : AFX_LI
     limiter_cell<PM>(m, i, c, qk, gx, gy, lim, limiter_k, walls, pm);
 }
 
+// ---- the reference's other limiter: Michalak (solver.h:557-576 under RANS_MICHALAK_LIMITER, physics.h:581-592) ----------------------
+// Off in the reference's default build (nothing defines the macro); opt-in here with afx_rans_set_limiter.  Per component: a
+// smooth switch sig between "no limiting" (the spread of the neighbour values is below K^3 a) and Michalak's monotone cubic of
+// y = delta / (g . dx); lim = sig + (1 - sig) * phi(y), minimum over the cell's faces.  The reference's expressions in the
+// reference's order in both arithmetic modes (the function is not on the benchmarked path; fast mode only allows FMA contraction).
+__device__ __forceinline__ double michalak_phi(double y)  // physics.h:583-592, RANS_YT = 2
+{
+    if (y >= 2.0) return 1.0;
+    constexpr double a = 1.0 / (2.0 * 2.0) - 2.0 / (2.0 * 2.0 * 2.0);
+    constexpr double b = -3.0 / 2.0 * a * 2.0 - 0.5 / 2.0;
+    return a * y * y * y + b * y * y + y;
+}
+__device__ __forceinline__ double michalak_one(double dqg, double dmax, double dmin, double K3a)
+{
+    const double dMaxMin2 = (dmax - dmin) * (dmax - dmin);
+    double lim = 1.0, sig;
+    if (dMaxMin2 <= K3a) sig = 1.;
+    else if (dMaxMin2 <= 2 * K3a) { const double y = (dMaxMin2 / K3a - 1.0); sig = 2.0 * y * y * y - 3.0 * y * y + 1.0; }
+    else sig = 0.;
+    if (sig < 1.0) {
+        if (dqg > 1e-14) lim = michalak_phi(dmax / dqg);
+        else if (dqg < -1e-14) lim = michalak_phi(dmin / dqg);
+        else lim = 1.0;
+    }
+    return sig + (1.0 - sig) * lim;
+}
+__global__ void __launch_bounds__(128) k_limiter_michalak(DevMesh m, const d4* qk, const d4* gx, const d4* gy, d4* lim, double limiter_k, int walls,
+                                                          uint32_t lo1, uint32_t n1, uint32_t lo2, uint32_t n2)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n1 + n2) return;
+    const uint32_t i = t < n1 ? lo1 + t : lo2 + (t - n1);
+    pdl_launch_dependents();
+    const LimCell c = limiter_load_static(m, i, true);
+    pdl_wait();
+    const d4 qi = qk[i];
+    d4 lo = qi, hi = qi;
+    unsigned valid = 0;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {  // min / max over the edge neighbours, exactly as limiter_cell
+        if (c.nbs[s] == CF_NONE) continue;
+        const uint32_t j = c.nbs[s] & CF_ID;
+        valid |= 1u << s;
+        bool wall_ghost = false;
+        if (walls && (c.nbs[s] & CF_BND)) {
+            const int kind = m.fkind[m.cf[(size_t)s * m.N + i] & CF_ID];
+            wall_ghost = (kind == K_SLIPWALL || kind == K_WALL);
+        }
+        const d4 qj = wall_ghost ? qi : qk[j];
+        lo.x = dmin2(lo.x, qj.x); lo.y = dmin2(lo.y, qj.y); lo.z = dmin2(lo.z, qj.z); lo.w = dmin2(lo.w, qj.w);
+        hi.x = dmax2(hi.x, qj.x); hi.y = dmax2(hi.y, qj.y); hi.z = dmax2(hi.z, qj.z); hi.w = dmax2(hi.w, qj.w);
+    }
+    const d4 gxi = gx[i], gyi = gy[i];
+    const double K3a = limiter_k3a(c.area, limiter_k);
+    const d4 dmax = mk4(hi.x - qi.x, hi.y - qi.y, hi.z - qi.z, hi.w - qi.w);
+    const d4 dmin = mk4(lo.x - qi.x, lo.y - qi.y, lo.z - qi.z, lo.w - qi.w);
+    d4 l = mk4(1, 1, 1, 1);
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        if (!(valid & (1u << s))) continue;
+        const double dx = c.dxy[s].x, dy = c.dxy[s].y;
+        l.x = dmin2(l.x, michalak_one(gxi.x * dx + gyi.x * dy, dmax.x, dmin.x, K3a));
+        l.y = dmin2(l.y, michalak_one(gxi.y * dx + gyi.y * dy, dmax.y, dmin.y, K3a));
+        l.z = dmin2(l.z, michalak_one(gxi.z * dx + gyi.z * dy, dmax.z, dmin.z, K3a));
+        l.w = dmin2(l.w, michalak_one(gxi.w * dx + gyi.w * dy, dmax.w, dmin.w, K3a));
+    }
+    lim[i] = l;
+}
+
 // ---------------------------------------------------------------------------
 // Face loop, one thread per face: MUSCL reconstruction + flux, written once.
 // explicitSolver::calc_residual (solver.h:751-786) / fillRhoRHS (1097-1134) /
@@ -1030,6 +1099,12 @@ static void limiter(const DevMesh& m, const d4* qk, const d4* gx, const d4* gy, 
     if (n1 + n2 == 0) return;
     if (AFX_FAST && pm) launch_pdl(k_limiter<1>, nblk(n1 + n2, AFX_LIM_THREADS), AFX_LIM_THREADS, st, m, qk, gx, gy, lim, k, walls, lo1, n1, lo2, n2, pm);
     else launch_pdl(k_limiter<0>, nblk(n1 + n2, AFX_LIM_THREADS), AFX_LIM_THREADS, st, m, qk, gx, gy, lim, k, walls, lo1, n1, lo2, n2, (const d4*)nullptr);
+}
+static void limiter_michalak(const DevMesh& m, const d4* qk, const d4* gx, const d4* gy, d4* lim, double k, int walls, uint32_t lo1, uint32_t n1,
+                             uint32_t lo2, uint32_t n2, cudaStream_t st)
+{
+    if (n1 + n2 == 0) return;
+    launch_pdl(k_limiter_michalak, nblk(n1 + n2, 128), 128u, st, m, qk, gx, gy, lim, k, walls, lo1, n1, lo2, n2);
 }
 static void flux(int second, int visc, int uniform, const DevMesh& m, const d4* qk, const d4* q0, const d4* gx, const d4* gy,
                  const d4* lim, d4* fl, const GasC& g, d4 qfar, cudaStream_t st)

@@ -21,7 +21,7 @@ const KernelTable& table()
         launch::jacobian, launch::jac_diag,
         launch::wall_forces, launch::prolongate, launch::fill_cells, launch::ghost_fill, launch::ghost_follow, launch::permute4, launch::permute1, launch::scatter4,
         launch::spmv, launch::jacobi_sweep, launch::invert_blocks, launch::multi_dot, launch::multi_axpy, launch::multi_dot1, launch::axpy_norm, launch::spmv_sweep0, launch::scale_from, launch::gmres_begin, launch::givens_step, launch::gmres_solve_y, launch::gmres_state_doubles, launch::sub,
-        launch::axpy_state, launch::axpy_norm_givens};
+        launch::axpy_state, launch::axpy_norm_givens, launch::limiter_michalak};
     return t;
 }
 

@@ -228,7 +228,7 @@ struct Solver {
     uint64_t tile_local_cells = 0;
     void build_tile_tables(const std::vector<uint32_t>& h_cf, const std::vector<uint32_t>& h_cnb, const std::vector<double2>& h_cdxy,
                            const std::vector<double>& h_area, const std::vector<d4>& h_gA);
-    bool fused_stage() const { return tiles_ready && use_fused && second_order && viscous_type == 0 && !(halo && halo_overlap); }
+    bool fused_stage() const { return tiles_ready && use_fused && second_order && viscous_type == 0 && !(halo && halo_overlap) && limiter_kind == 0; }
     void launch_stage(int s, const d4* qk_in, d4* qk_out, double alpha);
     // pipelined stage kernel on L2-resident chunks (rans_pipe.cuh); [0] without, [1] with the limiter phase
     DBuf<uint4> p_items[2]; DBuf<uint2> p_chunk_items; DBuf<uint32_t> p_far_faces, p_far_cells, p_far_mask; DBuf<unsigned int> p_ctr;
@@ -236,7 +236,7 @@ struct Solver {
     bool pipe_ready = false, use_pipe = false;
     unsigned pipe_grid = 0;
     void build_pipe_tables();
-    bool pipe_stage() const { return pipe_ready && use_pipe && viscous_type == 0 && !(halo && halo_overlap) && !fused_stage(); }
+    bool pipe_stage() const { return pipe_ready && use_pipe && viscous_type == 0 && !(halo && halo_overlap) && !fused_stage() && limiter_kind == 0; }
     void launch_pipe(int s, const d4* qk_in, d4* qk_out, double alpha, bool has_l);
     int* pipe_err_word() { return reinterpret_cast<int*>(h_pinned + 49); }
     DBuf<uint32_t> bface, bghost, bowner; DBuf<int32_t> bpatch; DBuf<d4> bstate; DBuf<double> bcx, bcy;
@@ -348,8 +348,18 @@ struct Solver {
     void push_params(double relax, bool keep_qW = true);
     void launch_dt_grad(bool want_grad, bool walls, bool with_lim = false);
     bool fuse_lim0 = true;  // AFX_FUSE_LIM0=0: keep the first stage's limiter in its own k_limiter launch
+    // afx_rans_set_limiter: AFX_LIMITER_VENKATAKRISHNAN (the reference's default build) or AFX_LIMITER_MICHALAK (its
+    // RANS_MICHALAK_LIMITER build, solver.h:557-576).  The Michalak function runs in its own kernel on the three-kernel stage:
+    // no limiter inside k_dt_grad, no stored extremes, no fused / pipelined stage kernel.
+    int limiter_kind = 0;
+    void set_limiter(int kind)
+    {
+        if (kind != AFX_LIMITER_VENKATAKRISHNAN && kind != AFX_LIMITER_MICHALAK) throw InvalidArg("unknown limiter");
+        if (kind != limiter_kind) { limiter_kind = kind; pm_valid = false; invalidate_graph(); }
+    }
+    bool lim0_fused() const { return fuse_lim0 && second_order && limiter_kind == 0; }
     // the first stage limits the iteration-start state: k_dt_grad can do it from the neighbour states it has just read
-    bool lim0_in_dt_grad() const { return fuse_lim0 && second_order && !fused_stage(); }  // also ahead of the pipelined stage
+    bool lim0_in_dt_grad() const { return lim0_fused() && !fused_stage(); }  // also ahead of the pipelined stage
     void launch_limiter(const d4* qk);
     void launch_flux(const d4* qk, bool uniform, d4 qfar);
     template <int MODE, int LAST>
@@ -765,6 +775,19 @@ void Solver::launch_dt_grad(bool want_grad, bool walls, bool with_lim)
 void Solver::launch_limiter(const d4* qk)
 {
     const int walls = (visc_not_inviscid || second_order) ? 1 : 0;
+    if (limiter_kind == AFX_LIMITER_MICHALAK) {  // same cell ranges, its own kernel
+        if (halo_pending && n_front > 0 && n_front < n_upd) {
+            kt->limiter_michalak(dm, qk, gx.p, gy.p, lim.p, limiter_k, walls, n_front, n_upd - n_front, 0, 0, st);
+            ensure_halo();
+            kt->limiter_michalak(dm, qk, gx.p, gy.p, lim.p, limiter_k, walls, 0, n_front, n_upd, n_grad - n_upd, st);
+            launches += 2;
+            return;
+        }
+        ensure_halo();
+        kt->limiter_michalak(dm, qk, gx.p, gy.p, lim.p, limiter_k, walls, 0, n_grad, 0, 0, st);
+        ++launches;
+        return;
+    }
     if (halo_pending && n_front > 0 && n_front < n_upd) {
         // owned cells farther than two hops from any foreign cell do not see the halo: limit them while it is in flight
         kt->limiter(dm, qk, gx.p, gy.p, lim.p, limiter_k, walls, n_front, n_upd - n_front, 0, 0, pm_for_limiter(), st);
@@ -1434,7 +1457,7 @@ double Solver::residual_rhs()
     if (!bcs_set) throw InvalidArg("set_bcs has not been called");
     push_params(relax_dev < 0 ? 1.0 : relax_dev);
     const bool grads = second_order || visc_not_inviscid;  // solver.h:1083
-    const bool lim0 = fuse_lim0 && second_order;
+    const bool lim0 = lim0_fused();
     launch_dt_grad(grads, grads, lim0);
     if (second_order && !lim0) launch_limiter(q.p);
     launch_flux(q.p, false, d4{0, 0, 0, 0});
@@ -1839,6 +1862,12 @@ int afx_rans_set_bcs(afx_rans* s, int n_patch, const uint8_t* patch_kind, const 
 int afx_rans_set_options(afx_rans* s, int second_order, int gradient_scheme, double limiter_k)
 {
     return guard([&] { s->s.set_options(second_order, gradient_scheme, limiter_k); });
+}
+
+int afx_rans_set_limiter(afx_rans* s, int limiter)
+{
+    if (!s) { afx::set_error("null argument"); return AFX_ERR_INVALID; }
+    return guard([&] { s->s.set_limiter(limiter); });
 }
 
 int afx_rans_set_math_mode(afx_rans* s, int mode)

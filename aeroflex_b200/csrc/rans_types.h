@@ -235,6 +235,9 @@ struct KernelTable {
     // partitioned step all-reduces the norm between the two)
     void (*axpy_norm_givens)(uint32_t n, const d4* V, size_t stride, int k, const double* c, double sign, d4* w, double* partial, double* h,
                              unsigned int* counter, int m, double* state, double tol, int* stop, cudaStream_t st);
+    // calc_limiters built with RANS_MICHALAK_LIMITER (solver.h:557-576): same cell ranges as `limiter`
+    void (*limiter_michalak)(const DevMesh& m, const d4* qk, const d4* gx, const d4* gy, d4* lim, double k, int walls, uint32_t lo1, uint32_t n1,
+                             uint32_t lo2, uint32_t n2, cudaStream_t st);
 };
 
 namespace strict { const KernelTable& table(); }  // -fmad=false, reference expression order: bit-identical to the CPU reference

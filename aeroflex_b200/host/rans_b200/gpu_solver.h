@@ -45,6 +45,9 @@ protected:
         const afx_gas cg = g.c_abi();
         check(afx_rans_create(&s, &m.desc(), &cg, visc_id(viscosity_model), device_));
         h_.reset(s, Deleter());
+#ifdef RANS_MICHALAK_LIMITER  // the reference's compile-time switch (solver.h:557) selects the library's run-time one
+        check(afx_rans_set_limiter(s, AFX_LIMITER_MICHALAK));
+#endif
         q_host_.assign(4 * (m.cellsAreas.size()), 0.0);
     }
     void push_options() {

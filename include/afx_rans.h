@@ -191,6 +191,12 @@ int afx_rans_halo_mode(afx_rans* s);
 int afx_rans_set_bcs(afx_rans* s, int n_patch, const uint8_t* patch_kind, const afx_bvars* patch_vars);
 /* set_second_order / set_gradient_scheme / set_limiter_k (solver.h:135,149-152,162) */
 int afx_rans_set_options(afx_rans* s, int second_order, int gradient_scheme, double limiter_k);
+/* Which limiter function calc_limiters (solver.h:517-593) evaluates: Venkatakrishnan (the reference's default build, solver.h:578-584)
+ * or Michalak (solver.h:557-576 + michalak_limiter, physics.h:581-592 -- what the reference compiles when RANS_MICHALAK_LIMITER is
+ * defined; nothing in its build defines it).  Replaces that compile-time switch with a run-time one; the adapter headers map the
+ * macro onto this call.  Michalak runs on the three-kernel stage (no limiter inside the dt/gradient kernel, no fused stage). */
+enum { AFX_LIMITER_VENKATAKRISHNAN = 0, AFX_LIMITER_MICHALAK = 1 };
+int afx_rans_set_limiter(afx_rans* s, int limiter);
 /* arithmetic mode (AFX_MATH_*); the environment variable AFX_MATH=strict|fast sets the default at creation */
 int afx_rans_set_math_mode(afx_rans* s, int mode);
 int afx_rans_get_math_mode(afx_rans* s);

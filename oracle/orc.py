@@ -52,7 +52,7 @@ class Solver(C.Structure):
                 ("viscous_type", C.c_int), ("visc_not_inviscid", C.c_int), ("second_order", C.c_int),
                 ("gradient_scheme", C.c_int), ("limiter_k", C.c_double), ("cfl", C.c_double)] + \
                [(n, C.POINTER(C.c_double)) for n in ("q", "qk", "qW", "gx", "gy", "lim", "qmin", "qmax", "rhs", "dt", "lsq")] + \
-               [("cf_sorted", C.POINTER(C.c_uint32)), ("fluxbuf", C.POINTER(C.c_double))]
+               [("cf_sorted", C.POINTER(C.c_uint32)), ("fluxbuf", C.POINTER(C.c_double)), ("limiter_kind", C.c_int)]
 
 
 _libs = {}
@@ -226,6 +226,10 @@ class OracleSolver:
 
     def set_cfl(self, cfl):
         self.s.cfl = cfl
+
+    def set_limiter(self, name="venkatakrishnan"):
+        """"venkatakrishnan": the reference's default build; "michalak": its RANS_MICHALAK_LIMITER build (solver.h:557-576)."""
+        self.s.limiter_kind = {"venkatakrishnan": 0, "michalak": 1}[name]
 
     def init(self): self.L.orc_init_field(C.byref(self.s))
     def refill_bcs(self): self.L.orc_refill_bcs(C.byref(self.s))

@@ -413,6 +413,7 @@ int orc_solver_init(orc_solver *s, const orc_mesh *m, const orc_gas *g, int visc
     s->second_order = 1;
     s->gradient_scheme = ORC_GREEN_GAUSS;
     s->limiter_k = 5.;
+    s->limiter_kind = 0;
     s->cfl = 1;
     const size_t NT = (size_t)m->N + m->G, n4 = 4 * NT;
     double **v[] = {&s->q, &s->qk, &s->qW, &s->gx, &s->gy, &s->lim, &s->qmin, &s->qmax, &s->rhs};
@@ -635,7 +636,31 @@ void orc_calc_gradients(orc_solver *s)
     }
 }
 
-/* Venkatakrishnan limiter, solver.h:517-593 (non-Michalak build) */
+/* michalak_limiter, physics.h:581-592 (RANS_YT = 2.0; the constants as the reference writes them) */
+static double orc_michalak_phi(double y)
+{
+    if (y >= 2.0) return 1.0;
+    const double a = 1.0 / (2.0 * 2.0) - 2.0 / (2.0 * 2.0 * 2.0);
+    const double b = -3.0 / 2.0 * a * 2.0 - 0.5 / 2.0;
+    return a * y * y * y + b * y * y + y;
+}
+/* the limiter of one component at one face under RANS_MICHALAK_LIMITER, solver.h:553-576 */
+static double orc_michalak_one(double dqg, double delta_max, double delta_min, double K3a)
+{
+    const double dMaxMin2 = (delta_max - delta_min) * (delta_max - delta_min);
+    double lim = 1.0, sig;
+    if (dMaxMin2 <= K3a) sig = 1.;
+    else if (dMaxMin2 <= 2 * K3a) { const double y = (dMaxMin2 / K3a - 1.0); sig = 2.0 * y * y * y - 3.0 * y * y + 1.0; }
+    else sig = 0.;
+    if (sig < 1.0) {
+        if (dqg > 1e-14) lim = orc_michalak_phi(delta_max / dqg);
+        else if (dqg < -1e-14) lim = orc_michalak_phi(delta_min / dqg);
+        else lim = 1.0;
+    }
+    return sig + (1.0 - sig) * lim;
+}
+
+/* calc_limiters, solver.h:517-593: Venkatakrishnan (the default build) or, limiter_kind = 1, the RANS_MICHALAK_LIMITER build */
 void orc_calc_limiters(orc_solver *s, const double *q_)
 {
     const orc_mesh *m = &s->m;
@@ -664,7 +689,9 @@ void orc_calc_limiters(orc_solver *s, const double *q_)
                 const double Ka = s->limiter_k * sqrt_area;
                 const double K3a = Ka * Ka * Ka;
                 double lim = 1.0;
-                if (dqg > 1e-16)
+                if (s->limiter_kind == 1)
+                    lim = orc_michalak_one(dqg, dmax, dmin, K3a);
+                else if (dqg > 1e-16)
                     lim = 1 / dqg * ((dmax * dmax + K3a) * dqg + 2 * dqg * dqg * dmax) / (dmax * dmax + 2 * dqg * dqg + dmax * dqg + K3a);
                 else if (dqg < -1e-16)
                     lim = 1 / dqg * ((dmin * dmin + K3a) * dqg + 2 * dqg * dqg * dmin) / (dmin * dmin + 2 * dqg * dqg + dmin * dqg + K3a);
@@ -983,7 +1010,8 @@ double orc_explicit_solve_omp(orc_solver *s, double relaxation)
                             const double dqg = s->gx[4 * i + c] * dx + s->gy[4 * i + c] * dy;
                             const double dmax = hi[c] - qk[4 * i + c], dmin = lo[c] - qk[4 * i + c];
                             double v = 1.0;
-                            if (dqg > 1e-16) v = 1 / dqg * ((dmax * dmax + K3a) * dqg + 2 * dqg * dqg * dmax) / (dmax * dmax + 2 * dqg * dqg + dmax * dqg + K3a);
+                            if (s->limiter_kind == 1) v = orc_michalak_one(dqg, dmax, dmin, K3a);
+                            else if (dqg > 1e-16) v = 1 / dqg * ((dmax * dmax + K3a) * dqg + 2 * dqg * dqg * dmax) / (dmax * dmax + 2 * dqg * dqg + dmax * dqg + K3a);
                             else if (dqg < -1e-16) v = 1 / dqg * ((dmin * dmin + K3a) * dqg + 2 * dqg * dqg * dmin) / (dmin * dmin + 2 * dqg * dqg + dmin * dqg + K3a);
                             l[c] = fmin(l[c], v);
                         }

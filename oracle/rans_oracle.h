@@ -77,6 +77,7 @@ typedef struct {
     /* scratch of the threaded variant (orc_explicit_solve_omp): faces of a cell in ascending edge id, face fluxes */
     uint32_t *cf_sorted; /* [N][4] */
     double *fluxbuf; /* [E][4] */
+    int limiter_kind; /* 0 Venkatakrishnan (default build), 1 Michalak (RANS_MICHALAK_LIMITER build, solver.h:557-576) */
 } orc_solver;
 
 /* ---- physics.h ---- */

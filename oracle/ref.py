@@ -13,7 +13,10 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO = os.path.join(HERE, "_ref", "libafx_ref.so")
+# AFX_REF_VARIANT=michalak (set before the import): the same unmodified headers compiled with -DRANS_MICHALAK_LIMITER, the
+# reference's compile-time switch to its other limiter (solver.h:557-576); used by oracle/make_golden_michalak.py only
+VARIANT = os.environ.get("AFX_REF_VARIANT", "")
+SO = os.path.join(HERE, "_ref", "libafx_ref%s.so" % ("_" + VARIANT if VARIANT else ""))
 
 f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
 u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")

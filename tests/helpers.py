@@ -43,12 +43,16 @@ MESH_ARRAYS = ("edge_cells", "enx", "eny", "elen", "ecx", "ecy", "ccx", "ccy", "
 EXPLICIT_CASES = ["naca0012q_coarse_euler_gg_o2", "naca0012_coarse_laminar_lsq_o2", "naca0012_coarse_sa_gg_o1",
                   "naca0012_coarse_euler_gg_o1", "flat_plate_laminar_gg_o2", "flat_plate_sa_gg_o2"]
 IMPLICIT_CASES = ["naca0012q_coarse_implicit_blocks", "naca0012_coarse_implicit_laminar_blocks"]
+# the reference headers compiled with -DRANS_MICHALAK_LIMITER (oracle/make_golden_michalak.py)
+MICHALAK_CASES = ["michalak_naca0012q_coarse_euler_gg", "michalak_naca0012_coarse_laminar_lsq"]
 
 
 def setup_solver(s, meta, cfl=None):
     """Apply a fixture's settings to an OracleSolver or a GpuSolver (same interface)."""
     s.set_bcs(meta["bcs"])
-    s.set_options(meta["second_order"], meta["gradient"], 5.0, meta["cfl"] if cfl is None else cfl)
+    s.set_options(meta["second_order"], meta["gradient"], meta.get("limiter_k", 5.0), meta["cfl"] if cfl is None else cfl)
+    if "limiter" in meta:
+        s.set_limiter(meta["limiter"])
 
 
 def synth_state(mesh_N, q_uniform, seed=12345, amp=1e-3):

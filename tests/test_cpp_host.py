@@ -54,6 +54,18 @@ def _build(afx, src, out):
     return str(out)
 
 
+def test_adapter_maps_the_reference_michalak_macro_onto_the_library_switch():
+    """The reference selects its other limiter at compile time (#ifdef RANS_MICHALAK_LIMITER, solver.h:557); the adapter's solver class
+    turns the macro into afx_rans_set_limiter(AFX_LIMITER_MICHALAK) when it creates the device solver.  Compile check, no device."""
+    src = os.path.join(HOST, "rans_cli.cpp")
+    for extra in ([], ["-DRANS_MICHALAK_LIMITER"]):
+        subprocess.run(["/usr/bin/g++", "-std=c++17", "-fsyntax-only", "-fopenmp", "-Wall", "-Werror", "-I" + HOST] + extra + [src], check=True)
+    pre = subprocess.run(["/usr/bin/g++", "-std=c++17", "-E", "-fopenmp", "-DRANS_MICHALAK_LIMITER", "-I" + HOST, src], check=True, capture_output=True, text=True).stdout
+    assert "afx_rans_set_limiter(s, AFX_LIMITER_MICHALAK)" in pre
+    pre0 = subprocess.run(["/usr/bin/g++", "-std=c++17", "-E", "-fopenmp", "-I" + HOST, src], check=True, capture_output=True, text=True).stdout
+    assert "afx_rans_set_limiter(s, AFX_LIMITER_MICHALAK)" not in pre0
+
+
 @pytest.fixture(scope="module")
 def exes(afx, tmp_path_factory):
     d = tmp_path_factory.mktemp("cpp")

@@ -15,9 +15,11 @@ BCS = {"farfield": ("farfield", dict(mach=0.2, angle=0.03, T=1.0, p=1.0)), "wall
 DIMS = (256, 160, 64)  # 65 536 mixed cells
 
 
-def _single(afx, mesh, visc, grad, so, n_iter, seed=77, amp=1e-3):
+def _single(afx, mesh, visc, grad, so, n_iter, seed=77, amp=1e-3, limiter=None, limk=5.0):
     s = afx.GpuSolver(mesh, viscosity=visc, math="strict", device=0)
-    s.set_bcs(BCS); s.set_options(so, grad, 5.0, 1.4); s.init(); s.refill_bcs()
+    s.set_bcs(BCS); s.set_options(so, grad, limk, 1.4); s.init(); s.refill_bcs()
+    if limiter:
+        s.set_limiter(limiter)
     q_init = s.get_q().reshape(-1, 4).copy()
     q0 = s.get_q()
     rng = np.random.default_rng(seed)
@@ -32,7 +34,7 @@ def _single(afx, mesh, visc, grad, so, n_iter, seed=77, amp=1e-3):
     return out
 
 
-def _group_run(afx, mesh, world, halo, math, visc, grad, so, n_iter, q0, ndev, fused=0):
+def _group_run(afx, mesh, world, halo, math, visc, grad, so, n_iter, q0, ndev, fused=0, limiter=None, limk=5.0):
     group = afx.Group(world)
     parts = [afx.Partition(mesh, world, r) for r in range(world)]
     solvers = [None] * world
@@ -55,7 +57,9 @@ def _group_run(afx, mesh, world, halo, math, visc, grad, so, n_iter, q0, ndev, f
     def work(r):
         def f():
             s, part = solvers[r], parts[r]
-            s.set_bcs(BCS); s.set_options(so, grad, 5.0, 1.4); s.init(); s.refill_bcs()
+            s.set_bcs(BCS); s.set_options(so, grad, limk, 1.4); s.init(); s.refill_bcs()
+            if limiter:
+                s.set_limiter(limiter)
             qi = np.full(4 * (mesh.N + mesh.G), np.nan)
             s.get_q(qi)
             s.set_q(q0)
@@ -113,6 +117,24 @@ def test_partition_variants_on_one_gpu(afx, gpu, world, visc, grad, so, halo):
     mesh = afx.Mesh.synth_omesh(*DIMS, 150.0)
     ref = _single(afx, mesh, visc, grad, so, n_iter, amp=1e-4 if visc == "laminar" else 1e-3)
     res, _ = _group_run(afx, mesh, world, halo, "strict", visc, grad, so, n_iter, ref["q0"], gpu)
+    for d in res:
+        own = d["own"]
+        assert np.array_equal(d["q"][own], ref["Q"][own])
+        np.testing.assert_allclose(d["norms"], ref["norms"], rtol=1e-12)
+        np.testing.assert_allclose(d["forces"], ref["F"], rtol=1e-12, atol=1e-15)
+        assert np.array_equal(d["rhs_own"], ref["RHS"][own])
+
+
+@pytest.mark.parametrize("world,halo", [(3, "p2p"), (2, "staged")])
+def test_michalak_limiter_partitioned_on_one_gpu(afx, gpu, world, halo):
+    """The reference's other limiter (afx_rans_set_limiter, solver.h:557-576) on partitioned solvers: its kernel takes the same
+    interior / halo-dependent cell ranges as k_limiter; same bits as the single-GPU run, implicit right-hand side included."""
+    n_iter = 8
+    mesh = afx.Mesh.synth_omesh(*DIMS, 150.0)
+    ref = _single(afx, mesh, "spallart-allmaras", "green-gauss", True, n_iter, amp=1e-2, limiter="michalak", limk=0.5)
+    plain = _single(afx, mesh, "spallart-allmaras", "green-gauss", True, n_iter, amp=1e-2, limk=0.5)
+    assert not np.array_equal(ref["Q"], plain["Q"])  # the limiter is active: the two functions give different states
+    res, _ = _group_run(afx, mesh, world, halo, "strict", "spallart-allmaras", "green-gauss", True, n_iter, ref["q0"], gpu, limiter="michalak", limk=0.5)
     for d in res:
         own = d["own"]
         assert np.array_equal(d["q"][own], ref["Q"][own])

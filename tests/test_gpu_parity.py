@@ -52,6 +52,45 @@ def test_explicit_history_vs_reference_golden(afx, gpu, tag):
     np.testing.assert_allclose(s.wall_forces(str(d["forces_patch"])), d["forces"], rtol=FORCE_RTOL, atol=1e-15)
 
 
+@pytest.mark.parametrize("tag", H.MICHALAK_CASES)
+def test_michalak_limiter_vs_reference_macro_build(afx, gpu, tag):
+    """afx_rans_set_limiter(AFX_LIMITER_MICHALAK) = the reference compiled with -DRANS_MICHALAK_LIMITER (solver.h:557-576): strict mode
+    bit-identical to that build over 30 iterations (limiters, states, residual vector), fast mode within the north-star tolerances;
+    the implicit right-hand side takes the same limiter; switching back restores the default build's bits."""
+    d = H.load(tag)
+    meta = d["meta"]
+    m, s = gpu_solver(afx, d)  # setup_solver applies meta["limiter"]
+    s.init(); s.refill_bcs()
+    s.set_q(d["q0"])
+    l0 = s.launch_count()
+    first = s.solve(meta["relax"])
+    assert s.launch_count() - l0 == 11  # dt/gradient kernel without the limiter epilogue + a limiter launch per stage
+    for nm in ("q", "qW", "limiters"):
+        assert np.array_equal(s.get(nm) + 0.0, d["it1_" + nm] + 0.0), nm
+    norms = np.concatenate([[first], s.run(meta["n_iter"] - 1, meta["relax"])])
+    np.testing.assert_allclose(norms, d["norms"], rtol=NORM_RTOL, atol=0)
+    assert np.array_equal(s.get_q(), d["qN"]) and np.array_equal(s.get("limiters") + 0.0, d["limN"] + 0.0)
+    np.testing.assert_allclose(s.wall_forces(str(d["forces_patch"])), d["forces"], rtol=FORCE_RTOL, atol=1e-15)
+    # fast arithmetic
+    mf, f = gpu_solver(afx, d, math="fast")
+    f.init(); f.refill_bcs(); f.set_q(d["q0"])
+    fn = f.run(meta["n_iter"], meta["relax"])
+    np.testing.assert_allclose(fn, d["norms"], rtol=1e-10, atol=0)
+    np.testing.assert_allclose(f.wall_forces(str(d["forces_patch"])), d["forces"], rtol=1e-8, atol=1e-12)
+    # the implicit right-hand side (fillRhoRHS calls the same calc_limiters) against the oracle with the same switch
+    om = H.oracle_mesh(d); o = orc.OracleSolver(om, viscosity=meta["viscosity"]); H.setup_solver(o, meta)
+    o.init(); o.refill_bcs(); o.q[:] = d["q0"]; s.set_q(d["q0"])
+    assert s.residual() == pytest.approx(o.implicit_rhs(), rel=NORM_RTOL)
+    assert np.array_equal(s.get("rhs"), o.rhs)
+    # back to the default build's function: the bits of the Venkatakrishnan oracle
+    s.set_limiter("venkatakrishnan"); o.set_limiter("venkatakrishnan")
+    s.set_q(d["q0"]); o.q[:] = d["q0"]
+    gn = s.run(3, meta["relax"]); on = [o.explicit_solve(meta["relax"]) for _ in range(3)]
+    np.testing.assert_allclose(gn, on, rtol=NORM_RTOL, atol=0)
+    assert np.array_equal(s.get_q(), o.q)
+    assert s.L.afx_rans_set_limiter(s.h, 7) == -1 and b"unknown limiter" in s.L.afx_last_error()  # AFX_ERR_INVALID
+
+
 @pytest.mark.parametrize("tag", H.IMPLICIT_CASES)
 def test_implicit_rhs_and_jacobian_vs_reference_golden(afx, gpu, tag):
     d = H.load(tag)

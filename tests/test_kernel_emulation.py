@@ -121,9 +121,9 @@ def test_in_process_group_under_emulation(emu_lib):
     """tests/test_gpu_group.py (N partitioned solvers of one process on one device: what the 1-GPU box runs on hardware):
     staged halo between host rendezvous, peer-memory push with plain pointers, the bounded halo wait giving up on a dead
     peer (AFX_ERR_COMM), cp of a partition's wall edges."""
-    tail = run_gpu_tests_under_emulation(emu_lib, ["test_gpu_group.py"], "2-p2p-strict or 4-staged-strict or dead_peer or wall_cp or 3-inviscid",
+    tail = run_gpu_tests_under_emulation(emu_lib, ["test_gpu_group.py"], "2-p2p-strict or 4-staged-strict or dead_peer or wall_cp or 3-inviscid or (michalak and staged)",
                                          extra_env={"AFX_EMU_DEVICES": "1", "OMP_NUM_THREADS": "2", "OMP_WAIT_POLICY": "passive"})
-    assert "5 passed" in tail
+    assert "6 passed" in tail
 
 
 def test_pipelined_stage_kernel_under_emulation(emu_lib):

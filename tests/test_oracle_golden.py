@@ -57,6 +57,35 @@ def test_explicit_history_matches_reference(tag):
     np.testing.assert_allclose(s.wall_forces(str(d["forces_patch"])), d["forces"], rtol=1e-14, atol=1e-16)
 
 
+@pytest.mark.parametrize("tag", H.MICHALAK_CASES)
+def test_michalak_limiter_history_matches_the_reference_macro_build(tag):
+    """calc_limiters under RANS_MICHALAK_LIMITER (solver.h:557-576, physics.h:581-592): the restatement against the unmodified
+    headers compiled with that macro -- limiters, states and residuals bit for bit over 30 iterations, with 11-14 % of the limiter
+    values below one (the smooth switch and both branches of the cubic are exercised)."""
+    d = H.load(tag)
+    meta = d["meta"]
+    m = H.oracle_mesh(d)
+    s = orc.OracleSolver(m, viscosity=meta["viscosity"])
+    H.setup_solver(s, meta)
+    s.init(); s.refill_bcs()
+    s.q[:] = d["q0"]
+    norms = np.zeros(meta["n_iter"])
+    for it in range(meta["n_iter"]):
+        norms[it] = s.explicit_solve(meta["relax"])
+        if it == 0:
+            for nm, attr in (("q", "q"), ("qW", "qW"), ("limiters", "lim")):
+                assert np.array_equal(getattr(s, attr) + 0.0, d["it1_" + nm] + 0.0), nm
+    l1 = d["it1_limiters"][:4 * m.N]
+    assert 0.05 < np.mean(l1 < 1) < 0.5 and l1.min() == 0.0 and np.any((l1 > 0) & (l1 < 1))
+    np.testing.assert_allclose(norms, d["norms"], rtol=1e-13, atol=0)
+    assert np.array_equal(s.q, d["qN"]) and np.array_equal(s.lim + 0.0, d["limN"] + 0.0)
+    np.testing.assert_allclose(s.wall_forces(str(d["forces_patch"])), d["forces"], rtol=1e-14, atol=1e-16)
+    # and it is a different function: the default build's limiter on the same state differs
+    s.set_limiter("venkatakrishnan")
+    s.calc_limiters(0)
+    assert not np.array_equal(s.lim, d["limN"])
+
+
 @pytest.mark.parametrize("tag", H.IMPLICIT_CASES)
 def test_implicit_rhs_and_jacobian_blocks_match_reference(tag):
     d = H.load(tag)
@@ -92,7 +121,7 @@ def test_sanity_anchors_independent_of_any_oracle():
     assert np.abs(qW[~touches_bnd]).max() < 1e-9 * np.abs(qW).max() + 1e-9
 
 
-@pytest.mark.parametrize("tag", ["naca0012q_coarse_euler_gg_o2", "naca0012_coarse_laminar_lsq_o2", "naca0012_coarse_sa_gg_o1"])
+@pytest.mark.parametrize("tag", ["naca0012q_coarse_euler_gg_o2", "naca0012_coarse_laminar_lsq_o2", "naca0012_coarse_sa_gg_o1", "michalak_naca0012q_coarse_euler_gg"])
 def test_threaded_port_is_bit_identical_to_the_serial_restatement(tag):
     """orc_explicit_solve_omp (the multi-core CPU baseline of bench.py) = orc_explicit_solve, bit for bit."""
     d = H.load(tag)
