@@ -112,8 +112,9 @@ def bind_to_gpu_numa_node(local):
                 return None
             idx = int(ids[local])
         mask = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(idx), ((os.cpu_count() or 64) + 63) // 64)
-        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1} & os.sched_getaffinity(0)
-        if len(cpus) < 2:
+        allowed = os.sched_getaffinity(0)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1} & allowed
+        if len(cpus) < max(4, len(allowed) // 4):  # a container that shows only a sliver of the GPU's socket: leave the rank where it is
             return None
         os.sched_setaffinity(0, cpus)
         return len(cpus)
