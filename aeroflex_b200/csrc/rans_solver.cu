@@ -1746,6 +1746,8 @@ int guard(F&& f)
     catch (const std::exception& e) { afx::set_error(e.what()); return AFX_ERR_INVALID; }
     catch (...) { afx::set_error("unknown error"); return AFX_ERR_INVALID; }
 }
+// every entry point that takes a solver handle refuses a null one instead of dereferencing it
+int null_handle() { afx::set_error("null solver handle"); return AFX_ERR_INVALID; }
 
 }  // namespace
 
@@ -1796,15 +1798,17 @@ int afx_nccl_unique_id(char out[128])
 
 int afx_rans_p2p_export(afx_rans* s, void* blob, size_t* size)
 {
+    if (!s) return null_handle();
     return guard([&] { const size_t n = s->s.p2p_export(blob); if (size) *size = n; });
 }
 
 int afx_rans_p2p_connect(afx_rans* s, const void* blobs, size_t blob_size, int nranks)
 {
+    if (!s) return null_handle();
     return guard([&] { s->s.p2p_connect(blobs, blob_size, nranks); });
 }
 
-int afx_rans_halo_mode(afx_rans* s) { return !s->s.halo ? 0 : (s->s.halo->p2p ? 2 : 1); }
+int afx_rans_halo_mode(afx_rans* s) { return !s ? null_handle() : (!s->s.halo ? 0 : (s->s.halo->p2p ? 2 : 1)); }
 
 int afx_rans_create_partitioned(afx_rans** out, const afx_partition* part, const afx_gas* gas, int viscosity_model, int device,
                                 const char nccl_id[128])
@@ -1856,11 +1860,13 @@ void afx_rans_destroy(afx_rans* s) { delete s; }
 
 int afx_rans_set_bcs(afx_rans* s, int n_patch, const uint8_t* patch_kind, const afx_bvars* patch_vars)
 {
+    if (!s) return null_handle();
     return guard([&] { s->s.set_bcs(n_patch, patch_kind, patch_vars); });
 }
 
 int afx_rans_set_options(afx_rans* s, int second_order, int gradient_scheme, double limiter_k)
 {
+    if (!s) return null_handle();
     return guard([&] { s->s.set_options(second_order, gradient_scheme, limiter_k); });
 }
 
@@ -1872,6 +1878,7 @@ int afx_rans_set_limiter(afx_rans* s, int limiter)
 
 int afx_rans_set_math_mode(afx_rans* s, int mode)
 {
+    if (!s) return null_handle();
     return guard([&] { s->s.set_math_mode(mode); });
 }
 
@@ -1915,11 +1922,13 @@ int afx_tiling_plan_partition(const afx_partition* part, uint32_t tile_cells, co
 
 int afx_rans_set_fused(afx_rans* s, int on)
 {
+    if (!s) return null_handle();
     return guard([&] { if (s->s.use_fused != (on != 0)) { s->s.use_fused = (on != 0); s->s.invalidate_graph(); } });
 }
 
 int afx_rans_tile_info(afx_rans* s, uint64_t out[8])
 {
+    if (!s) return null_handle();
     const auto& S = s->s;
     out[0] = S.fused_stage() ? 1 : 0; out[1] = S.n_tiles; out[2] = S.tile_cells; out[3] = S.stage_smem; out[4] = (uint64_t)S.stage_ctas_per_sm;
     out[5] = S.tt.max_loc; out[6] = S.tt.max_nf; out[7] = S.tile_local_cells;
@@ -1944,7 +1953,7 @@ int afx_rans_pipe_info(afx_rans* s, uint64_t out[8])
     return AFX_OK;
 }
 
-int afx_rans_get_math_mode(afx_rans* s) { return s->s.kt == &afx::strict::table() ? AFX_MATH_STRICT : AFX_MATH_FAST; }
+int afx_rans_get_math_mode(afx_rans* s) { return !s ? null_handle() : (s->s.kt == &afx::strict::table() ? AFX_MATH_STRICT : AFX_MATH_FAST); }
 
 int afx_rans_set_cfl(afx_rans* s, double cfl)
 {
@@ -1955,6 +1964,7 @@ int afx_rans_set_cfl(afx_rans* s, double cfl)
 
 int afx_rans_init(afx_rans* s)
 {
+    if (!s) return null_handle();
     return guard([&] {
         auto& S = s->s;
         S.use();
@@ -1972,6 +1982,7 @@ int afx_rans_init(afx_rans* s)
 
 int afx_rans_refill_bcs(afx_rans* s)
 {
+    if (!s) return null_handle();
     return guard([&] {
         auto& S = s->s;
         S.use();
@@ -1989,6 +2000,7 @@ int afx_rans_refill_bcs(afx_rans* s)
 
 int afx_rans_bcs_from_internal(afx_rans* s)
 {
+    if (!s) return null_handle();
     return guard([&] {
         auto& S = s->s;
         S.use();
@@ -2005,6 +2017,7 @@ int afx_rans_bcs_from_internal(afx_rans* s)
 
 int afx_rans_set_q(afx_rans* s, const double* q)
 {
+    if (!s) return null_handle();
     return guard([&] {
         auto& S = s->s;
         S.use();
@@ -2023,6 +2036,7 @@ int afx_rans_set_q(afx_rans* s, const double* q)
 
 int afx_rans_get_q(afx_rans* s, double* q)
 {
+    if (!s) return null_handle();
     return guard([&] {
         auto& S = s->s;
         S.use();
@@ -2037,6 +2051,7 @@ int afx_rans_get_q(afx_rans* s, double* q)
 
 int afx_rans_set_q_local(afx_rans* s, const double* q_local)
 {
+    if (!s) return null_handle();
     return guard([&] {
         auto& S = s->s;
         S.use();
@@ -2049,11 +2064,13 @@ int afx_rans_set_q_local(afx_rans* s, const double* q_local)
 
 int afx_rans_get_q_local(afx_rans* s, double* q_local)
 {
+    if (!s) return null_handle();
     return guard([&] { s->s.use(); s->s.to_ref_order4(s->s.q.p, q_local); });
 }
 
 int afx_rans_get_field(afx_rans* s, int field, double* out)
 {
+    if (!s) return null_handle();
     return guard([&] {
         auto& S = s->s;
         S.use();
@@ -2076,15 +2093,17 @@ int afx_rans_get_field(afx_rans* s, int field, double* out)
     });
 }
 
-int afx_rans_boundary_variables(afx_rans* s, afx_bvars* out) { return s->s.boundary_variables(out) ? 1 : 0; }
+int afx_rans_boundary_variables(afx_rans* s, afx_bvars* out) { return (!s || !out) ? null_handle() : (s->s.boundary_variables(out) ? 1 : 0); }
 
 int afx_rans_uniform_residual(afx_rans* s, double* norm)
 {
+    if (!s) return null_handle();
     return guard([&] { const double v = s->s.uniform_residual(); if (norm) *norm = v; });
 }
 
 int afx_rans_step_explicit(afx_rans* s, double relaxation, double* norm)
 {
+    if (!s) return null_handle();
     return guard([&] {
         double v = 0;
         s->s.run_explicit(relaxation, 1, &v);
@@ -2095,6 +2114,7 @@ int afx_rans_step_explicit(afx_rans* s, double relaxation, double* norm)
 
 int afx_rans_run_explicit(afx_rans* s, double relaxation, int n_iter, double* norms)
 {
+    if (!s) return null_handle();
     return guard([&] {
         if (n_iter <= 0) return;
         std::vector<double> tmp;
@@ -2107,6 +2127,7 @@ int afx_rans_run_explicit(afx_rans* s, double relaxation, int n_iter, double* no
 
 int afx_rans_phase_dt_gradients(afx_rans* s)
 {
+    if (!s) return null_handle();
     return guard([&] {
         auto& S = s->s;
         S.use();
@@ -2120,6 +2141,7 @@ int afx_rans_phase_dt_gradients(afx_rans* s)
 
 int afx_rans_phase_limiters(afx_rans* s)
 {
+    if (!s) return null_handle();
     return guard([&] {
         auto& S = s->s;
         S.use();
@@ -2131,6 +2153,7 @@ int afx_rans_phase_limiters(afx_rans* s)
 
 int afx_rans_phase_residual(afx_rans* s, double* norm)
 {
+    if (!s) return null_handle();
     return guard([&] {
         auto& S = s->s;
         S.use();
@@ -2146,16 +2169,19 @@ int afx_rans_phase_residual(afx_rans* s, double* norm)
 
 int afx_rans_residual(afx_rans* s, double* norm)
 {
+    if (!s) return null_handle();
     return guard([&] { const double v = s->s.residual_rhs(); if (norm) *norm = v; });
 }
 
 int afx_rans_fill_jacobian(afx_rans* s)
 {
+    if (!s) return null_handle();
     return guard([&] { s->s.fill_jacobian(); });
 }
 
 int afx_rans_get_jacobian_blocks(afx_rans* s, double* diag, double* off01, double* off10)
 {
+    if (!s) return null_handle();
     return guard([&] {
         auto& S = s->s;
         S.use();
@@ -2179,6 +2205,7 @@ int afx_rans_get_jacobian_blocks(afx_rans* s, double* diag, double* off01, doubl
 
 int afx_rans_compute(afx_rans* s)
 {
+    if (!s) return null_handle();
     int r = 0;
     const int rc = guard([&] { r = s->s.compute_preconditioner(); });
     return rc ? rc : (r == 0 ? AFX_OK : AFX_ERR_NUMERIC);
@@ -2186,6 +2213,7 @@ int afx_rans_compute(afx_rans* s)
 
 int afx_rans_step_implicit(afx_rans* s, double relaxation, double tol, int rhs_iterations, double* norm)
 {
+    if (!s) return null_handle();
     double v = -1;
     const int rc = guard([&] {
         v = s->s.step_implicit(relaxation, tol, rhs_iterations);
@@ -2197,6 +2225,7 @@ int afx_rans_step_implicit(afx_rans* s, double relaxation, double tol, int rhs_i
 
 int afx_rans_set_linear_solver(afx_rans* s, int restart, int max_iterations, double tolerance, int precond_sweeps)
 {
+    if (!s) return null_handle();
     return guard([&] {
         auto& S = s->s;
         if (restart < 1 || max_iterations < 1 || tolerance <= 0 || precond_sweeps < 1) throw afx::InvalidArg("bad linear solver settings");
@@ -2206,10 +2235,11 @@ int afx_rans_set_linear_solver(afx_rans* s, int restart, int max_iterations, dou
     });
 }
 
-int afx_rans_last_linear_iterations(afx_rans* s) { return s->s.last_linear_iters; }
+int afx_rans_last_linear_iterations(afx_rans* s) { return s ? s->s.last_linear_iters : null_handle(); }
 
 int afx_rans_wall_forces(afx_rans* s, int patch, double out[3])
 {
+    if (!s) return null_handle();
     return guard([&] {
         auto& S = s->s;
         S.use();
@@ -2248,6 +2278,7 @@ int afx_rans_wall_forces(afx_rans* s, int patch, double out[3])
 
 int afx_rans_wall_cp(afx_rans* s, int patch, double* cp)
 {
+    if (!s) return null_handle();
     int count = 0;
     const int rc = guard([&] {
         auto& S = s->s;
@@ -2445,6 +2476,7 @@ int64_t afx_rans_launch_count(afx_rans* s) { return s ? s->s.launches : 0; }
 
 int afx_rans_profile_explicit(afx_rans* s, double relaxation, int n_iter, double out_ms[6])
 {
+    if (!s) return null_handle();
     return guard([&] {
         auto& S = s->s;
         S.use();
