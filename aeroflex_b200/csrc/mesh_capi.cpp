@@ -84,14 +84,15 @@ int afx_mesh_get_desc(const afx_mesh* m, afx_mesh_desc* out)
     return AFX_OK;
 }
 
-uint32_t afx_mesh_n_nodes(const afx_mesh* m) { return (uint32_t)m->m.x.size(); }
-int afx_mesh_n_patches(const afx_mesh* m) { return (int)m->m.patch_names.size(); }
+uint32_t afx_mesh_n_nodes(const afx_mesh* m) { return m ? (uint32_t)m->m.x.size() : 0u; }
+int afx_mesh_n_patches(const afx_mesh* m) { return m ? (int)m->m.patch_names.size() : 0; }
 const char* afx_mesh_patch_name(const afx_mesh* m, int p)
 {
-    return (p >= 0 && p < (int)m->m.patch_names.size()) ? m->m.patch_names[(size_t)p].c_str() : nullptr;
+    return (m && p >= 0 && p < (int)m->m.patch_names.size()) ? m->m.patch_names[(size_t)p].c_str() : nullptr;
 }
 int afx_mesh_patch_id(const afx_mesh* m, const char* name)
 {
+    if (!m || !name) return -1;
     for (size_t p = 0; p < m->m.patch_names.size(); ++p)
         if (m->m.patch_names[p] == name) return (int)p;
     return -1;

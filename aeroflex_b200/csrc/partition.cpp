@@ -240,18 +240,20 @@ int afx_partition_get_desc(const afx_partition* p, afx_mesh_desc* out)
 /* out = {n_own, n_ring1, n_ring2, n_boundary_ghosts, n_local_edges, n_peers, rank, nranks} */
 int afx_partition_info(const afx_partition* p, uint32_t out[8])
 {
+    if (!p || !out) { afx::set_error("null argument"); return AFX_ERR_INVALID; }
     const auto& q = p->p;
     out[0] = q.n_own; out[1] = q.n_r1; out[2] = q.n_r2; out[3] = q.n_bc; out[4] = (uint32_t)q.edge_l2g.size();
     out[5] = (uint32_t)q.peers.size(); out[6] = (uint32_t)q.rank; out[7] = (uint32_t)q.nranks;
     return AFX_OK;
 }
 
-const uint32_t* afx_partition_cell_l2g(const afx_partition* p) { return p->p.cell_l2g.data(); }
-const uint32_t* afx_partition_edge_l2g(const afx_partition* p) { return p->p.edge_l2g.data(); }
+const uint32_t* afx_partition_cell_l2g(const afx_partition* p) { return p ? p->p.cell_l2g.data() : nullptr; }
+const uint32_t* afx_partition_edge_l2g(const afx_partition* p) { return p ? p->p.edge_l2g.data() : nullptr; }
 
 int afx_partition_peer(const afx_partition* p, int i, int* peer_rank, const uint32_t** send, uint32_t* n_send,
                        const uint32_t** recv, uint32_t* n_recv)
 {
+    if (!p) { afx::set_error("null argument"); return AFX_ERR_INVALID; }
     if (i < 0 || i >= (int)p->p.peers.size()) { afx::set_error("peer index out of range"); return AFX_ERR_INVALID; }
     const auto& q = p->p.peers[(size_t)i];
     if (peer_rank) *peer_rank = q.rank;

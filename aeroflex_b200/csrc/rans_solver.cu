@@ -1789,6 +1789,7 @@ int afx_rans_create(afx_rans** out, const afx_mesh_desc* mesh, const afx_gas* ga
 
 int afx_nccl_unique_id(char out[128])
 {
+    if (!out) { afx::set_error("null argument"); return AFX_ERR_INVALID; }
     return guard([&] {
         ncclUniqueId id;
         NK(afx::NcclApi::get().GetUniqueId(&id));

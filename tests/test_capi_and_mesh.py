@@ -99,9 +99,10 @@ def test_reference_reader_accepts_our_msh_writer(afx, tmp_path):
     assert [m.patch_names[i] for i in m.bnd_patch] == rm.bnd_names
 
 
-def test_every_solver_entry_point_refuses_a_null_handle(afx):
-    """The ABI is called from C and C++ hosts: a null handle comes back as AFX_ERR_INVALID with a message, never as a crash.
-    Run in a child process so that a missing check fails this test instead of taking the test run down."""
+def test_no_entry_point_crashes_on_null_arguments(afx):
+    """The ABI is called from C and C++ hosts: a null handle comes back as an error code (AFX_ERR_INVALID for the solver entry points,
+    0 / -1 / NULL for the small accessors), never as a crash.  Every function include/afx_rans.h declares is called with nulls, each
+    in a child process so that a missing check fails this test instead of taking the test run down."""
     import subprocess
     import sys
     code = r'''
@@ -110,17 +111,19 @@ sys.path.insert(0, %r)
 import aeroflex_b200 as afx
 L = C.CDLL(afx.library_path())  # a fresh handle: no argtypes, so that nulls can be passed everywhere
 hdr = re.sub(r"/\*.*?\*/", "", open(%r).read(), flags=re.S)
-names = sorted(set(re.findall(r"\bint\s+(afx_rans_[a-z0-9_]+)\s*\(\s*afx_rans\s*\*\s*s\b", hdr)))
-assert len(names) >= 35, names
+solver = sorted(set(re.findall(r"\bint\s+(afx_rans_[a-z0-9_]+)\s*\(\s*afx_rans\s*\*\s*s\b", hdr)))
+assert len(solver) >= 35, solver
+every = sorted(set(re.findall(r"\b(afx_[a-z0-9_]+)\s*\(", hdr)) - {"afx_pinned_alloc"})
 bad = []
-for n in names:
+for n in every:
+    print(n, flush=True)  # the last name printed is the one that crashed
     f = getattr(L, n)
     f.restype = C.c_int
-    rc = f(*([None] + [C.c_void_p(0)] * 12))  # null handle, nulls / zeros for everything else (never reached)
-    if rc != -1:
+    rc = f(*([None] + [C.c_void_p(0)] * 13))  # nulls / zeros for everything
+    if n in solver and rc != -1:
         bad.append((n, rc))
-print("checked", len(names), "bad", bad)
+print("checked", len(every), "bad", bad)
 assert not bad
 ''' % (ROOT, os.path.join(ROOT, "include", "afx_rans.h"))
-    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
-    assert r.returncode == 0, (r.returncode, r.stdout[-500:], r.stderr[-1500:])
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.returncode, r.stdout[-300:], r.stderr[-1500:])
